@@ -1,0 +1,58 @@
+"""ctypes binding of libb200rl.so (the C-ABI declared in include/b200rl.h).
+
+The library is the product: there is NO fallback.  If it is missing or a call
+fails, a RuntimeError is raised.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from pathlib import Path
+
+PKG = Path(__file__).resolve().parent
+LIB_PATH = PKG / "libb200rl.so"
+
+_p = C.c_void_p
+_i64 = C.c_int64
+_i = C.c_int
+_d = C.c_double
+_sz = C.c_size_t
+
+# name -> (restype, argtypes)   -- must list every symbol include/b200rl.h declares
+SIGNATURES = {
+    "b200rl_version": (_i, []),
+    "b200rl_last_error": (C.c_char_p, []),
+    "b200rl_compiled_arch": (_i, []),
+    "b200rl_gae_f32": (_i, [_p, _p, _p, _p, _p, _p, _p, _i64, _i64, _d, _d, _i, _p]),
+    "b200rl_categorical_sample_f32": (_i, [_p, _i64, _p, _p, _i64, _i64, _i, _p, _p, _p, _p, _p]),
+    "b200rl_ppo_loss_workspace_bytes": (_sz, [_i64]),
+    "b200rl_ppo_loss_f32": (_i, [_p, _i64, _p, _i64, _p, _p, _p, _p, _p, _p, _i64, _i, _d, _d, _d, _i, _i,
+                                 _p, _i64, _p, _i64, _p, _p, _sz, _p]),
+    "b200rl_clip_adam_workspace_bytes": (_sz, [_i64]),
+    "b200rl_clip_adam_f32": (_i, [_p, _p, _p, _p, _i64, _i64, _d, _d, _d, _d, _d, _i, _p, _p, _sz, _p]),
+}
+
+_lib = None
+
+
+def load():
+    """Load the shared library (once) and attach prototypes."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not LIB_PATH.exists():
+        raise RuntimeError(
+            f"{LIB_PATH} is missing: build it with `python -m cleanrl_b200.build` "
+            "(the CUDA extension is the product; there is no CPU/torch fallback)")
+    lib = C.CDLL(str(LIB_PATH))
+    for name, (res, args) in SIGNATURES.items():
+        fn = getattr(lib, name)  # AttributeError => header/library out of sync
+        fn.restype = res
+        fn.argtypes = args
+    _lib = lib
+    return lib
+
+
+def check(rc, what):
+    if rc != 0:
+        msg = load().b200rl_last_error().decode("utf-8", "replace")
+        raise RuntimeError(f"libb200rl {what} failed (status {rc}): {msg}")

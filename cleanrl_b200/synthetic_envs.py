@@ -1,0 +1,214 @@
+"""Synthetic vector environments (host side, numpy).
+
+The image this framework is built and measured in has no envpool / ALE /
+gymnasium and no network, so real Breakout-v5 cannot run.
+These classes supply deterministic, seeded stand-ins with the exact API surface
+the reference loops touch:
+
+* ``SyntheticAtariVec`` -- the gym-0.23 / envpool flavour used by
+  ``ppo_atari_envpool.py`` (reference: cleanrl/ppo_atari_envpool.py:185-196,
+  :237-247): ``reset() -> obs``, ``step(a) -> (obs, reward, done, info)`` with
+  ``info = {"reward", "terminated", "lives"}``.
+* ``SyntheticGymnasiumVec`` -- the gymnasium-0.29 flavour used by ``ppo.py`` /
+  ``ppo_atari_multigpu.py`` / ``ppo_continuous_action.py``
+  (reference: cleanrl/ppo.py:162-164,181,205-215): ``reset(seed=) -> (obs, info)``,
+  ``step(a) -> (obs, reward, terminated, truncated, infos)`` with
+  ``infos["final_info"]`` carrying ``{"episode": {"r", "l"}}``.
+
+Two observation modes:
+
+``fresh``  every env picks its next frame from a pool as a function of its own
+           state and the action it received, so a wrong action changes every
+           later observation (used for parity runs).
+``pool``   whole pre-generated pinned batches are handed out round-robin at
+           ~zero host cost (used for throughput runs; data = "synthetic").
+
+The environments own their ``np.random.Generator`` and never touch numpy's
+global RNG (that one drives the minibatch shuffle, cleanrl/ppo.py:155,245).
+"""
+from __future__ import annotations
+
+import numpy as np
+
+
+class Discrete:
+    """Minimal stand-in for gym.spaces.Discrete."""
+
+    def __init__(self, n):
+        self.n = int(n)
+        self.shape = ()
+        self.dtype = np.int64
+
+    def __repr__(self):
+        return f"Discrete({self.n})"
+
+
+class Box:
+    """Minimal stand-in for gym.spaces.Box."""
+
+    def __init__(self, low, high, shape, dtype):
+        self.low = np.full(shape, low, dtype=dtype)
+        self.high = np.full(shape, high, dtype=dtype)
+        self.shape = tuple(shape)
+        self.dtype = np.dtype(dtype)
+
+    def __repr__(self):
+        return f"Box({self.shape}, {self.dtype})"
+
+
+def _alloc_host(shape, dtype, pinned):
+    """Host buffer, page-locked when torch+CUDA is usable so H2D copies are async."""
+    if pinned:
+        import torch
+
+        if torch.cuda.is_available():
+            t = torch.empty(shape, dtype=getattr(torch, np.dtype(dtype).name), pin_memory=True)
+            return t.numpy()
+    return np.empty(shape, dtype=dtype)
+
+
+class SyntheticAtariVec:
+    """Breakout-shaped vector env: uint8 obs [N,4,84,84], Discrete(4) actions."""
+
+    def __init__(self, num_envs, seed=1, mode="fresh", n_actions=4, obs_shape=(4, 84, 84),
+                 pool=32, p_done=0.02, pinned=False):
+        assert mode in ("fresh", "pool")
+        self.num_envs = int(num_envs)
+        self.mode = mode
+        self.observation_space = Box(0, 255, obs_shape, np.uint8)
+        self.action_space = Discrete(n_actions)
+        self.p_done = float(p_done)
+        self._rng = np.random.default_rng(seed)
+        self._t = 0
+        if mode == "fresh":
+            self._frames = self._rng.integers(0, 256, size=(pool,) + tuple(obs_shape), dtype=np.uint8)
+            self._idx = np.zeros(self.num_envs, dtype=np.int64)
+            self._obs = _alloc_host((self.num_envs,) + tuple(obs_shape), np.uint8, pinned)
+        else:
+            pool = min(int(pool), 8)
+            self._batches = _alloc_host((pool, self.num_envs) + tuple(obs_shape), np.uint8, pinned)
+            # fill in chunks; 29 MB per batch at N=1024
+            for b in range(pool):
+                self._batches[b] = self._rng.integers(
+                    0, 256, size=(self.num_envs,) + tuple(obs_shape), dtype=np.uint8)
+        self._lives = np.full(self.num_envs, 5, dtype=np.int32)
+
+    # -- gym 0.23 API -------------------------------------------------------
+    def reset(self, **kwargs):
+        self._t = 0
+        if self.mode == "fresh":
+            self._idx = self._rng.integers(0, len(self._frames), size=self.num_envs)
+            np.take(self._frames, self._idx, axis=0, out=self._obs)
+            return self._obs
+        return self._batches[0]
+
+    def step(self, action):
+        action = np.asarray(action).reshape(self.num_envs).astype(np.int64)
+        self._t += 1
+        n = self.num_envs
+        raw = self._rng.integers(0, 3, size=n).astype(np.float32)  # raw game score 0,1,2
+        raw *= (action != 0)                                           # NOOP never scores
+        reward = np.sign(raw).astype(np.float32)                       # reward_clip=True
+        done = self._rng.random(n) < self.p_done
+        lost_life = done
+        self._lives = np.where(lost_life, self._lives - 1, self._lives).astype(np.int32)
+        game_over = self._lives <= 0
+        info = {
+            "reward": raw,
+            "terminated": game_over.astype(np.int32),
+            "lives": self._lives.copy(),
+        }
+        self._lives = np.where(game_over, 5, self._lives).astype(np.int32)
+        if self.mode == "fresh":
+            self._idx = (self._idx * 5 + action + 1 + self._t) % len(self._frames)
+            np.take(self._frames, self._idx, axis=0, out=self._obs)
+            obs = self._obs
+        else:
+            obs = self._batches[self._t % len(self._batches)]
+        return obs, reward, done, info
+
+    def close(self):
+        pass
+
+
+class SyntheticGymnasiumVec:
+    """gymnasium-style vector env with float observations.
+
+    ``kind="discrete"``: CartPole-shaped (obs f32 [N,4], Discrete(2)).
+    ``kind="continuous"``: HalfCheetah-shaped (obs f32 [N,17] clipped to +-10, Box(6) actions).
+    ``kind="atari"``: uint8 [N,4,84,84], Discrete(4) (for the multigpu script).
+    """
+
+    def __init__(self, num_envs, kind="discrete", obs_dim=None, act_dim=None, p_done=0.02, max_len=500):
+        self.num_envs = int(num_envs)
+        self.kind = kind
+        if kind == "discrete":
+            od = obs_dim or 4
+            self.single_observation_space = Box(-np.inf, np.inf, (od,), np.float32)
+            self.single_action_space = Discrete(act_dim or 2)
+        elif kind == "continuous":
+            od = obs_dim or 17
+            self.single_observation_space = Box(-np.inf, np.inf, (od,), np.float32)
+            self.single_action_space = Box(-1.0, 1.0, (act_dim or 6,), np.float32)
+        elif kind == "atari":
+            self.single_observation_space = Box(0, 255, (4, 84, 84), np.uint8)
+            self.single_action_space = Discrete(act_dim or 4)
+        else:
+            raise ValueError(kind)
+        self.observation_space = self.single_observation_space
+        self.action_space = self.single_action_space
+        self.p_done = float(p_done)
+        self.max_len = int(max_len)
+        self._rng = None
+        self._ep_ret = np.zeros(self.num_envs, dtype=np.float64)
+        self._ep_len = np.zeros(self.num_envs, dtype=np.int64)
+        self._state = None
+
+    def _draw_obs(self, act_term):
+        n = self.num_envs
+        shp = self.single_observation_space.shape
+        if self.kind == "atari":
+            return self._rng.integers(0, 256, size=(n,) + shp, dtype=np.uint8)
+        self._state = 0.9 * self._state + 0.3 * self._rng.standard_normal((n,) + shp) + 0.05 * act_term
+        return np.clip(self._state, -10, 10).astype(np.float32)
+
+    def reset(self, seed=None, **kwargs):
+        self._rng = np.random.default_rng(seed)
+        self._ep_ret[:] = 0
+        self._ep_len[:] = 0
+        self._state = np.zeros((self.num_envs,) + self.single_observation_space.shape, dtype=np.float64)
+        return self._draw_obs(0.0), {}
+
+    def step(self, action):
+        n = self.num_envs
+        action = np.asarray(action)
+        if self.kind == "continuous":
+            act_term = np.clip(action, -1, 1).reshape(n, -1).mean(axis=1, keepdims=True)
+            reward = np.clip(self._rng.standard_normal(n) + act_term[:, 0], -10, 10).astype(np.float32)
+        else:
+            a = action.reshape(n).astype(np.float64)
+            act_term = (a - 0.5).reshape((n,) + (1,) * len(self.single_observation_space.shape))
+            reward = np.ones(n, dtype=np.float32) if self.kind == "discrete" else \
+                np.sign(self._rng.integers(0, 3, size=n) * (a != 0)).astype(np.float32)
+        self._ep_ret += reward
+        self._ep_len += 1
+        terminated = self._rng.random(n) < self.p_done
+        truncated = (self._ep_len >= self.max_len) & ~terminated
+        done = terminated | truncated
+        obs = self._draw_obs(act_term)
+        infos = {}
+        if done.any():
+            final = np.empty(n, dtype=object)
+            for i in np.nonzero(done)[0]:
+                final[i] = {"episode": {"r": np.array([self._ep_ret[i]], dtype=np.float32),
+                                        "l": np.array([self._ep_len[i]], dtype=np.int32)}}
+            infos["final_info"] = final
+            infos["_final_info"] = done.copy()
+            self._ep_ret[done] = 0
+            self._ep_len[done] = 0
+            if self.kind != "atari":
+                self._state[done] = 0
+        return obs, reward, terminated, truncated, infos
+
+    def close(self):
+        pass

@@ -1,0 +1,179 @@
+/*
+ * b200rl.h -- C-ABI of libb200rl.so: the B200-native (sm_100a) PPO hot path.
+ *
+ * The reference (vwxyzjn/cleanrl) is pure Python/PyTorch and has NO native
+ * interface; this header is the boundary SURVEY.md section 8(b) defines for it.
+ * Every entry point replaces a block of torch calls inside the reference's
+ * training loop (file:line cited per function, relative to the reference root).
+ *
+ * Conventions
+ *   - plain C: raw DEVICE pointers + explicit sizes, scalars by value.  No
+ *     torch / C++ types.  The caller (PyTorch in the shipped host code) owns
+ *     every buffer including workspaces; nothing here allocates or frees
+ *     device memory, and nothing synchronises the device.
+ *   - every function only ENQUEUES work on `stream` (a cudaStream_t passed as
+ *     void*; NULL = legacy default stream) and is CUDA-graph capturable.
+ *   - return value: 0 on success, negative b200rl_status on failure.  The
+ *     failing call's message is kept per host thread: b200rl_last_error().
+ *   - "f32" = IEEE binary32.  All matrices are dense row-major unless a leading
+ *     dimension / layout is spelled out.
+ *   - python-double hyper-parameters (gamma, lr, betas, eps ...) are passed as
+ *     double and rounded exactly where the reference rounds them.
+ */
+#ifndef B200RL_H
+#define B200RL_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef enum {
+    B200RL_OK = 0,
+    B200RL_ERR_INVALID_ARGUMENT = -1,
+    B200RL_ERR_CUDA = -2,
+    B200RL_ERR_UNSUPPORTED = -3,
+    B200RL_ERR_WORKSPACE = -4
+} b200rl_status;
+
+/* library version: major*10000 + minor*100 + patch */
+int b200rl_version(void);
+/* message of the last failing call on this host thread ("" if none) */
+const char* b200rl_last_error(void);
+/* compute capability the kernels were compiled for (100 = sm_100a) */
+int b200rl_compiled_arch(void);
+
+/* ---------------------------------------------------------------- GAE -----
+ * Reverse-scan generalised advantage estimation over a (T x N) rollout.
+ * Replaces the python loop cleanrl/ppo.py:218-231 (identical in
+ * ppo_atari_envpool.py:250-263, ppo_atari_multigpu.py:288-301,
+ * ppo_continuous_action.py:233-246).
+ *   rewards, values, dones : f32 [T, N] (N contiguous)
+ *   next_value, next_done  : f32 [N]
+ *   advantages, returns    : f32 [T, N] out  (returns = advantages + values)
+ *   gamma, gae_lambda      : python doubles; gamma -> f32 once,
+ *                            gamma*gae_lambda -> f32 once (ppo.py:230)
+ *   mode 0: one thread per env, every op individually rounded (no FMA):
+ *           bit-identical to the reference loop.
+ *   mode 1: time-chunked affine scan (3 short dependent phases instead of T
+ *           steps); re-associated, |err| ~1e-7 relative.
+ */
+int b200rl_gae_f32(const float* rewards, const float* values, const float* dones,
+                   const float* next_value, const float* next_done,
+                   float* advantages, float* returns,
+                   int64_t T, int64_t N, double gamma, double gae_lambda,
+                   int mode, void* stream);
+
+/* ------------------------------------------------ categorical policy head --
+ * Rollout-side policy epilogue.  Replaces Categorical(logits) + sample() +
+ * log_prob() + entropy() in Agent.get_action_and_value
+ * (cleanrl/ppo_atari_envpool.py:143-149, cleanrl/ppo.py:121-126) and the four
+ * rollout-buffer stores ppo.py:200-202.
+ *   logits  : f32 [n, A], row stride ld_logits elements
+ *   noise   : f32 [n, A] Exp(1) draws from the CALLER's generator (torch's
+ *             multinomial consumes exactly `empty_like(probs).exponential_(1)`),
+ *             action = argmax(softmax(normalised logits) / noise), first max wins.
+ *   value_in: optional f32 [n] (stride ld_value) copied to value_out (may be NULL)
+ *   outputs : action i64 [n], logprob f32 [n], entropy f32 [n] (entropy may be NULL)
+ */
+int b200rl_categorical_sample_f32(const float* logits, int64_t ld_logits, const float* noise,
+                                  const float* value_in, int64_t ld_value,
+                                  int64_t n, int A,
+                                  int64_t* action, float* logprob, float* entropy, float* value_out,
+                                  void* stream);
+
+/* -------------------------------------------------------------- PPO loss ---
+ * Fused minibatch loss: gather by mb_inds, advantage normalisation (unbiased
+ * std), ratio, both KL estimates, clipfrac, clipped surrogate, clipped value
+ * loss, entropy bonus, AND the gradients wrt the policy logits / value that
+ * autograd would produce.  Replaces cleanrl/ppo.py:250-285 (+ the part of
+ * loss.backward() :288 above the network).
+ *   new_logits : f32 [M, A] (row stride ld_logits); new_value: f32 [M] (stride ld_value)
+ *   mb_inds    : i64 [M] rows of the flat batch (NULL = 0..M-1)
+ *   b_*        : flat batch tensors of length B >= max(mb_inds)+1
+ *                b_actions i64, b_logprobs/b_advantages/b_returns/b_values f32
+ *   dlogits    : f32 [M, A] (row stride ld_dlogits) out; dvalue: f32 [M] (stride ld_dvalue) out
+ *   stats      : f32 [16] out: 0 pg_loss, 1 v_loss, 2 entropy, 3 old_approx_kl,
+ *                4 approx_kl, 5 clipfrac, 6 loss, 7 adv_mean, 8 adv_std
+ *   workspace  : >= b200rl_ppo_loss_workspace_bytes(M) bytes, 16-B aligned.
+ * Deterministic: fixed-order two-level reductions, no float atomics.
+ */
+size_t b200rl_ppo_loss_workspace_bytes(int64_t M);
+int b200rl_ppo_loss_f32(const float* new_logits, int64_t ld_logits,
+                        const float* new_value, int64_t ld_value,
+                        const int64_t* mb_inds,
+                        const int64_t* b_actions, const float* b_logprobs,
+                        const float* b_advantages, const float* b_returns, const float* b_values,
+                        int64_t M, int A,
+                        double clip_coef, double ent_coef, double vf_coef,
+                        int norm_adv, int clip_vloss,
+                        float* dlogits, int64_t ld_dlogits, float* dvalue, int64_t ld_dvalue,
+                        float* stats, void* workspace, size_t workspace_bytes, void* stream);
+
+/* ------------------------------------------------- grad clip + Adam step ---
+ * One fused optimiser step over a FLAT f32 parameter vector: optional DP
+ * averaging (grads hold the all-reduced SUM; divided by world_size first, as
+ * ppo_atari_multigpu.py:369-373 does), global-L2 clip_grad_norm_
+ * (torch/nn/utils/clip_grad.py: coef = max_norm/(norm+1e-6) clamped to 1) and
+ * Adam (torch/optim/adam.py _single_tensor_adam op order).  Replaces
+ * cleanrl/ppo.py:289-290.
+ *   params, exp_avg, exp_avg_sq : f32 [P] in/out;  grads: f32 [P] in
+ *   step       : 1-based count of this step (bias corrections in double)
+ *   max_norm   : < 0 disables clipping (dqn_atari.py has none)
+ *   norm_out   : optional f32 [1] device scalar receiving the pre-clip norm
+ *   workspace  : >= b200rl_clip_adam_workspace_bytes(P) bytes
+ */
+size_t b200rl_clip_adam_workspace_bytes(int64_t P);
+int b200rl_clip_adam_f32(float* params, const float* grads, float* exp_avg, float* exp_avg_sq,
+                         int64_t P, int64_t step, double lr, double beta1, double beta2, double eps,
+                         double max_norm, int world_size, float* norm_out,
+                         void* workspace, size_t workspace_bytes, void* stream);
+
+/* ------------------------------------------------ fp32 network layers ------
+ * Exact-arithmetic (fp32 FMA, CUDA cores) layers in the reference's own NCHW /
+ * [out,in] layouts.  They carry configs 1 and 4 (64-wide MLPs,
+ * cleanrl/ppo.py:100-116, ppo_continuous_action.py:112-129) and are the
+ * validation mode of the NatureCNN (ppo_atari_envpool.py:123-139); the bf16
+ * tensor-core path below is the fast path.
+ *
+ * act: 0 none, 1 ReLU, 2 tanh.  `rows` (i64, may be NULL) gathers the batch
+ * dimension of x: sample i of the call reads x[rows[i]] (the minibatch gather
+ * ppo.py:250 `b_obs[mb_inds]` without materialising it).
+ */
+enum { B200RL_ACT_NONE = 0, B200RL_ACT_RELU = 1, B200RL_ACT_TANH = 2 };
+enum { B200RL_DT_F32 = 0, B200RL_DT_U8 = 1 };
+
+/* y[n,Cout,OH,OW] = act(in_scale * conv(x[n,Cin,H,W], w[Cout,Cin,KH,KW]) + b) */
+int b200rl_conv2d_fwd_f32(const void* x, int x_dtype, const int64_t* rows, double in_scale,
+                          const float* w, const float* b, float* y,
+                          int64_t n, int Cin, int H, int W, int Cout, int KH, int KW, int stride,
+                          int act, void* stream);
+/* dx = conv_transpose(dy, w) * act'(x_post) ; x_post = the layer input as the
+ * previous layer's post-activation output (prev_act selects the derivative). */
+int b200rl_conv2d_bwd_data_f32(const float* dy, const float* w, const float* x_post, int prev_act,
+                               float* dx,
+                               int64_t n, int Cin, int H, int W, int Cout, int KH, int KW, int stride,
+                               void* stream);
+/* dw[Cout,Cin,KH,KW] = sum_m dy * im2col(x)*in_scale ; db[Cout] = sum dy.  Deterministic split
+ * reduction through `workspace` (b200rl_conv2d_bwd_weight_workspace_bytes). */
+size_t b200rl_conv2d_bwd_weight_workspace_bytes(int64_t n, int Cin, int H, int W, int Cout, int KH, int KW, int stride);
+int b200rl_conv2d_bwd_weight_f32(const void* x, int x_dtype, const int64_t* rows, double in_scale,
+                                 const float* dy, float* dw, float* db,
+                                 int64_t n, int Cin, int H, int W, int Cout, int KH, int KW, int stride,
+                                 void* workspace, size_t workspace_bytes, void* stream);
+/* y[n,out] = act(x[n,in] @ w[out,in]^T + b) ; x rows optionally gathered */
+int b200rl_linear_fwd_f32(const float* x, const int64_t* rows, const float* w, const float* b, float* y,
+                          int64_t n, int in_features, int out_features, int act, void* stream);
+int b200rl_linear_bwd_data_f32(const float* dy, const float* w, const float* x_post, int prev_act, float* dx,
+                               int64_t n, int in_features, int out_features, void* stream);
+size_t b200rl_linear_bwd_weight_workspace_bytes(int64_t n, int in_features, int out_features);
+int b200rl_linear_bwd_weight_f32(const float* x, const int64_t* rows, const float* dy, float* dw, float* db,
+                                 int64_t n, int in_features, int out_features,
+                                 void* workspace, size_t workspace_bytes, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* B200RL_H */
