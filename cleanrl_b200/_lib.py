@@ -24,11 +24,20 @@ SIGNATURES = {
     "b200rl_compiled_arch": (_i, []),
     "b200rl_gae_f32": (_i, [_p, _p, _p, _p, _p, _p, _p, _i64, _i64, _d, _d, _i, _p]),
     "b200rl_categorical_sample_f32": (_i, [_p, _i64, _p, _p, _i64, _i64, _i, _p, _p, _p, _p, _p]),
+    "b200rl_categorical_eval_f32": (_i, [_p, _i64, _p, _i64, _i, _p, _p, _p]),
     "b200rl_ppo_loss_workspace_bytes": (_sz, [_i64]),
     "b200rl_ppo_loss_f32": (_i, [_p, _i64, _p, _i64, _p, _p, _p, _p, _p, _p, _i64, _i, _d, _d, _d, _i, _i,
                                  _p, _i64, _p, _i64, _p, _p, _sz, _p]),
     "b200rl_clip_adam_workspace_bytes": (_sz, [_i64]),
     "b200rl_clip_adam_f32": (_i, [_p, _p, _p, _p, _i64, _i64, _d, _d, _d, _d, _d, _i, _p, _p, _sz, _p]),
+    "b200rl_conv2d_fwd_f32": (_i, [_p, _i, _p, _d, _p, _p, _p, _i64, _i, _i, _i, _i, _i, _i, _i, _i, _p]),
+    "b200rl_conv2d_bwd_data_f32": (_i, [_p, _p, _p, _i, _p, _i64, _i, _i, _i, _i, _i, _i, _i, _p]),
+    "b200rl_conv2d_bwd_weight_workspace_bytes": (_sz, [_i64, _i, _i, _i, _i, _i, _i, _i]),
+    "b200rl_conv2d_bwd_weight_f32": (_i, [_p, _i, _p, _d, _p, _p, _p, _i64, _i, _i, _i, _i, _i, _i, _i, _p, _sz, _p]),
+    "b200rl_linear_fwd_f32": (_i, [_p, _p, _p, _p, _p, _i64, _i, _i, _i, _p]),
+    "b200rl_linear_bwd_data_f32": (_i, [_p, _p, _p, _i, _p, _i64, _i, _i, _p]),
+    "b200rl_linear_bwd_weight_workspace_bytes": (_sz, [_i64, _i, _i]),
+    "b200rl_linear_bwd_weight_f32": (_i, [_p, _p, _p, _p, _p, _i64, _i, _i, _p, _sz, _p]),
 }
 
 _lib = None

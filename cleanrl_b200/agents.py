@@ -1,0 +1,198 @@
+"""Agent nn.Modules with the reference's surface, executed by libb200rl kernels.
+
+Surface kept: ctor ``Agent(envs)`` reading
+``envs.single_observation_space`` / ``envs.single_action_space``; sub-module
+names (=> identical ``state_dict`` keys); ``get_value(x)`` and
+``get_action_and_value(x, action=None)`` returning
+``(action i64 [n], logprob f32 [n], entropy f32 [n], value f32 [n,1])``.
+Initialisation calls torch's ``orthogonal_`` in the reference's layer order so
+a seed yields the reference's weights (cleanrl/ppo_atari_envpool.py:117-138,
+cleanrl/ppo.py:94-116).
+
+Forward/backward never touch autograd or cuDNN: they are explicit kernel
+launches on CUDA tensors, and raise on CPU tensors (no fallback).
+"""
+from __future__ import annotations
+
+import numpy as np
+import torch
+import torch.nn as nn
+
+from . import nets, ops
+
+
+def layer_init(layer, std=np.sqrt(2), bias_const=0.0):
+    torch.nn.init.orthogonal_(layer.weight, std)
+    torch.nn.init.constant_(layer.bias, bias_const)
+    return layer
+
+
+def _exp_noise(n, A, device):
+    # what torch.multinomial consumes internally: empty_like(probs).exponential_(1)
+    return torch.empty(n, A, dtype=torch.float32, device=device).exponential_(1)
+
+
+class KernelAgent(nn.Module):
+    """Shared plumbing: flat parameter binding + categorical head."""
+
+    def __init__(self):
+        super().__init__()
+        self._flat = None
+        self.noise_fn = _exp_noise   # tests may inject CPU-generator noise for cross-device parity
+
+    # -- flat-buffer binding ------------------------------------------------
+    def _param_order(self):
+        return list(self.parameters())
+
+    def bind(self):
+        dev = next(self.parameters()).device
+        if dev.type != "cuda":
+            raise RuntimeError("cleanrl_b200 agents execute on CUDA only (libb200rl kernels); "
+                               f"parameters are on {dev}. There is no CPU fallback.")
+        self._flat = nets.FlatParams(self._param_order(), dev)
+        self._build_plan()
+        return self._flat
+
+    @property
+    def flat(self):
+        p = next(self.parameters())
+        if self._flat is None or self._flat.flat.device != p.device or \
+                p.data_ptr() < self._flat.flat.data_ptr() or \
+                p.data_ptr() >= self._flat.flat.data_ptr() + self._flat.flat.numel() * 4:
+            self.bind()
+        return self._flat
+
+    # -- to be provided by subclasses --------------------------------------
+    def _build_plan(self):
+        raise NotImplementedError
+
+    def _forward_heads(self, x, rows=None, keep=False):
+        """returns (logits view [n,A] , value view [n] ) possibly strided"""
+        raise NotImplementedError
+
+    def backward(self, dlogits, dvalue):
+        raise NotImplementedError
+
+    # -- reference API ---------------------------------------------------------
+    def get_value(self, x):
+        self.flat
+        _, value = self._forward_heads(x)
+        return value.reshape(-1, 1).clone() if not value.is_contiguous() else value.reshape(-1, 1)
+
+    def get_action_and_value(self, x, action=None):
+        self.flat
+        logits, value = self._forward_heads(x)
+        n, A = logits.shape
+        if action is None:
+            q = self.noise_fn(n, A, logits.device)
+            action, logprob, entropy, v = ops.categorical_sample(logits, q, value)
+        else:
+            logprob, entropy = ops.categorical_eval(logits, action)
+            v = value.clone() if not value.is_contiguous() else value
+        return action, logprob, entropy, v.reshape(-1, 1)
+
+
+class NatureCNNAgent(KernelAgent):
+    """NatureCNN actor-critic (reference: cleanrl/ppo_atari_envpool.py:123-149)."""
+
+    def __init__(self, envs):
+        super().__init__()
+        c, h, w = envs.single_observation_space.shape
+        assert (c, h, w) == (4, 84, 84), "NatureCNN geometry is 4x84x84"
+        trunk = []
+        for cin, cout, k, s in ((4, 32, 8, 4), (32, 64, 4, 2), (64, 64, 3, 1)):
+            trunk += [layer_init(nn.Conv2d(cin, cout, k, stride=s)), nn.ReLU()]
+        trunk += [nn.Flatten(), layer_init(nn.Linear(64 * 7 * 7, 512)), nn.ReLU()]
+        self.network = nn.Sequential(*trunk)
+        self.actor = layer_init(nn.Linear(512, envs.single_action_space.n), std=0.01)
+        self.critic = layer_init(nn.Linear(512, 1), std=1)
+        self.num_actions = int(envs.single_action_space.n)
+
+    def _param_order(self):
+        net = [p for m in self.network for p in m.parameters()]
+        # both heads adjacent => one [A+1, 512] GEMM operand and one [A+1] bias
+        return net + [self.actor.weight, self.critic.weight, self.actor.bias, self.critic.bias]
+
+    def _build_plan(self):
+        f = self._flat
+        A = self.num_actions
+        wa, ga = f.view_of(self.actor.weight)
+        ba, gba = f.view_of(self.actor.bias)
+        off_w = (wa.data_ptr() - f.flat.data_ptr()) // 4
+        off_b = (ba.data_ptr() - f.flat.data_ptr()) // 4
+        self._head_w = f.flat[off_w:off_w + (A + 1) * 512].view(A + 1, 512)
+        self._head_b = f.flat[off_b:off_b + A + 1]
+        self._head_dw = f.grad[off_w:off_w + (A + 1) * 512].view(A + 1, 512)
+        self._head_db = f.grad[off_b:off_b + A + 1]
+        n = self.network
+        self.trunk = nets.Chain([
+            nets.Conv(n[0], "relu", in_div=255.0), nets.Conv(n[2], "relu"), nets.Conv(n[4], "relu"),
+            nets.Linear(n[7], "relu")])
+        self.head = nets.Linear(None, None, self._head_w, self._head_b, self._head_dw, self._head_db)
+
+    def _forward_heads(self, x, rows=None, keep=False):
+        if x.dtype not in (torch.uint8, torch.float32):
+            x = x.float()
+        hidden = self.trunk.fwd(x.contiguous(), rows=rows, keep=keep)
+        out = self.head.fwd(hidden)
+        if keep:
+            self._hidden = hidden
+        A = self.num_actions
+        return out[:, :A], out[:, A]
+
+    def forward_train(self, b_obs, mb_inds):
+        """Minibatch forward with fused row gather (b_obs[mb_inds] never materialised); keeps activations."""
+        self.flat
+        return self._forward_heads(b_obs, rows=mb_inds, keep=True)
+
+    def alloc_head_grad(self, M, device):
+        A = self.num_actions
+        d = torch.empty(M, A + 1, dtype=torch.float32, device=device)
+        return d, d[:, :A], d[:, A]
+
+    def backward(self, dhead):
+        """dhead [M, A+1] = [dlogits | dvalue]; fills the flat gradient buffer."""
+        hidden = self._hidden
+        self.head.bwd_weight(hidden, dhead)
+        dh = self.head.bwd_data(dhead, hidden, "relu")
+        self.trunk.bwd(dh)
+        self._hidden = None
+
+
+class MLPAgent(KernelAgent):
+    """Two 64-wide tanh MLPs, discrete actions (reference: cleanrl/ppo.py:100-126)."""
+
+    def __init__(self, envs):
+        super().__init__()
+        d = int(np.array(envs.single_observation_space.shape).prod())
+        A = int(envs.single_action_space.n)
+        self.critic = nn.Sequential(layer_init(nn.Linear(d, 64)), nn.Tanh(), layer_init(nn.Linear(64, 64)), nn.Tanh(),
+                                    layer_init(nn.Linear(64, 1), std=1.0))
+        self.actor = nn.Sequential(layer_init(nn.Linear(d, 64)), nn.Tanh(), layer_init(nn.Linear(64, 64)), nn.Tanh(),
+                                   layer_init(nn.Linear(64, A), std=0.01))
+        self.num_actions = A
+
+    def _build_plan(self):
+        mk = lambda seq: nets.Chain([nets.Linear(seq[0], "tanh"), nets.Linear(seq[2], "tanh"), nets.Linear(seq[4], None)])
+        self.c_chain, self.a_chain = mk(self.critic), mk(self.actor)
+
+    def _forward_heads(self, x, rows=None, keep=False):
+        x = x.float() if x.dtype != torch.float32 else x
+        x = x.reshape(x.shape[0], -1).contiguous()
+        logits = self.a_chain.fwd(x, rows=rows, keep=keep)
+        value = self.c_chain.fwd(x, rows=rows, keep=keep)
+        return logits, value[:, 0]
+
+    def forward_train(self, b_obs, mb_inds):
+        self.flat
+        return self._forward_heads(b_obs, rows=mb_inds, keep=True)
+
+    def alloc_head_grad(self, M, device):
+        dl = torch.empty(M, self.num_actions, dtype=torch.float32, device=device)
+        dv = torch.empty(M, 1, dtype=torch.float32, device=device)
+        return (dl, dv), dl, dv[:, 0]
+
+    def backward(self, dhead):
+        dl, dv = dhead
+        self.a_chain.bwd(dl)
+        self.c_chain.bwd(dv)

@@ -65,6 +65,25 @@ __global__ void __launch_bounds__(128) categorical_sample_kernel(
     if (value_out && value_in) value_out[i] = value_in[i * ldv];
 }
 
+// log_prob / entropy of GIVEN actions (Agent.get_action_and_value(x, action), ppo.py:121-126)
+__global__ void __launch_bounds__(128) categorical_eval_kernel(
+    const float* __restrict__ logits, int64_t ld, const int64_t* __restrict__ action, int64_t n, int A,
+    float* __restrict__ logprob, float* __restrict__ entropy) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const float* x = logits + i * ld;
+    const RowStats rs = row_stats(x, A);
+    float ent = 0.f;
+    for (int k = 0; k < A; ++k) {
+        const float nl = x[k] - rs.lse;
+        ent += fmaxf(nl, -FLT_MAX) * (expf(nl - rs.m2) / rs.s2);
+    }
+    int a = (int)action[i];
+    a = a < 0 ? 0 : (a >= A ? A - 1 : a);
+    logprob[i] = x[a] - rs.lse;
+    if (entropy) entropy[i] = -ent;
+}
+
 // ---- advantage statistics of the gathered minibatch (single block, 2 passes)
 __global__ void __launch_bounds__(1024) adv_stats_kernel(
     const float* __restrict__ b_adv, const int64_t* __restrict__ inds, int64_t M, float* __restrict__ out2) {
@@ -231,6 +250,19 @@ extern "C" int b200rl_categorical_sample_f32(const float* logits, int64_t ld_log
     categorical_sample_kernel<<<blocks, 128, 0, (cudaStream_t)stream>>>(
         logits, ld_logits, noise, value_in, ld_value, n, A, action, logprob, entropy, value_out);
     return check_launch("categorical_sample");
+}
+
+extern "C" int b200rl_categorical_eval_f32(const float* logits, int64_t ld_logits, const int64_t* action,
+                                           int64_t n, int A, float* logprob, float* entropy, void* stream) {
+    using namespace b200rl;
+    B200RL_REQUIRE(n >= 0, "categorical_eval: negative n");
+    if (n == 0) return B200RL_OK;
+    B200RL_REQUIRE(A >= 1 && A <= kMaxA, "categorical_eval: A=%d outside [1,%d]", A, kMaxA);
+    B200RL_REQUIRE(logits && action && logprob, "categorical_eval: null pointer");
+    B200RL_REQUIRE(ld_logits >= A, "categorical_eval: ld_logits < A");
+    categorical_eval_kernel<<<(unsigned)ceil_div(n, 128), 128, 0, (cudaStream_t)stream>>>(
+        logits, ld_logits, action, n, A, logprob, entropy);
+    return check_launch("categorical_eval");
 }
 
 extern "C" size_t b200rl_ppo_loss_workspace_bytes(int64_t M) {

@@ -113,6 +113,23 @@ def categorical_sample(logits, noise, value_in=None, out=None):
     return action, logprob, entropy, value
 
 
+def categorical_eval(logits, action):
+    """logprob, entropy of given actions (reference: probs.log_prob(action), probs.entropy())."""
+    lib = _lib.load()
+    n, A = logits.shape
+    assert logits.stride(1) == 1
+    action = _contig(action.reshape(-1), "action")
+    if action.dtype != torch.int64:
+        action = action.long()
+    f = torch.float32
+    logprob = torch.empty(n, dtype=f, device=logits.device)
+    entropy = torch.empty(n, dtype=f, device=logits.device)
+    rc = lib.b200rl_categorical_eval_f32(_ptr(logits, f, "logits"), logits.stride(0), _ptr(action, torch.int64, "action"),
+                                         n, A, _ptr(logprob, f, "logprob"), _ptr(entropy, f, "entropy"), _stream())
+    _lib.check(rc, "categorical_eval")
+    return logprob, entropy
+
+
 def ppo_loss(new_logits, new_value, mb_inds, b_actions, b_logprobs, b_advantages, b_returns, b_values,
              clip_coef, ent_coef, vf_coef, norm_adv=True, clip_vloss=True, dlogits=None, dvalue=None, stats=None):
     """Fused PPO minibatch loss + gradients (reference: cleanrl/ppo.py:250-285).
@@ -169,3 +186,109 @@ def clip_adam(params, grads, exp_avg, exp_avg_sq, step, lr, beta1=0.9, beta2=0.9
         _ptr(norm_out, f, "norm_out", True), ws.data_ptr(), ws.numel(), _stream())
     _lib.check(rc, "clip_adam")
     return params
+
+
+# ----------------------------------------------------------------- fp32 layers
+ACT = {None: 0, "none": 0, "relu": 1, "tanh": 2}
+
+
+def _xdtype(x):
+    if x.dtype == torch.uint8:
+        return 1
+    if x.dtype == torch.float32:
+        return 0
+    raise TypeError(f"unsupported input dtype {x.dtype} (need uint8 or float32)")
+
+
+def conv2d_fwd(x, w, b, stride, act, rows=None, in_div=1.0, out=None):
+    """y = act(conv2d(x / in_div, w) + b), NCHW (reference: nn.Conv2d + ReLU, ppo_atari_envpool.py:126-132).
+    ``rows`` (int64) gathers the batch dimension of x without materialising it (ppo.py:250)."""
+    lib = _lib.load()
+    _contig(x, "x"); _contig(w, "w")
+    Cout, Cin, KH, KW = w.shape
+    H, W = x.shape[-2:]
+    assert x.shape[-3] == Cin
+    n = rows.numel() if rows is not None else x.shape[0]
+    OH, OW = (H - KH) // stride + 1, (W - KW) // stride + 1
+    if out is None:
+        out = torch.empty(n, Cout, OH, OW, dtype=torch.float32, device=x.device)
+    rc = lib.b200rl_conv2d_fwd_f32(_ptr(x, None, "x"), _xdtype(x), _ptr(rows, torch.int64, "rows", True), float(in_div),
+                                   _ptr(w, torch.float32, "w"), _ptr(b, torch.float32, "b", True),
+                                   _ptr(out, torch.float32, "y"), n, Cin, H, W, Cout, KH, KW, stride, ACT[act], _stream())
+    _lib.check(rc, "conv2d_fwd")
+    return out
+
+
+def conv2d_bwd_data(dy, w, x_post, prev_act, stride, out=None):
+    lib = _lib.load()
+    _contig(dy, "dy"); _contig(w, "w")
+    Cout, Cin, KH, KW = w.shape
+    n = dy.shape[0]
+    H, W = x_post.shape[-2:]
+    if out is None:
+        out = torch.empty(n, Cin, H, W, dtype=torch.float32, device=dy.device)
+    rc = lib.b200rl_conv2d_bwd_data_f32(_ptr(dy, torch.float32, "dy"), _ptr(w, torch.float32, "w"),
+                                        _ptr(x_post, torch.float32, "x_post"), ACT[prev_act],
+                                        _ptr(out, torch.float32, "dx"), n, Cin, H, W, Cout, KH, KW, stride, _stream())
+    _lib.check(rc, "conv2d_bwd_data")
+    return out
+
+
+def conv2d_bwd_weight(x, dy, dw, db, stride, rows=None, in_div=1.0):
+    lib = _lib.load()
+    _contig(x, "x"); _contig(dy, "dy"); _contig(dw, "dw")
+    Cout, Cin, KH, KW = dw.shape
+    H, W = x.shape[-2:]
+    n = dy.shape[0]
+    nbytes = lib.b200rl_conv2d_bwd_weight_workspace_bytes(n, Cin, H, W, Cout, KH, KW, stride)
+    ws = _workspace(x.device, "wgrad", nbytes)
+    rc = lib.b200rl_conv2d_bwd_weight_f32(_ptr(x, None, "x"), _xdtype(x), _ptr(rows, torch.int64, "rows", True),
+                                          float(in_div), _ptr(dy, torch.float32, "dy"), _ptr(dw, torch.float32, "dw"),
+                                          _ptr(db, torch.float32, "db", True), n, Cin, H, W, Cout, KH, KW, stride,
+                                          ws.data_ptr(), ws.numel(), _stream())
+    _lib.check(rc, "conv2d_bwd_weight")
+
+
+def linear_fwd(x, w, b, act, rows=None, out=None):
+    """y = act(x @ w.T + b) (reference: nn.Linear + activation)."""
+    lib = _lib.load()
+    _contig(x, "x"); _contig(w, "w")
+    out_f, in_f = w.shape
+    x2 = x.reshape(x.shape[0], -1)
+    assert x2.shape[1] == in_f, f"linear_fwd: x has {x2.shape[1]} features, w expects {in_f}"
+    n = rows.numel() if rows is not None else x2.shape[0]
+    if out is None:
+        out = torch.empty(n, out_f, dtype=torch.float32, device=x.device)
+    rc = lib.b200rl_linear_fwd_f32(_ptr(x2, torch.float32, "x"), _ptr(rows, torch.int64, "rows", True),
+                                   _ptr(w, torch.float32, "w"), _ptr(b, torch.float32, "b", True),
+                                   _ptr(out, torch.float32, "y"), n, in_f, out_f, ACT[act], _stream())
+    _lib.check(rc, "linear_fwd")
+    return out
+
+
+def linear_bwd_data(dy, w, x_post, prev_act, out=None):
+    lib = _lib.load()
+    _contig(dy, "dy"); _contig(w, "w")
+    out_f, in_f = w.shape
+    n = dy.shape[0]
+    if out is None:
+        out = torch.empty(n, in_f, dtype=torch.float32, device=dy.device)
+    rc = lib.b200rl_linear_bwd_data_f32(_ptr(dy, torch.float32, "dy"), _ptr(w, torch.float32, "w"),
+                                        _ptr(x_post, torch.float32, "x_post", True), ACT[prev_act],
+                                        _ptr(out, torch.float32, "dx"), n, in_f, out_f, _stream())
+    _lib.check(rc, "linear_bwd_data")
+    return out
+
+
+def linear_bwd_weight(x, dy, dw, db, rows=None):
+    lib = _lib.load()
+    _contig(x, "x"); _contig(dy, "dy"); _contig(dw, "dw")
+    out_f, in_f = dw.shape
+    n = dy.shape[0]
+    nbytes = lib.b200rl_linear_bwd_weight_workspace_bytes(n, in_f, out_f)
+    ws = _workspace(x.device, "wgrad", nbytes)
+    rc = lib.b200rl_linear_bwd_weight_f32(_ptr(x, torch.float32, "x"), _ptr(rows, torch.int64, "rows", True),
+                                          _ptr(dy, torch.float32, "dy"), _ptr(dw, torch.float32, "dw"),
+                                          _ptr(db, torch.float32, "db", True), n, in_f, out_f,
+                                          ws.data_ptr(), ws.numel(), _stream())
+    _lib.check(rc, "linear_bwd_weight")

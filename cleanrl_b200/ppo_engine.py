@@ -1,0 +1,181 @@
+"""B200-native PPO iteration engine: rollout storage, policy step, GAE, minibatch update.
+
+This is the loop body of the reference scripts (cleanrl/ppo.py:185-310 and its
+twins in ppo_atari_envpool.py / ppo_atari_multigpu.py) re-designed around
+device-resident buffers and fused kernels:
+
+* observations stay uint8 end to end: pinned host batch -> async H2D straight
+  into the rollout slot ``obs[t]`` (the reference converts to fp32 on the host
+  and keeps a 14.8 GB fp32 buffer, ppo_atari_envpool.py:203,239);
+* rewards / dones are kept in pinned host memory during the rollout and
+  uploaded once per iteration (the reference does 2 H2D + N scalar syncs per step);
+* one launch per network layer + one sampler launch per env step, no autograd;
+* GAE is one kernel; the loss (+its gradient) is one kernel; clip+Adam is one
+  fused pass over a flat parameter vector; the DP gradient exchange is ONE
+  in-place all-reduce of that flat vector (ppo_atari_multigpu.py:360-374).
+
+numpy's global RNG still drives the minibatch shuffle and torch's generator the
+sampling noise, so seeds mean what they mean in the reference (ppo.py:153-157).
+"""
+from __future__ import annotations
+
+import numpy as np
+import torch
+
+from . import ops
+
+STAT_NAMES = ops.STAT_NAMES
+
+
+def _torch_dtype(np_dtype):
+    return torch.uint8 if np.dtype(np_dtype) == np.uint8 else torch.float32
+
+
+class PPOEngine:
+    def __init__(self, agent, args, obs_shape, obs_dtype, num_envs, device, world_size=1, gae_mode=0,
+                 all_reduce=None):
+        if device.type != "cuda":
+            raise RuntimeError("PPOEngine drives libb200rl CUDA kernels and needs a CUDA device; "
+                               "there is no CPU fallback (got device=%s)" % device)
+        self.agent, self.args, self.device = agent, args, device
+        self.T, self.N = int(args.num_steps), int(num_envs)
+        self.B = self.T * self.N
+        self.num_minibatches = int(args.num_minibatches)
+        self.M = self.B // self.num_minibatches
+        self.world_size = int(world_size)
+        self.all_reduce = all_reduce
+        self.gae_mode = gae_mode
+        T, N = self.T, self.N
+        self.obs_dtype = _torch_dtype(obs_dtype)
+        f32 = torch.float32
+        self.obs = torch.zeros((T, N) + tuple(obs_shape), dtype=self.obs_dtype, device=device)
+        self.actions = torch.zeros((T, N), dtype=torch.int64, device=device)
+        self.logprobs = torch.zeros((T, N), dtype=f32, device=device)
+        self.values = torch.zeros((T, N), dtype=f32, device=device)
+        self.rewards = torch.zeros((T, N), dtype=f32, device=device)
+        self.dones = torch.zeros((T, N), dtype=f32, device=device)
+        self.advantages = torch.zeros((T, N), dtype=f32, device=device)
+        self.returns = torch.zeros((T, N), dtype=f32, device=device)
+        self.next_obs = torch.zeros((N,) + tuple(obs_shape), dtype=self.obs_dtype, device=device)
+        self.next_done = torch.zeros(N, dtype=f32, device=device)
+        self.next_value = torch.zeros(N, dtype=f32, device=device)
+        # pinned host mirrors
+        self.rewards_h = torch.zeros((T, N), dtype=f32).pin_memory()
+        self.dones_h = torch.zeros((T, N), dtype=f32).pin_memory()
+        self.next_done_h = torch.zeros(N, dtype=f32).pin_memory()
+        self.actions_h = torch.zeros(N, dtype=torch.int64).pin_memory()
+        self.obs_stage_h = torch.zeros((N,) + tuple(obs_shape), dtype=self.obs_dtype).pin_memory()
+        self.b_inds_h = torch.zeros(self.B, dtype=torch.int64).pin_memory()
+        self.b_inds = torch.zeros(self.B, dtype=torch.int64, device=device)
+        n_upd = int(args.update_epochs) * self.num_minibatches
+        self.stats = torch.zeros(max(n_upd, 1), 16, dtype=f32, device=device)
+        self.stats_h = torch.zeros(max(n_upd, 1), 16, dtype=f32).pin_memory()
+        self.grad_norm = torch.zeros(1, dtype=f32, device=device)
+        self.flat = agent.flat
+        self.h2d_bytes = 0
+        self.d2h_bytes = 0
+        self.kernel_launches = 0
+
+    # ------------------------------------------------------------------ rollout
+    def _upload_obs(self, dst, obs_np):
+        src = torch.from_numpy(np.ascontiguousarray(obs_np))
+        if src.dtype != self.obs_dtype:
+            src = src.to(self.obs_dtype)
+        if not src.is_pinned():
+            self.obs_stage_h.copy_(src)
+            src = self.obs_stage_h
+        dst.copy_(src, non_blocking=True)
+        self.h2d_bytes += src.numel() * src.element_size()
+
+    @torch.no_grad()
+    def policy_step(self, step, next_obs_np, next_done_np):
+        """obs[step] <- next_obs (H2D), sample actions, return them as a host int64 array.
+        Reference: ppo.py:194-205 (store obs/done, no-grad policy, action.cpu())."""
+        self._upload_obs(self.obs[step], next_obs_np)
+        self.dones_h[step].copy_(torch.as_tensor(np.asarray(next_done_np, dtype=np.float32)))
+        logits, value = self.agent._forward_heads(self.obs[step])
+        n, A = logits.shape
+        q = self.agent.noise_fn(n, A, self.device)
+        ops.categorical_sample(logits, q, value,
+                               out=(self.actions[step], self.logprobs[step], None, self.values[step]))
+        self.actions_h.copy_(self.actions[step], non_blocking=True)
+        self.d2h_bytes += self.actions_h.numel() * 8
+        torch.cuda.current_stream().synchronize()
+        return self.actions_h.numpy()
+
+    def record_reward(self, step, reward_np):
+        self.rewards_h[step].copy_(torch.as_tensor(np.asarray(reward_np, dtype=np.float32).reshape(-1)))
+
+    @torch.no_grad()
+    def finish_rollout(self, next_obs_np, next_done_np):
+        """Bootstrap value + GAE (reference: ppo.py:217-231)."""
+        self.rewards.copy_(self.rewards_h, non_blocking=True)
+        self.dones.copy_(self.dones_h, non_blocking=True)
+        self.next_done_h.copy_(torch.as_tensor(np.asarray(next_done_np, dtype=np.float32)))
+        self.next_done.copy_(self.next_done_h, non_blocking=True)
+        self.h2d_bytes += 2 * self.B * 4 + self.N * 4
+        self._upload_obs(self.next_obs, next_obs_np)
+        _, value = self.agent._forward_heads(self.next_obs)
+        self.next_value.copy_(value)
+        ops.gae(self.rewards, self.values, self.dones, self.next_value, self.next_done,
+                self.args.gamma, self.args.gae_lambda, mode=self.gae_mode,
+                out=(self.advantages, self.returns))
+
+    # ------------------------------------------------------------------- update
+    @torch.no_grad()
+    def update(self, lr):
+        """update_epochs x num_minibatches fused updates (reference: ppo.py:233-293).
+        Returns dict of the logged scalars (last minibatch's losses, mean clipfrac)."""
+        a = self.args
+        B, M = self.B, self.M
+        agent, flat = self.agent, self.flat
+        b_obs = self.obs.view((B,) + tuple(self.obs.shape[2:]))
+        b_actions = self.actions.view(B)
+        b_logprobs = self.logprobs.view(B)
+        b_adv = self.advantages.view(B)
+        b_ret = self.returns.view(B)
+        b_val = self.values.view(B)
+        b_inds_np = np.arange(B)
+        dhead, dlogits, dvalue = agent.alloc_head_grad(M, self.device)
+        k = 0
+        stop = False
+        for epoch in range(int(a.update_epochs)):
+            np.random.shuffle(b_inds_np)                    # numpy global RNG, as the reference
+            self.b_inds_h.copy_(torch.from_numpy(b_inds_np))
+            self.b_inds.copy_(self.b_inds_h, non_blocking=True)
+            self.h2d_bytes += B * 8
+            for start in range(0, B, M):
+                mb_inds = self.b_inds[start:start + M]
+                logits, value = agent.forward_train(b_obs, mb_inds)
+                ops.ppo_loss(logits, value, mb_inds, b_actions, b_logprobs, b_adv, b_ret, b_val,
+                             a.clip_coef, a.ent_coef, a.vf_coef, a.norm_adv, a.clip_vloss,
+                             dlogits=dlogits, dvalue=dvalue, stats=self.stats[k])
+                agent.backward(dhead)
+                if self.world_size > 1:
+                    self.all_reduce(flat.grad)
+                flat.step += 1
+                ops.clip_adam(flat.flat, flat.grad, flat.exp_avg, flat.exp_avg_sq, flat.step, lr,
+                              eps=1e-5, max_norm=a.max_grad_norm, world_size=self.world_size,
+                              norm_out=self.grad_norm)
+                k += 1
+            if a.target_kl is not None:
+                approx_kl = self.stats[k - 1, 4].item()
+                if approx_kl > a.target_kl:
+                    break
+        self.stats_h[:k].copy_(self.stats[:k], non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+        self.d2h_bytes += k * 64
+        s = self.stats_h[:k].numpy()
+        out = {name: float(s[k - 1, i]) for i, name in enumerate(STAT_NAMES)}
+        out["clipfrac_mean"] = float(np.mean(s[:, 5].astype(np.float64)))   # np.mean(clipfracs), ppo.py:306
+        out["num_updates"] = k
+        out["per_update"] = s.copy()
+        return out
+
+    def explained_variance(self):
+        """ppo.py:295-297 on host numpy."""
+        y_pred = self.values.view(-1).cpu().numpy()
+        y_true = self.returns.view(-1).cpu().numpy()
+        self.d2h_bytes += 2 * self.B * 4
+        var_y = np.var(y_true)
+        return np.nan if var_y == 0 else 1 - np.var(y_true - y_pred) / var_y

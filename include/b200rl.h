@@ -84,6 +84,11 @@ int b200rl_categorical_sample_f32(const float* logits, int64_t ld_logits, const 
                                   int64_t* action, float* logprob, float* entropy, float* value_out,
                                   void* stream);
 
+/* log_prob and entropy of GIVEN actions (the action != None branch of
+ * Agent.get_action_and_value, cleanrl/ppo.py:121-126).  action i64 [n] (clamped to [0,A)). */
+int b200rl_categorical_eval_f32(const float* logits, int64_t ld_logits, const int64_t* action,
+                                int64_t n, int A, float* logprob, float* entropy, void* stream);
+
 /* -------------------------------------------------------------- PPO loss ---
  * Fused minibatch loss: gather by mb_inds, advantage normalisation (unbiased
  * std), ratio, both KL estimates, clipfrac, clipped surrogate, clipped value
@@ -145,8 +150,8 @@ int b200rl_clip_adam_f32(float* params, const float* grads, float* exp_avg, floa
 enum { B200RL_ACT_NONE = 0, B200RL_ACT_RELU = 1, B200RL_ACT_TANH = 2 };
 enum { B200RL_DT_F32 = 0, B200RL_DT_U8 = 1 };
 
-/* y[n,Cout,OH,OW] = act(in_scale * conv(x[n,Cin,H,W], w[Cout,Cin,KH,KW]) + b) */
-int b200rl_conv2d_fwd_f32(const void* x, int x_dtype, const int64_t* rows, double in_scale,
+/* y[n,Cout,OH,OW] = act(conv(x[n,Cin,H,W] / in_div, w[Cout,Cin,KH,KW]) + b)  (in_div = 255 for uint8 obs, 1 otherwise) */
+int b200rl_conv2d_fwd_f32(const void* x, int x_dtype, const int64_t* rows, double in_div,
                           const float* w, const float* b, float* y,
                           int64_t n, int Cin, int H, int W, int Cout, int KH, int KW, int stride,
                           int act, void* stream);
@@ -156,10 +161,10 @@ int b200rl_conv2d_bwd_data_f32(const float* dy, const float* w, const float* x_p
                                float* dx,
                                int64_t n, int Cin, int H, int W, int Cout, int KH, int KW, int stride,
                                void* stream);
-/* dw[Cout,Cin,KH,KW] = sum_m dy * im2col(x)*in_scale ; db[Cout] = sum dy.  Deterministic split
+/* dw[Cout,Cin,KH,KW] = sum_m dy * im2col(x / in_div) ; db[Cout] = sum dy.  Deterministic split
  * reduction through `workspace` (b200rl_conv2d_bwd_weight_workspace_bytes). */
 size_t b200rl_conv2d_bwd_weight_workspace_bytes(int64_t n, int Cin, int H, int W, int Cout, int KH, int KW, int stride);
-int b200rl_conv2d_bwd_weight_f32(const void* x, int x_dtype, const int64_t* rows, double in_scale,
+int b200rl_conv2d_bwd_weight_f32(const void* x, int x_dtype, const int64_t* rows, double in_div,
                                  const float* dy, float* dw, float* db,
                                  int64_t n, int Cin, int H, int W, int Cout, int KH, int KW, int stride,
                                  void* workspace, size_t workspace_bytes, void* stream);

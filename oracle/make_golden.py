@@ -1,0 +1,83 @@
+"""Generate tests/golden/*.npz from the UNMODIFIED reference (build container only).
+
+    python -m oracle.make_golden
+
+Each fixture records what the reference script computed on CPU for a small,
+seeded configuration of the synthetic envs; the GPU box (which has no
+/root/reference) replays the same configuration through the CUDA path and
+compares.  TEST INFRASTRUCTURE ONLY.
+"""
+from __future__ import annotations
+
+import sys
+from pathlib import Path
+
+import numpy as np
+
+from oracle.ref_harness import run_reference
+
+OUT = Path(__file__).resolve().parent.parent / "tests" / "golden"
+
+
+def _stack(recs, key):
+    return np.stack([r[key] for r in recs])
+
+
+def atari_envpool(name, argv, n_iter):
+    rec, g = run_reference("ppo_atari_envpool.py", argv, atari_mode="fresh")
+    assert len(rec.iterations) == n_iter
+    out = {"argv": np.array(argv)}
+    for k in ("actions", "logprobs", "rewards", "dones", "values", "advantages", "returns", "next_value", "next_done",
+              "param_sums", "param_abs_sums"):
+        out[k] = _stack(rec.iterations, k)
+    for k in ("pg_loss", "v_loss", "entropy_loss", "old_approx_kl", "approx_kl", "loss", "clipfrac", "lr",
+              "grad_norm_postclip"):
+        out["upd_" + k] = np.array([u[k] for u in rec.updates])
+    out["upd_param_sums"] = _stack(rec.updates, "param_sums")
+    out["upd_mb_inds_head"] = _stack(rec.updates, "mb_inds_head")
+    out["shuffles"] = np.stack(rec.shuffles)
+    tags = sorted({t for t, _, _ in rec.scalars})
+    for t in tags:
+        vals = [(s, v) for tt, v, s in rec.scalars if tt == t]
+        out["tb/" + t] = np.array(vals, dtype=np.float64)
+    np.savez_compressed(OUT / name, **out)
+    print("wrote", name, {k: v.shape for k, v in out.items() if hasattr(v, "shape")})
+
+
+def mlp_ppo(name, argv):
+    """cleanrl/ppo.py with the CartPole-shaped synthetic env: per-update tensors for loss/Adam oracles."""
+    rec, g = run_reference("ppo.py", argv, gymnasium_kind="discrete", keep_params=True)
+    out = {"argv": np.array(argv)}
+    for k in ("actions", "logprobs", "rewards", "dones", "values", "advantages", "returns", "next_value", "next_done"):
+        out[k] = _stack(rec.iterations, k)
+    ups = rec.updates[:6]
+    for k in ("pg_loss", "v_loss", "entropy_loss", "old_approx_kl", "approx_kl", "loss", "clipfrac", "lr"):
+        out["upd_" + k] = np.array([u[k] for u in rec.updates])
+    for k in ("mb_inds", "newlogprob", "entropy", "newvalue", "logits", "mb_advantages"):
+        out["mb_" + k] = _stack(ups, k)
+    for k in ("b_logprobs", "b_advantages", "b_returns", "b_values", "b_actions"):
+        out[k] = ups[0][k]
+    flat = lambda lst: np.concatenate([x.reshape(-1) for x in lst])
+    out["grads_flat"] = np.stack([flat(u["grads"]) for u in ups])          # AFTER clip_grad_norm_
+    out["params_before_flat"] = np.stack([flat(u["params_before"]) for u in ups])
+    out["params_after_flat"] = np.stack([flat(u["params"]) for u in ups])
+    out["param_shapes"] = np.array([list(x.shape) + [0] * (2 - x.ndim) for x in ups[0]["params"]])
+    out["shuffles"] = np.stack(rec.shuffles)
+    np.savez_compressed(OUT / name, **out)
+    print("wrote", name)
+
+
+def main():
+    OUT.mkdir(parents=True, exist_ok=True)
+    atari_envpool("ppo_atari_envpool_n8_t32_seed1.npz",
+                  ["--no-cuda", "--num-envs", "8", "--num-steps", "32", "--total-timesteps", "768", "--seed", "1"], 3)
+    atari_envpool("ppo_atari_envpool_n16_t16_seed3_noclipv.npz",
+                  ["--no-cuda", "--num-envs", "16", "--num-steps", "16", "--total-timesteps", "512", "--seed", "3",
+                   "--no-clip-vloss", "--gamma", "0.98", "--gae-lambda", "0.9", "--no-anneal-lr",
+                   "--update-epochs", "2", "--ent-coef", "0.02"], 2)
+    mlp_ppo("ppo_mlp_n4_t128_seed1.npz",
+            ["--no-cuda", "--num-envs", "4", "--num-steps", "128", "--total-timesteps", "1024", "--seed", "1"])
+
+
+if __name__ == "__main__":
+    sys.exit(main())

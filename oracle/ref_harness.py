@@ -47,6 +47,7 @@ class Recorder:
         self.shuffles = []
         self.texts = []
         self.keep_params = keep_params
+        self.last_logits = None
 
     # called from the capturing writer on 'charts/learning_rate' (first scalar after the update loop)
     def end_of_iteration(self, g):
@@ -73,6 +74,13 @@ class Recorder:
             rec["grad_norm_postclip"] = float(torch.sqrt(sum((x.double() ** 2).sum() for x in grads)))
             if self.keep_params:
                 rec["grads"] = [_np(x) for x in grads]
+                rec["params_before"] = [_np(p) for p in g["agent"].parameters()]
+                for k in ("mb_inds", "newlogprob", "entropy", "newvalue", "b_logprobs", "b_advantages",
+                          "b_returns", "b_values", "b_actions", "mb_advantages"):
+                    if k in g:
+                        rec[k] = _np(g[k])
+                if self.last_logits is not None:
+                    rec["logits"] = _np(self.last_logits)
             self.updates.append(rec)
         else:
             rec = self.updates[-1]
@@ -134,6 +142,15 @@ def run_reference(script, argv, atari_mode="fresh", gymnasium_kind="discrete", k
             rec.on_adam_step(g, before=False)
         return out
 
+    from torch.distributions.categorical import Categorical
+    orig_cat_init = Categorical.__init__
+
+    def cat_init(self_, probs=None, logits=None, validate_args=None):
+        if logits is not None:
+            rec.last_logits = logits.detach()
+        return orig_cat_init(self_, probs=probs, logits=logits, validate_args=validate_args)
+
+    Categorical.__init__ = cat_init
     tb.SummaryWriter = CapturingWriter
     np.random.shuffle = shuffle
     torch.optim.Adam.step = step
@@ -145,6 +162,7 @@ def run_reference(script, argv, atari_mode="fresh", gymnasium_kind="discrete", k
         g = runpy.run_path(str(path), run_name="__main__")
     finally:
         tb.SummaryWriter = orig_writer
+        Categorical.__init__ = orig_cat_init
         np.random.shuffle = orig_shuffle
         torch.optim.Adam.step = orig_step
         sys.argv = orig_argv

@@ -1,0 +1,120 @@
+"""CPU tests: the C-ABI library builds for sm_100a, loads, and exports every symbol
+include/b200rl.h declares; the CLI surface matches the reference; the product has no
+CPU fallback and never imports the oracle."""
+import ctypes
+import re
+import subprocess
+import sys
+from pathlib import Path
+
+import pytest
+
+ROOT = Path(__file__).resolve().parent.parent
+
+
+def _declared_symbols():
+    txt = (ROOT / "include" / "b200rl.h").read_text()
+    txt = re.sub(r"/\*.*?\*/", "", txt, flags=re.S)
+    return sorted(set(re.findall(r"\b(b200rl_[a-z0-9_]+)\s*\(", txt)))
+
+
+def test_library_exports_every_declared_symbol(lib):
+    syms = _declared_symbols()
+    assert len(syms) >= 15
+    raw = ctypes.CDLL(str(ROOT / "cleanrl_b200" / "libb200rl.so"))
+    for s in syms:
+        assert hasattr(raw, s), f"{s} declared in include/b200rl.h but not exported"
+    from cleanrl_b200 import _lib
+    assert sorted(_lib.SIGNATURES) == syms, "python binding table out of sync with the header"
+    assert lib.b200rl_compiled_arch() == 100
+    assert lib.b200rl_version() >= 100
+
+
+def test_library_contains_sm100a_code_only():
+    out = subprocess.run(["cuobjdump", "-lelf", str(ROOT / "cleanrl_b200" / "libb200rl.so")], capture_output=True, text=True)
+    if out.returncode != 0:
+        pytest.skip("cuobjdump unavailable")
+    archs = set(re.findall(r"sm_(\d+a?)", out.stdout))
+    assert archs == {"100a"}, archs
+
+
+def test_argument_validation_without_gpu(lib):
+    """Validation happens before any CUDA call, so it is testable on a CPU-only box."""
+    rc = lib.b200rl_gae_f32(None, None, None, None, None, None, None, 4, 4, 0.99, 0.95, 0, None)
+    assert rc == -1 and b"null" in lib.b200rl_last_error()
+    rc = lib.b200rl_gae_f32(None, None, None, None, None, None, None, 0, 4, 0.99, 0.95, 0, None)
+    assert rc == 0  # empty rollout is a no-op
+    rc = lib.b200rl_categorical_sample_f32(1, 4, 1, None, 0, 8, 100, 1, 1, None, None, None)
+    assert rc == -1 and b"outside" in lib.b200rl_last_error()
+    rc = lib.b200rl_clip_adam_f32(16, 16, 16, 16, 8, 0, 1e-3, 0.9, 0.999, 1e-5, 0.5, 1, None, 16, 1 << 20, None)
+    assert rc == -1 and b"1-based" in lib.b200rl_last_error()
+    rc = lib.b200rl_ppo_loss_f32(16, 4, 16, 1, None, 16, 16, 16, 16, 16, 8, 4, .1, .01, .5, 1, 1, 16, 4, 16, 1, 16, 16, 8, None)
+    assert rc == -4  # workspace too small
+
+
+def test_ops_reject_cpu_tensors(lib):
+    import torch
+    from cleanrl_b200 import ops
+    x = torch.zeros(4, 4)
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        ops.gae(x, x, x, x[0], x[0], 0.99, 0.95)
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        ops.clip_adam(x.view(-1), x.view(-1), x.view(-1), x.view(-1), 1, 1e-3)
+
+
+def test_script_refuses_to_run_without_cuda():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("CUDA present")
+    from cleanrl_b200 import ppo_atari_envpool as S
+
+    class W:
+        def __init__(self, *a): pass
+        def add_text(self, *a): pass
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        S.main(["--num-envs", "2", "--num-steps", "4", "--total-timesteps", "8"], writer_factory=W)
+
+
+def test_product_never_imports_oracle():
+    for p in list((ROOT / "cleanrl_b200").rglob("*.py")):
+        txt = p.read_text()
+        assert not re.search(r"^\s*(from|import)\s+oracle\b", txt, flags=re.M), f"{p} imports the oracle"
+
+
+@pytest.mark.reference
+@pytest.mark.parametrize("script,factory", [
+    ("ppo.py", "ppo_args"), ("ppo_atari_envpool.py", "ppo_atari_envpool_args"),
+    ("ppo_atari_multigpu.py", "ppo_atari_multigpu_args"), ("ppo_continuous_action.py", "ppo_continuous_action_args")])
+def test_cli_fields_match_reference_args(script, factory):
+    """Every reference flag exists with the same default and help text (reference Args dataclasses)."""
+    import ast
+    import dataclasses
+    from cleanrl_b200 import cli
+    src = Path("/root/reference/cleanrl") / script
+    tree = ast.parse(src.read_text())
+    cls = next(n for n in tree.body if isinstance(n, ast.ClassDef) and n.name == "Args")
+    ref = {}
+    body = cls.body
+    for i, node in enumerate(body):
+        if isinstance(node, ast.AnnAssign):
+            name = node.target.id
+            try:
+                default = ast.literal_eval(node.value)
+            except Exception:
+                default = "<expr>"
+            doc = None
+            if i + 1 < len(body) and isinstance(body[i + 1], ast.Expr) and isinstance(body[i + 1].value, ast.Constant):
+                doc = body[i + 1].value.value
+            ref[name] = (default, doc)
+    ours = getattr(cli, factory)()
+    fields = {f.name: f for f in dataclasses.fields(ours)}
+    for name, (default, doc) in ref.items():
+        assert name in fields, f"{script}: flag {name} missing"
+        f = fields[name]
+        if default != "<expr>":
+            d = f.default if f.default is not dataclasses.MISSING else f.default_factory()
+            assert d == default, (name, d, default)
+        helps = [m.help for m in getattr(f.type, "__metadata__", ()) if hasattr(m, "help")]
+        assert helps and helps[0] == doc, (name, helps, doc)
+    extra = set(fields) - set(ref)
+    assert extra <= {"precision", "gae_kernel", "synthetic_env"}, extra

@@ -1,0 +1,97 @@
+"""-m gpu: the whole drop-in script (cleanrl_b200/ppo_atari_envpool.py, fp32 kernels) replays the
+configurations of tests/golden/ppo_atari_envpool_*.npz -- produced by the UNMODIFIED reference script on CPU
+(oracle/make_golden.py) -- and must reproduce them: actions bit-exact, everything else <= 1e-5 (fp32)
+relative to the tensor's scale.  Sampling noise is drawn from torch's CPU generator (as the CPU
+reference run did) and copied to the device, so the RNG stream is identical."""
+import numpy as np
+import pytest
+import torch
+
+from conftest import GOLDEN
+
+pytestmark = pytest.mark.gpu
+
+
+class _Writer:
+    def __init__(self, *a, **k):
+        self.scalars = []
+    def add_text(self, *a, **k): pass
+    def add_scalar(self, tag, v, step): self.scalars.append((tag, float(v), int(step)))
+    def close(self): pass
+
+
+def _cpu_noise(n, A, device):
+    return torch.empty(n, A, dtype=torch.float32).exponential_(1).to(device)
+
+
+def _run(name, extra=()):
+    from cleanrl_b200 import ppo_atari_envpool as S
+    from cleanrl_b200.agents import NatureCNNAgent
+    z = np.load(GOLDEN / name)
+    argv = [a for a in z["argv"].tolist() if a != "--no-cuda"] + list(extra)
+    snaps = []
+    writers = []
+
+    def on_it(it, eng, st):
+        snaps.append({k: getattr(eng, k).cpu().numpy().copy() for k in
+                      ("actions", "logprobs", "values", "rewards", "dones", "advantages", "returns")} | {"st": st})
+
+    orig = NatureCNNAgent.__init__
+
+    def patched(self, envs):
+        orig(self, envs)
+        self.noise_fn = _cpu_noise
+    NatureCNNAgent.__init__ = patched
+    try:
+        def wf(path):
+            w = _Writer(); writers.append(w); return w
+        S.main(argv, writer_factory=wf, on_iteration=on_it)
+    finally:
+        NatureCNNAgent.__init__ = orig
+    return z, snaps, writers[0]
+
+
+def _rel(a, b):
+    return np.abs(a.astype(np.float64) - b.astype(np.float64)).max() / max(1.0, np.abs(b).max())
+
+
+@pytest.mark.parametrize("name", ["ppo_atari_envpool_n8_t32_seed1.npz", "ppo_atari_envpool_n16_t16_seed3_noclipv.npz"])
+@pytest.mark.parametrize("gae_kernel", ["sequential", "scan"])
+def test_script_reproduces_reference_run(lib, name, gae_kernel):
+    z, snaps, w = _run(name, ["--gae-kernel", gae_kernel])
+    n_it = z["actions"].shape[0]
+    assert len(snaps) == n_it
+    TOL = 1e-5
+    upd = 0
+    for it in range(n_it):
+        s = snaps[it]
+        assert np.array_equal(s["actions"], z["actions"][it].astype(np.int64)), f"iteration {it}: actions differ"
+        assert np.array_equal(s["rewards"], z["rewards"][it]) and np.array_equal(s["dones"], z["dones"][it])
+        for k in ("logprobs", "values", "advantages", "returns"):
+            assert _rel(s[k], z[k][it]) <= TOL * (4 if it else 1), (it, k, _rel(s[k], z[k][it]))
+        per = s["st"]["per_update"]
+        for u in range(per.shape[0]):
+            for col, key in ((0, "upd_pg_loss"), (1, "upd_v_loss"), (2, "upd_entropy_loss"), (3, "upd_old_approx_kl"),
+                             (4, "upd_approx_kl"), (5, "upd_clipfrac"), (6, "upd_loss")):
+                ref = float(z[key][upd])
+                assert abs(per[u, col] - ref) <= 3e-5 * max(1.0, abs(ref)), (it, u, key, per[u, col], ref)
+            upd += 1
+    # TensorBoard surface: same tags, same steps, same values
+    ours = {}
+    for tag, v, step in w.scalars:
+        ours.setdefault(tag, []).append((step, v))
+    for key in z.files:
+        if not key.startswith("tb/"):
+            continue
+        tag = key[3:]
+        ref = z[key]
+        assert tag in ours, tag
+        if tag == "charts/SPS":
+            continue
+        got = np.array(ours[tag])
+        assert got.shape == ref.shape, tag
+        assert np.array_equal(got[:, 0], ref[:, 0]), tag
+        if tag.startswith("charts/episodic") or tag.startswith("charts/avg") or tag == "charts/learning_rate":
+            assert np.allclose(got[:, 1], ref[:, 1], rtol=1e-6, atol=0), tag
+        else:
+            assert np.allclose(got[:, 1], ref[:, 1], rtol=2e-4, atol=3e-5), (tag, got[:, 1], ref[:, 1])
