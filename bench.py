@@ -1,0 +1,349 @@
+#!/usr/bin/env python
+"""Headline benchmark: env steps/sec of the PPO hot path (BASELINE.json metric) on N B200s.
+
+    python bench.py --gpus 1 --steps K --warmup W            # our arm (libb200rl kernels)
+    python bench.py --impl reference --gpus N --steps K ...  # reference arm: the reference's CPU path
+    torchrun --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...   (N > 1; one rank per GPU, NCCL)
+
+Workload (config.workload): ppo_atari_envpool at BASELINE.json configs[1] -- per GPU num_envs=1024,
+num_steps=128 (131 072 env steps per iteration), 4 epochs x 4 minibatches of 32 768, NatureCNN,
+Breakout-shaped SYNTHETIC vector env (no envpool/ALE in the image).  A "step" of this benchmark is
+one PPO iteration = rollout (128 policy steps) + bootstrap + GAE + 16 minibatch updates.
+
+  value : whole-job SPS with the observation batches already resident in HBM (no host round trips)
+  e2e   : the same metric through the public loop (PPOEngine as the drop-in scripts drive it) with
+          HOST buffers: every policy step copies the pinned uint8 batch H2D and the actions D2H,
+          rewards/dones go up once per iteration, losses come back once per iteration.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+from pathlib import Path
+from types import SimpleNamespace
+
+import numpy as np
+
+ROOT = Path(__file__).resolve().parent
+sys.path.insert(0, str(ROOT))
+
+METRIC = "env steps/sec (SPS) PPO Breakout num_envs=1024"
+FLOP_PER_ENV_STEP = 243.1e6     # fwd 18.69 MFLOP x [129/128 + 4 epochs x 3]
+HBM_BYTES_PER_ENV_STEP = 169344  # uint8 frame x [1 H2D write + 1 rollout read + 4 epoch reads]
+
+
+def ppo_args(num_envs, num_steps, num_iterations, precision):
+    """Reference defaults of ppo_atari_envpool.py:19-80."""
+    a = SimpleNamespace(
+        seed=1, learning_rate=2.5e-4, num_envs=num_envs, num_steps=num_steps, anneal_lr=True, gamma=0.99,
+        gae_lambda=0.95, num_minibatches=4, update_epochs=4, norm_adv=True, clip_coef=0.1, clip_vloss=True,
+        ent_coef=0.01, vf_coef=0.5, max_grad_norm=0.5, target_kl=None, precision=precision)
+    a.batch_size = num_envs * num_steps
+    a.minibatch_size = a.batch_size // a.num_minibatches
+    a.num_iterations = num_iterations
+    return a
+
+
+class ClockSampler:
+    """nvidia-smi clocks/throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.idx = gpu_index
+        self.proc = None
+        self.lines = []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.idx}", f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "200"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, smmax, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1])); smmax.append(float(f[2]))
+            except ValueError:
+                continue
+            for nm, v in zip(names, f[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(nm)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(smmax) if smmax else None,
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def measured_peaks():
+    p = ROOT / "MEASURED_PEAKS.json"
+    if p.exists():
+        z = json.loads(p.read_text())
+        return z.get("bf16_tflops_sustained", 1400.0), z.get("hbm_gbs", 6650.0), "measured"
+    return 1400.0, 6650.0, "fallback"
+
+
+# --------------------------------------------------------------------------------- our arm
+def run_ours(opt):
+    import torch
+    import torch.distributed as dist
+    from cleanrl_b200 import _lib, build
+    from cleanrl_b200.agents import NatureCNNAgent
+    from cleanrl_b200.ppo_engine import PPOEngine
+    from cleanrl_b200.synthetic_envs import SyntheticAtariVec
+
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if not torch.cuda.is_available():
+        raise RuntimeError("bench.py (impl=ours) needs a CUDA device: the product has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    device = torch.device("cuda", local_rank)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", rank=rank, world_size=world, device_id=device)
+    build.build()
+    lib = _lib.load()
+
+    N, T, K, W = opt.num_envs, opt.num_steps, opt.steps, opt.warmup
+    total_iters = 2 * (K + W) + 4
+    args = ppo_args(N, T, total_iters, opt.precision)
+    seed = args.seed + rank                      # per-rank env / numpy streams (ppo_atari_multigpu.py:208-210)
+    np.random.seed(seed)
+    torch.manual_seed(args.seed)                  # identical initial weights on every rank (:211)
+    envs = SyntheticAtariVec(N, seed=seed, mode="pool", pinned=True)
+    envs.single_observation_space, envs.single_action_space = envs.observation_space, envs.action_space
+    agent = NatureCNNAgent(envs).to(device)
+    agent.precision = opt.precision
+    torch.manual_seed(seed)
+    all_reduce = (lambda t: dist.all_reduce(t, op=dist.ReduceOp.SUM)) if world > 1 else None
+    eng = PPOEngine(agent, args, envs.observation_space.shape, np.uint8, N, device, world_size=world,
+                    gae_mode=1, all_reduce=all_reduce)
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    it_counter = [0]
+
+    def lr_now():
+        it_counter[0] += 1
+        return (1.0 - (it_counter[0] - 1.0) / total_iters) * args.learning_rate
+
+    # ---- e2e: the public loop with host buffers
+    state = {"obs": envs.reset(), "done": np.zeros(N, dtype=np.float32)}
+
+    def iteration_e2e():
+        next_obs, next_done = state["obs"], state["done"]
+        for step in range(T):
+            action = eng.policy_step(step, next_obs, next_done)
+            next_obs, reward, next_done, info = envs.step(action)
+            eng.record_reward(step, reward)
+        eng.finish_rollout(next_obs, next_done)
+        st = eng.update(lr_now())
+        state["obs"], state["done"] = next_obs, next_done
+        return st
+
+    # ---- resident: observation batches, rewards and dones already in HBM
+    pool_dev = torch.from_numpy(envs._batches).to(device)
+    g = torch.Generator(device="cpu").manual_seed(seed)
+    eng_rewards = torch.randint(0, 2, (T, N), generator=g).float().to(device)
+    eng_dones = (torch.rand(T, N, generator=g) < 0.02).float().to(device)
+
+    def iteration_resident():
+        P = pool_dev.shape[0]
+        for step in range(T):
+            eng.policy_step_resident(step, pool_dev[step % P])
+        eng.rewards.copy_(eng_rewards)
+        eng.dones.copy_(eng_dones)
+        eng.next_obs.copy_(pool_dev[T % P])
+        eng.finish_rollout(None, None, resident=True)
+        return eng.update(lr_now())
+
+    def timed(fn, profile=False):
+        for _ in range(W):
+            fn()
+        barrier()
+        sampler = ClockSampler(local_rank)
+        sampler.start()
+        h2d0, d2h0, l0 = eng.h2d_bytes, eng.d2h_bytes, lib.b200rl_launch_count()
+        if profile:
+            lib.b200rl_profile_reset()
+            lib.b200rl_profile_enable(1)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        st = None
+        for _ in range(K):
+            st = fn()
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1)
+        prof = None
+        if profile:
+            lib.b200rl_profile_enable(0)
+            buf = (b"\0" * (1 << 16))
+            import ctypes
+            cbuf = ctypes.create_string_buffer(1 << 16)
+            _lib.check(lib.b200rl_profile_summary(cbuf, 1 << 16), "profile_summary")
+            prof = json.loads(cbuf.value.decode())
+        barrier()
+        clocks = sampler.stop()
+        t = torch.tensor([ms], device=device)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return dict(ms=float(t.item()), h2d=(eng.h2d_bytes - h2d0) / K, d2h=(eng.d2h_bytes - d2h0) / K,
+                    launches=lib.b200rl_launch_count() - l0, clocks=clocks, stats=st, prof=prof)
+
+    res = timed(iteration_resident, profile=True)
+    e2e = timed(iteration_e2e)
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+    steps_total = N * T * world
+    sps = steps_total * K / (res["ms"] * 1e-3)
+    sps_e2e = steps_total * K / (e2e["ms"] * 1e-3)
+    peak_tf, peak_hbm, which = measured_peaks()
+    # dominant kernel family by device time inside the timed region
+    prof = sorted(res["prof"], key=lambda r: -r["ms"])
+    tot_ms = sum(r["ms"] for r in prof) or 1.0
+    top = next((r for r in prof if r["flops"] > 0), prof[0])
+    ach = top["flops"] / (top["ms"] * 1e-3) / 1e12 if top["ms"] > 0 else 0.0
+    roofline = {
+        "bound": "tensor", "kernel": top["name"], "achieved": round(ach, 2), "peak": peak_tf, "unit": "TFLOP/s",
+        "frac": round(ach / peak_tf, 4), "traffic": None, "peak_source": f"{which} bf16_tflops_sustained",
+        "share_of_kernel_time": round(top["ms"] / tot_ms, 4), "launches": top["launches"],
+        "avg_launch_us": round(1e3 * top["ms"] / max(top["launches"], 1), 2),
+        "job_tensor_frac": round(sps / world * FLOP_PER_ENV_STEP / (peak_tf * 1e12), 4),
+        "job_hbm_frac": round(sps / world * HBM_BYTES_PER_ENV_STEP / (peak_hbm * 1e9), 4),
+        "kernels": [{"name": r["name"], "ms_per_step": round(r["ms"] / K, 4), "launches_per_step": r["launches"] // K,
+                     "tflops": round(r["flops"] / (r["ms"] * 1e-3) / 1e12, 2) if r["ms"] > 0 and r["flops"] > 0 else None,
+                     "gbs": round(r["bytes"] / (r["ms"] * 1e-3) / 1e9, 1) if r["ms"] > 0 and r["bytes"] > 0 else None}
+                    for r in prof],
+    }
+    out = {
+        "metric": METRIC, "value": round(sps, 1), "unit": "env_steps/s", "n_gpus": world, "steps": K, "warmup": W,
+        "ms_per_step": round(res["ms"] / K, 3), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": opt.precision, "data": "synthetic",
+        "config": {"workload": "ppo_atari_envpool Breakout-shaped synthetic vec env; per GPU num_envs=%d num_steps=%d, "
+                               "4 epochs x 4 minibatches, NatureCNN A=4; one step = one PPO iteration" % (N, T),
+                   "global_num_envs": N * world, "parallelism": f"dp{world}", "timing": "inputs_larger_than_L2 "
+                   "(3.7 GB uint8 rollout + 2.8 GB activations per minibatch vs 126 MB L2)",
+                   "gae_kernel": "scan"},
+        "clocks": res["clocks"],
+        "e2e": {"value": round(sps_e2e, 1), "unit": "env_steps/s", "ms_per_step": round(e2e["ms"] / K, 3),
+                "h2d_bytes_per_step": int(e2e["h2d"]), "d2h_bytes_per_step": int(e2e["d2h"]), "clocks": e2e["clocks"]},
+        "gpu_launches": int(res["launches"]),
+        "roofline": roofline,
+        "losses_last": {k: (float(v) if isinstance(v, (int, float)) else None) for k, v in (e2e["stats"] or {}).items()
+                        if k in ("pg_loss", "v_loss", "entropy", "approx_kl")},
+    }
+    if world == 1 and not opt.no_cpu_baseline:
+        out["cpu_baseline"] = cpu_baseline(opt)
+    print(json.dumps(out))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+# ---------------------------------------------------------------------- reference / cpu legs
+def cpu_sample(num_envs, sample_steps, iters, threads):
+    from oracle import ppo_port
+    r = ppo_port.run(num_envs=num_envs, num_steps=sample_steps, num_iterations=iters, total_iterations=1000,
+                     seed=1, env_mode="pool", threads=threads)
+    return r
+
+
+def cpu_baseline(opt):
+    """Oracle port (oracle/ppo_port.py: the reference's torch-CPU loop restated) on the host cores, on a
+    bounded sample: same per-env-step work (1 rollout forward + 4 epochs fwd/bwd per sample), fewer
+    policy steps per iteration."""
+    import torch
+    cores = os.cpu_count() or 1
+    threads = min(cores, 64)
+    t_s = opt.cpu_sample_steps
+    r = cpu_sample(opt.num_envs, t_s, 1, threads)
+    sps = r["env_steps"] / r["seconds"]
+    return {"value": round(sps, 1), "unit": "env_steps/s", "cores": threads, "kind": "port",
+            "sample": f"1 PPO iteration at num_envs={opt.num_envs}, num_steps={t_s} (instead of {opt.num_steps}): "
+                      f"{r['env_steps']} env steps in {r['seconds']:.1f} s, torch {torch.__version__} CPU, "
+                      f"{threads} threads of {cores} host cores"}
+
+
+def run_reference(opt):
+    """--impl reference: the reference's own CPU implementation of the path (torch CPU loop, all host
+    threads it can use) -- here the oracle port, because /root/reference does not exist on the GPU box."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    import torch
+    cores = os.cpu_count() or 1
+    threads = min(cores, 64)
+    K, W, t_s = opt.steps, opt.warmup, opt.cpu_sample_steps
+    W = min(W, 1)
+    r = cpu_sample(opt.num_envs, t_s, W + K, threads)
+    secs = sum(r["iter_seconds"][W:])
+    steps = opt.num_envs * t_s * K
+    sps = steps / secs
+    line = {
+        "impl": "reference", "metric": METRIC, "value": round(sps, 1), "unit": "env_steps/s", "n_gpus": opt.gpus,
+        "steps": K, "warmup": W, "ms_per_step": round(1e3 * secs / K, 1), "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": "ppo_atari_envpool Breakout-shaped synthetic vec env; num_envs=%d, NatureCNN A=4; "
+                               "each step = one PPO iteration on a bounded sample (num_steps=%d instead of %d)"
+                               % (opt.num_envs, t_s, opt.num_steps)},
+        "cpu_baseline": {"value": round(sps, 1), "unit": "env_steps/s", "cores": threads, "kind": "port",
+                         "sample": f"{K} iterations x num_envs={opt.num_envs} x num_steps={t_s}, torch {torch.__version__} "
+                                   f"CPU, {threads} threads of {cores} host cores"},
+        "e2e": {"value": round(sps, 1), "unit": "env_steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", choices=["ours", "reference"], default="ours")
+    ap.add_argument("--num-envs", type=int, default=1024)
+    ap.add_argument("--num-steps", type=int, default=128)
+    ap.add_argument("--precision", choices=["bf16", "fp32"], default="bf16")
+    ap.add_argument("--cpu-sample-steps", type=int, default=4)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    opt = ap.parse_args()
+    if opt.impl == "reference":
+        run_reference(opt)
+    else:
+        run_ours(opt)
+
+
+if __name__ == "__main__":
+    main()

@@ -22,6 +22,10 @@ SIGNATURES = {
     "b200rl_version": (_i, []),
     "b200rl_last_error": (C.c_char_p, []),
     "b200rl_compiled_arch": (_i, []),
+    "b200rl_launch_count": (C.c_longlong, []),
+    "b200rl_profile_enable": (None, [_i]),
+    "b200rl_profile_reset": (None, []),
+    "b200rl_profile_summary": (_i, [C.c_char_p, _sz]),
     "b200rl_gae_f32": (_i, [_p, _p, _p, _p, _p, _p, _p, _i64, _i64, _d, _d, _i, _p]),
     "b200rl_categorical_sample_f32": (_i, [_p, _i64, _p, _p, _i64, _i64, _i, _p, _p, _p, _p, _p]),
     "b200rl_categorical_eval_f32": (_i, [_p, _i64, _p, _i64, _i, _p, _p, _p]),
@@ -38,6 +42,13 @@ SIGNATURES = {
     "b200rl_linear_bwd_data_f32": (_i, [_p, _p, _p, _i, _p, _i64, _i, _i, _p]),
     "b200rl_linear_bwd_weight_workspace_bytes": (_sz, [_i64, _i, _i]),
     "b200rl_linear_bwd_weight_f32": (_i, [_p, _p, _p, _p, _p, _i64, _i, _i, _p, _sz, _p]),
+    "b200rl_naturecnn_param_count": (_i64, [_i]),
+    "b200rl_naturecnn_bf16_packed_bytes": (_sz, [_i]),
+    "b200rl_naturecnn_bf16_acts_bytes": (_sz, [_i64]),
+    "b200rl_naturecnn_bf16_workspace_bytes": (_sz, [_i64, _i]),
+    "b200rl_naturecnn_bf16_pack": (_i, [_p, _i, _p, _p]),
+    "b200rl_naturecnn_bf16_forward": (_i, [_p, _p, _i64, _i, _p, _p, _p, _p, _p]),
+    "b200rl_naturecnn_bf16_backward": (_i, [_p, _p, _i64, _i, _p, _p, _p, _p, _p, _p, _sz, _p]),
 }
 
 _lib = None

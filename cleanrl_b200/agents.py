@@ -129,8 +129,41 @@ class NatureCNNAgent(KernelAgent):
             nets.Conv(n[0], "relu", in_div=255.0), nets.Conv(n[2], "relu"), nets.Conv(n[4], "relu"),
             nets.Linear(n[7], "relu")])
         self.head = nets.Linear(None, None, self._head_w, self._head_b, self._head_dw, self._head_db)
+        self._tc = None
+        self._tc_dirty = True
+
+    # -- bf16 tensor-core plan ("--precision bf16") ------------------------------
+    precision = "fp32"
+
+    def params_updated(self):
+        """Call after the optimiser changed the flat parameters: the packed bf16 operands are stale."""
+        self._tc_dirty = True
+
+    def _tc_plan(self):
+        f = self._flat
+        if self._tc is None:
+            assert f.flat.numel() >= ops._lib.load().b200rl_naturecnn_param_count(self.num_actions)
+            self._tc = ops.NatureCNNBf16(self.num_actions, f.flat.device)
+        if self._tc_dirty:
+            self._tc.pack(f.flat)
+            self._tc_dirty = False
+        return self._tc
+
+    def load_state_dict(self, *a, **k):
+        out = super().load_state_dict(*a, **k)
+        self._tc_dirty = True
+        return out
 
     def _forward_heads(self, x, rows=None, keep=False):
+        if self.precision == "bf16":
+            if x.dtype != torch.uint8:
+                x = x.to(torch.uint8)       # frames are integers 0..255 (reference passes them as fp32)
+            tc = self._tc_plan()
+            out = tc.forward(x.contiguous(), rows, self._flat.flat)
+            if keep:
+                self._tc_obs, self._tc_rows = x, rows
+            A = self.num_actions
+            return out[:, :A], out[:, A]
         if x.dtype not in (torch.uint8, torch.float32):
             x = x.float()
         hidden = self.trunk.fwd(x.contiguous(), rows=rows, keep=keep)
@@ -152,6 +185,10 @@ class NatureCNNAgent(KernelAgent):
 
     def backward(self, dhead):
         """dhead [M, A+1] = [dlogits | dvalue]; fills the flat gradient buffer."""
+        if self.precision == "bf16":
+            self._tc.backward(self._tc_obs, self._tc_rows, self._flat.flat, dhead, self._flat.grad)
+            self._tc_obs = self._tc_rows = None
+            return
         hidden = self._hidden
         self.head.bwd_weight(hidden, dhead)
         dh = self.head.bwd_data(dhead, hidden, "relu")

@@ -12,7 +12,9 @@ namespace b200rl {
 char* err_buf();
 int fail(int code, const char* fmt, ...);
 
-inline int check_launch(const char* what) {
+void note_launches(int n);
+inline int check_launch(const char* what, int kernels = 1) {
+    note_launches(kernels);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return fail(B200RL_ERR_CUDA, "%s: %s", what, cudaGetErrorString(e));
     return B200RL_OK;
@@ -23,6 +25,18 @@ inline int check_launch(const char* what) {
 
 inline bool aligned(const void* p, size_t a) { return (reinterpret_cast<uintptr_t>(p) % a) == 0; }
 inline int64_t ceil_div(int64_t a, int64_t b) { return (a + b - 1) / b; }
+
+// ---- optional per-kernel timing (b200rl_profile_*): CUDA events on the launching stream
+bool prof_enabled();
+void prof_begin(cudaStream_t s, const char* name, double flops, double bytes);
+void prof_end(cudaStream_t s);
+struct ProfScope {
+    cudaStream_t s; bool on;
+    ProfScope(cudaStream_t s_, const char* name, double flops, double bytes) : s(s_), on(prof_enabled()) {
+        if (on) prof_begin(s, name, flops, bytes);
+    }
+    ~ProfScope() { if (on) prof_end(s); }
+};
 
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll

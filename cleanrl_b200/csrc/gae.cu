@@ -137,6 +137,7 @@ extern "C" int b200rl_gae_f32(const float* rewards, const float* values, const f
     const float g = (float)gamma;
     const float gl = (float)(gamma * gae_lambda);  // double product rounded once (ppo.py:230)
     cudaStream_t s = (cudaStream_t)stream;
+    ProfScope ps(s, mode == 0 ? "gae_seq" : "gae_scan", 0, 20.0 * T * N + 8.0 * N);
     if (mode == 0) {
         const int threads = (N >= 148 * 64) ? 64 : 32;
         const unsigned blocks = (unsigned)ceil_div(N, threads);

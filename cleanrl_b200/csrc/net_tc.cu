@@ -1,0 +1,921 @@
+// NatureCNN on the 5th-gen tensor cores (tcgen05.mma, accumulators in TMEM), bf16 operands,
+// fp32 accumulation.  Reference network: cleanrl/ppo_atari_envpool.py:123-139.
+//
+// Every layer -- forward, data-gradient and weight-gradient -- is an implicit GEMM whose A operand
+// is GATHERED by the CTA's threads straight from the NHWC bf16 activations (or, for conv1, from the
+// stacked-frame uint8 observations, converted to bf16 on the fly: 0..255 is exact in bf16; the /255
+// of ppo_atari_envpool.py:144 is applied to the fp32 accumulator in the epilogue) into the UMMA
+// canonical SWIZZLE_128B shared-memory image.  No im2col matrix, no gathered minibatch copy and no
+// fp32 observation tensor ever exists in HBM (the reference materialises a 3.7 GB fp32 gather per
+// minibatch, ppo.py:250).
+//
+// Data layout in HBM
+//   obs          uint8 [B, 4, 84, 84]   (as envpool delivers it; rows selected through mb_inds)
+//   act1/2/3     bf16  [n, 20,20,32] / [n, 9,9,64] / [n, 7,7,64]   NHWC == row-major [pixels, C]
+//   hidden       bf16  [n, 512]
+//   packed weights bf16 [N, K] K-contiguous, K ordered (ky,kx,c) to match NHWC patches
+//                (conv1: (c,ky,kx) to match the NCHW uint8 frames); transposed copies for dgrad.
+//
+// Kernel 1 (tc_gemm_kmajor): D[128 x BN] = sum_chunks A_chunk[128 x 64] * W_chunk[BN x 64]^T
+//   128 threads stage chunk j+1 while the single-thread-issued MMAs of chunk j run asynchronously;
+//   a tcgen05.commit on an mbarrier frees a stage.  Epilogue: tcgen05.ld, bias/ReLU/(ReLU-mask),
+//   bf16 NHWC store.
+// Kernel 2 (tc_wgrad): dW^T[k, co] = sum_m X[m, k] * dY[m, co]; both operands are read as
+//   MN-major views of the very same row images (rows = reduction index m).
+#include "common.cuh"
+#include "tc_common.cuh"
+
+namespace b200rl {
+using namespace tc;
+typedef __nv_bfloat16 bf16;
+
+constexpr int kMaxChunks = 64;
+
+struct KGemmParams {
+    // ---- A operand (gathered rows)
+    const void* A;
+    const int64_t* rows;   // conv1 only: observation row gather (minibatch indices), may be null
+    int64_t M;             // valid GEMM rows per class
+    int rpi, Ws;           // rows per image and row-grid width: row -> (img, y, x)
+    int SH, SW, CP;        // source pixel grid and channels per pixel (bf16 elements)
+    int sy, sx;            // row-grid -> source-grid stride
+    int nchunks, check;    // K = 64*nchunks; check = bounds-test taps (zero fill outside)
+    signed char dy[kMaxChunks], dx[kMaxChunks];
+    int nclasses;          // 1, or 4 stride-parity classes (conv2 data-gradient)
+    int tiles_per_class;
+    // ---- B operand: packed weights [N, 64*nchunks] (+ class stride)
+    const bf16* Bw;
+    int N;
+    int64_t b_class_stride;
+    // ---- epilogue
+    bf16* out;
+    int OH, OW, osy, osx, ldo;
+    const float* bias;
+    float scale;
+    int relu;
+    const bf16* mask;      // same layout as out: multiply by (mask > 0)
+};
+
+__device__ __forceinline__ int4 ldg16(const void* p) { return __ldg(reinterpret_cast<const int4*>(p)); }
+
+// ------------------------------------------------------------------ kernel 1
+template <int BN, int STAGES, bool A_U8>
+__global__ void __launch_bounds__(128) tc_gemm_kmajor(const KGemmParams p) {
+    constexpr int A_BYTES = 128 * 128;
+    constexpr int B_BYTES = BN * 128;
+    constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+    constexpr uint32_t TMEM_COLS = BN < 32 ? 32 : BN;
+    extern __shared__ uint8_t smem_raw[];
+    __shared__ uint64_t empty_bar[STAGES];
+    __shared__ uint32_t tmem_base_smem;
+
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    const int tid = threadIdx.x, warp = tid >> 5;
+    const int cls = blockIdx.x / p.tiles_per_class;
+    const int64_t row0 = (int64_t)(blockIdx.x - cls * p.tiles_per_class) * 128;
+    const int n0 = blockIdx.y * BN;
+    const bf16* Bw = p.Bw + (int64_t)cls * p.b_class_stride;
+    const int K = p.nchunks * 64;
+
+    if (tid == 0) {
+        for (int s = 0; s < STAGES; ++s) mbar_init(&empty_bar[s], 1);
+        fence_barrier_init();
+    }
+    if (warp == 0) tmem_alloc(&tmem_base_smem, TMEM_COLS);
+    tc_fence_before_sync();
+    __syncthreads();
+    tc_fence_after_sync();
+    const uint32_t tmem_d = tmem_base_smem;
+
+    // ---- per-thread row contexts (fixed for the whole K loop)
+    // generic loader: 8 threads per row (one 16-B chunk each), rows tid/8 + 16*pass
+    // uint8 loader : one thread per row
+    int64_t boff[8];
+    int pos[8];   // (ys << 16) | xs, or -1 when the row is out of range
+    const uint8_t* u8base = nullptr;
+    if (A_U8) {
+        const int64_t r = row0 + tid;
+        if (r < p.M) {
+            const int64_t i = r / p.rpi;
+            const int rem = (int)(r - i * p.rpi);
+            const int oy = rem / p.Ws, ox = rem - oy * p.Ws;
+            const int64_t img = p.rows ? p.rows[i] : i;
+            u8base = reinterpret_cast<const uint8_t*>(p.A) + img * (int64_t)(p.CP * p.SH * p.SW) +
+                     (int64_t)(oy * p.sy) * p.SW + ox * p.sx;
+        }
+    } else {
+#pragma unroll
+        for (int ps = 0; ps < 8; ++ps) {
+            const int64_t r = row0 + ps * 16 + (tid >> 3);
+            if (r < p.M) {
+                const int64_t i = r / p.rpi;
+                const int rem = (int)(r - i * p.rpi);
+                const int y = rem / p.Ws, x = rem - y * p.Ws;
+                const int ys = y * p.sy, xs = x * p.sx;
+                boff[ps] = ((i * p.SH + ys) * p.SW + xs) * (int64_t)p.CP;
+                pos[ps] = (ys << 16) | xs;
+            } else {
+                boff[ps] = 0;
+                pos[ps] = -1;
+            }
+        }
+    }
+    const int ppc = 64 / p.CP;   // source pixels covered by one 64-element chunk
+    constexpr uint32_t idesc = make_idesc(128, BN, 0, 0);
+
+    for (int j = 0; j < p.nchunks; ++j) {
+        const int s = j % STAGES;
+        const int use = j / STAGES;
+        if (use > 0) mbar_wait(&empty_bar[s], (use - 1) & 1);   // MMAs that read this stage are done
+        uint8_t* sA = smem + s * STAGE_BYTES;
+        uint8_t* sB = sA + A_BYTES;
+        // ---- stage A chunk j
+        if (A_U8) {
+            // chunk j = input channel j: 8 (ky) x 8 (kx) bytes -> 8 x 16-byte bf16 chunks of this thread's row
+            const uint8_t* src = u8base ? u8base + (int64_t)j * p.SH * p.SW : nullptr;
+#pragma unroll
+            for (int ky = 0; ky < 8; ++ky) {
+                uint32_t w0 = 0, w1 = 0;
+                if (src) {
+                    const uint32_t* q = reinterpret_cast<const uint32_t*>(src + ky * p.SW);
+                    w0 = __ldg(q);
+                    w1 = __ldg(q + 1);
+                }
+                int4 v;
+                v.x = (int)pack_bf16x2((float)(w0 & 0xFF), (float)((w0 >> 8) & 0xFF));
+                v.y = (int)pack_bf16x2((float)((w0 >> 16) & 0xFF), (float)(w0 >> 24));
+                v.z = (int)pack_bf16x2((float)(w1 & 0xFF), (float)((w1 >> 8) & 0xFF));
+                v.w = (int)pack_bf16x2((float)((w1 >> 16) & 0xFF), (float)(w1 >> 24));
+                *reinterpret_cast<int4*>(sA + img_off(tid, ky)) = v;
+            }
+        } else {
+            const int dyj = p.dy[j], dxj = p.dx[j];
+            const int64_t doff = ((int64_t)dyj * p.SW + dxj) * p.CP + (tid & 7) * 8;
+#pragma unroll
+            for (int ps = 0; ps < 8; ++ps) {
+                int4 v = make_int4(0, 0, 0, 0);
+                bool ok = pos[ps] >= 0;
+                if (ok && p.check) {
+                    const int yy = (pos[ps] >> 16) + dyj, xx = (pos[ps] & 0xFFFF) + dxj;
+                    ok = (yy >= 0) && (yy < p.SH) && (xx >= 0) && (xx + ppc <= p.SW);
+                }
+                if (ok) v = ldg16(reinterpret_cast<const bf16*>(p.A) + boff[ps] + doff);
+                *reinterpret_cast<int4*>(sA + img_off(ps * 16 + (tid >> 3), tid & 7)) = v;
+            }
+        }
+        // ---- stage B chunk j: BN weight rows x 128 B
+#pragma unroll
+        for (int ps = 0; ps < BN / 16; ++ps) {
+            const int r = ps * 16 + (tid >> 3);
+            int4 v = make_int4(0, 0, 0, 0);
+            if (n0 + r < p.N) v = ldg16(Bw + (int64_t)(n0 + r) * K + j * 64 + (tid & 7) * 8);
+            *reinterpret_cast<int4*>(sB + img_off(r, tid & 7)) = v;
+        }
+        fence_proxy_async_smem();
+        __syncthreads();
+        if (tid == 0) {
+            tc_fence_after_sync();
+            const uint64_t adesc = desc_kmajor(smem_u32(sA));
+            const uint64_t bdesc = desc_kmajor(smem_u32(sB));
+#pragma unroll
+            for (int kk = 0; kk < 4; ++kk)   // 4 x (K = 16) per 64-wide chunk: +32 B inside the swizzle row
+                umma_bf16(tmem_d, adesc + 2 * kk, bdesc + 2 * kk, idesc, (j | kk) != 0);
+            umma_commit(&empty_bar[s]);
+        }
+    }
+    // ---- wait for the last chunk's MMAs (commit covers all earlier ones)
+    {
+        const int jl = p.nchunks - 1;
+        mbar_wait(&empty_bar[jl % STAGES], (jl / STAGES) & 1);
+        tc_fence_after_sync();
+    }
+    // ---- epilogue: thread <-> accumulator row (TMEM lane), 16 columns at a time
+    const int64_t r = row0 + tid;
+    int64_t ooff = 0;
+    bool rvalid = r < p.M;
+    if (rvalid) {
+        const int64_t i = r / p.rpi;
+        const int rem = (int)(r - i * p.rpi);
+        const int y = rem / p.Ws, x = rem - y * p.Ws;
+        const int ooy = p.nclasses > 1 ? (cls >> 1) : 0, oox = p.nclasses > 1 ? (cls & 1) : 0;
+        ooff = ((i * p.OH + y * p.osy + ooy) * p.OW + x * p.osx + oox) * (int64_t)p.ldo;
+    }
+    const uint32_t lane_addr = tmem_d + ((uint32_t)(warp * 32) << 16);
+#pragma unroll 1
+    for (int c0 = 0; c0 < BN; c0 += 16) {
+        uint32_t v[16];
+        tmem_ld16(lane_addr + c0, v);
+        tmem_ld_wait();
+        const int col = n0 + c0;
+        if (!rvalid || col >= p.N) continue;
+        float f[16];
+#pragma unroll
+        for (int e = 0; e < 16; ++e) {
+            f[e] = __uint_as_float(v[e]) * p.scale;
+            if (p.bias) f[e] += __ldg(p.bias + col + e);
+            if (p.relu) f[e] = fmaxf(f[e], 0.f);
+        }
+        if (p.mask) {
+            const int4 m0 = ldg16(p.mask + ooff + col);
+            const int4 m1 = ldg16(p.mask + ooff + col + 8);
+            const uint32_t mw[8] = {(uint32_t)m0.x, (uint32_t)m0.y, (uint32_t)m0.z, (uint32_t)m0.w,
+                                    (uint32_t)m1.x, (uint32_t)m1.y, (uint32_t)m1.z, (uint32_t)m1.w};
+#pragma unroll
+            for (int e = 0; e < 8; ++e) {
+                // post-ReLU activations are >= 0: "> 0" <=> any non-sign bit set
+                if ((mw[e] & 0x7FFFu) == 0u) f[2 * e] = 0.f;
+                if ((mw[e] & 0x7FFF0000u) == 0u) f[2 * e + 1] = 0.f;
+            }
+        }
+        int4 o0, o1;
+        o0.x = (int)pack_bf16x2(f[0], f[1]);   o0.y = (int)pack_bf16x2(f[2], f[3]);
+        o0.z = (int)pack_bf16x2(f[4], f[5]);   o0.w = (int)pack_bf16x2(f[6], f[7]);
+        o1.x = (int)pack_bf16x2(f[8], f[9]);   o1.y = (int)pack_bf16x2(f[10], f[11]);
+        o1.z = (int)pack_bf16x2(f[12], f[13]); o1.w = (int)pack_bf16x2(f[14], f[15]);
+        int4* dst = reinterpret_cast<int4*>(p.out + ooff + col);
+        dst[0] = o0;
+        dst[1] = o1;
+    }
+    tc_fence_before_sync();
+    __syncthreads();
+    if (warp == 0) tmem_dealloc(tmem_d, TMEM_COLS);
+}
+
+template <int BN, int STAGES, bool A_U8>
+static int launch_kgemm(const KGemmParams& p, cudaStream_t s, const char* what) {
+    const size_t smem = (size_t)STAGES * (128 * 128 + BN * 128) + 1024;
+    static bool attr_done = false;
+    if (!attr_done) {
+        cudaError_t e = cudaFuncSetAttribute(tc_gemm_kmajor<BN, STAGES, A_U8>,
+                                             cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return fail(B200RL_ERR_CUDA, "%s: smem attribute: %s", what, cudaGetErrorString(e));
+        attr_done = true;
+    }
+    dim3 grid((unsigned)(p.tiles_per_class * p.nclasses), (unsigned)ceil_div(p.N, BN));
+    tc_gemm_kmajor<BN, STAGES, A_U8><<<grid, 128, smem, s>>>(p);
+    return check_launch(what);
+}
+
+// ------------------------------------------------------------------ kernel 2: weight gradient
+// D[kidx, co] = sum_m X[m, kidx] * dY[m, co].  X-side: nxc chunk images (64 kidx each); Y-side: nyc chunk
+// images (64 co each).  Each CTA owns the row range [m_begin, m_end) and ALL (X-tile, Y) outputs:
+// TMEM columns = (nxc/2) * 64*nyc.  Partials are written fp32 to ws[split][nxc*64][nyc*64].
+struct WGradParams {
+    KGemmParams x;          // gather description of the X side (A/rows/M/rpi/Ws/SH/SW/CP/sy/sx/nchunks/check/dy/dx)
+    const bf16* Y;          // dY rows [M, ldy] bf16 (NHWC rows == GEMM rows)
+    int ldy;                // elements per dY row
+    int nyc;                // Y chunks (64 columns each)
+    int ncolsY;             // valid dY columns
+    int nxc;                // X chunks per CTA (even; blockIdx.y selects the group; zero-padded beyond x.nchunks)
+    int64_t rows_per_cta;   // multiple of 32
+    float* ws;              // [gridDim.x][gridDim.y*nxc*64][gridDim.z*nyc*64] fp32
+};
+
+template <bool A_U8>
+__global__ void __launch_bounds__(128) tc_wgrad(const WGradParams p) {
+    constexpr int R = 32;            // reduction rows per stage (2 MMAs of K = 16)
+    constexpr int STAGES = 3;
+    extern __shared__ uint8_t smem_raw[];
+    __shared__ uint64_t empty_bar[STAGES];
+    __shared__ uint32_t tmem_base_smem;
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    const int tid = threadIdx.x, warp = tid >> 5;
+    const KGemmParams& g = p.x;
+    const int nxc = p.nxc, nyc = p.nyc;
+    const int NY = nyc * 64;
+    const int xc0 = blockIdx.y * nxc;            // first X chunk of this CTA
+    const int yc0 = blockIdx.z * nyc;            // first Y chunk of this CTA
+    const int xt = nxc / 2;                      // 128-row output tiles
+    const int chunk_img = R * 128;               // bytes of one chunk image (R rows)
+    const int stage_bytes = (nxc + nyc) * chunk_img;
+    uint32_t tmem_cols = 32;
+    while ((int)tmem_cols < xt * NY) tmem_cols <<= 1;
+
+    if (tid == 0) {
+        for (int s = 0; s < STAGES; ++s) mbar_init(&empty_bar[s], 1);
+        fence_barrier_init();
+    }
+    if (warp == 0) tmem_alloc(&tmem_base_smem, tmem_cols);
+    tc_fence_before_sync();
+    __syncthreads();
+    tc_fence_after_sync();
+    const uint32_t tmem_d = tmem_base_smem;
+
+    const int64_t m_begin = (int64_t)blockIdx.x * p.rows_per_cta;
+    int64_t m_end = m_begin + p.rows_per_cta;
+    if (m_end > g.M) m_end = g.M;
+    const int ppc = 64 / (A_U8 ? 64 : g.CP);
+    const uint32_t idesc = make_idesc(128, NY, 1, 1);
+    int it = 0;
+    for (int64_t m0 = m_begin; m0 < m_end; m0 += R, ++it) {
+        const int s = it % STAGES, use = it / STAGES;
+        if (use > 0) mbar_wait(&empty_bar[s], (use - 1) & 1);
+        uint8_t* sX = smem + s * stage_bytes;
+        uint8_t* sY = sX + nxc * chunk_img;
+        // ---- X side: R rows x nxc chunks
+        if (A_U8) {
+            // thread -> (row = tid & 31, ky pair = tid >> 5): each thread converts 2 ky rows of every channel chunk
+            const int rr = tid & 31;
+            const int64_t r = m0 + rr;
+            const uint8_t* base = nullptr;
+            if (r < m_end) {
+                const int64_t i = r / g.rpi;
+                const int rem = (int)(r - i * g.rpi);
+                const int oy = rem / g.Ws, ox = rem - oy * g.Ws;
+                const int64_t img = g.rows ? g.rows[i] : i;
+                base = reinterpret_cast<const uint8_t*>(g.A) + img * (int64_t)(g.CP * g.SH * g.SW) +
+                       (int64_t)(oy * g.sy) * g.SW + ox * g.sx;
+            }
+            for (int c = 0; c < nxc; ++c) {
+                const int ch = xc0 + c;
+#pragma unroll
+                for (int q = 0; q < 2; ++q) {
+                    const int ky = (tid >> 5) * 2 + q;
+                    uint32_t w0 = 0, w1 = 0;
+                    if (base && ch < g.nchunks) {
+                        const uint32_t* src = reinterpret_cast<const uint32_t*>(base + (int64_t)ch * g.SH * g.SW + ky * g.SW);
+                        w0 = __ldg(src);
+                        w1 = __ldg(src + 1);
+                    }
+                    int4 v;
+                    v.x = (int)pack_bf16x2((float)(w0 & 0xFF), (float)((w0 >> 8) & 0xFF));
+                    v.y = (int)pack_bf16x2((float)((w0 >> 16) & 0xFF), (float)(w0 >> 24));
+                    v.z = (int)pack_bf16x2((float)(w1 & 0xFF), (float)((w1 >> 8) & 0xFF));
+                    v.w = (int)pack_bf16x2((float)((w1 >> 16) & 0xFF), (float)(w1 >> 24));
+                    *reinterpret_cast<int4*>(sX + c * chunk_img + img_off(rr, ky)) = v;
+                }
+            }
+        } else {
+            // 8 threads per row, 16 rows per pass, 2 passes for R = 32
+#pragma unroll
+            for (int ps = 0; ps < R / 16; ++ps) {
+                const int rr = ps * 16 + (tid >> 3);
+                const int64_t r = m0 + rr;
+                bool rok = r < m_end;
+                int64_t bo = 0;
+                int ys = 0, xs = 0;
+                if (rok) {
+                    const int64_t i = r / g.rpi;
+                    const int rem = (int)(r - i * g.rpi);
+                    const int y = rem / g.Ws, x = rem - y * g.Ws;
+                    ys = y * g.sy; xs = x * g.sx;
+                    bo = ((i * g.SH + ys) * g.SW + xs) * (int64_t)g.CP;
+                }
+                for (int c = 0; c < nxc; ++c) {
+                    const int ch = xc0 + c;
+                    int4 v = make_int4(0, 0, 0, 0);
+                    bool ok = rok && ch < g.nchunks;
+                    if (ok) {
+                        const int dyj = g.dy[ch], dxj = g.dx[ch];
+                        if (g.check) {
+                            const int yy = ys + dyj, xx = xs + dxj;
+                            ok = (yy >= 0) && (yy < g.SH) && (xx >= 0) && (xx + ppc <= g.SW);
+                        }
+                        if (ok) v = ldg16(reinterpret_cast<const bf16*>(g.A) + bo + ((int64_t)dyj * g.SW + dxj) * g.CP + (tid & 7) * 8);
+                    }
+                    *reinterpret_cast<int4*>(sX + c * chunk_img + img_off(rr, tid & 7)) = v;
+                }
+            }
+        }
+        // ---- Y side: R rows x nyc chunks of dY
+#pragma unroll
+        for (int ps = 0; ps < R / 16; ++ps) {
+            const int rr = ps * 16 + (tid >> 3);
+            const int64_t r = m0 + rr;
+            for (int c = 0; c < nyc; ++c) {
+                int4 v = make_int4(0, 0, 0, 0);
+                const int col = (yc0 + c) * 64 + (tid & 7) * 8;
+                if (r < m_end && col < p.ncolsY) v = ldg16(p.Y + r * (int64_t)p.ldy + col);
+                *reinterpret_cast<int4*>(sY + c * chunk_img + img_off(rr, tid & 7)) = v;
+            }
+        }
+        fence_proxy_async_smem();
+        __syncthreads();
+        if (tid == 0) {
+            tc_fence_after_sync();
+            const uint32_t xa = smem_u32(sX), ya = smem_u32(sY);
+            for (int t = 0; t < xt; ++t) {
+#pragma unroll
+                for (int kk = 0; kk < R / 16; ++kk) {
+                    // A: 128 kidx = chunks 2t, 2t+1 (LBO = chunk image), K rows 16kk..16kk+15 (2 atoms, SBO 1024)
+                    const uint64_t adesc = desc_mnmajor(xa + (2 * t) * chunk_img + kk * 2048, chunk_img);
+                    const uint64_t bdesc = desc_mnmajor(ya + kk * 2048, chunk_img);
+                    umma_bf16(tmem_d + t * NY, adesc, bdesc, idesc, (it | kk) != 0);
+                }
+            }
+            umma_commit(&empty_bar[s]);
+        }
+    }
+    if (it > 0) {
+        const int il = it - 1;
+        mbar_wait(&empty_bar[il % STAGES], (il / STAGES) & 1);
+        tc_fence_after_sync();
+    }
+    // ---- epilogue: fp32 partials ws[cta][kidx][co]
+    const int64_t KXtot = (int64_t)gridDim.y * nxc * 64, NYtot = (int64_t)gridDim.z * NY;
+    float* wsb = p.ws + (int64_t)blockIdx.x * KXtot * NYtot;
+    const uint32_t lane_addr = tmem_d + ((uint32_t)(warp * 32) << 16);
+    for (int t = 0; t < xt; ++t) {
+        float* dst = wsb + ((int64_t)xc0 * 64 + t * 128 + tid) * NYtot + (int64_t)yc0 * 64;
+        for (int c0 = 0; c0 < NY; c0 += 16) {
+            uint32_t v[16];
+            if (it > 0) {
+                tmem_ld16(lane_addr + t * NY + c0, v);
+                tmem_ld_wait();
+            } else {
+#pragma unroll
+                for (int e = 0; e < 16; ++e) v[e] = 0u;
+            }
+#pragma unroll
+            for (int e = 0; e < 16; e += 4)
+                *reinterpret_cast<float4*>(dst + c0 + e) = make_float4(__uint_as_float(v[e]), __uint_as_float(v[e + 1]),
+                                                                         __uint_as_float(v[e + 2]), __uint_as_float(v[e + 3]));
+        }
+    }
+    tc_fence_before_sync();
+    __syncthreads();
+    if (warp == 0) tmem_dealloc(tmem_d, tmem_cols);
+}
+
+// fold partials ws[S][KX][NY] -> fp32 gradient in the REFERENCE's parameter layout.
+// mode 0: dst[co][k] (conv1: K order (c,ky,kx) == torch's)                      src (k, co)
+// mode 1: dst[co][c][ky][kx] from K order (ky,kx,c) with C channels, KK taps       src (k, co)
+// mode 2: dst[o][c*49 + p] from X-side = o (rows), Y-side k = p*64 + c (fc)         src (o, k)
+__global__ void tc_fold_kernel(const float* __restrict__ ws, int S, int KX, int NY, int validX, int validY,
+                               int mode, int C, int KK, float scale, float* __restrict__ dst) {
+    const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int64_t total = (int64_t)validX * validY;
+    if (idx >= total) return;
+    const int xi = (int)(idx / validY), yi = (int)(idx - (int64_t)xi * validY);
+    float s = 0.f;
+    const int64_t slab = (int64_t)KX * NY;
+    for (int z = 0; z < S; ++z) s += ws[z * slab + (int64_t)xi * NY + yi];
+    s *= scale;
+    int64_t o;
+    if (mode == 0) {
+        o = (int64_t)yi * validX + xi;
+    } else if (mode == 1) {
+        const int tap = xi / C, c = xi - tap * C;          // xi = tap*C + c
+        o = ((int64_t)yi * C + c) * KK + tap;
+    } else {
+        const int pp = yi / C, c = yi - pp * C;            // yi = p*64 + c ; torch flatten index = c*49 + p
+        o = (int64_t)xi * validY + (int64_t)c * KK + pp;
+    }
+    dst[o] = s;
+}
+
+// column sums of a bf16 matrix [M, ld] (bias gradients): two-level deterministic reduction
+__global__ void __launch_bounds__(256) tc_colsum_partial(const bf16* __restrict__ Y, int64_t M, int ld, int ncols,
+                                                         int64_t rows_per_block, float* __restrict__ part) {
+    // thread -> column (ncols <= 512), loops over a row block; coalesced across columns
+    const int64_t r0 = (int64_t)blockIdx.x * rows_per_block;
+    int64_t r1 = r0 + rows_per_block;
+    if (r1 > M) r1 = M;
+    for (int c = threadIdx.x; c < ncols; c += blockDim.x) {
+        float s = 0.f;
+        for (int64_t r = r0; r < r1; ++r) s += __bfloat162float(Y[r * ld + c]);
+        part[(int64_t)blockIdx.x * ncols + c] = s;
+    }
+}
+__global__ void tc_colsum_final(const float* __restrict__ part, int nblocks, int ncols, float* __restrict__ db) {
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= ncols) return;
+    float s = 0.f;
+    for (int b = 0; b < nblocks; ++b) s += part[(int64_t)b * ncols + c];
+    db[c] = s;
+}
+
+// ------------------------------------------------------------------ weight packing (fp32 master -> bf16 GEMM operands)
+// conv weight w[co][c][ky][kx] -> fwd[co][(ky,kx,c)] (nhwc_k) or [co][(c,ky,kx)] (conv1), and
+// dgrad[c][(ky,kx,co)] with taps FLIPPED implicitly by the loader's negative offsets (no flip needed here).
+__global__ void tc_pack_conv(const float* __restrict__ w, int Cout, int Cin, int KH, int KW, int nchw_k,
+                             bf16* __restrict__ fwd, bf16* __restrict__ dgrad) {
+    const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int64_t total = (int64_t)Cout * Cin * KH * KW;
+    if (idx >= total) return;
+    int kx = (int)(idx % KW); int64_t t = idx / KW;
+    int ky = (int)(t % KH); t /= KH;
+    int c = (int)(t % Cin); int co = (int)(t / Cin);
+    const bf16 v = __float2bfloat16(w[idx]);
+    const int K = Cin * KH * KW;
+    if (nchw_k) fwd[(int64_t)co * K + (c * KH + ky) * KW + kx] = v;
+    else fwd[(int64_t)co * K + (ky * KW + kx) * Cin + c] = v;
+    if (dgrad) dgrad[(int64_t)c * (KH * KW * Cout) + (ky * KW + kx) * Cout + co] = v;
+}
+// conv2 data-gradient weights per stride-parity class: dg[cls][c][(a,b,co)] = w[co][c][py+2a][px+2b]
+__global__ void tc_pack_conv_s2_classes(const float* __restrict__ w, int Cout, int Cin, bf16* __restrict__ dg) {
+    const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int64_t total = (int64_t)4 * Cin * 4 * Cout;
+    if (idx >= total) return;
+    int co = (int)(idx % Cout); int64_t t = idx / Cout;
+    int ab = (int)(t % 4); t /= 4;
+    int c = (int)(t % Cin); int cls = (int)(t / Cin);
+    const int py = cls >> 1, px = cls & 1, a = ab >> 1, b = ab & 1;
+    dg[idx] = __float2bfloat16(w[(((int64_t)co * Cin + c) * 4 + (py + 2 * a)) * 4 + (px + 2 * b)]);
+}
+// fc weight w[o][c*49+p] -> fwd[o][p*64+c]; dgrad[p*64+c][o]
+__global__ void tc_pack_fc(const float* __restrict__ w, int O, int C, int PP, bf16* __restrict__ fwd, bf16* __restrict__ dgrad) {
+    const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int64_t total = (int64_t)O * C * PP;
+    if (idx >= total) return;
+    const int pp = (int)(idx % PP); int64_t t = idx / PP;
+    const int c = (int)(t % C); const int o = (int)(t / C);
+    const bf16 v = __float2bfloat16(w[idx]);
+    fwd[(int64_t)o * (C * PP) + pp * C + c] = v;
+    dgrad[((int64_t)pp * C + c) * O + o] = v;
+}
+
+// ------------------------------------------------------------------ policy/value heads (tiny: CUDA cores, fp32 math)
+// out[n][A1] = hidden[n][512](bf16) . Wh[A1][512]^T + bh    (one warp per row)
+__global__ void __launch_bounds__(256) tc_heads_fwd(const bf16* __restrict__ hid, const float* __restrict__ Wh,
+                                                    const float* __restrict__ bh, int64_t n, int A1, int H,
+                                                    float* __restrict__ out) {
+    const int64_t row = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const int lane = threadIdx.x & 31;
+    if (row >= n) return;
+    float hv[16];
+    const bf16* hp = hid + row * H;
+    for (int q = 0; q < H / 32 && q < 16; ++q) hv[q] = __bfloat162float(hp[q * 32 + lane]);
+    for (int a = 0; a < A1; ++a) {
+        float s = 0.f;
+        for (int q = 0; q < H / 32 && q < 16; ++q) s = fmaf(hv[q], __ldg(Wh + (int64_t)a * H + q * 32 + lane), s);
+        s = warp_sum(s);
+        if (lane == 0) out[row * A1 + a] = s + bh[a];
+    }
+}
+// dhid_pre[n][512] (bf16) = (dhead[n][A1] . Wh[A1][512]) * (hid > 0)
+__global__ void __launch_bounds__(256) tc_heads_bwd_data(const float* __restrict__ dhead, const float* __restrict__ Wh,
+                                                         const bf16* __restrict__ hid, int64_t n, int A1, int H,
+                                                         bf16* __restrict__ dhid) {
+    const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= n * H) return;
+    const int64_t row = idx / H;
+    const int h = (int)(idx - row * H);
+    float s = 0.f;
+    for (int a = 0; a < A1; ++a) s = fmaf(dhead[row * A1 + a], __ldg(Wh + (int64_t)a * H + h), s);
+    if (!(__bfloat162float(hid[idx]) > 0.f)) s = 0.f;
+    dhid[idx] = __float2bfloat16(s);
+}
+// dWh[a][h] = sum_m dhead[m][a] * hid[m][h]; dbh[a] = sum_m dhead[m][a]  (partials per row block, then fold)
+__global__ void __launch_bounds__(512) tc_heads_bwd_weight(const float* __restrict__ dhead, const bf16* __restrict__ hid,
+                                                           int64_t n, int A1, int H, int64_t rows_per_block,
+                                                           float* __restrict__ part) {
+    // thread -> h ; part[block][a][h] (+ [block][a][H] for the bias)
+    const int h = threadIdx.x;
+    const int64_t r0 = (int64_t)blockIdx.x * rows_per_block;
+    int64_t r1 = r0 + rows_per_block;
+    if (r1 > n) r1 = n;
+    float acc[8], bacc[8];
+    for (int a = 0; a < 8; ++a) { acc[a] = 0.f; bacc[a] = 0.f; }
+    for (int64_t r = r0; r < r1; ++r) {
+        const float hv = h < H ? __bfloat162float(hid[r * H + h]) : 0.f;
+#pragma unroll
+        for (int a = 0; a < 8; ++a) {
+            if (a < A1) {
+                const float d = __ldg(dhead + r * A1 + a);
+                acc[a] = fmaf(d, hv, acc[a]);
+                bacc[a] += d;
+            }
+        }
+    }
+    float* pb = part + (int64_t)blockIdx.x * A1 * (H + 1);
+    for (int a = 0; a < A1 && a < 8; ++a) {
+        if (h < H) pb[(int64_t)a * (H + 1) + h] = acc[a];
+        if (h == 0) pb[(int64_t)a * (H + 1) + H] = bacc[a];
+    }
+}
+__global__ void tc_heads_fold(const float* __restrict__ part, int nblocks, int A1, int H, float* __restrict__ dW,
+                              float* __restrict__ db) {
+    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= A1 * (H + 1)) return;
+    float s = 0.f;
+    for (int b = 0; b < nblocks; ++b) s += part[(int64_t)b * A1 * (H + 1) + idx];
+    const int a = idx / (H + 1), h = idx - a * (H + 1);
+    if (h == H) db[a] = s; else dW[(int64_t)a * H + h] = s;
+}
+
+}  // namespace b200rl
+
+// =====================================================================================
+// Host side: NatureCNN plan over the kernels above (C-ABI entry points, include/b200rl.h)
+// =====================================================================================
+namespace b200rl {
+
+struct NatureLayout {
+    int A;
+    // flat fp32 parameter offsets (libb200rl order: trunk, then both head weights, then both head biases)
+    int64_t c1w, c1b, c2w, c2b, c3w, c3b, fcw, fcb, hw, hb, total;
+    // packed bf16 operand offsets (elements)
+    int64_t w1f, w2f, w2dg, w3f, w3dg, wfcf, wfcdg, packed_total;
+    explicit NatureLayout(int A_) : A(A_) {
+        int64_t o = 0;
+        c1w = o; o += 32 * 4 * 8 * 8;  c1b = o; o += 32;
+        c2w = o; o += 64 * 32 * 4 * 4; c2b = o; o += 64;
+        c3w = o; o += 64 * 64 * 3 * 3; c3b = o; o += 64;
+        fcw = o; o += 512 * 3136;      fcb = o; o += 512;
+        hw = o;  o += (int64_t)(A + 1) * 512;
+        hb = o;  o += A + 1;
+        total = o;
+        int64_t q = 0;
+        w1f = q; q += 32 * 256;
+        w2f = q; q += 64 * 512;
+        w2dg = q; q += 4 * 32 * 256;
+        w3f = q; q += 64 * 576;
+        w3dg = q; q += 64 * 576;
+        wfcf = q; q += 512 * 3136;
+        wfcdg = q; q += 3136 * 512;
+        packed_total = q;
+    }
+};
+
+struct NatureActs {   // bf16 element offsets inside the activation workspace for batch n
+    int64_t act1, act2, act3, hid, dhid, dact3, dact2, dact1, total;
+    explicit NatureActs(int64_t n) {
+        int64_t o = 0;
+        act1 = o; o += n * 12800;
+        act2 = o; o += n * 5184;
+        act3 = o; o += n * 3136;
+        hid = o;  o += n * 512;
+        dhid = o; o += n * 512;
+        dact3 = o; o += n * 3136;
+        dact2 = o; o += n * 5184;
+        dact1 = o; o += n * 12800;
+        total = o;
+    }
+};
+
+static void gemm_defaults(KGemmParams& p) {
+    memset(&p, 0, sizeof(p));
+    p.nclasses = 1;
+    p.scale = 1.f;
+    p.osy = p.osx = 1;
+    p.sy = p.sx = 1;
+}
+static void set_rows(KGemmParams& p, int64_t M, int rpi, int Ws) {
+    p.M = M; p.rpi = rpi; p.Ws = Ws;
+    p.tiles_per_class = (int)ceil_div(M, 128);
+}
+
+static void conv1_gather(KGemmParams& p, const uint8_t* obs, const int64_t* rows, int64_t n) {
+    p.A = obs; p.rows = rows;
+    set_rows(p, n * 400, 400, 20);
+    p.SH = 84; p.SW = 84; p.CP = 4; p.sy = p.sx = 4; p.nchunks = 4; p.check = 0;
+}
+static void conv2_gather(KGemmParams& p, const bf16* act1, int64_t n) {
+    p.A = act1;
+    set_rows(p, n * 81, 81, 9);
+    p.SH = 20; p.SW = 20; p.CP = 32; p.sy = p.sx = 2; p.nchunks = 8; p.check = 0;
+    for (int ky = 0; ky < 4; ++ky) for (int h = 0; h < 2; ++h) { p.dy[ky * 2 + h] = (signed char)ky; p.dx[ky * 2 + h] = (signed char)(2 * h); }
+}
+static void conv3_gather(KGemmParams& p, const bf16* act2, int64_t n) {
+    p.A = act2;
+    set_rows(p, n * 49, 49, 7);
+    p.SH = 9; p.SW = 9; p.CP = 64; p.nchunks = 9; p.check = 0;
+    for (int ky = 0; ky < 3; ++ky) for (int kx = 0; kx < 3; ++kx) { p.dy[ky * 3 + kx] = (signed char)ky; p.dx[ky * 3 + kx] = (signed char)kx; }
+}
+static void rowmajor_gather(KGemmParams& p, const bf16* x, int64_t n, int nchunks) {   // x [n, 64*nchunks]
+    p.A = x;
+    set_rows(p, n, 1, 1);
+    p.SH = 1; p.SW = nchunks; p.CP = 64; p.nchunks = nchunks; p.check = 0;
+    for (int j = 0; j < nchunks; ++j) { p.dy[j] = 0; p.dx[j] = (signed char)j; }
+}
+
+static int64_t round_up(int64_t a, int64_t b) { return ceil_div(a, b) * b; }
+
+struct WPlan { int64_t rows_per_cta; int splits; };
+static WPlan wgrad_plan(int64_t M, int target_ctas) {
+    WPlan w;
+    w.rows_per_cta = round_up(ceil_div(M, target_ctas), 32);
+    if (w.rows_per_cta < 32) w.rows_per_cta = 32;
+    w.splits = (int)ceil_div(M, w.rows_per_cta);
+    if (w.splits < 1) w.splits = 1;
+    return w;
+}
+static const int kC1Ctas = 444, kC2Ctas = 296, kC3Ctas = 148, kFcSplits = 8;
+
+template <bool A_U8>
+static int launch_wgrad(const WGradParams& p, dim3 grid, cudaStream_t s, const char* what) {
+    const size_t smem = (size_t)3 * (p.nxc + p.nyc) * 32 * 128 + 1024;
+    static size_t attr = 0;
+    if (smem > attr) {
+        cudaError_t e = cudaFuncSetAttribute(tc_wgrad<A_U8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return fail(B200RL_ERR_CUDA, "%s: smem attribute (%zu B): %s", what, smem, cudaGetErrorString(e));
+        attr = smem;
+    }
+    tc_wgrad<A_U8><<<grid, 128, smem, s>>>(p);
+    return check_launch(what);
+}
+
+static int colsum(const bf16* Y, int64_t M, int ld, int ncols, float* part, float* db, cudaStream_t s) {
+    int64_t rpb = ceil_div(M, 148 * 4);
+    if (rpb < 16) rpb = 16;
+    const int nb = (int)ceil_div(M, rpb);
+    tc_colsum_partial<<<nb, 256, 0, s>>>(Y, M, ld, ncols, rpb, part);
+    tc_colsum_final<<<(unsigned)ceil_div(ncols, 128), 128, 0, s>>>(part, nb, ncols, db);
+    return check_launch("colsum", 2);
+}
+static size_t colsum_ws(int64_t M, int ncols) {
+    int64_t rpb = ceil_div(M, 148 * 4);
+    if (rpb < 16) rpb = 16;
+    return (size_t)ceil_div(M, rpb) * ncols * sizeof(float);
+}
+
+}  // namespace b200rl
+
+using namespace b200rl;
+
+extern "C" int64_t b200rl_naturecnn_param_count(int A) { return A >= 1 ? NatureLayout(A).total : -1; }
+extern "C" size_t b200rl_naturecnn_bf16_packed_bytes(int A) { return A >= 1 ? (size_t)NatureLayout(A).packed_total * 2 : 0; }
+extern "C" size_t b200rl_naturecnn_bf16_acts_bytes(int64_t n) { return n >= 0 ? (size_t)NatureActs(n).total * 2 + 256 : 0; }
+
+extern "C" size_t b200rl_naturecnn_bf16_workspace_bytes(int64_t n, int A) {
+    if (n < 1 || A < 1) return 0;
+    size_t a = 0;
+    auto mx = [&](size_t v) { if (v > a) a = v; };
+    mx((size_t)wgrad_plan(n * 400, kC1Ctas).splits * 256 * 64 * 4);
+    mx((size_t)wgrad_plan(n * 81, kC2Ctas).splits * 512 * 64 * 4);
+    mx((size_t)wgrad_plan(n * 49, kC3Ctas).splits * 640 * 64 * 4);
+    mx((size_t)wgrad_plan(n, kFcSplits).splits * 512 * (13 * 256) * 4);
+    size_t b = 0;
+    auto mb = [&](size_t v) { if (v > b) b = v; };
+    mb(colsum_ws(n * 400, 32)); mb(colsum_ws(n * 81, 64)); mb(colsum_ws(n * 49, 64)); mb(colsum_ws(n, 512));
+    mb((size_t)296 * (A + 1) * 513 * 4);
+    return a + b + 512;
+}
+
+extern "C" int b200rl_naturecnn_bf16_pack(const float* params, int A, void* packed, void* stream) {
+    B200RL_REQUIRE(params && packed && A >= 1 && A <= 7, "naturecnn_pack: bad arguments (A must be in [1,7])");
+    B200RL_REQUIRE(aligned(packed, 16), "naturecnn_pack: packed buffer must be 16-B aligned");
+    const NatureLayout L(A);
+    bf16* P = reinterpret_cast<bf16*>(packed);
+    cudaStream_t s = (cudaStream_t)stream;
+    ProfScope ps(s, "pack_weights", 0, (double)L.total * 4 + (double)L.packed_total * 2);
+    tc_pack_conv<<<(unsigned)ceil_div(8192, 256), 256, 0, s>>>(params + L.c1w, 32, 4, 8, 8, 1, P + L.w1f, nullptr);
+    tc_pack_conv<<<(unsigned)ceil_div(32768, 256), 256, 0, s>>>(params + L.c2w, 64, 32, 4, 4, 0, P + L.w2f, nullptr);
+    tc_pack_conv_s2_classes<<<(unsigned)ceil_div(32768, 256), 256, 0, s>>>(params + L.c2w, 64, 32, P + L.w2dg);
+    tc_pack_conv<<<(unsigned)ceil_div(36864, 256), 256, 0, s>>>(params + L.c3w, 64, 64, 3, 3, 0, P + L.w3f, P + L.w3dg);
+    tc_pack_fc<<<(unsigned)ceil_div(512 * 3136, 256), 256, 0, s>>>(params + L.fcw, 512, 64, 49, P + L.wfcf, P + L.wfcdg);
+    return check_launch("naturecnn_pack", 5);
+}
+
+extern "C" int b200rl_naturecnn_bf16_forward(const uint8_t* obs, const int64_t* rows, int64_t n, int A,
+                                             const float* params, const void* packed, void* acts,
+                                             float* head_out, void* stream) {
+    B200RL_REQUIRE(n >= 0, "naturecnn_forward: negative n");
+    if (n == 0) return B200RL_OK;
+    B200RL_REQUIRE(obs && params && packed && acts && head_out, "naturecnn_forward: null pointer");
+    B200RL_REQUIRE(A >= 1 && A <= 7, "naturecnn_forward: A=%d outside [1,7]", A);
+    B200RL_REQUIRE(aligned(obs, 4) && aligned(acts, 16) && aligned(packed, 16), "naturecnn_forward: misaligned buffer");
+    B200RL_REQUIRE(n <= (int64_t)1 << 22, "naturecnn_forward: n too large");
+    const NatureLayout L(A);
+    const NatureActs Q(n);
+    const bf16* P = reinterpret_cast<const bf16*>(packed);
+    bf16* act = reinterpret_cast<bf16*>(acts);
+    cudaStream_t s = (cudaStream_t)stream;
+    int rc;
+    KGemmParams p;
+    // conv1: uint8 frames -> act1 [n,20,20,32]
+    gemm_defaults(p); conv1_gather(p, obs, rows, n);
+    p.Bw = P + L.w1f; p.N = 32; p.out = act + Q.act1; p.OH = 20; p.OW = 20; p.ldo = 32;
+    p.bias = params + L.c1b; p.scale = 1.0f / 255.0f; p.relu = 1;
+    { ProfScope ps(s, "conv1_fwd", 2.0 * n * 400 * 32 * 256, (double)n * (28224 + 12800 * 2));
+      if ((rc = launch_kgemm<32, 3, true>(p, s, "naturecnn/conv1"))) return rc; }
+    // conv2 -> act2 [n,9,9,64]
+    gemm_defaults(p); conv2_gather(p, act + Q.act1, n);
+    p.Bw = P + L.w2f; p.N = 64; p.out = act + Q.act2; p.OH = 9; p.OW = 9; p.ldo = 64; p.bias = params + L.c2b; p.relu = 1;
+    { ProfScope ps(s, "conv2_fwd", 2.0 * n * 81 * 64 * 512, (double)n * (12800 + 5184) * 2);
+      if ((rc = launch_kgemm<64, 3, false>(p, s, "naturecnn/conv2"))) return rc; }
+    // conv3 -> act3 [n,7,7,64]
+    gemm_defaults(p); conv3_gather(p, act + Q.act2, n);
+    p.Bw = P + L.w3f; p.N = 64; p.out = act + Q.act3; p.OH = 7; p.OW = 7; p.ldo = 64; p.bias = params + L.c3b; p.relu = 1;
+    { ProfScope ps(s, "conv3_fwd", 2.0 * n * 49 * 64 * 576, (double)n * (5184 + 3136) * 2);
+      if ((rc = launch_kgemm<64, 3, false>(p, s, "naturecnn/conv3"))) return rc; }
+    // fc -> hidden [n,512]
+    gemm_defaults(p); rowmajor_gather(p, act + Q.act3, n, 49);
+    p.Bw = P + L.wfcf; p.N = 512; p.out = act + Q.hid; p.OH = 1; p.OW = 1; p.ldo = 512; p.bias = params + L.fcb; p.relu = 1;
+    { ProfScope ps(s, "fc_fwd", 2.0 * n * 512 * 3136, (double)n * (3136 + 512) * 2 + 512.0 * 3136 * 2);
+      if ((rc = launch_kgemm<256, 2, false>(p, s, "naturecnn/fc"))) return rc; }
+    // heads (fp32 math on CUDA cores): head_out [n, A+1] = [logits | value]
+    { ProfScope ps(s, "heads_fwd", 2.0 * n * 512 * (A + 1), (double)n * (1024 + 4 * (A + 1)));
+      tc_heads_fwd<<<(unsigned)ceil_div(n, 8), 256, 0, s>>>(act + Q.hid, params + L.hw, params + L.hb, n, A + 1, 512, head_out); }
+    return check_launch("naturecnn/heads");
+}
+
+extern "C" int b200rl_naturecnn_bf16_backward(const uint8_t* obs, const int64_t* rows, int64_t n, int A,
+                                              const float* params, const void* packed, void* acts,
+                                              const float* dhead, float* grads,
+                                              void* workspace, size_t workspace_bytes, void* stream) {
+    B200RL_REQUIRE(n >= 1, "naturecnn_backward: n must be >= 1");
+    B200RL_REQUIRE(obs && params && packed && acts && dhead && grads && workspace, "naturecnn_backward: null pointer");
+    B200RL_REQUIRE(A >= 1 && A <= 7, "naturecnn_backward: A=%d outside [1,7]", A);
+    B200RL_REQUIRE(aligned(workspace, 16), "naturecnn_backward: workspace misaligned");
+    const size_t need = b200rl_naturecnn_bf16_workspace_bytes(n, A);
+    if (workspace_bytes < need) return fail(B200RL_ERR_WORKSPACE, "naturecnn_backward: workspace %zu < %zu", workspace_bytes, need);
+    const NatureLayout L(A);
+    const NatureActs Q(n);
+    const bf16* P = reinterpret_cast<const bf16*>(packed);
+    bf16* act = reinterpret_cast<bf16*>(acts);
+    cudaStream_t s = (cudaStream_t)stream;
+    // workspace split: [wgrad partials | small partials]
+    size_t big = 0;
+    {
+        auto mx = [&](size_t v) { if (v > big) big = v; };
+        mx((size_t)wgrad_plan(n * 400, kC1Ctas).splits * 256 * 64 * 4);
+        mx((size_t)wgrad_plan(n * 81, kC2Ctas).splits * 512 * 64 * 4);
+        mx((size_t)wgrad_plan(n * 49, kC3Ctas).splits * 640 * 64 * 4);
+        mx((size_t)wgrad_plan(n, kFcSplits).splits * 512 * (13 * 256) * 4);
+        big = (big + 255) & ~(size_t)255;
+    }
+    float* wsbig = reinterpret_cast<float*>(workspace);
+    float* wssmall = reinterpret_cast<float*>(reinterpret_cast<char*>(workspace) + big);
+    int rc;
+    const int A1 = A + 1;
+    // ---- heads: dW, db, then dhid_pre = (dhead . Wh) * (hid > 0)
+    {
+        int64_t rpb = ceil_div(n, 296);
+        if (rpb < 8) rpb = 8;
+        const int nb = (int)ceil_div(n, rpb);
+        ProfScope ps(s, "heads_bwd", 4.0 * n * 512 * A1, (double)n * (2048 + 8 * A1));
+        tc_heads_bwd_weight<<<nb, 512, 0, s>>>(dhead, act + Q.hid, n, A1, 512, rpb, wssmall);
+        tc_heads_fold<<<(unsigned)ceil_div(A1 * 513, 128), 128, 0, s>>>(wssmall, nb, A1, 512, grads + L.hw, grads + L.hb);
+        tc_heads_bwd_data<<<(unsigned)ceil_div(n * 512, 256), 256, 0, s>>>(dhead, params + L.hw, act + Q.hid, n, A1, 512, act + Q.dhid);
+        if ((rc = check_launch("naturecnn/heads_bwd", 3))) return rc;
+    }
+    WGradParams w;
+    KGemmParams p;
+    // ---- fc: dW[o][c*49+p] = sum_m dhid[m][o] * act3[m][p*64+c]
+    {
+        memset(&w, 0, sizeof(w));
+        gemm_defaults(w.x); rowmajor_gather(w.x, act + Q.dhid, n, 8);
+        w.Y = act + Q.act3; w.ldy = 3136; w.nyc = 4; w.ncolsY = 3136; w.nxc = 2;
+        const WPlan pl = wgrad_plan(n, kFcSplits);
+        w.rows_per_cta = pl.rows_per_cta; w.ws = wsbig;
+        { ProfScope ps(s, "fc_wgrad", 2.0 * n * 512 * 3136, (double)n * (3136 + 512) * 2 + 512.0 * 3136 * 4);
+          if ((rc = launch_wgrad<false>(w, dim3(pl.splits, 4, 13), s, "naturecnn/fc_wgrad"))) return rc; }
+        { ProfScope ps(s, "wgrad_fold_bias", 0, 0);
+          note_launches(1); tc_fold_kernel<<<(unsigned)ceil_div((int64_t)512 * 3136, 256), 256, 0, s>>>(wsbig, pl.splits, 512, 13 * 256, 512, 3136, 2, 64, 49, 1.f, grads + L.fcw);
+          if ((rc = colsum(act + Q.dhid, n, 512, 512, wssmall, grads + L.fcb, s))) return rc; }
+        // dact3_pre = (dhid . Wfc) * (act3 > 0)
+        gemm_defaults(p); rowmajor_gather(p, act + Q.dhid, n, 8);
+        p.Bw = P + L.wfcdg; p.N = 3136; p.out = act + Q.dact3; p.OH = 1; p.OW = 1; p.ldo = 3136; p.mask = act + Q.act3;
+        { ProfScope ps(s, "fc_dgrad", 2.0 * n * 512 * 3136, (double)n * (3136 * 2 + 512) * 2 + 512.0 * 3136 * 2);
+          if ((rc = launch_kgemm<256, 2, false>(p, s, "naturecnn/fc_dgrad"))) return rc; }
+    }
+    // ---- conv3
+    {
+        memset(&w, 0, sizeof(w));
+        gemm_defaults(w.x); conv3_gather(w.x, act + Q.act2, n);
+        w.Y = act + Q.dact3; w.ldy = 64; w.nyc = 1; w.ncolsY = 64; w.nxc = 10;
+        const WPlan pl = wgrad_plan(n * 49, kC3Ctas);
+        w.rows_per_cta = pl.rows_per_cta; w.ws = wsbig;
+        { ProfScope ps(s, "conv3_wgrad", 2.0 * n * 49 * 64 * 576, (double)n * (5184 + 3136) * 2);
+          if ((rc = launch_wgrad<false>(w, dim3(pl.splits, 1, 1), s, "naturecnn/conv3_wgrad"))) return rc; }
+        { ProfScope ps(s, "wgrad_fold_bias", 0, 0);
+          note_launches(1); tc_fold_kernel<<<(unsigned)ceil_div(576 * 64, 256), 256, 0, s>>>(wsbig, pl.splits, 640, 64, 576, 64, 1, 64, 9, 1.f, grads + L.c3w);
+          if ((rc = colsum(act + Q.dact3, n * 49, 64, 64, wssmall, grads + L.c3b, s))) return rc; }
+        // dact2_pre[n,9,9,64] = full-correlation of dact3 with W3, masked by act2 > 0
+        gemm_defaults(p);
+        p.A = act + Q.dact3; set_rows(p, n * 81, 81, 9);
+        p.SH = 7; p.SW = 7; p.CP = 64; p.nchunks = 9; p.check = 1;
+        for (int ky = 0; ky < 3; ++ky) for (int kx = 0; kx < 3; ++kx) { p.dy[ky * 3 + kx] = (signed char)-ky; p.dx[ky * 3 + kx] = (signed char)-kx; }
+        p.Bw = P + L.w3dg; p.N = 64; p.out = act + Q.dact2; p.OH = 9; p.OW = 9; p.ldo = 64; p.mask = act + Q.act2;
+        { ProfScope ps(s, "conv3_dgrad", 2.0 * n * 81 * 64 * 576, (double)n * (3136 + 5184 * 2) * 2);
+          if ((rc = launch_kgemm<64, 3, false>(p, s, "naturecnn/conv3_dgrad"))) return rc; }
+    }
+    // ---- conv2
+    {
+        memset(&w, 0, sizeof(w));
+        gemm_defaults(w.x); conv2_gather(w.x, act + Q.act1, n);
+        w.Y = act + Q.dact2; w.ldy = 64; w.nyc = 1; w.ncolsY = 64; w.nxc = 8;
+        const WPlan pl = wgrad_plan(n * 81, kC2Ctas);
+        w.rows_per_cta = pl.rows_per_cta; w.ws = wsbig;
+        { ProfScope ps(s, "conv2_wgrad", 2.0 * n * 81 * 64 * 512, (double)n * (12800 + 5184) * 2);
+          if ((rc = launch_wgrad<false>(w, dim3(pl.splits, 1, 1), s, "naturecnn/conv2_wgrad"))) return rc; }
+        { ProfScope ps(s, "wgrad_fold_bias", 0, 0);
+          note_launches(1); tc_fold_kernel<<<(unsigned)ceil_div(512 * 64, 256), 256, 0, s>>>(wsbig, pl.splits, 512, 64, 512, 64, 1, 32, 16, 1.f, grads + L.c2w);
+          if ((rc = colsum(act + Q.dact2, n * 81, 64, 64, wssmall, grads + L.c2b, s))) return rc; }
+        // dact1_pre[n,20,20,32]: 4 stride-parity classes, each a 2x2-tap stride-1 problem on a 10x10 grid
+        gemm_defaults(p);
+        p.A = act + Q.dact2; set_rows(p, n * 100, 100, 10);
+        p.SH = 9; p.SW = 9; p.CP = 64; p.nchunks = 4; p.check = 1; p.nclasses = 4;
+        for (int a = 0; a < 2; ++a) for (int b = 0; b < 2; ++b) { p.dy[a * 2 + b] = (signed char)-a; p.dx[a * 2 + b] = (signed char)-b; }
+        p.Bw = P + L.w2dg; p.b_class_stride = 32 * 256; p.N = 32;
+        p.out = act + Q.dact1; p.OH = 20; p.OW = 20; p.osy = 2; p.osx = 2; p.ldo = 32; p.mask = act + Q.act1;
+        { ProfScope ps(s, "conv2_dgrad", 2.0 * n * 400 * 32 * 256, (double)n * (5184 + 12800 * 2) * 2);
+          if ((rc = launch_kgemm<32, 3, false>(p, s, "naturecnn/conv2_dgrad"))) return rc; }
+    }
+    // ---- conv1 (no data gradient: the input is the observation)
+    {
+        memset(&w, 0, sizeof(w));
+        gemm_defaults(w.x); conv1_gather(w.x, obs, rows, n);
+        w.Y = act + Q.dact1; w.ldy = 32; w.nyc = 1; w.ncolsY = 32; w.nxc = 4;
+        const WPlan pl = wgrad_plan(n * 400, kC1Ctas);
+        w.rows_per_cta = pl.rows_per_cta; w.ws = wsbig;
+        { ProfScope ps(s, "conv1_wgrad", 2.0 * n * 400 * 32 * 256, (double)n * (28224 + 12800 * 2));
+          if ((rc = launch_wgrad<true>(w, dim3(pl.splits, 1, 1), s, "naturecnn/conv1_wgrad"))) return rc; }
+        { ProfScope ps(s, "wgrad_fold_bias", 0, 0);
+          note_launches(1); tc_fold_kernel<<<(unsigned)ceil_div(256 * 32, 256), 256, 0, s>>>(wsbig, pl.splits, 256, 64, 256, 32, 0, 0, 0, 1.0f / 255.0f, grads + L.c1w);
+          if ((rc = colsum(act + Q.dact1, n * 400, 32, 32, wssmall, grads + L.c1b, s))) return rc; }
+    }
+    return B200RL_OK;
+}

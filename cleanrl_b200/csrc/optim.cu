@@ -146,6 +146,7 @@ extern "C" int b200rl_clip_adam_f32(float* params, const float* grads, float* ex
     OptScratch* sc = reinterpret_cast<OptScratch*>(workspace);
     double* partials = reinterpret_cast<double*>(reinterpret_cast<char*>(workspace) + sizeof(OptScratch));
     const unsigned blocks = opt_blocks(P);
+    ProfScope ps(s, "clip_adam", 0, 32.0 * P);
     const bool need_norm = (max_norm >= 0.0) || (norm_out != nullptr);
     if (need_norm) {
         cudaError_t e = cudaMemsetAsync(&sc->ticket, 0, sizeof(unsigned int), s);

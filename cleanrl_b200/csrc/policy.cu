@@ -247,6 +247,7 @@ extern "C" int b200rl_categorical_sample_f32(const float* logits, int64_t ld_log
     B200RL_REQUIRE(logits && noise && action && logprob, "categorical_sample: null pointer");
     B200RL_REQUIRE(ld_logits >= A, "categorical_sample: ld_logits < A");
     const unsigned blocks = (unsigned)ceil_div(n, 128);
+    ProfScope ps((cudaStream_t)stream, "categorical_sample", 0, (double)n * (8.0 * A + 24));
     categorical_sample_kernel<<<blocks, 128, 0, (cudaStream_t)stream>>>(
         logits, ld_logits, noise, value_in, ld_value, n, A, action, logprob, entropy, value_out);
     return check_launch("categorical_sample");
@@ -299,9 +300,10 @@ extern "C" int b200rl_ppo_loss_f32(const float* new_logits, int64_t ld_logits,
     float* adv_stats = reinterpret_cast<float*>(workspace);
     unsigned int* ticket = reinterpret_cast<unsigned int*>(reinterpret_cast<char*>(workspace) + 16);
     float* partials = reinterpret_cast<float*>(reinterpret_cast<char*>(workspace) + 32);
+    ProfScope ps(s, "ppo_loss", 0, (double)M * (44.0 + 8.0 * A));
     cudaError_t e = cudaMemsetAsync(ticket, 0, sizeof(unsigned int), s);
     if (e != cudaSuccess) return fail(B200RL_ERR_CUDA, "ppo_loss: memset: %s", cudaGetErrorString(e));
-    if (norm_adv) adv_stats_kernel<<<1, 1024, 0, s>>>(b_advantages, mb_inds, M, adv_stats);
+    if (norm_adv) { note_launches(1); adv_stats_kernel<<<1, 1024, 0, s>>>(b_advantages, mb_inds, M, adv_stats); }
     LossParams P;
     P.logits = new_logits; P.ld = ld_logits; P.value = new_value; P.ldv = ld_value;
     P.inds = mb_inds; P.b_actions = b_actions; P.b_logprobs = b_logprobs; P.b_adv = b_advantages;

@@ -292,3 +292,58 @@ def linear_bwd_weight(x, dy, dw, db, rows=None):
                                           _ptr(db, torch.float32, "db", True), n, in_f, out_f,
                                           ws.data_ptr(), ws.numel(), _stream())
     _lib.check(rc, "linear_bwd_weight")
+
+
+# ------------------------------------------------------ NatureCNN bf16 (tcgen05) plan
+class NatureCNNBf16:
+    """Owns the packed bf16 weights and activation workspaces of the tensor-core NatureCNN path."""
+
+    def __init__(self, A, device):
+        lib = _lib.load()
+        self.A, self.device = int(A), device
+        self.param_count = lib.b200rl_naturecnn_param_count(self.A)
+        self.packed = torch.empty(lib.b200rl_naturecnn_bf16_packed_bytes(self.A), dtype=torch.uint8, device=device)
+        self._acts = {}
+        self._ws = None
+
+    def acts(self, n):
+        lib = _lib.load()
+        if n not in self._acts:
+            if len(self._acts) > 4:
+                self._acts.clear()
+            self._acts[n] = torch.empty(lib.b200rl_naturecnn_bf16_acts_bytes(n), dtype=torch.uint8, device=self.device)
+        return self._acts[n]
+
+    def pack(self, flat_params):
+        lib = _lib.load()
+        rc = lib.b200rl_naturecnn_bf16_pack(_ptr(flat_params, torch.float32, "params"), self.A,
+                                            self.packed.data_ptr(), _stream())
+        _lib.check(rc, "naturecnn_bf16_pack")
+
+    def forward(self, obs, rows, flat_params, head_out=None):
+        lib = _lib.load()
+        if obs.dtype != torch.uint8:
+            raise TypeError("the bf16 NatureCNN path consumes uint8 frames (got %s)" % obs.dtype)
+        _contig(obs, "obs")
+        n = rows.numel() if rows is not None else obs.shape[0]
+        if head_out is None:
+            head_out = torch.empty(n, self.A + 1, dtype=torch.float32, device=self.device)
+        rc = lib.b200rl_naturecnn_bf16_forward(_ptr(obs, torch.uint8, "obs"), _ptr(rows, torch.int64, "rows", True), n, self.A,
+                                               _ptr(flat_params, torch.float32, "params"), self.packed.data_ptr(),
+                                               self.acts(n).data_ptr(), _ptr(head_out, torch.float32, "head_out"), _stream())
+        _lib.check(rc, "naturecnn_bf16_forward")
+        return head_out
+
+    def backward(self, obs, rows, flat_params, dhead, flat_grads):
+        lib = _lib.load()
+        n = dhead.shape[0]
+        _contig(dhead, "dhead")
+        nbytes = lib.b200rl_naturecnn_bf16_workspace_bytes(n, self.A)
+        if self._ws is None or self._ws.numel() < nbytes:
+            self._ws = torch.empty(nbytes, dtype=torch.uint8, device=self.device)
+        rc = lib.b200rl_naturecnn_bf16_backward(_ptr(obs, torch.uint8, "obs"), _ptr(rows, torch.int64, "rows", True), n, self.A,
+                                                _ptr(flat_params, torch.float32, "params"), self.packed.data_ptr(),
+                                                self.acts(n).data_ptr(), _ptr(dhead, torch.float32, "dhead"),
+                                                _ptr(flat_grads, torch.float32, "grads"),
+                                                self._ws.data_ptr(), self._ws.numel(), _stream())
+        _lib.check(rc, "naturecnn_bf16_backward")

@@ -65,8 +65,9 @@ class PPOEngine:
         self.next_done_h = torch.zeros(N, dtype=f32).pin_memory()
         self.actions_h = torch.zeros(N, dtype=torch.int64).pin_memory()
         self.obs_stage_h = torch.zeros((N,) + tuple(obs_shape), dtype=self.obs_dtype).pin_memory()
-        self.b_inds_h = torch.zeros(self.B, dtype=torch.int64).pin_memory()
-        self.b_inds = torch.zeros(self.B, dtype=torch.int64, device=device)
+        E = int(args.update_epochs)
+        self.b_inds_h = torch.zeros((E, self.B), dtype=torch.int64).pin_memory()   # one slot per epoch: a pinned
+        self.b_inds = torch.zeros((E, self.B), dtype=torch.int64, device=device)  # source is never rewritten in flight
         n_upd = int(args.update_epochs) * self.num_minibatches
         self.stats = torch.zeros(max(n_upd, 1), 16, dtype=f32, device=device)
         self.stats_h = torch.zeros(max(n_upd, 1), 16, dtype=f32).pin_memory()
@@ -103,18 +104,31 @@ class PPOEngine:
         torch.cuda.current_stream().synchronize()
         return self.actions_h.numpy()
 
+    @torch.no_grad()
+    def policy_step_resident(self, step, obs_dev, done_dev=None):
+        """Device-resident variant (inputs already in HBM, no host round trip): used to measure the
+        kernel-side throughput of the rollout step; actions stay on the device."""
+        self.obs[step].copy_(obs_dev)
+        logits, value = self.agent._forward_heads(self.obs[step])
+        n, A = logits.shape
+        q = self.agent.noise_fn(n, A, self.device)
+        ops.categorical_sample(logits, q, value,
+                               out=(self.actions[step], self.logprobs[step], None, self.values[step]))
+
     def record_reward(self, step, reward_np):
         self.rewards_h[step].copy_(torch.as_tensor(np.asarray(reward_np, dtype=np.float32).reshape(-1)))
 
     @torch.no_grad()
-    def finish_rollout(self, next_obs_np, next_done_np):
-        """Bootstrap value + GAE (reference: ppo.py:217-231)."""
-        self.rewards.copy_(self.rewards_h, non_blocking=True)
-        self.dones.copy_(self.dones_h, non_blocking=True)
-        self.next_done_h.copy_(torch.as_tensor(np.asarray(next_done_np, dtype=np.float32)))
-        self.next_done.copy_(self.next_done_h, non_blocking=True)
-        self.h2d_bytes += 2 * self.B * 4 + self.N * 4
-        self._upload_obs(self.next_obs, next_obs_np)
+    def finish_rollout(self, next_obs_np, next_done_np, resident=False):
+        """Bootstrap value + GAE (reference: ppo.py:217-231).  ``resident``: rewards/dones/next_obs
+        were already written on the device."""
+        if not resident:
+            self.rewards.copy_(self.rewards_h, non_blocking=True)
+            self.dones.copy_(self.dones_h, non_blocking=True)
+            self.next_done_h.copy_(torch.as_tensor(np.asarray(next_done_np, dtype=np.float32)))
+            self.next_done.copy_(self.next_done_h, non_blocking=True)
+            self.h2d_bytes += 2 * self.B * 4 + self.N * 4
+            self._upload_obs(self.next_obs, next_obs_np)
         _, value = self.agent._forward_heads(self.next_obs)
         self.next_value.copy_(value)
         ops.gae(self.rewards, self.values, self.dones, self.next_value, self.next_done,
@@ -138,14 +152,24 @@ class PPOEngine:
         b_inds_np = np.arange(B)
         dhead, dlogits, dvalue = agent.alloc_head_grad(M, self.device)
         k = 0
-        stop = False
-        for epoch in range(int(a.update_epochs)):
-            np.random.shuffle(b_inds_np)                    # numpy global RNG, as the reference
-            self.b_inds_h.copy_(torch.from_numpy(b_inds_np))
+        E = int(a.update_epochs)
+        pre = a.target_kl is None
+        if pre:
+            # no early exit possible: draw every epoch's permutation now (same numpy RNG consumption
+            # as the reference's in-place shuffles, ppo.py:245) and upload them in one copy
+            for epoch in range(E):
+                np.random.shuffle(b_inds_np)
+                self.b_inds_h[epoch].copy_(torch.from_numpy(b_inds_np))
             self.b_inds.copy_(self.b_inds_h, non_blocking=True)
-            self.h2d_bytes += B * 8
+            self.h2d_bytes += E * B * 8
+        for epoch in range(E):
+            if not pre:
+                np.random.shuffle(b_inds_np)                # numpy global RNG, as the reference
+                self.b_inds_h[epoch].copy_(torch.from_numpy(b_inds_np))
+                self.b_inds[epoch].copy_(self.b_inds_h[epoch], non_blocking=True)
+                self.h2d_bytes += B * 8
             for start in range(0, B, M):
-                mb_inds = self.b_inds[start:start + M]
+                mb_inds = self.b_inds[epoch, start:start + M]
                 logits, value = agent.forward_train(b_obs, mb_inds)
                 ops.ppo_loss(logits, value, mb_inds, b_actions, b_logprobs, b_adv, b_ret, b_val,
                              a.clip_coef, a.ent_coef, a.vf_coef, a.norm_adv, a.clip_vloss,
@@ -157,6 +181,8 @@ class PPOEngine:
                 ops.clip_adam(flat.flat, flat.grad, flat.exp_avg, flat.exp_avg_sq, flat.step, lr,
                               eps=1e-5, max_norm=a.max_grad_norm, world_size=self.world_size,
                               norm_out=self.grad_norm)
+                if hasattr(agent, "params_updated"):
+                    agent.params_updated()
                 k += 1
             if a.target_kl is not None:
                 approx_kl = self.stats[k - 1, 4].item()

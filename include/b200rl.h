@@ -45,6 +45,16 @@ const char* b200rl_last_error(void);
 /* compute capability the kernels were compiled for (100 = sm_100a) */
 int b200rl_compiled_arch(void);
 
+/* Optional per-kernel timing: when enabled, every kernel launch below is bracketed by CUDA events
+ * on its stream.  b200rl_profile_summary synchronises the device and writes a JSON array
+ * [{"name","launches","ms","flops","bytes"}] (algorithmic flops/bytes per kernel family) into buf.
+ * Do not enable during CUDA-graph capture. */
+/* number of kernels this library has launched in this process (host-side counter) */
+long long b200rl_launch_count(void);
+void b200rl_profile_enable(int on);
+void b200rl_profile_reset(void);
+int b200rl_profile_summary(char* buf, size_t capacity);
+
 /* ---------------------------------------------------------------- GAE -----
  * Reverse-scan generalised advantage estimation over a (T x N) rollout.
  * Replaces the python loop cleanrl/ppo.py:218-231 (identical in
@@ -177,6 +187,37 @@ size_t b200rl_linear_bwd_weight_workspace_bytes(int64_t n, int in_features, int 
 int b200rl_linear_bwd_weight_f32(const float* x, const int64_t* rows, const float* dy, float* dw, float* db,
                                  int64_t n, int in_features, int out_features,
                                  void* workspace, size_t workspace_bytes, void* stream);
+
+/* ------------------------------------------- NatureCNN, bf16 tensor cores ---
+ * The throughput path of Agent.network/actor/critic (cleanrl/ppo_atari_envpool.py:123-149):
+ * every conv / linear contraction (forward, data-gradient, weight-gradient) is an implicit GEMM
+ * on tcgen05.mma with bf16 operands and fp32 accumulation in TMEM; the uint8 frames are gathered
+ * (optionally through minibatch indices) and converted inside the conv1 kernels; the two heads
+ * (A+1 outputs) run in fp32 on CUDA cores.
+ *
+ * params / grads: ONE flat f32 vector in libb200rl order
+ *     conv1.w[32,4,8,8] conv1.b[32] conv2.w[64,32,4,4] conv2.b[64] conv3.w[64,64,3,3] conv3.b[64]
+ *     fc.w[512,3136] fc.b[512] actor.w[A,512] critic.w[1,512] actor.b[A] critic.b[1]
+ *   (each tensor in torch's own element order; b200rl_naturecnn_param_count(A) elements).
+ * packed : bf16 GEMM operand copies of the weights (b200rl_naturecnn_bf16_packed_bytes), refreshed
+ *          by b200rl_naturecnn_bf16_pack after every optimiser step.
+ * acts   : activation + activation-gradient workspace for batch n (b200rl_naturecnn_bf16_acts_bytes);
+ *          forward fills it, backward consumes it.
+ * obs    : uint8 [*, 4, 84, 84]; rows (i64 [n], may be NULL) selects the samples (ppo.py:250 gather).
+ * head_out / dhead : f32 [n, A+1] = [logits | value] and its gradient.
+ */
+int64_t b200rl_naturecnn_param_count(int A);
+size_t b200rl_naturecnn_bf16_packed_bytes(int A);
+size_t b200rl_naturecnn_bf16_acts_bytes(int64_t n);
+size_t b200rl_naturecnn_bf16_workspace_bytes(int64_t n, int A);
+int b200rl_naturecnn_bf16_pack(const float* params, int A, void* packed, void* stream);
+int b200rl_naturecnn_bf16_forward(const uint8_t* obs, const int64_t* rows, int64_t n, int A,
+                                  const float* params, const void* packed, void* acts,
+                                  float* head_out, void* stream);
+int b200rl_naturecnn_bf16_backward(const uint8_t* obs, const int64_t* rows, int64_t n, int A,
+                                   const float* params, const void* packed, void* acts,
+                                   const float* dhead, float* grads,
+                                   void* workspace, size_t workspace_bytes, void* stream);
 
 #ifdef __cplusplus
 }

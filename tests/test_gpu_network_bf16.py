@@ -1,0 +1,122 @@
+"""-m gpu: bf16 tcgen05 NatureCNN path vs a torch fp32 reference of the same network
+(floating-point kernel => torch fp32 reference; tolerance = bf16 operand rounding, stated per check).
+
+Layer-by-layer: the activation workspace is read back and compared against torch's NCHW activations
+permuted to NHWC, then every parameter gradient against autograd."""
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+pytestmark = pytest.mark.gpu
+
+
+def _rel(a, b):
+    a = a.detach().float().cpu().double(); b = b.detach().float().cpu().double()
+    return ((a - b).norm() / max(b.norm().item(), 1e-30)).item()
+
+
+def _maxrel(a, b):
+    a = a.detach().float().cpu().double(); b = b.detach().float().cpu().double()
+    return ((a - b).abs().max() / max(b.abs().max().item(), 1e-30)).item()
+
+
+class _Envs:
+    def __init__(self, A):
+        from cleanrl_b200.synthetic_envs import Box, Discrete
+        self.single_observation_space = Box(0, 255, (4, 84, 84), np.uint8)
+        self.single_action_space = Discrete(A)
+
+
+def _bf16_round(t):
+    return t.to(torch.bfloat16).float()
+
+
+@pytest.mark.parametrize("n,B,A", [(24, 64, 4), (130, 130, 6), (1, 3, 4)])
+def test_bf16_forward_backward_layerwise(lib, n, B, A):
+    from cleanrl_b200.agents import NatureCNNAgent
+    torch.manual_seed(1)
+    agent = NatureCNNAgent(_Envs(A)).cuda()
+    agent.precision = "bf16"
+    agent.flat
+    sd = {k: v.detach().cpu().clone() for k, v in agent.state_dict().items()}
+    g = torch.Generator().manual_seed(2)
+    obs = torch.randint(0, 256, (B, 4, 84, 84), dtype=torch.uint8, generator=g)
+    rows = torch.randperm(B, generator=g)[:n]
+    # ---- torch reference with bf16-rounded weights and activations (what the kernels compute), fp32 accumulate
+    W = {k: (_bf16_round(v) if k.startswith("network") and k.endswith("weight") else v.clone()).requires_grad_(True)
+         for k, v in sd.items()}
+    x = obs[rows].float()
+    a1 = torch.relu(F.conv2d(x, W["network.0.weight"], None, stride=4) / 255.0 + W["network.0.bias"].view(1, -1, 1, 1))
+    a1r = a1 + (_bf16_round(a1) - a1).detach()
+    a2 = torch.relu(F.conv2d(a1r, W["network.2.weight"], W["network.2.bias"], stride=2))
+    a2r = a2 + (_bf16_round(a2) - a2).detach()
+    a3 = torch.relu(F.conv2d(a2r, W["network.4.weight"], W["network.4.bias"], stride=1))
+    a3r = a3 + (_bf16_round(a3) - a3).detach()
+    hid = torch.relu(F.linear(a3r.flatten(1), W["network.7.weight"], W["network.7.bias"]))
+    hidr = hid + (_bf16_round(hid) - hid).detach()
+    logits = F.linear(hidr, W["actor.weight"], W["actor.bias"])
+    value = F.linear(hidr, W["critic.weight"], W["critic.bias"])
+    # ---- kernels
+    lg, val = agent.forward_train(obs.cuda(), rows.cuda())
+    torch.cuda.synchronize()
+    acts = agent._tc.acts(n).view(torch.bfloat16)
+    o = 0
+    got = {}
+    for name, shape in (("act1", (n, 20, 20, 32)), ("act2", (n, 9, 9, 64)), ("act3", (n, 7, 7, 64)), ("hid", (n, 512))):
+        cnt = int(np.prod(shape))
+        got[name] = acts[o:o + cnt].view(shape).float().cpu()
+        o += cnt
+    errs = {
+        "act1": _maxrel(got["act1"], a1.permute(0, 2, 3, 1)),
+        "act2": _maxrel(got["act2"], a2.permute(0, 2, 3, 1)),
+        "act3": _maxrel(got["act3"], a3.permute(0, 2, 3, 1)),
+        "hid": _maxrel(got["hid"], hid),
+        "logits": _maxrel(lg, logits),
+        "value": _maxrel(val, value[:, 0]),
+    }
+    print("forward max-rel errors:", errs)
+    # bf16 output rounding = 2^-9 relative per element; accumulated differences stay below 1e-2 of the tensor max
+    for k, v in errs.items():
+        assert v < 1e-2, (k, errs)
+    # ---- backward
+    gl = torch.randn(n, A, generator=g)
+    gv = torch.randn(n, generator=g)
+    dhead, dl, dv = agent.alloc_head_grad(n, torch.device("cuda"))
+    dl.copy_(gl); dv.copy_(gv)
+    agent.backward(dhead)
+    torch.cuda.synchronize()
+    ((logits * gl).sum() + (value[:, 0] * gv).sum()).backward()
+    gerrs = {}
+    for k, p in agent.named_parameters():
+        gerrs[k] = _rel(p.grad, W[k].grad)
+    print("gradient rel-L2 errors:", gerrs)
+    # activation gradients are rounded to bf16 between layers (2^-9 each): 2e-2 relative L2 per tensor
+    for k, v in gerrs.items():
+        assert v < 2e-2, (k, gerrs)
+    # intermediate activation gradients (diagnostics for layer-level failures)
+    o = n * (12800 + 5184 + 3136 + 512)
+    dgot = {}
+    for name, shape in (("dhid", (n, 512)), ("dact3", (n, 7, 7, 64)), ("dact2", (n, 9, 9, 64)), ("dact1", (n, 20, 20, 32))):
+        cnt = int(np.prod(shape))
+        dgot[name] = acts[o:o + cnt].view(shape).float().cpu()
+        o += cnt
+    assert torch.isfinite(dgot["dact1"]).all()
+
+
+def test_bf16_rollout_path_matches_fp32_path(lib):
+    """Same agent, same frames: the tensor-core path and the exact fp32 path agree to bf16 accuracy,
+    and with identical noise they sample the same actions except where p/q is within bf16 error."""
+    from cleanrl_b200.agents import NatureCNNAgent
+    torch.manual_seed(5)
+    agent = NatureCNNAgent(_Envs(4)).cuda()
+    obs = torch.randint(0, 256, (1024, 4, 84, 84), dtype=torch.uint8).cuda()
+    q = torch.empty(1024, 4, device="cuda").exponential_(1)
+    agent.noise_fn = lambda n, A, d: q
+    agent.precision = "fp32"
+    a32, lp32, _, v32 = agent.get_action_and_value(obs)
+    agent.precision = "bf16"
+    a16, lp16, _, v16 = agent.get_action_and_value(obs)
+    assert (v32 - v16).abs().max().item() < 2e-2 * max(1.0, v32.abs().max().item())
+    assert (lp32 - lp16).abs().max().item() < 2e-2
+    assert (a32 != a16).float().mean().item() < 0.02
