@@ -112,7 +112,7 @@ def measured_peaks():
 def run_ours(opt):
     import torch
     import torch.distributed as dist
-    from cleanrl_b200 import _lib, build
+    from cleanrl_b200 import _lib, build, ops
     from cleanrl_b200.agents import NatureCNNAgent
     from cleanrl_b200.ppo_engine import PPOEngine
     from cleanrl_b200.synthetic_envs import SyntheticAtariVec
@@ -183,7 +183,10 @@ def run_ours(opt):
             eng.policy_step_resident(step, pool_dev[step % P])
         eng.rewards.copy_(eng_rewards)
         eng.dones.copy_(eng_dones)
-        eng.next_obs.copy_(pool_dev[T % P])
+        if eng.s2d:
+            ops.frames_to_s2d(pool_dev[T % P], out=eng.next_obs)
+        else:
+            eng.next_obs.copy_(pool_dev[T % P])
         eng.finish_rollout(None, None, resident=True)
         return eng.update(lr_now())
 

@@ -44,11 +44,12 @@ SIGNATURES = {
     "b200rl_linear_bwd_weight_f32": (_i, [_p, _p, _p, _p, _p, _i64, _i, _i, _p, _sz, _p]),
     "b200rl_naturecnn_param_count": (_i64, [_i]),
     "b200rl_naturecnn_bf16_packed_bytes": (_sz, [_i]),
-    "b200rl_naturecnn_bf16_acts_bytes": (_sz, [_i64]),
+    "b200rl_naturecnn_bf16_acts_bytes": (_sz, [_i64, _i]),
+    "b200rl_frames_to_s2d_bf16": (_i, [_p, _p, _i64, _p, _p]),
     "b200rl_naturecnn_bf16_workspace_bytes": (_sz, [_i64, _i]),
     "b200rl_naturecnn_bf16_pack": (_i, [_p, _i, _p, _p]),
-    "b200rl_naturecnn_bf16_forward": (_i, [_p, _p, _i64, _i, _p, _p, _p, _p, _p]),
-    "b200rl_naturecnn_bf16_backward": (_i, [_p, _p, _i64, _i, _p, _p, _p, _p, _p, _p, _sz, _p]),
+    "b200rl_naturecnn_bf16_forward": (_i, [_p, _i, _p, _i64, _i, _p, _p, _p, _p, _p]),
+    "b200rl_naturecnn_bf16_backward": (_i, [_p, _i, _p, _i64, _i, _p, _p, _p, _p, _p, _p, _sz, _p]),
 }
 
 _lib = None

@@ -156,7 +156,7 @@ class NatureCNNAgent(KernelAgent):
 
     def _forward_heads(self, x, rows=None, keep=False):
         if self.precision == "bf16":
-            if x.dtype != torch.uint8:
+            if x.dtype not in (torch.uint8, torch.bfloat16):
                 x = x.to(torch.uint8)       # frames are integers 0..255 (reference passes them as fp32)
             tc = self._tc_plan()
             out = tc.forward(x.contiguous(), rows, self._flat.flat)

@@ -59,7 +59,7 @@ struct KGemmParams {
 __device__ __forceinline__ int4 ldg16(const void* p) { return __ldg(reinterpret_cast<const int4*>(p)); }
 
 // ------------------------------------------------------------------ kernel 1
-template <int BN, int STAGES, bool A_U8>
+template <int BN, int STAGES>
 __global__ void __launch_bounds__(128) tc_gemm_kmajor(const KGemmParams p) {
     constexpr int A_BYTES = 128 * 128;
     constexpr int B_BYTES = BN * 128;
@@ -87,37 +87,24 @@ __global__ void __launch_bounds__(128) tc_gemm_kmajor(const KGemmParams p) {
     tc_fence_after_sync();
     const uint32_t tmem_d = tmem_base_smem;
 
-    // ---- per-thread row contexts (fixed for the whole K loop)
-    // generic loader: 8 threads per row (one 16-B chunk each), rows tid/8 + 16*pass
-    // uint8 loader : one thread per row
+    // ---- per-thread row contexts (fixed for the whole K loop): 8 threads per row (one 16-byte chunk
+    // each), rows tid/8 + 16*pass
     int64_t boff[8];
     int pos[8];   // (ys << 16) | xs, or -1 when the row is out of range
-    const uint8_t* u8base = nullptr;
-    if (A_U8) {
-        const int64_t r = row0 + tid;
+#pragma unroll
+    for (int ps = 0; ps < 8; ++ps) {
+        const int64_t r = row0 + ps * 16 + (tid >> 3);
         if (r < p.M) {
             const int64_t i = r / p.rpi;
             const int rem = (int)(r - i * p.rpi);
-            const int oy = rem / p.Ws, ox = rem - oy * p.Ws;
-            const int64_t img = p.rows ? p.rows[i] : i;
-            u8base = reinterpret_cast<const uint8_t*>(p.A) + img * (int64_t)(p.CP * p.SH * p.SW) +
-                     (int64_t)(oy * p.sy) * p.SW + ox * p.sx;
-        }
-    } else {
-#pragma unroll
-        for (int ps = 0; ps < 8; ++ps) {
-            const int64_t r = row0 + ps * 16 + (tid >> 3);
-            if (r < p.M) {
-                const int64_t i = r / p.rpi;
-                const int rem = (int)(r - i * p.rpi);
-                const int y = rem / p.Ws, x = rem - y * p.Ws;
-                const int ys = y * p.sy, xs = x * p.sx;
-                boff[ps] = ((i * p.SH + ys) * p.SW + xs) * (int64_t)p.CP;
-                pos[ps] = (ys << 16) | xs;
-            } else {
-                boff[ps] = 0;
-                pos[ps] = -1;
-            }
+            const int y = rem / p.Ws, x = rem - y * p.Ws;
+            const int ys = y * p.sy, xs = x * p.sx;
+            const int64_t img = p.rows ? __ldg(p.rows + i) : i;
+            boff[ps] = ((img * p.SH + ys) * p.SW + xs) * (int64_t)p.CP;
+            pos[ps] = (ys << 16) | xs;
+        } else {
+            boff[ps] = 0;
+            pos[ps] = -1;
         }
     }
     const int ppc = 64 / p.CP;   // source pixels covered by one 64-element chunk
@@ -130,25 +117,7 @@ __global__ void __launch_bounds__(128) tc_gemm_kmajor(const KGemmParams p) {
         uint8_t* sA = smem + s * STAGE_BYTES;
         uint8_t* sB = sA + A_BYTES;
         // ---- stage A chunk j
-        if (A_U8) {
-            // chunk j = input channel j: 8 (ky) x 8 (kx) bytes -> 8 x 16-byte bf16 chunks of this thread's row
-            const uint8_t* src = u8base ? u8base + (int64_t)j * p.SH * p.SW : nullptr;
-#pragma unroll
-            for (int ky = 0; ky < 8; ++ky) {
-                uint32_t w0 = 0, w1 = 0;
-                if (src) {
-                    const uint32_t* q = reinterpret_cast<const uint32_t*>(src + ky * p.SW);
-                    w0 = __ldg(q);
-                    w1 = __ldg(q + 1);
-                }
-                int4 v;
-                v.x = (int)pack_bf16x2((float)(w0 & 0xFF), (float)((w0 >> 8) & 0xFF));
-                v.y = (int)pack_bf16x2((float)((w0 >> 16) & 0xFF), (float)(w0 >> 24));
-                v.z = (int)pack_bf16x2((float)(w1 & 0xFF), (float)((w1 >> 8) & 0xFF));
-                v.w = (int)pack_bf16x2((float)((w1 >> 16) & 0xFF), (float)(w1 >> 24));
-                *reinterpret_cast<int4*>(sA + img_off(tid, ky)) = v;
-            }
-        } else {
+        {
             const int dyj = p.dy[j], dxj = p.dx[j];
             const int64_t doff = ((int64_t)dyj * p.SW + dxj) * p.CP + (tid & 7) * 8;
 #pragma unroll
@@ -241,18 +210,270 @@ __global__ void __launch_bounds__(128) tc_gemm_kmajor(const KGemmParams p) {
     if (warp == 0) tmem_dealloc(tmem_d, TMEM_COLS);
 }
 
-template <int BN, int STAGES, bool A_U8>
+
+// ------------------------------------------------------------------ kernel 1b: persistent, warp-specialised
+// Same GEMM as tc_gemm_kmajor, restructured so that global-load latency never stalls the tensor core:
+//   * one persistent CTA per SM walks tiles blockIdx.x, +gridDim.x, ...;
+//   * ALL weight chunks of the layer stay resident in shared memory (<= 72 KB);
+//   * warps 0-3 (producers) stream the gathered A chunks with cp.async into a STAGES-deep ring and keep
+//     LOOKAHEAD chunks in flight per thread; a chunk is published on full[s] after cp.async.wait_group +
+//     fence.proxy.async;
+//   * warp 4 (one lane) issues tcgen05.mma; tcgen05.commit frees ring slots (empty[s]) and publishes the
+//     accumulator (tmem_full[a]);
+//   * warps 5-8 drain TMEM (double-buffered accumulators) -> bias/ReLU/mask -> bf16 NHWC, overlapping the
+//     next tile's MMAs.
+template <int BN, int STAGES, bool WRES>
+__global__ void __launch_bounds__(288, 1) tc_gemm_ws(const KGemmParams p, int total_tiles, int ntiles_n) {
+    constexpr int LOOKAHEAD = STAGES - 2;      // chunks in flight per producer thread
+    static_assert(LOOKAHEAD >= 1, "ring must be deeper than the cp.async lookahead");
+    constexpr int A_BYTES = 128 * 128;
+    constexpr int B_CHUNK = BN * 128;
+    constexpr uint32_t TMEM_COLS = (2 * BN) < 32 ? 32 : 2 * BN;
+    extern __shared__ uint8_t smem_raw[];
+    __shared__ uint64_t full_bar[STAGES], empty_bar[STAGES], tfull_bar[2], tempty_bar[2];
+    __shared__ uint32_t tmem_base_smem;
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    const int tid = threadIdx.x, warp = tid >> 5;
+    const int nch = p.nchunks;
+    const int K = nch * 64;
+    // WRES: all weight chunks resident + ring of A chunks; otherwise every ring stage = A chunk + B chunk
+    constexpr int STAGE_BYTES = WRES ? A_BYTES : A_BYTES + B_CHUNK;
+    uint8_t* sW = smem;                                                        // [nclasses][nch][BN rows x 128 B]
+    uint8_t* sRing = smem + (WRES ? (size_t)p.nclasses * nch * B_CHUNK : 0);   // STAGES x STAGE_BYTES
+
+    if (tid == 0) {
+        for (int s = 0; s < STAGES; ++s) { mbar_init(&full_bar[s], 128); mbar_init(&empty_bar[s], 1); }
+        for (int a = 0; a < 2; ++a) { mbar_init(&tfull_bar[a], 1); mbar_init(&tempty_bar[a], 128); }
+        fence_barrier_init();
+    }
+    if (warp == 4) tmem_alloc(&tmem_base_smem, TMEM_COLS);
+    // resident weights (generic-proxy stores, made visible to the async proxy once)
+    for (int idx = tid; WRES && idx < p.nclasses * nch * BN * 8; idx += blockDim.x) {
+        const int c16 = idx & 7;
+        int t = idx >> 3;
+        const int r = t % BN; t /= BN;
+        const int j = t % nch; const int cls = t / nch;
+        int4 v = make_int4(0, 0, 0, 0);
+        if (r < p.N) v = ldg16(p.Bw + (int64_t)cls * p.b_class_stride + (int64_t)r * K + j * 64 + c16 * 8);
+        *reinterpret_cast<int4*>(sW + ((size_t)cls * nch + j) * B_CHUNK + img_off(r, c16)) = v;
+    }
+    fence_proxy_async_smem();
+    tc_fence_before_sync();
+    __syncthreads();
+    tc_fence_after_sync();
+    const uint32_t tmem_d = tmem_base_smem;
+    const int ppc = 64 / p.CP;
+
+    if (warp < 4) {
+        // ======================= producers =======================
+        const int c16 = tid & 7;
+        uint32_t q = 0;          // flat chunk counter of this CTA
+        for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+            const int mt = tile / ntiles_n, n0 = (tile - mt * ntiles_n) * BN;
+            const int cls = mt / p.tiles_per_class;
+            const int row0 = (mt - cls * p.tiles_per_class) * 128;
+            (void)cls; (void)n0;
+            int64_t boff[8];
+            int pos[8];
+#pragma unroll
+            for (int ps = 0; ps < 8; ++ps) {
+                const int r = row0 + ps * 16 + (tid >> 3);
+                if (r < (int)p.M) {
+                    const int i = r / p.rpi;
+                    const int rem = r - i * p.rpi;
+                    const int y = rem / p.Ws, x = rem - y * p.Ws;
+                    const int ys = y * p.sy, xs = x * p.sx;
+                    const int64_t img = p.rows ? __ldg(p.rows + i) : (int64_t)i;
+                    boff[ps] = ((img * p.SH + ys) * p.SW + xs) * (int64_t)p.CP;
+                    pos[ps] = (ys << 16) | xs;
+                } else {
+                    boff[ps] = 0;
+                    pos[ps] = -1;
+                }
+            }
+            for (int j = 0; j < nch; ++j, ++q) {
+                const uint32_t s = q % STAGES;
+                if (q >= (uint32_t)STAGES) mbar_wait(&empty_bar[s], ((q / STAGES) - 1) & 1);
+                const uint32_t sA = smem_u32(sRing + (size_t)s * STAGE_BYTES);
+                const int dyj = p.dy[j], dxj = p.dx[j];
+                const int64_t doff = ((int64_t)dyj * p.SW + dxj) * p.CP + c16 * 8;
+#pragma unroll
+                for (int ps = 0; ps < 8; ++ps) {
+                    bool ok = pos[ps] >= 0;
+                    if (ok && p.check) {
+                        const int yy = (pos[ps] >> 16) + dyj, xx = (pos[ps] & 0xFFFF) + dxj;
+                        ok = (yy >= 0) && (yy < p.SH) && (xx >= 0) && (xx + ppc <= p.SW);
+                    }
+                    const bf16* src = reinterpret_cast<const bf16*>(p.A) + (ok ? boff[ps] + doff : 0);
+                    cp_async16(sA + img_off(ps * 16 + (tid >> 3), c16), src, ok ? 16u : 0u);
+                }
+                if (!WRES) {
+#pragma unroll
+                    for (int ps = 0; ps < BN / 16; ++ps) {
+                        const int r = ps * 16 + (tid >> 3);
+                        const bool ok = n0 + r < p.N;
+                        const bf16* src = p.Bw + (ok ? (int64_t)(n0 + r) * K + j * 64 + c16 * 8 : 0);
+                        cp_async16(sA + A_BYTES + img_off(r, c16), src, ok ? 16u : 0u);
+                    }
+                }
+                cp_async_commit();
+                if (q >= (uint32_t)LOOKAHEAD) {
+                    cp_async_wait<LOOKAHEAD>();
+                    fence_proxy_async_smem();
+                    mbar_arrive(&full_bar[(q - LOOKAHEAD) % STAGES]);
+                }
+            }
+        }
+        // drain the last LOOKAHEAD chunks
+        cp_async_wait<0>();
+        fence_proxy_async_smem();
+        for (uint32_t d = (q >= (uint32_t)LOOKAHEAD ? q - LOOKAHEAD : 0); d < q; ++d) mbar_arrive(&full_bar[d % STAGES]);
+    } else if (warp == 4) {
+        // ======================= MMA issuer =======================
+        if ((tid & 31) == 0) {
+            constexpr uint32_t idesc = make_idesc(128, BN, 0, 0);
+            uint32_t q = 0, t = 0;
+            for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++t) {
+                const int mt = tile / ntiles_n;
+                const int cls = mt / p.tiles_per_class;
+                const uint32_t acc = t & 1;
+                if (t >= 2) mbar_wait(&tempty_bar[acc], ((t >> 1) - 1) & 1);
+                tc_fence_after_sync();
+                const uint32_t d_addr = tmem_d + acc * BN;
+                for (int j = 0; j < nch; ++j, ++q) {
+                    const uint32_t s = q % STAGES;
+                    mbar_wait(&full_bar[s], (q / STAGES) & 1);
+                    tc_fence_after_sync();
+                    const uint32_t stage_addr = smem_u32(sRing + (size_t)s * STAGE_BYTES);
+                    const uint64_t adesc = desc_kmajor(stage_addr);
+                    const uint64_t bdesc = WRES ? desc_kmajor(smem_u32(sW + ((size_t)cls * nch + j) * B_CHUNK))
+                                                : desc_kmajor(stage_addr + A_BYTES);
+#pragma unroll
+                    for (int kk = 0; kk < 4; ++kk)
+                        umma_bf16(d_addr, adesc + 2 * kk, bdesc + 2 * kk, idesc, (j | kk) != 0);
+                    umma_commit(&empty_bar[s]);
+                }
+                umma_commit(&tfull_bar[acc]);
+            }
+        }
+    } else {
+        // ======================= epilogue =======================
+        const int ew = warp & 3;                    // TMEM lane quadrant this warp may access
+        const int lrow = ew * 32 + (tid & 31);      // accumulator row handled by this thread
+        uint32_t t = 0;
+        for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++t) {
+            const int mt = tile / ntiles_n, n0 = (tile - mt * ntiles_n) * BN;
+            const int cls = mt / p.tiles_per_class;
+            const int row0 = (mt - cls * p.tiles_per_class) * 128;
+            const uint32_t acc = t & 1;
+            const int r = row0 + lrow;
+            const bool rvalid = r < (int)p.M;
+            int64_t ooff = 0;
+            if (rvalid) {
+                const int i = r / p.rpi;
+                const int rem = r - i * p.rpi;
+                const int y = rem / p.Ws, x = rem - y * p.Ws;
+                const int ooy = p.nclasses > 1 ? (cls >> 1) : 0, oox = p.nclasses > 1 ? (cls & 1) : 0;
+                ooff = (((int64_t)i * p.OH + y * p.osy + ooy) * p.OW + x * p.osx + oox) * (int64_t)p.ldo;
+            }
+            mbar_wait(&tfull_bar[acc], (t >> 1) & 1);
+            tc_fence_after_sync();
+            const uint32_t lane_addr = tmem_d + acc * BN + ((uint32_t)(ew * 32) << 16);
+#pragma unroll 1
+            for (int c0 = 0; c0 < BN; c0 += 16) {
+                uint32_t v[16];
+                tmem_ld16(lane_addr + c0, v);
+                tmem_ld_wait();
+                const int col = n0 + c0;
+                if (!rvalid || col >= p.N) continue;
+                float f[16];
+                if (p.bias) {
+                    const float4* bp = reinterpret_cast<const float4*>(p.bias + col);
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) {
+                        const float4 bv = __ldg(bp + e);
+                        f[4 * e] = fmaf(__uint_as_float(v[4 * e]), p.scale, bv.x);
+                        f[4 * e + 1] = fmaf(__uint_as_float(v[4 * e + 1]), p.scale, bv.y);
+                        f[4 * e + 2] = fmaf(__uint_as_float(v[4 * e + 2]), p.scale, bv.z);
+                        f[4 * e + 3] = fmaf(__uint_as_float(v[4 * e + 3]), p.scale, bv.w);
+                    }
+                } else {
+#pragma unroll
+                    for (int e = 0; e < 16; ++e) f[e] = __uint_as_float(v[e]) * p.scale;
+                }
+                if (p.relu) {
+#pragma unroll
+                    for (int e = 0; e < 16; ++e) f[e] = fmaxf(f[e], 0.f);
+                }
+                if (p.mask) {
+                    const int4 m0 = ldg16(p.mask + ooff + col);
+                    const int4 m1 = ldg16(p.mask + ooff + col + 8);
+                    const uint32_t mw[8] = {(uint32_t)m0.x, (uint32_t)m0.y, (uint32_t)m0.z, (uint32_t)m0.w,
+                                            (uint32_t)m1.x, (uint32_t)m1.y, (uint32_t)m1.z, (uint32_t)m1.w};
+#pragma unroll
+                    for (int e = 0; e < 8; ++e) {
+                        if ((mw[e] & 0x7FFFu) == 0u) f[2 * e] = 0.f;
+                        if ((mw[e] & 0x7FFF0000u) == 0u) f[2 * e + 1] = 0.f;
+                    }
+                }
+                int4 o0, o1;
+                o0.x = (int)pack_bf16x2(f[0], f[1]);   o0.y = (int)pack_bf16x2(f[2], f[3]);
+                o0.z = (int)pack_bf16x2(f[4], f[5]);   o0.w = (int)pack_bf16x2(f[6], f[7]);
+                o1.x = (int)pack_bf16x2(f[8], f[9]);   o1.y = (int)pack_bf16x2(f[10], f[11]);
+                o1.z = (int)pack_bf16x2(f[12], f[13]); o1.w = (int)pack_bf16x2(f[14], f[15]);
+                int4* dst = reinterpret_cast<int4*>(p.out + ooff + col);
+                dst[0] = o0;
+                dst[1] = o1;
+            }
+            tc_fence_before_sync();
+            mbar_arrive(&tempty_bar[acc]);
+        }
+    }
+    tc_fence_before_sync();
+    __syncthreads();
+    if (warp == 4) tmem_dealloc(tmem_d, TMEM_COLS);
+}
+
+static int g_num_sms = 0;
+static int num_sms() {
+    if (g_num_sms == 0) {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        if (cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || g_num_sms <= 0) g_num_sms = 148;
+    }
+    return g_num_sms;
+}
+
+template <int BN, int STAGES, bool WRES>
+static int launch_kgemm_ws(const KGemmParams& p, cudaStream_t s, const char* what) {
+    const size_t smem = (WRES ? (size_t)p.nclasses * p.nchunks * BN * 128 + (size_t)STAGES * 128 * 128
+                             : (size_t)STAGES * (128 * 128 + BN * 128)) + 1024;
+    static size_t attr = 0;
+    if (smem > attr) {
+        cudaError_t e = cudaFuncSetAttribute(tc_gemm_ws<BN, STAGES, WRES>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return fail(B200RL_ERR_CUDA, "%s: smem attribute (%zu B): %s", what, smem, cudaGetErrorString(e));
+        attr = smem;
+    }
+    const int ntn = WRES ? 1 : (int)ceil_div(p.N, BN);
+    const int total = p.tiles_per_class * p.nclasses * ntn;
+    int grid = num_sms();
+    if (grid > total) grid = total;
+    tc_gemm_ws<BN, STAGES, WRES><<<grid, 288, smem, s>>>(p, total, ntn);
+    return check_launch(what);
+}
+
+template <int BN, int STAGES>
 static int launch_kgemm(const KGemmParams& p, cudaStream_t s, const char* what) {
     const size_t smem = (size_t)STAGES * (128 * 128 + BN * 128) + 1024;
     static bool attr_done = false;
     if (!attr_done) {
-        cudaError_t e = cudaFuncSetAttribute(tc_gemm_kmajor<BN, STAGES, A_U8>,
+        cudaError_t e = cudaFuncSetAttribute(tc_gemm_kmajor<BN, STAGES>,
                                              cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return fail(B200RL_ERR_CUDA, "%s: smem attribute: %s", what, cudaGetErrorString(e));
         attr_done = true;
     }
     dim3 grid((unsigned)(p.tiles_per_class * p.nclasses), (unsigned)ceil_div(p.N, BN));
-    tc_gemm_kmajor<BN, STAGES, A_U8><<<grid, 128, smem, s>>>(p);
+    tc_gemm_kmajor<BN, STAGES><<<grid, 128, smem, s>>>(p);
     return check_launch(what);
 }
 
@@ -271,7 +492,6 @@ struct WGradParams {
     float* ws;              // [gridDim.x][gridDim.y*nxc*64][gridDim.z*nyc*64] fp32
 };
 
-template <bool A_U8>
 __global__ void __launch_bounds__(128) tc_wgrad(const WGradParams p) {
     constexpr int R = 32;            // reduction rows per stage (2 MMAs of K = 16)
     constexpr int STAGES = 3;
@@ -304,7 +524,7 @@ __global__ void __launch_bounds__(128) tc_wgrad(const WGradParams p) {
     const int64_t m_begin = (int64_t)blockIdx.x * p.rows_per_cta;
     int64_t m_end = m_begin + p.rows_per_cta;
     if (m_end > g.M) m_end = g.M;
-    const int ppc = 64 / (A_U8 ? 64 : g.CP);
+    const int ppc = 64 / g.CP;
     const uint32_t idesc = make_idesc(128, NY, 1, 1);
     int it = 0;
     for (int64_t m0 = m_begin; m0 < m_end; m0 += R, ++it) {
@@ -313,39 +533,7 @@ __global__ void __launch_bounds__(128) tc_wgrad(const WGradParams p) {
         uint8_t* sX = smem + s * stage_bytes;
         uint8_t* sY = sX + nxc * chunk_img;
         // ---- X side: R rows x nxc chunks
-        if (A_U8) {
-            // thread -> (row = tid & 31, ky pair = tid >> 5): each thread converts 2 ky rows of every channel chunk
-            const int rr = tid & 31;
-            const int64_t r = m0 + rr;
-            const uint8_t* base = nullptr;
-            if (r < m_end) {
-                const int64_t i = r / g.rpi;
-                const int rem = (int)(r - i * g.rpi);
-                const int oy = rem / g.Ws, ox = rem - oy * g.Ws;
-                const int64_t img = g.rows ? g.rows[i] : i;
-                base = reinterpret_cast<const uint8_t*>(g.A) + img * (int64_t)(g.CP * g.SH * g.SW) +
-                       (int64_t)(oy * g.sy) * g.SW + ox * g.sx;
-            }
-            for (int c = 0; c < nxc; ++c) {
-                const int ch = xc0 + c;
-#pragma unroll
-                for (int q = 0; q < 2; ++q) {
-                    const int ky = (tid >> 5) * 2 + q;
-                    uint32_t w0 = 0, w1 = 0;
-                    if (base && ch < g.nchunks) {
-                        const uint32_t* src = reinterpret_cast<const uint32_t*>(base + (int64_t)ch * g.SH * g.SW + ky * g.SW);
-                        w0 = __ldg(src);
-                        w1 = __ldg(src + 1);
-                    }
-                    int4 v;
-                    v.x = (int)pack_bf16x2((float)(w0 & 0xFF), (float)((w0 >> 8) & 0xFF));
-                    v.y = (int)pack_bf16x2((float)((w0 >> 16) & 0xFF), (float)(w0 >> 24));
-                    v.z = (int)pack_bf16x2((float)(w1 & 0xFF), (float)((w1 >> 8) & 0xFF));
-                    v.w = (int)pack_bf16x2((float)((w1 >> 16) & 0xFF), (float)(w1 >> 24));
-                    *reinterpret_cast<int4*>(sX + c * chunk_img + img_off(rr, ky)) = v;
-                }
-            }
-        } else {
+        {
             // 8 threads per row, 16 rows per pass, 2 passes for R = 32
 #pragma unroll
             for (int ps = 0; ps < R / 16; ++ps) {
@@ -359,7 +547,8 @@ __global__ void __launch_bounds__(128) tc_wgrad(const WGradParams p) {
                     const int rem = (int)(r - i * g.rpi);
                     const int y = rem / g.Ws, x = rem - y * g.Ws;
                     ys = y * g.sy; xs = x * g.sx;
-                    bo = ((i * g.SH + ys) * g.SW + xs) * (int64_t)g.CP;
+                    const int64_t img = g.rows ? __ldg(g.rows + i) : i;
+                    bo = ((img * g.SH + ys) * g.SW + xs) * (int64_t)g.CP;
                 }
                 for (int c = 0; c < nxc; ++c) {
                     const int ch = xc0 + c;
@@ -437,10 +626,155 @@ __global__ void __launch_bounds__(128) tc_wgrad(const WGradParams p) {
     if (warp == 0) tmem_dealloc(tmem_d, tmem_cols);
 }
 
+// ------------------------------------------------------------------ kernel 2b: warp-specialised weight gradient
+// Same math as tc_wgrad; warps 0-3 stream the X/Y row images with cp.async (LOOKAHEAD steps in flight),
+// warp 4 issues the MMAs, and warps 0-3 write the fp32 partial tile at the end.
+__global__ void __launch_bounds__(160, 1) tc_wgrad_ws(const WGradParams p) {
+    constexpr int R = 32;
+    constexpr int STAGES = 4, LOOKAHEAD = 2;
+    extern __shared__ uint8_t smem_raw[];
+    __shared__ uint64_t full_bar[STAGES], empty_bar[STAGES], done_bar;
+    __shared__ uint32_t tmem_base_smem;
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    const int tid = threadIdx.x, warp = tid >> 5;
+    const KGemmParams& g = p.x;
+    const int nxc = p.nxc, nyc = p.nyc;
+    const int NY = nyc * 64;
+    const int xc0 = blockIdx.y * nxc, yc0 = blockIdx.z * nyc;
+    const int xt = nxc / 2;
+    const int chunk_img = R * 128;
+    const int stage_bytes = (nxc + nyc) * chunk_img;
+    uint32_t tmem_cols = 32;
+    while ((int)tmem_cols < xt * NY) tmem_cols <<= 1;
+
+    if (tid == 0) {
+        for (int s = 0; s < STAGES; ++s) { mbar_init(&full_bar[s], 128); mbar_init(&empty_bar[s], 1); }
+        mbar_init(&done_bar, 1);
+        fence_barrier_init();
+    }
+    if (warp == 4) tmem_alloc(&tmem_base_smem, tmem_cols);
+    tc_fence_before_sync();
+    __syncthreads();
+    tc_fence_after_sync();
+    const uint32_t tmem_d = tmem_base_smem;
+
+    const int64_t m_begin = (int64_t)blockIdx.x * p.rows_per_cta;
+    int64_t m_end = m_begin + p.rows_per_cta;
+    if (m_end > g.M) m_end = g.M;
+    const int nsteps = m_end > m_begin ? (int)((m_end - m_begin + R - 1) / R) : 0;
+    const int ppc = 64 / g.CP;
+
+    if (warp < 4) {
+        const int c16 = tid & 7;
+        for (int it = 0; it < nsteps; ++it) {
+            const int s = it % STAGES;
+            if (it >= STAGES) mbar_wait(&empty_bar[s], ((it / STAGES) - 1) & 1);
+            const uint32_t sX = smem_u32(smem + (size_t)s * stage_bytes);
+            const uint32_t sY = sX + nxc * chunk_img;
+            const int64_t m0 = m_begin + (int64_t)it * R;
+#pragma unroll
+            for (int ps = 0; ps < R / 16; ++ps) {
+                const int rr = ps * 16 + (tid >> 3);
+                const int64_t r = m0 + rr;
+                const bool rok = r < m_end;
+                int64_t bo = 0;
+                int ys = 0, xs = 0;
+                if (rok) {
+                    const int ri = (int)r;
+                    const int i = ri / g.rpi;
+                    const int rem = ri - i * g.rpi;
+                    const int y = rem / g.Ws, x = rem - y * g.Ws;
+                    ys = y * g.sy; xs = x * g.sx;
+                    const int64_t img = g.rows ? __ldg(g.rows + i) : (int64_t)i;
+                    bo = ((img * g.SH + ys) * g.SW + xs) * (int64_t)g.CP;
+                }
+                const uint32_t roff = img_off(rr, c16);
+                for (int c = 0; c < nxc; ++c) {
+                    const int ch = xc0 + c;
+                    bool ok = rok && ch < g.nchunks;
+                    int64_t off = 0;
+                    if (ok) {
+                        const int dyj = g.dy[ch], dxj = g.dx[ch];
+                        if (g.check) {
+                            const int yy = ys + dyj, xx = xs + dxj;
+                            ok = (yy >= 0) && (yy < g.SH) && (xx >= 0) && (xx + ppc <= g.SW);
+                        }
+                        off = bo + ((int64_t)dyj * g.SW + dxj) * g.CP + c16 * 8;
+                    }
+                    cp_async16(sX + c * chunk_img + roff, reinterpret_cast<const bf16*>(g.A) + (ok ? off : 0), ok ? 16u : 0u);
+                }
+                for (int c = 0; c < nyc; ++c) {
+                    const int col = (yc0 + c) * 64 + c16 * 8;
+                    const bool ok = rok && col < p.ncolsY;
+                    cp_async16(sY + c * chunk_img + roff, p.Y + (ok ? r * (int64_t)p.ldy + col : 0), ok ? 16u : 0u);
+                }
+            }
+            cp_async_commit();
+            if (it >= LOOKAHEAD) {
+                cp_async_wait<LOOKAHEAD>();
+                fence_proxy_async_smem();
+                mbar_arrive(&full_bar[(it - LOOKAHEAD) % STAGES]);
+            }
+        }
+        cp_async_wait<0>();
+        fence_proxy_async_smem();
+        for (int d = (nsteps >= LOOKAHEAD ? nsteps - LOOKAHEAD : 0); d < nsteps; ++d) mbar_arrive(&full_bar[d % STAGES]);
+    } else if ((tid & 31) == 0) {
+        const uint32_t idesc = make_idesc(128, NY, 1, 1);
+        for (int it = 0; it < nsteps; ++it) {
+            const int s = it % STAGES;
+            mbar_wait(&full_bar[s], (it / STAGES) & 1);
+            tc_fence_after_sync();
+            const uint32_t xa = smem_u32(smem + (size_t)s * stage_bytes), ya = xa + nxc * chunk_img;
+            for (int t = 0; t < xt; ++t) {
+#pragma unroll
+                for (int kk = 0; kk < R / 16; ++kk) {
+                    const uint64_t adesc = desc_mnmajor(xa + (2 * t) * chunk_img + kk * 2048, chunk_img);
+                    const uint64_t bdesc = desc_mnmajor(ya + kk * 2048, chunk_img);
+                    umma_bf16(tmem_d + t * NY, adesc, bdesc, idesc, (it | kk) != 0);
+                }
+            }
+            umma_commit(&empty_bar[s]);
+        }
+        umma_commit(&done_bar);
+    }
+    if (warp < 4) {
+        // ---- epilogue: fp32 partials ws[cta][kidx][co]
+        if (nsteps > 0) {
+            mbar_wait(&done_bar, 0);
+            tc_fence_after_sync();
+        }
+        const int64_t KXtot = (int64_t)gridDim.y * nxc * 64, NYtot = (int64_t)gridDim.z * NY;
+        float* wsb = p.ws + (int64_t)blockIdx.x * KXtot * NYtot;
+        const uint32_t lane_addr = tmem_d + ((uint32_t)(warp * 32) << 16);
+        for (int t = 0; t < xt; ++t) {
+            float* dst = wsb + ((int64_t)xc0 * 64 + t * 128 + tid) * NYtot + (int64_t)yc0 * 64;
+            for (int c0 = 0; c0 < NY; c0 += 16) {
+                uint32_t v[16];
+                if (nsteps > 0) {
+                    tmem_ld16(lane_addr + t * NY + c0, v);
+                    tmem_ld_wait();
+                } else {
+#pragma unroll
+                    for (int e = 0; e < 16; ++e) v[e] = 0u;
+                }
+#pragma unroll
+                for (int e = 0; e < 16; e += 4)
+                    *reinterpret_cast<float4*>(dst + c0 + e) = make_float4(__uint_as_float(v[e]), __uint_as_float(v[e + 1]),
+                                                                             __uint_as_float(v[e + 2]), __uint_as_float(v[e + 3]));
+            }
+        }
+    }
+    tc_fence_before_sync();
+    __syncthreads();
+    if (warp == 4) tmem_dealloc(tmem_d, tmem_cols);
+}
+
 // fold partials ws[S][KX][NY] -> fp32 gradient in the REFERENCE's parameter layout.
 // mode 0: dst[co][k] (conv1: K order (c,ky,kx) == torch's)                      src (k, co)
 // mode 1: dst[co][c][ky][kx] from K order (ky,kx,c) with C channels, KK taps       src (k, co)
 // mode 2: dst[o][c*49 + p] from X-side = o (rows), Y-side k = p*64 + c (fc)         src (o, k)
+// mode 3: conv1 on space-to-depth frames (K order (a,b,c,sy,sx))                    src (k, co)
 __global__ void tc_fold_kernel(const float* __restrict__ ws, int S, int KX, int NY, int validX, int validY,
                                int mode, int C, int KK, float scale, float* __restrict__ dst) {
     const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -457,23 +791,51 @@ __global__ void tc_fold_kernel(const float* __restrict__ ws, int S, int KX, int 
     } else if (mode == 1) {
         const int tap = xi / C, c = xi - tap * C;          // xi = tap*C + c
         o = ((int64_t)yi * C + c) * KK + tap;
-    } else {
+    } else if (mode == 2) {
         const int pp = yi / C, c = yi - pp * C;            // yi = p*64 + c ; torch flatten index = c*49 + p
         o = (int64_t)xi * validY + (int64_t)c * KK + pp;
+    } else {
+        // conv1 on space-to-depth frames: xi = (a*2+b)*64 + c*16 + sy*4 + sx -> dst[co][c][4a+sy][4b+sx]
+        const int tap = xi >> 6, rr = xi & 63;
+        const int c = rr >> 4, sy = (rr >> 2) & 3, sx = rr & 3;
+        o = (((int64_t)yi * 4 + c) * 8 + ((tap >> 1) * 4 + sy)) * 8 + (tap & 1) * 4 + sx;
     }
     dst[o] = s;
 }
 
-// column sums of a bf16 matrix [M, ld] (bias gradients): two-level deterministic reduction
+// column sums of a bf16 matrix [M, ld] (bias gradients): two-level deterministic reduction.
+// Block = 256 threads = (256 / (ncols/8)) row lanes x (ncols/8) column groups; every thread streams
+// 16-byte vectors (8 columns) down its rows, then the row lanes are folded through shared memory.
 __global__ void __launch_bounds__(256) tc_colsum_partial(const bf16* __restrict__ Y, int64_t M, int ld, int ncols,
                                                          int64_t rows_per_block, float* __restrict__ part) {
-    // thread -> column (ncols <= 512), loops over a row block; coalesced across columns
+    __shared__ float red[256 * 8];
+    const int cg = ncols >> 3;                 // column groups of 8
+    const int lanes = 256 / cg;                // row lanes per block
+    const int tx = threadIdx.x % cg, ty = threadIdx.x / cg;
     const int64_t r0 = (int64_t)blockIdx.x * rows_per_block;
     int64_t r1 = r0 + rows_per_block;
     if (r1 > M) r1 = M;
+    float acc[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) acc[e] = 0.f;
+    if (ty < lanes) {
+        for (int64_t r = r0 + ty; r < r1; r += lanes) {
+            const int4 v = ldg16(Y + r * ld + tx * 8);
+            const uint32_t w[4] = {(uint32_t)v.x, (uint32_t)v.y, (uint32_t)v.z, (uint32_t)v.w};
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                acc[2 * e] += __uint_as_float(w[e] << 16);
+                acc[2 * e + 1] += __uint_as_float(w[e] & 0xFFFF0000u);
+            }
+        }
+    }
+#pragma unroll
+    for (int e = 0; e < 8; ++e) red[threadIdx.x * 8 + e] = acc[e];
+    __syncthreads();
     for (int c = threadIdx.x; c < ncols; c += blockDim.x) {
+        const int g = c >> 3, e = c & 7;
         float s = 0.f;
-        for (int64_t r = r0; r < r1; ++r) s += __bfloat162float(Y[r * ld + c]);
+        for (int l = 0; l < lanes; ++l) s += red[(l * cg + g) * 8 + e];
         part[(int64_t)blockIdx.x * ncols + c] = s;
     }
 }
@@ -483,6 +845,33 @@ __global__ void tc_colsum_final(const float* __restrict__ part, int nblocks, int
     float s = 0.f;
     for (int b = 0; b < nblocks; ++b) s += part[(int64_t)b * ncols + c];
     db[c] = s;
+}
+
+// uint8 frames [n,4,84,84] (NCHW, as envpool delivers them) -> space-to-depth bf16 [n,21,21,64] with
+// channel = c*16 + sy*4 + sx for source pixel (4Y+sy, 4X+sx).  conv1 (8x8, stride 4) becomes a 2x2,
+// stride-1 convolution over 64-channel NHWC pixels, i.e. the same 128-byte-per-tap gather as conv2/conv3.
+// Done ONCE per environment step; the minibatch updates then read the bf16 rollout directly.
+__global__ void __launch_bounds__(256) tc_frames_to_s2d(const uint8_t* __restrict__ obs, const int64_t* __restrict__ rows,
+                                                        int64_t n, bf16* __restrict__ out) {
+    const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;    // ((i*21 + Y)*21 + X)*4 + c
+    if (idx >= n * 21 * 21 * 4) return;
+    const int c = (int)(idx & 3);
+    int64_t t = idx >> 2;
+    const int X = (int)(t % 21); t /= 21;
+    const int Y = (int)(t % 21);
+    const int64_t i = t / 21;
+    const int64_t img = rows ? rows[i] : i;
+    const uint8_t* src = obs + img * 28224 + c * 7056 + (Y * 4) * 84 + X * 4;
+    uint32_t o[8];
+#pragma unroll
+    for (int sy = 0; sy < 4; ++sy) {
+        const uint32_t w = __ldg(reinterpret_cast<const uint32_t*>(src + sy * 84));
+        o[2 * sy] = pack_bf16x2((float)(w & 0xFF), (float)((w >> 8) & 0xFF));
+        o[2 * sy + 1] = pack_bf16x2((float)((w >> 16) & 0xFF), (float)(w >> 24));
+    }
+    int4* dst = reinterpret_cast<int4*>(out + (idx >> 2) * 64 + c * 16);
+    dst[0] = make_int4((int)o[0], (int)o[1], (int)o[2], (int)o[3]);
+    dst[1] = make_int4((int)o[4], (int)o[5], (int)o[6], (int)o[7]);
 }
 
 // ------------------------------------------------------------------ weight packing (fp32 master -> bf16 GEMM operands)
@@ -501,6 +890,15 @@ __global__ void tc_pack_conv(const float* __restrict__ w, int Cout, int Cin, int
     if (nchw_k) fwd[(int64_t)co * K + (c * KH + ky) * KW + kx] = v;
     else fwd[(int64_t)co * K + (ky * KW + kx) * Cin + c] = v;
     if (dgrad) dgrad[(int64_t)c * (KH * KW * Cout) + (ky * KW + kx) * Cout + co] = v;
+}
+// conv1 weight w[co][c][ky][kx] (8x8) -> [co][(a,b), c*16 + sy*4 + sx] with ky = 4a+sy, kx = 4b+sx
+// (K order of the space-to-depth frames)
+__global__ void tc_pack_conv1_s2d(const float* __restrict__ w, bf16* __restrict__ fwd) {
+    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= 32 * 256) return;
+    const int kx = idx & 7, ky = (idx >> 3) & 7, c = (idx >> 6) & 3, co = idx >> 8;
+    const int a = ky >> 2, sy = ky & 3, b = kx >> 2, sx = kx & 3;
+    fwd[co * 256 + (a * 2 + b) * 64 + c * 16 + sy * 4 + sx] = __float2bfloat16(w[idx]);
 }
 // conv2 data-gradient weights per stride-parity class: dg[cls][c][(a,b,co)] = w[co][c][py+2a][px+2b]
 __global__ void tc_pack_conv_s2_classes(const float* __restrict__ w, int Cout, int Cin, bf16* __restrict__ dg) {
@@ -629,9 +1027,10 @@ struct NatureLayout {
 };
 
 struct NatureActs {   // bf16 element offsets inside the activation workspace for batch n
-    int64_t act1, act2, act3, hid, dhid, dact3, dact2, dact1, total;
-    explicit NatureActs(int64_t n) {
+    int64_t x0, act1, act2, act3, hid, dhid, dact3, dact2, dact1, total;
+    explicit NatureActs(int64_t n, bool with_x0 = true) {
         int64_t o = 0;
+        x0 = o; if (with_x0) o += n * 28224;     // space-to-depth frames (only when the caller passes uint8)
         act1 = o; o += n * 12800;
         act2 = o; o += n * 5184;
         act3 = o; o += n * 3136;
@@ -656,10 +1055,11 @@ static void set_rows(KGemmParams& p, int64_t M, int rpi, int Ws) {
     p.tiles_per_class = (int)ceil_div(M, 128);
 }
 
-static void conv1_gather(KGemmParams& p, const uint8_t* obs, const int64_t* rows, int64_t n) {
-    p.A = obs; p.rows = rows;
+static void conv1_gather(KGemmParams& p, const bf16* s2d, const int64_t* rows, int64_t n) {   // s2d [*,21,21,64]
+    p.A = s2d; p.rows = rows;
     set_rows(p, n * 400, 400, 20);
-    p.SH = 84; p.SW = 84; p.CP = 4; p.sy = p.sx = 4; p.nchunks = 4; p.check = 0;
+    p.SH = 21; p.SW = 21; p.CP = 64; p.nchunks = 4; p.check = 0;
+    for (int a = 0; a < 2; ++a) for (int b = 0; b < 2; ++b) { p.dy[a * 2 + b] = (signed char)a; p.dx[a * 2 + b] = (signed char)b; }
 }
 static void conv2_gather(KGemmParams& p, const bf16* act1, int64_t n) {
     p.A = act1;
@@ -691,32 +1091,31 @@ static WPlan wgrad_plan(int64_t M, int target_ctas) {
     if (w.splits < 1) w.splits = 1;
     return w;
 }
-static const int kC1Ctas = 444, kC2Ctas = 296, kC3Ctas = 148, kFcSplits = 8;
+static const int kC1Ctas = 296, kC2Ctas = 148, kC3Ctas = 148, kFcSplits = 8;
 
-template <bool A_U8>
 static int launch_wgrad(const WGradParams& p, dim3 grid, cudaStream_t s, const char* what) {
-    const size_t smem = (size_t)3 * (p.nxc + p.nyc) * 32 * 128 + 1024;
+    const size_t smem = (size_t)4 * (p.nxc + p.nyc) * 32 * 128 + 1024;
     static size_t attr = 0;
     if (smem > attr) {
-        cudaError_t e = cudaFuncSetAttribute(tc_wgrad<A_U8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        cudaError_t e = cudaFuncSetAttribute(tc_wgrad_ws, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return fail(B200RL_ERR_CUDA, "%s: smem attribute (%zu B): %s", what, smem, cudaGetErrorString(e));
         attr = smem;
     }
-    tc_wgrad<A_U8><<<grid, 128, smem, s>>>(p);
+    tc_wgrad_ws<<<grid, 160, smem, s>>>(p);
     return check_launch(what);
 }
 
 static int colsum(const bf16* Y, int64_t M, int ld, int ncols, float* part, float* db, cudaStream_t s) {
-    int64_t rpb = ceil_div(M, 148 * 4);
-    if (rpb < 16) rpb = 16;
+    int64_t rpb = ceil_div(M, 148 * 8);
+    if (rpb < 64) rpb = 64;
     const int nb = (int)ceil_div(M, rpb);
     tc_colsum_partial<<<nb, 256, 0, s>>>(Y, M, ld, ncols, rpb, part);
     tc_colsum_final<<<(unsigned)ceil_div(ncols, 128), 128, 0, s>>>(part, nb, ncols, db);
     return check_launch("colsum", 2);
 }
 static size_t colsum_ws(int64_t M, int ncols) {
-    int64_t rpb = ceil_div(M, 148 * 4);
-    if (rpb < 16) rpb = 16;
+    int64_t rpb = ceil_div(M, 148 * 8);
+    if (rpb < 64) rpb = 64;
     return (size_t)ceil_div(M, rpb) * ncols * sizeof(float);
 }
 
@@ -726,7 +1125,20 @@ using namespace b200rl;
 
 extern "C" int64_t b200rl_naturecnn_param_count(int A) { return A >= 1 ? NatureLayout(A).total : -1; }
 extern "C" size_t b200rl_naturecnn_bf16_packed_bytes(int A) { return A >= 1 ? (size_t)NatureLayout(A).packed_total * 2 : 0; }
-extern "C" size_t b200rl_naturecnn_bf16_acts_bytes(int64_t n) { return n >= 0 ? (size_t)NatureActs(n).total * 2 + 256 : 0; }
+extern "C" size_t b200rl_naturecnn_bf16_acts_bytes(int64_t n, int obs_format) {
+    return n >= 0 ? (size_t)NatureActs(n, obs_format == B200RL_OBS_U8_NCHW).total * 2 + 256 : 0;
+}
+
+extern "C" int b200rl_frames_to_s2d_bf16(const uint8_t* obs, const int64_t* rows, int64_t n, void* out, void* stream) {
+    B200RL_REQUIRE(n >= 0, "frames_to_s2d: negative n");
+    if (n == 0) return B200RL_OK;
+    B200RL_REQUIRE(obs && out, "frames_to_s2d: null pointer");
+    B200RL_REQUIRE(aligned(obs, 4) && aligned(out, 16), "frames_to_s2d: misaligned buffer");
+    cudaStream_t s = (cudaStream_t)stream;
+    ProfScope ps(s, "frames_to_s2d", 0, (double)n * 28224 * 3);
+    tc_frames_to_s2d<<<(unsigned)ceil_div(n * 1764, 256), 256, 0, s>>>(obs, rows, n, reinterpret_cast<bf16*>(out));
+    return check_launch("frames_to_s2d");
+}
 
 extern "C" size_t b200rl_naturecnn_bf16_workspace_bytes(int64_t n, int A) {
     if (n < 1 || A < 1) return 0;
@@ -750,7 +1162,7 @@ extern "C" int b200rl_naturecnn_bf16_pack(const float* params, int A, void* pack
     bf16* P = reinterpret_cast<bf16*>(packed);
     cudaStream_t s = (cudaStream_t)stream;
     ProfScope ps(s, "pack_weights", 0, (double)L.total * 4 + (double)L.packed_total * 2);
-    tc_pack_conv<<<(unsigned)ceil_div(8192, 256), 256, 0, s>>>(params + L.c1w, 32, 4, 8, 8, 1, P + L.w1f, nullptr);
+    tc_pack_conv1_s2d<<<32, 256, 0, s>>>(params + L.c1w, P + L.w1f);
     tc_pack_conv<<<(unsigned)ceil_div(32768, 256), 256, 0, s>>>(params + L.c2w, 64, 32, 4, 4, 0, P + L.w2f, nullptr);
     tc_pack_conv_s2_classes<<<(unsigned)ceil_div(32768, 256), 256, 0, s>>>(params + L.c2w, 64, 32, P + L.w2dg);
     tc_pack_conv<<<(unsigned)ceil_div(36864, 256), 256, 0, s>>>(params + L.c3w, 64, 64, 3, 3, 0, P + L.w3f, P + L.w3dg);
@@ -758,50 +1170,57 @@ extern "C" int b200rl_naturecnn_bf16_pack(const float* params, int A, void* pack
     return check_launch("naturecnn_pack", 5);
 }
 
-extern "C" int b200rl_naturecnn_bf16_forward(const uint8_t* obs, const int64_t* rows, int64_t n, int A,
+extern "C" int b200rl_naturecnn_bf16_forward(const void* obs, int obs_format, const int64_t* rows, int64_t n, int A,
                                              const float* params, const void* packed, void* acts,
                                              float* head_out, void* stream) {
     B200RL_REQUIRE(n >= 0, "naturecnn_forward: negative n");
     if (n == 0) return B200RL_OK;
     B200RL_REQUIRE(obs && params && packed && acts && head_out, "naturecnn_forward: null pointer");
     B200RL_REQUIRE(A >= 1 && A <= 7, "naturecnn_forward: A=%d outside [1,7]", A);
-    B200RL_REQUIRE(aligned(obs, 4) && aligned(acts, 16) && aligned(packed, 16), "naturecnn_forward: misaligned buffer");
+    B200RL_REQUIRE(obs_format == B200RL_OBS_U8_NCHW || obs_format == B200RL_OBS_S2D_BF16, "naturecnn_forward: bad obs_format %d", obs_format);
+    B200RL_REQUIRE(aligned(obs, 16) && aligned(acts, 16) && aligned(packed, 16), "naturecnn_forward: misaligned buffer");
     B200RL_REQUIRE(n <= (int64_t)1 << 22, "naturecnn_forward: n too large");
     const NatureLayout L(A);
-    const NatureActs Q(n);
+    const NatureActs Q(n, obs_format == B200RL_OBS_U8_NCHW);
     const bf16* P = reinterpret_cast<const bf16*>(packed);
     bf16* act = reinterpret_cast<bf16*>(acts);
     cudaStream_t s = (cudaStream_t)stream;
     int rc;
     KGemmParams p;
-    // conv1: uint8 frames -> act1 [n,20,20,32]
-    gemm_defaults(p); conv1_gather(p, obs, rows, n);
+    // conv1 on space-to-depth frames -> act1 [n,20,20,32]
+    const bf16* x0 = reinterpret_cast<const bf16*>(obs);
+    const int64_t* x0rows = rows;
+    if (obs_format == B200RL_OBS_U8_NCHW) {
+        if ((rc = b200rl_frames_to_s2d_bf16(reinterpret_cast<const uint8_t*>(obs), rows, n, act + Q.x0, stream))) return rc;
+        x0 = act + Q.x0; x0rows = nullptr;
+    }
+    gemm_defaults(p); conv1_gather(p, x0, x0rows, n);
     p.Bw = P + L.w1f; p.N = 32; p.out = act + Q.act1; p.OH = 20; p.OW = 20; p.ldo = 32;
     p.bias = params + L.c1b; p.scale = 1.0f / 255.0f; p.relu = 1;
-    { ProfScope ps(s, "conv1_fwd", 2.0 * n * 400 * 32 * 256, (double)n * (28224 + 12800 * 2));
-      if ((rc = launch_kgemm<32, 3, true>(p, s, "naturecnn/conv1"))) return rc; }
+    { ProfScope ps(s, "conv1_fwd", 2.0 * n * 400 * 32 * 256, (double)n * (28224 + 12800) * 2);
+      if ((rc = launch_kgemm_ws<32, 8, true>(p, s, "naturecnn/conv1"))) return rc; }
     // conv2 -> act2 [n,9,9,64]
     gemm_defaults(p); conv2_gather(p, act + Q.act1, n);
     p.Bw = P + L.w2f; p.N = 64; p.out = act + Q.act2; p.OH = 9; p.OW = 9; p.ldo = 64; p.bias = params + L.c2b; p.relu = 1;
     { ProfScope ps(s, "conv2_fwd", 2.0 * n * 81 * 64 * 512, (double)n * (12800 + 5184) * 2);
-      if ((rc = launch_kgemm<64, 3, false>(p, s, "naturecnn/conv2"))) return rc; }
+      if ((rc = launch_kgemm_ws<64, 8, true>(p, s, "naturecnn/conv2"))) return rc; }
     // conv3 -> act3 [n,7,7,64]
     gemm_defaults(p); conv3_gather(p, act + Q.act2, n);
     p.Bw = P + L.w3f; p.N = 64; p.out = act + Q.act3; p.OH = 7; p.OW = 7; p.ldo = 64; p.bias = params + L.c3b; p.relu = 1;
     { ProfScope ps(s, "conv3_fwd", 2.0 * n * 49 * 64 * 576, (double)n * (5184 + 3136) * 2);
-      if ((rc = launch_kgemm<64, 3, false>(p, s, "naturecnn/conv3"))) return rc; }
+      if ((rc = launch_kgemm_ws<64, 8, true>(p, s, "naturecnn/conv3"))) return rc; }
     // fc -> hidden [n,512]
     gemm_defaults(p); rowmajor_gather(p, act + Q.act3, n, 49);
     p.Bw = P + L.wfcf; p.N = 512; p.out = act + Q.hid; p.OH = 1; p.OW = 1; p.ldo = 512; p.bias = params + L.fcb; p.relu = 1;
     { ProfScope ps(s, "fc_fwd", 2.0 * n * 512 * 3136, (double)n * (3136 + 512) * 2 + 512.0 * 3136 * 2);
-      if ((rc = launch_kgemm<256, 2, false>(p, s, "naturecnn/fc"))) return rc; }
+      if ((rc = launch_kgemm_ws<256, 4, false>(p, s, "naturecnn/fc"))) return rc; }
     // heads (fp32 math on CUDA cores): head_out [n, A+1] = [logits | value]
     { ProfScope ps(s, "heads_fwd", 2.0 * n * 512 * (A + 1), (double)n * (1024 + 4 * (A + 1)));
       tc_heads_fwd<<<(unsigned)ceil_div(n, 8), 256, 0, s>>>(act + Q.hid, params + L.hw, params + L.hb, n, A + 1, 512, head_out); }
     return check_launch("naturecnn/heads");
 }
 
-extern "C" int b200rl_naturecnn_bf16_backward(const uint8_t* obs, const int64_t* rows, int64_t n, int A,
+extern "C" int b200rl_naturecnn_bf16_backward(const void* obs, int obs_format, const int64_t* rows, int64_t n, int A,
                                               const float* params, const void* packed, void* acts,
                                               const float* dhead, float* grads,
                                               void* workspace, size_t workspace_bytes, void* stream) {
@@ -811,11 +1230,15 @@ extern "C" int b200rl_naturecnn_bf16_backward(const uint8_t* obs, const int64_t*
     B200RL_REQUIRE(aligned(workspace, 16), "naturecnn_backward: workspace misaligned");
     const size_t need = b200rl_naturecnn_bf16_workspace_bytes(n, A);
     if (workspace_bytes < need) return fail(B200RL_ERR_WORKSPACE, "naturecnn_backward: workspace %zu < %zu", workspace_bytes, need);
+    B200RL_REQUIRE(obs_format == B200RL_OBS_U8_NCHW || obs_format == B200RL_OBS_S2D_BF16, "naturecnn_backward: bad obs_format %d", obs_format);
     const NatureLayout L(A);
-    const NatureActs Q(n);
+    const NatureActs Q(n, obs_format == B200RL_OBS_U8_NCHW);
     const bf16* P = reinterpret_cast<const bf16*>(packed);
     bf16* act = reinterpret_cast<bf16*>(acts);
     cudaStream_t s = (cudaStream_t)stream;
+    // uint8 input: forward left the space-to-depth frames of this minibatch in the workspace
+    const bf16* x0 = obs_format == B200RL_OBS_U8_NCHW ? act + Q.x0 : reinterpret_cast<const bf16*>(obs);
+    const int64_t* x0rows = obs_format == B200RL_OBS_U8_NCHW ? nullptr : rows;
     // workspace split: [wgrad partials | small partials]
     size_t big = 0;
     {
@@ -851,7 +1274,7 @@ extern "C" int b200rl_naturecnn_bf16_backward(const uint8_t* obs, const int64_t*
         const WPlan pl = wgrad_plan(n, kFcSplits);
         w.rows_per_cta = pl.rows_per_cta; w.ws = wsbig;
         { ProfScope ps(s, "fc_wgrad", 2.0 * n * 512 * 3136, (double)n * (3136 + 512) * 2 + 512.0 * 3136 * 4);
-          if ((rc = launch_wgrad<false>(w, dim3(pl.splits, 4, 13), s, "naturecnn/fc_wgrad"))) return rc; }
+          if ((rc = launch_wgrad(w, dim3(pl.splits, 4, 13), s, "naturecnn/fc_wgrad"))) return rc; }
         { ProfScope ps(s, "wgrad_fold_bias", 0, 0);
           note_launches(1); tc_fold_kernel<<<(unsigned)ceil_div((int64_t)512 * 3136, 256), 256, 0, s>>>(wsbig, pl.splits, 512, 13 * 256, 512, 3136, 2, 64, 49, 1.f, grads + L.fcw);
           if ((rc = colsum(act + Q.dhid, n, 512, 512, wssmall, grads + L.fcb, s))) return rc; }
@@ -859,7 +1282,7 @@ extern "C" int b200rl_naturecnn_bf16_backward(const uint8_t* obs, const int64_t*
         gemm_defaults(p); rowmajor_gather(p, act + Q.dhid, n, 8);
         p.Bw = P + L.wfcdg; p.N = 3136; p.out = act + Q.dact3; p.OH = 1; p.OW = 1; p.ldo = 3136; p.mask = act + Q.act3;
         { ProfScope ps(s, "fc_dgrad", 2.0 * n * 512 * 3136, (double)n * (3136 * 2 + 512) * 2 + 512.0 * 3136 * 2);
-          if ((rc = launch_kgemm<256, 2, false>(p, s, "naturecnn/fc_dgrad"))) return rc; }
+          if ((rc = launch_kgemm_ws<256, 4, false>(p, s, "naturecnn/fc_dgrad"))) return rc; }
     }
     // ---- conv3
     {
@@ -869,7 +1292,7 @@ extern "C" int b200rl_naturecnn_bf16_backward(const uint8_t* obs, const int64_t*
         const WPlan pl = wgrad_plan(n * 49, kC3Ctas);
         w.rows_per_cta = pl.rows_per_cta; w.ws = wsbig;
         { ProfScope ps(s, "conv3_wgrad", 2.0 * n * 49 * 64 * 576, (double)n * (5184 + 3136) * 2);
-          if ((rc = launch_wgrad<false>(w, dim3(pl.splits, 1, 1), s, "naturecnn/conv3_wgrad"))) return rc; }
+          if ((rc = launch_wgrad(w, dim3(pl.splits, 1, 1), s, "naturecnn/conv3_wgrad"))) return rc; }
         { ProfScope ps(s, "wgrad_fold_bias", 0, 0);
           note_launches(1); tc_fold_kernel<<<(unsigned)ceil_div(576 * 64, 256), 256, 0, s>>>(wsbig, pl.splits, 640, 64, 576, 64, 1, 64, 9, 1.f, grads + L.c3w);
           if ((rc = colsum(act + Q.dact3, n * 49, 64, 64, wssmall, grads + L.c3b, s))) return rc; }
@@ -880,7 +1303,7 @@ extern "C" int b200rl_naturecnn_bf16_backward(const uint8_t* obs, const int64_t*
         for (int ky = 0; ky < 3; ++ky) for (int kx = 0; kx < 3; ++kx) { p.dy[ky * 3 + kx] = (signed char)-ky; p.dx[ky * 3 + kx] = (signed char)-kx; }
         p.Bw = P + L.w3dg; p.N = 64; p.out = act + Q.dact2; p.OH = 9; p.OW = 9; p.ldo = 64; p.mask = act + Q.act2;
         { ProfScope ps(s, "conv3_dgrad", 2.0 * n * 81 * 64 * 576, (double)n * (3136 + 5184 * 2) * 2);
-          if ((rc = launch_kgemm<64, 3, false>(p, s, "naturecnn/conv3_dgrad"))) return rc; }
+          if ((rc = launch_kgemm_ws<64, 8, true>(p, s, "naturecnn/conv3_dgrad"))) return rc; }
     }
     // ---- conv2
     {
@@ -890,7 +1313,7 @@ extern "C" int b200rl_naturecnn_bf16_backward(const uint8_t* obs, const int64_t*
         const WPlan pl = wgrad_plan(n * 81, kC2Ctas);
         w.rows_per_cta = pl.rows_per_cta; w.ws = wsbig;
         { ProfScope ps(s, "conv2_wgrad", 2.0 * n * 81 * 64 * 512, (double)n * (12800 + 5184) * 2);
-          if ((rc = launch_wgrad<false>(w, dim3(pl.splits, 1, 1), s, "naturecnn/conv2_wgrad"))) return rc; }
+          if ((rc = launch_wgrad(w, dim3(pl.splits, 1, 1), s, "naturecnn/conv2_wgrad"))) return rc; }
         { ProfScope ps(s, "wgrad_fold_bias", 0, 0);
           note_launches(1); tc_fold_kernel<<<(unsigned)ceil_div(512 * 64, 256), 256, 0, s>>>(wsbig, pl.splits, 512, 64, 512, 64, 1, 32, 16, 1.f, grads + L.c2w);
           if ((rc = colsum(act + Q.dact2, n * 81, 64, 64, wssmall, grads + L.c2b, s))) return rc; }
@@ -902,19 +1325,19 @@ extern "C" int b200rl_naturecnn_bf16_backward(const uint8_t* obs, const int64_t*
         p.Bw = P + L.w2dg; p.b_class_stride = 32 * 256; p.N = 32;
         p.out = act + Q.dact1; p.OH = 20; p.OW = 20; p.osy = 2; p.osx = 2; p.ldo = 32; p.mask = act + Q.act1;
         { ProfScope ps(s, "conv2_dgrad", 2.0 * n * 400 * 32 * 256, (double)n * (5184 + 12800 * 2) * 2);
-          if ((rc = launch_kgemm<32, 3, false>(p, s, "naturecnn/conv2_dgrad"))) return rc; }
+          if ((rc = launch_kgemm_ws<32, 8, true>(p, s, "naturecnn/conv2_dgrad"))) return rc; }
     }
     // ---- conv1 (no data gradient: the input is the observation)
     {
         memset(&w, 0, sizeof(w));
-        gemm_defaults(w.x); conv1_gather(w.x, obs, rows, n);
+        gemm_defaults(w.x); conv1_gather(w.x, x0, x0rows, n);
         w.Y = act + Q.dact1; w.ldy = 32; w.nyc = 1; w.ncolsY = 32; w.nxc = 4;
         const WPlan pl = wgrad_plan(n * 400, kC1Ctas);
         w.rows_per_cta = pl.rows_per_cta; w.ws = wsbig;
-        { ProfScope ps(s, "conv1_wgrad", 2.0 * n * 400 * 32 * 256, (double)n * (28224 + 12800 * 2));
-          if ((rc = launch_wgrad<true>(w, dim3(pl.splits, 1, 1), s, "naturecnn/conv1_wgrad"))) return rc; }
+        { ProfScope ps(s, "conv1_wgrad", 2.0 * n * 400 * 32 * 256, (double)n * (28224 + 12800) * 2);
+          if ((rc = launch_wgrad(w, dim3(pl.splits, 1, 1), s, "naturecnn/conv1_wgrad"))) return rc; }
         { ProfScope ps(s, "wgrad_fold_bias", 0, 0);
-          note_launches(1); tc_fold_kernel<<<(unsigned)ceil_div(256 * 32, 256), 256, 0, s>>>(wsbig, pl.splits, 256, 64, 256, 32, 0, 0, 0, 1.0f / 255.0f, grads + L.c1w);
+          note_launches(1); tc_fold_kernel<<<(unsigned)ceil_div(256 * 32, 256), 256, 0, s>>>(wsbig, pl.splits, 256, 64, 256, 32, 3, 0, 0, 1.0f / 255.0f, grads + L.c1w);
           if ((rc = colsum(act + Q.dact1, n * 400, 32, 32, wssmall, grads + L.c1b, s))) return rc; }
     }
     return B200RL_OK;

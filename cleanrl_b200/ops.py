@@ -306,13 +306,23 @@ class NatureCNNBf16:
         self._acts = {}
         self._ws = None
 
-    def acts(self, n):
+    def acts(self, n, fmt):
         lib = _lib.load()
-        if n not in self._acts:
+        key = (n, fmt)
+        if key not in self._acts:
             if len(self._acts) > 4:
                 self._acts.clear()
-            self._acts[n] = torch.empty(lib.b200rl_naturecnn_bf16_acts_bytes(n), dtype=torch.uint8, device=self.device)
-        return self._acts[n]
+            self._acts[key] = torch.empty(lib.b200rl_naturecnn_bf16_acts_bytes(n, fmt), dtype=torch.uint8, device=self.device)
+        return self._acts[key]
+
+    @staticmethod
+    def obs_format(obs):
+        if obs.dtype == torch.uint8 and tuple(obs.shape[-3:]) == (4, 84, 84):
+            return 0
+        if obs.dtype == torch.bfloat16 and tuple(obs.shape[-3:]) == (21, 21, 64):
+            return 1
+        raise TypeError("bf16 NatureCNN path consumes uint8 [*,4,84,84] frames or space-to-depth bf16 "
+                        f"[*,21,21,64] (got {obs.dtype} {tuple(obs.shape)})")
 
     def pack(self, flat_params):
         lib = _lib.load()
@@ -322,28 +332,41 @@ class NatureCNNBf16:
 
     def forward(self, obs, rows, flat_params, head_out=None):
         lib = _lib.load()
-        if obs.dtype != torch.uint8:
-            raise TypeError("the bf16 NatureCNN path consumes uint8 frames (got %s)" % obs.dtype)
+        fmt = self.obs_format(obs)
         _contig(obs, "obs")
         n = rows.numel() if rows is not None else obs.shape[0]
         if head_out is None:
             head_out = torch.empty(n, self.A + 1, dtype=torch.float32, device=self.device)
-        rc = lib.b200rl_naturecnn_bf16_forward(_ptr(obs, torch.uint8, "obs"), _ptr(rows, torch.int64, "rows", True), n, self.A,
+        rc = lib.b200rl_naturecnn_bf16_forward(_ptr(obs, None, "obs"), fmt, _ptr(rows, torch.int64, "rows", True), n, self.A,
                                                _ptr(flat_params, torch.float32, "params"), self.packed.data_ptr(),
-                                               self.acts(n).data_ptr(), _ptr(head_out, torch.float32, "head_out"), _stream())
+                                               self.acts(n, fmt).data_ptr(), _ptr(head_out, torch.float32, "head_out"), _stream())
         _lib.check(rc, "naturecnn_bf16_forward")
         return head_out
 
     def backward(self, obs, rows, flat_params, dhead, flat_grads):
         lib = _lib.load()
+        fmt = self.obs_format(obs)
         n = dhead.shape[0]
         _contig(dhead, "dhead")
         nbytes = lib.b200rl_naturecnn_bf16_workspace_bytes(n, self.A)
         if self._ws is None or self._ws.numel() < nbytes:
             self._ws = torch.empty(nbytes, dtype=torch.uint8, device=self.device)
-        rc = lib.b200rl_naturecnn_bf16_backward(_ptr(obs, torch.uint8, "obs"), _ptr(rows, torch.int64, "rows", True), n, self.A,
+        rc = lib.b200rl_naturecnn_bf16_backward(_ptr(obs, None, "obs"), fmt, _ptr(rows, torch.int64, "rows", True), n, self.A,
                                                 _ptr(flat_params, torch.float32, "params"), self.packed.data_ptr(),
-                                                self.acts(n).data_ptr(), _ptr(dhead, torch.float32, "dhead"),
+                                                self.acts(n, fmt).data_ptr(), _ptr(dhead, torch.float32, "dhead"),
                                                 _ptr(flat_grads, torch.float32, "grads"),
                                                 self._ws.data_ptr(), self._ws.numel(), _stream())
         _lib.check(rc, "naturecnn_bf16_backward")
+
+
+def frames_to_s2d(obs_u8, out=None, rows=None):
+    """uint8 [n,4,84,84] frames -> bf16 [n,21,21,64] space-to-depth frames (once per env step)."""
+    lib = _lib.load()
+    _contig(obs_u8, "obs")
+    n = rows.numel() if rows is not None else obs_u8.shape[0]
+    if out is None:
+        out = torch.empty(n, 21, 21, 64, dtype=torch.bfloat16, device=obs_u8.device)
+    rc = lib.b200rl_frames_to_s2d_bf16(_ptr(obs_u8, torch.uint8, "obs"), _ptr(rows, torch.int64, "rows", True), n,
+                                       _ptr(out, torch.bfloat16, "out"), _stream())
+    _lib.check(rc, "frames_to_s2d")
+    return out

@@ -31,10 +31,24 @@ def _torch_dtype(np_dtype):
     return torch.uint8 if np.dtype(np_dtype) == np.uint8 else torch.float32
 
 
+def _pin(t):
+    """Page-lock a host staging buffer when a CUDA runtime exists (async H2D/D2H need it)."""
+    return t.pin_memory() if torch.cuda.is_available() else t
+
+
+def _sync():
+    if torch.cuda.is_available():
+        torch.cuda.current_stream().synchronize()
+
+
 class PPOEngine:
+    # The product path is CUDA-only.  The CPU test-suite (tests/cpu_backend.py) flips this to drive the
+    # host-side logic (sharding, seeding, flat-gradient all-reduce over gloo) with injected torch ops.
+    ALLOW_NON_CUDA_FOR_TESTS = False
+
     def __init__(self, agent, args, obs_shape, obs_dtype, num_envs, device, world_size=1, gae_mode=0,
                  all_reduce=None):
-        if device.type != "cuda":
+        if device.type != "cuda" and not PPOEngine.ALLOW_NON_CUDA_FOR_TESTS:
             raise RuntimeError("PPOEngine drives libb200rl CUDA kernels and needs a CUDA device; "
                                "there is no CPU fallback (got device=%s)" % device)
         self.agent, self.args, self.device = agent, args, device
@@ -48,7 +62,16 @@ class PPOEngine:
         T, N = self.T, self.N
         self.obs_dtype = _torch_dtype(obs_dtype)
         f32 = torch.float32
-        self.obs = torch.zeros((T, N) + tuple(obs_shape), dtype=self.obs_dtype, device=device)
+        # bf16 tensor-core path on Atari frames: the rollout is stored ONCE as space-to-depth bf16
+        # [T,N,21,21,64] (converted per env step from the uint8 staging batch); every minibatch pass
+        # then gathers 128-byte pixels directly -- no per-minibatch uint8 decode, no fp32 obs.
+        self.s2d = (getattr(agent, "precision", "fp32") == "bf16" and self.obs_dtype == torch.uint8
+                    and tuple(obs_shape) == (4, 84, 84) and device.type == "cuda")
+        if self.s2d:
+            self.obs = torch.zeros((T, N, 21, 21, 64), dtype=torch.bfloat16, device=device)
+            self.obs_u8 = torch.zeros((N,) + tuple(obs_shape), dtype=torch.uint8, device=device)
+        else:
+            self.obs = torch.zeros((T, N) + tuple(obs_shape), dtype=self.obs_dtype, device=device)
         self.actions = torch.zeros((T, N), dtype=torch.int64, device=device)
         self.logprobs = torch.zeros((T, N), dtype=f32, device=device)
         self.values = torch.zeros((T, N), dtype=f32, device=device)
@@ -56,21 +79,21 @@ class PPOEngine:
         self.dones = torch.zeros((T, N), dtype=f32, device=device)
         self.advantages = torch.zeros((T, N), dtype=f32, device=device)
         self.returns = torch.zeros((T, N), dtype=f32, device=device)
-        self.next_obs = torch.zeros((N,) + tuple(obs_shape), dtype=self.obs_dtype, device=device)
+        self.next_obs = torch.zeros_like(self.obs[0])
         self.next_done = torch.zeros(N, dtype=f32, device=device)
         self.next_value = torch.zeros(N, dtype=f32, device=device)
         # pinned host mirrors
-        self.rewards_h = torch.zeros((T, N), dtype=f32).pin_memory()
-        self.dones_h = torch.zeros((T, N), dtype=f32).pin_memory()
-        self.next_done_h = torch.zeros(N, dtype=f32).pin_memory()
-        self.actions_h = torch.zeros(N, dtype=torch.int64).pin_memory()
-        self.obs_stage_h = torch.zeros((N,) + tuple(obs_shape), dtype=self.obs_dtype).pin_memory()
+        self.rewards_h = _pin(torch.zeros((T, N), dtype=f32))
+        self.dones_h = _pin(torch.zeros((T, N), dtype=f32))
+        self.next_done_h = _pin(torch.zeros(N, dtype=f32))
+        self.actions_h = _pin(torch.zeros(N, dtype=torch.int64))
+        self.obs_stage_h = _pin(torch.zeros((N,) + tuple(obs_shape), dtype=self.obs_dtype))
         E = int(args.update_epochs)
-        self.b_inds_h = torch.zeros((E, self.B), dtype=torch.int64).pin_memory()   # one slot per epoch: a pinned
+        self.b_inds_h = _pin(torch.zeros((E, self.B), dtype=torch.int64))   # one slot per epoch: a pinned
         self.b_inds = torch.zeros((E, self.B), dtype=torch.int64, device=device)  # source is never rewritten in flight
         n_upd = int(args.update_epochs) * self.num_minibatches
         self.stats = torch.zeros(max(n_upd, 1), 16, dtype=f32, device=device)
-        self.stats_h = torch.zeros(max(n_upd, 1), 16, dtype=f32).pin_memory()
+        self.stats_h = _pin(torch.zeros(max(n_upd, 1), 16, dtype=f32))
         self.grad_norm = torch.zeros(1, dtype=f32, device=device)
         self.flat = agent.flat
         self.h2d_bytes = 0
@@ -85,7 +108,11 @@ class PPOEngine:
         if not src.is_pinned():
             self.obs_stage_h.copy_(src)
             src = self.obs_stage_h
-        dst.copy_(src, non_blocking=True)
+        if self.s2d:
+            self.obs_u8.copy_(src, non_blocking=True)
+            ops.frames_to_s2d(self.obs_u8, out=dst)
+        else:
+            dst.copy_(src, non_blocking=True)
         self.h2d_bytes += src.numel() * src.element_size()
 
     @torch.no_grad()
@@ -101,14 +128,17 @@ class PPOEngine:
                                out=(self.actions[step], self.logprobs[step], None, self.values[step]))
         self.actions_h.copy_(self.actions[step], non_blocking=True)
         self.d2h_bytes += self.actions_h.numel() * 8
-        torch.cuda.current_stream().synchronize()
+        _sync()
         return self.actions_h.numpy()
 
     @torch.no_grad()
     def policy_step_resident(self, step, obs_dev, done_dev=None):
         """Device-resident variant (inputs already in HBM, no host round trip): used to measure the
         kernel-side throughput of the rollout step; actions stay on the device."""
-        self.obs[step].copy_(obs_dev)
+        if self.s2d and obs_dev.dtype == torch.uint8:
+            ops.frames_to_s2d(obs_dev, out=self.obs[step])
+        else:
+            self.obs[step].copy_(obs_dev)
         logits, value = self.agent._forward_heads(self.obs[step])
         n, A = logits.shape
         q = self.agent.noise_fn(n, A, self.device)
@@ -189,7 +219,7 @@ class PPOEngine:
                 if approx_kl > a.target_kl:
                     break
         self.stats_h[:k].copy_(self.stats[:k], non_blocking=True)
-        torch.cuda.current_stream().synchronize()
+        _sync()
         self.d2h_bytes += k * 64
         s = self.stats_h[:k].numpy()
         out = {name: float(s[k - 1, i]) for i, name in enumerate(STAT_NAMES)}

@@ -203,18 +203,25 @@ int b200rl_linear_bwd_weight_f32(const float* x, const int64_t* rows, const floa
  *          by b200rl_naturecnn_bf16_pack after every optimiser step.
  * acts   : activation + activation-gradient workspace for batch n (b200rl_naturecnn_bf16_acts_bytes);
  *          forward fills it, backward consumes it.
- * obs    : uint8 [*, 4, 84, 84]; rows (i64 [n], may be NULL) selects the samples (ppo.py:250 gather).
+ * obs    : obs_format B200RL_OBS_U8_NCHW  : uint8 [*, 4, 84, 84] frames as the env delivers them, or
+ *          obs_format B200RL_OBS_S2D_BF16 : bf16 [*, 21, 21, 64] space-to-depth frames produced ONCE per
+ *          env step by b200rl_frames_to_s2d_bf16 (channel = c*16 + sy*4 + sx of pixel (4Y+sy, 4X+sx)):
+ *          conv1 (8x8 stride 4) is then a 2x2 stride-1 convolution over 128-byte pixels and the 16
+ *          minibatch passes of an iteration never touch / convert the uint8 frames again.
+ *          rows (i64 [n], may be NULL) selects the samples (ppo.py:250 gather) in either format.
  * head_out / dhead : f32 [n, A+1] = [logits | value] and its gradient.
  */
+enum { B200RL_OBS_U8_NCHW = 0, B200RL_OBS_S2D_BF16 = 1 };
+int b200rl_frames_to_s2d_bf16(const uint8_t* obs, const int64_t* rows, int64_t n, void* out_s2d, void* stream);
 int64_t b200rl_naturecnn_param_count(int A);
 size_t b200rl_naturecnn_bf16_packed_bytes(int A);
-size_t b200rl_naturecnn_bf16_acts_bytes(int64_t n);
+size_t b200rl_naturecnn_bf16_acts_bytes(int64_t n, int obs_format);
 size_t b200rl_naturecnn_bf16_workspace_bytes(int64_t n, int A);
 int b200rl_naturecnn_bf16_pack(const float* params, int A, void* packed, void* stream);
-int b200rl_naturecnn_bf16_forward(const uint8_t* obs, const int64_t* rows, int64_t n, int A,
+int b200rl_naturecnn_bf16_forward(const void* obs, int obs_format, const int64_t* rows, int64_t n, int A,
                                   const float* params, const void* packed, void* acts,
                                   float* head_out, void* stream);
-int b200rl_naturecnn_bf16_backward(const uint8_t* obs, const int64_t* rows, int64_t n, int A,
+int b200rl_naturecnn_bf16_backward(const void* obs, int obs_format, const int64_t* rows, int64_t n, int A,
                                    const float* params, const void* packed, void* acts,
                                    const float* dhead, float* grads,
                                    void* workspace, size_t workspace_bytes, void* stream);

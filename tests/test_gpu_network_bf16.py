@@ -60,8 +60,11 @@ def test_bf16_forward_backward_layerwise(lib, n, B, A):
     # ---- kernels
     lg, val = agent.forward_train(obs.cuda(), rows.cuda())
     torch.cuda.synchronize()
-    acts = agent._tc.acts(n).view(torch.bfloat16)
-    o = 0
+    acts = agent._tc.acts(n, 0).view(torch.bfloat16)
+    o = n * 28224          # uint8 input: the workspace starts with the space-to-depth frames
+    x0 = acts[:o].view(n, 21, 21, 4, 4, 4).float().cpu()          # [n, Y, X, c, sy, sx]
+    ref0 = obs[rows].float().view(n, 4, 21, 4, 21, 4).permute(0, 2, 4, 1, 3, 5)
+    assert torch.equal(x0, ref0), "space-to-depth frames must be exact"
     got = {}
     for name, shape in (("act1", (n, 20, 20, 32)), ("act2", (n, 9, 9, 64)), ("act3", (n, 7, 7, 64)), ("hid", (n, 512))):
         cnt = int(np.prod(shape))
@@ -95,13 +98,36 @@ def test_bf16_forward_backward_layerwise(lib, n, B, A):
     for k, v in gerrs.items():
         assert v < 2e-2, (k, gerrs)
     # intermediate activation gradients (diagnostics for layer-level failures)
-    o = n * (12800 + 5184 + 3136 + 512)
+    o = n * (28224 + 12800 + 5184 + 3136 + 512)
     dgot = {}
     for name, shape in (("dhid", (n, 512)), ("dact3", (n, 7, 7, 64)), ("dact2", (n, 9, 9, 64)), ("dact1", (n, 20, 20, 32))):
         cnt = int(np.prod(shape))
         dgot[name] = acts[o:o + cnt].view(shape).float().cpu()
         o += cnt
     assert torch.isfinite(dgot["dact1"]).all()
+
+
+def test_s2d_input_equals_uint8_input(lib):
+    """Pre-converted space-to-depth frames (engine path) and raw uint8 frames (drop-in path) give identical
+    outputs and gradients, with and without the minibatch row gather."""
+    from cleanrl_b200 import ops
+    from cleanrl_b200.agents import NatureCNNAgent
+    torch.manual_seed(2)
+    agent = NatureCNNAgent(_Envs(4)).cuda()
+    agent.precision = "bf16"
+    B, n = 96, 40
+    obs = torch.randint(0, 256, (B, 4, 84, 84), dtype=torch.uint8).cuda()
+    rows = torch.randperm(B)[:n].cuda()
+    s2d = ops.frames_to_s2d(obs)
+    outs, grads = [], []
+    for x in (obs, s2d):
+        lg, v = agent.forward_train(x, rows)
+        dhead, dl, dv = agent.alloc_head_grad(n, torch.device("cuda"))
+        dl.copy_(torch.ones(n, 4, device="cuda") * 0.1); dv.copy_(torch.linspace(-1, 1, n, device="cuda"))
+        agent.backward(dhead)
+        outs.append((lg.clone(), v.clone())); grads.append(agent.flat.grad.clone())
+    assert torch.equal(outs[0][0], outs[1][0]) and torch.equal(outs[0][1], outs[1][1])
+    assert torch.equal(grads[0], grads[1])
 
 
 def test_bf16_rollout_path_matches_fp32_path(lib):

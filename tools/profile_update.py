@@ -1,0 +1,75 @@
+"""One PPO minibatch update (M = 32768, the BASELINE.json configs[1] minibatch) + a few rollout steps,
+for ncu: `ncu ... python tools/profile_update.py`.  Prints per-kernel CUDA-event times when run bare."""
+import json
+import sys
+import ctypes
+
+import numpy as np
+import torch
+
+sys.path.insert(0, ".")
+from bench import ppo_args  # noqa: E402
+from cleanrl_b200 import _lib, build, ops  # noqa: E402
+from cleanrl_b200.agents import NatureCNNAgent  # noqa: E402
+from cleanrl_b200.synthetic_envs import Box, Discrete  # noqa: E402
+
+build.build()
+lib = _lib.load()
+M = int(sys.argv[1]) if len(sys.argv) > 1 else 32768
+B = 4 * M
+reps = int(sys.argv[2]) if len(sys.argv) > 2 else 3
+
+
+class E:
+    single_observation_space = Box(0, 255, (4, 84, 84), np.uint8)
+    single_action_space = Discrete(4)
+
+
+torch.manual_seed(1)
+dev = torch.device("cuda:0")
+agent = NatureCNNAgent(E()).to(dev)
+agent.precision = "bf16"
+flat = agent.flat
+obs = torch.randint(0, 256, (B, 4, 84, 84), dtype=torch.uint8, device=dev)
+inds = torch.randperm(B, device=dev)[:M].contiguous()
+b_act = torch.randint(0, 4, (B,), device=dev)
+b_lp = torch.full((B,), -1.386, device=dev)
+b_adv = torch.randn(B, device=dev)
+b_ret = torch.randn(B, device=dev)
+b_val = torch.randn(B, device=dev)
+dhead, dl, dv = agent.alloc_head_grad(M, dev)
+stats = torch.zeros(16, device=dev)
+
+
+def minibatch(step):
+    logits, value = agent.forward_train(obs, inds)
+    ops.ppo_loss(logits, value, inds, b_act, b_lp, b_adv, b_ret, b_val, 0.1, 0.01, 0.5, dlogits=dl, dvalue=dv, stats=stats)
+    agent.backward(dhead)
+    ops.clip_adam(flat.flat, flat.grad, flat.exp_avg, flat.exp_avg_sq, step, 2.5e-4)
+    agent.params_updated()
+
+
+def rollout_step():
+    agent.get_action_and_value(obs[:1024])
+
+
+for i in range(2):
+    minibatch(i + 1)
+    rollout_step()
+torch.cuda.synchronize()
+lib.b200rl_profile_reset()
+lib.b200rl_profile_enable(1)
+for i in range(reps):
+    minibatch(i + 3)
+    rollout_step()
+lib.b200rl_profile_enable(0)
+buf = ctypes.create_string_buffer(1 << 16)
+lib.b200rl_profile_summary(buf, 1 << 16)
+rows = sorted(json.loads(buf.value.decode()), key=lambda r: -r["ms"])
+tot = sum(r["ms"] for r in rows)
+print(f"M={M}: total kernel ms per (minibatch + 1 rollout step) = {tot / reps:.3f}")
+for r in rows:
+    ms = r["ms"] / r["launches"]
+    tf = r["flops"] / r["launches"] / (ms * 1e-3) / 1e12 if r["flops"] else 0
+    gb = r["bytes"] / r["launches"] / (ms * 1e-3) / 1e9 if r["bytes"] else 0
+    print(f"  {r['name']:18s} x{r['launches'] // reps:3d}  {ms * 1e3:9.1f} us/launch  {tf:7.1f} TFLOP/s  {gb:7.1f} GB/s  share {r['ms'] / tot:5.1%}")
