@@ -242,8 +242,9 @@ __global__ void __launch_bounds__(288, 1) tc_gemm_ws(const KGemmParams p, int to
     uint8_t* sRing = smem + (WRES ? (size_t)p.nclasses * nch * B_CHUNK : 0);   // STAGES x STAGE_BYTES
 
     if (tid == 0) {
-        for (int s = 0; s < STAGES; ++s) { mbar_init(&full_bar[s], 128); mbar_init(&empty_bar[s], 1); }
-        for (int a = 0; a < 2; ++a) { mbar_init(&tfull_bar[a], 1); mbar_init(&tempty_bar[a], 128); }
+        // one arrival per producer / epilogue WARP (lane 0 after __syncwarp), not per thread
+        for (int s = 0; s < STAGES; ++s) { mbar_init(&full_bar[s], 4); mbar_init(&empty_bar[s], 1); }
+        for (int a = 0; a < 2; ++a) { mbar_init(&tfull_bar[a], 1); mbar_init(&tempty_bar[a], 4); }
         fence_barrier_init();
     }
     if (warp == 4) tmem_alloc(&tmem_base_smem, TMEM_COLS);
@@ -320,14 +321,17 @@ __global__ void __launch_bounds__(288, 1) tc_gemm_ws(const KGemmParams p, int to
                 if (q >= (uint32_t)LOOKAHEAD) {
                     cp_async_wait<LOOKAHEAD>();
                     fence_proxy_async_smem();
-                    mbar_arrive(&full_bar[(q - LOOKAHEAD) % STAGES]);
+                    __syncwarp();
+                    if ((tid & 31) == 0) mbar_arrive(&full_bar[(q - LOOKAHEAD) % STAGES]);
                 }
             }
         }
         // drain the last LOOKAHEAD chunks
         cp_async_wait<0>();
         fence_proxy_async_smem();
-        for (uint32_t d = (q >= (uint32_t)LOOKAHEAD ? q - LOOKAHEAD : 0); d < q; ++d) mbar_arrive(&full_bar[d % STAGES]);
+        __syncwarp();
+        if ((tid & 31) == 0)
+            for (uint32_t d = (q >= (uint32_t)LOOKAHEAD ? q - LOOKAHEAD : 0); d < q; ++d) mbar_arrive(&full_bar[d % STAGES]);
     } else if (warp == 4) {
         // ======================= MMA issuer =======================
         if ((tid & 31) == 0) {
@@ -426,7 +430,246 @@ __global__ void __launch_bounds__(288, 1) tc_gemm_ws(const KGemmParams p, int to
                 dst[1] = o1;
             }
             tc_fence_before_sync();
-            mbar_arrive(&tempty_bar[acc]);
+            __syncwarp();
+            if ((tid & 31) == 0) mbar_arrive(&tempty_bar[acc]);
+        }
+    }
+    tc_fence_before_sync();
+    __syncthreads();
+    if (warp == 4) tmem_dealloc(tmem_d, TMEM_COLS);
+}
+
+
+// ------------------------------------------------------------------ kernel 1c: "window" convolution
+// Stride-1 convolutions over activations stored as a LINEAR pixel grid [n*G rows, CPR*64 channels]
+// (G = Hp*Wp grid positions per image).  GEMM rows enumerate grid positions, so tap (dy,dx) of a row is
+// simply the row `dy*Wp+dx` further down: the CTA stages ONE window of 128+maxshift rows per tile and
+// every tap is a tcgen05 operand descriptor whose start address is shifted by whole 128-byte rows
+// (the SWIZZLE_128B pattern is a function of the shared-memory address bits, so any row shift is legal:
+// tools/experiments/umma_shift_test.cu).  Each activation row is therefore read from L2 once per tile
+// instead of once per tap, and the producers do no im2col index arithmetic at all.  Grid positions whose
+// window would leave the image (X >= vW or Y >= vH) are computed but not stored.
+enum { WOUT_DENSE = 0, WOUT_S2D2 = 1, WOUT_DACT2 = 2, WOUT_DACT1 = 3 };
+struct WinParams {
+    const bf16* A;           // [n*G, CPR*64]
+    const int64_t* rows;     // optional image gather (conv1 reads the rollout through mb_inds)
+    int64_t M;               // n*G
+    int n, G, Wp;
+    int ntaps;
+    int shift[16];           // dy*Wp + dx per tap (non-negative)
+    int WR;                  // window rows: 128 + max shift, rounded up to 8
+    const bf16* Bw;          // packed weights [N][ntaps*CPR*64]
+    int N;
+    int vH, vW;              // valid outputs: Y < vH && X < vW
+    int out_mode;
+    bf16* out;               // primary output
+    bf16* out2;              // WOUT_DACT2: padded 11x11 copy
+    const bf16* mask;        // ReLU mask source (layout depends on out_mode)
+    const float* bias;
+    float scale;
+    int relu;
+};
+
+template <int BN, int CPR, int STAGES>
+__global__ void __launch_bounds__(288, 1) tc_conv_win(const WinParams p, int total_tiles) {
+    constexpr int LOOKAHEAD = STAGES - 2;
+    constexpr int B_CHUNK = BN * 128;
+    constexpr uint32_t TMEM_COLS = (2 * BN) < 32 ? 32 : 2 * BN;
+    extern __shared__ uint8_t smem_raw[];
+    __shared__ uint64_t full_bar[STAGES], empty_bar[STAGES], tfull_bar[2], tempty_bar[2];
+    __shared__ uint32_t tmem_base_smem;
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    const int tid = threadIdx.x, warp = tid >> 5;
+    const int nchunks = p.ntaps * CPR;
+    const int K = nchunks * 64;
+    const int IMG = p.WR * 128;                 // one 64-channel column image of the window
+    const int STAGE_BYTES = IMG * CPR;
+    uint8_t* sW = smem;
+    uint8_t* sRing = smem + (size_t)nchunks * B_CHUNK;
+
+    if (tid == 0) {
+        for (int s = 0; s < STAGES; ++s) { mbar_init(&full_bar[s], 4); mbar_init(&empty_bar[s], 1); }
+        for (int a = 0; a < 2; ++a) { mbar_init(&tfull_bar[a], 1); mbar_init(&tempty_bar[a], 4); }
+        fence_barrier_init();
+    }
+    if (warp == 4) tmem_alloc(&tmem_base_smem, TMEM_COLS);
+    for (int idx = tid; idx < nchunks * BN * 8; idx += blockDim.x) {
+        const int c16 = idx & 7;
+        int t = idx >> 3;
+        const int r = t % BN; const int j = t / BN;
+        int4 v = make_int4(0, 0, 0, 0);
+        if (r < p.N) v = ldg16(p.Bw + (int64_t)r * K + j * 64 + c16 * 8);
+        *reinterpret_cast<int4*>(sW + (size_t)j * B_CHUNK + img_off(r, c16)) = v;
+    }
+    fence_proxy_async_smem();
+    tc_fence_before_sync();
+    __syncthreads();
+    tc_fence_after_sync();
+    const uint32_t tmem_d = tmem_base_smem;
+
+    if (warp < 4) {
+        // ======================= producers: one window per tile =======================
+        constexpr int PPR = CPR * 8;               // 16-byte pieces per grid row
+        constexpr int RSTEP = 128 / PPR;           // rows advanced per pass of the 128 producer threads
+        const int wr0 = tid / PPR, pc = tid % PPR;
+        const int cc = pc >> 3, c16 = pc & 7;
+        uint32_t q = 0;
+        for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++q) {
+            const uint32_t s = q % STAGES;
+            if (q >= (uint32_t)STAGES) mbar_wait(&empty_bar[s], ((q / STAGES) - 1) & 1);
+            const uint32_t sA = smem_u32(sRing + (size_t)s * STAGE_BYTES) + cc * IMG;
+            const int64_t row0 = (int64_t)tile * 128;
+            int64_t r = row0 + wr0;
+            int64_t img = 0; int rem = 0; int64_t ii = 0;
+            if (p.rows) {
+                ii = r / p.G; rem = (int)(r - ii * p.G);
+                img = ii < p.n ? __ldg(p.rows + ii) : 0;
+            }
+            for (int wr = wr0; wr < p.WR; wr += RSTEP, r += RSTEP) {
+                const bool ok = r < p.M;
+                const bf16* src = p.A;
+                if (ok) {
+                    if (p.rows) src = p.A + ((img * p.G + rem) * (int64_t)(CPR * 64) + pc * 8);
+                    else src = p.A + (r * (int64_t)(CPR * 64) + pc * 8);
+                }
+                cp_async16(sA + img_off(wr, c16), src, ok ? 16u : 0u);
+                if (p.rows) {
+                    rem += RSTEP;
+                    if (rem >= p.G) { rem -= p.G; ++ii; img = ii < p.n ? __ldg(p.rows + ii) : 0; }
+                }
+            }
+            cp_async_commit();
+            if (q >= (uint32_t)LOOKAHEAD) {
+                cp_async_wait<LOOKAHEAD>();
+                fence_proxy_async_smem();
+                __syncwarp();
+                if ((tid & 31) == 0) mbar_arrive(&full_bar[(q - LOOKAHEAD) % STAGES]);
+            }
+        }
+        cp_async_wait<0>();
+        fence_proxy_async_smem();
+        __syncwarp();
+        if ((tid & 31) == 0)
+            for (uint32_t d = (q >= (uint32_t)LOOKAHEAD ? q - LOOKAHEAD : 0); d < q; ++d) mbar_arrive(&full_bar[d % STAGES]);
+    } else if (warp == 4) {
+        // ======================= MMA issuer =======================
+        if ((tid & 31) == 0) {
+            constexpr uint32_t idesc = make_idesc(128, BN, 0, 0);
+            uint32_t q = 0;
+            for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++q) {
+                const uint32_t acc = q & 1, s = q % STAGES;
+                if (q >= 2) mbar_wait(&tempty_bar[acc], ((q >> 1) - 1) & 1);
+                mbar_wait(&full_bar[s], (q / STAGES) & 1);
+                tc_fence_after_sync();
+                const uint32_t d_addr = tmem_d + acc * BN;
+                const uint32_t win = smem_u32(sRing + (size_t)s * STAGE_BYTES);
+                uint32_t first = 1;
+                for (int t = 0; t < p.ntaps; ++t) {
+#pragma unroll
+                    for (int c = 0; c < CPR; ++c) {
+                        const uint64_t adesc = desc_kmajor(win + c * IMG + p.shift[t] * 128);
+                        const uint64_t bdesc = desc_kmajor(smem_u32(sW + (size_t)(t * CPR + c) * B_CHUNK));
+#pragma unroll
+                        for (int kk = 0; kk < 4; ++kk) {
+                            umma_bf16(d_addr, adesc + 2 * kk, bdesc + 2 * kk, idesc, first ? 0u : 1u);
+                            first = 0;
+                        }
+                    }
+                }
+                umma_commit(&empty_bar[s]);
+                umma_commit(&tfull_bar[acc]);
+            }
+        }
+    } else {
+        // ======================= epilogue =======================
+        const int ew = warp & 3;
+        const int lrow = ew * 32 + (tid & 31);
+        uint32_t q = 0;
+        for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++q) {
+            const uint32_t acc = q & 1;
+            const int64_t r = (int64_t)tile * 128 + lrow;
+            bool valid = r < p.M;
+            int i = 0, Y = 0, X = 0;
+            if (valid) {
+                i = (int)(r / p.G);
+                const int rem = (int)(r - (int64_t)i * p.G);
+                Y = rem / p.Wp; X = rem - Y * p.Wp;
+                valid = (Y < p.vH) && (X < p.vW);
+            }
+            int64_t o1 = 0, o2 = 0, om = 0;
+            if (p.out_mode == WOUT_DENSE) {
+                o1 = (((int64_t)i * p.vH + Y) * p.vW + X) * p.N;
+            } else if (p.out_mode == WOUT_S2D2) {
+                o1 = (((int64_t)i * 10 + (Y >> 1)) * 10 + (X >> 1)) * 128 + ((Y & 1) * 2 + (X & 1)) * 32;
+            } else if (p.out_mode == WOUT_DACT2) {
+                o1 = ((int64_t)i * 100 + Y * 10 + X) * 64;                 // 10-grid linear (conv2 wgrad)
+                o2 = ((int64_t)i * 121 + (Y + 1) * 11 + (X + 1)) * 64;     // zero-padded 11x11 (conv2 dgrad)
+                om = ((int64_t)i * 81 + Y * 9 + X) * 64;                   // act2 dense
+            } else {
+                om = ((int64_t)i * 100 + Y * 10 + X) * 128;                // act1 cells [n,100,128]
+            }
+            mbar_wait(&tfull_bar[acc], (q >> 1) & 1);
+            tc_fence_after_sync();
+            const uint32_t lane_addr = tmem_d + acc * BN + ((uint32_t)(ew * 32) << 16);
+#pragma unroll 1
+            for (int c0 = 0; c0 < BN; c0 += 16) {
+                uint32_t v[16];
+                tmem_ld16(lane_addr + c0, v);
+                tmem_ld_wait();
+                if (!valid || c0 >= p.N) continue;
+                float f[16];
+                if (p.bias) {
+                    const float4* bp = reinterpret_cast<const float4*>(p.bias + c0);
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) {
+                        const float4 bv = __ldg(bp + e);
+                        f[4 * e] = fmaf(__uint_as_float(v[4 * e]), p.scale, bv.x);
+                        f[4 * e + 1] = fmaf(__uint_as_float(v[4 * e + 1]), p.scale, bv.y);
+                        f[4 * e + 2] = fmaf(__uint_as_float(v[4 * e + 2]), p.scale, bv.z);
+                        f[4 * e + 3] = fmaf(__uint_as_float(v[4 * e + 3]), p.scale, bv.w);
+                    }
+                } else {
+#pragma unroll
+                    for (int e = 0; e < 16; ++e) f[e] = __uint_as_float(v[e]) * p.scale;
+                }
+                if (p.relu) {
+#pragma unroll
+                    for (int e = 0; e < 16; ++e) f[e] = fmaxf(f[e], 0.f);
+                }
+                if (p.mask) {
+                    const int4 m0 = ldg16(p.mask + om + c0);
+                    const int4 m1 = ldg16(p.mask + om + c0 + 8);
+                    const uint32_t mw[8] = {(uint32_t)m0.x, (uint32_t)m0.y, (uint32_t)m0.z, (uint32_t)m0.w,
+                                            (uint32_t)m1.x, (uint32_t)m1.y, (uint32_t)m1.z, (uint32_t)m1.w};
+#pragma unroll
+                    for (int e = 0; e < 8; ++e) {
+                        if ((mw[e] & 0x7FFFu) == 0u) f[2 * e] = 0.f;
+                        if ((mw[e] & 0x7FFF0000u) == 0u) f[2 * e + 1] = 0.f;
+                    }
+                }
+                int4 w0, w1;
+                w0.x = (int)pack_bf16x2(f[0], f[1]);   w0.y = (int)pack_bf16x2(f[2], f[3]);
+                w0.z = (int)pack_bf16x2(f[4], f[5]);   w0.w = (int)pack_bf16x2(f[6], f[7]);
+                w1.x = (int)pack_bf16x2(f[8], f[9]);   w1.y = (int)pack_bf16x2(f[10], f[11]);
+                w1.z = (int)pack_bf16x2(f[12], f[13]); w1.w = (int)pack_bf16x2(f[14], f[15]);
+                if (p.out_mode == WOUT_DACT1) {
+                    // column group g = (py,px) of the cell -> input pixel (2Y+py, 2X+px) of the 21-grid, 32 channels
+                    const int g = c0 >> 5;
+                    const int64_t od = ((int64_t)i * 441 + (2 * Y + (g >> 1)) * 21 + 2 * X + (g & 1)) * 32 + (c0 & 31);
+                    int4* dst = reinterpret_cast<int4*>(p.out + od);
+                    dst[0] = w0; dst[1] = w1;
+                } else {
+                    int4* dst = reinterpret_cast<int4*>(p.out + o1 + c0);
+                    dst[0] = w0; dst[1] = w1;
+                    if (p.out_mode == WOUT_DACT2) {
+                        int4* dst2 = reinterpret_cast<int4*>(p.out2 + o2 + c0);
+                        dst2[0] = w0; dst2[1] = w1;
+                    }
+                }
+            }
+            tc_fence_before_sync();
+            __syncwarp();
+            if ((tid & 31) == 0) mbar_arrive(&tempty_bar[acc]);
         }
     }
     tc_fence_before_sync();
@@ -442,6 +685,22 @@ static int num_sms() {
         if (cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || g_num_sms <= 0) g_num_sms = 148;
     }
     return g_num_sms;
+}
+
+template <int BN, int CPR, int STAGES>
+static int launch_conv_win(const WinParams& p, cudaStream_t s, const char* what) {
+    const size_t smem = (size_t)p.ntaps * CPR * BN * 128 + (size_t)STAGES * p.WR * 128 * CPR + 1024;
+    static size_t attr = 0;
+    if (smem > attr) {
+        cudaError_t e = cudaFuncSetAttribute(tc_conv_win<BN, CPR, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return fail(B200RL_ERR_CUDA, "%s: smem attribute (%zu B): %s", what, smem, cudaGetErrorString(e));
+        attr = smem;
+    }
+    const int total = (int)ceil_div(p.M, 128);
+    int grid = num_sms();
+    if (grid > total) grid = total;
+    tc_conv_win<BN, CPR, STAGES><<<grid, 288, smem, s>>>(p, total);
+    return check_launch(what);
 }
 
 template <int BN, int STAGES, bool WRES>
@@ -648,7 +907,7 @@ __global__ void __launch_bounds__(160, 1) tc_wgrad_ws(const WGradParams p) {
     while ((int)tmem_cols < xt * NY) tmem_cols <<= 1;
 
     if (tid == 0) {
-        for (int s = 0; s < STAGES; ++s) { mbar_init(&full_bar[s], 128); mbar_init(&empty_bar[s], 1); }
+        for (int s = 0; s < STAGES; ++s) { mbar_init(&full_bar[s], 4); mbar_init(&empty_bar[s], 1); }
         mbar_init(&done_bar, 1);
         fence_barrier_init();
     }
@@ -713,12 +972,15 @@ __global__ void __launch_bounds__(160, 1) tc_wgrad_ws(const WGradParams p) {
             if (it >= LOOKAHEAD) {
                 cp_async_wait<LOOKAHEAD>();
                 fence_proxy_async_smem();
-                mbar_arrive(&full_bar[(it - LOOKAHEAD) % STAGES]);
+                __syncwarp();
+                if ((tid & 31) == 0) mbar_arrive(&full_bar[(it - LOOKAHEAD) % STAGES]);
             }
         }
         cp_async_wait<0>();
         fence_proxy_async_smem();
-        for (int d = (nsteps >= LOOKAHEAD ? nsteps - LOOKAHEAD : 0); d < nsteps; ++d) mbar_arrive(&full_bar[d % STAGES]);
+        __syncwarp();
+        if ((tid & 31) == 0)
+            for (int d = (nsteps >= LOOKAHEAD ? nsteps - LOOKAHEAD : 0); d < nsteps; ++d) mbar_arrive(&full_bar[d % STAGES]);
     } else if ((tid & 31) == 0) {
         const uint32_t idesc = make_idesc(128, NY, 1, 1);
         for (int it = 0; it < nsteps; ++it) {
