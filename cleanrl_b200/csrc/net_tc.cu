@@ -54,6 +54,10 @@ struct KGemmParams {
     float scale;
     int relu;
     const bf16* mask;      // same layout as out: multiply by (mask > 0)
+    // fc data-gradient only: write dact3 on the 9x9 linear grid (out) and zero-padded 11x11 grid (out2);
+    // mask is read from the dense [n, 3136] act3
+    int dual_dact3;
+    bf16* out2;
 };
 
 __device__ __forceinline__ int4 ldg16(const void* p) { return __ldg(reinterpret_cast<const int4*>(p)); }
@@ -425,9 +429,18 @@ __global__ void __launch_bounds__(288, 1) tc_gemm_ws(const KGemmParams p, int to
                 o0.z = (int)pack_bf16x2(f[4], f[5]);   o0.w = (int)pack_bf16x2(f[6], f[7]);
                 o1.x = (int)pack_bf16x2(f[8], f[9]);   o1.y = (int)pack_bf16x2(f[10], f[11]);
                 o1.z = (int)pack_bf16x2(f[12], f[13]); o1.w = (int)pack_bf16x2(f[14], f[15]);
-                int4* dst = reinterpret_cast<int4*>(p.out + ooff + col);
-                dst[0] = o0;
-                dst[1] = o1;
+                if (p.dual_dact3) {
+                    const int px = col >> 6, ch = col & 63;          // pixel (oy,ox) of the 7x7 map, channel
+                    const int oy = px / 7, ox = px - oy * 7;
+                    int4* da = reinterpret_cast<int4*>(p.out + ((int64_t)r * 81 + oy * 9 + ox) * 64 + ch);
+                    int4* db = reinterpret_cast<int4*>(p.out2 + ((int64_t)r * 121 + (oy + 2) * 11 + ox + 2) * 64 + ch);
+                    da[0] = o0; da[1] = o1;
+                    db[0] = o0; db[1] = o1;
+                } else {
+                    int4* dst = reinterpret_cast<int4*>(p.out + ooff + col);
+                    dst[0] = o0;
+                    dst[1] = o1;
+                }
             }
             tc_fence_before_sync();
             __syncwarp();
@@ -1032,6 +1045,179 @@ __global__ void __launch_bounds__(160, 1) tc_wgrad_ws(const WGradParams p) {
     if (warp == 4) tmem_dealloc(tmem_d, tmem_cols);
 }
 
+// ------------------------------------------------------------------ kernel 2c: window weight gradient
+// dW^T[(tap,channel), co] = sum over grid rows r of X[r + shift_tap, channel] * dY[r, co] with X and dY on the
+// SAME linear grid (dY is zero at positions that are not valid outputs).  Per step of 128 rows the CTA
+// stages one X window (128 + max shift rows) and 128 dY rows; every tap is an MN-major descriptor shifted by
+// whole rows.  Output tile t pairs the 64-channel chunks slot[2t], slot[2t+1].
+struct WGradWinParams {
+    const bf16* X; const int64_t* rows; int64_t M; int n, G;
+    int cpr;                 // 64-channel column chunks per X row
+    int nslots;              // even; chunk of slot s = (tap slot_tap[s], column chunk slot_cc[s])
+    int slot_tap[16], slot_cc[16];
+    int shift[16];           // per tap
+    int WRX;                 // X window rows
+    const bf16* Y; int ldy, ncolsY;
+    int64_t rows_per_cta;    // multiple of 128
+    float* ws;               // [gridDim.x][nslots*64][64]
+};
+
+__global__ void __launch_bounds__(160, 1) tc_wgrad_win(const WGradWinParams p) {
+    constexpr int R = 128, STAGES = 3, LOOKAHEAD = 1, NY = 64;
+    extern __shared__ uint8_t smem_raw[];
+    __shared__ uint64_t full_bar[STAGES], empty_bar[STAGES], done_bar;
+    __shared__ uint32_t tmem_base_smem;
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    const int tid = threadIdx.x, warp = tid >> 5;
+    const int IMGX = p.WRX * 128;
+    const int XBYTES = IMGX * p.cpr;
+    const int stage_bytes = XBYTES + R * 128;
+    const int xt = p.nslots / 2;
+    uint32_t tmem_cols = 32;
+    while ((int)tmem_cols < xt * NY) tmem_cols <<= 1;
+    if (tid == 0) {
+        for (int s = 0; s < STAGES; ++s) { mbar_init(&full_bar[s], 4); mbar_init(&empty_bar[s], 1); }
+        mbar_init(&done_bar, 1);
+        fence_barrier_init();
+    }
+    if (warp == 4) tmem_alloc(&tmem_base_smem, tmem_cols);
+    tc_fence_before_sync();
+    __syncthreads();
+    tc_fence_after_sync();
+    const uint32_t tmem_d = tmem_base_smem;
+    const int64_t m_begin = (int64_t)blockIdx.x * p.rows_per_cta;
+    int64_t m_end = m_begin + p.rows_per_cta;
+    if (m_end > p.M) m_end = p.M;
+    const int nsteps = m_end > m_begin ? (int)((m_end - m_begin + R - 1) / R) : 0;
+
+    if (warp < 4) {
+        const int ppr = p.cpr * 8;               // 16-byte pieces per X row
+        const int rstep = 128 / ppr;
+        const int wr0 = tid / ppr, pc = tid % ppr;
+        const int cc = pc >> 3, c16 = pc & 7;
+        for (int it = 0; it < nsteps; ++it) {
+            const int s = it % STAGES;
+            if (it >= STAGES) mbar_wait(&empty_bar[s], ((it / STAGES) - 1) & 1);
+            const uint32_t sX = smem_u32(smem + (size_t)s * stage_bytes);
+            const uint32_t sY = sX + XBYTES;
+            const int64_t m0 = m_begin + (int64_t)it * R;
+            // X window: rows m0 .. m0+WRX-1 (may run past m_end: those rows belong to the next CTA / are zero)
+            {
+                int64_t r = m0 + wr0;
+                int64_t img = 0, ii = 0; int rem = 0;
+                if (p.rows) { ii = r / p.G; rem = (int)(r - ii * p.G); img = ii < p.n ? __ldg(p.rows + ii) : 0; }
+                for (int wr = wr0; wr < p.WRX; wr += rstep, r += rstep) {
+                    const bool ok = r < p.M;
+                    const bf16* src = p.X;
+                    if (ok) src = p.rows ? p.X + ((img * p.G + rem) * (int64_t)(p.cpr * 64) + pc * 8)
+                                         : p.X + (r * (int64_t)(p.cpr * 64) + pc * 8);
+                    cp_async16(sX + cc * IMGX + img_off(wr, c16), src, ok ? 16u : 0u);
+                    if (p.rows) { rem += rstep; if (rem >= p.G) { rem -= p.G; ++ii; img = ii < p.n ? __ldg(p.rows + ii) : 0; } }
+                }
+            }
+            // dY rows m0 .. m0+127 (zero beyond this CTA's range so that boundary rows are counted once)
+#pragma unroll
+            for (int ps = 0; ps < R / 16; ++ps) {
+                const int rr = ps * 16 + (tid >> 3);
+                const int64_t r = m0 + rr;
+                const int col = (tid & 7) * 8;
+                const bool ok = r < m_end && col < p.ncolsY;
+                cp_async16(sY + img_off(rr, tid & 7), p.Y + (ok ? r * (int64_t)p.ldy + col : 0), ok ? 16u : 0u);
+            }
+            cp_async_commit();
+            if (it >= LOOKAHEAD) {
+                cp_async_wait<LOOKAHEAD>();
+                fence_proxy_async_smem();
+                __syncwarp();
+                if ((tid & 31) == 0) mbar_arrive(&full_bar[(it - LOOKAHEAD) % STAGES]);
+            }
+        }
+        cp_async_wait<0>();
+        fence_proxy_async_smem();
+        __syncwarp();
+        if ((tid & 31) == 0)
+            for (int d = (nsteps >= LOOKAHEAD ? nsteps - LOOKAHEAD : 0); d < nsteps; ++d) mbar_arrive(&full_bar[d % STAGES]);
+    } else if ((tid & 31) == 0) {
+        const uint32_t idesc = make_idesc(128, NY, 1, 1);
+        for (int it = 0; it < nsteps; ++it) {
+            const int s = it % STAGES;
+            mbar_wait(&full_bar[s], (it / STAGES) & 1);
+            tc_fence_after_sync();
+            const uint32_t xa = smem_u32(smem + (size_t)s * stage_bytes), ya = xa + XBYTES;
+            for (int t = 0; t < xt; ++t) {
+                const uint32_t a0 = xa + p.slot_cc[2 * t] * IMGX + p.shift[p.slot_tap[2 * t]] * 128;
+                const uint32_t a1 = xa + p.slot_cc[2 * t + 1] * IMGX + p.shift[p.slot_tap[2 * t + 1]] * 128;
+#pragma unroll
+                for (int kk = 0; kk < R / 16; ++kk) {
+                    const uint64_t adesc = desc_mnmajor(a0 + kk * 2048, a1 - a0);
+                    const uint64_t bdesc = desc_mnmajor(ya + kk * 2048, R * 128);
+                    umma_bf16(tmem_d + t * NY, adesc, bdesc, idesc, (it | kk) != 0);
+                }
+            }
+            umma_commit(&empty_bar[s]);
+        }
+        umma_commit(&done_bar);
+    }
+    if (warp < 4) {
+        if (nsteps > 0) {
+            mbar_wait(&done_bar, 0);
+            tc_fence_after_sync();
+        }
+        float* wsb = p.ws + (int64_t)blockIdx.x * (p.nslots * 64) * NY;
+        const uint32_t lane_addr = tmem_d + ((uint32_t)(warp * 32) << 16);
+        for (int t = 0; t < xt; ++t) {
+            float* dst = wsb + (int64_t)(t * 128 + tid) * NY;
+            for (int c0 = 0; c0 < NY; c0 += 16) {
+                uint32_t v[16];
+                if (nsteps > 0) {
+                    tmem_ld16(lane_addr + t * NY + c0, v);
+                    tmem_ld_wait();
+                } else {
+#pragma unroll
+                    for (int e = 0; e < 16; ++e) v[e] = 0u;
+                }
+#pragma unroll
+                for (int e = 0; e < 16; e += 4)
+                    *reinterpret_cast<float4*>(dst + c0 + e) = make_float4(__uint_as_float(v[e]), __uint_as_float(v[e + 1]),
+                                                                             __uint_as_float(v[e + 2]), __uint_as_float(v[e + 3]));
+            }
+        }
+    }
+    tc_fence_before_sync();
+    __syncthreads();
+    if (warp == 4) tmem_dealloc(tmem_d, tmem_cols);
+}
+
+// fold for the window weight gradients: ws[S][nslots*64][64] -> torch layout dst[co][c][ky][kx].
+//   layer 1: slot = tap (a,b); row channel q = c*16 + sy*4 + sx; ky = 4a+sy, kx = 4b+sx; 32 outputs, Cin 4, 8x8
+//   layer 2: slot = (tap (a,b), cc); q = cc*64 + row = (py*2+px)*32 + c; ky = 2a+py, kx = 2b+px; Cin 32, 4x4
+//   layer 3: slot -> tap (ky,kx) via slot_tap (a duplicate slot is skipped); q = c; Cin 64, 3x3
+struct FoldWin { int layer, S, nslots, Cout; int slot_tap[16], slot_cc[16], slot_skip[16]; float scale; };
+__global__ void tc_fold_win(const float* __restrict__ ws, const FoldWin f, float* __restrict__ dst) {
+    const int idx = blockIdx.x * blockDim.x + threadIdx.x;           // (slot*64 + row) * Cout + co
+    const int KX = f.nslots * 64;
+    if (idx >= KX * f.Cout) return;
+    const int xi = idx / f.Cout, co = idx - xi * f.Cout;
+    const int slot = xi >> 6, row = xi & 63;
+    if (f.slot_skip[slot]) return;
+    float s = 0.f;
+    for (int z = 0; z < f.S; ++z) s += ws[((int64_t)z * KX + xi) * 64 + co];
+    s *= f.scale;
+    const int tap = f.slot_tap[slot];
+    int64_t o;
+    if (f.layer == 1) {
+        const int c = row >> 4, sy = (row >> 2) & 3, sx = row & 3;
+        o = (((int64_t)co * 4 + c) * 8 + ((tap >> 1) * 4 + sy)) * 8 + (tap & 1) * 4 + sx;
+    } else if (f.layer == 2) {
+        const int q = f.slot_cc[slot] * 64 + row;
+        const int g = q >> 5, c = q & 31;
+        o = (((int64_t)co * 32 + c) * 4 + (2 * (tap >> 1) + (g >> 1))) * 4 + 2 * (tap & 1) + (g & 1);
+    } else {
+        o = ((int64_t)co * 64 + row) * 9 + tap;
+    }
+    dst[o] = s;
+}
+
 // fold partials ws[S][KX][NY] -> fp32 gradient in the REFERENCE's parameter layout.
 // mode 0: dst[co][k] (conv1: K order (c,ky,kx) == torch's)                      src (k, co)
 // mode 1: dst[co][c][ky][kx] from K order (ky,kx,c) with C channels, KK taps       src (k, co)
@@ -1162,6 +1348,15 @@ __global__ void tc_pack_conv1_s2d(const float* __restrict__ w, bf16* __restrict_
     const int a = ky >> 2, sy = ky & 3, b = kx >> 2, sx = kx & 3;
     fwd[co * 256 + (a * 2 + b) * 64 + c * 16 + sy * 4 + sx] = __float2bfloat16(w[idx]);
 }
+// conv2 weight w[co][c][ky][kx] (4x4, stride 2) -> [co][(a,b) tap][(py,px,c)] with ky = 2a+py, kx = 2b+px:
+// K order of the 2x2-cell (space-to-depth 2) activations [n,10,10,128]
+__global__ void tc_pack_conv2_cells(const float* __restrict__ w, bf16* __restrict__ fwd) {
+    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= 64 * 512) return;
+    const int kx = idx & 3, ky = (idx >> 2) & 3, c = (idx >> 4) & 31, co = idx >> 9;
+    const int a = ky >> 1, py = ky & 1, b = kx >> 1, px = kx & 1;
+    fwd[co * 512 + (a * 2 + b) * 128 + (py * 2 + px) * 32 + c] = __float2bfloat16(w[idx]);
+}
 // conv2 data-gradient weights per stride-parity class: dg[cls][c][(a,b,co)] = w[co][c][py+2a][px+2b]
 __global__ void tc_pack_conv_s2_classes(const float* __restrict__ w, int Cout, int Cin, bf16* __restrict__ dg) {
     const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -1288,19 +1483,21 @@ struct NatureLayout {
     }
 };
 
-struct NatureActs {   // bf16 element offsets inside the activation workspace for batch n
-    int64_t x0, act1, act2, act3, hid, dhid, dact3, dact2, dact1, total;
+struct NatureActs {   // bf16 element offsets inside the (zero-initialised) activation workspace for batch n
+    int64_t x0, act1, act2, act3, hid, dhid, dact3a, dact3b, dact2a, dact2b, dact1, total;
     explicit NatureActs(int64_t n, bool with_x0 = true) {
         int64_t o = 0;
-        x0 = o; if (with_x0) o += n * 28224;     // space-to-depth frames (only when the caller passes uint8)
-        act1 = o; o += n * 12800;
-        act2 = o; o += n * 5184;
-        act3 = o; o += n * 3136;
+        x0 = o; if (with_x0) o += n * 28224;     // space-to-depth frames [n,441,64] (only for uint8 input)
+        act1 = o; o += n * 12800;                // conv1 out as 2x2 cells   [n,100,128]
+        act2 = o; o += n * 5184;                 // conv2 out               [n, 81, 64]
+        act3 = o; o += n * 3136;                 // conv3 out               [n, 49, 64]
         hid = o;  o += n * 512;
         dhid = o; o += n * 512;
-        dact3 = o; o += n * 3136;
-        dact2 = o; o += n * 5184;
-        dact1 = o; o += n * 12800;
+        dact3a = o; o += n * 5184;               // d(act3) on the 9x9 linear grid (zeros outside 7x7)
+        dact3b = o; o += n * 7744;               // d(act3) zero-padded to 11x11 (interior at +2,+2)
+        dact2a = o; o += n * 6400;               // d(act2) on the 10x10 linear grid (zeros at row/col 9)
+        dact2b = o; o += n * 7744;               // d(act2) zero-padded to 11x11 (interior at +1,+1)
+        dact1 = o; o += n * 14112;               // d(act1) on the 21x21 linear grid, 32 channels
         total = o;
     }
 };
@@ -1342,13 +1539,32 @@ static void rowmajor_gather(KGemmParams& p, const bf16* x, int64_t n, int nchunk
     for (int j = 0; j < nchunks; ++j) { p.dy[j] = 0; p.dx[j] = (signed char)j; }
 }
 
+
+// ---- window-convolution descriptions of the three conv layers
+static void win_defaults(WinParams& p) { memset(&p, 0, sizeof(p)); p.scale = 1.f; }
+static int round8(int v) { return (v + 7) & ~7; }
+static void win_conv1(WinParams& p, const bf16* x0, const int64_t* rows, int64_t n) {     // 2x2 taps on the 21x21 s2d grid
+    p.A = x0; p.rows = rows; p.n = (int)n; p.G = 441; p.Wp = 21; p.M = n * 441;
+    p.ntaps = 4; p.shift[0] = 0; p.shift[1] = 1; p.shift[2] = 21; p.shift[3] = 22; p.WR = round8(128 + 22);
+}
+static void win_conv2(WinParams& p, const bf16* act1, int64_t n) {                         // 2x2 taps on the 10x10 cell grid
+    p.A = act1; p.n = (int)n; p.G = 100; p.Wp = 10; p.M = n * 100;
+    p.ntaps = 4; p.shift[0] = 0; p.shift[1] = 1; p.shift[2] = 10; p.shift[3] = 11; p.WR = round8(128 + 11);
+}
+static void win_conv3(WinParams& p, const bf16* act2, int64_t n) {                         // 3x3 taps on the 9x9 grid
+    p.A = act2; p.n = (int)n; p.G = 81; p.Wp = 9; p.M = n * 81;
+    p.ntaps = 9; for (int ky = 0; ky < 3; ++ky) for (int kx = 0; kx < 3; ++kx) p.shift[ky * 3 + kx] = ky * 9 + kx;
+    p.WR = round8(128 + 20);
+}
+static void wgw_defaults(WGradWinParams& w) { memset(&w, 0, sizeof(w)); }
+
 static int64_t round_up(int64_t a, int64_t b) { return ceil_div(a, b) * b; }
 
 struct WPlan { int64_t rows_per_cta; int splits; };
-static WPlan wgrad_plan(int64_t M, int target_ctas) {
+static WPlan wgrad_plan(int64_t M, int target_ctas, int quantum = 32) {
     WPlan w;
-    w.rows_per_cta = round_up(ceil_div(M, target_ctas), 32);
-    if (w.rows_per_cta < 32) w.rows_per_cta = 32;
+    w.rows_per_cta = round_up(ceil_div(M, target_ctas), quantum);
+    if (w.rows_per_cta < quantum) w.rows_per_cta = quantum;
     w.splits = (int)ceil_div(M, w.rows_per_cta);
     if (w.splits < 1) w.splits = 1;
     return w;
@@ -1364,6 +1580,18 @@ static int launch_wgrad(const WGradParams& p, dim3 grid, cudaStream_t s, const c
         attr = smem;
     }
     tc_wgrad_ws<<<grid, 160, smem, s>>>(p);
+    return check_launch(what);
+}
+
+static int launch_wgrad_win(const WGradWinParams& p, int ctas, cudaStream_t s, const char* what) {
+    const size_t smem = (size_t)3 * ((size_t)p.WRX * 128 * p.cpr + 128 * 128) + 1024;
+    static size_t attr = 0;
+    if (smem > attr) {
+        cudaError_t e = cudaFuncSetAttribute(tc_wgrad_win, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return fail(B200RL_ERR_CUDA, "%s: smem attribute (%zu B): %s", what, smem, cudaGetErrorString(e));
+        attr = smem;
+    }
+    tc_wgrad_win<<<ctas, 160, smem, s>>>(p);
     return check_launch(what);
 }
 
@@ -1406,13 +1634,13 @@ extern "C" size_t b200rl_naturecnn_bf16_workspace_bytes(int64_t n, int A) {
     if (n < 1 || A < 1) return 0;
     size_t a = 0;
     auto mx = [&](size_t v) { if (v > a) a = v; };
-    mx((size_t)wgrad_plan(n * 400, kC1Ctas).splits * 256 * 64 * 4);
-    mx((size_t)wgrad_plan(n * 81, kC2Ctas).splits * 512 * 64 * 4);
-    mx((size_t)wgrad_plan(n * 49, kC3Ctas).splits * 640 * 64 * 4);
+    mx((size_t)wgrad_plan(n * 441, kC1Ctas, 128).splits * 256 * 64 * 4);
+    mx((size_t)wgrad_plan(n * 100, kC2Ctas, 128).splits * 512 * 64 * 4);
+    mx((size_t)wgrad_plan(n * 81, kC3Ctas, 128).splits * 640 * 64 * 4);
     mx((size_t)wgrad_plan(n, kFcSplits).splits * 512 * (13 * 256) * 4);
     size_t b = 0;
     auto mb = [&](size_t v) { if (v > b) b = v; };
-    mb(colsum_ws(n * 400, 32)); mb(colsum_ws(n * 81, 64)); mb(colsum_ws(n * 49, 64)); mb(colsum_ws(n, 512));
+    mb(colsum_ws(n * 441, 32)); mb(colsum_ws(n * 100, 64)); mb(colsum_ws(n * 81, 64)); mb(colsum_ws(n, 512));
     mb((size_t)296 * (A + 1) * 513 * 4);
     return a + b + 512;
 }
@@ -1425,7 +1653,7 @@ extern "C" int b200rl_naturecnn_bf16_pack(const float* params, int A, void* pack
     cudaStream_t s = (cudaStream_t)stream;
     ProfScope ps(s, "pack_weights", 0, (double)L.total * 4 + (double)L.packed_total * 2);
     tc_pack_conv1_s2d<<<32, 256, 0, s>>>(params + L.c1w, P + L.w1f);
-    tc_pack_conv<<<(unsigned)ceil_div(32768, 256), 256, 0, s>>>(params + L.c2w, 64, 32, 4, 4, 0, P + L.w2f, nullptr);
+    tc_pack_conv2_cells<<<128, 256, 0, s>>>(params + L.c2w, P + L.w2f);
     tc_pack_conv_s2_classes<<<(unsigned)ceil_div(32768, 256), 256, 0, s>>>(params + L.c2w, 64, 32, P + L.w2dg);
     tc_pack_conv<<<(unsigned)ceil_div(36864, 256), 256, 0, s>>>(params + L.c3w, 64, 64, 3, 3, 0, P + L.w3f, P + L.w3dg);
     tc_pack_fc<<<(unsigned)ceil_div(512 * 3136, 256), 256, 0, s>>>(params + L.fcw, 512, 64, 49, P + L.wfcf, P + L.wfcdg);
@@ -1449,28 +1677,31 @@ extern "C" int b200rl_naturecnn_bf16_forward(const void* obs, int obs_format, co
     cudaStream_t s = (cudaStream_t)stream;
     int rc;
     KGemmParams p;
-    // conv1 on space-to-depth frames -> act1 [n,20,20,32]
+    WinParams wp;
+    // conv1: 2x2 window conv on space-to-depth frames -> act1 as 2x2 cells [n,10,10,128]
     const bf16* x0 = reinterpret_cast<const bf16*>(obs);
     const int64_t* x0rows = rows;
     if (obs_format == B200RL_OBS_U8_NCHW) {
         if ((rc = b200rl_frames_to_s2d_bf16(reinterpret_cast<const uint8_t*>(obs), rows, n, act + Q.x0, stream))) return rc;
         x0 = act + Q.x0; x0rows = nullptr;
     }
-    gemm_defaults(p); conv1_gather(p, x0, x0rows, n);
-    p.Bw = P + L.w1f; p.N = 32; p.out = act + Q.act1; p.OH = 20; p.OW = 20; p.ldo = 32;
-    p.bias = params + L.c1b; p.scale = 1.0f / 255.0f; p.relu = 1;
+    win_defaults(wp); win_conv1(wp, x0, x0rows, n);
+    wp.Bw = P + L.w1f; wp.N = 32; wp.vH = 20; wp.vW = 20; wp.out_mode = WOUT_S2D2; wp.out = act + Q.act1;
+    wp.bias = params + L.c1b; wp.scale = 1.0f / 255.0f; wp.relu = 1;
     { ProfScope ps(s, "conv1_fwd", 2.0 * n * 400 * 32 * 256, (double)n * (28224 + 12800) * 2);
-      if ((rc = launch_kgemm_ws<32, 8, true>(p, s, "naturecnn/conv1"))) return rc; }
-    // conv2 -> act2 [n,9,9,64]
-    gemm_defaults(p); conv2_gather(p, act + Q.act1, n);
-    p.Bw = P + L.w2f; p.N = 64; p.out = act + Q.act2; p.OH = 9; p.OW = 9; p.ldo = 64; p.bias = params + L.c2b; p.relu = 1;
+      if ((rc = launch_conv_win<32, 1, 6>(wp, s, "naturecnn/conv1"))) return rc; }
+    // conv2: 2x2 window conv on the 128-channel cells -> act2 [n,9,9,64]
+    win_defaults(wp); win_conv2(wp, act + Q.act1, n);
+    wp.Bw = P + L.w2f; wp.N = 64; wp.vH = 9; wp.vW = 9; wp.out_mode = WOUT_DENSE; wp.out = act + Q.act2;
+    wp.bias = params + L.c2b; wp.relu = 1;
     { ProfScope ps(s, "conv2_fwd", 2.0 * n * 81 * 64 * 512, (double)n * (12800 + 5184) * 2);
-      if ((rc = launch_kgemm_ws<64, 8, true>(p, s, "naturecnn/conv2"))) return rc; }
-    // conv3 -> act3 [n,7,7,64]
-    gemm_defaults(p); conv3_gather(p, act + Q.act2, n);
-    p.Bw = P + L.w3f; p.N = 64; p.out = act + Q.act3; p.OH = 7; p.OW = 7; p.ldo = 64; p.bias = params + L.c3b; p.relu = 1;
+      if ((rc = launch_conv_win<64, 2, 4>(wp, s, "naturecnn/conv2"))) return rc; }
+    // conv3: 3x3 window conv -> act3 [n,7,7,64]
+    win_defaults(wp); win_conv3(wp, act + Q.act2, n);
+    wp.Bw = P + L.w3f; wp.N = 64; wp.vH = 7; wp.vW = 7; wp.out_mode = WOUT_DENSE; wp.out = act + Q.act3;
+    wp.bias = params + L.c3b; wp.relu = 1;
     { ProfScope ps(s, "conv3_fwd", 2.0 * n * 49 * 64 * 576, (double)n * (5184 + 3136) * 2);
-      if ((rc = launch_kgemm_ws<64, 8, true>(p, s, "naturecnn/conv3"))) return rc; }
+      if ((rc = launch_conv_win<64, 1, 6>(wp, s, "naturecnn/conv3"))) return rc; }
     // fc -> hidden [n,512]
     gemm_defaults(p); rowmajor_gather(p, act + Q.act3, n, 49);
     p.Bw = P + L.wfcf; p.N = 512; p.out = act + Q.hid; p.OH = 1; p.OW = 1; p.ldo = 512; p.bias = params + L.fcb; p.relu = 1;
@@ -1505,9 +1736,9 @@ extern "C" int b200rl_naturecnn_bf16_backward(const void* obs, int obs_format, c
     size_t big = 0;
     {
         auto mx = [&](size_t v) { if (v > big) big = v; };
-        mx((size_t)wgrad_plan(n * 400, kC1Ctas).splits * 256 * 64 * 4);
-        mx((size_t)wgrad_plan(n * 81, kC2Ctas).splits * 512 * 64 * 4);
-        mx((size_t)wgrad_plan(n * 49, kC3Ctas).splits * 640 * 64 * 4);
+        mx((size_t)wgrad_plan(n * 441, kC1Ctas, 128).splits * 256 * 64 * 4);
+        mx((size_t)wgrad_plan(n * 100, kC2Ctas, 128).splits * 512 * 64 * 4);
+        mx((size_t)wgrad_plan(n * 81, kC3Ctas, 128).splits * 640 * 64 * 4);
         mx((size_t)wgrad_plan(n, kFcSplits).splits * 512 * (13 * 256) * 4);
         big = (big + 255) & ~(size_t)255;
     }
@@ -1540,67 +1771,87 @@ extern "C" int b200rl_naturecnn_bf16_backward(const void* obs, int obs_format, c
         { ProfScope ps(s, "wgrad_fold_bias", 0, 0);
           note_launches(1); tc_fold_kernel<<<(unsigned)ceil_div((int64_t)512 * 3136, 256), 256, 0, s>>>(wsbig, pl.splits, 512, 13 * 256, 512, 3136, 2, 64, 49, 1.f, grads + L.fcw);
           if ((rc = colsum(act + Q.dhid, n, 512, 512, wssmall, grads + L.fcb, s))) return rc; }
-        // dact3_pre = (dhid . Wfc) * (act3 > 0)
+        // dact3_pre = (dhid . Wfc) * (act3 > 0), written on the 9x9 linear grid and the zero-padded 11x11 grid
         gemm_defaults(p); rowmajor_gather(p, act + Q.dhid, n, 8);
-        p.Bw = P + L.wfcdg; p.N = 3136; p.out = act + Q.dact3; p.OH = 1; p.OW = 1; p.ldo = 3136; p.mask = act + Q.act3;
+        p.Bw = P + L.wfcdg; p.N = 3136; p.out = act + Q.dact3a; p.out2 = act + Q.dact3b; p.dual_dact3 = 1;
+        p.OH = 1; p.OW = 1; p.ldo = 3136; p.mask = act + Q.act3;
         { ProfScope ps(s, "fc_dgrad", 2.0 * n * 512 * 3136, (double)n * (3136 * 2 + 512) * 2 + 512.0 * 3136 * 2);
           if ((rc = launch_kgemm_ws<256, 4, false>(p, s, "naturecnn/fc_dgrad"))) return rc; }
     }
-    // ---- conv3
+    WGradWinParams gw;
+    WinParams wp;
+    FoldWin fw;
+    // ---- conv3: dW from act2 windows x dact3 (9x9 grid), then dact2 = full correlation of padded dact3 with W3
     {
-        memset(&w, 0, sizeof(w));
-        gemm_defaults(w.x); conv3_gather(w.x, act + Q.act2, n);
-        w.Y = act + Q.dact3; w.ldy = 64; w.nyc = 1; w.ncolsY = 64; w.nxc = 10;
-        const WPlan pl = wgrad_plan(n * 49, kC3Ctas);
-        w.rows_per_cta = pl.rows_per_cta; w.ws = wsbig;
-        { ProfScope ps(s, "conv3_wgrad", 2.0 * n * 49 * 64 * 576, (double)n * (5184 + 3136) * 2);
-          if ((rc = launch_wgrad(w, dim3(pl.splits, 1, 1), s, "naturecnn/conv3_wgrad"))) return rc; }
+        wgw_defaults(gw);
+        gw.X = act + Q.act2; gw.M = n * 81; gw.n = (int)n; gw.G = 81; gw.cpr = 1; gw.nslots = 10; gw.WRX = round8(128 + 20);
+        for (int t = 0; t < 9; ++t) gw.shift[t] = (t / 3) * 9 + (t % 3);
+        const int st[10] = {0, 1, 2, 3, 4, 5, 6, 7, 7, 8};      // slot 8 duplicates tap 7 so that tap 8 has a partner
+        for (int k = 0; k < 10; ++k) { gw.slot_tap[k] = st[k]; gw.slot_cc[k] = 0; }
+        gw.Y = act + Q.dact3a; gw.ldy = 64; gw.ncolsY = 64;
+        const WPlan pl = wgrad_plan(n * 81, kC3Ctas, 128);
+        gw.rows_per_cta = pl.rows_per_cta; gw.ws = wsbig;
+        { ProfScope ps(s, "conv3_wgrad", 2.0 * n * 49 * 64 * 576, (double)n * (5184 + 5184) * 2);
+          if ((rc = launch_wgrad_win(gw, pl.splits, s, "naturecnn/conv3_wgrad"))) return rc; }
+        memset(&fw, 0, sizeof(fw));
+        fw.layer = 3; fw.S = pl.splits; fw.nslots = 10; fw.Cout = 64; fw.scale = 1.f;
+        for (int k = 0; k < 10; ++k) { fw.slot_tap[k] = st[k]; fw.slot_skip[k] = (k == 8); }
         { ProfScope ps(s, "wgrad_fold_bias", 0, 0);
-          note_launches(1); tc_fold_kernel<<<(unsigned)ceil_div(576 * 64, 256), 256, 0, s>>>(wsbig, pl.splits, 640, 64, 576, 64, 1, 64, 9, 1.f, grads + L.c3w);
-          if ((rc = colsum(act + Q.dact3, n * 49, 64, 64, wssmall, grads + L.c3b, s))) return rc; }
-        // dact2_pre[n,9,9,64] = full-correlation of dact3 with W3, masked by act2 > 0
-        gemm_defaults(p);
-        p.A = act + Q.dact3; set_rows(p, n * 81, 81, 9);
-        p.SH = 7; p.SW = 7; p.CP = 64; p.nchunks = 9; p.check = 1;
-        for (int ky = 0; ky < 3; ++ky) for (int kx = 0; kx < 3; ++kx) { p.dy[ky * 3 + kx] = (signed char)-ky; p.dx[ky * 3 + kx] = (signed char)-kx; }
-        p.Bw = P + L.w3dg; p.N = 64; p.out = act + Q.dact2; p.OH = 9; p.OW = 9; p.ldo = 64; p.mask = act + Q.act2;
-        { ProfScope ps(s, "conv3_dgrad", 2.0 * n * 81 * 64 * 576, (double)n * (3136 + 5184 * 2) * 2);
-          if ((rc = launch_kgemm_ws<64, 8, true>(p, s, "naturecnn/conv3_dgrad"))) return rc; }
+          note_launches(1); tc_fold_win<<<(unsigned)ceil_div(640 * 64, 256), 256, 0, s>>>(wsbig, fw, grads + L.c3w);
+          if ((rc = colsum(act + Q.dact3a, n * 81, 64, 64, wssmall, grads + L.c3b, s))) return rc; }
+        win_defaults(wp);
+        wp.A = act + Q.dact3b; wp.n = (int)n; wp.G = 121; wp.Wp = 11; wp.M = n * 121; wp.ntaps = 9;
+        for (int ky = 0; ky < 3; ++ky) for (int kx = 0; kx < 3; ++kx) wp.shift[ky * 3 + kx] = (2 - ky) * 11 + (2 - kx);
+        wp.WR = round8(128 + 24);
+        wp.Bw = P + L.w3dg; wp.N = 64; wp.vH = 9; wp.vW = 9; wp.out_mode = WOUT_DACT2;
+        wp.out = act + Q.dact2a; wp.out2 = act + Q.dact2b; wp.mask = act + Q.act2;
+        { ProfScope ps(s, "conv3_dgrad", 2.0 * n * 81 * 64 * 576, (double)n * (7744 + 5184 + 6400 + 7744) * 2);
+          if ((rc = launch_conv_win<64, 1, 6>(wp, s, "naturecnn/conv3_dgrad"))) return rc; }
     }
-    // ---- conv2
+    // ---- conv2: dW from act1 cell windows x dact2 (10x10 grid); dact1 = one N=128 GEMM over the 4 stride-parity
+    //      classes (the 4 channel groups of a cell)
     {
-        memset(&w, 0, sizeof(w));
-        gemm_defaults(w.x); conv2_gather(w.x, act + Q.act1, n);
-        w.Y = act + Q.dact2; w.ldy = 64; w.nyc = 1; w.ncolsY = 64; w.nxc = 8;
-        const WPlan pl = wgrad_plan(n * 81, kC2Ctas);
-        w.rows_per_cta = pl.rows_per_cta; w.ws = wsbig;
-        { ProfScope ps(s, "conv2_wgrad", 2.0 * n * 81 * 64 * 512, (double)n * (12800 + 5184) * 2);
-          if ((rc = launch_wgrad(w, dim3(pl.splits, 1, 1), s, "naturecnn/conv2_wgrad"))) return rc; }
+        wgw_defaults(gw);
+        gw.X = act + Q.act1; gw.M = n * 100; gw.n = (int)n; gw.G = 100; gw.cpr = 2; gw.nslots = 8; gw.WRX = round8(128 + 11);
+        gw.shift[0] = 0; gw.shift[1] = 1; gw.shift[2] = 10; gw.shift[3] = 11;
+        for (int k = 0; k < 8; ++k) { gw.slot_tap[k] = k >> 1; gw.slot_cc[k] = k & 1; }
+        gw.Y = act + Q.dact2a; gw.ldy = 64; gw.ncolsY = 64;
+        const WPlan pl = wgrad_plan(n * 100, kC2Ctas, 128);
+        gw.rows_per_cta = pl.rows_per_cta; gw.ws = wsbig;
+        { ProfScope ps(s, "conv2_wgrad", 2.0 * n * 81 * 64 * 512, (double)n * (12800 + 6400) * 2);
+          if ((rc = launch_wgrad_win(gw, pl.splits, s, "naturecnn/conv2_wgrad"))) return rc; }
+        memset(&fw, 0, sizeof(fw));
+        fw.layer = 2; fw.S = pl.splits; fw.nslots = 8; fw.Cout = 64; fw.scale = 1.f;
+        for (int k = 0; k < 8; ++k) { fw.slot_tap[k] = k >> 1; fw.slot_cc[k] = k & 1; }
         { ProfScope ps(s, "wgrad_fold_bias", 0, 0);
-          note_launches(1); tc_fold_kernel<<<(unsigned)ceil_div(512 * 64, 256), 256, 0, s>>>(wsbig, pl.splits, 512, 64, 512, 64, 1, 32, 16, 1.f, grads + L.c2w);
-          if ((rc = colsum(act + Q.dact2, n * 81, 64, 64, wssmall, grads + L.c2b, s))) return rc; }
-        // dact1_pre[n,20,20,32]: 4 stride-parity classes, each a 2x2-tap stride-1 problem on a 10x10 grid
-        gemm_defaults(p);
-        p.A = act + Q.dact2; set_rows(p, n * 100, 100, 10);
-        p.SH = 9; p.SW = 9; p.CP = 64; p.nchunks = 4; p.check = 1; p.nclasses = 4;
-        for (int a = 0; a < 2; ++a) for (int b = 0; b < 2; ++b) { p.dy[a * 2 + b] = (signed char)-a; p.dx[a * 2 + b] = (signed char)-b; }
-        p.Bw = P + L.w2dg; p.b_class_stride = 32 * 256; p.N = 32;
-        p.out = act + Q.dact1; p.OH = 20; p.OW = 20; p.osy = 2; p.osx = 2; p.ldo = 32; p.mask = act + Q.act1;
-        { ProfScope ps(s, "conv2_dgrad", 2.0 * n * 400 * 32 * 256, (double)n * (5184 + 12800 * 2) * 2);
-          if ((rc = launch_kgemm_ws<32, 8, true>(p, s, "naturecnn/conv2_dgrad"))) return rc; }
+          note_launches(1); tc_fold_win<<<(unsigned)ceil_div(512 * 64, 256), 256, 0, s>>>(wsbig, fw, grads + L.c2w);
+          if ((rc = colsum(act + Q.dact2a, n * 100, 64, 64, wssmall, grads + L.c2b, s))) return rc; }
+        win_defaults(wp);
+        wp.A = act + Q.dact2b; wp.n = (int)n; wp.G = 121; wp.Wp = 11; wp.M = n * 121; wp.ntaps = 4;
+        for (int a = 0; a < 2; ++a) for (int b = 0; b < 2; ++b) wp.shift[a * 2 + b] = (1 - a) * 11 + (1 - b);
+        wp.WR = round8(128 + 12);
+        wp.Bw = P + L.w2dg; wp.N = 128; wp.vH = 10; wp.vW = 10; wp.out_mode = WOUT_DACT1;
+        wp.out = act + Q.dact1; wp.mask = act + Q.act1;
+        { ProfScope ps(s, "conv2_dgrad", 2.0 * n * 400 * 32 * 256, (double)n * (7744 + 12800 + 14112) * 2);
+          if ((rc = launch_conv_win<128, 1, 6>(wp, s, "naturecnn/conv2_dgrad"))) return rc; }
     }
     // ---- conv1 (no data gradient: the input is the observation)
     {
-        memset(&w, 0, sizeof(w));
-        gemm_defaults(w.x); conv1_gather(w.x, x0, x0rows, n);
-        w.Y = act + Q.dact1; w.ldy = 32; w.nyc = 1; w.ncolsY = 32; w.nxc = 4;
-        const WPlan pl = wgrad_plan(n * 400, kC1Ctas);
-        w.rows_per_cta = pl.rows_per_cta; w.ws = wsbig;
-        { ProfScope ps(s, "conv1_wgrad", 2.0 * n * 400 * 32 * 256, (double)n * (28224 + 12800) * 2);
-          if ((rc = launch_wgrad(w, dim3(pl.splits, 1, 1), s, "naturecnn/conv1_wgrad"))) return rc; }
+        wgw_defaults(gw);
+        gw.X = x0; gw.rows = x0rows; gw.M = n * 441; gw.n = (int)n; gw.G = 441; gw.cpr = 1; gw.nslots = 4; gw.WRX = round8(128 + 22);
+        gw.shift[0] = 0; gw.shift[1] = 1; gw.shift[2] = 21; gw.shift[3] = 22;
+        for (int k = 0; k < 4; ++k) { gw.slot_tap[k] = k; gw.slot_cc[k] = 0; }
+        gw.Y = act + Q.dact1; gw.ldy = 32; gw.ncolsY = 32;
+        const WPlan pl = wgrad_plan(n * 441, kC1Ctas, 128);
+        gw.rows_per_cta = pl.rows_per_cta; gw.ws = wsbig;
+        { ProfScope ps(s, "conv1_wgrad", 2.0 * n * 400 * 32 * 256, (double)n * (28224 + 14112) * 2);
+          if ((rc = launch_wgrad_win(gw, pl.splits, s, "naturecnn/conv1_wgrad"))) return rc; }
+        memset(&fw, 0, sizeof(fw));
+        fw.layer = 1; fw.S = pl.splits; fw.nslots = 4; fw.Cout = 32; fw.scale = 1.0f / 255.0f;
+        for (int k = 0; k < 4; ++k) fw.slot_tap[k] = k;
         { ProfScope ps(s, "wgrad_fold_bias", 0, 0);
-          note_launches(1); tc_fold_kernel<<<(unsigned)ceil_div(256 * 32, 256), 256, 0, s>>>(wsbig, pl.splits, 256, 64, 256, 32, 3, 0, 0, 1.0f / 255.0f, grads + L.c1w);
-          if ((rc = colsum(act + Q.dact1, n * 400, 32, 32, wssmall, grads + L.c1b, s))) return rc; }
+          note_launches(1); tc_fold_win<<<(unsigned)ceil_div(256 * 32, 256), 256, 0, s>>>(wsbig, fw, grads + L.c1w);
+          if ((rc = colsum(act + Q.dact1, n * 441, 32, 32, wssmall, grads + L.c1b, s))) return rc; }
     }
     return B200RL_OK;
 }

@@ -312,7 +312,8 @@ class NatureCNNBf16:
         if key not in self._acts:
             if len(self._acts) > 4:
                 self._acts.clear()
-            self._acts[key] = torch.empty(lib.b200rl_naturecnn_bf16_acts_bytes(n, fmt), dtype=torch.uint8, device=self.device)
+            # zero-initialised: the padded-grid gradient buffers rely on never-written positions being 0
+            self._acts[key] = torch.zeros(lib.b200rl_naturecnn_bf16_acts_bytes(n, fmt), dtype=torch.uint8, device=self.device)
         return self._acts[key]
 
     @staticmethod
