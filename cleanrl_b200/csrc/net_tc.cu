@@ -1,27 +1,31 @@
 // NatureCNN on the 5th-gen tensor cores (tcgen05.mma, accumulators in TMEM), bf16 operands,
 // fp32 accumulation.  Reference network: cleanrl/ppo_atari_envpool.py:123-139.
 //
-// Every layer -- forward, data-gradient and weight-gradient -- is an implicit GEMM whose A operand
-// is GATHERED by the CTA's threads straight from the NHWC bf16 activations (or, for conv1, from the
-// stacked-frame uint8 observations, converted to bf16 on the fly: 0..255 is exact in bf16; the /255
-// of ppo_atari_envpool.py:144 is applied to the fp32 accumulator in the epilogue) into the UMMA
-// canonical SWIZZLE_128B shared-memory image.  No im2col matrix, no gathered minibatch copy and no
-// fp32 observation tensor ever exists in HBM (the reference materialises a 3.7 GB fp32 gather per
-// minibatch, ppo.py:250).
+// Data layout in HBM (all activations are LINEAR PIXEL GRIDS: row = grid position, 128 bytes = 64 channels)
+//   frames   bf16 [n, 21x21, 64]   space-to-depth(4) of the uint8 frames: channel = c*16 + sy*4 + sx of source
+//                                  pixel (4Y+sy, 4X+sx); written once per env step (tc_frames_to_s2d), 0..255 is
+//                                  exact in bf16 and the /255 of ppo_atari_envpool.py:144 is applied to the fp32
+//                                  accumulator.  conv1 (8x8 s4) = 2x2 stride-1 conv on this grid.
+//   act1     bf16 [n, 10x10, 128]  conv1 output as 2x2 cells (space-to-depth(2)): conv2 (4x4 s2) = 2x2 stride-1.
+//   act2     bf16 [n,  9x9,  64]   act3 bf16 [n, 7x7, 64]   hidden bf16 [n, 512]
+//   gradients of act3 / act2 are written twice by their producer: on the consumer-weight-gradient's grid
+//   (zeros at positions that are not valid outputs) and zero-padded for the data-gradient's "full" correlation;
+//   d(act1) lives on the 21x21 grid with 32 channels.  Never-written positions rely on a zero-initialised
+//   workspace.  The minibatch gather b_obs[mb_inds] (ppo.py:250, 3.7 GB fp32 per minibatch in the reference)
+//   is an image-index indirection inside the conv1 kernels.
 //
-// Data layout in HBM
-//   obs          uint8 [B, 4, 84, 84]   (as envpool delivers it; rows selected through mb_inds)
-//   act1/2/3     bf16  [n, 20,20,32] / [n, 9,9,64] / [n, 7,7,64]   NHWC == row-major [pixels, C]
-//   hidden       bf16  [n, 512]
-//   packed weights bf16 [N, K] K-contiguous, K ordered (ky,kx,c) to match NHWC patches
-//                (conv1: (c,ky,kx) to match the NCHW uint8 frames); transposed copies for dgrad.
-//
-// Kernel 1 (tc_gemm_kmajor): D[128 x BN] = sum_chunks A_chunk[128 x 64] * W_chunk[BN x 64]^T
-//   128 threads stage chunk j+1 while the single-thread-issued MMAs of chunk j run asynchronously;
-//   a tcgen05.commit on an mbarrier frees a stage.  Epilogue: tcgen05.ld, bias/ReLU/(ReLU-mask),
-//   bf16 NHWC store.
-// Kernel 2 (tc_wgrad): dW^T[k, co] = sum_m X[m, k] * dY[m, co]; both operands are read as
-//   MN-major views of the very same row images (rows = reduction index m).
+// Kernels
+//   tc_conv_win<BN,CPR,STAGES>   stride-1 "window" convolution (conv1/2/3 forward, conv3/conv2 data-gradient):
+//       GEMM rows enumerate grid positions, so tap (dy,dx) of row r is row r + dy*Wp + dx.  A persistent CTA
+//       stages ONE window of 128+maxshift rows per tile with cp.async and every tap is a UMMA descriptor whose
+//       start address is shifted by whole 128-byte rows (legal for SWIZZLE_128B: the pattern is a function of
+//       the smem address bits; tools/experiments/umma_shift_test.cu).  Weights stay resident in smem.
+//       Warps 0-3 produce, warp 4 issues tcgen05.mma, warps 5-8 drain double-buffered TMEM accumulators.
+//   tc_wgrad_win                 weight gradients: dW^T[(tap,c), co] = sum_r X[r+shift_tap, c] * dY[r, co]; the same
+//       row images are read as MN-major operands (rows = reduction index), taps again by row shifts.
+//   tc_gemm_ws<BN,STAGES,WRES>   fc forward / data-gradient: row-major A, weights streamed through the ring.
+//   tc_wgrad_ws                  fc weight gradient (MN-major views of dhid / act3 rows).
+//   tc_heads_*                   the A+1 head outputs in fp32 on CUDA cores.
 #include "common.cuh"
 #include "tc_common.cuh"
 
@@ -61,159 +65,6 @@ struct KGemmParams {
 };
 
 __device__ __forceinline__ int4 ldg16(const void* p) { return __ldg(reinterpret_cast<const int4*>(p)); }
-
-// ------------------------------------------------------------------ kernel 1
-template <int BN, int STAGES>
-__global__ void __launch_bounds__(128) tc_gemm_kmajor(const KGemmParams p) {
-    constexpr int A_BYTES = 128 * 128;
-    constexpr int B_BYTES = BN * 128;
-    constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-    constexpr uint32_t TMEM_COLS = BN < 32 ? 32 : BN;
-    extern __shared__ uint8_t smem_raw[];
-    __shared__ uint64_t empty_bar[STAGES];
-    __shared__ uint32_t tmem_base_smem;
-
-    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-    const int tid = threadIdx.x, warp = tid >> 5;
-    const int cls = blockIdx.x / p.tiles_per_class;
-    const int64_t row0 = (int64_t)(blockIdx.x - cls * p.tiles_per_class) * 128;
-    const int n0 = blockIdx.y * BN;
-    const bf16* Bw = p.Bw + (int64_t)cls * p.b_class_stride;
-    const int K = p.nchunks * 64;
-
-    if (tid == 0) {
-        for (int s = 0; s < STAGES; ++s) mbar_init(&empty_bar[s], 1);
-        fence_barrier_init();
-    }
-    if (warp == 0) tmem_alloc(&tmem_base_smem, TMEM_COLS);
-    tc_fence_before_sync();
-    __syncthreads();
-    tc_fence_after_sync();
-    const uint32_t tmem_d = tmem_base_smem;
-
-    // ---- per-thread row contexts (fixed for the whole K loop): 8 threads per row (one 16-byte chunk
-    // each), rows tid/8 + 16*pass
-    int64_t boff[8];
-    int pos[8];   // (ys << 16) | xs, or -1 when the row is out of range
-#pragma unroll
-    for (int ps = 0; ps < 8; ++ps) {
-        const int64_t r = row0 + ps * 16 + (tid >> 3);
-        if (r < p.M) {
-            const int64_t i = r / p.rpi;
-            const int rem = (int)(r - i * p.rpi);
-            const int y = rem / p.Ws, x = rem - y * p.Ws;
-            const int ys = y * p.sy, xs = x * p.sx;
-            const int64_t img = p.rows ? __ldg(p.rows + i) : i;
-            boff[ps] = ((img * p.SH + ys) * p.SW + xs) * (int64_t)p.CP;
-            pos[ps] = (ys << 16) | xs;
-        } else {
-            boff[ps] = 0;
-            pos[ps] = -1;
-        }
-    }
-    const int ppc = 64 / p.CP;   // source pixels covered by one 64-element chunk
-    constexpr uint32_t idesc = make_idesc(128, BN, 0, 0);
-
-    for (int j = 0; j < p.nchunks; ++j) {
-        const int s = j % STAGES;
-        const int use = j / STAGES;
-        if (use > 0) mbar_wait(&empty_bar[s], (use - 1) & 1);   // MMAs that read this stage are done
-        uint8_t* sA = smem + s * STAGE_BYTES;
-        uint8_t* sB = sA + A_BYTES;
-        // ---- stage A chunk j
-        {
-            const int dyj = p.dy[j], dxj = p.dx[j];
-            const int64_t doff = ((int64_t)dyj * p.SW + dxj) * p.CP + (tid & 7) * 8;
-#pragma unroll
-            for (int ps = 0; ps < 8; ++ps) {
-                int4 v = make_int4(0, 0, 0, 0);
-                bool ok = pos[ps] >= 0;
-                if (ok && p.check) {
-                    const int yy = (pos[ps] >> 16) + dyj, xx = (pos[ps] & 0xFFFF) + dxj;
-                    ok = (yy >= 0) && (yy < p.SH) && (xx >= 0) && (xx + ppc <= p.SW);
-                }
-                if (ok) v = ldg16(reinterpret_cast<const bf16*>(p.A) + boff[ps] + doff);
-                *reinterpret_cast<int4*>(sA + img_off(ps * 16 + (tid >> 3), tid & 7)) = v;
-            }
-        }
-        // ---- stage B chunk j: BN weight rows x 128 B
-#pragma unroll
-        for (int ps = 0; ps < BN / 16; ++ps) {
-            const int r = ps * 16 + (tid >> 3);
-            int4 v = make_int4(0, 0, 0, 0);
-            if (n0 + r < p.N) v = ldg16(Bw + (int64_t)(n0 + r) * K + j * 64 + (tid & 7) * 8);
-            *reinterpret_cast<int4*>(sB + img_off(r, tid & 7)) = v;
-        }
-        fence_proxy_async_smem();
-        __syncthreads();
-        if (tid == 0) {
-            tc_fence_after_sync();
-            const uint64_t adesc = desc_kmajor(smem_u32(sA));
-            const uint64_t bdesc = desc_kmajor(smem_u32(sB));
-#pragma unroll
-            for (int kk = 0; kk < 4; ++kk)   // 4 x (K = 16) per 64-wide chunk: +32 B inside the swizzle row
-                umma_bf16(tmem_d, adesc + 2 * kk, bdesc + 2 * kk, idesc, (j | kk) != 0);
-            umma_commit(&empty_bar[s]);
-        }
-    }
-    // ---- wait for the last chunk's MMAs (commit covers all earlier ones)
-    {
-        const int jl = p.nchunks - 1;
-        mbar_wait(&empty_bar[jl % STAGES], (jl / STAGES) & 1);
-        tc_fence_after_sync();
-    }
-    // ---- epilogue: thread <-> accumulator row (TMEM lane), 16 columns at a time
-    const int64_t r = row0 + tid;
-    int64_t ooff = 0;
-    bool rvalid = r < p.M;
-    if (rvalid) {
-        const int64_t i = r / p.rpi;
-        const int rem = (int)(r - i * p.rpi);
-        const int y = rem / p.Ws, x = rem - y * p.Ws;
-        const int ooy = p.nclasses > 1 ? (cls >> 1) : 0, oox = p.nclasses > 1 ? (cls & 1) : 0;
-        ooff = ((i * p.OH + y * p.osy + ooy) * p.OW + x * p.osx + oox) * (int64_t)p.ldo;
-    }
-    const uint32_t lane_addr = tmem_d + ((uint32_t)(warp * 32) << 16);
-#pragma unroll 1
-    for (int c0 = 0; c0 < BN; c0 += 16) {
-        uint32_t v[16];
-        tmem_ld16(lane_addr + c0, v);
-        tmem_ld_wait();
-        const int col = n0 + c0;
-        if (!rvalid || col >= p.N) continue;
-        float f[16];
-#pragma unroll
-        for (int e = 0; e < 16; ++e) {
-            f[e] = __uint_as_float(v[e]) * p.scale;
-            if (p.bias) f[e] += __ldg(p.bias + col + e);
-            if (p.relu) f[e] = fmaxf(f[e], 0.f);
-        }
-        if (p.mask) {
-            const int4 m0 = ldg16(p.mask + ooff + col);
-            const int4 m1 = ldg16(p.mask + ooff + col + 8);
-            const uint32_t mw[8] = {(uint32_t)m0.x, (uint32_t)m0.y, (uint32_t)m0.z, (uint32_t)m0.w,
-                                    (uint32_t)m1.x, (uint32_t)m1.y, (uint32_t)m1.z, (uint32_t)m1.w};
-#pragma unroll
-            for (int e = 0; e < 8; ++e) {
-                // post-ReLU activations are >= 0: "> 0" <=> any non-sign bit set
-                if ((mw[e] & 0x7FFFu) == 0u) f[2 * e] = 0.f;
-                if ((mw[e] & 0x7FFF0000u) == 0u) f[2 * e + 1] = 0.f;
-            }
-        }
-        int4 o0, o1;
-        o0.x = (int)pack_bf16x2(f[0], f[1]);   o0.y = (int)pack_bf16x2(f[2], f[3]);
-        o0.z = (int)pack_bf16x2(f[4], f[5]);   o0.w = (int)pack_bf16x2(f[6], f[7]);
-        o1.x = (int)pack_bf16x2(f[8], f[9]);   o1.y = (int)pack_bf16x2(f[10], f[11]);
-        o1.z = (int)pack_bf16x2(f[12], f[13]); o1.w = (int)pack_bf16x2(f[14], f[15]);
-        int4* dst = reinterpret_cast<int4*>(p.out + ooff + col);
-        dst[0] = o0;
-        dst[1] = o1;
-    }
-    tc_fence_before_sync();
-    __syncthreads();
-    if (warp == 0) tmem_dealloc(tmem_d, TMEM_COLS);
-}
-
 
 // ------------------------------------------------------------------ kernel 1b: persistent, warp-specialised
 // Same GEMM as tc_gemm_kmajor, restructured so that global-load latency never stalls the tensor core:
@@ -734,21 +585,6 @@ static int launch_kgemm_ws(const KGemmParams& p, cudaStream_t s, const char* wha
     return check_launch(what);
 }
 
-template <int BN, int STAGES>
-static int launch_kgemm(const KGemmParams& p, cudaStream_t s, const char* what) {
-    const size_t smem = (size_t)STAGES * (128 * 128 + BN * 128) + 1024;
-    static bool attr_done = false;
-    if (!attr_done) {
-        cudaError_t e = cudaFuncSetAttribute(tc_gemm_kmajor<BN, STAGES>,
-                                             cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e != cudaSuccess) return fail(B200RL_ERR_CUDA, "%s: smem attribute: %s", what, cudaGetErrorString(e));
-        attr_done = true;
-    }
-    dim3 grid((unsigned)(p.tiles_per_class * p.nclasses), (unsigned)ceil_div(p.N, BN));
-    tc_gemm_kmajor<BN, STAGES><<<grid, 128, smem, s>>>(p);
-    return check_launch(what);
-}
-
 // ------------------------------------------------------------------ kernel 2: weight gradient
 // D[kidx, co] = sum_m X[m, kidx] * dY[m, co].  X-side: nxc chunk images (64 kidx each); Y-side: nyc chunk
 // images (64 co each).  Each CTA owns the row range [m_begin, m_end) and ALL (X-tile, Y) outputs:
@@ -763,140 +599,6 @@ struct WGradParams {
     int64_t rows_per_cta;   // multiple of 32
     float* ws;              // [gridDim.x][gridDim.y*nxc*64][gridDim.z*nyc*64] fp32
 };
-
-__global__ void __launch_bounds__(128) tc_wgrad(const WGradParams p) {
-    constexpr int R = 32;            // reduction rows per stage (2 MMAs of K = 16)
-    constexpr int STAGES = 3;
-    extern __shared__ uint8_t smem_raw[];
-    __shared__ uint64_t empty_bar[STAGES];
-    __shared__ uint32_t tmem_base_smem;
-    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-    const int tid = threadIdx.x, warp = tid >> 5;
-    const KGemmParams& g = p.x;
-    const int nxc = p.nxc, nyc = p.nyc;
-    const int NY = nyc * 64;
-    const int xc0 = blockIdx.y * nxc;            // first X chunk of this CTA
-    const int yc0 = blockIdx.z * nyc;            // first Y chunk of this CTA
-    const int xt = nxc / 2;                      // 128-row output tiles
-    const int chunk_img = R * 128;               // bytes of one chunk image (R rows)
-    const int stage_bytes = (nxc + nyc) * chunk_img;
-    uint32_t tmem_cols = 32;
-    while ((int)tmem_cols < xt * NY) tmem_cols <<= 1;
-
-    if (tid == 0) {
-        for (int s = 0; s < STAGES; ++s) mbar_init(&empty_bar[s], 1);
-        fence_barrier_init();
-    }
-    if (warp == 0) tmem_alloc(&tmem_base_smem, tmem_cols);
-    tc_fence_before_sync();
-    __syncthreads();
-    tc_fence_after_sync();
-    const uint32_t tmem_d = tmem_base_smem;
-
-    const int64_t m_begin = (int64_t)blockIdx.x * p.rows_per_cta;
-    int64_t m_end = m_begin + p.rows_per_cta;
-    if (m_end > g.M) m_end = g.M;
-    const int ppc = 64 / g.CP;
-    const uint32_t idesc = make_idesc(128, NY, 1, 1);
-    int it = 0;
-    for (int64_t m0 = m_begin; m0 < m_end; m0 += R, ++it) {
-        const int s = it % STAGES, use = it / STAGES;
-        if (use > 0) mbar_wait(&empty_bar[s], (use - 1) & 1);
-        uint8_t* sX = smem + s * stage_bytes;
-        uint8_t* sY = sX + nxc * chunk_img;
-        // ---- X side: R rows x nxc chunks
-        {
-            // 8 threads per row, 16 rows per pass, 2 passes for R = 32
-#pragma unroll
-            for (int ps = 0; ps < R / 16; ++ps) {
-                const int rr = ps * 16 + (tid >> 3);
-                const int64_t r = m0 + rr;
-                bool rok = r < m_end;
-                int64_t bo = 0;
-                int ys = 0, xs = 0;
-                if (rok) {
-                    const int64_t i = r / g.rpi;
-                    const int rem = (int)(r - i * g.rpi);
-                    const int y = rem / g.Ws, x = rem - y * g.Ws;
-                    ys = y * g.sy; xs = x * g.sx;
-                    const int64_t img = g.rows ? __ldg(g.rows + i) : i;
-                    bo = ((img * g.SH + ys) * g.SW + xs) * (int64_t)g.CP;
-                }
-                for (int c = 0; c < nxc; ++c) {
-                    const int ch = xc0 + c;
-                    int4 v = make_int4(0, 0, 0, 0);
-                    bool ok = rok && ch < g.nchunks;
-                    if (ok) {
-                        const int dyj = g.dy[ch], dxj = g.dx[ch];
-                        if (g.check) {
-                            const int yy = ys + dyj, xx = xs + dxj;
-                            ok = (yy >= 0) && (yy < g.SH) && (xx >= 0) && (xx + ppc <= g.SW);
-                        }
-                        if (ok) v = ldg16(reinterpret_cast<const bf16*>(g.A) + bo + ((int64_t)dyj * g.SW + dxj) * g.CP + (tid & 7) * 8);
-                    }
-                    *reinterpret_cast<int4*>(sX + c * chunk_img + img_off(rr, tid & 7)) = v;
-                }
-            }
-        }
-        // ---- Y side: R rows x nyc chunks of dY
-#pragma unroll
-        for (int ps = 0; ps < R / 16; ++ps) {
-            const int rr = ps * 16 + (tid >> 3);
-            const int64_t r = m0 + rr;
-            for (int c = 0; c < nyc; ++c) {
-                int4 v = make_int4(0, 0, 0, 0);
-                const int col = (yc0 + c) * 64 + (tid & 7) * 8;
-                if (r < m_end && col < p.ncolsY) v = ldg16(p.Y + r * (int64_t)p.ldy + col);
-                *reinterpret_cast<int4*>(sY + c * chunk_img + img_off(rr, tid & 7)) = v;
-            }
-        }
-        fence_proxy_async_smem();
-        __syncthreads();
-        if (tid == 0) {
-            tc_fence_after_sync();
-            const uint32_t xa = smem_u32(sX), ya = smem_u32(sY);
-            for (int t = 0; t < xt; ++t) {
-#pragma unroll
-                for (int kk = 0; kk < R / 16; ++kk) {
-                    // A: 128 kidx = chunks 2t, 2t+1 (LBO = chunk image), K rows 16kk..16kk+15 (2 atoms, SBO 1024)
-                    const uint64_t adesc = desc_mnmajor(xa + (2 * t) * chunk_img + kk * 2048, chunk_img);
-                    const uint64_t bdesc = desc_mnmajor(ya + kk * 2048, chunk_img);
-                    umma_bf16(tmem_d + t * NY, adesc, bdesc, idesc, (it | kk) != 0);
-                }
-            }
-            umma_commit(&empty_bar[s]);
-        }
-    }
-    if (it > 0) {
-        const int il = it - 1;
-        mbar_wait(&empty_bar[il % STAGES], (il / STAGES) & 1);
-        tc_fence_after_sync();
-    }
-    // ---- epilogue: fp32 partials ws[cta][kidx][co]
-    const int64_t KXtot = (int64_t)gridDim.y * nxc * 64, NYtot = (int64_t)gridDim.z * NY;
-    float* wsb = p.ws + (int64_t)blockIdx.x * KXtot * NYtot;
-    const uint32_t lane_addr = tmem_d + ((uint32_t)(warp * 32) << 16);
-    for (int t = 0; t < xt; ++t) {
-        float* dst = wsb + ((int64_t)xc0 * 64 + t * 128 + tid) * NYtot + (int64_t)yc0 * 64;
-        for (int c0 = 0; c0 < NY; c0 += 16) {
-            uint32_t v[16];
-            if (it > 0) {
-                tmem_ld16(lane_addr + t * NY + c0, v);
-                tmem_ld_wait();
-            } else {
-#pragma unroll
-                for (int e = 0; e < 16; ++e) v[e] = 0u;
-            }
-#pragma unroll
-            for (int e = 0; e < 16; e += 4)
-                *reinterpret_cast<float4*>(dst + c0 + e) = make_float4(__uint_as_float(v[e]), __uint_as_float(v[e + 1]),
-                                                                         __uint_as_float(v[e + 2]), __uint_as_float(v[e + 3]));
-        }
-    }
-    tc_fence_before_sync();
-    __syncthreads();
-    if (warp == 0) tmem_dealloc(tmem_d, tmem_cols);
-}
 
 // ------------------------------------------------------------------ kernel 2b: warp-specialised weight gradient
 // Same math as tc_wgrad; warps 0-3 stream the X/Y row images with cp.async (LOOKAHEAD steps in flight),
@@ -1514,24 +1216,6 @@ static void set_rows(KGemmParams& p, int64_t M, int rpi, int Ws) {
     p.tiles_per_class = (int)ceil_div(M, 128);
 }
 
-static void conv1_gather(KGemmParams& p, const bf16* s2d, const int64_t* rows, int64_t n) {   // s2d [*,21,21,64]
-    p.A = s2d; p.rows = rows;
-    set_rows(p, n * 400, 400, 20);
-    p.SH = 21; p.SW = 21; p.CP = 64; p.nchunks = 4; p.check = 0;
-    for (int a = 0; a < 2; ++a) for (int b = 0; b < 2; ++b) { p.dy[a * 2 + b] = (signed char)a; p.dx[a * 2 + b] = (signed char)b; }
-}
-static void conv2_gather(KGemmParams& p, const bf16* act1, int64_t n) {
-    p.A = act1;
-    set_rows(p, n * 81, 81, 9);
-    p.SH = 20; p.SW = 20; p.CP = 32; p.sy = p.sx = 2; p.nchunks = 8; p.check = 0;
-    for (int ky = 0; ky < 4; ++ky) for (int h = 0; h < 2; ++h) { p.dy[ky * 2 + h] = (signed char)ky; p.dx[ky * 2 + h] = (signed char)(2 * h); }
-}
-static void conv3_gather(KGemmParams& p, const bf16* act2, int64_t n) {
-    p.A = act2;
-    set_rows(p, n * 49, 49, 7);
-    p.SH = 9; p.SW = 9; p.CP = 64; p.nchunks = 9; p.check = 0;
-    for (int ky = 0; ky < 3; ++ky) for (int kx = 0; kx < 3; ++kx) { p.dy[ky * 3 + kx] = (signed char)ky; p.dx[ky * 3 + kx] = (signed char)kx; }
-}
 static void rowmajor_gather(KGemmParams& p, const bf16* x, int64_t n, int nchunks) {   // x [n, 64*nchunks]
     p.A = x;
     set_rows(p, n, 1, 1);

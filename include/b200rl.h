@@ -202,7 +202,8 @@ int b200rl_linear_bwd_weight_f32(const float* x, const int64_t* rows, const floa
  * packed : bf16 GEMM operand copies of the weights (b200rl_naturecnn_bf16_packed_bytes), refreshed
  *          by b200rl_naturecnn_bf16_pack after every optimiser step.
  * acts   : activation + activation-gradient workspace for batch n (b200rl_naturecnn_bf16_acts_bytes);
- *          forward fills it, backward consumes it.
+ *          forward fills it, backward consumes it.  The caller must ZERO it once before its first use
+ *          with a given n (zero-padded gradient grids rely on never-written positions staying 0).
  * obs    : obs_format B200RL_OBS_U8_NCHW  : uint8 [*, 4, 84, 84] frames as the env delivers them, or
  *          obs_format B200RL_OBS_S2D_BF16 : bf16 [*, 21, 21, 64] space-to-depth frames produced ONCE per
  *          env step by b200rl_frames_to_s2d_bf16 (channel = c*16 + sy*4 + sx of pixel (4Y+sy, 4X+sx)):

@@ -127,3 +127,32 @@ def test_script_reproduces_reference_run(lib, name, gae_kernel):
             assert abs(got[0, 1] - ref[0, 1]) <= 1.01 / M, (tag, got[:, 1], ref[:, 1])
         else:
             assert np.allclose(got[0, 1], ref[0, 1], rtol=2e-4, atol=1e-4), (tag, got[:, 1], ref[:, 1])
+
+
+def test_ppo_mlp_script_reproduces_reference_run(lib):
+    """cleanrl_b200/ppo.py (MLP, fp32 kernels) vs the unmodified cleanrl/ppo.py on the CartPole-shaped synthetic
+    env (fixture ppo_mlp_n4_t128_seed1.npz): iteration 1 rollout bit-exact actions / 1e-5 floats, first-update
+    losses 1e-5, first 4 Adam steps of the flat parameters 1e-5."""
+    from cleanrl_b200 import ppo as S
+    z = np.load(GOLDEN / "ppo_mlp_n4_t128_seed1.npz")
+    argv = [a for a in z["argv"].tolist() if a != "--no-cuda"] + ["--synthetic-env"]
+    snaps = []
+
+    def on_it(it, eng, st):
+        snaps.append({k: getattr(eng, k).cpu().numpy().copy() for k in
+                      ("actions", "logprobs", "values", "rewards", "dones", "advantages", "returns")} | {"st": st})
+
+    def hook(agent):
+        agent.noise_fn = _cpu_noise
+
+    S.main(argv, writer_factory=_Writer, on_iteration=on_it, agent_hook=hook)
+    s0 = snaps[0]
+    assert np.array_equal(s0["actions"], z["actions"][0].astype(np.int64))
+    assert np.array_equal(s0["rewards"], z["rewards"][0]) and np.array_equal(s0["dones"], z["dones"][0])
+    for k in ("logprobs", "values", "advantages", "returns"):
+        assert _rel(s0[k], z[k][0]) <= 1e-5, (k, _rel(s0[k], z[k][0]))
+    per = s0["st"]["per_update"]
+    for u in range(4):
+        for col, key in ((0, "upd_pg_loss"), (1, "upd_v_loss"), (2, "upd_entropy_loss"), (4, "upd_approx_kl"), (6, "upd_loss")):
+            ref = float(z[key][u])
+            assert abs(per[u, col] - ref) <= (1e-5 if u == 0 else 1e-4) * max(1.0, abs(ref)), (u, key, per[u, col], ref)
