@@ -32,6 +32,11 @@ SIGNATURES = {
     "b200rl_ppo_loss_workspace_bytes": (_sz, [_i64]),
     "b200rl_ppo_loss_f32": (_i, [_p, _i64, _p, _i64, _p, _p, _p, _p, _p, _p, _i64, _i, _d, _d, _d, _i, _i,
                                  _p, _i64, _p, _i64, _p, _p, _sz, _p]),
+    "b200rl_gaussian_sample_f32": (_i, [_p, _i64, _p, _p, _p, _i64, _i64, _i, _p, _p, _p, _p, _p]),
+    "b200rl_gaussian_eval_f32": (_i, [_p, _i64, _p, _p, _i64, _i, _p, _p, _p]),
+    "b200rl_ppo_loss_gaussian_workspace_bytes": (_sz, [_i64]),
+    "b200rl_ppo_loss_gaussian_f32": (_i, [_p, _i64, _p, _p, _i64, _p, _p, _p, _p, _p, _p, _i64, _i, _d, _d, _d, _i, _i,
+                                          _p, _i64, _p, _p, _i64, _p, _p, _sz, _p]),
     "b200rl_clip_adam_workspace_bytes": (_sz, [_i64]),
     "b200rl_clip_adam_f32": (_i, [_p, _p, _p, _p, _i64, _i64, _d, _d, _d, _d, _d, _i, _p, _p, _sz, _p]),
     "b200rl_conv2d_fwd_f32": (_i, [_p, _i, _p, _d, _p, _p, _p, _i64, _i, _i, _i, _i, _i, _i, _i, _i, _p]),
@@ -42,6 +47,9 @@ SIGNATURES = {
     "b200rl_linear_bwd_data_f32": (_i, [_p, _p, _p, _i, _p, _i64, _i, _i, _p]),
     "b200rl_linear_bwd_weight_workspace_bytes": (_sz, [_i64, _i, _i]),
     "b200rl_linear_bwd_weight_f32": (_i, [_p, _p, _p, _p, _p, _i64, _i, _i, _p, _sz, _p]),
+    "b200rl_dqn_td_loss_workspace_bytes": (_sz, [_i64]),
+    "b200rl_dqn_td_loss_f32": (_i, [_p, _i64, _p, _i64, _p, _p, _p, _i64, _i, _d, _i, _p, _i64, _p, _p, _sz, _p]),
+    "b200rl_argmax_f32": (_i, [_p, _i64, _i64, _i, _p, _p]),
     "b200rl_naturecnn_param_count": (_i64, [_i]),
     "b200rl_naturecnn_bf16_packed_bytes": (_sz, [_i]),
     "b200rl_naturecnn_bf16_acts_bytes": (_sz, [_i64, _i]),

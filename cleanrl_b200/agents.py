@@ -73,6 +73,27 @@ class KernelAgent(nn.Module):
     def backward(self, dlogits, dvalue):
         raise NotImplementedError
 
+    # -- engine hooks (one policy step / one minibatch loss+backward) ---------------
+    action_dim = 0          # 0 = discrete (int64 actions [n]); D > 0 = continuous (f32 actions [n, D])
+
+    def sample_into(self, obs, actions_out, logprobs_out, values_out):
+        """Rollout step: forward + sample, writing straight into the rollout slots (ppo.py:197-202)."""
+        logits, value = self._forward_heads(obs)
+        n, A = logits.shape
+        q = self.noise_fn(n, A, logits.device)
+        ops.categorical_sample(logits, q, value, out=(actions_out, logprobs_out, None, values_out))
+
+    def loss_backward(self, policy_out, value, mb_inds, b, a, stats_row, scratch):
+        """Minibatch loss (+ its gradient) and the network backward (ppo.py:251-288)."""
+        M = policy_out.shape[0]
+        if scratch.get("M") != M:
+            scratch["M"] = M
+            scratch["dhead"], scratch["dl"], scratch["dv"] = self.alloc_head_grad(M, policy_out.device)
+        ops.ppo_loss(policy_out, value, mb_inds, b["actions"], b["logprobs"], b["advantages"], b["returns"], b["values"],
+                     a.clip_coef, a.ent_coef, a.vf_coef, a.norm_adv, a.clip_vloss,
+                     dlogits=scratch["dl"], dvalue=scratch["dv"], stats=stats_row)
+        self.backward(scratch["dhead"])
+
     # -- reference API ---------------------------------------------------------
     def get_value(self, x):
         self.flat
@@ -233,3 +254,75 @@ class MLPAgent(KernelAgent):
         dl, dv = dhead
         self.a_chain.bwd(dl)
         self.c_chain.bwd(dv)
+
+
+def _normal_noise(n, D, device):
+    # what Normal(mean, std).sample() == torch.normal(mean, std) consumes: one N(0,1) per element
+    return torch.randn(n, D, dtype=torch.float32, device=device)
+
+
+class ContinuousMLPAgent(KernelAgent):
+    """Gaussian-policy MLP agent (reference: cleanrl/ppo_continuous_action.py:112-141): ``critic`` and
+    ``actor_mean`` Sequentials plus the state-independent ``actor_logstd`` parameter [1, D]."""
+
+    def __init__(self, envs):
+        super().__init__()
+        d = int(np.array(envs.single_observation_space.shape).prod())
+        D = int(np.prod(envs.single_action_space.shape))
+        self.critic = nn.Sequential(layer_init(nn.Linear(d, 64)), nn.Tanh(), layer_init(nn.Linear(64, 64)), nn.Tanh(),
+                                    layer_init(nn.Linear(64, 1), std=1.0))
+        self.actor_mean = nn.Sequential(layer_init(nn.Linear(d, 64)), nn.Tanh(), layer_init(nn.Linear(64, 64)), nn.Tanh(),
+                                        layer_init(nn.Linear(64, D), std=0.01))
+        self.actor_logstd = nn.Parameter(torch.zeros(1, D))
+        self.action_dim = D
+        self.noise_fn = _normal_noise
+
+    def _build_plan(self):
+        mk = lambda seq: nets.Chain([nets.Linear(seq[0], "tanh"), nets.Linear(seq[2], "tanh"), nets.Linear(seq[4], None)])
+        self.c_chain, self.a_chain = mk(self.critic), mk(self.actor_mean)
+
+    def _forward_heads(self, x, rows=None, keep=False):
+        x = x.float() if x.dtype != torch.float32 else x
+        x = x.reshape(x.shape[0], -1).contiguous()
+        mean = self.a_chain.fwd(x, rows=rows, keep=keep)
+        value = self.c_chain.fwd(x, rows=rows, keep=keep)
+        return mean, value[:, 0]
+
+    def forward_train(self, b_obs, mb_inds):
+        self.flat
+        return self._forward_heads(b_obs, rows=mb_inds, keep=True)
+
+    def _logstd(self):
+        return self.actor_logstd.data.view(-1)
+
+    def sample_into(self, obs, actions_out, logprobs_out, values_out):
+        mean, value = self._forward_heads(obs)
+        n, D = mean.shape
+        eps = self.noise_fn(n, D, mean.device)
+        ops.gaussian_sample(mean, self._logstd(), eps, value, out=(actions_out, logprobs_out, None, values_out))
+
+    def loss_backward(self, policy_out, value, mb_inds, b, a, stats_row, scratch):
+        M, D = policy_out.shape
+        dev = policy_out.device
+        if scratch.get("M") != M:
+            scratch["M"] = M
+            scratch["dmean"] = torch.empty(M, D, dtype=torch.float32, device=dev)
+            scratch["dv"] = torch.empty(M, 1, dtype=torch.float32, device=dev)
+        ops.ppo_loss_gaussian(policy_out, self._logstd(), value, mb_inds, b["actions"], b["logprobs"], b["advantages"],
+                              b["returns"], b["values"], a.clip_coef, a.ent_coef, a.vf_coef, a.norm_adv, a.clip_vloss,
+                              dmean=scratch["dmean"], dlogstd=self.actor_logstd.grad.view(-1), dvalue=scratch["dv"][:, 0],
+                              stats=stats_row)
+        self.a_chain.bwd(scratch["dmean"])
+        self.c_chain.bwd(scratch["dv"])
+
+    def get_action_and_value(self, x, action=None):
+        self.flat
+        mean, value = self._forward_heads(x)
+        n, D = mean.shape
+        if action is None:
+            eps = self.noise_fn(n, D, mean.device)
+            action, logprob, entropy, v = ops.gaussian_sample(mean, self._logstd(), eps, value)
+        else:
+            logprob, entropy = ops.gaussian_eval(mean, self._logstd(), action)
+            v = value.clone() if not value.is_contiguous() else value
+        return action, logprob, entropy, v.reshape(-1, 1)

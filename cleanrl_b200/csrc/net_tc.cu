@@ -1083,21 +1083,27 @@ __global__ void tc_pack_fc(const float* __restrict__ w, int O, int C, int PP, bf
 }
 
 // ------------------------------------------------------------------ policy/value heads (tiny: CUDA cores, fp32 math)
-// out[n][A1] = hidden[n][512](bf16) . Wh[A1][512]^T + bh    (one warp per row)
+// out[n][A1] = hidden[n][512](bf16) . Wh[A1][512]^T + bh.  Head weights staged in smem once per block,
+// one warp per row (16 hidden values per lane, coalesced 64-B loads), rows strided over a persistent grid.
 __global__ void __launch_bounds__(256) tc_heads_fwd(const bf16* __restrict__ hid, const float* __restrict__ Wh,
                                                     const float* __restrict__ bh, int64_t n, int A1, int H,
                                                     float* __restrict__ out) {
-    const int64_t row = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-    const int lane = threadIdx.x & 31;
-    if (row >= n) return;
-    float hv[16];
-    const bf16* hp = hid + row * H;
-    for (int q = 0; q < H / 32 && q < 16; ++q) hv[q] = __bfloat162float(hp[q * 32 + lane]);
-    for (int a = 0; a < A1; ++a) {
-        float s = 0.f;
-        for (int q = 0; q < H / 32 && q < 16; ++q) s = fmaf(hv[q], __ldg(Wh + (int64_t)a * H + q * 32 + lane), s);
-        s = warp_sum(s);
-        if (lane == 0) out[row * A1 + a] = s + bh[a];
+    __shared__ float sW[8 * 512];
+    for (int i = threadIdx.x; i < A1 * 512; i += blockDim.x) sW[i] = Wh[i];
+    __syncthreads();
+    const int lane = threadIdx.x & 31, wpb = blockDim.x >> 5;
+    for (int64_t row = (int64_t)blockIdx.x * wpb + (threadIdx.x >> 5); row < n; row += (int64_t)gridDim.x * wpb) {
+        float hv[16];
+        const bf16* hp = hid + row * 512;
+#pragma unroll
+        for (int q = 0; q < 16; ++q) hv[q] = __bfloat162float(hp[q * 32 + lane]);
+        for (int a = 0; a < A1; ++a) {
+            float s = 0.f;
+#pragma unroll
+            for (int q = 0; q < 16; ++q) s = fmaf(hv[q], sW[a * 512 + q * 32 + lane], s);
+            s = warp_sum(s);
+            if (lane == 0) out[row * A1 + a] = s + bh[a];
+        }
     }
 }
 // dhid_pre[n][512] (bf16) = (dhead[n][A1] . Wh[A1][512]) * (hid > 0)
@@ -1390,10 +1396,13 @@ extern "C" int b200rl_naturecnn_bf16_forward(const void* obs, int obs_format, co
     gemm_defaults(p); rowmajor_gather(p, act + Q.act3, n, 49);
     p.Bw = P + L.wfcf; p.N = 512; p.out = act + Q.hid; p.OH = 1; p.OW = 1; p.ldo = 512; p.bias = params + L.fcb; p.relu = 1;
     { ProfScope ps(s, "fc_fwd", 2.0 * n * 512 * 3136, (double)n * (3136 + 512) * 2 + 512.0 * 3136 * 2);
-      if ((rc = launch_kgemm_ws<256, 4, false>(p, s, "naturecnn/fc"))) return rc; }
+      // small batches (rollout step): narrower N tiles => 4x more CTAs for the same work
+      if (n <= 8192) { if ((rc = launch_kgemm_ws<64, 8, false>(p, s, "naturecnn/fc"))) return rc; }
+      else if ((rc = launch_kgemm_ws<256, 4, false>(p, s, "naturecnn/fc"))) return rc; }
     // heads (fp32 math on CUDA cores): head_out [n, A+1] = [logits | value]
     { ProfScope ps(s, "heads_fwd", 2.0 * n * 512 * (A + 1), (double)n * (1024 + 4 * (A + 1)));
-      tc_heads_fwd<<<(unsigned)ceil_div(n, 8), 256, 0, s>>>(act + Q.hid, params + L.hw, params + L.hb, n, A + 1, 512, head_out); }
+      int hb = (int)ceil_div(n, 8); if (hb > num_sms() * 8) hb = num_sms() * 8;
+      tc_heads_fwd<<<hb, 256, 0, s>>>(act + Q.hid, params + L.hw, params + L.hb, n, A + 1, 512, head_out); }
     return check_launch("naturecnn/heads");
 }
 

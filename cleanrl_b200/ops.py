@@ -371,3 +371,105 @@ def frames_to_s2d(obs_u8, out=None, rows=None):
                                        _ptr(out, torch.bfloat16, "out"), _stream())
     _lib.check(rc, "frames_to_s2d")
     return out
+
+
+# ----------------------------------------------------------- diagonal Gaussian policy
+def gaussian_sample(mean, logstd, noise, value_in=None, out=None):
+    """action, logprob, entropy[, value] for Normal(mean, exp(logstd)) with caller-supplied N(0,1) noise
+    (reference: ppo_continuous_action.py:134-141)."""
+    lib = _lib.load()
+    n, D = mean.shape
+    assert mean.stride(1) == 1
+    _contig(noise, "noise"); _contig(logstd, "logstd")
+    dev = mean.device
+    f = torch.float32
+    if out is None:
+        action = torch.empty(n, D, dtype=f, device=dev)
+        logprob = torch.empty(n, dtype=f, device=dev)
+        entropy = torch.empty(n, dtype=f, device=dev)
+        value = torch.empty(n, dtype=f, device=dev) if value_in is not None else None
+    else:
+        action, logprob, entropy, value = out
+    ldv = 0
+    if value_in is not None:
+        value_in = value_in.reshape(n, -1)
+        ldv = value_in.stride(0)
+    rc = lib.b200rl_gaussian_sample_f32(_ptr(mean, f, "mean"), mean.stride(0), _ptr(logstd, f, "logstd"), _ptr(noise, f, "noise"),
+                                        _ptr(value_in, f, "value_in", True), ldv, n, D, _ptr(action, f, "action"),
+                                        _ptr(logprob, f, "logprob"), _ptr(entropy, f, "entropy", True),
+                                        _ptr(value, f, "value_out", True), _stream())
+    _lib.check(rc, "gaussian_sample")
+    return action, logprob, entropy, value
+
+
+def gaussian_eval(mean, logstd, action):
+    lib = _lib.load()
+    n, D = mean.shape
+    f = torch.float32
+    action = _contig(action.reshape(n, D), "action")
+    logprob = torch.empty(n, dtype=f, device=mean.device)
+    entropy = torch.empty(n, dtype=f, device=mean.device)
+    rc = lib.b200rl_gaussian_eval_f32(_ptr(mean, f, "mean"), mean.stride(0), _ptr(logstd, f, "logstd"), _ptr(action, f, "action"),
+                                      n, D, _ptr(logprob, f, "logprob"), _ptr(entropy, f, "entropy"), _stream())
+    _lib.check(rc, "gaussian_eval")
+    return logprob, entropy
+
+
+def ppo_loss_gaussian(new_mean, logstd, new_value, mb_inds, b_actions, b_logprobs, b_advantages, b_returns, b_values,
+                      clip_coef, ent_coef, vf_coef, norm_adv=True, clip_vloss=True, dmean=None, dlogstd=None, dvalue=None,
+                      stats=None):
+    """Continuous-action PPO loss + gradients (reference: ppo_continuous_action.py:262-300)."""
+    lib = _lib.load()
+    M, D = new_mean.shape
+    dev = new_mean.device
+    f = torch.float32
+    new_value = new_value.reshape(M, -1)
+    if dmean is None:
+        dmean = torch.empty(M, D, dtype=f, device=dev)
+    if dlogstd is None:
+        dlogstd = torch.empty(D, dtype=f, device=dev)
+    if dvalue is None:
+        dvalue = torch.empty(M, dtype=f, device=dev)
+    dv2 = dvalue.reshape(M, -1)
+    if stats is None:
+        stats = torch.zeros(16, dtype=f, device=dev)
+    ws = _workspace(dev, "gloss", lib.b200rl_ppo_loss_gaussian_workspace_bytes(M))
+    rc = lib.b200rl_ppo_loss_gaussian_f32(
+        _ptr(new_mean, f, "new_mean"), new_mean.stride(0), _ptr(logstd, f, "logstd"),
+        _ptr(new_value, f, "new_value"), new_value.stride(0), _ptr(mb_inds, torch.int64, "mb_inds", True),
+        _ptr(b_actions, f, "b_actions"), _ptr(b_logprobs, f, "b_logprobs"), _ptr(b_advantages, f, "b_advantages"),
+        _ptr(b_returns, f, "b_returns"), _ptr(b_values, f, "b_values"), M, D, float(clip_coef), float(ent_coef),
+        float(vf_coef), int(bool(norm_adv)), int(bool(clip_vloss)), _ptr(dmean, f, "dmean"), dmean.stride(0),
+        _ptr(dlogstd, f, "dlogstd"), _ptr(dv2, f, "dvalue"), dv2.stride(0), _ptr(stats, f, "stats"),
+        ws.data_ptr(), ws.numel(), _stream())
+    _lib.check(rc, "ppo_loss_gaussian")
+    return stats, dmean, dlogstd, dvalue
+
+
+# ------------------------------------------------------------------------ DQN
+def dqn_td_loss(q, q_target_next, actions, rewards, dones, gamma, huber=False, dq=None, stats=None):
+    """TD target, loss and dL/dQ (reference: dqn_atari.py:220-224).  Returns (stats[2] = td_loss, mean Q; dq)."""
+    lib = _lib.load()
+    B, A = q.shape
+    f = torch.float32
+    if dq is None:
+        dq = torch.empty(B, A, dtype=f, device=q.device)
+    if stats is None:
+        stats = torch.zeros(2, dtype=f, device=q.device)
+    ws = _workspace(q.device, "td", lib.b200rl_dqn_td_loss_workspace_bytes(B))
+    rc = lib.b200rl_dqn_td_loss_f32(_ptr(q, f, "q"), q.stride(0), _ptr(q_target_next, f, "q_target_next"), q_target_next.stride(0),
+                                    _ptr(_contig(actions.reshape(-1), "actions"), torch.int64, "actions"),
+                                    _ptr(_contig(rewards.reshape(-1), "rewards"), f, "rewards"),
+                                    _ptr(_contig(dones.reshape(-1), "dones"), f, "dones"), B, A, float(gamma), int(bool(huber)),
+                                    _ptr(dq, f, "dq"), dq.stride(0), _ptr(stats, f, "stats"), ws.data_ptr(), ws.numel(), _stream())
+    _lib.check(rc, "dqn_td_loss")
+    return stats, dq
+
+
+def argmax(q):
+    lib = _lib.load()
+    n, A = q.shape
+    out = torch.empty(n, dtype=torch.int64, device=q.device)
+    rc = lib.b200rl_argmax_f32(_ptr(q, torch.float32, "q"), q.stride(0), n, A, _ptr(out, torch.int64, "out"), _stream())
+    _lib.check(rc, "argmax")
+    return out

@@ -72,7 +72,11 @@ class PPOEngine:
             self.obs_u8 = torch.zeros((N,) + tuple(obs_shape), dtype=torch.uint8, device=device)
         else:
             self.obs = torch.zeros((T, N) + tuple(obs_shape), dtype=self.obs_dtype, device=device)
-        self.actions = torch.zeros((T, N), dtype=torch.int64, device=device)
+        self.act_dim = int(getattr(agent, "action_dim", 0))
+        if self.act_dim:     # continuous actions (ppo_continuous_action.py:213): f32 [T, N, D]
+            self.actions = torch.zeros((T, N, self.act_dim), dtype=f32, device=device)
+        else:                # discrete: stored as int64 (the reference stores fp32 and re-casts .long() per minibatch)
+            self.actions = torch.zeros((T, N), dtype=torch.int64, device=device)
         self.logprobs = torch.zeros((T, N), dtype=f32, device=device)
         self.values = torch.zeros((T, N), dtype=f32, device=device)
         self.rewards = torch.zeros((T, N), dtype=f32, device=device)
@@ -86,7 +90,7 @@ class PPOEngine:
         self.rewards_h = _pin(torch.zeros((T, N), dtype=f32))
         self.dones_h = _pin(torch.zeros((T, N), dtype=f32))
         self.next_done_h = _pin(torch.zeros(N, dtype=f32))
-        self.actions_h = _pin(torch.zeros(N, dtype=torch.int64))
+        self.actions_h = _pin(torch.zeros_like(self.actions[0], device="cpu"))
         self.obs_stage_h = _pin(torch.zeros((N,) + tuple(obs_shape), dtype=self.obs_dtype))
         E = int(args.update_epochs)
         self.b_inds_h = _pin(torch.zeros((E, self.B), dtype=torch.int64))   # one slot per epoch: a pinned
@@ -121,13 +125,9 @@ class PPOEngine:
         Reference: ppo.py:194-205 (store obs/done, no-grad policy, action.cpu())."""
         self._upload_obs(self.obs[step], next_obs_np)
         self.dones_h[step].copy_(torch.as_tensor(np.asarray(next_done_np, dtype=np.float32)))
-        logits, value = self.agent._forward_heads(self.obs[step])
-        n, A = logits.shape
-        q = self.agent.noise_fn(n, A, self.device)
-        ops.categorical_sample(logits, q, value,
-                               out=(self.actions[step], self.logprobs[step], None, self.values[step]))
+        self.agent.sample_into(self.obs[step], self.actions[step], self.logprobs[step], self.values[step])
         self.actions_h.copy_(self.actions[step], non_blocking=True)
-        self.d2h_bytes += self.actions_h.numel() * 8
+        self.d2h_bytes += self.actions_h.numel() * self.actions_h.element_size()
         _sync()
         return self.actions_h.numpy()
 
@@ -139,11 +139,7 @@ class PPOEngine:
             ops.frames_to_s2d(obs_dev, out=self.obs[step])
         else:
             self.obs[step].copy_(obs_dev)
-        logits, value = self.agent._forward_heads(self.obs[step])
-        n, A = logits.shape
-        q = self.agent.noise_fn(n, A, self.device)
-        ops.categorical_sample(logits, q, value,
-                               out=(self.actions[step], self.logprobs[step], None, self.values[step]))
+        self.agent.sample_into(self.obs[step], self.actions[step], self.logprobs[step], self.values[step])
 
     def record_reward(self, step, reward_np):
         self.rewards_h[step].copy_(torch.as_tensor(np.asarray(reward_np, dtype=np.float32).reshape(-1)))
@@ -174,13 +170,11 @@ class PPOEngine:
         B, M = self.B, self.M
         agent, flat = self.agent, self.flat
         b_obs = self.obs.view((B,) + tuple(self.obs.shape[2:]))
-        b_actions = self.actions.view(B)
-        b_logprobs = self.logprobs.view(B)
-        b_adv = self.advantages.view(B)
-        b_ret = self.returns.view(B)
-        b_val = self.values.view(B)
+        b = {"actions": self.actions.view((B,) + tuple(self.actions.shape[2:])), "logprobs": self.logprobs.view(B),
+             "advantages": self.advantages.view(B), "returns": self.returns.view(B), "values": self.values.view(B)}
         b_inds_np = np.arange(B)
-        dhead, dlogits, dvalue = agent.alloc_head_grad(M, self.device)
+        if not hasattr(self, "_scratch"):
+            self._scratch = {}
         k = 0
         E = int(a.update_epochs)
         pre = a.target_kl is None
@@ -200,11 +194,8 @@ class PPOEngine:
                 self.h2d_bytes += B * 8
             for start in range(0, B, M):
                 mb_inds = self.b_inds[epoch, start:start + M]
-                logits, value = agent.forward_train(b_obs, mb_inds)
-                ops.ppo_loss(logits, value, mb_inds, b_actions, b_logprobs, b_adv, b_ret, b_val,
-                             a.clip_coef, a.ent_coef, a.vf_coef, a.norm_adv, a.clip_vloss,
-                             dlogits=dlogits, dvalue=dvalue, stats=self.stats[k])
-                agent.backward(dhead)
+                policy_out, value = agent.forward_train(b_obs, mb_inds)
+                agent.loss_backward(policy_out, value, mb_inds, b, a, self.stats[k], self._scratch)
                 if self.world_size > 1:
                     self.all_reduce(flat.grad)
                 flat.step += 1

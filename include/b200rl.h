@@ -127,6 +127,28 @@ int b200rl_ppo_loss_f32(const float* new_logits, int64_t ld_logits,
                         float* dlogits, int64_t ld_dlogits, float* dvalue, int64_t ld_dvalue,
                         float* stats, void* workspace, size_t workspace_bytes, void* stream);
 
+/* ------------------------------------------------ diagonal Gaussian policy --
+ * Continuous-action twin of the three entry points above (cleanrl/ppo_continuous_action.py:134-141:
+ * Normal(action_mean, exp(actor_logstd)), log_prob(a).sum(1), entropy().sum(1)).
+ *   mean f32 [n, D] (row stride ld_mean), logstd f32 [D] (the state-independent actor_logstd parameter),
+ *   noise f32 [n, D] N(0,1) from the caller's generator (torch.normal(mean, std) == randn*std + mean),
+ *   action f32 [n, D].  The loss additionally returns dlogstd [D] (deterministic batch reduction).
+ */
+int b200rl_gaussian_sample_f32(const float* mean, int64_t ld_mean, const float* logstd, const float* noise,
+                               const float* value_in, int64_t ld_value, int64_t n, int D,
+                               float* action, float* logprob, float* entropy, float* value_out, void* stream);
+int b200rl_gaussian_eval_f32(const float* mean, int64_t ld_mean, const float* logstd, const float* action,
+                             int64_t n, int D, float* logprob, float* entropy, void* stream);
+size_t b200rl_ppo_loss_gaussian_workspace_bytes(int64_t M);
+int b200rl_ppo_loss_gaussian_f32(const float* new_mean, int64_t ld_mean, const float* logstd,
+                                 const float* new_value, int64_t ld_value, const int64_t* mb_inds,
+                                 const float* b_actions, const float* b_logprobs,
+                                 const float* b_advantages, const float* b_returns, const float* b_values,
+                                 int64_t M, int D, double clip_coef, double ent_coef, double vf_coef,
+                                 int norm_adv, int clip_vloss,
+                                 float* dmean, int64_t ld_dmean, float* dlogstd, float* dvalue, int64_t ld_dvalue,
+                                 float* stats, void* workspace, size_t workspace_bytes, void* stream);
+
 /* ------------------------------------------------- grad clip + Adam step ---
  * One fused optimiser step over a FLAT f32 parameter vector: optional DP
  * averaging (grads hold the all-reduced SUM; divided by world_size first, as
@@ -226,6 +248,21 @@ int b200rl_naturecnn_bf16_backward(const void* obs, int obs_format, const int64_
                                    const float* params, const void* packed, void* acts,
                                    const float* dhead, float* grads,
                                    void* workspace, size_t workspace_bytes, void* stream);
+
+/* --------------------------------------------------------- DQN TD update ---
+ * td_target = r + gamma * max_a' Q_target(s')[a'] * (1 - done); old = Q(s)[a]; loss = mean((td - old)^2)
+ * (F.mse_loss, cleanrl/dqn_atari.py:220-224; huber = 1: smooth-L1) and dL/dQ [B, A] in one pass.
+ *   q, q_target_next : f32 [B, A] (row strides ld_q, ld_qt); actions i64 [B]; rewards, dones f32 [B]
+ *   dq f32 [B, A] out; stats f32 [2] out: td_loss, mean chosen Q (the two logged scalars, dqn_atari.py:227-228)
+ * b200rl_argmax_f32: greedy action of the epsilon-greedy policy (dqn_atari.py:192-193), first maximum.
+ */
+size_t b200rl_dqn_td_loss_workspace_bytes(int64_t B);
+int b200rl_dqn_td_loss_f32(const float* q, int64_t ld_q, const float* q_target_next, int64_t ld_qt,
+                           const int64_t* actions, const float* rewards, const float* dones,
+                           int64_t B, int A, double gamma, int huber,
+                           float* dq, int64_t ld_dq, float* stats,
+                           void* workspace, size_t workspace_bytes, void* stream);
+int b200rl_argmax_f32(const float* q, int64_t ld_q, int64_t n, int A, int64_t* out, void* stream);
 
 #ifdef __cplusplus
 }

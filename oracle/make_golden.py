@@ -67,8 +67,28 @@ def mlp_ppo(name, argv):
     print("wrote", name)
 
 
+def continuous(name, argv, n_iter):
+    """cleanrl/ppo_continuous_action.py on the HalfCheetah-shaped synthetic env (obs 17, act 6)."""
+    rec, g = run_reference("ppo_continuous_action.py", argv, gymnasium_kind="continuous")
+    assert len(rec.iterations) == n_iter
+    out = {"argv": np.array(argv)}
+    for k in ("actions", "logprobs", "rewards", "dones", "values", "advantages", "returns", "next_value", "next_done",
+              "param_sums"):
+        out[k] = _stack(rec.iterations, k)
+    for k in ("pg_loss", "v_loss", "entropy_loss", "old_approx_kl", "approx_kl", "loss", "clipfrac", "lr"):
+        out["upd_" + k] = np.array([u[k] for u in rec.updates])
+    out["upd_param_sums"] = _stack(rec.updates, "param_sums")
+    out["shuffles"] = np.stack(rec.shuffles)
+    out["state_dict_keys"] = np.array(list(g["agent"].state_dict().keys()))
+    np.savez_compressed(OUT / name, **out)
+    print("wrote", name)
+
+
 def main():
     OUT.mkdir(parents=True, exist_ok=True)
+    continuous("ppo_continuous_n4_t64_seed2.npz",
+               ["--no-cuda", "--num-envs", "4", "--num-steps", "64", "--total-timesteps", "512", "--seed", "2",
+                "--num-minibatches", "4", "--update-epochs", "2"], 2)
     atari_envpool("ppo_atari_envpool_n8_t32_seed1.npz",
                   ["--no-cuda", "--num-envs", "8", "--num-steps", "32", "--total-timesteps", "768", "--seed", "1"], 3)
     atari_envpool("ppo_atari_envpool_n16_t16_seed3_noclipv.npz",

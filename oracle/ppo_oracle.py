@@ -204,3 +204,107 @@ def explained_variance(values, returns):
     y_pred, y_true = np.asarray(values), np.asarray(returns)
     var_y = np.var(y_true)
     return np.nan if var_y == 0 else 1 - np.var(y_true - y_pred) / var_y
+
+
+# ------------------------------------------------------------- diagonal Gaussian
+_LOG_SQRT_2PI = f32(0.9189385332046727)   # math.log(math.sqrt(2 * math.pi)), torch/distributions/normal.py
+
+
+def gaussian_eval(mean, logstd, action):
+    """``Normal(mean, exp(logstd)).log_prob(a).sum(1)`` and ``.entropy().sum(1)``
+    (cleanrl/ppo_continuous_action.py:134-141; torch/distributions/normal.py log_prob / entropy)."""
+    mean = np.asarray(mean, dtype=f32)
+    a = np.asarray(action, dtype=f32)
+    std = np.exp(np.asarray(logstd, dtype=f32).reshape(1, -1))
+    var = std * std
+    ls = np.log(std)
+    lp = (-((a - mean) ** 2) / (f32(2) * var) - ls - _LOG_SQRT_2PI).sum(axis=1, dtype=f32)
+    ent = np.broadcast_to(f32(0.5) + _LOG_SQRT_2PI + ls, mean.shape).sum(axis=1, dtype=f32)
+    return lp.astype(f32), ent.astype(f32)
+
+
+def gaussian_sample(mean, logstd, noise):
+    """``Normal.sample()`` == ``torch.normal(mean, std)`` == ``randn.mul_(std).add_(mean)`` with the N(0,1)
+    draws supplied by the caller's generator."""
+    mean = np.asarray(mean, dtype=f32)
+    std = np.exp(np.asarray(logstd, dtype=f32).reshape(1, -1))
+    a = (np.asarray(noise, dtype=f32) * std + mean).astype(f32)
+    return (a,) + gaussian_eval(mean, logstd, a)
+
+
+def ppo_loss_gaussian(new_mean, logstd, new_value, mb_inds, b_actions, b_logprobs, b_advantages, b_returns, b_values,
+                      clip_coef, ent_coef, vf_coef, norm_adv=True, clip_vloss=True):
+    """Continuous-action twin of ``ppo_loss`` (cleanrl/ppo_continuous_action.py:262-300).
+    Returns (stats, dmean [M,D], dlogstd [D], dvalue [M])."""
+    new_mean = np.asarray(new_mean, dtype=f32)
+    M, D = new_mean.shape
+    idx = np.arange(M) if mb_inds is None else np.asarray(mb_inds)
+    a = np.asarray(b_actions, dtype=f32).reshape(-1, D)[idx]
+    newlogprob, entropy = gaussian_eval(new_mean, logstd, a)
+    logratio = newlogprob - np.asarray(b_logprobs, dtype=f32)[idx]
+    ratio = np.exp(logratio, dtype=f32)
+    adv = np.asarray(b_advantages, dtype=f32)[idx]
+    adv_mean, adv_std = f32(0), f32(1)
+    if norm_adv:
+        adv_mean = adv.mean(dtype=f32)
+        adv_std = f32(np.sqrt(((adv - adv_mean) ** 2).sum(dtype=f32) / f32(M - 1)))
+        adv = (adv - adv_mean) / (adv_std + f32(1e-8))
+    lo, hi = f32(1 - clip_coef), f32(1 + clip_coef)
+    pg1 = -adv * ratio
+    pg2 = -adv * np.clip(ratio, lo, hi)
+    pg_loss = np.maximum(pg1, pg2).mean(dtype=f32)
+    nv = np.asarray(new_value, dtype=f32).reshape(M)
+    R = np.asarray(b_returns, dtype=f32)[idx]
+    V = np.asarray(b_values, dtype=f32)[idx]
+    c = f32(clip_coef)
+    if clip_vloss:
+        vu = (nv - R) ** 2
+        d = nv - V
+        vcl = V + np.clip(d, -c, c)
+        vc = (vcl - R) ** 2
+        v_loss = f32(0.5) * np.maximum(vu, vc).mean(dtype=f32)
+        gu = f32(2) * (nv - R)
+        gc = f32(2) * (vcl - R) * ((d >= -c) & (d <= c)).astype(f32)
+        gv = np.where(vu > vc, gu, f32(0)) + np.where(vc > vu, gc, f32(0)) + np.where(vu == vc, f32(0.5) * (gu + gc), f32(0))
+    else:
+        v_loss = f32(0.5) * ((nv - R) ** 2).mean(dtype=f32)
+        gv = f32(2) * (nv - R)
+    ent_loss = entropy.mean(dtype=f32)
+    loss = pg_loss - f32(ent_coef) * ent_loss + v_loss * f32(vf_coef)
+    invM = f32(1.0) / f32(M)
+    inrange = ((ratio >= lo) & (ratio <= hi)).astype(f32)
+    g_ratio = np.where(pg1 > pg2, -adv, f32(0)) + np.where(pg1 == pg2, f32(0.5) * (-adv) * (f32(1) + inrange), f32(0))
+    g_lp = (g_ratio * ratio * invM).astype(f32)
+    std = np.exp(np.asarray(logstd, dtype=f32).reshape(1, -1))
+    var = std * std
+    diff = a - new_mean
+    dmean = g_lp[:, None] * diff / var
+    dlogstd = (g_lp[:, None] * (diff * diff / var - f32(1))).sum(axis=0, dtype=f32) - f32(ent_coef)
+    dvalue = f32(vf_coef) * f32(0.5) * invM * gv
+    stats = dict(pg_loss=pg_loss, v_loss=v_loss, entropy=ent_loss, old_approx_kl=(-logratio).mean(dtype=f32),
+                 approx_kl=((ratio - f32(1)) - logratio).mean(dtype=f32),
+                 clipfrac=(np.abs(ratio - f32(1.0)) > c).astype(f32).mean(dtype=f32), loss=loss,
+                 adv_mean=adv_mean, adv_std=adv_std)
+    return stats, dmean.astype(f32), dlogstd.astype(f32), dvalue.astype(f32)
+
+
+# ------------------------------------------------------------------------ DQN
+def dqn_td_loss(q, q_target_next, actions, rewards, dones, gamma, huber=False):
+    """cleanrl/dqn_atari.py:220-224: td_target = r + gamma * max_a' Qt * (1 - d); old = Q[a]; F.mse_loss(td, old)
+    (``huber``: F.smooth_l1_loss).  Returns (td_loss, mean chosen Q, dL/dQ [B, A])."""
+    q = np.asarray(q, dtype=f32); qt = np.asarray(q_target_next, dtype=f32)
+    B, A = q.shape
+    a = np.asarray(actions).reshape(B).astype(np.int64)
+    td = np.asarray(rewards, dtype=f32).reshape(B) + (f32(gamma) * qt.max(axis=1)) * (f32(1) - np.asarray(dones, dtype=f32).reshape(B))
+    old = q[np.arange(B), a]
+    x = old - td
+    if huber:
+        ax = np.abs(x)
+        per = np.where(ax < 1, f32(0.5) * x * x, ax - f32(0.5))
+        g = np.clip(x, -1, 1)
+    else:
+        per = x * x
+        g = f32(2) * x
+    dq = np.zeros((B, A), dtype=f32)
+    dq[np.arange(B), a] = g / f32(B)
+    return per.mean(dtype=f32), old.mean(dtype=f32), dq

@@ -169,3 +169,45 @@ def test_loss_oracle_gradients_vs_torch_autograd():
         assert abs(float(st["loss"]) - float(loss)) < 1e-6
         assert np.abs(dl - logits.grad.numpy()).max() < 1e-8
         assert np.abs(dv - nv.grad.numpy()).max() < 1e-8
+
+
+def test_gaussian_oracle_vs_torch_normal_and_autograd():
+    """Gaussian policy oracle vs torch.distributions.Normal (sample stream, log_prob, entropy) and autograd of
+    the continuous PPO loss (cleanrl/ppo_continuous_action.py:134-141,262-300)."""
+    import torch
+    from torch.distributions.normal import Normal
+    torch.manual_seed(0)
+    M, D, B = 256, 6, 1024
+    mean = torch.randn(M, D, requires_grad=True)
+    logstd = (torch.randn(1, D) * 0.3).requires_grad_(True)
+    nv = torch.randn(M, requires_grad=True)
+    torch.manual_seed(9)
+    act = Normal(mean, logstd.expand_as(mean).exp()).sample()
+    torch.manual_seed(9)
+    eps = torch.randn(M, D)
+    a, lp, ent = O.gaussian_sample(mean.detach().numpy(), logstd.detach().numpy(), eps.numpy())
+    # same N(0,1) stream; exp(logstd) differs by <= 1 ulp between numpy and torch => compare at 1e-6
+    assert np.abs(a - act.numpy()).max() <= 1e-6 * np.abs(act.numpy()).max()
+    a = act.numpy()
+    lp, ent = O.gaussian_eval(mean.detach().numpy(), logstd.detach().numpy(), a)
+    dist = Normal(mean, logstd.expand_as(mean).exp())
+    assert np.abs(lp - dist.log_prob(act).sum(1).detach().numpy()).max() < 1e-5
+    assert np.abs(ent - dist.entropy().sum(1).detach().numpy()).max() < 1e-5
+    b_act = torch.randn(B, D); b_lp = torch.randn(B) * 0.2 - 5.0; b_adv = torch.randn(B)
+    b_ret = torch.randn(B); b_val = b_ret + 0.3 * torch.randn(B)
+    inds = torch.randperm(B)[:M]
+    dist = Normal(mean, logstd.expand_as(mean).exp())
+    ratio = (dist.log_prob(b_act[inds]).sum(1) - b_lp[inds]).exp()
+    mb = b_adv[inds]; mb = (mb - mb.mean()) / (mb.std() + 1e-8)
+    pg = torch.max(-mb * ratio, -mb * torch.clamp(ratio, 0.8, 1.2)).mean()
+    vu = (nv - b_ret[inds]) ** 2
+    vc = (b_val[inds] + torch.clamp(nv - b_val[inds], -0.2, 0.2) - b_ret[inds]) ** 2
+    vl = 0.5 * torch.max(vu, vc).mean()
+    loss = pg - 0.01 * dist.entropy().sum(1).mean() + vl * 0.5
+    loss.backward()
+    st, dm, dls, dv = O.ppo_loss_gaussian(mean.detach().numpy(), logstd.detach().numpy(), nv.detach().numpy(), inds.numpy(),
+                                          b_act.numpy(), b_lp.numpy(), b_adv.numpy(), b_ret.numpy(), b_val.numpy(), 0.2, 0.01, 0.5)
+    assert abs(float(st["loss"]) - float(loss.detach())) < 1e-5 * max(1.0, abs(float(loss.detach())))
+    assert np.abs(dm - mean.grad.numpy()).max() <= 1e-5 * np.abs(mean.grad.numpy()).max()
+    assert np.abs(dls - logstd.grad.numpy().reshape(-1)).max() <= 1e-5 * max(1.0, np.abs(logstd.grad.numpy()).max())
+    assert np.abs(dv - nv.grad.numpy()).max() <= 1e-7
