@@ -32,6 +32,9 @@ def _exp_noise(n, A, device):
     return torch.empty(n, A, dtype=torch.float32, device=device).exponential_(1)
 
 
+_exp_noise.graph_safe = True      # device-generator draw: capturable in a CUDA graph
+
+
 class KernelAgent(nn.Module):
     """Shared plumbing: flat parameter binding + categorical head."""
 
@@ -75,6 +78,13 @@ class KernelAgent(nn.Module):
 
     # -- engine hooks (one policy step / one minibatch loss+backward) ---------------
     action_dim = 0          # 0 = discrete (int64 actions [n]); D > 0 = continuous (f32 actions [n, D])
+
+    @property
+    def graph_friendly(self):
+        """May the engine capture the per-step device work in CUDA graphs?  (small per-step temporaries, noise
+        drawn on the device)"""
+        return getattr(self.noise_fn, "graph_safe", False) and (getattr(self, "precision", "bf16") == "bf16" or
+                                                                not hasattr(self, "network"))
 
     def sample_into(self, obs, actions_out, logprobs_out, values_out):
         """Rollout step: forward + sample, writing straight into the rollout slots (ppo.py:197-202)."""
@@ -261,6 +271,9 @@ def _normal_noise(n, D, device):
     return torch.randn(n, D, dtype=torch.float32, device=device)
 
 
+_normal_noise.graph_safe = True
+
+
 class ContinuousMLPAgent(KernelAgent):
     """Gaussian-policy MLP agent (reference: cleanrl/ppo_continuous_action.py:112-141): ``critic`` and
     ``actor_mean`` Sequentials plus the state-independent ``actor_logstd`` parameter [1, D]."""
@@ -326,3 +339,103 @@ class ContinuousMLPAgent(KernelAgent):
             logprob, entropy = ops.gaussian_eval(mean, self._logstd(), action)
             v = value.clone() if not value.is_contiguous() else value
         return action, logprob, entropy, v.reshape(-1, 1)
+
+
+class QNetworkAgent(nn.Module):
+    """DQN Q-network (reference: cleanrl/dqn_atari.py:108-125): NatureCNN trunk + Linear(512, A), default torch
+    initialisation, ``forward(x)`` -> Q-values [n, A]; state_dict keys ``network.{0,2,4,7,9}.*``."""
+
+    def __init__(self, env):
+        super().__init__()
+        A = int(env.single_action_space.n)
+        self.network = nn.Sequential(
+            nn.Conv2d(4, 32, 8, stride=4), nn.ReLU(), nn.Conv2d(32, 64, 4, stride=2), nn.ReLU(),
+            nn.Conv2d(64, 64, 3, stride=1), nn.ReLU(), nn.Flatten(), nn.Linear(3136, 512), nn.ReLU(), nn.Linear(512, A))
+        self.num_actions = A
+        self.precision = "fp32"
+        self._flat = None
+        self._tc = None
+        self._tc_dirty = True
+
+    def bind(self):
+        dev = next(self.parameters()).device
+        if dev.type != "cuda":
+            raise RuntimeError("cleanrl_b200 agents execute on CUDA only (libb200rl kernels); "
+                               f"parameters are on {dev}. There is no CPU fallback.")
+        self._flat = nets.FlatParams(list(self.parameters()), dev)   # natural order == libb200rl NatureCNN order
+        n = self.network
+        self.chain = nets.Chain([nets.Conv(n[0], "relu", in_div=255.0), nets.Conv(n[2], "relu"), nets.Conv(n[4], "relu"),
+                                 nets.Linear(n[7], "relu"), nets.Linear(n[9], None)])
+        return self._flat
+
+    @property
+    def flat(self):
+        if self._flat is None or self._flat.flat.device != next(self.parameters()).device:
+            self.bind()
+        return self._flat
+
+    def params_updated(self):
+        self._tc_dirty = True
+
+    def load_state_dict(self, *a, **k):
+        out = super().load_state_dict(*a, **k)
+        self._tc_dirty = True
+        return out
+
+    def _plan(self):
+        f = self.flat
+        if self._tc is None:
+            self._tc = ops.NatureCNNBf16(self.num_actions - 1, f.flat.device)   # heads = (A-1) + 1 = A outputs
+        if self._tc_dirty:
+            self._tc.pack(f.flat)
+            self._tc_dirty = False
+        return self._tc
+
+    def q_values(self, frames, rows=None, keep=False):
+        """Q(s, .) for frames[rows] (uint8 [*,4,84,84]; rows gathers without materialising)."""
+        self.flat
+        if frames.dtype != torch.uint8:
+            frames = frames.to(torch.uint8)
+        if self.precision == "bf16":
+            out = self._plan().forward(frames.contiguous(), rows, self._flat.flat)
+            if keep:
+                self._saved = (frames, rows)
+            return out
+        return self.chain.fwd(frames.contiguous(), rows=rows, keep=keep)
+
+    def forward(self, x):
+        return self.q_values(x)
+
+    def backward(self, dq):
+        if self.precision == "bf16":
+            frames, rows = self._saved
+            self._tc.backward(frames, rows, self._flat.flat, dq, self._flat.grad)
+            self._saved = None
+        else:
+            self.chain.bwd(dq)
+
+
+def dqn_update(q_network, target_network, ring, batch, gamma, lr, huber=False, stats=None):
+    """One TD update (reference: dqn_atari.py:219-235): target forward, online forward, fused TD loss + dL/dQ,
+    hand-written backward, Adam (torch defaults eps=1e-8, no gradient clipping)."""
+    frames = ring.frames
+    with torch.no_grad():
+        qt = target_network.q_values(frames, rows=batch["next_rows"])
+        q = q_network.q_values(frames, rows=batch["rows"], keep=True)
+        stats, dq = ops.dqn_td_loss(q, qt, batch["actions"], batch["rewards"], batch["dones"], gamma, huber=huber, stats=stats)
+        q_network.backward(dq)
+        f = q_network.flat
+        f.step += 1
+        ops.clip_adam(f.flat, f.grad, f.exp_avg, f.exp_avg_sq, f.step, lr, eps=1e-8, max_norm=None)
+        q_network.params_updated()
+    return stats
+
+
+def dqn_sync_target(q_network, target_network, tau=1.0):
+    """dqn_atari.py:238-242: target <- tau * online + (1 - tau) * target (flat buffers, one fused axpby)."""
+    t, q = target_network.flat.flat, q_network.flat.flat
+    if tau == 1.0:
+        t.copy_(q)
+    else:
+        t.mul_(1.0 - tau).add_(q, alpha=tau)
+    target_network.params_updated()

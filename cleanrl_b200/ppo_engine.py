@@ -19,6 +19,8 @@ sampling noise, so seeds mean what they mean in the reference (ppo.py:153-157).
 """
 from __future__ import annotations
 
+import os
+
 import numpy as np
 import torch
 
@@ -47,7 +49,7 @@ class PPOEngine:
     ALLOW_NON_CUDA_FOR_TESTS = False
 
     def __init__(self, agent, args, obs_shape, obs_dtype, num_envs, device, world_size=1, gae_mode=0,
-                 all_reduce=None):
+                 all_reduce=None, cuda_graphs=None):
         if device.type != "cuda" and not PPOEngine.ALLOW_NON_CUDA_FOR_TESTS:
             raise RuntimeError("PPOEngine drives libb200rl CUDA kernels and needs a CUDA device; "
                                "there is no CPU fallback (got device=%s)" % device)
@@ -100,12 +102,20 @@ class PPOEngine:
         self.stats_h = _pin(torch.zeros(max(n_upd, 1), 16, dtype=f32))
         self.grad_norm = torch.zeros(1, dtype=f32, device=device)
         self.flat = agent.flat
+        # One CUDA graph per rollout slot: the per-step device work (frame conversion, 5 network launches, noise
+        # draw, sampler) becomes a single graph launch that writes straight into obs[t]/actions[t]/...; the
+        # rollout is launch-latency bound otherwise (~12 launches + torch ops per 1024-env step).
+        if cuda_graphs is None:
+            cuda_graphs = os.environ.get("CLEANRL_B200_CUDA_GRAPHS", "1") != "0"
+        self.cuda_graphs = bool(cuda_graphs) and device.type == "cuda"
+        self._graphs = {}
+        self._graph_warm = False
         self.h2d_bytes = 0
         self.d2h_bytes = 0
         self.kernel_launches = 0
 
     # ------------------------------------------------------------------ rollout
-    def _upload_obs(self, dst, obs_np):
+    def _upload_obs(self, dst, obs_np, convert=True):
         src = torch.from_numpy(np.ascontiguousarray(obs_np))
         if src.dtype != self.obs_dtype:
             src = src.to(self.obs_dtype)
@@ -114,18 +124,42 @@ class PPOEngine:
             src = self.obs_stage_h
         if self.s2d:
             self.obs_u8.copy_(src, non_blocking=True)
-            ops.frames_to_s2d(self.obs_u8, out=dst)
+            if convert:
+                ops.frames_to_s2d(self.obs_u8, out=dst)
         else:
             dst.copy_(src, non_blocking=True)
         self.h2d_bytes += src.numel() * src.element_size()
+
+    def _step_device_work(self, step):
+        """Everything a policy step does on the device after the observation batch has landed."""
+        if self.s2d:
+            ops.frames_to_s2d(self.obs_u8, out=self.obs[step])
+        self.agent.sample_into(self.obs[step], self.actions[step], self.logprobs[step], self.values[step])
+
+    def _run_step(self, step):
+        if not (self.cuda_graphs and getattr(self.agent, "graph_friendly", False)):
+            return self._step_device_work(step)
+        if hasattr(self.agent, "_tc_plan") and getattr(self.agent, "precision", "fp32") == "bf16":
+            self.agent._tc_plan()                      # (re)pack weights outside the graph
+        g = self._graphs.get(step)
+        if g is None:
+            if not self._graph_warm:                   # allocate workspaces / JIT-free warm-up, then capture
+                self._step_device_work(step)
+                torch.cuda.current_stream().synchronize()
+                self._graph_warm = True
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
+                self._step_device_work(step)
+            self._graphs[step] = g
+        g.replay()
 
     @torch.no_grad()
     def policy_step(self, step, next_obs_np, next_done_np):
         """obs[step] <- next_obs (H2D), sample actions, return them as a host int64 array.
         Reference: ppo.py:194-205 (store obs/done, no-grad policy, action.cpu())."""
-        self._upload_obs(self.obs[step], next_obs_np)
+        self._upload_obs(self.obs[step], next_obs_np, convert=False)
         self.dones_h[step].copy_(torch.as_tensor(np.asarray(next_done_np, dtype=np.float32)))
-        self.agent.sample_into(self.obs[step], self.actions[step], self.logprobs[step], self.values[step])
+        self._run_step(step)
         self.actions_h.copy_(self.actions[step], non_blocking=True)
         self.d2h_bytes += self.actions_h.numel() * self.actions_h.element_size()
         _sync()
@@ -136,10 +170,10 @@ class PPOEngine:
         """Device-resident variant (inputs already in HBM, no host round trip): used to measure the
         kernel-side throughput of the rollout step; actions stay on the device."""
         if self.s2d and obs_dev.dtype == torch.uint8:
-            ops.frames_to_s2d(obs_dev, out=self.obs[step])
+            self.obs_u8.copy_(obs_dev)
         else:
             self.obs[step].copy_(obs_dev)
-        self.agent.sample_into(self.obs[step], self.actions[step], self.logprobs[step], self.values[step])
+        self._run_step(step)
 
     def record_reward(self, step, reward_np):
         self.rewards_h[step].copy_(torch.as_tensor(np.asarray(reward_np, dtype=np.float32).reshape(-1)))

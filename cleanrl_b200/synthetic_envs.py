@@ -38,6 +38,13 @@ class Discrete:
         self.n = int(n)
         self.shape = ()
         self.dtype = np.int64
+        self._rng = np.random.default_rng(0)
+
+    def seed(self, seed=None):
+        self._rng = np.random.default_rng(seed)
+
+    def sample(self):
+        return int(self._rng.integers(0, self.n))
 
     def __repr__(self):
         return f"Discrete({self.n})"
@@ -204,6 +211,10 @@ class SyntheticGymnasiumVec:
                                         "l": np.array([self._ep_len[i]], dtype=np.int32)}}
             infos["final_info"] = final
             infos["_final_info"] = done.copy()
+            fobs = np.empty(n, dtype=object)
+            for i in np.nonzero(done)[0]:
+                fobs[i] = obs[i].copy()
+            infos["final_observation"] = fobs
             self._ep_ret[done] = 0
             self._ep_len[done] = 0
             if self.kind != "atari":

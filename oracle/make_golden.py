@@ -84,8 +84,47 @@ def continuous(name, argv, n_iter):
     print("wrote", name)
 
 
+def dqn(name, argv):
+    """cleanrl/dqn_atari.py (+ the reference's own cleanrl_utils/buffers.py ReplayBuffer) on the synthetic
+    gymnasium Atari env: every F.mse_loss value, the sampled index stream and the final parameters."""
+    import torch
+    import torch.nn.functional as F
+    losses, qmeans, samples = [], [], []
+    orig_mse = F.mse_loss
+
+    def mse(a, b, *aa, **kk):
+        out = orig_mse(a, b, *aa, **kk)
+        losses.append(float(out.detach())); qmeans.append(float(b.detach().mean()))
+        return out
+    orig_randint = np.random.randint
+
+    def randint(*a, **k):
+        out = orig_randint(*a, **k)
+        samples.append(np.array(out).reshape(-1)[:8].copy())
+        return out
+    F.mse_loss = mse
+    np.random.randint = randint
+    try:
+        rec, g = run_reference("dqn_atari.py", argv, gymnasium_kind="atari")
+    finally:
+        F.mse_loss = orig_mse
+        np.random.randint = orig_randint
+    out = {"argv": np.array(argv), "td_losses": np.array(losses), "q_means": np.array(qmeans),
+           "randint_heads": np.stack(samples[:64]) if samples else np.zeros((0, 8)),
+           "param_sums": np.array([p.detach().double().sum().item() for p in g["q_network"].parameters()]),
+           "param_abs_sums": np.array([p.detach().double().abs().sum().item() for p in g["q_network"].parameters()]),
+           "state_dict_keys": np.array(list(g["q_network"].state_dict().keys()))}
+    for t in sorted({t for t, _, _ in rec.scalars}):
+        out["tb/" + t] = np.array([(s_, v) for tt, v, s_ in rec.scalars if tt == t], dtype=np.float64)
+    np.savez_compressed(OUT / name, **out)
+    print("wrote", name, len(losses), "updates")
+
+
 def main():
     OUT.mkdir(parents=True, exist_ok=True)
+    dqn("dqn_atari_b8_seed1.npz",
+        ["--no-cuda", "--total-timesteps", "260", "--learning-starts", "40", "--buffer-size", "64", "--batch-size", "8",
+         "--train-frequency", "4", "--target-network-frequency", "20", "--seed", "1"])
     continuous("ppo_continuous_n4_t64_seed2.npz",
                ["--no-cuda", "--num-envs", "4", "--num-steps", "64", "--total-timesteps", "512", "--seed", "2",
                 "--num-minibatches", "4", "--update-epochs", "2"], 2)

@@ -84,7 +84,8 @@ def test_product_never_imports_oracle():
 @pytest.mark.reference
 @pytest.mark.parametrize("script,factory", [
     ("ppo.py", "ppo_args"), ("ppo_atari_envpool.py", "ppo_atari_envpool_args"),
-    ("ppo_atari_multigpu.py", "ppo_atari_multigpu_args"), ("ppo_continuous_action.py", "ppo_continuous_action_args")])
+    ("ppo_atari_multigpu.py", "ppo_atari_multigpu_args"), ("ppo_continuous_action.py", "ppo_continuous_action_args"),
+    ("dqn_atari.py", "dqn_atari_args")])
 def test_cli_fields_match_reference_args(script, factory):
     """Every reference flag exists with the same default and help text (reference Args dataclasses)."""
     import ast
@@ -117,4 +118,4 @@ def test_cli_fields_match_reference_args(script, factory):
         helps = [m.help for m in getattr(f.type, "__metadata__", ()) if hasattr(m, "help")]
         assert helps and helps[0] == doc, (name, helps, doc)
     extra = set(fields) - set(ref)
-    assert extra <= {"precision", "gae_kernel", "synthetic_env"}, extra
+    assert extra <= {"precision", "gae_kernel", "synthetic_env", "huber_loss"}, extra

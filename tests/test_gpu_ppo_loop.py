@@ -156,3 +156,49 @@ def test_ppo_mlp_script_reproduces_reference_run(lib):
         for col, key in ((0, "upd_pg_loss"), (1, "upd_v_loss"), (2, "upd_entropy_loss"), (4, "upd_approx_kl"), (6, "upd_loss")):
             ref = float(z[key][u])
             assert abs(per[u, col] - ref) <= (1e-5 if u == 0 else 1e-4) * max(1.0, abs(ref)), (u, key, per[u, col], ref)
+
+
+@pytest.mark.parametrize("kind", ["atari_bf16", "mlp"])
+def test_cuda_graph_rollout_equals_eager(lib, kind):
+    """The per-slot CUDA graphs of PPOEngine replay exactly the eager step: same generator state => identical
+    actions / logprobs / values over two iterations (incl. weight re-packing between iterations)."""
+    from bench import ppo_args
+    from cleanrl_b200.agents import MLPAgent, NatureCNNAgent
+    from cleanrl_b200.ppo_engine import PPOEngine
+    from cleanrl_b200.synthetic_envs import SyntheticAtariVec, SyntheticGymnasiumVec
+    dev = torch.device("cuda")
+    outs = []
+    for graphs in (False, True):
+        np.random.seed(3); torch.manual_seed(3)
+        N, T = 32, 6
+        args = ppo_args(N, T, 4, "bf16")
+        if kind == "atari_bf16":
+            envs = SyntheticAtariVec(N, seed=3, mode="fresh")
+            envs.single_observation_space, envs.single_action_space = envs.observation_space, envs.action_space
+            agent = NatureCNNAgent(envs).to(dev); agent.precision = "bf16"
+            obs = envs.reset(); step_env = lambda a: envs.step(a)[:3]
+            odt = np.uint8
+        else:
+            envs = SyntheticGymnasiumVec(N, kind="discrete")
+            agent = MLPAgent(envs).to(dev)
+            obs, _ = envs.reset(seed=3)
+            def step_env(a):
+                o, r, te, tr, _ = envs.step(a)
+                return o, r, np.logical_or(te, tr)
+            odt = np.float32
+        torch.manual_seed(11)
+        eng = PPOEngine(agent, args, envs.single_observation_space.shape, odt, N, dev, cuda_graphs=graphs)
+        done = np.zeros(N, dtype=np.float32)
+        rec = []
+        for it in range(2):
+            for t in range(T):
+                a = eng.policy_step(t, obs, done)
+                obs, r, done = step_env(a.copy())
+                eng.record_reward(t, r)
+            eng.finish_rollout(obs, done)
+            eng.update(2.5e-4)
+            rec.append((eng.actions.clone(), eng.logprobs.clone(), eng.values.clone()))
+        assert (len(eng._graphs) == T) == graphs
+        outs.append(rec)
+    for (a0, l0, v0), (a1, l1, v1) in zip(*outs):
+        assert torch.equal(a0, a1) and torch.equal(l0, l1) and torch.equal(v0, v1)
