@@ -196,7 +196,7 @@ def run_ours(opt):
         barrier()
         sampler = ClockSampler(local_rank)
         sampler.start()
-        h2d0, d2h0, l0 = eng.h2d_bytes, eng.d2h_bytes, lib.b200rl_launch_count()
+        h2d0, d2h0, l0 = eng.h2d_bytes, eng.d2h_bytes, lib.b200rl_launch_count() + eng.graph_launches
         if profile:
             lib.b200rl_profile_reset()
             lib.b200rl_profile_enable(1)
@@ -222,10 +222,45 @@ def run_ours(opt):
         if world > 1:
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return dict(ms=float(t.item()), h2d=(eng.h2d_bytes - h2d0) / K, d2h=(eng.d2h_bytes - d2h0) / K,
-                    launches=lib.b200rl_launch_count() - l0, clocks=clocks, stats=st, prof=prof)
+                    launches=lib.b200rl_launch_count() + eng.graph_launches - l0, clocks=clocks, stats=st, prof=prof)
 
     res = timed(iteration_resident, profile=True)
     e2e = timed(iteration_e2e)
+
+    # ---- second headline metric: GAE microseconds per rollout (T x N per GPU), kernel time via CUDA-graph
+    #      replays of 20 back-to-back launches (no launch gaps), plus the reference loop with torch ops on the GPU
+    def gae_us(mode):
+        fn = lambda: ops.gae(eng.rewards, eng.values, eng.dones, eng.next_value, eng.next_done, args.gamma,
+                             args.gae_lambda, mode=mode, out=(eng.advantages, eng.returns))
+        fn(); torch.cuda.synchronize()
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g):
+            for _ in range(20):
+                fn()
+        ts = []
+        for _ in range(10):
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record(); g.replay(); b.record(); torch.cuda.synchronize()
+            ts.append(a.elapsed_time(b) * 1e3 / 20)
+        return float(np.median(ts))
+
+    def gae_ref_us():
+        r, v, d, nv, nd = eng.rewards, eng.values, eng.dones, eng.next_value.view(1, -1), eng.next_done
+        ts = []
+        for _ in range(3):
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            adv = torch.zeros_like(r); last = 0
+            for t in reversed(range(T)):
+                nnt = 1.0 - (nd if t == T - 1 else d[t + 1]); nvs = nv if t == T - 1 else v[t + 1]
+                delta = r[t] + args.gamma * nvs * nnt - v[t]
+                adv[t] = last = delta + args.gamma * args.gae_lambda * nnt * last
+            b.record(); torch.cuda.synchronize()
+            ts.append(a.elapsed_time(b) * 1e3)
+        return float(np.median(ts))
+
+    gae = {"T": T, "N": N, "sequential_bit_exact_us": round(gae_us(0), 2), "chunked_scan_us": round(gae_us(1), 2),
+           "reference_torch_loop_on_gpu_us": round(gae_ref_us(), 1), "algorithmic_bytes": 20 * T * N + 8 * N}
 
     if rank != 0:
         if world > 1:
@@ -240,9 +275,16 @@ def run_ours(opt):
     tot_ms = sum(r["ms"] for r in prof) or 1.0
     top = next((r for r in prof if r["flops"] > 0), prof[0])
     ach = top["flops"] / (top["ms"] * 1e-3) / 1e12 if top["ms"] > 0 else 0.0
+    traffic = None
+    tp = ROOT / "profiles" / "r1_traffic.json"
+    if tp.exists():
+        tr = json.loads(tp.read_text()).get(top["name"])
+        if tr:
+            traffic = {"dram_bytes_per_launch": tr["dram_bytes"], "algorithmic_bytes_per_launch": tr["algorithmic_bytes"],
+                       "at_n": tr["n"], "from": "profiles/r1_traffic.json (ncu --set full)"}
     roofline = {
         "bound": "tensor", "kernel": top["name"], "achieved": round(ach, 2), "peak": peak_tf, "unit": "TFLOP/s",
-        "frac": round(ach / peak_tf, 4), "traffic": None, "peak_source": f"{which} bf16_tflops_sustained",
+        "frac": round(ach / peak_tf, 4), "traffic": traffic, "peak_source": f"{which} bf16_tflops_sustained",
         "share_of_kernel_time": round(top["ms"] / tot_ms, 4), "launches": top["launches"],
         "avg_launch_us": round(1e3 * top["ms"] / max(top["launches"], 1), 2),
         "job_tensor_frac": round(sps / world * FLOP_PER_ENV_STEP / (peak_tf * 1e12), 4),
@@ -265,6 +307,7 @@ def run_ours(opt):
         "e2e": {"value": round(sps_e2e, 1), "unit": "env_steps/s", "ms_per_step": round(e2e["ms"] / K, 3),
                 "h2d_bytes_per_step": int(e2e["h2d"]), "d2h_bytes_per_step": int(e2e["d2h"]), "clocks": e2e["clocks"]},
         "gpu_launches": int(res["launches"]),
+        "gae_us_per_rollout": gae,
         "roofline": roofline,
         "losses_last": {k: (float(v) if isinstance(v, (int, float)) else None) for k, v in (e2e["stats"] or {}).items()
                         if k in ("pg_loss", "v_loss", "entropy", "approx_kl")},

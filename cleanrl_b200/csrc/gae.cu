@@ -144,7 +144,8 @@ extern "C" int b200rl_gae_f32(const float* rewards, const float* values, const f
         gae_seq_kernel<8><<<blocks, threads, 0, s>>>(rewards, values, dones, next_value, next_done,
                                                      advantages, returns, T, N, g, gl);
     } else {
-        int C = (int)ceil_div(T, 16);
+        // up to 32 time chunks per env (block = 32 envs x C chunks): the dependent chain is L + C + L steps
+        int C = (int)ceil_div(T, 4);
         if (C > 32) C = 32;
         if (C < 1) C = 1;
         const int L = (int)ceil_div(T, C);

@@ -109,7 +109,9 @@ class PPOEngine:
             cuda_graphs = os.environ.get("CLEANRL_B200_CUDA_GRAPHS", "1") != "0"
         self.cuda_graphs = bool(cuda_graphs) and device.type == "cuda"
         self._graphs = {}
+        self._graph_kernels = {}
         self._graph_warm = False
+        self.graph_launches = 0          # libb200rl kernels executed through graph replays
         self.h2d_bytes = 0
         self.d2h_bytes = 0
         self.kernel_launches = 0
@@ -143,15 +145,21 @@ class PPOEngine:
             self.agent._tc_plan()                      # (re)pack weights outside the graph
         g = self._graphs.get(step)
         if g is None:
-            if not self._graph_warm:                   # allocate workspaces / JIT-free warm-up, then capture
+            if not self._graph_warm:                   # allocate workspaces once (eager), then capture
+                rng = torch.cuda.get_rng_state(self.device)     # the warm-up must not consume sampling noise
                 self._step_device_work(step)
                 torch.cuda.current_stream().synchronize()
+                torch.cuda.set_rng_state(rng, self.device)
                 self._graph_warm = True
+            from . import _lib
+            l0 = _lib.load().b200rl_launch_count()
             g = torch.cuda.CUDAGraph()
             with torch.cuda.graph(g):
                 self._step_device_work(step)
             self._graphs[step] = g
+            self._graph_kernels[step] = _lib.load().b200rl_launch_count() - l0
         g.replay()
+        self.graph_launches += self._graph_kernels[step]
 
     @torch.no_grad()
     def policy_step(self, step, next_obs_np, next_done_np):
