@@ -235,6 +235,9 @@ __global__ void __launch_bounds__(288, 1) tc_gemm_ws(const KGemmParams p, int to
                 const int ooy = p.nclasses > 1 ? (cls >> 1) : 0, oox = p.nclasses > 1 ? (cls & 1) : 0;
                 ooff = (((int64_t)i * p.OH + y * p.osy + ooy) * p.OW + x * p.osx + oox) * (int64_t)p.ldo;
             }
+            const bool use_mask = p.mask != nullptr && rvalid;
+            int4 mk0 = make_int4(0, 0, 0, 0), mk1 = make_int4(0, 0, 0, 0);
+            if (use_mask && n0 < p.N) { mk0 = ldg16(p.mask + ooff + n0); mk1 = ldg16(p.mask + ooff + n0 + 8); }
             mbar_wait(&tfull_bar[acc], (t >> 1) & 1);
             tc_fence_after_sync();
             const uint32_t lane_addr = tmem_d + acc * BN + ((uint32_t)(ew * 32) << 16);
@@ -242,6 +245,10 @@ __global__ void __launch_bounds__(288, 1) tc_gemm_ws(const KGemmParams p, int to
             for (int c0 = 0; c0 < BN; c0 += 16) {
                 uint32_t v[16];
                 tmem_ld16(lane_addr + c0, v);
+                const int4 m0 = mk0, m1 = mk1;
+                if (use_mask && c0 + 16 < BN && n0 + c0 + 16 < p.N) {
+                    mk0 = ldg16(p.mask + ooff + n0 + c0 + 16); mk1 = ldg16(p.mask + ooff + n0 + c0 + 24);
+                }
                 tmem_ld_wait();
                 const int col = n0 + c0;
                 if (!rvalid || col >= p.N) continue;
@@ -265,8 +272,6 @@ __global__ void __launch_bounds__(288, 1) tc_gemm_ws(const KGemmParams p, int to
                     for (int e = 0; e < 16; ++e) f[e] = fmaxf(f[e], 0.f);
                 }
                 if (p.mask) {
-                    const int4 m0 = ldg16(p.mask + ooff + col);
-                    const int4 m1 = ldg16(p.mask + ooff + col + 8);
                     const uint32_t mw[8] = {(uint32_t)m0.x, (uint32_t)m0.y, (uint32_t)m0.z, (uint32_t)m0.w,
                                             (uint32_t)m1.x, (uint32_t)m1.y, (uint32_t)m1.z, (uint32_t)m1.w};
 #pragma unroll
@@ -370,6 +375,10 @@ __global__ void __launch_bounds__(288, 1) tc_conv_win(const WinParams p, int tot
     __syncthreads();
     tc_fence_after_sync();
     const uint32_t tmem_d = tmem_base_smem;
+    // each CTA walks a CONTIGUOUS range of tiles: with the minibatch gather every image (3-4 tiles) is then
+    // touched by one SM only (TLB / L2 locality), and the image indices of tile+1 can be prefetched
+    const int tile_begin = (int)(((int64_t)total_tiles * blockIdx.x) / gridDim.x);
+    const int tile_end = (int)(((int64_t)total_tiles * (blockIdx.x + 1)) / gridDim.x);
 
     if (warp < 4) {
         // ======================= producers: one window per tile =======================
@@ -378,29 +387,44 @@ __global__ void __launch_bounds__(288, 1) tc_conv_win(const WinParams p, int tot
         const int wr0 = tid / PPR, pc = tid % PPR;
         const int cc = pc >> 3, c16 = pc & 7;
         uint32_t q = 0;
-        for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++q) {
+        // image gather (conv1 reads the rollout through mb_inds): a window spans at most two images (WR < G);
+        // their indices are fetched ONE TILE AHEAD so the dependent global load never stalls cp.async issue
+        int64_t nimg0 = 0, nimg1 = 0;
+        if (p.rows && tile_begin < tile_end) {
+            const int64_t i0 = ((int64_t)tile_begin * 128) / p.G;
+            nimg0 = i0 < p.n ? __ldg(p.rows + i0) : 0;
+            nimg1 = i0 + 1 < p.n ? __ldg(p.rows + i0 + 1) : 0;
+        }
+        for (int tile = tile_begin; tile < tile_end; ++tile, ++q) {
             const uint32_t s = q % STAGES;
+            const int64_t row0 = (int64_t)tile * 128;
+            const int64_t cimg0 = nimg0, cimg1 = nimg1;
+            int64_t ibase = 0;
+            if (p.rows) {
+                ibase = row0 / p.G;
+                const int ntile = tile + 1;
+                if (ntile < tile_end) {
+                    const int64_t i0 = ((int64_t)ntile * 128) / p.G;
+                    nimg0 = i0 < p.n ? __ldg(p.rows + i0) : 0;
+                    nimg1 = i0 + 1 < p.n ? __ldg(p.rows + i0 + 1) : 0;
+                }
+            }
             if (q >= (uint32_t)STAGES) mbar_wait(&empty_bar[s], ((q / STAGES) - 1) & 1);
             const uint32_t sA = smem_u32(sRing + (size_t)s * STAGE_BYTES) + cc * IMG;
-            const int64_t row0 = (int64_t)tile * 128;
             int64_t r = row0 + wr0;
-            int64_t img = 0; int rem = 0; int64_t ii = 0;
-            if (p.rows) {
-                ii = r / p.G; rem = (int)(r - ii * p.G);
-                img = ii < p.n ? __ldg(p.rows + ii) : 0;
-            }
-            for (int wr = wr0; wr < p.WR; wr += RSTEP, r += RSTEP) {
+            int rem = p.rows ? (int)(r - ibase * p.G) : 0;      // may exceed G: second image of the window
+            for (int wr = wr0; wr < p.WR; wr += RSTEP, r += RSTEP, rem += RSTEP) {
                 const bool ok = r < p.M;
                 const bf16* src = p.A;
                 if (ok) {
-                    if (p.rows) src = p.A + ((img * p.G + rem) * (int64_t)(CPR * 64) + pc * 8);
-                    else src = p.A + (r * (int64_t)(CPR * 64) + pc * 8);
+                    if (p.rows) {
+                        const bool second = rem >= p.G;
+                        src = p.A + (((second ? cimg1 : cimg0) * p.G + (second ? rem - p.G : rem)) * (int64_t)(CPR * 64) + pc * 8);
+                    } else {
+                        src = p.A + (r * (int64_t)(CPR * 64) + pc * 8);
+                    }
                 }
                 cp_async16(sA + img_off(wr, c16), src, ok ? 16u : 0u);
-                if (p.rows) {
-                    rem += RSTEP;
-                    if (rem >= p.G) { rem -= p.G; ++ii; img = ii < p.n ? __ldg(p.rows + ii) : 0; }
-                }
             }
             cp_async_commit();
             if (q >= (uint32_t)LOOKAHEAD) {
@@ -420,7 +444,7 @@ __global__ void __launch_bounds__(288, 1) tc_conv_win(const WinParams p, int tot
         if ((tid & 31) == 0) {
             constexpr uint32_t idesc = make_idesc(128, BN, 0, 0);
             uint32_t q = 0;
-            for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++q) {
+            for (int tile = tile_begin; tile < tile_end; ++tile, ++q) {
                 const uint32_t acc = q & 1, s = q % STAGES;
                 if (q >= 2) mbar_wait(&tempty_bar[acc], ((q >> 1) - 1) & 1);
                 mbar_wait(&full_bar[s], (q / STAGES) & 1);
@@ -449,7 +473,7 @@ __global__ void __launch_bounds__(288, 1) tc_conv_win(const WinParams p, int tot
         const int ew = warp & 3;
         const int lrow = ew * 32 + (tid & 31);
         uint32_t q = 0;
-        for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++q) {
+        for (int tile = tile_begin; tile < tile_end; ++tile, ++q) {
             const uint32_t acc = q & 1;
             const int64_t r = (int64_t)tile * 128 + lrow;
             bool valid = r < p.M;
@@ -472,6 +496,11 @@ __global__ void __launch_bounds__(288, 1) tc_conv_win(const WinParams p, int tot
             } else {
                 om = ((int64_t)i * 100 + Y * 10 + X) * 128;                // act1 cells [n,100,128]
             }
+            // ReLU-mask words are fetched one column group AHEAD (the first one before waiting for the
+            // accumulator), so their global-memory latency overlaps the MMAs / the previous group's stores
+            const bool use_mask = p.mask != nullptr && valid;
+            int4 mk0 = make_int4(0, 0, 0, 0), mk1 = make_int4(0, 0, 0, 0);
+            if (use_mask) { mk0 = ldg16(p.mask + om); mk1 = ldg16(p.mask + om + 8); }
             mbar_wait(&tfull_bar[acc], (q >> 1) & 1);
             tc_fence_after_sync();
             const uint32_t lane_addr = tmem_d + acc * BN + ((uint32_t)(ew * 32) << 16);
@@ -479,6 +508,8 @@ __global__ void __launch_bounds__(288, 1) tc_conv_win(const WinParams p, int tot
             for (int c0 = 0; c0 < BN; c0 += 16) {
                 uint32_t v[16];
                 tmem_ld16(lane_addr + c0, v);
+                const int4 m0 = mk0, m1 = mk1;
+                if (use_mask && c0 + 16 < p.N) { mk0 = ldg16(p.mask + om + c0 + 16); mk1 = ldg16(p.mask + om + c0 + 24); }
                 tmem_ld_wait();
                 if (!valid || c0 >= p.N) continue;
                 float f[16];
@@ -501,8 +532,6 @@ __global__ void __launch_bounds__(288, 1) tc_conv_win(const WinParams p, int tot
                     for (int e = 0; e < 16; ++e) f[e] = fmaxf(f[e], 0.f);
                 }
                 if (p.mask) {
-                    const int4 m0 = ldg16(p.mask + om + c0);
-                    const int4 m1 = ldg16(p.mask + om + c0 + 8);
                     const uint32_t mw[8] = {(uint32_t)m0.x, (uint32_t)m0.y, (uint32_t)m0.z, (uint32_t)m0.w,
                                             (uint32_t)m1.x, (uint32_t)m1.y, (uint32_t)m1.z, (uint32_t)m1.w};
 #pragma unroll
@@ -797,24 +826,44 @@ __global__ void __launch_bounds__(160, 1) tc_wgrad_win(const WGradWinParams p) {
         const int rstep = 128 / ppr;
         const int wr0 = tid / ppr, pc = tid % ppr;
         const int cc = pc >> 3, c16 = pc & 7;
+        int64_t nimg0 = 0, nimg1 = 0;          // gather indices of the NEXT step's window, fetched one step ahead
+        if (p.rows && nsteps > 0) {
+            const int64_t i0 = m_begin / p.G;
+            nimg0 = i0 < p.n ? __ldg(p.rows + i0) : 0;
+            nimg1 = i0 + 1 < p.n ? __ldg(p.rows + i0 + 1) : 0;
+        }
         for (int it = 0; it < nsteps; ++it) {
             const int s = it % STAGES;
+            const int64_t m0 = m_begin + (int64_t)it * R;
+            const int64_t cimg0 = nimg0, cimg1 = nimg1;
+            int64_t ibase = 0;
+            if (p.rows) {
+                ibase = m0 / p.G;
+                if (it + 1 < nsteps) {
+                    const int64_t i0 = (m0 + R) / p.G;
+                    nimg0 = i0 < p.n ? __ldg(p.rows + i0) : 0;
+                    nimg1 = i0 + 1 < p.n ? __ldg(p.rows + i0 + 1) : 0;
+                }
+            }
             if (it >= STAGES) mbar_wait(&empty_bar[s], ((it / STAGES) - 1) & 1);
             const uint32_t sX = smem_u32(smem + (size_t)s * stage_bytes);
             const uint32_t sY = sX + XBYTES;
-            const int64_t m0 = m_begin + (int64_t)it * R;
             // X window: rows m0 .. m0+WRX-1 (may run past m_end: those rows belong to the next CTA / are zero)
             {
                 int64_t r = m0 + wr0;
-                int64_t img = 0, ii = 0; int rem = 0;
-                if (p.rows) { ii = r / p.G; rem = (int)(r - ii * p.G); img = ii < p.n ? __ldg(p.rows + ii) : 0; }
-                for (int wr = wr0; wr < p.WRX; wr += rstep, r += rstep) {
+                int rem = p.rows ? (int)(r - ibase * p.G) : 0;
+                for (int wr = wr0; wr < p.WRX; wr += rstep, r += rstep, rem += rstep) {
                     const bool ok = r < p.M;
                     const bf16* src = p.X;
-                    if (ok) src = p.rows ? p.X + ((img * p.G + rem) * (int64_t)(p.cpr * 64) + pc * 8)
-                                         : p.X + (r * (int64_t)(p.cpr * 64) + pc * 8);
+                    if (ok) {
+                        if (p.rows) {
+                            const bool second = rem >= p.G;
+                            src = p.X + (((second ? cimg1 : cimg0) * p.G + (second ? rem - p.G : rem)) * (int64_t)(p.cpr * 64) + pc * 8);
+                        } else {
+                            src = p.X + (r * (int64_t)(p.cpr * 64) + pc * 8);
+                        }
+                    }
                     cp_async16(sX + cc * IMGX + img_off(wr, c16), src, ok ? 16u : 0u);
-                    if (p.rows) { rem += rstep; if (rem >= p.G) { rem -= p.G; ++ii; img = ii < p.n ? __ldg(p.rows + ii) : 0; } }
                 }
             }
             // dY rows m0 .. m0+127 (zero beyond this CTA's range so that boundary rows are counted once)
