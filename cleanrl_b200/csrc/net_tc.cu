@@ -1155,18 +1155,37 @@ __global__ void __launch_bounds__(256) tc_heads_fwd(const bf16* __restrict__ hid
         }
     }
 }
-// dhid_pre[n][512] (bf16) = (dhead[n][A1] . Wh[A1][512]) * (hid > 0)
+// dhid_pre[n][512] (bf16) = (dhead[n][A1] . Wh[A1][512]) * (hid > 0).  Thread = 8 consecutive hidden units of one
+// row (16-byte load of the mask / 16-byte store), head weights staged in smem.
 __global__ void __launch_bounds__(256) tc_heads_bwd_data(const float* __restrict__ dhead, const float* __restrict__ Wh,
                                                          const bf16* __restrict__ hid, int64_t n, int A1, int H,
                                                          bf16* __restrict__ dhid) {
-    const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (idx >= n * H) return;
-    const int64_t row = idx / H;
-    const int h = (int)(idx - row * H);
-    float s = 0.f;
-    for (int a = 0; a < A1; ++a) s = fmaf(dhead[row * A1 + a], __ldg(Wh + (int64_t)a * H + h), s);
-    if (!(__bfloat162float(hid[idx]) > 0.f)) s = 0.f;
-    dhid[idx] = __float2bfloat16(s);
+    __shared__ float sW[8 * 512];
+    for (int i = threadIdx.x; i < A1 * 512; i += blockDim.x) sW[i] = Wh[i];
+    __syncthreads();
+    const int64_t total = n * 64;                      // 64 groups of 8 per row
+    for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t row = idx >> 6;
+        const int h0 = (int)(idx & 63) * 8;
+        float d[8];
+#pragma unroll
+        for (int a = 0; a < 8; ++a) d[a] = a < A1 ? __ldg(dhead + row * A1 + a) : 0.f;
+        const int4 m = ldg16(hid + row * 512 + h0);
+        const uint32_t mw[4] = {(uint32_t)m.x, (uint32_t)m.y, (uint32_t)m.z, (uint32_t)m.w};
+        float o[8];
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+            float s = 0.f;
+#pragma unroll
+            for (int a = 0; a < 8; ++a) if (a < A1) s = fmaf(d[a], sW[a * 512 + h0 + e], s);
+            const uint32_t half = (e & 1) ? (mw[e >> 1] >> 16) : (mw[e >> 1] & 0xFFFFu);
+            o[e] = (half & 0x7FFFu) && !(half & 0x8000u) ? s : 0.f;     // hid > 0
+        }
+        int4 w;
+        w.x = (int)pack_bf16x2(o[0], o[1]); w.y = (int)pack_bf16x2(o[2], o[3]);
+        w.z = (int)pack_bf16x2(o[4], o[5]); w.w = (int)pack_bf16x2(o[6], o[7]);
+        *reinterpret_cast<int4*>(dhid + row * 512 + h0) = w;
+    }
 }
 // dWh[a][h] = sum_m dhead[m][a] * hid[m][h]; dbh[a] = sum_m dhead[m][a]  (partials per row block, then fold)
 __global__ void __launch_bounds__(512) tc_heads_bwd_weight(const float* __restrict__ dhead, const bf16* __restrict__ hid,
@@ -1179,7 +1198,24 @@ __global__ void __launch_bounds__(512) tc_heads_bwd_weight(const float* __restri
     if (r1 > n) r1 = n;
     float acc[8], bacc[8];
     for (int a = 0; a < 8; ++a) { acc[a] = 0.f; bacc[a] = 0.f; }
-    for (int64_t r = r0; r < r1; ++r) {
+    int64_t r = r0;
+    for (; r + 4 <= r1; r += 4) {          // 4 rows in flight per thread
+        float hv[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) hv[u] = h < H ? __bfloat162float(hid[(r + u) * H + h]) : 0.f;
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+#pragma unroll
+            for (int a = 0; a < 8; ++a) {
+                if (a < A1) {
+                    const float d = __ldg(dhead + (r + u) * A1 + a);
+                    acc[a] = fmaf(d, hv[u], acc[a]);
+                    bacc[a] += d;
+                }
+            }
+        }
+    }
+    for (; r < r1; ++r) {
         const float hv = h < H ? __bfloat162float(hid[r * H + h]) : 0.f;
 #pragma unroll
         for (int a = 0; a < 8; ++a) {
@@ -1335,7 +1371,7 @@ static int launch_wgrad_win(const WGradWinParams& p, int ctas, cudaStream_t s, c
 }
 
 static int colsum(const bf16* Y, int64_t M, int ld, int ncols, float* part, float* db, cudaStream_t s) {
-    int64_t rpb = ceil_div(M, 148 * 8);
+    int64_t rpb = ceil_div(M, 148 * 3);
     if (rpb < 64) rpb = 64;
     const int nb = (int)ceil_div(M, rpb);
     tc_colsum_partial<<<nb, 256, 0, s>>>(Y, M, ld, ncols, rpb, part);
@@ -1343,7 +1379,7 @@ static int colsum(const bf16* Y, int64_t M, int ld, int ncols, float* part, floa
     return check_launch("colsum", 2);
 }
 static size_t colsum_ws(int64_t M, int ncols) {
-    int64_t rpb = ceil_div(M, 148 * 8);
+    int64_t rpb = ceil_div(M, 148 * 3);
     if (rpb < 64) rpb = 64;
     return (size_t)ceil_div(M, rpb) * ncols * sizeof(float);
 }
@@ -1496,7 +1532,8 @@ extern "C" int b200rl_naturecnn_bf16_backward(const void* obs, int obs_format, c
         ProfScope ps(s, "heads_bwd", 4.0 * n * 512 * A1, (double)n * (2048 + 8 * A1));
         tc_heads_bwd_weight<<<nb, 512, 0, s>>>(dhead, act + Q.hid, n, A1, 512, rpb, wssmall);
         tc_heads_fold<<<(unsigned)ceil_div(A1 * 513, 128), 128, 0, s>>>(wssmall, nb, A1, 512, grads + L.hw, grads + L.hb);
-        tc_heads_bwd_data<<<(unsigned)ceil_div(n * 512, 256), 256, 0, s>>>(dhead, params + L.hw, act + Q.hid, n, A1, 512, act + Q.dhid);
+        int db_blocks = (int)ceil_div(n * 64, 256); if (db_blocks > num_sms() * 8) db_blocks = num_sms() * 8;
+        tc_heads_bwd_data<<<db_blocks, 256, 0, s>>>(dhead, params + L.hw, act + Q.hid, n, A1, 512, act + Q.dhid);
         if ((rc = check_launch("naturecnn/heads_bwd", 3))) return rc;
     }
     WGradParams w;

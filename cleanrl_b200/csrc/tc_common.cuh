@@ -37,8 +37,16 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
         : "memory");
     return ok != 0;
 }
+// Bounded wait: a protocol bug must surface as a launch failure (trap), never as a hung GPU.
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
-    while (!mbar_try_wait(bar, parity)) {}
+    if (mbar_try_wait(bar, parity)) return;
+    uint64_t t0;
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t0));
+    while (!mbar_try_wait(bar, parity)) {
+        uint64_t t1;
+        asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t1));
+        if (t1 - t0 > 4000000000ull) __trap();      // 4 s without progress
+    }
 }
 
 // generic-proxy smem writes -> visible to the async proxy (tcgen05.mma operand reads)

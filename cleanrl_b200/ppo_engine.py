@@ -67,6 +67,7 @@ class PPOEngine:
         # bf16 tensor-core path on Atari frames: the rollout is stored ONCE as space-to-depth bf16
         # [T,N,21,21,64] (converted per env step from the uint8 staging batch); every minibatch pass
         # then gathers 128-byte pixels directly -- no per-minibatch uint8 decode, no fp32 obs.
+        self.sort_minibatch = os.environ.get("CLEANRL_B200_SORT_MINIBATCH", "1") != "0"
         self.s2d = (getattr(agent, "precision", "fp32") == "bf16" and self.obs_dtype == torch.uint8
                     and tuple(obs_shape) == (4, 84, 84) and device.type == "cuda")
         if self.s2d:
@@ -228,6 +229,11 @@ class PPOEngine:
                 self.b_inds_h[epoch].copy_(torch.from_numpy(b_inds_np))
             self.b_inds.copy_(self.b_inds_h, non_blocking=True)
             self.h2d_bytes += E * B * 8
+            if self.s2d and self.sort_minibatch:
+                # same minibatch SETS as the reference's shuffle; rows visited in ascending address order so the
+                # 56 KB frames gathered by conv1 share DRAM pages / TLB entries (the sums over a minibatch are
+                # order-independent up to fp rounding)
+                self.b_inds.copy_(torch.sort(self.b_inds.view(E, self.num_minibatches, M), dim=2).values.view(E, B))
         for epoch in range(E):
             if not pre:
                 np.random.shuffle(b_inds_np)                # numpy global RNG, as the reference
