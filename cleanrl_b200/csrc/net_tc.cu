@@ -412,19 +412,17 @@ __global__ void __launch_bounds__(288, 1) tc_conv_win(const WinParams p, int tot
             if (q >= (uint32_t)STAGES) mbar_wait(&empty_bar[s], ((q / STAGES) - 1) & 1);
             const uint32_t sA = smem_u32(sRing + (size_t)s * STAGE_BYTES) + cc * IMG;
             int64_t r = row0 + wr0;
-            int rem = p.rows ? (int)(r - ibase * p.G) : 0;      // may exceed G: second image of the window
-            for (int wr = wr0; wr < p.WR; wr += RSTEP, r += RSTEP, rem += RSTEP) {
-                const bool ok = r < p.M;
-                const bf16* src = p.A;
-                if (ok) {
-                    if (p.rows) {
-                        const bool second = rem >= p.G;
-                        src = p.A + (((second ? cimg1 : cimg0) * p.G + (second ? rem - p.G : rem)) * (int64_t)(CPR * 64) + pc * 8);
-                    } else {
-                        src = p.A + (r * (int64_t)(CPR * 64) + pc * 8);
-                    }
-                }
-                cp_async16(sA + img_off(wr, c16), src, ok ? 16u : 0u);
+            // row -> source pointer with one compare + select + multiply-add per row: the window lies in at most
+            // two images, whose bases (pre-biased so that `rem` indexes both) are computed once per tile
+            int rem = p.rows ? (int)(r - ibase * p.G) : 0;
+            const bf16* base0 = p.rows ? p.A + (cimg0 * p.G) * (int64_t)(CPR * 64) + pc * 8 : p.A + row0 * (int64_t)(CPR * 64) + pc * 8;
+            const bf16* base1 = p.rows ? p.A + ((cimg1 - 1) * p.G) * (int64_t)(CPR * 64) + pc * 8 : base0;
+            if (!p.rows) rem = wr0;
+            const int64_t rows_left = p.M - row0;           // rows of this window that exist at all
+            for (int wr = wr0; wr < p.WR; wr += RSTEP, rem += RSTEP) {
+                const bool ok = wr < rows_left;
+                const bf16* src = ((p.rows && rem >= p.G) ? base1 : base0) + (int64_t)rem * (CPR * 64);
+                cp_async16(sA + img_off(wr, c16), ok ? src : p.A, ok ? 16u : 0u);
             }
             cp_async_commit();
             if (q >= (uint32_t)LOOKAHEAD) {
@@ -850,20 +848,15 @@ __global__ void __launch_bounds__(160, 1) tc_wgrad_win(const WGradWinParams p) {
             const uint32_t sY = sX + XBYTES;
             // X window: rows m0 .. m0+WRX-1 (may run past m_end: those rows belong to the next CTA / are zero)
             {
-                int64_t r = m0 + wr0;
-                int rem = p.rows ? (int)(r - ibase * p.G) : 0;
-                for (int wr = wr0; wr < p.WRX; wr += rstep, r += rstep, rem += rstep) {
-                    const bool ok = r < p.M;
-                    const bf16* src = p.X;
-                    if (ok) {
-                        if (p.rows) {
-                            const bool second = rem >= p.G;
-                            src = p.X + (((second ? cimg1 : cimg0) * p.G + (second ? rem - p.G : rem)) * (int64_t)(p.cpr * 64) + pc * 8);
-                        } else {
-                            src = p.X + (r * (int64_t)(p.cpr * 64) + pc * 8);
-                        }
-                    }
-                    cp_async16(sX + cc * IMGX + img_off(wr, c16), src, ok ? 16u : 0u);
+                const int rw = p.cpr * 64;                 // elements per X row
+                int rem = p.rows ? (int)(m0 + wr0 - ibase * p.G) : wr0;
+                const bf16* base0 = p.rows ? p.X + (cimg0 * p.G) * (int64_t)rw + pc * 8 : p.X + m0 * (int64_t)rw + pc * 8;
+                const bf16* base1 = p.rows ? p.X + ((cimg1 - 1) * p.G) * (int64_t)rw + pc * 8 : base0;
+                const int64_t rows_left = p.M - m0;
+                for (int wr = wr0; wr < p.WRX; wr += rstep, rem += rstep) {
+                    const bool ok = wr < rows_left;
+                    const bf16* src = ((p.rows && rem >= p.G) ? base1 : base0) + (int64_t)rem * rw;
+                    cp_async16(sX + cc * IMGX + img_off(wr, c16), ok ? src : p.X, ok ? 16u : 0u);
                 }
             }
             // dY rows m0 .. m0+127 (zero beyond this CTA's range so that boundary rows are counted once)
