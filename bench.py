@@ -126,6 +126,7 @@ def run_ours(opt):
     device = torch.device("cuda", local_rank)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        os.environ["NCCL_DEBUG"] = "WARN"        # keep stdout to the single JSON line (NCCL prints its version there)
         dist.init_process_group("nccl", rank=rank, world_size=world, device_id=device)
     build.build()
     lib = _lib.load()

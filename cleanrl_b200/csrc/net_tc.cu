@@ -26,6 +26,7 @@
 //   tc_gemm_ws<BN,STAGES,WRES>   fc forward / data-gradient: row-major A, weights streamed through the ring.
 //   tc_wgrad_ws                  fc weight gradient (MN-major views of dhid / act3 rows).
 //   tc_heads_*                   the A+1 head outputs in fp32 on CUDA cores.
+#include <cuda.h>            // CUtensorMap types only; the encoder is resolved at run time (no libcuda link)
 #include "common.cuh"
 #include "tc_common.cuh"
 
@@ -568,6 +569,279 @@ __global__ void __launch_bounds__(288, 1) tc_conv_win(const WinParams p, int tot
     if (warp == 4) tmem_dealloc(tmem_d, TMEM_COLS);
 }
 
+
+// ------------------------------------------------------------------ kernel 1d: TMA-fed GEMM (fc forward / data-gradient)
+// Plain row-major operands => the tiles are rectangular boxes: ONE thread issues cp.async.bulk.tensor (TMA,
+// SWIZZLE_128B) loads for the A chunk [128 x 64] and the weight chunk [BN x 64]; the hardware does the address
+// generation, zero-fills out-of-range rows and signals the stage's mbarrier with complete_tx.  Warp 0 = TMA
+// producer, warp 1 = TMEM allocator + MMA issuer, warps 2-5 = epilogue over double-buffered accumulators.
+template <int BN, int STAGES>
+__global__ void __launch_bounds__(192, 1) tc_gemm_tma(const __grid_constant__ CUtensorMap tmA,
+                                                      const __grid_constant__ CUtensorMap tmB,
+                                                      const KGemmParams p, int total_tiles, int ntiles_n) {
+    constexpr int A_BYTES = 128 * 128;
+    constexpr int B_BYTES = BN * 128;
+    constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+    constexpr uint32_t TMEM_COLS = (2 * BN) < 32 ? 32 : 2 * BN;
+    extern __shared__ uint8_t smem_raw[];
+    __shared__ uint64_t full_bar[STAGES], empty_bar[STAGES], tfull_bar[2], tempty_bar[2];
+    __shared__ uint32_t tmem_base_smem;
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    const int tid = threadIdx.x, warp = tid >> 5;
+    const int nch = p.nchunks;
+    if (tid == 0) {
+        for (int s = 0; s < STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
+        for (int a = 0; a < 2; ++a) { mbar_init(&tfull_bar[a], 1); mbar_init(&tempty_bar[a], 4); }
+        fence_barrier_init();
+        tma_prefetch_desc(&tmA);
+        tma_prefetch_desc(&tmB);
+    }
+    if (warp == 1) tmem_alloc(&tmem_base_smem, TMEM_COLS);
+    tc_fence_before_sync();
+    __syncthreads();
+    tc_fence_after_sync();
+    const uint32_t tmem_d = tmem_base_smem;
+
+    if (warp == 0) {
+        if ((tid & 31) == 0) {
+            uint32_t q = 0;
+            for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+                const int mt = tile / ntiles_n, n0 = (tile - mt * ntiles_n) * BN;
+                for (int j = 0; j < nch; ++j, ++q) {
+                    const uint32_t s = q % STAGES;
+                    if (q >= (uint32_t)STAGES) mbar_wait(&empty_bar[s], ((q / STAGES) - 1) & 1);
+                    const uint32_t dst = smem_u32(smem + (size_t)s * STAGE_BYTES);
+                    mbar_arrive_expect_tx(&full_bar[s], STAGE_BYTES);
+                    tma_load_2d(dst, &tmA, j * 64, mt * 128, &full_bar[s]);
+                    tma_load_2d(dst + A_BYTES, &tmB, j * 64, n0, &full_bar[s]);
+                }
+            }
+        }
+    } else if (warp == 1) {
+        if ((tid & 31) == 0) {
+            constexpr uint32_t idesc = make_idesc(128, BN, 0, 0);
+            uint32_t q = 0, t = 0;
+            for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++t) {
+                const uint32_t acc = t & 1;
+                if (t >= 2) mbar_wait(&tempty_bar[acc], ((t >> 1) - 1) & 1);
+                tc_fence_after_sync();
+                const uint32_t d_addr = tmem_d + acc * BN;
+                for (int j = 0; j < nch; ++j, ++q) {
+                    const uint32_t s = q % STAGES;
+                    mbar_wait(&full_bar[s], (q / STAGES) & 1);
+                    tc_fence_after_sync();
+                    const uint32_t stage_addr = smem_u32(smem + (size_t)s * STAGE_BYTES);
+                    const uint64_t adesc = desc_kmajor(stage_addr), bdesc = desc_kmajor(stage_addr + A_BYTES);
+#pragma unroll
+                    for (int kk = 0; kk < 4; ++kk) umma_bf16(d_addr, adesc + 2 * kk, bdesc + 2 * kk, idesc, (j | kk) != 0);
+                    umma_commit(&empty_bar[s]);
+                }
+                umma_commit(&tfull_bar[acc]);
+            }
+        }
+    } else {
+        const int ew = warp & 3;
+        const int lrow = ew * 32 + (tid & 31);
+        uint32_t t = 0;
+        for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++t) {
+            const int mt = tile / ntiles_n, n0 = (tile - mt * ntiles_n) * BN;
+            const uint32_t acc = t & 1;
+            const int r = mt * 128 + lrow;
+            const bool rvalid = r < (int)p.M;
+            const int64_t ooff = (int64_t)r * p.ldo;
+            const bool use_mask = p.mask != nullptr && rvalid;
+            int4 mk0 = make_int4(0, 0, 0, 0), mk1 = make_int4(0, 0, 0, 0);
+            if (use_mask && n0 < p.N) { mk0 = ldg16(p.mask + ooff + n0); mk1 = ldg16(p.mask + ooff + n0 + 8); }
+            mbar_wait(&tfull_bar[acc], (t >> 1) & 1);
+            tc_fence_after_sync();
+            const uint32_t lane_addr = tmem_d + acc * BN + ((uint32_t)(ew * 32) << 16);
+#pragma unroll 1
+            for (int c0 = 0; c0 < BN; c0 += 16) {
+                uint32_t v[16];
+                tmem_ld16(lane_addr + c0, v);
+                const int4 m0 = mk0, m1 = mk1;
+                if (use_mask && c0 + 16 < BN && n0 + c0 + 16 < p.N) {
+                    mk0 = ldg16(p.mask + ooff + n0 + c0 + 16); mk1 = ldg16(p.mask + ooff + n0 + c0 + 24);
+                }
+                tmem_ld_wait();
+                const int col = n0 + c0;
+                if (!rvalid || col >= p.N) continue;
+                float f[16];
+                if (p.bias) {
+                    const float4* bp = reinterpret_cast<const float4*>(p.bias + col);
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) {
+                        const float4 bv = __ldg(bp + e);
+                        f[4 * e] = fmaf(__uint_as_float(v[4 * e]), p.scale, bv.x);
+                        f[4 * e + 1] = fmaf(__uint_as_float(v[4 * e + 1]), p.scale, bv.y);
+                        f[4 * e + 2] = fmaf(__uint_as_float(v[4 * e + 2]), p.scale, bv.z);
+                        f[4 * e + 3] = fmaf(__uint_as_float(v[4 * e + 3]), p.scale, bv.w);
+                    }
+                } else {
+#pragma unroll
+                    for (int e = 0; e < 16; ++e) f[e] = __uint_as_float(v[e]) * p.scale;
+                }
+                if (p.relu) {
+#pragma unroll
+                    for (int e = 0; e < 16; ++e) f[e] = fmaxf(f[e], 0.f);
+                }
+                if (p.mask) {
+                    const uint32_t mw[8] = {(uint32_t)m0.x, (uint32_t)m0.y, (uint32_t)m0.z, (uint32_t)m0.w,
+                                            (uint32_t)m1.x, (uint32_t)m1.y, (uint32_t)m1.z, (uint32_t)m1.w};
+#pragma unroll
+                    for (int e = 0; e < 8; ++e) {
+                        if ((mw[e] & 0x7FFFu) == 0u) f[2 * e] = 0.f;
+                        if ((mw[e] & 0x7FFF0000u) == 0u) f[2 * e + 1] = 0.f;
+                    }
+                }
+                int4 o0, o1;
+                o0.x = (int)pack_bf16x2(f[0], f[1]);   o0.y = (int)pack_bf16x2(f[2], f[3]);
+                o0.z = (int)pack_bf16x2(f[4], f[5]);   o0.w = (int)pack_bf16x2(f[6], f[7]);
+                o1.x = (int)pack_bf16x2(f[8], f[9]);   o1.y = (int)pack_bf16x2(f[10], f[11]);
+                o1.z = (int)pack_bf16x2(f[12], f[13]); o1.w = (int)pack_bf16x2(f[14], f[15]);
+                if (p.dual_dact3) {
+                    const int px = col >> 6, ch = col & 63;
+                    const int oy = px / 7, ox = px - oy * 7;
+                    int4* da = reinterpret_cast<int4*>(p.out + ((int64_t)r * 81 + oy * 9 + ox) * 64 + ch);
+                    int4* db = reinterpret_cast<int4*>(p.out2 + ((int64_t)r * 121 + (oy + 2) * 11 + ox + 2) * 64 + ch);
+                    da[0] = o0; da[1] = o1;
+                    db[0] = o0; db[1] = o1;
+                } else {
+                    int4* dst = reinterpret_cast<int4*>(p.out + ooff + col);
+                    dst[0] = o0; dst[1] = o1;
+                }
+            }
+            tc_fence_before_sync();
+            __syncwarp();
+            if ((tid & 31) == 0) mbar_arrive(&tempty_bar[acc]);
+        }
+    }
+    tc_fence_before_sync();
+    __syncthreads();
+    if (warp == 1) tmem_dealloc(tmem_d, TMEM_COLS);
+}
+
+// ------------------------------------------------------------------ kernel 2d: TMA-fed weight gradient (fc)
+// D[o, k] = sum_m dhid[m, o] * act3[m, k]: both operands are row-major, so each 64-row x 64-column chunk image is
+// one TMA box; they are consumed as MN-major operands.  grid = (row splits, X groups of 2 chunks, Y groups of 4).
+__global__ void __launch_bounds__(160, 1) tc_wgrad_tma(const __grid_constant__ CUtensorMap tmX,
+                                                       const __grid_constant__ CUtensorMap tmY,
+                                                       int64_t M, int64_t rows_per_cta, int nxc, int nyc, float* ws) {
+    constexpr int R = 64, STAGES = 4;
+    extern __shared__ uint8_t smem_raw[];
+    __shared__ uint64_t full_bar[STAGES], empty_bar[STAGES], done_bar;
+    __shared__ uint32_t tmem_base_smem;
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    const int tid = threadIdx.x, warp = tid >> 5;
+    const int NY = nyc * 64;
+    const int xc0 = blockIdx.y * nxc, yc0 = blockIdx.z * nyc;
+    const int xt = nxc / 2;
+    constexpr int chunk_img = R * 128;
+    const int stage_bytes = (nxc + nyc) * chunk_img;
+    uint32_t tmem_cols = 32;
+    while ((int)tmem_cols < xt * NY) tmem_cols <<= 1;
+    if (tid == 0) {
+        for (int s = 0; s < STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
+        mbar_init(&done_bar, 1);
+        fence_barrier_init();
+        tma_prefetch_desc(&tmX);
+        tma_prefetch_desc(&tmY);
+    }
+    if (warp == 4) tmem_alloc(&tmem_base_smem, tmem_cols);
+    tc_fence_before_sync();
+    __syncthreads();
+    tc_fence_after_sync();
+    const uint32_t tmem_d = tmem_base_smem;
+    const int64_t m_begin = (int64_t)blockIdx.x * rows_per_cta;
+    int64_t m_end = m_begin + rows_per_cta;
+    if (m_end > M) m_end = M;
+    const int nsteps = m_end > m_begin ? (int)((m_end - m_begin + R - 1) / R) : 0;
+
+    if (warp == 0 && (tid & 31) == 0) {
+        for (int it = 0; it < nsteps; ++it) {
+            const int s = it % STAGES;
+            if (it >= STAGES) mbar_wait(&empty_bar[s], ((it / STAGES) - 1) & 1);
+            const uint32_t dst = smem_u32(smem + (size_t)s * stage_bytes);
+            const int m0 = (int)(m_begin + (int64_t)it * R);
+            mbar_arrive_expect_tx(&full_bar[s], (uint32_t)stage_bytes);
+            for (int c = 0; c < nxc; ++c) tma_load_2d(dst + c * chunk_img, &tmX, (xc0 + c) * 64, m0, &full_bar[s]);
+            for (int c = 0; c < nyc; ++c) tma_load_2d(dst + (nxc + c) * chunk_img, &tmY, (yc0 + c) * 64, m0, &full_bar[s]);
+        }
+    } else if (warp == 4 && (tid & 31) == 0) {
+        const uint32_t idesc = make_idesc(128, NY, 1, 1);
+        for (int it = 0; it < nsteps; ++it) {
+            const int s = it % STAGES;
+            mbar_wait(&full_bar[s], (it / STAGES) & 1);
+            tc_fence_after_sync();
+            const uint32_t xa = smem_u32(smem + (size_t)s * stage_bytes), ya = xa + nxc * chunk_img;
+            for (int t = 0; t < xt; ++t) {
+#pragma unroll
+                for (int kk = 0; kk < R / 16; ++kk) {
+                    const uint64_t adesc = desc_mnmajor(xa + (2 * t) * chunk_img + kk * 2048, chunk_img);
+                    const uint64_t bdesc = desc_mnmajor(ya + kk * 2048, chunk_img);
+                    umma_bf16(tmem_d + t * NY, adesc, bdesc, idesc, (it | kk) != 0);
+                }
+            }
+            umma_commit(&empty_bar[s]);
+        }
+        umma_commit(&done_bar);
+    }
+    if (warp < 4) {
+        if (nsteps > 0) {
+            mbar_wait(&done_bar, 0);
+            tc_fence_after_sync();
+        }
+        const int64_t KXtot = (int64_t)gridDim.y * nxc * 64, NYtot = (int64_t)gridDim.z * NY;
+        float* wsb = ws + (int64_t)blockIdx.x * KXtot * NYtot;
+        const uint32_t lane_addr = tmem_d + ((uint32_t)(warp * 32) << 16);
+        for (int t = 0; t < xt; ++t) {
+            float* dst = wsb + ((int64_t)xc0 * 64 + t * 128 + tid) * NYtot + (int64_t)yc0 * 64;
+            for (int c0 = 0; c0 < NY; c0 += 16) {
+                uint32_t v[16];
+                if (nsteps > 0) {
+                    tmem_ld16(lane_addr + t * NY + c0, v);
+                    tmem_ld_wait();
+                } else {
+#pragma unroll
+                    for (int e = 0; e < 16; ++e) v[e] = 0u;
+                }
+#pragma unroll
+                for (int e = 0; e < 16; e += 4)
+                    *reinterpret_cast<float4*>(dst + c0 + e) = make_float4(__uint_as_float(v[e]), __uint_as_float(v[e + 1]),
+                                                                             __uint_as_float(v[e + 2]), __uint_as_float(v[e + 3]));
+            }
+        }
+    }
+    tc_fence_before_sync();
+    __syncthreads();
+    if (warp == 4) tmem_dealloc(tmem_d, tmem_cols);
+}
+
+// ---- host: tensor maps for row-major bf16 matrices (cuTensorMapEncodeTiled resolved through the runtime)
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static EncodeTiledFn g_encode = nullptr;
+static int make_tmap_2d(CUtensorMap* tm, const void* base, int64_t rows, int64_t cols, int box_rows, const char* what) {
+    if (!g_encode) {
+        void* fn = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        cudaError_t e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres);
+        if (e != cudaSuccess || qres != cudaDriverEntryPointSuccess || !fn)
+            return fail(B200RL_ERR_CUDA, "%s: cuTensorMapEncodeTiled not available (%s)", what, cudaGetErrorString(e));
+        g_encode = reinterpret_cast<EncodeTiledFn>(fn);
+    }
+    const cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+    const cuuint64_t strides[1] = {(cuuint64_t)cols * 2};
+    const cuuint32_t box[2] = {64u, (cuuint32_t)box_rows};
+    const cuuint32_t estr[2] = {1u, 1u};
+    CUresult r = g_encode(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides, box, estr,
+                          CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                          CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return fail(B200RL_ERR_CUDA, "%s: cuTensorMapEncodeTiled failed (%d)", what, (int)r);
+    return B200RL_OK;
+}
+
 static int g_num_sms = 0;
 static int num_sms() {
     if (g_num_sms == 0) {
@@ -576,6 +850,29 @@ static int num_sms() {
         if (cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || g_num_sms <= 0) g_num_sms = 148;
     }
     return g_num_sms;
+}
+
+// A: row-major [M, 64*nchunks] bf16 (p.A), weights p.Bw [N, 64*nchunks]; epilogue fields as tc_gemm_ws
+template <int BN, int STAGES>
+static int launch_gemm_tma(const KGemmParams& p, cudaStream_t s, const char* what) {
+    const size_t smem = (size_t)STAGES * (128 * 128 + BN * 128) + 1024;
+    static size_t attr = 0;
+    if (smem > attr) {
+        cudaError_t e = cudaFuncSetAttribute(tc_gemm_tma<BN, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return fail(B200RL_ERR_CUDA, "%s: smem attribute (%zu B): %s", what, smem, cudaGetErrorString(e));
+        attr = smem;
+    }
+    CUtensorMap tmA, tmB;
+    int rc;
+    const int64_t K = (int64_t)p.nchunks * 64;
+    if ((rc = make_tmap_2d(&tmA, p.A, p.M, K, 128, what))) return rc;
+    if ((rc = make_tmap_2d(&tmB, p.Bw, p.N, K, BN, what))) return rc;
+    const int ntn = (int)ceil_div(p.N, BN);
+    const int total = (int)ceil_div(p.M, 128) * ntn;
+    int grid = num_sms();
+    if (grid > total) grid = total;
+    tc_gemm_tma<BN, STAGES><<<grid, 192, smem, s>>>(tmA, tmB, p, total, ntn);
+    return check_launch(what);
 }
 
 template <int BN, int CPR, int STAGES>
@@ -789,6 +1086,7 @@ struct WGradWinParams {
     const bf16* Y; int ldy, ncolsY;
     int64_t rows_per_cta;    // multiple of 128
     float* ws;               // [gridDim.x][nslots*64][64]
+    float* wsb;              // [gridDim.x][64] bias-gradient partials: sum_r dY[r, co] (an extra all-ones X tile)
 };
 
 __global__ void __launch_bounds__(160, 1) tc_wgrad_win(const WGradWinParams p) {
@@ -803,7 +1101,12 @@ __global__ void __launch_bounds__(160, 1) tc_wgrad_win(const WGradWinParams p) {
     const int stage_bytes = XBYTES + R * 128;
     const int xt = p.nslots / 2;
     uint32_t tmem_cols = 32;
-    while ((int)tmem_cols < xt * NY) tmem_cols <<= 1;
+    while ((int)tmem_cols < (xt + 1) * NY) tmem_cols <<= 1;     // + one tile for the bias gradient
+    // 4 KB of bf16 1.0 after the ring: an MN-major operand whose every element is 1 (atoms 2 KB apart, K groups
+    // 1 KB apart all fall inside it) => D_ones[., co] = sum_r dY[r, co] = the bias gradient, for one extra MMA/step
+    uint8_t* sOnes = smem + (size_t)STAGES * stage_bytes;
+    for (int i = tid; i < 4096 / 4; i += blockDim.x) reinterpret_cast<uint32_t*>(sOnes)[i] = 0x3F803F80u;
+    fence_proxy_async_smem();
     if (tid == 0) {
         for (int s = 0; s < STAGES; ++s) { mbar_init(&full_bar[s], 4); mbar_init(&empty_bar[s], 1); }
         mbar_init(&done_bar, 1);
@@ -898,6 +1201,10 @@ __global__ void __launch_bounds__(160, 1) tc_wgrad_win(const WGradWinParams p) {
                     umma_bf16(tmem_d + t * NY, adesc, bdesc, idesc, (it | kk) != 0);
                 }
             }
+#pragma unroll
+            for (int kk = 0; kk < R / 16; ++kk)
+                umma_bf16(tmem_d + xt * NY, desc_mnmajor(smem_u32(sOnes), 2048), desc_mnmajor(ya + kk * 2048, R * 128), idesc,
+                          (it | kk) != 0);
             umma_commit(&empty_bar[s]);
         }
         umma_commit(&done_bar);
@@ -909,6 +1216,20 @@ __global__ void __launch_bounds__(160, 1) tc_wgrad_win(const WGradWinParams p) {
         }
         float* wsb = p.ws + (int64_t)blockIdx.x * (p.nslots * 64) * NY;
         const uint32_t lane_addr = tmem_d + ((uint32_t)(warp * 32) << 16);
+        if (warp == 0) {      // bias partial: any row of the all-ones tile (row 0)
+            for (int c0 = 0; c0 < NY; c0 += 16) {
+                uint32_t v[16];
+                if (nsteps > 0) { tmem_ld16(lane_addr + xt * NY + c0, v); tmem_ld_wait(); }
+                else {
+#pragma unroll
+                    for (int e = 0; e < 16; ++e) v[e] = 0u;
+                }
+                if (tid == 0) {
+#pragma unroll
+                    for (int e = 0; e < 16; ++e) p.wsb[(int64_t)blockIdx.x * NY + c0 + e] = __uint_as_float(v[e]);
+                }
+            }
+        }
         for (int t = 0; t < xt; ++t) {
             float* dst = wsb + (int64_t)(t * 128 + tid) * NY;
             for (int c0 = 0; c0 < NY; c0 += 16) {
@@ -936,11 +1257,20 @@ __global__ void __launch_bounds__(160, 1) tc_wgrad_win(const WGradWinParams p) {
 //   layer 1: slot = tap (a,b); row channel q = c*16 + sy*4 + sx; ky = 4a+sy, kx = 4b+sx; 32 outputs, Cin 4, 8x8
 //   layer 2: slot = (tap (a,b), cc); q = cc*64 + row = (py*2+px)*32 + c; ky = 2a+py, kx = 2b+px; Cin 32, 4x4
 //   layer 3: slot -> tap (ky,kx) via slot_tap (a duplicate slot is skipped); q = c; Cin 64, 3x3
-struct FoldWin { int layer, S, nslots, Cout; int slot_tap[16], slot_cc[16], slot_skip[16]; float scale; };
+struct FoldWin { int layer, S, nslots, Cout; int slot_tap[16], slot_cc[16], slot_skip[16]; float scale;
+                 const float* wsb; float* db; };
 __global__ void tc_fold_win(const float* __restrict__ ws, const FoldWin f, float* __restrict__ dst) {
     const int idx = blockIdx.x * blockDim.x + threadIdx.x;           // (slot*64 + row) * Cout + co
     const int KX = f.nslots * 64;
-    if (idx >= KX * f.Cout) return;
+    if (idx >= KX * f.Cout) {
+        const int co = idx - KX * f.Cout;                            // trailing threads fold the bias partials
+        if (co < f.Cout && f.db) {
+            float s = 0.f;
+            for (int z = 0; z < f.S; ++z) s += f.wsb[(int64_t)z * 64 + co];
+            f.db[co] = s;
+        }
+        return;
+    }
     const int xi = idx / f.Cout, co = idx - xi * f.Cout;
     const int slot = xi >> 6, row = xi & 63;
     if (f.slot_skip[slot]) return;
@@ -1352,7 +1682,7 @@ static int launch_wgrad(const WGradParams& p, dim3 grid, cudaStream_t s, const c
 }
 
 static int launch_wgrad_win(const WGradWinParams& p, int ctas, cudaStream_t s, const char* what) {
-    const size_t smem = (size_t)3 * ((size_t)p.WRX * 128 * p.cpr + 128 * 128) + 1024;
+    const size_t smem = (size_t)3 * ((size_t)p.WRX * 128 * p.cpr + 128 * 128) + 4096 + 1024;
     static size_t attr = 0;
     if (smem > attr) {
         cudaError_t e = cudaFuncSetAttribute(tc_wgrad_win, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
@@ -1405,7 +1735,7 @@ extern "C" size_t b200rl_naturecnn_bf16_workspace_bytes(int64_t n, int A) {
     mx((size_t)wgrad_plan(n * 441, kC1Ctas, 128).splits * 256 * 64 * 4);
     mx((size_t)wgrad_plan(n * 100, kC2Ctas, 128).splits * 512 * 64 * 4);
     mx((size_t)wgrad_plan(n * 81, kC3Ctas, 128).splits * 640 * 64 * 4);
-    mx((size_t)wgrad_plan(n, kFcSplits).splits * 512 * (13 * 256) * 4);
+    mx((size_t)wgrad_plan(n, kFcSplits, 64).splits * 512 * (13 * 256) * 4);
     size_t b = 0;
     auto mb = [&](size_t v) { if (v > b) b = v; };
     mb(colsum_ws(n * 441, 32)); mb(colsum_ws(n * 100, 64)); mb(colsum_ws(n * 81, 64)); mb(colsum_ws(n, 512));
@@ -1475,8 +1805,8 @@ extern "C" int b200rl_naturecnn_bf16_forward(const void* obs, int obs_format, co
     p.Bw = P + L.wfcf; p.N = 512; p.out = act + Q.hid; p.OH = 1; p.OW = 1; p.ldo = 512; p.bias = params + L.fcb; p.relu = 1;
     { ProfScope ps(s, "fc_fwd", 2.0 * n * 512 * 3136, (double)n * (3136 + 512) * 2 + 512.0 * 3136 * 2);
       // small batches (rollout step): narrower N tiles => 4x more CTAs for the same work
-      if (n <= 8192) { if ((rc = launch_kgemm_ws<64, 8, false>(p, s, "naturecnn/fc"))) return rc; }
-      else if ((rc = launch_kgemm_ws<256, 4, false>(p, s, "naturecnn/fc"))) return rc; }
+      if (n <= 8192) { if ((rc = launch_gemm_tma<64, 8>(p, s, "naturecnn/fc"))) return rc; }
+      else if ((rc = launch_gemm_tma<256, 4>(p, s, "naturecnn/fc"))) return rc; }
     // heads (fp32 math on CUDA cores): head_out [n, A+1] = [logits | value]
     { ProfScope ps(s, "heads_fwd", 2.0 * n * 512 * (A + 1), (double)n * (1024 + 4 * (A + 1)));
       int hb = (int)ceil_div(n, 8); if (hb > num_sms() * 8) hb = num_sms() * 8;
@@ -1510,7 +1840,7 @@ extern "C" int b200rl_naturecnn_bf16_backward(const void* obs, int obs_format, c
         mx((size_t)wgrad_plan(n * 441, kC1Ctas, 128).splits * 256 * 64 * 4);
         mx((size_t)wgrad_plan(n * 100, kC2Ctas, 128).splits * 512 * 64 * 4);
         mx((size_t)wgrad_plan(n * 81, kC3Ctas, 128).splits * 640 * 64 * 4);
-        mx((size_t)wgrad_plan(n, kFcSplits).splits * 512 * (13 * 256) * 4);
+        mx((size_t)wgrad_plan(n, kFcSplits, 64).splits * 512 * (13 * 256) * 4);
         big = (big + 255) & ~(size_t)255;
     }
     float* wsbig = reinterpret_cast<float*>(workspace);
@@ -1536,10 +1866,21 @@ extern "C" int b200rl_naturecnn_bf16_backward(const void* obs, int obs_format, c
         memset(&w, 0, sizeof(w));
         gemm_defaults(w.x); rowmajor_gather(w.x, act + Q.dhid, n, 8);
         w.Y = act + Q.act3; w.ldy = 3136; w.nyc = 4; w.ncolsY = 3136; w.nxc = 2;
-        const WPlan pl = wgrad_plan(n, kFcSplits);
+        const WPlan pl = wgrad_plan(n, kFcSplits, 64);
         w.rows_per_cta = pl.rows_per_cta; w.ws = wsbig;
         { ProfScope ps(s, "fc_wgrad", 2.0 * n * 512 * 3136, (double)n * (3136 + 512) * 2 + 512.0 * 3136 * 4);
-          if ((rc = launch_wgrad(w, dim3(pl.splits, 4, 13), s, "naturecnn/fc_wgrad"))) return rc; }
+          CUtensorMap tmX, tmY;
+          if ((rc = make_tmap_2d(&tmX, act + Q.dhid, n, 512, 64, "naturecnn/fc_wgrad"))) return rc;
+          if ((rc = make_tmap_2d(&tmY, act + Q.act3, n, 3136, 64, "naturecnn/fc_wgrad"))) return rc;
+          const size_t smem = (size_t)4 * (2 + 4) * 64 * 128 + 1024;
+          static bool attr_done = false;
+          if (!attr_done) {
+              cudaError_t e = cudaFuncSetAttribute(tc_wgrad_tma, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+              if (e != cudaSuccess) return fail(B200RL_ERR_CUDA, "fc_wgrad: smem attribute: %s", cudaGetErrorString(e));
+              attr_done = true;
+          }
+          tc_wgrad_tma<<<dim3(pl.splits, 4, 13), 160, smem, s>>>(tmX, tmY, n, pl.rows_per_cta, 2, 4, wsbig);
+          if ((rc = check_launch("naturecnn/fc_wgrad"))) return rc; }
         { ProfScope ps(s, "wgrad_fold_bias", 0, 0);
           note_launches(1); tc_fold_kernel<<<(unsigned)ceil_div((int64_t)512 * 3136, 256), 256, 0, s>>>(wsbig, pl.splits, 512, 13 * 256, 512, 3136, 2, 64, 49, 1.f, grads + L.fcw);
           if ((rc = colsum(act + Q.dhid, n, 512, 512, wssmall, grads + L.fcb, s))) return rc; }
@@ -1548,7 +1889,7 @@ extern "C" int b200rl_naturecnn_bf16_backward(const void* obs, int obs_format, c
         p.Bw = P + L.wfcdg; p.N = 3136; p.out = act + Q.dact3a; p.out2 = act + Q.dact3b; p.dual_dact3 = 1;
         p.OH = 1; p.OW = 1; p.ldo = 3136; p.mask = act + Q.act3;
         { ProfScope ps(s, "fc_dgrad", 2.0 * n * 512 * 3136, (double)n * (3136 * 2 + 512) * 2 + 512.0 * 3136 * 2);
-          if ((rc = launch_kgemm_ws<256, 4, false>(p, s, "naturecnn/fc_dgrad"))) return rc; }
+          if ((rc = launch_gemm_tma<256, 4>(p, s, "naturecnn/fc_dgrad"))) return rc; }
     }
     WGradWinParams gw;
     WinParams wp;
@@ -1562,15 +1903,16 @@ extern "C" int b200rl_naturecnn_bf16_backward(const void* obs, int obs_format, c
         for (int k = 0; k < 10; ++k) { gw.slot_tap[k] = st[k]; gw.slot_cc[k] = 0; }
         gw.Y = act + Q.dact3a; gw.ldy = 64; gw.ncolsY = 64;
         const WPlan pl = wgrad_plan(n * 81, kC3Ctas, 128);
-        gw.rows_per_cta = pl.rows_per_cta; gw.ws = wsbig;
+        gw.rows_per_cta = pl.rows_per_cta; gw.ws = wsbig; gw.wsb = wssmall;
         { ProfScope ps(s, "conv3_wgrad", 2.0 * n * 49 * 64 * 576, (double)n * (5184 + 5184) * 2);
           if ((rc = launch_wgrad_win(gw, pl.splits, s, "naturecnn/conv3_wgrad"))) return rc; }
         memset(&fw, 0, sizeof(fw));
         fw.layer = 3; fw.S = pl.splits; fw.nslots = 10; fw.Cout = 64; fw.scale = 1.f;
         for (int k = 0; k < 10; ++k) { fw.slot_tap[k] = st[k]; fw.slot_skip[k] = (k == 8); }
         { ProfScope ps(s, "wgrad_fold_bias", 0, 0);
-          note_launches(1); tc_fold_win<<<(unsigned)ceil_div(640 * 64, 256), 256, 0, s>>>(wsbig, fw, grads + L.c3w);
-          if ((rc = colsum(act + Q.dact3a, n * 81, 64, 64, wssmall, grads + L.c3b, s))) return rc; }
+          fw.wsb = wssmall; fw.db = grads + L.c3b;
+          tc_fold_win<<<(unsigned)ceil_div(640 * 64 + 64, 256), 256, 0, s>>>(wsbig, fw, grads + L.c3w);
+          if ((rc = check_launch("naturecnn/conv3_fold"))) return rc; }
         win_defaults(wp);
         wp.A = act + Q.dact3b; wp.n = (int)n; wp.G = 121; wp.Wp = 11; wp.M = n * 121; wp.ntaps = 9;
         for (int ky = 0; ky < 3; ++ky) for (int kx = 0; kx < 3; ++kx) wp.shift[ky * 3 + kx] = (2 - ky) * 11 + (2 - kx);
@@ -1589,15 +1931,16 @@ extern "C" int b200rl_naturecnn_bf16_backward(const void* obs, int obs_format, c
         for (int k = 0; k < 8; ++k) { gw.slot_tap[k] = k >> 1; gw.slot_cc[k] = k & 1; }
         gw.Y = act + Q.dact2a; gw.ldy = 64; gw.ncolsY = 64;
         const WPlan pl = wgrad_plan(n * 100, kC2Ctas, 128);
-        gw.rows_per_cta = pl.rows_per_cta; gw.ws = wsbig;
+        gw.rows_per_cta = pl.rows_per_cta; gw.ws = wsbig; gw.wsb = wssmall;
         { ProfScope ps(s, "conv2_wgrad", 2.0 * n * 81 * 64 * 512, (double)n * (12800 + 6400) * 2);
           if ((rc = launch_wgrad_win(gw, pl.splits, s, "naturecnn/conv2_wgrad"))) return rc; }
         memset(&fw, 0, sizeof(fw));
         fw.layer = 2; fw.S = pl.splits; fw.nslots = 8; fw.Cout = 64; fw.scale = 1.f;
         for (int k = 0; k < 8; ++k) { fw.slot_tap[k] = k >> 1; fw.slot_cc[k] = k & 1; }
         { ProfScope ps(s, "wgrad_fold_bias", 0, 0);
-          note_launches(1); tc_fold_win<<<(unsigned)ceil_div(512 * 64, 256), 256, 0, s>>>(wsbig, fw, grads + L.c2w);
-          if ((rc = colsum(act + Q.dact2a, n * 100, 64, 64, wssmall, grads + L.c2b, s))) return rc; }
+          fw.wsb = wssmall; fw.db = grads + L.c2b;
+          tc_fold_win<<<(unsigned)ceil_div(512 * 64 + 64, 256), 256, 0, s>>>(wsbig, fw, grads + L.c2w);
+          if ((rc = check_launch("naturecnn/conv2_fold"))) return rc; }
         win_defaults(wp);
         wp.A = act + Q.dact2b; wp.n = (int)n; wp.G = 121; wp.Wp = 11; wp.M = n * 121; wp.ntaps = 4;
         for (int a = 0; a < 2; ++a) for (int b = 0; b < 2; ++b) wp.shift[a * 2 + b] = (1 - a) * 11 + (1 - b);
@@ -1615,15 +1958,16 @@ extern "C" int b200rl_naturecnn_bf16_backward(const void* obs, int obs_format, c
         for (int k = 0; k < 4; ++k) { gw.slot_tap[k] = k; gw.slot_cc[k] = 0; }
         gw.Y = act + Q.dact1; gw.ldy = 32; gw.ncolsY = 32;
         const WPlan pl = wgrad_plan(n * 441, kC1Ctas, 128);
-        gw.rows_per_cta = pl.rows_per_cta; gw.ws = wsbig;
+        gw.rows_per_cta = pl.rows_per_cta; gw.ws = wsbig; gw.wsb = wssmall;
         { ProfScope ps(s, "conv1_wgrad", 2.0 * n * 400 * 32 * 256, (double)n * (28224 + 14112) * 2);
           if ((rc = launch_wgrad_win(gw, pl.splits, s, "naturecnn/conv1_wgrad"))) return rc; }
         memset(&fw, 0, sizeof(fw));
         fw.layer = 1; fw.S = pl.splits; fw.nslots = 4; fw.Cout = 32; fw.scale = 1.0f / 255.0f;
         for (int k = 0; k < 4; ++k) fw.slot_tap[k] = k;
         { ProfScope ps(s, "wgrad_fold_bias", 0, 0);
-          note_launches(1); tc_fold_win<<<(unsigned)ceil_div(256 * 32, 256), 256, 0, s>>>(wsbig, fw, grads + L.c1w);
-          if ((rc = colsum(act + Q.dact1, n * 441, 32, 32, wssmall, grads + L.c1b, s))) return rc; }
+          fw.wsb = wssmall; fw.db = grads + L.c1b;
+          tc_fold_win<<<(unsigned)ceil_div(256 * 32 + 32, 256), 256, 0, s>>>(wsbig, fw, grads + L.c1w);
+          if ((rc = check_launch("naturecnn/conv1_fold"))) return rc; }
     }
     return B200RL_OK;
 }
