@@ -341,7 +341,8 @@ struct WinParams {
 };
 
 template <int BN, int CPR, int STAGES>
-__global__ void __launch_bounds__(288, 1) tc_conv_win(const WinParams p, int total_tiles) {
+__global__ void __launch_bounds__(416, 1) tc_conv_win(const __grid_constant__ CUtensorMap tmA, const WinParams p,
+                                                      int total_tiles) {
     constexpr int LOOKAHEAD = STAGES - 2;
     constexpr int B_CHUNK = BN * 128;
     constexpr uint32_t TMEM_COLS = (2 * BN) < 32 ? 32 : 2 * BN;
@@ -358,9 +359,11 @@ __global__ void __launch_bounds__(288, 1) tc_conv_win(const WinParams p, int tot
     uint8_t* sRing = smem + (size_t)nchunks * B_CHUNK;
 
     if (tid == 0) {
-        for (int s = 0; s < STAGES; ++s) { mbar_init(&full_bar[s], 4); mbar_init(&empty_bar[s], 1); }
-        for (int a = 0; a < 2; ++a) { mbar_init(&tfull_bar[a], 1); mbar_init(&tempty_bar[a], 4); }
+        // window producers: one TMA issuer (expect_tx arrival) when rows are contiguous, 4 cp.async warps for the gather
+        for (int s = 0; s < STAGES; ++s) { mbar_init(&full_bar[s], p.rows ? 4 : 1); mbar_init(&empty_bar[s], 1); }
+        for (int a = 0; a < 2; ++a) { mbar_init(&tfull_bar[a], 1); mbar_init(&tempty_bar[a], 8); }
         fence_barrier_init();
+        if (!p.rows) tma_prefetch_desc(&tmA);
     }
     if (warp == 4) tmem_alloc(&tmem_base_smem, TMEM_COLS);
     for (int idx = tid; idx < nchunks * BN * 8; idx += blockDim.x) {
@@ -381,8 +384,21 @@ __global__ void __launch_bounds__(288, 1) tc_conv_win(const WinParams p, int tot
     const int tile_begin = (int)(((int64_t)total_tiles * blockIdx.x) / gridDim.x);
     const int tile_end = (int)(((int64_t)total_tiles * (blockIdx.x + 1)) / gridDim.x);
 
-    if (warp < 4) {
-        // ======================= producers: one window per tile =======================
+    if (warp < 4 && !p.rows) {
+        // ======================= TMA producer: the window is one rectangular box per 64-channel column chunk ====
+        if (tid == 0) {
+            uint32_t q = 0;
+            for (int tile = tile_begin; tile < tile_end; ++tile, ++q) {
+                const uint32_t s = q % STAGES;
+                if (q >= (uint32_t)STAGES) mbar_wait(&empty_bar[s], ((q / STAGES) - 1) & 1);
+                const uint32_t dst = smem_u32(sRing + (size_t)s * STAGE_BYTES);
+                mbar_arrive_expect_tx(&full_bar[s], (uint32_t)STAGE_BYTES);
+#pragma unroll
+                for (int c = 0; c < CPR; ++c) tma_load_2d(dst + c * IMG, &tmA, c * 64, tile * 128, &full_bar[s]);
+            }
+        }
+    } else if (warp < 4) {
+        // ======================= cp.async producers (image gather): one window per tile =======================
         constexpr int PPR = CPR * 8;               // 16-byte pieces per grid row
         constexpr int RSTEP = 128 / PPR;           // rows advanced per pass of the 128 producer threads
         const int wr0 = tid / PPR, pc = tid % PPR;
@@ -468,8 +484,10 @@ __global__ void __launch_bounds__(288, 1) tc_conv_win(const WinParams p, int tot
             }
         }
     } else {
-        // ======================= epilogue =======================
+        // ======================= epilogue: warps 5-12, two per TMEM lane quadrant; the pair splits the 16-column
+        // groups even/odd so that two warps per scheduler hide each other's tcgen05.ld / global latencies =========
         const int ew = warp & 3;
+        const int half = (warp - 5) >> 2;
         const int lrow = ew * 32 + (tid & 31);
         uint32_t q = 0;
         for (int tile = tile_begin; tile < tile_end; ++tile, ++q) {
@@ -498,17 +516,18 @@ __global__ void __launch_bounds__(288, 1) tc_conv_win(const WinParams p, int tot
             // ReLU-mask words are fetched one column group AHEAD (the first one before waiting for the
             // accumulator), so their global-memory latency overlaps the MMAs / the previous group's stores
             const bool use_mask = p.mask != nullptr && valid;
+            const int cfirst = half * 16;
             int4 mk0 = make_int4(0, 0, 0, 0), mk1 = make_int4(0, 0, 0, 0);
-            if (use_mask) { mk0 = ldg16(p.mask + om); mk1 = ldg16(p.mask + om + 8); }
+            if (use_mask && cfirst < p.N) { mk0 = ldg16(p.mask + om + cfirst); mk1 = ldg16(p.mask + om + cfirst + 8); }
             mbar_wait(&tfull_bar[acc], (q >> 1) & 1);
             tc_fence_after_sync();
             const uint32_t lane_addr = tmem_d + acc * BN + ((uint32_t)(ew * 32) << 16);
 #pragma unroll 1
-            for (int c0 = 0; c0 < BN; c0 += 16) {
+            for (int c0 = cfirst; c0 < BN; c0 += 32) {
                 uint32_t v[16];
                 tmem_ld16(lane_addr + c0, v);
                 const int4 m0 = mk0, m1 = mk1;
-                if (use_mask && c0 + 16 < p.N) { mk0 = ldg16(p.mask + om + c0 + 16); mk1 = ldg16(p.mask + om + c0 + 24); }
+                if (use_mask && c0 + 32 < p.N) { mk0 = ldg16(p.mask + om + c0 + 32); mk1 = ldg16(p.mask + om + c0 + 40); }
                 tmem_ld_wait();
                 if (!valid || c0 >= p.N) continue;
                 float f[16];
@@ -576,7 +595,7 @@ __global__ void __launch_bounds__(288, 1) tc_conv_win(const WinParams p, int tot
 // generation, zero-fills out-of-range rows and signals the stage's mbarrier with complete_tx.  Warp 0 = TMA
 // producer, warp 1 = TMEM allocator + MMA issuer, warps 2-5 = epilogue over double-buffered accumulators.
 template <int BN, int STAGES>
-__global__ void __launch_bounds__(192, 1) tc_gemm_tma(const __grid_constant__ CUtensorMap tmA,
+__global__ void __launch_bounds__(320, 1) tc_gemm_tma(const __grid_constant__ CUtensorMap tmA,
                                                       const __grid_constant__ CUtensorMap tmB,
                                                       const KGemmParams p, int total_tiles, int ntiles_n) {
     constexpr int A_BYTES = 128 * 128;
@@ -591,7 +610,7 @@ __global__ void __launch_bounds__(192, 1) tc_gemm_tma(const __grid_constant__ CU
     const int nch = p.nchunks;
     if (tid == 0) {
         for (int s = 0; s < STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
-        for (int a = 0; a < 2; ++a) { mbar_init(&tfull_bar[a], 1); mbar_init(&tempty_bar[a], 4); }
+        for (int a = 0; a < 2; ++a) { mbar_init(&tfull_bar[a], 1); mbar_init(&tempty_bar[a], 8); }
         fence_barrier_init();
         tma_prefetch_desc(&tmA);
         tma_prefetch_desc(&tmB);
@@ -640,7 +659,9 @@ __global__ void __launch_bounds__(192, 1) tc_gemm_tma(const __grid_constant__ CU
             }
         }
     } else {
+        // warps 2-9: two per TMEM lane quadrant, splitting the 16-column groups even/odd
         const int ew = warp & 3;
+        const int half = (warp - 2) >> 2;
         const int lrow = ew * 32 + (tid & 31);
         uint32_t t = 0;
         for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++t) {
@@ -650,18 +671,19 @@ __global__ void __launch_bounds__(192, 1) tc_gemm_tma(const __grid_constant__ CU
             const bool rvalid = r < (int)p.M;
             const int64_t ooff = (int64_t)r * p.ldo;
             const bool use_mask = p.mask != nullptr && rvalid;
+            const int cfirst = half * 16;
             int4 mk0 = make_int4(0, 0, 0, 0), mk1 = make_int4(0, 0, 0, 0);
-            if (use_mask && n0 < p.N) { mk0 = ldg16(p.mask + ooff + n0); mk1 = ldg16(p.mask + ooff + n0 + 8); }
+            if (use_mask && n0 + cfirst < p.N) { mk0 = ldg16(p.mask + ooff + n0 + cfirst); mk1 = ldg16(p.mask + ooff + n0 + cfirst + 8); }
             mbar_wait(&tfull_bar[acc], (t >> 1) & 1);
             tc_fence_after_sync();
             const uint32_t lane_addr = tmem_d + acc * BN + ((uint32_t)(ew * 32) << 16);
 #pragma unroll 1
-            for (int c0 = 0; c0 < BN; c0 += 16) {
+            for (int c0 = cfirst; c0 < BN; c0 += 32) {
                 uint32_t v[16];
                 tmem_ld16(lane_addr + c0, v);
                 const int4 m0 = mk0, m1 = mk1;
-                if (use_mask && c0 + 16 < BN && n0 + c0 + 16 < p.N) {
-                    mk0 = ldg16(p.mask + ooff + n0 + c0 + 16); mk1 = ldg16(p.mask + ooff + n0 + c0 + 24);
+                if (use_mask && c0 + 32 < BN && n0 + c0 + 32 < p.N) {
+                    mk0 = ldg16(p.mask + ooff + n0 + c0 + 32); mk1 = ldg16(p.mask + ooff + n0 + c0 + 40);
                 }
                 tmem_ld_wait();
                 const int col = n0 + c0;
@@ -871,7 +893,7 @@ static int launch_gemm_tma(const KGemmParams& p, cudaStream_t s, const char* wha
     const int total = (int)ceil_div(p.M, 128) * ntn;
     int grid = num_sms();
     if (grid > total) grid = total;
-    tc_gemm_tma<BN, STAGES><<<grid, 192, smem, s>>>(tmA, tmB, p, total, ntn);
+    tc_gemm_tma<BN, STAGES><<<grid, 320, smem, s>>>(tmA, tmB, p, total, ntn);
     return check_launch(what);
 }
 
@@ -887,7 +909,13 @@ static int launch_conv_win(const WinParams& p, cudaStream_t s, const char* what)
     const int total = (int)ceil_div(p.M, 128);
     int grid = num_sms();
     if (grid > total) grid = total;
-    tc_conv_win<BN, CPR, STAGES><<<grid, 288, smem, s>>>(p, total);
+    CUtensorMap tmA;
+    memset(&tmA, 0, sizeof(tmA));
+    if (!p.rows) {     // contiguous rows: the window is a TMA box [WR rows x 64 channels] per column chunk
+        int rc = make_tmap_2d(&tmA, p.A, p.M, (int64_t)CPR * 64, p.WR, what);
+        if (rc) return rc;
+    }
+    tc_conv_win<BN, CPR, STAGES><<<grid, 416, smem, s>>>(tmA, p, total);
     return check_launch(what);
 }
 
@@ -1089,7 +1117,8 @@ struct WGradWinParams {
     float* wsb;              // [gridDim.x][64] bias-gradient partials: sum_r dY[r, co] (an extra all-ones X tile)
 };
 
-__global__ void __launch_bounds__(160, 1) tc_wgrad_win(const WGradWinParams p) {
+__global__ void __launch_bounds__(160, 1) tc_wgrad_win(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmY,
+                                                       const WGradWinParams p, int use_tma) {
     constexpr int R = 128, STAGES = 3, LOOKAHEAD = 1, NY = 64;
     extern __shared__ uint8_t smem_raw[];
     __shared__ uint64_t full_bar[STAGES], empty_bar[STAGES], done_bar;
@@ -1108,9 +1137,10 @@ __global__ void __launch_bounds__(160, 1) tc_wgrad_win(const WGradWinParams p) {
     for (int i = tid; i < 4096 / 4; i += blockDim.x) reinterpret_cast<uint32_t*>(sOnes)[i] = 0x3F803F80u;
     fence_proxy_async_smem();
     if (tid == 0) {
-        for (int s = 0; s < STAGES; ++s) { mbar_init(&full_bar[s], 4); mbar_init(&empty_bar[s], 1); }
+        for (int s = 0; s < STAGES; ++s) { mbar_init(&full_bar[s], use_tma ? 1 : 4); mbar_init(&empty_bar[s], 1); }
         mbar_init(&done_bar, 1);
         fence_barrier_init();
+        if (use_tma) { tma_prefetch_desc(&tmX); tma_prefetch_desc(&tmY); }
     }
     if (warp == 4) tmem_alloc(&tmem_base_smem, tmem_cols);
     tc_fence_before_sync();
@@ -1122,7 +1152,20 @@ __global__ void __launch_bounds__(160, 1) tc_wgrad_win(const WGradWinParams p) {
     if (m_end > p.M) m_end = p.M;
     const int nsteps = m_end > m_begin ? (int)((m_end - m_begin + R - 1) / R) : 0;
 
-    if (warp < 4) {
+    if (warp < 4 && use_tma) {
+        // contiguous rows: X window = one TMA box per column chunk, dY = one box of 128 rows
+        if (tid == 0) {
+            for (int it = 0; it < nsteps; ++it) {
+                const int s = it % STAGES;
+                if (it >= STAGES) mbar_wait(&empty_bar[s], ((it / STAGES) - 1) & 1);
+                const uint32_t dst = smem_u32(smem + (size_t)s * stage_bytes);
+                const int m0 = (int)(m_begin + (int64_t)it * R);
+                mbar_arrive_expect_tx(&full_bar[s], (uint32_t)stage_bytes);
+                for (int c = 0; c < p.cpr; ++c) tma_load_2d(dst + c * IMGX, &tmX, c * 64, m0, &full_bar[s]);
+                tma_load_2d(dst + XBYTES, &tmY, 0, m0, &full_bar[s]);
+            }
+        }
+    } else if (warp < 4) {
         const int ppr = p.cpr * 8;               // 16-byte pieces per X row
         const int rstep = 128 / ppr;
         const int wr0 = tid / ppr, pc = tid % ppr;
@@ -1689,7 +1732,16 @@ static int launch_wgrad_win(const WGradWinParams& p, int ctas, cudaStream_t s, c
         if (e != cudaSuccess) return fail(B200RL_ERR_CUDA, "%s: smem attribute (%zu B): %s", what, smem, cudaGetErrorString(e));
         attr = smem;
     }
-    tc_wgrad_win<<<ctas, 160, smem, s>>>(p);
+    CUtensorMap tmX, tmY;
+    memset(&tmX, 0, sizeof(tmX)); memset(&tmY, 0, sizeof(tmY));
+    // TMA when rows are contiguous, dY rows are exactly 128 bytes and every CTA owns whole 128-row steps
+    const int use_tma = (!p.rows && p.ldy == 64 && p.ncolsY == 64 && p.rows_per_cta % 128 == 0) ? 1 : 0;
+    if (use_tma) {
+        int rc;
+        if ((rc = make_tmap_2d(&tmX, p.X, p.M, (int64_t)p.cpr * 64, p.WRX, what))) return rc;
+        if ((rc = make_tmap_2d(&tmY, p.Y, p.M, 64, 128, what))) return rc;
+    }
+    tc_wgrad_win<<<ctas, 160, smem, s>>>(tmX, tmY, p, use_tma);
     return check_launch(what);
 }
 
