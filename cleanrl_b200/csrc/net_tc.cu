@@ -517,17 +517,26 @@ __global__ void __launch_bounds__(416, 1) tc_conv_win(const __grid_constant__ CU
             // accumulator), so their global-memory latency overlaps the MMAs / the previous group's stores
             const bool use_mask = p.mask != nullptr && valid;
             const int cfirst = half * 16;
-            int4 mk0 = make_int4(0, 0, 0, 0), mk1 = make_int4(0, 0, 0, 0);
-            if (use_mask && cfirst < p.N) { mk0 = ldg16(p.mask + om + cfirst); mk1 = ldg16(p.mask + om + cfirst + 8); }
+            // all ReLU-mask words of this thread's column groups are requested BEFORE waiting for the accumulator:
+            // their global-memory latency (~1-2 us under load) overlaps the tile's MMAs
+            constexpr int NG = (BN + 31) / 32;
+            int4 mk[2 * NG];
+#pragma unroll
+            for (int g = 0; g < NG; ++g) {
+                const int c = cfirst + 32 * g;
+                if (use_mask && c < p.N) { mk[2 * g] = ldg16(p.mask + om + c); mk[2 * g + 1] = ldg16(p.mask + om + c + 8); }
+                else { mk[2 * g] = make_int4(0, 0, 0, 0); mk[2 * g + 1] = make_int4(0, 0, 0, 0); }
+            }
             mbar_wait(&tfull_bar[acc], (q >> 1) & 1);
             tc_fence_after_sync();
             const uint32_t lane_addr = tmem_d + acc * BN + ((uint32_t)(ew * 32) << 16);
-#pragma unroll 1
-            for (int c0 = cfirst; c0 < BN; c0 += 32) {
+#pragma unroll
+            for (int g = 0; g < NG; ++g) {
+                const int c0 = cfirst + 32 * g;
+                if (c0 >= BN) break;
                 uint32_t v[16];
                 tmem_ld16(lane_addr + c0, v);
-                const int4 m0 = mk0, m1 = mk1;
-                if (use_mask && c0 + 32 < p.N) { mk0 = ldg16(p.mask + om + c0 + 32); mk1 = ldg16(p.mask + om + c0 + 40); }
+                const int4 m0 = mk[2 * g], m1 = mk[2 * g + 1];
                 tmem_ld_wait();
                 if (!valid || c0 >= p.N) continue;
                 float f[16];
@@ -672,19 +681,24 @@ __global__ void __launch_bounds__(320, 1) tc_gemm_tma(const __grid_constant__ CU
             const int64_t ooff = (int64_t)r * p.ldo;
             const bool use_mask = p.mask != nullptr && rvalid;
             const int cfirst = half * 16;
-            int4 mk0 = make_int4(0, 0, 0, 0), mk1 = make_int4(0, 0, 0, 0);
-            if (use_mask && n0 + cfirst < p.N) { mk0 = ldg16(p.mask + ooff + n0 + cfirst); mk1 = ldg16(p.mask + ooff + n0 + cfirst + 8); }
+            constexpr int NG = (BN + 31) / 32;
+            int4 mk[2 * NG];
+#pragma unroll
+            for (int g = 0; g < NG; ++g) {
+                const int c = n0 + cfirst + 32 * g;
+                if (use_mask && c < p.N) { mk[2 * g] = ldg16(p.mask + ooff + c); mk[2 * g + 1] = ldg16(p.mask + ooff + c + 8); }
+                else { mk[2 * g] = make_int4(0, 0, 0, 0); mk[2 * g + 1] = make_int4(0, 0, 0, 0); }
+            }
             mbar_wait(&tfull_bar[acc], (t >> 1) & 1);
             tc_fence_after_sync();
             const uint32_t lane_addr = tmem_d + acc * BN + ((uint32_t)(ew * 32) << 16);
-#pragma unroll 1
-            for (int c0 = cfirst; c0 < BN; c0 += 32) {
+#pragma unroll
+            for (int g = 0; g < NG; ++g) {
+                const int c0 = cfirst + 32 * g;
+                if (c0 >= BN) break;
                 uint32_t v[16];
                 tmem_ld16(lane_addr + c0, v);
-                const int4 m0 = mk0, m1 = mk1;
-                if (use_mask && c0 + 32 < BN && n0 + c0 + 32 < p.N) {
-                    mk0 = ldg16(p.mask + ooff + n0 + c0 + 32); mk1 = ldg16(p.mask + ooff + n0 + c0 + 40);
-                }
+                const int4 m0 = mk[2 * g], m1 = mk[2 * g + 1];
                 tmem_ld_wait();
                 const int col = n0 + c0;
                 if (!rvalid || col >= p.N) continue;
