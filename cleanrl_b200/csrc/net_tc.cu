@@ -17,14 +17,16 @@
 // Kernels
 //   tc_conv_win<BN,CPR,STAGES>   stride-1 "window" convolution (conv1/2/3 forward, conv3/conv2 data-gradient):
 //       GEMM rows enumerate grid positions, so tap (dy,dx) of row r is row r + dy*Wp + dx.  A persistent CTA
-//       stages ONE window of 128+maxshift rows per tile with cp.async and every tap is a UMMA descriptor whose
-//       start address is shifted by whole 128-byte rows (legal for SWIZZLE_128B: the pattern is a function of
-//       the smem address bits; tools/experiments/umma_shift_test.cu).  Weights stay resident in smem.
-//       Warps 0-3 produce, warp 4 issues tcgen05.mma, warps 5-8 drain double-buffered TMEM accumulators.
-//   tc_wgrad_win                 weight gradients: dW^T[(tap,c), co] = sum_r X[r+shift_tap, c] * dY[r, co]; the same
-//       row images are read as MN-major operands (rows = reduction index), taps again by row shifts.
-//   tc_gemm_ws<BN,STAGES,WRES>   fc forward / data-gradient: row-major A, weights streamed through the ring.
-//   tc_wgrad_ws                  fc weight gradient (MN-major views of dhid / act3 rows).
+//       stages ONE window of 128+maxshift rows per tile -- by TMA (cp.async.bulk.tensor box) when rows are
+//       contiguous, by 4 cp.async producer warps when conv1 gathers frames through mb_inds -- and every tap is a
+//       UMMA descriptor whose start address is shifted by whole 128-byte rows (legal for SWIZZLE_128B: the pattern
+//       is a function of the smem address bits; tools/experiments/umma_shift_test.cu).  Weights stay resident in
+//       smem.  Warp 4 issues tcgen05.mma; warps 5-12 (two per TMEM lane quadrant) drain double-buffered accumulators.
+//   tc_wgrad_win                 conv weight gradients: dW^T[(tap,c), co] = sum_r X[r+shift_tap, c] * dY[r, co]; the same
+//       row images are read as MN-major operands (rows = reduction index), taps again by row shifts; the bias
+//       gradient is one extra MMA per step against an all-ones operand.
+//   tc_gemm_tma<BN,STAGES>       fc forward / data-gradient: both operands are TMA boxes of row-major matrices.
+//   tc_wgrad_tma                 fc weight gradient (MN-major views of TMA-loaded dhid / act3 row boxes).
 //   tc_heads_*                   the A+1 head outputs in fp32 on CUDA cores.
 #include <cuda.h>            // CUtensorMap types only; the encoder is resolved at run time (no libcuda link)
 #include "common.cuh"
@@ -66,249 +68,6 @@ struct KGemmParams {
 };
 
 __device__ __forceinline__ int4 ldg16(const void* p) { return __ldg(reinterpret_cast<const int4*>(p)); }
-
-// ------------------------------------------------------------------ kernel 1b: persistent, warp-specialised
-// Same GEMM as tc_gemm_kmajor, restructured so that global-load latency never stalls the tensor core:
-//   * one persistent CTA per SM walks tiles blockIdx.x, +gridDim.x, ...;
-//   * ALL weight chunks of the layer stay resident in shared memory (<= 72 KB);
-//   * warps 0-3 (producers) stream the gathered A chunks with cp.async into a STAGES-deep ring and keep
-//     LOOKAHEAD chunks in flight per thread; a chunk is published on full[s] after cp.async.wait_group +
-//     fence.proxy.async;
-//   * warp 4 (one lane) issues tcgen05.mma; tcgen05.commit frees ring slots (empty[s]) and publishes the
-//     accumulator (tmem_full[a]);
-//   * warps 5-8 drain TMEM (double-buffered accumulators) -> bias/ReLU/mask -> bf16 NHWC, overlapping the
-//     next tile's MMAs.
-template <int BN, int STAGES, bool WRES>
-__global__ void __launch_bounds__(288, 1) tc_gemm_ws(const KGemmParams p, int total_tiles, int ntiles_n) {
-    constexpr int LOOKAHEAD = STAGES - 2;      // chunks in flight per producer thread
-    static_assert(LOOKAHEAD >= 1, "ring must be deeper than the cp.async lookahead");
-    constexpr int A_BYTES = 128 * 128;
-    constexpr int B_CHUNK = BN * 128;
-    constexpr uint32_t TMEM_COLS = (2 * BN) < 32 ? 32 : 2 * BN;
-    extern __shared__ uint8_t smem_raw[];
-    __shared__ uint64_t full_bar[STAGES], empty_bar[STAGES], tfull_bar[2], tempty_bar[2];
-    __shared__ uint32_t tmem_base_smem;
-    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-    const int tid = threadIdx.x, warp = tid >> 5;
-    const int nch = p.nchunks;
-    const int K = nch * 64;
-    // WRES: all weight chunks resident + ring of A chunks; otherwise every ring stage = A chunk + B chunk
-    constexpr int STAGE_BYTES = WRES ? A_BYTES : A_BYTES + B_CHUNK;
-    uint8_t* sW = smem;                                                        // [nclasses][nch][BN rows x 128 B]
-    uint8_t* sRing = smem + (WRES ? (size_t)p.nclasses * nch * B_CHUNK : 0);   // STAGES x STAGE_BYTES
-
-    if (tid == 0) {
-        // one arrival per producer / epilogue WARP (lane 0 after __syncwarp), not per thread
-        for (int s = 0; s < STAGES; ++s) { mbar_init(&full_bar[s], 4); mbar_init(&empty_bar[s], 1); }
-        for (int a = 0; a < 2; ++a) { mbar_init(&tfull_bar[a], 1); mbar_init(&tempty_bar[a], 4); }
-        fence_barrier_init();
-    }
-    if (warp == 4) tmem_alloc(&tmem_base_smem, TMEM_COLS);
-    // resident weights (generic-proxy stores, made visible to the async proxy once)
-    for (int idx = tid; WRES && idx < p.nclasses * nch * BN * 8; idx += blockDim.x) {
-        const int c16 = idx & 7;
-        int t = idx >> 3;
-        const int r = t % BN; t /= BN;
-        const int j = t % nch; const int cls = t / nch;
-        int4 v = make_int4(0, 0, 0, 0);
-        if (r < p.N) v = ldg16(p.Bw + (int64_t)cls * p.b_class_stride + (int64_t)r * K + j * 64 + c16 * 8);
-        *reinterpret_cast<int4*>(sW + ((size_t)cls * nch + j) * B_CHUNK + img_off(r, c16)) = v;
-    }
-    fence_proxy_async_smem();
-    tc_fence_before_sync();
-    __syncthreads();
-    tc_fence_after_sync();
-    const uint32_t tmem_d = tmem_base_smem;
-    const int ppc = 64 / p.CP;
-
-    if (warp < 4) {
-        // ======================= producers =======================
-        const int c16 = tid & 7;
-        uint32_t q = 0;          // flat chunk counter of this CTA
-        for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-            const int mt = tile / ntiles_n, n0 = (tile - mt * ntiles_n) * BN;
-            const int cls = mt / p.tiles_per_class;
-            const int row0 = (mt - cls * p.tiles_per_class) * 128;
-            (void)cls; (void)n0;
-            int64_t boff[8];
-            int pos[8];
-#pragma unroll
-            for (int ps = 0; ps < 8; ++ps) {
-                const int r = row0 + ps * 16 + (tid >> 3);
-                if (r < (int)p.M) {
-                    const int i = r / p.rpi;
-                    const int rem = r - i * p.rpi;
-                    const int y = rem / p.Ws, x = rem - y * p.Ws;
-                    const int ys = y * p.sy, xs = x * p.sx;
-                    const int64_t img = p.rows ? __ldg(p.rows + i) : (int64_t)i;
-                    boff[ps] = ((img * p.SH + ys) * p.SW + xs) * (int64_t)p.CP;
-                    pos[ps] = (ys << 16) | xs;
-                } else {
-                    boff[ps] = 0;
-                    pos[ps] = -1;
-                }
-            }
-            for (int j = 0; j < nch; ++j, ++q) {
-                const uint32_t s = q % STAGES;
-                if (q >= (uint32_t)STAGES) mbar_wait(&empty_bar[s], ((q / STAGES) - 1) & 1);
-                const uint32_t sA = smem_u32(sRing + (size_t)s * STAGE_BYTES);
-                const int dyj = p.dy[j], dxj = p.dx[j];
-                const int64_t doff = ((int64_t)dyj * p.SW + dxj) * p.CP + c16 * 8;
-#pragma unroll
-                for (int ps = 0; ps < 8; ++ps) {
-                    bool ok = pos[ps] >= 0;
-                    if (ok && p.check) {
-                        const int yy = (pos[ps] >> 16) + dyj, xx = (pos[ps] & 0xFFFF) + dxj;
-                        ok = (yy >= 0) && (yy < p.SH) && (xx >= 0) && (xx + ppc <= p.SW);
-                    }
-                    const bf16* src = reinterpret_cast<const bf16*>(p.A) + (ok ? boff[ps] + doff : 0);
-                    cp_async16(sA + img_off(ps * 16 + (tid >> 3), c16), src, ok ? 16u : 0u);
-                }
-                if (!WRES) {
-#pragma unroll
-                    for (int ps = 0; ps < BN / 16; ++ps) {
-                        const int r = ps * 16 + (tid >> 3);
-                        const bool ok = n0 + r < p.N;
-                        const bf16* src = p.Bw + (ok ? (int64_t)(n0 + r) * K + j * 64 + c16 * 8 : 0);
-                        cp_async16(sA + A_BYTES + img_off(r, c16), src, ok ? 16u : 0u);
-                    }
-                }
-                cp_async_commit();
-                if (q >= (uint32_t)LOOKAHEAD) {
-                    cp_async_wait<LOOKAHEAD>();
-                    fence_proxy_async_smem();
-                    __syncwarp();
-                    if ((tid & 31) == 0) mbar_arrive(&full_bar[(q - LOOKAHEAD) % STAGES]);
-                }
-            }
-        }
-        // drain the last LOOKAHEAD chunks
-        cp_async_wait<0>();
-        fence_proxy_async_smem();
-        __syncwarp();
-        if ((tid & 31) == 0)
-            for (uint32_t d = (q >= (uint32_t)LOOKAHEAD ? q - LOOKAHEAD : 0); d < q; ++d) mbar_arrive(&full_bar[d % STAGES]);
-    } else if (warp == 4) {
-        // ======================= MMA issuer =======================
-        if ((tid & 31) == 0) {
-            constexpr uint32_t idesc = make_idesc(128, BN, 0, 0);
-            uint32_t q = 0, t = 0;
-            for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++t) {
-                const int mt = tile / ntiles_n;
-                const int cls = mt / p.tiles_per_class;
-                const uint32_t acc = t & 1;
-                if (t >= 2) mbar_wait(&tempty_bar[acc], ((t >> 1) - 1) & 1);
-                tc_fence_after_sync();
-                const uint32_t d_addr = tmem_d + acc * BN;
-                for (int j = 0; j < nch; ++j, ++q) {
-                    const uint32_t s = q % STAGES;
-                    mbar_wait(&full_bar[s], (q / STAGES) & 1);
-                    tc_fence_after_sync();
-                    const uint32_t stage_addr = smem_u32(sRing + (size_t)s * STAGE_BYTES);
-                    const uint64_t adesc = desc_kmajor(stage_addr);
-                    const uint64_t bdesc = WRES ? desc_kmajor(smem_u32(sW + ((size_t)cls * nch + j) * B_CHUNK))
-                                                : desc_kmajor(stage_addr + A_BYTES);
-#pragma unroll
-                    for (int kk = 0; kk < 4; ++kk)
-                        umma_bf16(d_addr, adesc + 2 * kk, bdesc + 2 * kk, idesc, (j | kk) != 0);
-                    umma_commit(&empty_bar[s]);
-                }
-                umma_commit(&tfull_bar[acc]);
-            }
-        }
-    } else {
-        // ======================= epilogue =======================
-        const int ew = warp & 3;                    // TMEM lane quadrant this warp may access
-        const int lrow = ew * 32 + (tid & 31);      // accumulator row handled by this thread
-        uint32_t t = 0;
-        for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++t) {
-            const int mt = tile / ntiles_n, n0 = (tile - mt * ntiles_n) * BN;
-            const int cls = mt / p.tiles_per_class;
-            const int row0 = (mt - cls * p.tiles_per_class) * 128;
-            const uint32_t acc = t & 1;
-            const int r = row0 + lrow;
-            const bool rvalid = r < (int)p.M;
-            int64_t ooff = 0;
-            if (rvalid) {
-                const int i = r / p.rpi;
-                const int rem = r - i * p.rpi;
-                const int y = rem / p.Ws, x = rem - y * p.Ws;
-                const int ooy = p.nclasses > 1 ? (cls >> 1) : 0, oox = p.nclasses > 1 ? (cls & 1) : 0;
-                ooff = (((int64_t)i * p.OH + y * p.osy + ooy) * p.OW + x * p.osx + oox) * (int64_t)p.ldo;
-            }
-            const bool use_mask = p.mask != nullptr && rvalid;
-            int4 mk0 = make_int4(0, 0, 0, 0), mk1 = make_int4(0, 0, 0, 0);
-            if (use_mask && n0 < p.N) { mk0 = ldg16(p.mask + ooff + n0); mk1 = ldg16(p.mask + ooff + n0 + 8); }
-            mbar_wait(&tfull_bar[acc], (t >> 1) & 1);
-            tc_fence_after_sync();
-            const uint32_t lane_addr = tmem_d + acc * BN + ((uint32_t)(ew * 32) << 16);
-#pragma unroll 1
-            for (int c0 = 0; c0 < BN; c0 += 16) {
-                uint32_t v[16];
-                tmem_ld16(lane_addr + c0, v);
-                const int4 m0 = mk0, m1 = mk1;
-                if (use_mask && c0 + 16 < BN && n0 + c0 + 16 < p.N) {
-                    mk0 = ldg16(p.mask + ooff + n0 + c0 + 16); mk1 = ldg16(p.mask + ooff + n0 + c0 + 24);
-                }
-                tmem_ld_wait();
-                const int col = n0 + c0;
-                if (!rvalid || col >= p.N) continue;
-                float f[16];
-                if (p.bias) {
-                    const float4* bp = reinterpret_cast<const float4*>(p.bias + col);
-#pragma unroll
-                    for (int e = 0; e < 4; ++e) {
-                        const float4 bv = __ldg(bp + e);
-                        f[4 * e] = fmaf(__uint_as_float(v[4 * e]), p.scale, bv.x);
-                        f[4 * e + 1] = fmaf(__uint_as_float(v[4 * e + 1]), p.scale, bv.y);
-                        f[4 * e + 2] = fmaf(__uint_as_float(v[4 * e + 2]), p.scale, bv.z);
-                        f[4 * e + 3] = fmaf(__uint_as_float(v[4 * e + 3]), p.scale, bv.w);
-                    }
-                } else {
-#pragma unroll
-                    for (int e = 0; e < 16; ++e) f[e] = __uint_as_float(v[e]) * p.scale;
-                }
-                if (p.relu) {
-#pragma unroll
-                    for (int e = 0; e < 16; ++e) f[e] = fmaxf(f[e], 0.f);
-                }
-                if (p.mask) {
-                    const uint32_t mw[8] = {(uint32_t)m0.x, (uint32_t)m0.y, (uint32_t)m0.z, (uint32_t)m0.w,
-                                            (uint32_t)m1.x, (uint32_t)m1.y, (uint32_t)m1.z, (uint32_t)m1.w};
-#pragma unroll
-                    for (int e = 0; e < 8; ++e) {
-                        if ((mw[e] & 0x7FFFu) == 0u) f[2 * e] = 0.f;
-                        if ((mw[e] & 0x7FFF0000u) == 0u) f[2 * e + 1] = 0.f;
-                    }
-                }
-                int4 o0, o1;
-                o0.x = (int)pack_bf16x2(f[0], f[1]);   o0.y = (int)pack_bf16x2(f[2], f[3]);
-                o0.z = (int)pack_bf16x2(f[4], f[5]);   o0.w = (int)pack_bf16x2(f[6], f[7]);
-                o1.x = (int)pack_bf16x2(f[8], f[9]);   o1.y = (int)pack_bf16x2(f[10], f[11]);
-                o1.z = (int)pack_bf16x2(f[12], f[13]); o1.w = (int)pack_bf16x2(f[14], f[15]);
-                if (p.dual_dact3) {
-                    const int px = col >> 6, ch = col & 63;          // pixel (oy,ox) of the 7x7 map, channel
-                    const int oy = px / 7, ox = px - oy * 7;
-                    int4* da = reinterpret_cast<int4*>(p.out + ((int64_t)r * 81 + oy * 9 + ox) * 64 + ch);
-                    int4* db = reinterpret_cast<int4*>(p.out2 + ((int64_t)r * 121 + (oy + 2) * 11 + ox + 2) * 64 + ch);
-                    da[0] = o0; da[1] = o1;
-                    db[0] = o0; db[1] = o1;
-                } else {
-                    int4* dst = reinterpret_cast<int4*>(p.out + ooff + col);
-                    dst[0] = o0;
-                    dst[1] = o1;
-                }
-            }
-            tc_fence_before_sync();
-            __syncwarp();
-            if ((tid & 31) == 0) mbar_arrive(&tempty_bar[acc]);
-        }
-    }
-    tc_fence_before_sync();
-    __syncthreads();
-    if (warp == 4) tmem_dealloc(tmem_d, TMEM_COLS);
-}
-
 
 // ------------------------------------------------------------------ kernel 1c: "window" convolution
 // Stride-1 convolutions over activations stored as a LINEAR pixel grid [n*G rows, CPR*64 channels]
@@ -933,186 +692,6 @@ static int launch_conv_win(const WinParams& p, cudaStream_t s, const char* what)
     return check_launch(what);
 }
 
-template <int BN, int STAGES, bool WRES>
-static int launch_kgemm_ws(const KGemmParams& p, cudaStream_t s, const char* what) {
-    const size_t smem = (WRES ? (size_t)p.nclasses * p.nchunks * BN * 128 + (size_t)STAGES * 128 * 128
-                             : (size_t)STAGES * (128 * 128 + BN * 128)) + 1024;
-    static size_t attr = 0;
-    if (smem > attr) {
-        cudaError_t e = cudaFuncSetAttribute(tc_gemm_ws<BN, STAGES, WRES>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e != cudaSuccess) return fail(B200RL_ERR_CUDA, "%s: smem attribute (%zu B): %s", what, smem, cudaGetErrorString(e));
-        attr = smem;
-    }
-    const int ntn = WRES ? 1 : (int)ceil_div(p.N, BN);
-    const int total = p.tiles_per_class * p.nclasses * ntn;
-    int grid = num_sms();
-    if (grid > total) grid = total;
-    tc_gemm_ws<BN, STAGES, WRES><<<grid, 288, smem, s>>>(p, total, ntn);
-    return check_launch(what);
-}
-
-// ------------------------------------------------------------------ kernel 2: weight gradient
-// D[kidx, co] = sum_m X[m, kidx] * dY[m, co].  X-side: nxc chunk images (64 kidx each); Y-side: nyc chunk
-// images (64 co each).  Each CTA owns the row range [m_begin, m_end) and ALL (X-tile, Y) outputs:
-// TMEM columns = (nxc/2) * 64*nyc.  Partials are written fp32 to ws[split][nxc*64][nyc*64].
-struct WGradParams {
-    KGemmParams x;          // gather description of the X side (A/rows/M/rpi/Ws/SH/SW/CP/sy/sx/nchunks/check/dy/dx)
-    const bf16* Y;          // dY rows [M, ldy] bf16 (NHWC rows == GEMM rows)
-    int ldy;                // elements per dY row
-    int nyc;                // Y chunks (64 columns each)
-    int ncolsY;             // valid dY columns
-    int nxc;                // X chunks per CTA (even; blockIdx.y selects the group; zero-padded beyond x.nchunks)
-    int64_t rows_per_cta;   // multiple of 32
-    float* ws;              // [gridDim.x][gridDim.y*nxc*64][gridDim.z*nyc*64] fp32
-};
-
-// ------------------------------------------------------------------ kernel 2b: warp-specialised weight gradient
-// Same math as tc_wgrad; warps 0-3 stream the X/Y row images with cp.async (LOOKAHEAD steps in flight),
-// warp 4 issues the MMAs, and warps 0-3 write the fp32 partial tile at the end.
-__global__ void __launch_bounds__(160, 1) tc_wgrad_ws(const WGradParams p) {
-    constexpr int R = 32;
-    constexpr int STAGES = 4, LOOKAHEAD = 2;
-    extern __shared__ uint8_t smem_raw[];
-    __shared__ uint64_t full_bar[STAGES], empty_bar[STAGES], done_bar;
-    __shared__ uint32_t tmem_base_smem;
-    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-    const int tid = threadIdx.x, warp = tid >> 5;
-    const KGemmParams& g = p.x;
-    const int nxc = p.nxc, nyc = p.nyc;
-    const int NY = nyc * 64;
-    const int xc0 = blockIdx.y * nxc, yc0 = blockIdx.z * nyc;
-    const int xt = nxc / 2;
-    const int chunk_img = R * 128;
-    const int stage_bytes = (nxc + nyc) * chunk_img;
-    uint32_t tmem_cols = 32;
-    while ((int)tmem_cols < xt * NY) tmem_cols <<= 1;
-
-    if (tid == 0) {
-        for (int s = 0; s < STAGES; ++s) { mbar_init(&full_bar[s], 4); mbar_init(&empty_bar[s], 1); }
-        mbar_init(&done_bar, 1);
-        fence_barrier_init();
-    }
-    if (warp == 4) tmem_alloc(&tmem_base_smem, tmem_cols);
-    tc_fence_before_sync();
-    __syncthreads();
-    tc_fence_after_sync();
-    const uint32_t tmem_d = tmem_base_smem;
-
-    const int64_t m_begin = (int64_t)blockIdx.x * p.rows_per_cta;
-    int64_t m_end = m_begin + p.rows_per_cta;
-    if (m_end > g.M) m_end = g.M;
-    const int nsteps = m_end > m_begin ? (int)((m_end - m_begin + R - 1) / R) : 0;
-    const int ppc = 64 / g.CP;
-
-    if (warp < 4) {
-        const int c16 = tid & 7;
-        for (int it = 0; it < nsteps; ++it) {
-            const int s = it % STAGES;
-            if (it >= STAGES) mbar_wait(&empty_bar[s], ((it / STAGES) - 1) & 1);
-            const uint32_t sX = smem_u32(smem + (size_t)s * stage_bytes);
-            const uint32_t sY = sX + nxc * chunk_img;
-            const int64_t m0 = m_begin + (int64_t)it * R;
-#pragma unroll
-            for (int ps = 0; ps < R / 16; ++ps) {
-                const int rr = ps * 16 + (tid >> 3);
-                const int64_t r = m0 + rr;
-                const bool rok = r < m_end;
-                int64_t bo = 0;
-                int ys = 0, xs = 0;
-                if (rok) {
-                    const int ri = (int)r;
-                    const int i = ri / g.rpi;
-                    const int rem = ri - i * g.rpi;
-                    const int y = rem / g.Ws, x = rem - y * g.Ws;
-                    ys = y * g.sy; xs = x * g.sx;
-                    const int64_t img = g.rows ? __ldg(g.rows + i) : (int64_t)i;
-                    bo = ((img * g.SH + ys) * g.SW + xs) * (int64_t)g.CP;
-                }
-                const uint32_t roff = img_off(rr, c16);
-                for (int c = 0; c < nxc; ++c) {
-                    const int ch = xc0 + c;
-                    bool ok = rok && ch < g.nchunks;
-                    int64_t off = 0;
-                    if (ok) {
-                        const int dyj = g.dy[ch], dxj = g.dx[ch];
-                        if (g.check) {
-                            const int yy = ys + dyj, xx = xs + dxj;
-                            ok = (yy >= 0) && (yy < g.SH) && (xx >= 0) && (xx + ppc <= g.SW);
-                        }
-                        off = bo + ((int64_t)dyj * g.SW + dxj) * g.CP + c16 * 8;
-                    }
-                    cp_async16(sX + c * chunk_img + roff, reinterpret_cast<const bf16*>(g.A) + (ok ? off : 0), ok ? 16u : 0u);
-                }
-                for (int c = 0; c < nyc; ++c) {
-                    const int col = (yc0 + c) * 64 + c16 * 8;
-                    const bool ok = rok && col < p.ncolsY;
-                    cp_async16(sY + c * chunk_img + roff, p.Y + (ok ? r * (int64_t)p.ldy + col : 0), ok ? 16u : 0u);
-                }
-            }
-            cp_async_commit();
-            if (it >= LOOKAHEAD) {
-                cp_async_wait<LOOKAHEAD>();
-                fence_proxy_async_smem();
-                __syncwarp();
-                if ((tid & 31) == 0) mbar_arrive(&full_bar[(it - LOOKAHEAD) % STAGES]);
-            }
-        }
-        cp_async_wait<0>();
-        fence_proxy_async_smem();
-        __syncwarp();
-        if ((tid & 31) == 0)
-            for (int d = (nsteps >= LOOKAHEAD ? nsteps - LOOKAHEAD : 0); d < nsteps; ++d) mbar_arrive(&full_bar[d % STAGES]);
-    } else if ((tid & 31) == 0) {
-        const uint32_t idesc = make_idesc(128, NY, 1, 1);
-        for (int it = 0; it < nsteps; ++it) {
-            const int s = it % STAGES;
-            mbar_wait(&full_bar[s], (it / STAGES) & 1);
-            tc_fence_after_sync();
-            const uint32_t xa = smem_u32(smem + (size_t)s * stage_bytes), ya = xa + nxc * chunk_img;
-            for (int t = 0; t < xt; ++t) {
-#pragma unroll
-                for (int kk = 0; kk < R / 16; ++kk) {
-                    const uint64_t adesc = desc_mnmajor(xa + (2 * t) * chunk_img + kk * 2048, chunk_img);
-                    const uint64_t bdesc = desc_mnmajor(ya + kk * 2048, chunk_img);
-                    umma_bf16(tmem_d + t * NY, adesc, bdesc, idesc, (it | kk) != 0);
-                }
-            }
-            umma_commit(&empty_bar[s]);
-        }
-        umma_commit(&done_bar);
-    }
-    if (warp < 4) {
-        // ---- epilogue: fp32 partials ws[cta][kidx][co]
-        if (nsteps > 0) {
-            mbar_wait(&done_bar, 0);
-            tc_fence_after_sync();
-        }
-        const int64_t KXtot = (int64_t)gridDim.y * nxc * 64, NYtot = (int64_t)gridDim.z * NY;
-        float* wsb = p.ws + (int64_t)blockIdx.x * KXtot * NYtot;
-        const uint32_t lane_addr = tmem_d + ((uint32_t)(warp * 32) << 16);
-        for (int t = 0; t < xt; ++t) {
-            float* dst = wsb + ((int64_t)xc0 * 64 + t * 128 + tid) * NYtot + (int64_t)yc0 * 64;
-            for (int c0 = 0; c0 < NY; c0 += 16) {
-                uint32_t v[16];
-                if (nsteps > 0) {
-                    tmem_ld16(lane_addr + t * NY + c0, v);
-                    tmem_ld_wait();
-                } else {
-#pragma unroll
-                    for (int e = 0; e < 16; ++e) v[e] = 0u;
-                }
-#pragma unroll
-                for (int e = 0; e < 16; e += 4)
-                    *reinterpret_cast<float4*>(dst + c0 + e) = make_float4(__uint_as_float(v[e]), __uint_as_float(v[e + 1]),
-                                                                             __uint_as_float(v[e + 2]), __uint_as_float(v[e + 3]));
-            }
-        }
-    }
-    tc_fence_before_sync();
-    __syncthreads();
-    if (warp == 4) tmem_dealloc(tmem_d, tmem_cols);
-}
-
 // ------------------------------------------------------------------ kernel 2c: window weight gradient
 // dW^T[(tap,channel), co] = sum over grid rows r of X[r + shift_tap, channel] * dY[r, co] with X and dY on the
 // SAME linear grid (dY is zero at positions that are not valid outputs).  Per step of 128 rows the CTA
@@ -1726,18 +1305,6 @@ static WPlan wgrad_plan(int64_t M, int target_ctas, int quantum = 32) {
 }
 static const int kC1Ctas = 296, kC2Ctas = 148, kC3Ctas = 148, kFcSplits = 8;
 
-static int launch_wgrad(const WGradParams& p, dim3 grid, cudaStream_t s, const char* what) {
-    const size_t smem = (size_t)4 * (p.nxc + p.nyc) * 32 * 128 + 1024;
-    static size_t attr = 0;
-    if (smem > attr) {
-        cudaError_t e = cudaFuncSetAttribute(tc_wgrad_ws, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e != cudaSuccess) return fail(B200RL_ERR_CUDA, "%s: smem attribute (%zu B): %s", what, smem, cudaGetErrorString(e));
-        attr = smem;
-    }
-    tc_wgrad_ws<<<grid, 160, smem, s>>>(p);
-    return check_launch(what);
-}
-
 static int launch_wgrad_win(const WGradWinParams& p, int ctas, cudaStream_t s, const char* what) {
     const size_t smem = (size_t)3 * ((size_t)p.WRX * 128 * p.cpr + 128 * 128) + 4096 + 1024;
     static size_t attr = 0;
@@ -1925,15 +1492,10 @@ extern "C" int b200rl_naturecnn_bf16_backward(const void* obs, int obs_format, c
         tc_heads_bwd_data<<<db_blocks, 256, 0, s>>>(dhead, params + L.hw, act + Q.hid, n, A1, 512, act + Q.dhid);
         if ((rc = check_launch("naturecnn/heads_bwd", 3))) return rc;
     }
-    WGradParams w;
     KGemmParams p;
     // ---- fc: dW[o][c*49+p] = sum_m dhid[m][o] * act3[m][p*64+c]
     {
-        memset(&w, 0, sizeof(w));
-        gemm_defaults(w.x); rowmajor_gather(w.x, act + Q.dhid, n, 8);
-        w.Y = act + Q.act3; w.ldy = 3136; w.nyc = 4; w.ncolsY = 3136; w.nxc = 2;
         const WPlan pl = wgrad_plan(n, kFcSplits, 64);
-        w.rows_per_cta = pl.rows_per_cta; w.ws = wsbig;
         { ProfScope ps(s, "fc_wgrad", 2.0 * n * 512 * 3136, (double)n * (3136 + 512) * 2 + 512.0 * 3136 * 4);
           CUtensorMap tmX, tmY;
           if ((rc = make_tmap_2d(&tmX, act + Q.dhid, n, 512, 64, "naturecnn/fc_wgrad"))) return rc;
