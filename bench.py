@@ -275,7 +275,14 @@ def run_ours(opt):
     prof = sorted(res["prof"], key=lambda r: -r["ms"])
     tot_ms = sum(r["ms"] for r in prof) or 1.0
     top = next((r for r in prof if r["flops"] > 0), prof[0])
-    ach = top["flops"] / (top["ms"] * 1e-3) / 1e12 if top["ms"] > 0 else 0.0
+    # which roof bounds the dominant kernel: its arithmetic intensity (algorithmic flops / algorithmic bytes)
+    # against the ridge of the measured peaks
+    ridge = peak_tf * 1e12 / (peak_hbm * 1e9)
+    intensity = top["flops"] / top["bytes"] if top["bytes"] > 0 else float("inf")
+    hbm_bound = top["flops"] == 0 or intensity < ridge
+    secs = top["ms"] * 1e-3
+    ach_tf = top["flops"] / secs / 1e12 if secs > 0 else 0.0
+    ach_gb = top["bytes"] / secs / 1e9 if secs > 0 else 0.0
     traffic = None
     tp = ROOT / "profiles" / "r1_traffic.json"
     if tp.exists():
@@ -284,15 +291,21 @@ def run_ours(opt):
             traffic = {"dram_bytes_per_launch": tr["dram_bytes"], "algorithmic_bytes_per_launch": tr["algorithmic_bytes"],
                        "at_n": tr["n"], "from": "profiles/r1_traffic.json (ncu --set full)"}
     roofline = {
-        "bound": "tensor", "kernel": top["name"], "achieved": round(ach, 2), "peak": peak_tf, "unit": "TFLOP/s",
-        "frac": round(ach / peak_tf, 4), "traffic": traffic, "peak_source": f"{which} bf16_tflops_sustained",
+        "bound": "hbm" if hbm_bound else "tensor", "kernel": top["name"],
+        "achieved": round(ach_gb if hbm_bound else ach_tf, 2), "peak": peak_hbm if hbm_bound else peak_tf,
+        "unit": "GB/s" if hbm_bound else "TFLOP/s",
+        "frac": round(ach_gb / peak_hbm if hbm_bound else ach_tf / peak_tf, 4), "traffic": traffic,
+        "peak_source": f"{which} " + ("hbm_gbps" if hbm_bound else "bf16_tflops_sustained"),
+        "arithmetic_intensity_flop_per_byte": round(intensity, 1), "ridge_flop_per_byte": round(ridge, 1),
+        "achieved_tflops": round(ach_tf, 2), "achieved_gbs": round(ach_gb, 1),
         "share_of_kernel_time": round(top["ms"] / tot_ms, 4), "launches": top["launches"],
         "avg_launch_us": round(1e3 * top["ms"] / max(top["launches"], 1), 2),
         "job_tensor_frac": round(sps / world * FLOP_PER_ENV_STEP / (peak_tf * 1e12), 4),
         "job_hbm_frac": round(sps / world * HBM_BYTES_PER_ENV_STEP / (peak_hbm * 1e9), 4),
         "kernels": [{"name": r["name"], "ms_per_step": round(r["ms"] / K, 4), "launches_per_step": r["launches"] // K,
                      "tflops": round(r["flops"] / (r["ms"] * 1e-3) / 1e12, 2) if r["ms"] > 0 and r["flops"] > 0 else None,
-                     "gbs": round(r["bytes"] / (r["ms"] * 1e-3) / 1e9, 1) if r["ms"] > 0 and r["bytes"] > 0 else None}
+                     "gbs": round(r["bytes"] / (r["ms"] * 1e-3) / 1e9, 1) if r["ms"] > 0 and r["bytes"] > 0 else None,
+                     "hbm_frac": round(r["bytes"] / (r["ms"] * 1e-3) / 1e9 / peak_hbm, 3) if r["ms"] > 0 and r["bytes"] > 0 else None}
                     for r in prof],
     }
     out = {

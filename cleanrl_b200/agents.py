@@ -33,6 +33,7 @@ def _exp_noise(n, A, device):
 
 
 _exp_noise.graph_safe = True      # device-generator draw: capturable in a CUDA graph
+_exp_noise.inplace = lambda buf: buf.exponential_(1)     # same generator consumption as the out-of-place draw
 
 
 class KernelAgent(nn.Module):
@@ -86,11 +87,22 @@ class KernelAgent(nn.Module):
         return getattr(self.noise_fn, "graph_safe", False) and (getattr(self, "precision", "bf16") == "bf16" or
                                                                 not hasattr(self, "network"))
 
-    def sample_into(self, obs, actions_out, logprobs_out, values_out):
-        """Rollout step: forward + sample, writing straight into the rollout slots (ppo.py:197-202)."""
+    def noise_shape(self, n):
+        return (n, self.num_actions)
+
+    def draw_noise_into(self, buf):
+        """Fill ``buf`` [n, A] with this step's sampling noise (one draw for the whole env batch)."""
+        if hasattr(self.noise_fn, "inplace"):
+            self.noise_fn.inplace(buf)
+        else:
+            buf.copy_(self.noise_fn(buf.shape[0], buf.shape[1], buf.device))
+
+    def sample_into(self, obs, actions_out, logprobs_out, values_out, noise=None):
+        """Rollout step: forward + sample, writing straight into the rollout slots (ppo.py:197-202).
+        ``noise``: pre-drawn rows of the step's noise tensor (chunked H2D/compute pipeline)."""
         logits, value = self._forward_heads(obs)
         n, A = logits.shape
-        q = self.noise_fn(n, A, logits.device)
+        q = noise if noise is not None else self.noise_fn(n, A, logits.device)
         ops.categorical_sample(logits, q, value, out=(actions_out, logprobs_out, None, values_out))
 
     def loss_backward(self, policy_out, value, mb_inds, b, a, stats_row, scratch):
@@ -272,6 +284,7 @@ def _normal_noise(n, D, device):
 
 
 _normal_noise.graph_safe = True
+_normal_noise.inplace = lambda buf: buf.normal_(0, 1)
 
 
 class ContinuousMLPAgent(KernelAgent):
@@ -308,10 +321,13 @@ class ContinuousMLPAgent(KernelAgent):
     def _logstd(self):
         return self.actor_logstd.data.view(-1)
 
-    def sample_into(self, obs, actions_out, logprobs_out, values_out):
+    def noise_shape(self, n):
+        return (n, self.action_dim)
+
+    def sample_into(self, obs, actions_out, logprobs_out, values_out, noise=None):
         mean, value = self._forward_heads(obs)
         n, D = mean.shape
-        eps = self.noise_fn(n, D, mean.device)
+        eps = noise if noise is not None else self.noise_fn(n, D, mean.device)
         ops.gaussian_sample(mean, self._logstd(), eps, value, out=(actions_out, logprobs_out, None, values_out))
 
     def loss_backward(self, policy_out, value, mb_inds, b, a, stats_row, scratch):

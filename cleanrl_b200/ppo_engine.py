@@ -109,9 +109,18 @@ class PPOEngine:
         if cuda_graphs is None:
             cuda_graphs = os.environ.get("CLEANRL_B200_CUDA_GRAPHS", "1") != "0"
         self.cuda_graphs = bool(cuda_graphs) and device.type == "cuda"
+        # e2e pipeline: the pinned batch goes up in H2D_CHUNKS pieces on a copy stream while the compute stream
+        # already converts / evaluates the pieces that have landed (PCIe is the longest stage of a step)
+        chunks = int(os.environ.get("CLEANRL_B200_H2D_CHUNKS", "4"))
+        self.h2d_chunks = chunks if (self.cuda_graphs and getattr(self, "s2d", False) and chunks > 1
+                                     and N % chunks == 0 and N // chunks >= 128) else 1
+        if self.h2d_chunks > 1:
+            self.copy_stream = torch.cuda.Stream(device=device)
+            self.chunk_events = [torch.cuda.Event() for _ in range(self.h2d_chunks)]
+            self.noise_buf = torch.zeros(agent.noise_shape(N), dtype=f32, device=device)
         self._graphs = {}
         self._graph_kernels = {}
-        self._graph_warm = False
+        self._graph_warm = set()
         self.graph_launches = 0          # libb200rl kernels executed through graph replays
         self.h2d_bytes = 0
         self.d2h_bytes = 0
@@ -139,40 +148,76 @@ class PPOEngine:
             ops.frames_to_s2d(self.obs_u8, out=self.obs[step])
         self.agent.sample_into(self.obs[step], self.actions[step], self.logprobs[step], self.values[step])
 
-    def _run_step(self, step):
+    def _chunk_device_work(self, step, c):
+        n = self.N // self.h2d_chunks
+        sl = slice(c * n, (c + 1) * n)
+        ops.frames_to_s2d(self.obs_u8[sl], out=self.obs[step][sl])
+        self.agent.sample_into(self.obs[step][sl], self.actions[step][sl], self.logprobs[step][sl],
+                               self.values[step][sl], noise=self.noise_buf[sl])
+
+    def _run_step(self, step, chunk=None):
+        if chunk is not None:
+            work, key = (lambda: self._chunk_device_work(step, chunk)), (step, chunk)
+        else:
+            work, key = (lambda: self._step_device_work(step)), step
+        return self._run_graphed(work, key, warm_key="c" if chunk is not None else "f")
+
+    def _run_graphed(self, work, key, warm_key):
         if not (self.cuda_graphs and getattr(self.agent, "graph_friendly", False)):
-            return self._step_device_work(step)
+            return work()
         if hasattr(self.agent, "_tc_plan") and getattr(self.agent, "precision", "fp32") == "bf16":
             self.agent._tc_plan()                      # (re)pack weights outside the graph
-        g = self._graphs.get(step)
+        g = self._graphs.get(key)
         if g is None:
-            if not self._graph_warm:                   # allocate workspaces once (eager), then capture
+            if warm_key not in self._graph_warm:       # allocate workspaces once (eager), then capture
                 rng = torch.cuda.get_rng_state(self.device)     # the warm-up must not consume sampling noise
-                self._step_device_work(step)
+                work()
                 torch.cuda.current_stream().synchronize()
                 torch.cuda.set_rng_state(rng, self.device)
-                self._graph_warm = True
+                self._graph_warm.add(warm_key)
             from . import _lib
             l0 = _lib.load().b200rl_launch_count()
             g = torch.cuda.CUDAGraph()
             with torch.cuda.graph(g):
-                self._step_device_work(step)
-            self._graphs[step] = g
-            self._graph_kernels[step] = _lib.load().b200rl_launch_count() - l0
+                work()
+            self._graphs[key] = g
+            self._graph_kernels[key] = _lib.load().b200rl_launch_count() - l0
         g.replay()
-        self.graph_launches += self._graph_kernels[step]
+        self.graph_launches += self._graph_kernels[key]
 
     @torch.no_grad()
     def policy_step(self, step, next_obs_np, next_done_np):
         """obs[step] <- next_obs (H2D), sample actions, return them as a host int64 array.
         Reference: ppo.py:194-205 (store obs/done, no-grad policy, action.cpu())."""
-        self._upload_obs(self.obs[step], next_obs_np, convert=False)
         self.dones_h[step].copy_(torch.as_tensor(np.asarray(next_done_np, dtype=np.float32)))
-        self._run_step(step)
+        if self.h2d_chunks > 1 and getattr(self.agent, "graph_friendly", False):
+            self._pipelined_step(step, next_obs_np)
+        else:
+            self._upload_obs(self.obs[step], next_obs_np, convert=False)
+            self._run_step(step)
         self.actions_h.copy_(self.actions[step], non_blocking=True)
         self.d2h_bytes += self.actions_h.numel() * self.actions_h.element_size()
         _sync()
         return self.actions_h.numpy()
+
+    def _pipelined_step(self, step, obs_np):
+        """H2D of chunk c+1 overlaps frame conversion + policy of chunk c (separate copy stream + events); the
+        step's sampling noise is ONE draw for the whole batch, as in the unchunked path and the reference."""
+        src = torch.from_numpy(np.ascontiguousarray(obs_np))
+        if not src.is_pinned():
+            self.obs_stage_h.copy_(src)
+            src = self.obs_stage_h
+        C, n = self.h2d_chunks, self.N // self.h2d_chunks
+        main = torch.cuda.current_stream()
+        with torch.cuda.stream(self.copy_stream):
+            for c in range(C):
+                self.obs_u8[c * n:(c + 1) * n].copy_(src[c * n:(c + 1) * n], non_blocking=True)
+                self.chunk_events[c].record(self.copy_stream)
+        self.h2d_bytes += src.numel()
+        self.agent.draw_noise_into(self.noise_buf)
+        for c in range(C):
+            main.wait_event(self.chunk_events[c])
+            self._run_step(step, chunk=c)
 
     @torch.no_grad()
     def policy_step_resident(self, step, obs_dev, done_dev=None):

@@ -158,7 +158,7 @@ def test_ppo_mlp_script_reproduces_reference_run(lib):
             assert abs(per[u, col] - ref) <= (1e-5 if u == 0 else 1e-4) * max(1.0, abs(ref)), (u, key, per[u, col], ref)
 
 
-@pytest.mark.parametrize("kind", ["atari_bf16", "mlp"])
+@pytest.mark.parametrize("kind", ["atari_bf16", "atari_bf16_chunked", "mlp"])
 def test_cuda_graph_rollout_equals_eager(lib, kind):
     """The per-slot CUDA graphs of PPOEngine replay exactly the eager step: same generator state => identical
     actions / logprobs / values over two iterations (incl. weight re-packing between iterations)."""
@@ -170,9 +170,9 @@ def test_cuda_graph_rollout_equals_eager(lib, kind):
     outs = []
     for graphs in (False, True):
         np.random.seed(3); torch.manual_seed(3)
-        N, T = 32, 6
+        N, T = (512, 3) if kind == "atari_bf16_chunked" else (32, 6)    # 512 envs => 4-chunk H2D/compute pipeline
         args = ppo_args(N, T, 4, "bf16")
-        if kind == "atari_bf16":
+        if kind.startswith("atari_bf16"):
             envs = SyntheticAtariVec(N, seed=3, mode="fresh")
             envs.single_observation_space, envs.single_action_space = envs.observation_space, envs.action_space
             agent = NatureCNNAgent(envs).to(dev); agent.precision = "bf16"
@@ -198,7 +198,8 @@ def test_cuda_graph_rollout_equals_eager(lib, kind):
             eng.finish_rollout(obs, done)
             eng.update(2.5e-4)
             rec.append((eng.actions.clone(), eng.logprobs.clone(), eng.values.clone()))
-        assert (len(eng._graphs) == T) == graphs
+        assert (len(eng._graphs) == T * eng.h2d_chunks) == graphs
+        assert eng.h2d_chunks == (4 if (graphs and kind == "atari_bf16_chunked") else 1)
         outs.append(rec)
     for (a0, l0, v0), (a1, l1, v1) in zip(*outs):
         assert torch.equal(a0, a1) and torch.equal(l0, l1) and torch.equal(v0, v1)
