@@ -60,9 +60,10 @@ struct KGemmParams {
     const float* bias;
     float scale;
     int relu;
-    const bf16* mask;      // same layout as out: multiply by (mask > 0)
-    // fc data-gradient only: write dact3 on the 9x9 linear grid (out) and zero-padded 11x11 grid (out2);
-    // mask is read from the dense [n, 3136] act3
+    // ReLU masks as bits, word (row * N/32 + col/32) of a dense [M, N] tensor (see WinParams)
+    const uint32_t* mask_bits;   // multiply the output by the mask (data-gradient)
+    uint32_t* mask_out;          // record (output > 0) (forward with relu)
+    // fc data-gradient only: write dact3 on the 9x9 linear grid (out) and zero-padded 11x11 grid (out2)
     int dual_dact3;
     bf16* out2;
 };
@@ -93,13 +94,16 @@ struct WinParams {
     int out_mode;
     bf16* out;               // primary output
     bf16* out2;              // WOUT_DACT2: padded 11x11 copy
-    const bf16* mask;        // ReLU mask source (layout depends on out_mode)
+    // ReLU masks travel as BITS (1 = the forward activation was > 0), one 32-bit word per 32 channels, in the row
+    // order of the tensor they describe: 16x fewer bytes than re-reading the bf16 activation
+    const uint32_t* mask_bits;   // input mask (data-gradient kernels): words of the row this thread writes
+    uint32_t* mask_out;          // output mask (forward kernels with relu)
     const float* bias;
     float scale;
     int relu;
 };
 
-template <int BN, int CPR, int STAGES>
+template <int BN, int CPR, int STAGES, int NTAPS>
 __global__ void __launch_bounds__(416, 1) tc_conv_win(const __grid_constant__ CUtensorMap tmA, const WinParams p,
                                                       int total_tiles) {
     constexpr int LOOKAHEAD = STAGES - 2;
@@ -120,7 +124,7 @@ __global__ void __launch_bounds__(416, 1) tc_conv_win(const __grid_constant__ CU
     if (tid == 0) {
         // window producers: one TMA issuer (expect_tx arrival) when rows are contiguous, 4 cp.async warps for the gather
         for (int s = 0; s < STAGES; ++s) { mbar_init(&full_bar[s], p.rows ? 4 : 1); mbar_init(&empty_bar[s], 1); }
-        for (int a = 0; a < 2; ++a) { mbar_init(&tfull_bar[a], 1); mbar_init(&tempty_bar[a], 8); }
+        for (int a = 0; a < 2; ++a) { mbar_init(&tfull_bar[a], 1); mbar_init(&tempty_bar[a], 4); }
         fence_barrier_init();
         if (!p.rows) tma_prefetch_desc(&tmA);
     }
@@ -214,141 +218,154 @@ __global__ void __launch_bounds__(416, 1) tc_conv_win(const __grid_constant__ CU
         if ((tid & 31) == 0)
             for (uint32_t d = (q >= (uint32_t)LOOKAHEAD ? q - LOOKAHEAD : 0); d < q; ++d) mbar_arrive(&full_bar[d % STAGES]);
     } else if (warp == 4) {
-        // ======================= MMA issuer =======================
-        if ((tid & 31) == 0) {
-            constexpr uint32_t idesc = make_idesc(128, BN, 0, 0);
-            uint32_t q = 0;
-            for (int tile = tile_begin; tile < tile_end; ++tile, ++q) {
-                const uint32_t acc = q & 1, s = q % STAGES;
-                if (q >= 2) mbar_wait(&tempty_bar[acc], ((q >> 1) - 1) & 1);
-                mbar_wait(&full_bar[s], (q / STAGES) & 1);
-                tc_fence_after_sync();
+        // ======================= MMA issuer: the WHOLE warp walks the tile loop (uniform control flow keeps the
+        // descriptor arithmetic in uniform registers), one elected lane issues.  Descriptors differ from a per-stage /
+        // per-tap base only in their 14-bit start-address field, so each MMA costs two 32-bit adds.
+        const bool leader = elect_one();
+        constexpr uint32_t idesc = make_idesc(128, BN, 0, 0);
+        const uint64_t desc_hi = desc_kmajor(0) & 0xFFFFFFFF00000000ull;
+        const uint32_t desc_lo_flags = (uint32_t)(desc_kmajor(0) & 0xFFFFFFFFull);       // LBO field
+        const uint32_t w_lo = ((smem_u32(sW) & 0x3FFFFu) >> 4) | desc_lo_flags;
+        uint32_t q = 0;
+        for (int tile = tile_begin; tile < tile_end; ++tile, ++q) {
+            const uint32_t acc = q & 1, s = q % STAGES;
+            if (q >= 2) mbar_wait(&tempty_bar[acc], ((q >> 1) - 1) & 1);
+            mbar_wait(&full_bar[s], (q / STAGES) & 1);
+            tc_fence_after_sync();
+            if (leader) {
                 const uint32_t d_addr = tmem_d + acc * BN;
-                const uint32_t win = smem_u32(sRing + (size_t)s * STAGE_BYTES);
-                uint32_t first = 1;
-                for (int t = 0; t < p.ntaps; ++t) {
+                const uint32_t win_lo = ((smem_u32(sRing + (size_t)s * STAGE_BYTES) & 0x3FFFFu) >> 4) | desc_lo_flags;
+#pragma unroll
+                for (int t = 0; t < NTAPS; ++t) {
 #pragma unroll
                     for (int c = 0; c < CPR; ++c) {
-                        const uint64_t adesc = desc_kmajor(win + c * IMG + p.shift[t] * 128);
-                        const uint64_t bdesc = desc_kmajor(smem_u32(sW + (size_t)(t * CPR + c) * B_CHUNK));
+                        const uint32_t a_lo = win_lo + (uint32_t)((c * IMG) >> 4) + (uint32_t)p.shift[t] * 8u;
+                        const uint32_t b_lo = w_lo + (uint32_t)(((t * CPR + c) * B_CHUNK) >> 4);
 #pragma unroll
-                        for (int kk = 0; kk < 4; ++kk) {
-                            umma_bf16(d_addr, adesc + 2 * kk, bdesc + 2 * kk, idesc, first ? 0u : 1u);
-                            first = 0;
-                        }
+                        for (int kk = 0; kk < 4; ++kk)
+                            umma_bf16(d_addr, desc_hi | (uint64_t)(a_lo + 2 * kk), desc_hi | (uint64_t)(b_lo + 2 * kk), idesc,
+                                      (t | c | kk) != 0 ? 1u : 0u);
                     }
                 }
                 umma_commit(&empty_bar[s]);
                 umma_commit(&tfull_bar[acc]);
             }
+            __syncwarp();
         }
     } else {
-        // ======================= epilogue: warps 5-12, two per TMEM lane quadrant; the pair splits the 16-column
-        // groups even/odd so that two warps per scheduler hide each other's tcgen05.ld / global latencies =========
+        // ======================= epilogue: warps 5-12 = two groups of four (one warp per TMEM lane quadrant).
+        // Group h owns accumulator buffer h, i.e. every other tile of the CTA's range, and handles ALL BN columns
+        // of its rows: the row -> (image, Y, X) -> output offset arithmetic is paid once per tile and thread, and
+        // is incremental (a tile step is 256 grid rows; Y = rem / Wp by multiply-shift, exact for G*Wp < 65536).
         const int ew = warp & 3;
-        const int half = (warp - 5) >> 2;
+        const int h = (warp - 5) >> 2;
         const int lrow = ew * 32 + (tid & 31);
-        uint32_t q = 0;
-        for (int tile = tile_begin; tile < tile_end; ++tile, ++q) {
-            const uint32_t acc = q & 1;
-            const int64_t r = (int64_t)tile * 128 + lrow;
-            bool valid = r < p.M;
-            int i = 0, Y = 0, X = 0;
-            if (valid) {
-                i = (int)(r / p.G);
-                const int rem = (int)(r - (int64_t)i * p.G);
-                Y = rem / p.Wp; X = rem - Y * p.Wp;
-                valid = (Y < p.vH) && (X < p.vW);
-            }
-            int64_t o1 = 0, o2 = 0, om = 0;
+        const uint32_t mW = (65536u + (uint32_t)p.Wp - 1u) / (uint32_t)p.Wp;
+        const int step_i = 256 / p.G, step_rem = 256 % p.G;
+        int64_t r = ((int64_t)tile_begin + h) * 128 + lrow;
+        int i = (int)(r / p.G);
+        int rem = (int)(r - (int64_t)i * p.G);
+        const uint32_t lane_addr = tmem_d + h * BN + ((uint32_t)(ew * 32) << 16);
+        constexpr int NW = BN / 32;                          // 32-column groups = mask words per row
+        uint32_t k = 0;                                      // use count of accumulator buffer h
+        for (int tile = tile_begin + h; tile < tile_end; tile += 2, ++k) {
+            const int Y = (int)(((uint32_t)rem * mW) >> 16), X = rem - Y * p.Wp;
+            const bool valid = (r < p.M) && (Y < p.vH) && (X < p.vW);
+            int64_t o1 = 0, o2 = 0, ob = 0;
             if (p.out_mode == WOUT_DENSE) {
-                o1 = (((int64_t)i * p.vH + Y) * p.vW + X) * p.N;
+                const int64_t orow = ((int64_t)i * p.vH + Y) * p.vW + X;
+                o1 = orow * p.N; ob = orow * (p.N >> 5);
             } else if (p.out_mode == WOUT_S2D2) {
-                o1 = (((int64_t)i * 10 + (Y >> 1)) * 10 + (X >> 1)) * 128 + ((Y & 1) * 2 + (X & 1)) * 32;
+                const int64_t cell = ((int64_t)i * 10 + (Y >> 1)) * 10 + (X >> 1);
+                const int cls = (Y & 1) * 2 + (X & 1);
+                o1 = cell * 128 + cls * 32; ob = cell * 4 + cls;
             } else if (p.out_mode == WOUT_DACT2) {
                 o1 = ((int64_t)i * 100 + Y * 10 + X) * 64;                 // 10-grid linear (conv2 wgrad)
                 o2 = ((int64_t)i * 121 + (Y + 1) * 11 + (X + 1)) * 64;     // zero-padded 11x11 (conv2 dgrad)
-                om = ((int64_t)i * 81 + Y * 9 + X) * 64;                   // act2 dense
+                ob = ((int64_t)i * 81 + Y * 9 + X) * 2;                    // act2 mask words
             } else {
-                om = ((int64_t)i * 100 + Y * 10 + X) * 128;                // act1 cells [n,100,128]
+                ob = ((int64_t)i * 100 + Y * 10 + X) * 4;                  // act1 (2x2 cells) mask words
             }
-            // ReLU-mask words are fetched one column group AHEAD (the first one before waiting for the
-            // accumulator), so their global-memory latency overlaps the MMAs / the previous group's stores
-            const bool use_mask = p.mask != nullptr && valid;
-            const int cfirst = half * 16;
-            // all ReLU-mask words of this thread's column groups are requested BEFORE waiting for the accumulator:
-            // their global-memory latency (~1-2 us under load) overlaps the tile's MMAs
-            constexpr int NG = (BN + 31) / 32;
-            int4 mk[2 * NG];
+            // the row's mask words are requested BEFORE waiting for the accumulator (latency overlaps the MMAs)
+            uint32_t mb[NW];
 #pragma unroll
-            for (int g = 0; g < NG; ++g) {
-                const int c = cfirst + 32 * g;
-                if (use_mask && c < p.N) { mk[2 * g] = ldg16(p.mask + om + c); mk[2 * g + 1] = ldg16(p.mask + om + c + 8); }
-                else { mk[2 * g] = make_int4(0, 0, 0, 0); mk[2 * g + 1] = make_int4(0, 0, 0, 0); }
-            }
-            mbar_wait(&tfull_bar[acc], (q >> 1) & 1);
-            tc_fence_after_sync();
-            const uint32_t lane_addr = tmem_d + acc * BN + ((uint32_t)(ew * 32) << 16);
-#pragma unroll
-            for (int g = 0; g < NG; ++g) {
-                const int c0 = cfirst + 32 * g;
-                if (c0 >= BN) break;
-                uint32_t v[16];
-                tmem_ld16(lane_addr + c0, v);
-                const int4 m0 = mk[2 * g], m1 = mk[2 * g + 1];
-                tmem_ld_wait();
-                if (!valid || c0 >= p.N) continue;
-                float f[16];
-                if (p.bias) {
-                    const float4* bp = reinterpret_cast<const float4*>(p.bias + c0);
-#pragma unroll
-                    for (int e = 0; e < 4; ++e) {
-                        const float4 bv = __ldg(bp + e);
-                        f[4 * e] = fmaf(__uint_as_float(v[4 * e]), p.scale, bv.x);
-                        f[4 * e + 1] = fmaf(__uint_as_float(v[4 * e + 1]), p.scale, bv.y);
-                        f[4 * e + 2] = fmaf(__uint_as_float(v[4 * e + 2]), p.scale, bv.z);
-                        f[4 * e + 3] = fmaf(__uint_as_float(v[4 * e + 3]), p.scale, bv.w);
-                    }
+            for (int g = 0; g < NW; ++g) mb[g] = 0xFFFFFFFFu;
+            if (p.mask_bits != nullptr && valid) {
+                if (NW == 4) {
+                    const int4 t = ldg16(p.mask_bits + ob);
+                    mb[0] = (uint32_t)t.x; mb[1 % NW] = (uint32_t)t.y; mb[2 % NW] = (uint32_t)t.z; mb[3 % NW] = (uint32_t)t.w;
+                } else if (NW == 2) {
+                    const uint2 t = __ldg(reinterpret_cast<const uint2*>(p.mask_bits + ob));
+                    mb[0] = t.x; mb[1 % NW] = t.y;
                 } else {
-#pragma unroll
-                    for (int e = 0; e < 16; ++e) f[e] = __uint_as_float(v[e]) * p.scale;
+                    mb[0] = __ldg(p.mask_bits + ob);
                 }
-                if (p.relu) {
+            }
+            mbar_wait(&tfull_bar[h], k & 1);
+            tc_fence_after_sync();
 #pragma unroll
-                    for (int e = 0; e < 16; ++e) f[e] = fmaxf(f[e], 0.f);
+            for (int g = 0; g < NW; ++g) {
+                uint32_t v[32];
+                tmem_ld32(lane_addr + g * 32, v);
+                tmem_ld_wait();
+                if (g == NW - 1) {             // accumulator drained: hand the buffer back before the global stores
+                    tc_fence_before_sync();
+                    __syncwarp();
+                    if ((tid & 31) == 0) mbar_arrive(&tempty_bar[h]);
                 }
-                if (p.mask) {
-                    const uint32_t mw[8] = {(uint32_t)m0.x, (uint32_t)m0.y, (uint32_t)m0.z, (uint32_t)m0.w,
-                                            (uint32_t)m1.x, (uint32_t)m1.y, (uint32_t)m1.z, (uint32_t)m1.w};
+                if (!valid || g * 32 >= p.N) continue;
+                if (p.bias) {
+                    const float4* bp = reinterpret_cast<const float4*>(p.bias + g * 32);
 #pragma unroll
                     for (int e = 0; e < 8; ++e) {
-                        if ((mw[e] & 0x7FFFu) == 0u) f[2 * e] = 0.f;
-                        if ((mw[e] & 0x7FFF0000u) == 0u) f[2 * e + 1] = 0.f;
+                        const float4 bv = __ldg(bp + e);
+                        v[4 * e] = __float_as_uint(fmaf(__uint_as_float(v[4 * e]), p.scale, bv.x));
+                        v[4 * e + 1] = __float_as_uint(fmaf(__uint_as_float(v[4 * e + 1]), p.scale, bv.y));
+                        v[4 * e + 2] = __float_as_uint(fmaf(__uint_as_float(v[4 * e + 2]), p.scale, bv.z));
+                        v[4 * e + 3] = __float_as_uint(fmaf(__uint_as_float(v[4 * e + 3]), p.scale, bv.w));
                     }
+                } else {
+#pragma unroll
+                    for (int e = 0; e < 32; ++e) v[e] = __float_as_uint(__uint_as_float(v[e]) * p.scale);
                 }
-                int4 w0, w1;
-                w0.x = (int)pack_bf16x2(f[0], f[1]);   w0.y = (int)pack_bf16x2(f[2], f[3]);
-                w0.z = (int)pack_bf16x2(f[4], f[5]);   w0.w = (int)pack_bf16x2(f[6], f[7]);
-                w1.x = (int)pack_bf16x2(f[8], f[9]);   w1.y = (int)pack_bf16x2(f[10], f[11]);
-                w1.z = (int)pack_bf16x2(f[12], f[13]); w1.w = (int)pack_bf16x2(f[14], f[15]);
+                if (p.relu) {
+                    uint32_t bits = 0u;
+#pragma unroll
+                    for (int e = 0; e < 32; ++e) {
+                        const float f = __uint_as_float(v[e]);
+                        const bool pos = f > 0.f;
+                        bits |= (pos ? 1u : 0u) << e;
+                        v[e] = pos ? v[e] : 0u;
+                    }
+                    if (p.mask_out) p.mask_out[ob + g] = bits;
+                }
+                if (p.mask_bits) {
+#pragma unroll
+                    for (int e = 0; e < 32; ++e) if (!((mb[g] >> e) & 1u)) v[e] = 0u;
+                }
+                int4 w[4];
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                    w[e].x = (int)pack_bf16x2(__uint_as_float(v[8 * e]), __uint_as_float(v[8 * e + 1]));
+                    w[e].y = (int)pack_bf16x2(__uint_as_float(v[8 * e + 2]), __uint_as_float(v[8 * e + 3]));
+                    w[e].z = (int)pack_bf16x2(__uint_as_float(v[8 * e + 4]), __uint_as_float(v[8 * e + 5]));
+                    w[e].w = (int)pack_bf16x2(__uint_as_float(v[8 * e + 6]), __uint_as_float(v[8 * e + 7]));
+                }
+                int4* dst;
                 if (p.out_mode == WOUT_DACT1) {
                     // column group g = (py,px) of the cell -> input pixel (2Y+py, 2X+px) of the 21-grid, 32 channels
-                    const int g = c0 >> 5;
-                    const int64_t od = ((int64_t)i * 441 + (2 * Y + (g >> 1)) * 21 + 2 * X + (g & 1)) * 32 + (c0 & 31);
-                    int4* dst = reinterpret_cast<int4*>(p.out + od);
-                    dst[0] = w0; dst[1] = w1;
+                    dst = reinterpret_cast<int4*>(p.out + ((int64_t)i * 441 + (2 * Y + (g >> 1)) * 21 + 2 * X + (g & 1)) * 32);
                 } else {
-                    int4* dst = reinterpret_cast<int4*>(p.out + o1 + c0);
-                    dst[0] = w0; dst[1] = w1;
-                    if (p.out_mode == WOUT_DACT2) {
-                        int4* dst2 = reinterpret_cast<int4*>(p.out2 + o2 + c0);
-                        dst2[0] = w0; dst2[1] = w1;
-                    }
+                    dst = reinterpret_cast<int4*>(p.out + o1 + g * 32);
+                }
+                dst[0] = w[0]; dst[1] = w[1]; dst[2] = w[2]; dst[3] = w[3];
+                if (p.out_mode == WOUT_DACT2) {
+                    int4* dst2 = reinterpret_cast<int4*>(p.out2 + o2 + g * 32);
+                    dst2[0] = w[0]; dst2[1] = w[1]; dst2[2] = w[2]; dst2[3] = w[3];
                 }
             }
-            tc_fence_before_sync();
-            __syncwarp();
-            if ((tid & 31) == 0) mbar_arrive(&tempty_bar[acc]);
+            r += 256; i += step_i; rem += step_rem;
+            if (rem >= p.G) { rem -= p.G; ++i; }
         }
     }
     tc_fence_before_sync();
@@ -378,7 +395,7 @@ __global__ void __launch_bounds__(320, 1) tc_gemm_tma(const __grid_constant__ CU
     const int nch = p.nchunks;
     if (tid == 0) {
         for (int s = 0; s < STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
-        for (int a = 0; a < 2; ++a) { mbar_init(&tfull_bar[a], 1); mbar_init(&tempty_bar[a], 8); }
+        for (int a = 0; a < 2; ++a) { mbar_init(&tfull_bar[a], 1); mbar_init(&tempty_bar[a], 4); }
         fence_barrier_init();
         tma_prefetch_desc(&tmA);
         tma_prefetch_desc(&tmB);
@@ -427,88 +444,87 @@ __global__ void __launch_bounds__(320, 1) tc_gemm_tma(const __grid_constant__ CU
             }
         }
     } else {
-        // warps 2-9: two per TMEM lane quadrant, splitting the 16-column groups even/odd
+        // warps 2-9 = two groups of four (one warp per TMEM lane quadrant); group h owns accumulator buffer h
+        // (every other tile of this CTA) and handles all BN columns of its rows in 32-column steps
         const int ew = warp & 3;
-        const int half = (warp - 2) >> 2;
+        const int h = (warp - 2) >> 2;
         const int lrow = ew * 32 + (tid & 31);
-        uint32_t t = 0;
-        for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++t) {
+        const uint32_t lane_addr = tmem_d + h * BN + ((uint32_t)(ew * 32) << 16);
+        const int nwords = p.N >> 5;                         // mask words per row (N is a multiple of 32)
+        constexpr int NW = BN / 32;
+        uint32_t k = 0;
+        for (int tile = blockIdx.x + h * (int)gridDim.x; tile < total_tiles; tile += 2 * (int)gridDim.x, ++k) {
             const int mt = tile / ntiles_n, n0 = (tile - mt * ntiles_n) * BN;
-            const uint32_t acc = t & 1;
             const int r = mt * 128 + lrow;
             const bool rvalid = r < (int)p.M;
             const int64_t ooff = (int64_t)r * p.ldo;
-            const bool use_mask = p.mask != nullptr && rvalid;
-            const int cfirst = half * 16;
-            constexpr int NG = (BN + 31) / 32;
-            int4 mk[2 * NG];
+            const int64_t wb = (int64_t)r * nwords + (n0 >> 5);
+            uint32_t mb[NW];
 #pragma unroll
-            for (int g = 0; g < NG; ++g) {
-                const int c = n0 + cfirst + 32 * g;
-                if (use_mask && c < p.N) { mk[2 * g] = ldg16(p.mask + ooff + c); mk[2 * g + 1] = ldg16(p.mask + ooff + c + 8); }
-                else { mk[2 * g] = make_int4(0, 0, 0, 0); mk[2 * g + 1] = make_int4(0, 0, 0, 0); }
-            }
-            mbar_wait(&tfull_bar[acc], (t >> 1) & 1);
+            for (int g = 0; g < NW; ++g)
+                mb[g] = (p.mask_bits != nullptr && rvalid && n0 + g * 32 < p.N) ? __ldg(p.mask_bits + wb + g) : 0xFFFFFFFFu;
+            mbar_wait(&tfull_bar[h], k & 1);
             tc_fence_after_sync();
-            const uint32_t lane_addr = tmem_d + acc * BN + ((uint32_t)(ew * 32) << 16);
 #pragma unroll
-            for (int g = 0; g < NG; ++g) {
-                const int c0 = cfirst + 32 * g;
-                if (c0 >= BN) break;
-                uint32_t v[16];
-                tmem_ld16(lane_addr + c0, v);
-                const int4 m0 = mk[2 * g], m1 = mk[2 * g + 1];
+            for (int g = 0; g < NW; ++g) {
+                uint32_t v[32];
+                tmem_ld32(lane_addr + g * 32, v);
                 tmem_ld_wait();
-                const int col = n0 + c0;
+                if (g == NW - 1) {
+                    tc_fence_before_sync();
+                    __syncwarp();
+                    if ((tid & 31) == 0) mbar_arrive(&tempty_bar[h]);
+                }
+                const int col = n0 + g * 32;
                 if (!rvalid || col >= p.N) continue;
-                float f[16];
                 if (p.bias) {
                     const float4* bp = reinterpret_cast<const float4*>(p.bias + col);
 #pragma unroll
-                    for (int e = 0; e < 4; ++e) {
+                    for (int e = 0; e < 8; ++e) {
                         const float4 bv = __ldg(bp + e);
-                        f[4 * e] = fmaf(__uint_as_float(v[4 * e]), p.scale, bv.x);
-                        f[4 * e + 1] = fmaf(__uint_as_float(v[4 * e + 1]), p.scale, bv.y);
-                        f[4 * e + 2] = fmaf(__uint_as_float(v[4 * e + 2]), p.scale, bv.z);
-                        f[4 * e + 3] = fmaf(__uint_as_float(v[4 * e + 3]), p.scale, bv.w);
+                        v[4 * e] = __float_as_uint(fmaf(__uint_as_float(v[4 * e]), p.scale, bv.x));
+                        v[4 * e + 1] = __float_as_uint(fmaf(__uint_as_float(v[4 * e + 1]), p.scale, bv.y));
+                        v[4 * e + 2] = __float_as_uint(fmaf(__uint_as_float(v[4 * e + 2]), p.scale, bv.z));
+                        v[4 * e + 3] = __float_as_uint(fmaf(__uint_as_float(v[4 * e + 3]), p.scale, bv.w));
                     }
                 } else {
 #pragma unroll
-                    for (int e = 0; e < 16; ++e) f[e] = __uint_as_float(v[e]) * p.scale;
+                    for (int e = 0; e < 32; ++e) v[e] = __float_as_uint(__uint_as_float(v[e]) * p.scale);
                 }
                 if (p.relu) {
+                    uint32_t bits = 0u;
 #pragma unroll
-                    for (int e = 0; e < 16; ++e) f[e] = fmaxf(f[e], 0.f);
-                }
-                if (p.mask) {
-                    const uint32_t mw[8] = {(uint32_t)m0.x, (uint32_t)m0.y, (uint32_t)m0.z, (uint32_t)m0.w,
-                                            (uint32_t)m1.x, (uint32_t)m1.y, (uint32_t)m1.z, (uint32_t)m1.w};
-#pragma unroll
-                    for (int e = 0; e < 8; ++e) {
-                        if ((mw[e] & 0x7FFFu) == 0u) f[2 * e] = 0.f;
-                        if ((mw[e] & 0x7FFF0000u) == 0u) f[2 * e + 1] = 0.f;
+                    for (int e = 0; e < 32; ++e) {
+                        const bool pos = __uint_as_float(v[e]) > 0.f;
+                        bits |= (pos ? 1u : 0u) << e;
+                        v[e] = pos ? v[e] : 0u;
                     }
+                    if (p.mask_out) p.mask_out[wb + g] = bits;
                 }
-                int4 o0, o1;
-                o0.x = (int)pack_bf16x2(f[0], f[1]);   o0.y = (int)pack_bf16x2(f[2], f[3]);
-                o0.z = (int)pack_bf16x2(f[4], f[5]);   o0.w = (int)pack_bf16x2(f[6], f[7]);
-                o1.x = (int)pack_bf16x2(f[8], f[9]);   o1.y = (int)pack_bf16x2(f[10], f[11]);
-                o1.z = (int)pack_bf16x2(f[12], f[13]); o1.w = (int)pack_bf16x2(f[14], f[15]);
+                if (p.mask_bits) {
+#pragma unroll
+                    for (int e = 0; e < 32; ++e) if (!((mb[g] >> e) & 1u)) v[e] = 0u;
+                }
+                int4 w[4];
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                    w[e].x = (int)pack_bf16x2(__uint_as_float(v[8 * e]), __uint_as_float(v[8 * e + 1]));
+                    w[e].y = (int)pack_bf16x2(__uint_as_float(v[8 * e + 2]), __uint_as_float(v[8 * e + 3]));
+                    w[e].z = (int)pack_bf16x2(__uint_as_float(v[8 * e + 4]), __uint_as_float(v[8 * e + 5]));
+                    w[e].w = (int)pack_bf16x2(__uint_as_float(v[8 * e + 6]), __uint_as_float(v[8 * e + 7]));
+                }
                 if (p.dual_dact3) {
                     const int px = col >> 6, ch = col & 63;
                     const int oy = px / 7, ox = px - oy * 7;
                     int4* da = reinterpret_cast<int4*>(p.out + ((int64_t)r * 81 + oy * 9 + ox) * 64 + ch);
                     int4* db = reinterpret_cast<int4*>(p.out2 + ((int64_t)r * 121 + (oy + 2) * 11 + ox + 2) * 64 + ch);
-                    da[0] = o0; da[1] = o1;
-                    db[0] = o0; db[1] = o1;
+                    da[0] = w[0]; da[1] = w[1]; da[2] = w[2]; da[3] = w[3];
+                    db[0] = w[0]; db[1] = w[1]; db[2] = w[2]; db[3] = w[3];
                 } else {
                     int4* dst = reinterpret_cast<int4*>(p.out + ooff + col);
-                    dst[0] = o0; dst[1] = o1;
+                    dst[0] = w[0]; dst[1] = w[1]; dst[2] = w[2]; dst[3] = w[3];
                 }
             }
-            tc_fence_before_sync();
-            __syncwarp();
-            if ((tid & 31) == 0) mbar_arrive(&tempty_bar[acc]);
         }
     }
     tc_fence_before_sync();
@@ -670,15 +686,18 @@ static int launch_gemm_tma(const KGemmParams& p, cudaStream_t s, const char* wha
     return check_launch(what);
 }
 
-template <int BN, int CPR, int STAGES>
+template <int BN, int CPR, int STAGES, int NTAPS>
 static int launch_conv_win(const WinParams& p, cudaStream_t s, const char* what) {
+    if (p.ntaps != NTAPS) return fail(B200RL_ERR_INVALID_ARGUMENT, "%s: %d taps, kernel instance has %d", what, p.ntaps, NTAPS);
     const size_t smem = (size_t)p.ntaps * CPR * BN * 128 + (size_t)STAGES * p.WR * 128 * CPR + 1024;
     static size_t attr = 0;
     if (smem > attr) {
-        cudaError_t e = cudaFuncSetAttribute(tc_conv_win<BN, CPR, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        cudaError_t e = cudaFuncSetAttribute(tc_conv_win<BN, CPR, STAGES, NTAPS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return fail(B200RL_ERR_CUDA, "%s: smem attribute (%zu B): %s", what, smem, cudaGetErrorString(e));
         attr = smem;
     }
+    if ((int64_t)p.G * p.Wp >= 65536 || p.G < 1 || p.N % 32 != 0)
+        return fail(B200RL_ERR_INVALID_ARGUMENT, "%s: grid %d x width %d outside the epilogue's multiply-shift range, or N %% 32 != 0", what, p.G, p.Wp);
     const int total = (int)ceil_div(p.M, 128);
     int grid = num_sms();
     if (grid > total) grid = total;
@@ -688,7 +707,7 @@ static int launch_conv_win(const WinParams& p, cudaStream_t s, const char* what)
         int rc = make_tmap_2d(&tmA, p.A, p.M, (int64_t)CPR * 64, p.WR, what);
         if (rc) return rc;
     }
-    tc_conv_win<BN, CPR, STAGES><<<grid, 416, smem, s>>>(tmA, p, total);
+    tc_conv_win<BN, CPR, STAGES, NTAPS><<<grid, 416, smem, s>>>(tmA, p, total);
     return check_launch(what);
 }
 
@@ -820,30 +839,54 @@ __global__ void __launch_bounds__(160, 1) tc_wgrad_win(const __grid_constant__ C
         __syncwarp();
         if ((tid & 31) == 0)
             for (int d = (nsteps >= LOOKAHEAD ? nsteps - LOOKAHEAD : 0); d < nsteps; ++d) mbar_arrive(&full_bar[d % STAGES]);
-    } else if ((tid & 31) == 0) {
-        const uint32_t idesc = make_idesc(128, NY, 1, 1);
+    } else {
+        // MMA issuer: the whole warp walks the step loop (uniform control flow), one elected lane issues.  Everything
+        // that does not depend on the stage is hoisted: per output tile the X operand's offset inside the stage and its
+        // LBO field; descriptors then differ only in the 14-bit start-address field.
+        const bool leader = elect_one();
+        constexpr uint32_t idesc = make_idesc(128, NY, 1, 1);
+        const uint64_t desc_hi = desc_mnmajor(0, 0) & 0xFFFFFFFF00000000ull;
+        uint32_t arel[8], albo[8];
+#pragma unroll
+        for (int t = 0; t < 8; ++t) {
+            arel[t] = 0; albo[t] = 0;
+            if (t < xt) {
+                const uint32_t r0 = (uint32_t)(p.slot_cc[2 * t] * IMGX + p.shift[p.slot_tap[2 * t]] * 128);
+                const uint32_t r1 = (uint32_t)(p.slot_cc[2 * t + 1] * IMGX + p.shift[p.slot_tap[2 * t + 1]] * 128);
+                arel[t] = r0 >> 4;
+                albo[t] = (((r1 - r0) >> 4) & 0x3FFFu) << 16;
+            }
+        }
+        const uint32_t ylbo = (uint32_t)(((R * 128) >> 4) & 0x3FFF) << 16;
+        const uint32_t ones_lo = ((smem_u32(sOnes) & 0x3FFFFu) >> 4) | ((uint32_t)((2048 >> 4) & 0x3FFF) << 16);
         for (int it = 0; it < nsteps; ++it) {
             const int s = it % STAGES;
             mbar_wait(&full_bar[s], (it / STAGES) & 1);
             tc_fence_after_sync();
-            const uint32_t xa = smem_u32(smem + (size_t)s * stage_bytes), ya = xa + XBYTES;
-            for (int t = 0; t < xt; ++t) {
-                const uint32_t a0 = xa + p.slot_cc[2 * t] * IMGX + p.shift[p.slot_tap[2 * t]] * 128;
-                const uint32_t a1 = xa + p.slot_cc[2 * t + 1] * IMGX + p.shift[p.slot_tap[2 * t + 1]] * 128;
+            if (leader) {
+                const uint32_t xa = smem_u32(smem + (size_t)s * stage_bytes);
+                const uint32_t xa16 = (xa & 0x3FFFFu) >> 4, ya16 = (((xa + XBYTES) & 0x3FFFFu) >> 4) | ylbo;
+                const uint32_t accum = it != 0 ? 1u : 0u;
 #pragma unroll
-                for (int kk = 0; kk < R / 16; ++kk) {
-                    const uint64_t adesc = desc_mnmajor(a0 + kk * 2048, a1 - a0);
-                    const uint64_t bdesc = desc_mnmajor(ya + kk * 2048, R * 128);
-                    umma_bf16(tmem_d + t * NY, adesc, bdesc, idesc, (it | kk) != 0);
+                for (int t = 0; t < 8; ++t) {
+                    if (t < xt) {
+                        const uint32_t a_lo = (xa16 + arel[t]) | albo[t];
+#pragma unroll
+                        for (int kk = 0; kk < R / 16; ++kk)
+                            umma_bf16(tmem_d + t * NY, desc_hi | (uint64_t)(a_lo + kk * 128), desc_hi | (uint64_t)(ya16 + kk * 128),
+                                      idesc, kk != 0 ? 1u : accum);
+                    }
                 }
-            }
 #pragma unroll
-            for (int kk = 0; kk < R / 16; ++kk)
-                umma_bf16(tmem_d + xt * NY, desc_mnmajor(smem_u32(sOnes), 2048), desc_mnmajor(ya + kk * 2048, R * 128), idesc,
-                          (it | kk) != 0);
-            umma_commit(&empty_bar[s]);
+                for (int kk = 0; kk < R / 16; ++kk)
+                    umma_bf16(tmem_d + xt * NY, desc_hi | (uint64_t)ones_lo, desc_hi | (uint64_t)(ya16 + kk * 128), idesc,
+                              kk != 0 ? 1u : accum);
+                umma_commit(&empty_bar[s]);
+            }
+            __syncwarp();
         }
-        umma_commit(&done_bar);
+        if (leader) umma_commit(&done_bar);
+        __syncwarp();
     }
     if (warp < 4) {
         if (nsteps > 0) {
@@ -889,29 +932,53 @@ __global__ void __launch_bounds__(160, 1) tc_wgrad_win(const __grid_constant__ C
     if (warp == 4) tmem_dealloc(tmem_d, tmem_cols);
 }
 
+// out[idx] = sum_z part[z][idx], z < nslabs: block = 8 z-lanes x 32 consecutive outputs; every z-lane sums its
+// slabs (z = lane, lane+8, ...) in ascending order, lane 0 then adds the 8 lane sums in order (deterministic).
+__device__ __forceinline__ float zlane_sum(const float* __restrict__ part, int64_t slab, int nslabs, int64_t idx, bool valid,
+                                           float* red /* [256] */) {
+    const int zl = threadIdx.x >> 5, ol = threadIdx.x & 31;
+    float s = 0.f;
+    if (valid) {
+        int z = zl;
+        for (; z + 24 < nslabs; z += 32) {
+            const float v0 = part[(int64_t)z * slab + idx], v1 = part[(int64_t)(z + 8) * slab + idx];
+            const float v2 = part[(int64_t)(z + 16) * slab + idx], v3 = part[(int64_t)(z + 24) * slab + idx];
+            s += v0; s += v1; s += v2; s += v3;
+        }
+        for (; z < nslabs; z += 8) s += part[(int64_t)z * slab + idx];
+    }
+    red[threadIdx.x] = s;
+    __syncthreads();
+    float t = 0.f;
+    if (zl == 0) {
+#pragma unroll
+        for (int l = 0; l < 8; ++l) t += red[l * 32 + ol];
+    }
+    return t;                                           // meaningful for zl == 0
+}
+
 // fold for the window weight gradients: ws[S][nslots*64][64] -> torch layout dst[co][c][ky][kx].
 //   layer 1: slot = tap (a,b); row channel q = c*16 + sy*4 + sx; ky = 4a+sy, kx = 4b+sx; 32 outputs, Cin 4, 8x8
 //   layer 2: slot = (tap (a,b), cc); q = cc*64 + row = (py*2+px)*32 + c; ky = 2a+py, kx = 2b+px; Cin 32, 4x4
 //   layer 3: slot -> tap (ky,kx) via slot_tap (a duplicate slot is skipped); q = c; Cin 64, 3x3
 struct FoldWin { int layer, S, nslots, Cout; int slot_tap[16], slot_cc[16], slot_skip[16]; float scale;
                  const float* wsb; float* db; };
-__global__ void tc_fold_win(const float* __restrict__ ws, const FoldWin f, float* __restrict__ dst) {
-    const int idx = blockIdx.x * blockDim.x + threadIdx.x;           // (slot*64 + row) * Cout + co
+__global__ void __launch_bounds__(256) tc_fold_win(const float* __restrict__ ws, const FoldWin f, float* __restrict__ dst) {
+    __shared__ float red[256];
+    const int idx = blockIdx.x * 32 + (threadIdx.x & 31);            // (slot*64 + row) * Cout + co
     const int KX = f.nslots * 64;
-    if (idx >= KX * f.Cout) {
-        const int co = idx - KX * f.Cout;                            // trailing threads fold the bias partials
-        if (co < f.Cout && f.db) {
-            float s = 0.f;
-            for (int z = 0; z < f.S; ++z) s += f.wsb[(int64_t)z * 64 + co];
-            f.db[co] = s;
-        }
+    if (idx >= KX * f.Cout) {                                        // trailing blocks fold the bias partials
+        const int co = idx - KX * f.Cout;
+        const bool valid = co < f.Cout && f.db != nullptr;
+        const float s = zlane_sum(f.wsb, 64, f.S, co, valid, red);
+        if (valid && threadIdx.x < 32) f.db[co] = s;
         return;
     }
     const int xi = idx / f.Cout, co = idx - xi * f.Cout;
     const int slot = xi >> 6, row = xi & 63;
-    if (f.slot_skip[slot]) return;
-    float s = 0.f;
-    for (int z = 0; z < f.S; ++z) s += ws[((int64_t)z * KX + xi) * 64 + co];
+    const bool valid = !f.slot_skip[slot];
+    float s = zlane_sum(ws, (int64_t)KX * 64, f.S, (int64_t)xi * 64 + co, valid, red);
+    if (!valid || threadIdx.x >= 32) return;
     s *= f.scale;
     const int tap = f.slot_tap[slot];
     int64_t o;
@@ -997,12 +1064,12 @@ __global__ void __launch_bounds__(256) tc_colsum_partial(const bf16* __restrict_
         part[(int64_t)blockIdx.x * ncols + c] = s;
     }
 }
-__global__ void tc_colsum_final(const float* __restrict__ part, int nblocks, int ncols, float* __restrict__ db) {
-    const int c = blockIdx.x * blockDim.x + threadIdx.x;
-    if (c >= ncols) return;
-    float s = 0.f;
-    for (int b = 0; b < nblocks; ++b) s += part[(int64_t)b * ncols + c];
-    db[c] = s;
+__global__ void __launch_bounds__(256) tc_colsum_final(const float* __restrict__ part, int nblocks, int ncols,
+                                                       float* __restrict__ db) {
+    __shared__ float red[256];
+    const int c = blockIdx.x * 32 + (threadIdx.x & 31);
+    const float s = zlane_sum(part, ncols, nblocks, c, c < ncols, red);
+    if (c < ncols && threadIdx.x < 32) db[c] = s;
 }
 
 // uint8 frames [n,4,84,84] (NCHW, as envpool delivers them) -> space-to-depth bf16 [n,21,21,64] with
@@ -1091,12 +1158,23 @@ __global__ void tc_pack_fc(const float* __restrict__ w, int O, int C, int PP, bf
 }
 
 // ------------------------------------------------------------------ policy/value heads (tiny: CUDA cores, fp32 math)
-// out[n][A1] = hidden[n][512](bf16) . Wh[A1][512]^T + bh.  Head weights staged in smem once per block,
-// one warp per row (16 hidden values per lane, coalesced 64-B loads), rows strided over a persistent grid.
+// A1 = A + 1 head outputs (logits | value), 1 <= A1 <= kMaxHeads.  Head weights live in dynamic shared memory.
+constexpr int kMaxHeads = 32;
+constexpr int kHeadsPartialBlocks = 148;     // row blocks of the head weight gradient (x2 row lanes = partial slabs)
+// rows per block of tc_heads_bwd_weight: its dhead rows are staged in (static-limit) shared memory, <= 256 x 32 floats
+static inline int64_t heads_rows_per_block(int64_t n) {
+    int64_t rpb = (n + kHeadsPartialBlocks - 1) / kHeadsPartialBlocks;
+    if (rpb < 16) rpb = 16;
+    if (rpb > 256) rpb = 256;
+    return rpb;
+}
+
+// out[n][A1] = hidden[n][512](bf16) . Wh[A1][512]^T + bh.  One warp per row: lane l holds hidden units
+// [8l, 8l+8) and [256+8l, 256+8l+8) (two 16-byte loads), weights are read as float4 from shared memory.
 __global__ void __launch_bounds__(256) tc_heads_fwd(const bf16* __restrict__ hid, const float* __restrict__ Wh,
                                                     const float* __restrict__ bh, int64_t n, int A1, int H,
                                                     float* __restrict__ out) {
-    __shared__ float sW[8 * 512];
+    extern __shared__ float sW[];                       // [A1][512]
     for (int i = threadIdx.x; i < A1 * 512; i += blockDim.x) sW[i] = Wh[i];
     __syncthreads();
     const int lane = threadIdx.x & 31, wpb = blockDim.x >> 5;
@@ -1104,100 +1182,132 @@ __global__ void __launch_bounds__(256) tc_heads_fwd(const bf16* __restrict__ hid
         float hv[16];
         const bf16* hp = hid + row * 512;
 #pragma unroll
-        for (int q = 0; q < 16; ++q) hv[q] = __bfloat162float(hp[q * 32 + lane]);
+        for (int q = 0; q < 2; ++q) {
+            const int4 v = ldg16(hp + q * 256 + lane * 8);
+            const uint32_t w[4] = {(uint32_t)v.x, (uint32_t)v.y, (uint32_t)v.z, (uint32_t)v.w};
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                hv[q * 8 + 2 * e] = __uint_as_float(w[e] << 16);
+                hv[q * 8 + 2 * e + 1] = __uint_as_float(w[e] & 0xFFFF0000u);
+            }
+        }
+        float mine = 0.f;                               // lane a keeps output a
         for (int a = 0; a < A1; ++a) {
             float s = 0.f;
 #pragma unroll
-            for (int q = 0; q < 16; ++q) s = fmaf(hv[q], sW[a * 512 + q * 32 + lane], s);
+            for (int q = 0; q < 2; ++q) {
+                const float4 w0 = *reinterpret_cast<const float4*>(sW + a * 512 + q * 256 + lane * 8);
+                const float4 w1 = *reinterpret_cast<const float4*>(sW + a * 512 + q * 256 + lane * 8 + 4);
+                s = fmaf(hv[q * 8 + 0], w0.x, s); s = fmaf(hv[q * 8 + 1], w0.y, s);
+                s = fmaf(hv[q * 8 + 2], w0.z, s); s = fmaf(hv[q * 8 + 3], w0.w, s);
+                s = fmaf(hv[q * 8 + 4], w1.x, s); s = fmaf(hv[q * 8 + 5], w1.y, s);
+                s = fmaf(hv[q * 8 + 6], w1.z, s); s = fmaf(hv[q * 8 + 7], w1.w, s);
+            }
             s = warp_sum(s);
-            if (lane == 0) out[row * A1 + a] = s + bh[a];
+            if (lane == a) mine = s + bh[a];
         }
+        if (lane < A1) out[row * A1 + lane] = mine;     // one coalesced store per row
     }
 }
 // dhid_pre[n][512] (bf16) = (dhead[n][A1] . Wh[A1][512]) * (hid > 0).  Thread = 8 consecutive hidden units of one
-// row (16-byte load of the mask / 16-byte store), head weights staged in smem.
+// row (one mask byte in, one 16-byte store out).  Weights are staged transposed, sWt[a][e][group], so the 32 lanes
+// of a warp (consecutive groups) hit 32 different banks.
 __global__ void __launch_bounds__(256) tc_heads_bwd_data(const float* __restrict__ dhead, const float* __restrict__ Wh,
-                                                         const bf16* __restrict__ hid, int64_t n, int A1, int H,
+                                                         const uint8_t* __restrict__ hid_bits, int64_t n, int A1, int H,
                                                          bf16* __restrict__ dhid) {
-    __shared__ float sW[8 * 512];
-    for (int i = threadIdx.x; i < A1 * 512; i += blockDim.x) sW[i] = Wh[i];
+    extern __shared__ float sWt[];                      // [A1][8][64]
+    for (int i = threadIdx.x; i < A1 * 512; i += blockDim.x) {
+        const int a = i >> 9, h = i & 511;
+        sWt[a * 512 + (h & 7) * 64 + (h >> 3)] = Wh[i];
+    }
     __syncthreads();
     const int64_t total = n * 64;                      // 64 groups of 8 per row
     for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (int64_t)gridDim.x * blockDim.x) {
         const int64_t row = idx >> 6;
-        const int h0 = (int)(idx & 63) * 8;
-        float d[8];
-#pragma unroll
-        for (int a = 0; a < 8; ++a) d[a] = a < A1 ? __ldg(dhead + row * A1 + a) : 0.f;
-        const int4 m = ldg16(hid + row * 512 + h0);
-        const uint32_t mw[4] = {(uint32_t)m.x, (uint32_t)m.y, (uint32_t)m.z, (uint32_t)m.w};
+        const int g = (int)(idx & 63);
+        const uint32_t m = hid_bits[idx];               // bit e: hid[row][8g + e] > 0
         float o[8];
 #pragma unroll
-        for (int e = 0; e < 8; ++e) {
-            float s = 0.f;
+        for (int e = 0; e < 8; ++e) o[e] = 0.f;
+        for (int a = 0; a < A1; ++a) {
+            const float d = __ldg(dhead + row * A1 + a);
 #pragma unroll
-            for (int a = 0; a < 8; ++a) if (a < A1) s = fmaf(d[a], sW[a * 512 + h0 + e], s);
-            const uint32_t half = (e & 1) ? (mw[e >> 1] >> 16) : (mw[e >> 1] & 0xFFFFu);
-            o[e] = (half & 0x7FFFu) && !(half & 0x8000u) ? s : 0.f;     // hid > 0
+            for (int e = 0; e < 8; ++e) o[e] = fmaf(d, sWt[a * 512 + e * 64 + g], o[e]);
         }
+#pragma unroll
+        for (int e = 0; e < 8; ++e) if (!((m >> e) & 1u)) o[e] = 0.f;
         int4 w;
         w.x = (int)pack_bf16x2(o[0], o[1]); w.y = (int)pack_bf16x2(o[2], o[3]);
         w.z = (int)pack_bf16x2(o[4], o[5]); w.w = (int)pack_bf16x2(o[6], o[7]);
-        *reinterpret_cast<int4*>(dhid + row * 512 + h0) = w;
+        *reinterpret_cast<int4*>(dhid + row * 512 + g * 8) = w;
     }
 }
-// dWh[a][h] = sum_m dhead[m][a] * hid[m][h]; dbh[a] = sum_m dhead[m][a]  (partials per row block, then fold)
+// dWh[a][h] = sum_m dhead[m][a] * hid[m][h]; dbh[a] = sum_m dhead[m][a]  (partial slabs per (row block, row lane),
+// folded by tc_heads_fold).  Block = 512 threads = 2 row lanes x 256 hidden pairs; the block's dhead rows are staged
+// in shared memory once, 8 rows of hidden values are in flight per thread.
+template <int MAXA>
 __global__ void __launch_bounds__(512) tc_heads_bwd_weight(const float* __restrict__ dhead, const bf16* __restrict__ hid,
                                                            int64_t n, int A1, int H, int64_t rows_per_block,
                                                            float* __restrict__ part) {
-    // thread -> h ; part[block][a][h] (+ [block][a][H] for the bias)
-    const int h = threadIdx.x;
+    extern __shared__ float sD[];                       // [rows_per_block][A1]
+    const int hp = threadIdx.x & 255, rl = threadIdx.x >> 8;
     const int64_t r0 = (int64_t)blockIdx.x * rows_per_block;
     int64_t r1 = r0 + rows_per_block;
     if (r1 > n) r1 = n;
-    float acc[8], bacc[8];
-    for (int a = 0; a < 8; ++a) { acc[a] = 0.f; bacc[a] = 0.f; }
-    int64_t r = r0;
-    for (; r + 4 <= r1; r += 4) {          // 4 rows in flight per thread
-        float hv[4];
+    const int nrows = (int)(r1 > r0 ? r1 - r0 : 0);
+    for (int i = threadIdx.x; i < nrows * A1; i += blockDim.x) sD[i] = dhead[r0 * A1 + i];
+    __syncthreads();
+    float acc0[MAXA], acc1[MAXA], bacc[MAXA];
 #pragma unroll
-        for (int u = 0; u < 4; ++u) hv[u] = h < H ? __bfloat162float(hid[(r + u) * H + h]) : 0.f;
+    for (int a = 0; a < MAXA; ++a) { acc0[a] = 0.f; acc1[a] = 0.f; bacc[a] = 0.f; }
+    const uint32_t* h2 = reinterpret_cast<const uint32_t*>(hid);      // bf16 pairs
+    int r = rl;
+    for (; r + 14 < nrows; r += 16) {                   // 8 rows (stride 2) in flight
+        uint32_t hv[8];
 #pragma unroll
-        for (int u = 0; u < 4; ++u) {
+        for (int u = 0; u < 8; ++u) hv[u] = __ldg(h2 + (r0 + r + 2 * u) * 256 + hp);
 #pragma unroll
-            for (int a = 0; a < 8; ++a) {
+        for (int u = 0; u < 8; ++u) {
+            const float x0 = __uint_as_float(hv[u] << 16), x1 = __uint_as_float(hv[u] & 0xFFFF0000u);
+            const float* dr = sD + (r + 2 * u) * A1;
+#pragma unroll
+            for (int a = 0; a < MAXA; ++a) {
                 if (a < A1) {
-                    const float d = __ldg(dhead + (r + u) * A1 + a);
-                    acc[a] = fmaf(d, hv[u], acc[a]);
-                    bacc[a] += d;
+                    const float d = dr[a];
+                    acc0[a] = fmaf(d, x0, acc0[a]); acc1[a] = fmaf(d, x1, acc1[a]); bacc[a] += d;
                 }
             }
         }
     }
-    for (; r < r1; ++r) {
-        const float hv = h < H ? __bfloat162float(hid[r * H + h]) : 0.f;
+    for (; r < nrows; r += 2) {
+        const uint32_t hv = __ldg(h2 + (r0 + r) * 256 + hp);
+        const float x0 = __uint_as_float(hv << 16), x1 = __uint_as_float(hv & 0xFFFF0000u);
+        const float* dr = sD + r * A1;
 #pragma unroll
-        for (int a = 0; a < 8; ++a) {
+        for (int a = 0; a < MAXA; ++a) {
             if (a < A1) {
-                const float d = __ldg(dhead + r * A1 + a);
-                acc[a] = fmaf(d, hv, acc[a]);
-                bacc[a] += d;
+                const float d = dr[a];
+                acc0[a] = fmaf(d, x0, acc0[a]); acc1[a] = fmaf(d, x1, acc1[a]); bacc[a] += d;
             }
         }
     }
-    float* pb = part + (int64_t)blockIdx.x * A1 * (H + 1);
-    for (int a = 0; a < A1 && a < 8; ++a) {
-        if (h < H) pb[(int64_t)a * (H + 1) + h] = acc[a];
-        if (h == 0) pb[(int64_t)a * (H + 1) + H] = bacc[a];
+    float* pb = part + ((int64_t)blockIdx.x * 2 + rl) * A1 * (H + 2);      // slab rows: H weights, bias, pad
+#pragma unroll
+    for (int a = 0; a < MAXA; ++a) {
+        if (a < A1) {
+            *reinterpret_cast<float2*>(pb + (int64_t)a * (H + 2) + 2 * hp) = make_float2(acc0[a], acc1[a]);
+            if (hp == 0) pb[(int64_t)a * (H + 2) + H] = bacc[a];
+        }
     }
 }
-__global__ void tc_heads_fold(const float* __restrict__ part, int nblocks, int A1, int H, float* __restrict__ dW,
-                              float* __restrict__ db) {
-    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
-    if (idx >= A1 * (H + 1)) return;
-    float s = 0.f;
-    for (int b = 0; b < nblocks; ++b) s += part[(int64_t)b * A1 * (H + 1) + idx];
-    const int a = idx / (H + 1), h = idx - a * (H + 1);
+__global__ void __launch_bounds__(256) tc_heads_fold(const float* __restrict__ part, int nslabs, int A1, int H,
+                                                     float* __restrict__ dW, float* __restrict__ db) {
+    __shared__ float red[256];
+    const int idx = blockIdx.x * 32 + (threadIdx.x & 31);
+    const int a = idx / (H + 2), h = idx - a * (H + 2);
+    const bool valid = a < A1 && h <= H;                // h == H: bias; h == H + 1: padding
+    const float s = zlane_sum(part, (int64_t)A1 * (H + 2), nslabs, idx, valid, red);
+    if (!valid || threadIdx.x >= 32) return;
     if (h == H) db[a] = s; else dW[(int64_t)a * H + h] = s;
 }
 
@@ -1236,7 +1346,7 @@ struct NatureLayout {
 };
 
 struct NatureActs {   // bf16 element offsets inside the (zero-initialised) activation workspace for batch n
-    int64_t x0, act1, act2, act3, hid, dhid, dact3a, dact3b, dact2a, dact2b, dact1, total;
+    int64_t x0, act1, act2, act3, hid, dhid, dact3a, dact3b, dact2a, dact2b, dact1, m1, m2, m3, m4, total;
     explicit NatureActs(int64_t n, bool with_x0 = true) {
         int64_t o = 0;
         x0 = o; if (with_x0) o += n * 28224;     // space-to-depth frames [n,441,64] (only for uint8 input)
@@ -1250,6 +1360,12 @@ struct NatureActs {   // bf16 element offsets inside the (zero-initialised) acti
         dact2a = o; o += n * 6400;               // d(act2) on the 10x10 linear grid (zeros at row/col 9)
         dact2b = o; o += n * 7744;               // d(act2) zero-padded to 11x11 (interior at +1,+1)
         dact1 = o; o += n * 14112;               // d(act1) on the 21x21 linear grid, 32 channels
+        // ReLU masks as bits (uint32 words; offsets stay in bf16 elements = 2 words per 4 elements)
+        auto pad8 = [](int64_t v) { return (v + 7) & ~int64_t(7); };
+        m1 = o; o += pad8(n * 100 * 4 * 2);      // act1 > 0: [n,100 cells] x 4 words (128 channels)
+        m2 = o; o += pad8(n * 81 * 2 * 2);       // act2 > 0: [n,81] x 2 words
+        m3 = o; o += pad8(n * 49 * 2 * 2);       // act3 > 0: [n,49] x 2 words (= dense [n,3136] / 32)
+        m4 = o; o += pad8(n * 16 * 2);           // hid  > 0: [n] x 16 words
         total = o;
     }
 };
@@ -1331,7 +1447,7 @@ static int colsum(const bf16* Y, int64_t M, int ld, int ncols, float* part, floa
     if (rpb < 64) rpb = 64;
     const int nb = (int)ceil_div(M, rpb);
     tc_colsum_partial<<<nb, 256, 0, s>>>(Y, M, ld, ncols, rpb, part);
-    tc_colsum_final<<<(unsigned)ceil_div(ncols, 128), 128, 0, s>>>(part, nb, ncols, db);
+    tc_colsum_final<<<(unsigned)ceil_div(ncols, 32), 256, 0, s>>>(part, nb, ncols, db);
     return check_launch("colsum", 2);
 }
 static size_t colsum_ws(int64_t M, int ncols) {
@@ -1372,12 +1488,12 @@ extern "C" size_t b200rl_naturecnn_bf16_workspace_bytes(int64_t n, int A) {
     size_t b = 0;
     auto mb = [&](size_t v) { if (v > b) b = v; };
     mb(colsum_ws(n * 441, 32)); mb(colsum_ws(n * 100, 64)); mb(colsum_ws(n * 81, 64)); mb(colsum_ws(n, 512));
-    mb((size_t)296 * (A + 1) * 513 * 4);
+    mb((size_t)2 * ceil_div(n, heads_rows_per_block(n)) * (A + 1) * 514 * 4);
     return a + b + 512;
 }
 
 extern "C" int b200rl_naturecnn_bf16_pack(const float* params, int A, void* packed, void* stream) {
-    B200RL_REQUIRE(params && packed && A >= 1 && A <= 7, "naturecnn_pack: bad arguments (A must be in [1,7])");
+    B200RL_REQUIRE(params && packed && A >= 1 && A < kMaxHeads, "naturecnn_pack: bad arguments (A must be in [1,31])");
     B200RL_REQUIRE(aligned(packed, 16), "naturecnn_pack: packed buffer must be 16-B aligned");
     const NatureLayout L(A);
     bf16* P = reinterpret_cast<bf16*>(packed);
@@ -1397,7 +1513,7 @@ extern "C" int b200rl_naturecnn_bf16_forward(const void* obs, int obs_format, co
     B200RL_REQUIRE(n >= 0, "naturecnn_forward: negative n");
     if (n == 0) return B200RL_OK;
     B200RL_REQUIRE(obs && params && packed && acts && head_out, "naturecnn_forward: null pointer");
-    B200RL_REQUIRE(A >= 1 && A <= 7, "naturecnn_forward: A=%d outside [1,7]", A);
+    B200RL_REQUIRE(A >= 1 && A < kMaxHeads, "naturecnn_forward: A=%d outside [1,31]", A);
     B200RL_REQUIRE(obs_format == B200RL_OBS_U8_NCHW || obs_format == B200RL_OBS_S2D_BF16, "naturecnn_forward: bad obs_format %d", obs_format);
     B200RL_REQUIRE(aligned(obs, 16) && aligned(acts, 16) && aligned(packed, 16), "naturecnn_forward: misaligned buffer");
     B200RL_REQUIRE(n <= (int64_t)1 << 22, "naturecnn_forward: n too large");
@@ -1418,24 +1534,25 @@ extern "C" int b200rl_naturecnn_bf16_forward(const void* obs, int obs_format, co
     }
     win_defaults(wp); win_conv1(wp, x0, x0rows, n);
     wp.Bw = P + L.w1f; wp.N = 32; wp.vH = 20; wp.vW = 20; wp.out_mode = WOUT_S2D2; wp.out = act + Q.act1;
-    wp.bias = params + L.c1b; wp.scale = 1.0f / 255.0f; wp.relu = 1;
-    { ProfScope ps(s, "conv1_fwd", 2.0 * n * 400 * 32 * 256, (double)n * (28224 + 12800) * 2);
-      if ((rc = launch_conv_win<32, 1, 6>(wp, s, "naturecnn/conv1"))) return rc; }
+    wp.bias = params + L.c1b; wp.scale = 1.0f / 255.0f; wp.relu = 1; wp.mask_out = reinterpret_cast<uint32_t*>(act + Q.m1);
+    { ProfScope ps(s, "conv1_fwd", 2.0 * n * 400 * 32 * 256, (double)n * ((28224 + 12800) * 2 + 1600));
+      if ((rc = launch_conv_win<32, 1, 6, 4>(wp, s, "naturecnn/conv1"))) return rc; }
     // conv2: 2x2 window conv on the 128-channel cells -> act2 [n,9,9,64]
     win_defaults(wp); win_conv2(wp, act + Q.act1, n);
     wp.Bw = P + L.w2f; wp.N = 64; wp.vH = 9; wp.vW = 9; wp.out_mode = WOUT_DENSE; wp.out = act + Q.act2;
-    wp.bias = params + L.c2b; wp.relu = 1;
-    { ProfScope ps(s, "conv2_fwd", 2.0 * n * 81 * 64 * 512, (double)n * (12800 + 5184) * 2);
-      if ((rc = launch_conv_win<64, 2, 4>(wp, s, "naturecnn/conv2"))) return rc; }
+    wp.bias = params + L.c2b; wp.relu = 1; wp.mask_out = reinterpret_cast<uint32_t*>(act + Q.m2);
+    { ProfScope ps(s, "conv2_fwd", 2.0 * n * 81 * 64 * 512, (double)n * ((12800 + 5184) * 2 + 648));
+      if ((rc = launch_conv_win<64, 2, 4, 4>(wp, s, "naturecnn/conv2"))) return rc; }
     // conv3: 3x3 window conv -> act3 [n,7,7,64]
     win_defaults(wp); win_conv3(wp, act + Q.act2, n);
     wp.Bw = P + L.w3f; wp.N = 64; wp.vH = 7; wp.vW = 7; wp.out_mode = WOUT_DENSE; wp.out = act + Q.act3;
-    wp.bias = params + L.c3b; wp.relu = 1;
-    { ProfScope ps(s, "conv3_fwd", 2.0 * n * 49 * 64 * 576, (double)n * (5184 + 3136) * 2);
-      if ((rc = launch_conv_win<64, 1, 6>(wp, s, "naturecnn/conv3"))) return rc; }
+    wp.bias = params + L.c3b; wp.relu = 1; wp.mask_out = reinterpret_cast<uint32_t*>(act + Q.m3);
+    { ProfScope ps(s, "conv3_fwd", 2.0 * n * 49 * 64 * 576, (double)n * ((5184 + 3136) * 2 + 392));
+      if ((rc = launch_conv_win<64, 1, 6, 9>(wp, s, "naturecnn/conv3"))) return rc; }
     // fc -> hidden [n,512]
     gemm_defaults(p); rowmajor_gather(p, act + Q.act3, n, 49);
     p.Bw = P + L.wfcf; p.N = 512; p.out = act + Q.hid; p.OH = 1; p.OW = 1; p.ldo = 512; p.bias = params + L.fcb; p.relu = 1;
+    p.mask_out = reinterpret_cast<uint32_t*>(act + Q.m4);
     { ProfScope ps(s, "fc_fwd", 2.0 * n * 512 * 3136, (double)n * (3136 + 512) * 2 + 512.0 * 3136 * 2);
       // small batches (rollout step): narrower N tiles => 4x more CTAs for the same work
       if (n <= 8192) { if ((rc = launch_gemm_tma<64, 8>(p, s, "naturecnn/fc"))) return rc; }
@@ -1443,7 +1560,7 @@ extern "C" int b200rl_naturecnn_bf16_forward(const void* obs, int obs_format, co
     // heads (fp32 math on CUDA cores): head_out [n, A+1] = [logits | value]
     { ProfScope ps(s, "heads_fwd", 2.0 * n * 512 * (A + 1), (double)n * (1024 + 4 * (A + 1)));
       int hb = (int)ceil_div(n, 8); if (hb > num_sms() * 8) hb = num_sms() * 8;
-      tc_heads_fwd<<<hb, 256, 0, s>>>(act + Q.hid, params + L.hw, params + L.hb, n, A + 1, 512, head_out); }
+      tc_heads_fwd<<<hb, 256, (size_t)(A + 1) * 2048, s>>>(act + Q.hid, params + L.hw, params + L.hb, n, A + 1, 512, head_out); }
     return check_launch("naturecnn/heads");
 }
 
@@ -1453,7 +1570,7 @@ extern "C" int b200rl_naturecnn_bf16_backward(const void* obs, int obs_format, c
                                               void* workspace, size_t workspace_bytes, void* stream) {
     B200RL_REQUIRE(n >= 1, "naturecnn_backward: n must be >= 1");
     B200RL_REQUIRE(obs && params && packed && acts && dhead && grads && workspace, "naturecnn_backward: null pointer");
-    B200RL_REQUIRE(A >= 1 && A <= 7, "naturecnn_backward: A=%d outside [1,7]", A);
+    B200RL_REQUIRE(A >= 1 && A < kMaxHeads, "naturecnn_backward: A=%d outside [1,31]", A);
     B200RL_REQUIRE(aligned(workspace, 16), "naturecnn_backward: workspace misaligned");
     const size_t need = b200rl_naturecnn_bf16_workspace_bytes(n, A);
     if (workspace_bytes < need) return fail(B200RL_ERR_WORKSPACE, "naturecnn_backward: workspace %zu < %zu", workspace_bytes, need);
@@ -1482,14 +1599,15 @@ extern "C" int b200rl_naturecnn_bf16_backward(const void* obs, int obs_format, c
     const int A1 = A + 1;
     // ---- heads: dW, db, then dhid_pre = (dhead . Wh) * (hid > 0)
     {
-        int64_t rpb = ceil_div(n, 296);
-        if (rpb < 8) rpb = 8;
+        const int64_t rpb = heads_rows_per_block(n);
         const int nb = (int)ceil_div(n, rpb);
-        ProfScope ps(s, "heads_bwd", 4.0 * n * 512 * A1, (double)n * (2048 + 8 * A1));
-        tc_heads_bwd_weight<<<nb, 512, 0, s>>>(dhead, act + Q.hid, n, A1, 512, rpb, wssmall);
-        tc_heads_fold<<<(unsigned)ceil_div(A1 * 513, 128), 128, 0, s>>>(wssmall, nb, A1, 512, grads + L.hw, grads + L.hb);
+        ProfScope ps(s, "heads_bwd", 4.0 * n * 512 * A1, (double)n * (2048 + 64 + 8 * A1));
+        const size_t sd = (size_t)rpb * A1 * sizeof(float);
+        if (A1 <= 8) tc_heads_bwd_weight<8><<<nb, 512, sd, s>>>(dhead, act + Q.hid, n, A1, 512, rpb, wssmall);
+        else tc_heads_bwd_weight<kMaxHeads><<<nb, 512, sd, s>>>(dhead, act + Q.hid, n, A1, 512, rpb, wssmall);
+        tc_heads_fold<<<(unsigned)ceil_div(A1 * 514, 32), 256, 0, s>>>(wssmall, 2 * nb, A1, 512, grads + L.hw, grads + L.hb);
         int db_blocks = (int)ceil_div(n * 64, 256); if (db_blocks > num_sms() * 8) db_blocks = num_sms() * 8;
-        tc_heads_bwd_data<<<db_blocks, 256, 0, s>>>(dhead, params + L.hw, act + Q.hid, n, A1, 512, act + Q.dhid);
+        tc_heads_bwd_data<<<db_blocks, 256, (size_t)A1 * 2048, s>>>(dhead, params + L.hw, reinterpret_cast<const uint8_t*>(act + Q.m4), n, A1, 512, act + Q.dhid);
         if ((rc = check_launch("naturecnn/heads_bwd", 3))) return rc;
     }
     KGemmParams p;
@@ -1515,8 +1633,8 @@ extern "C" int b200rl_naturecnn_bf16_backward(const void* obs, int obs_format, c
         // dact3_pre = (dhid . Wfc) * (act3 > 0), written on the 9x9 linear grid and the zero-padded 11x11 grid
         gemm_defaults(p); rowmajor_gather(p, act + Q.dhid, n, 8);
         p.Bw = P + L.wfcdg; p.N = 3136; p.out = act + Q.dact3a; p.out2 = act + Q.dact3b; p.dual_dact3 = 1;
-        p.OH = 1; p.OW = 1; p.ldo = 3136; p.mask = act + Q.act3;
-        { ProfScope ps(s, "fc_dgrad", 2.0 * n * 512 * 3136, (double)n * (3136 * 2 + 512) * 2 + 512.0 * 3136 * 2);
+        p.OH = 1; p.OW = 1; p.ldo = 3136; p.mask_bits = reinterpret_cast<const uint32_t*>(act + Q.m3);
+        { ProfScope ps(s, "fc_dgrad", 2.0 * n * 512 * 3136, (double)n * ((3136 + 512) * 2 + 392) + 512.0 * 3136 * 2);
           if ((rc = launch_gemm_tma<256, 4>(p, s, "naturecnn/fc_dgrad"))) return rc; }
     }
     WGradWinParams gw;
@@ -1539,16 +1657,16 @@ extern "C" int b200rl_naturecnn_bf16_backward(const void* obs, int obs_format, c
         for (int k = 0; k < 10; ++k) { fw.slot_tap[k] = st[k]; fw.slot_skip[k] = (k == 8); }
         { ProfScope ps(s, "wgrad_fold_bias", 0, 0);
           fw.wsb = wssmall; fw.db = grads + L.c3b;
-          tc_fold_win<<<(unsigned)ceil_div(640 * 64 + 64, 256), 256, 0, s>>>(wsbig, fw, grads + L.c3w);
+          tc_fold_win<<<(unsigned)ceil_div(640 * 64 + 64, 32), 256, 0, s>>>(wsbig, fw, grads + L.c3w);
           if ((rc = check_launch("naturecnn/conv3_fold"))) return rc; }
         win_defaults(wp);
         wp.A = act + Q.dact3b; wp.n = (int)n; wp.G = 121; wp.Wp = 11; wp.M = n * 121; wp.ntaps = 9;
         for (int ky = 0; ky < 3; ++ky) for (int kx = 0; kx < 3; ++kx) wp.shift[ky * 3 + kx] = (2 - ky) * 11 + (2 - kx);
         wp.WR = round8(128 + 24);
         wp.Bw = P + L.w3dg; wp.N = 64; wp.vH = 9; wp.vW = 9; wp.out_mode = WOUT_DACT2;
-        wp.out = act + Q.dact2a; wp.out2 = act + Q.dact2b; wp.mask = act + Q.act2;
-        { ProfScope ps(s, "conv3_dgrad", 2.0 * n * 81 * 64 * 576, (double)n * (7744 + 5184 + 6400 + 7744) * 2);
-          if ((rc = launch_conv_win<64, 1, 6>(wp, s, "naturecnn/conv3_dgrad"))) return rc; }
+        wp.out = act + Q.dact2a; wp.out2 = act + Q.dact2b; wp.mask_bits = reinterpret_cast<const uint32_t*>(act + Q.m2);
+        { ProfScope ps(s, "conv3_dgrad", 2.0 * n * 81 * 64 * 576, (double)n * ((7744 + 6400 + 7744) * 2 + 648));
+          if ((rc = launch_conv_win<64, 1, 6, 9>(wp, s, "naturecnn/conv3_dgrad"))) return rc; }
     }
     // ---- conv2: dW from act1 cell windows x dact2 (10x10 grid); dact1 = one N=128 GEMM over the 4 stride-parity
     //      classes (the 4 channel groups of a cell)
@@ -1567,16 +1685,16 @@ extern "C" int b200rl_naturecnn_bf16_backward(const void* obs, int obs_format, c
         for (int k = 0; k < 8; ++k) { fw.slot_tap[k] = k >> 1; fw.slot_cc[k] = k & 1; }
         { ProfScope ps(s, "wgrad_fold_bias", 0, 0);
           fw.wsb = wssmall; fw.db = grads + L.c2b;
-          tc_fold_win<<<(unsigned)ceil_div(512 * 64 + 64, 256), 256, 0, s>>>(wsbig, fw, grads + L.c2w);
+          tc_fold_win<<<(unsigned)ceil_div(512 * 64 + 64, 32), 256, 0, s>>>(wsbig, fw, grads + L.c2w);
           if ((rc = check_launch("naturecnn/conv2_fold"))) return rc; }
         win_defaults(wp);
         wp.A = act + Q.dact2b; wp.n = (int)n; wp.G = 121; wp.Wp = 11; wp.M = n * 121; wp.ntaps = 4;
         for (int a = 0; a < 2; ++a) for (int b = 0; b < 2; ++b) wp.shift[a * 2 + b] = (1 - a) * 11 + (1 - b);
         wp.WR = round8(128 + 12);
         wp.Bw = P + L.w2dg; wp.N = 128; wp.vH = 10; wp.vW = 10; wp.out_mode = WOUT_DACT1;
-        wp.out = act + Q.dact1; wp.mask = act + Q.act1;
-        { ProfScope ps(s, "conv2_dgrad", 2.0 * n * 400 * 32 * 256, (double)n * (7744 + 12800 + 14112) * 2);
-          if ((rc = launch_conv_win<128, 1, 6>(wp, s, "naturecnn/conv2_dgrad"))) return rc; }
+        wp.out = act + Q.dact1; wp.mask_bits = reinterpret_cast<const uint32_t*>(act + Q.m1);
+        { ProfScope ps(s, "conv2_dgrad", 2.0 * n * 400 * 32 * 256, (double)n * ((7744 + 14112) * 2 + 1600));
+          if ((rc = launch_conv_win<128, 1, 6, 4>(wp, s, "naturecnn/conv2_dgrad"))) return rc; }
     }
     // ---- conv1 (no data gradient: the input is the observation)
     {
@@ -1594,7 +1712,7 @@ extern "C" int b200rl_naturecnn_bf16_backward(const void* obs, int obs_format, c
         for (int k = 0; k < 4; ++k) fw.slot_tap[k] = k;
         { ProfScope ps(s, "wgrad_fold_bias", 0, 0);
           fw.wsb = wssmall; fw.db = grads + L.c1b;
-          tc_fold_win<<<(unsigned)ceil_div(256 * 32 + 32, 256), 256, 0, s>>>(wsbig, fw, grads + L.c1w);
+          tc_fold_win<<<(unsigned)ceil_div(256 * 32 + 32, 32), 256, 0, s>>>(wsbig, fw, grads + L.c1w);
           if ((rc = check_launch("naturecnn/conv1_fold"))) return rc; }
     }
     return B200RL_OK;

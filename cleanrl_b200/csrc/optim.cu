@@ -51,9 +51,18 @@ __global__ void __launch_bounds__(kOptThreads) grad_sumsq_kernel(
     __syncthreads();
     if (!is_last) return;
     __threadfence();
+    // last block: fixed-order two-level sum of the block partials (thread t takes t, t+256, ...; then lanes in order)
+    __shared__ double dred[kOptThreads];
+    double mine = 0.0;
+    for (unsigned b = threadIdx.x; b < gridDim.x; b += blockDim.x) mine += __ldcg(partials + b);
+    dred[threadIdx.x] = mine;
+    __syncthreads();
+    for (unsigned off = kOptThreads / 2; off > 0; off >>= 1) {
+        if (threadIdx.x < off) dred[threadIdx.x] += dred[threadIdx.x + off];
+        __syncthreads();
+    }
     if (threadIdx.x == 0) {
-        double tot = 0.0;
-        for (unsigned b = 0; b < gridDim.x; ++b) tot += __ldcg(partials + b);
+        const double tot = dred[0];
         const float norm = (float)sqrt(tot);
         sc->norm = norm;
         float coef = 1.f;

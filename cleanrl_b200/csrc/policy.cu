@@ -84,19 +84,39 @@ __global__ void __launch_bounds__(128) categorical_eval_kernel(
     if (entropy) entropy[i] = -ent;
 }
 
-// ---- advantage statistics of the gathered minibatch (single block, 2 passes)
+// ---- advantage statistics of the gathered minibatch (single block, 2 passes).
+// Loads are issued 8 at a time per thread (independent index -> value chains in flight), but every thread still
+// accumulates its strided elements in ascending order, so the result does not depend on the batching.
+__device__ __forceinline__ float adv_pass(const float* __restrict__ b_adv, const int64_t* __restrict__ inds, int64_t M,
+                                          float mean, bool squared) {
+    float s = 0.f;
+    const int64_t step = blockDim.x;
+    int64_t i = threadIdx.x;
+    for (; i + 7 * step < M; i += 8 * step) {
+        int64_t j[8];
+        float v[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) j[u] = inds ? __ldg(inds + i + u * step) : i + u * step;
+#pragma unroll
+        for (int u = 0; u < 8; ++u) v[u] = __ldg(b_adv + j[u]);
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+            const float d = v[u] - mean;
+            s += squared ? d * d : v[u];
+        }
+    }
+    for (; i < M; i += step) {
+        const float v = b_adv[inds ? inds[i] : i];
+        const float d = v - mean;
+        s += squared ? d * d : v;
+    }
+    return s;
+}
 __global__ void __launch_bounds__(1024) adv_stats_kernel(
     const float* __restrict__ b_adv, const int64_t* __restrict__ inds, int64_t M, float* __restrict__ out2) {
     __shared__ float red[32];
-    float s = 0.f;
-    for (int64_t i = threadIdx.x; i < M; i += blockDim.x) s += b_adv[inds ? inds[i] : i];
-    const float mean = block_sum(s, red) / (float)M;
-    float q = 0.f;
-    for (int64_t i = threadIdx.x; i < M; i += blockDim.x) {
-        const float d = b_adv[inds ? inds[i] : i] - mean;
-        q += d * d;
-    }
-    const float ss = block_sum(q, red);
+    const float mean = block_sum(adv_pass(b_adv, inds, M, 0.f, false), red) / (float)M;
+    const float ss = block_sum(adv_pass(b_adv, inds, M, mean, true), red);
     if (threadIdx.x == 0) {
         out2[0] = mean;
         out2[1] = sqrtf(ss / (float)(M - 1));  // unbiased, torch.std default

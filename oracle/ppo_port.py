@@ -49,22 +49,27 @@ class RefAgent(nn.Module):
 
 def run(num_envs=8, num_steps=32, num_iterations=2, seed=1, env_mode="fresh", num_minibatches=4, update_epochs=4,
         learning_rate=2.5e-4, gamma=0.99, gae_lambda=0.95, clip_coef=0.1, ent_coef=0.01, vf_coef=0.5,
-        max_grad_norm=0.5, anneal_lr=True, total_iterations=None, threads=None, log=None):
-    """Run ``num_iterations`` PPO iterations on CPU; returns dict(per-iteration losses, sps, seconds)."""
+        max_grad_norm=0.5, anneal_lr=True, total_iterations=None, threads=None, log=None, device="cpu"):
+    """Run ``num_iterations`` PPO iterations; returns dict(per-iteration losses, sps, seconds).
+
+    device="cpu" is the CPU baseline; device="cuda" reproduces what the reference does with --cuda (fp32 rollout
+    storage on the device, eager torch/cuDNN ops, per-step .cpu() sync) for tools/ref_eager_gpu.py."""
+    device = torch.device(device)
     import random
     if threads:
         torch.set_num_threads(threads)
     random.seed(seed); np.random.seed(seed); torch.manual_seed(seed)
     envs = SyntheticAtariVec(num_envs, seed=seed, mode=env_mode)
-    agent = RefAgent(envs.action_space.n)
+    agent = RefAgent(envs.action_space.n).to(device)
     opt = torch.optim.Adam(agent.parameters(), lr=learning_rate, eps=1e-5)
     T, N = num_steps, num_envs
     B = T * N
     M = B // num_minibatches
     total_iterations = total_iterations or num_iterations
-    obs = torch.zeros((T, N, 4, 84, 84)); actions = torch.zeros((T, N)); logprobs = torch.zeros((T, N))
-    rewards = torch.zeros((T, N)); dones = torch.zeros((T, N)); values = torch.zeros((T, N))
-    next_obs = torch.Tensor(envs.reset()); next_done = torch.zeros(N)
+    obs = torch.zeros((T, N, 4, 84, 84)).to(device); actions = torch.zeros((T, N)).to(device)
+    logprobs = torch.zeros((T, N)).to(device); rewards = torch.zeros((T, N)).to(device)
+    dones = torch.zeros((T, N)).to(device); values = torch.zeros((T, N)).to(device)
+    next_obs = torch.Tensor(envs.reset()).to(device); next_done = torch.zeros(N).to(device)
     out = {"losses": [], "iter_seconds": []}
     t_start = time.time()
     for it in range(1, num_iterations + 1):
@@ -77,9 +82,9 @@ def run(num_envs=8, num_steps=32, num_iterations=2, seed=1, env_mode="fresh", nu
                 a, lp, _, v = agent.get_action_and_value(next_obs)
                 values[step] = v.flatten()
             actions[step] = a; logprobs[step] = lp
-            o, r, d, info = envs.step(a.numpy())
-            rewards[step] = torch.tensor(r).view(-1)
-            next_obs, next_done = torch.Tensor(o), torch.Tensor(d)
+            o, r, d, info = envs.step(a.cpu().numpy())
+            rewards[step] = torch.tensor(r).to(device).view(-1)
+            next_obs, next_done = torch.Tensor(o).to(device), torch.Tensor(d).to(device)
         with torch.no_grad():
             next_value = agent.get_value(next_obs).reshape(1, -1)
             adv = torch.zeros_like(rewards); last = 0
@@ -110,6 +115,8 @@ def run(num_envs=8, num_steps=32, num_iterations=2, seed=1, env_mode="fresh", nu
                 nn.utils.clip_grad_norm_(agent.parameters(), max_grad_norm)
                 opt.step()
         out["losses"].append(dict(pg_loss=pg.item(), v_loss=vl.item(), entropy=el.item()))
+        if device.type == "cuda":
+            torch.cuda.synchronize()
         out["iter_seconds"].append(time.time() - t0)
         if log:
             log(f"[cpu port] iteration {it}: {B / out['iter_seconds'][-1]:.0f} SPS")

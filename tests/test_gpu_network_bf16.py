@@ -32,7 +32,7 @@ def _bf16_round(t):
     return t.to(torch.bfloat16).float()
 
 
-@pytest.mark.parametrize("n,B,A", [(24, 64, 4), (130, 130, 6), (1, 3, 4)])
+@pytest.mark.parametrize("n,B,A", [(24, 64, 4), (130, 130, 6), (1, 3, 4), (300, 300, 18), (70, 70, 9)])
 def test_bf16_forward_backward_layerwise(lib, n, B, A):
     from cleanrl_b200.agents import NatureCNNAgent
     torch.manual_seed(1)
