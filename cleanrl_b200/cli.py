@@ -89,6 +89,12 @@ def ppo_atari_envpool_args(exp_name="ppo_atari_envpool"):
     return _make("Args", _override(_COMMON, exp_name=exp_name) + algo + _RUNTIME + _EXTRA)
 
 
+def ppo_atari_args(exp_name="ppo_atari"):
+    """cleanrl/ppo_atari.py:20-90."""
+    algo = _override(_ALGO, env_id="BreakoutNoFrameskip-v4", total_timesteps=10000000, num_envs=8, clip_coef=0.1)
+    return _make("Args", _override(_COMMON, exp_name=exp_name) + algo + _RUNTIME + _EXTRA)
+
+
 def ppo_atari_multigpu_args(exp_name="ppo_atari_multigpu"):
     algo = _override(_ALGO, env_id="BreakoutNoFrameskip-v4", total_timesteps=10000000, clip_coef=0.1)
     algo = [r if r[0] != "num_envs" else

@@ -85,6 +85,11 @@ struct WinParams {
     const int64_t* rows;     // optional image gather (conv1 reads the rollout through mb_inds)
     int64_t M;               // n*G
     int n, G, Wp;
+    // image-aligned tiling (conv1): every image owns 2^tpi_shift tiles of 128 grid rows (rows >= G are padding),
+    // so a window never spans two images and the minibatch gather is just the TMA box's image coordinate.
+    // 0 = tiles walk the linear grid [n*G] (activations produced by this library, always contiguous).
+    int tpi_shift;
+    int64_t n_images;        // images addressable through `rows` (size of the tensor map's outer dimension)
     int ntaps;
     int shift[16];           // dy*Wp + dx per tap (non-negative)
     int WR;                  // window rows: 128 + max shift, rounded up to 8
@@ -106,7 +111,6 @@ struct WinParams {
 template <int BN, int CPR, int STAGES, int NTAPS>
 __global__ void __launch_bounds__(416, 1) tc_conv_win(const __grid_constant__ CUtensorMap tmA, const WinParams p,
                                                       int total_tiles) {
-    constexpr int LOOKAHEAD = STAGES - 2;
     constexpr int B_CHUNK = BN * 128;
     constexpr uint32_t TMEM_COLS = (2 * BN) < 32 ? 32 : 2 * BN;
     extern __shared__ uint8_t smem_raw[];
@@ -122,11 +126,10 @@ __global__ void __launch_bounds__(416, 1) tc_conv_win(const __grid_constant__ CU
     uint8_t* sRing = smem + (size_t)nchunks * B_CHUNK;
 
     if (tid == 0) {
-        // window producers: one TMA issuer (expect_tx arrival) when rows are contiguous, 4 cp.async warps for the gather
-        for (int s = 0; s < STAGES; ++s) { mbar_init(&full_bar[s], p.rows ? 4 : 1); mbar_init(&empty_bar[s], 1); }
+        for (int s = 0; s < STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
         for (int a = 0; a < 2; ++a) { mbar_init(&tfull_bar[a], 1); mbar_init(&tempty_bar[a], 4); }
         fence_barrier_init();
-        if (!p.rows) tma_prefetch_desc(&tmA);
+        tma_prefetch_desc(&tmA);
     }
     if (warp == 4) tmem_alloc(&tmem_base_smem, TMEM_COLS);
     for (int idx = tid; idx < nchunks * BN * 8; idx += blockDim.x) {
@@ -147,76 +150,37 @@ __global__ void __launch_bounds__(416, 1) tc_conv_win(const __grid_constant__ CU
     const int tile_begin = (int)(((int64_t)total_tiles * blockIdx.x) / gridDim.x);
     const int tile_end = (int)(((int64_t)total_tiles * (blockIdx.x + 1)) / gridDim.x);
 
-    if (warp < 4 && !p.rows) {
+    if (warp < 4) {
         // ======================= TMA producer: the window is one rectangular box per 64-channel column chunk ====
         if (tid == 0) {
             uint32_t q = 0;
+            const int tmask = (1 << p.tpi_shift) - 1;
+            // image-aligned mode: the box's image coordinate is the (optional) minibatch gather; the index of the
+            // NEXT tile's image is fetched one tile ahead so the dependent load never delays a TMA issue
+            int z_next = 0;
+            if (p.tpi_shift && tile_begin < tile_end) {
+                const int img = tile_begin >> p.tpi_shift;
+                z_next = p.rows ? (int)__ldg(p.rows + img) : img;
+            }
             for (int tile = tile_begin; tile < tile_end; ++tile, ++q) {
                 const uint32_t s = q % STAGES;
+                const int z = z_next;
+                if (p.tpi_shift && tile + 1 < tile_end) {
+                    const int img = (tile + 1) >> p.tpi_shift;
+                    z_next = p.rows ? (int)__ldg(p.rows + img) : img;
+                }
                 if (q >= (uint32_t)STAGES) mbar_wait(&empty_bar[s], ((q / STAGES) - 1) & 1);
                 const uint32_t dst = smem_u32(sRing + (size_t)s * STAGE_BYTES);
                 mbar_arrive_expect_tx(&full_bar[s], (uint32_t)STAGE_BYTES);
+                if (p.tpi_shift) {
 #pragma unroll
-                for (int c = 0; c < CPR; ++c) tma_load_2d(dst + c * IMG, &tmA, c * 64, tile * 128, &full_bar[s]);
-            }
-        }
-    } else if (warp < 4) {
-        // ======================= cp.async producers (image gather): one window per tile =======================
-        constexpr int PPR = CPR * 8;               // 16-byte pieces per grid row
-        constexpr int RSTEP = 128 / PPR;           // rows advanced per pass of the 128 producer threads
-        const int wr0 = tid / PPR, pc = tid % PPR;
-        const int cc = pc >> 3, c16 = pc & 7;
-        uint32_t q = 0;
-        // image gather (conv1 reads the rollout through mb_inds): a window spans at most two images (WR < G);
-        // their indices are fetched ONE TILE AHEAD so the dependent global load never stalls cp.async issue
-        int64_t nimg0 = 0, nimg1 = 0;
-        if (p.rows && tile_begin < tile_end) {
-            const int64_t i0 = ((int64_t)tile_begin * 128) / p.G;
-            nimg0 = i0 < p.n ? __ldg(p.rows + i0) : 0;
-            nimg1 = i0 + 1 < p.n ? __ldg(p.rows + i0 + 1) : 0;
-        }
-        for (int tile = tile_begin; tile < tile_end; ++tile, ++q) {
-            const uint32_t s = q % STAGES;
-            const int64_t row0 = (int64_t)tile * 128;
-            const int64_t cimg0 = nimg0, cimg1 = nimg1;
-            int64_t ibase = 0;
-            if (p.rows) {
-                ibase = row0 / p.G;
-                const int ntile = tile + 1;
-                if (ntile < tile_end) {
-                    const int64_t i0 = ((int64_t)ntile * 128) / p.G;
-                    nimg0 = i0 < p.n ? __ldg(p.rows + i0) : 0;
-                    nimg1 = i0 + 1 < p.n ? __ldg(p.rows + i0 + 1) : 0;
+                    for (int c = 0; c < CPR; ++c) tma_load_3d(dst + c * IMG, &tmA, c * 64, (tile & tmask) * 128, z, &full_bar[s]);
+                } else {
+#pragma unroll
+                    for (int c = 0; c < CPR; ++c) tma_load_2d(dst + c * IMG, &tmA, c * 64, tile * 128, &full_bar[s]);
                 }
             }
-            if (q >= (uint32_t)STAGES) mbar_wait(&empty_bar[s], ((q / STAGES) - 1) & 1);
-            const uint32_t sA = smem_u32(sRing + (size_t)s * STAGE_BYTES) + cc * IMG;
-            int64_t r = row0 + wr0;
-            // row -> source pointer with one compare + select + multiply-add per row: the window lies in at most
-            // two images, whose bases (pre-biased so that `rem` indexes both) are computed once per tile
-            int rem = p.rows ? (int)(r - ibase * p.G) : 0;
-            const bf16* base0 = p.rows ? p.A + (cimg0 * p.G) * (int64_t)(CPR * 64) + pc * 8 : p.A + row0 * (int64_t)(CPR * 64) + pc * 8;
-            const bf16* base1 = p.rows ? p.A + ((cimg1 - 1) * p.G) * (int64_t)(CPR * 64) + pc * 8 : base0;
-            if (!p.rows) rem = wr0;
-            const int64_t rows_left = p.M - row0;           // rows of this window that exist at all
-            for (int wr = wr0; wr < p.WR; wr += RSTEP, rem += RSTEP) {
-                const bool ok = wr < rows_left;
-                const bf16* src = ((p.rows && rem >= p.G) ? base1 : base0) + (int64_t)rem * (CPR * 64);
-                cp_async16(sA + img_off(wr, c16), ok ? src : p.A, ok ? 16u : 0u);
-            }
-            cp_async_commit();
-            if (q >= (uint32_t)LOOKAHEAD) {
-                cp_async_wait<LOOKAHEAD>();
-                fence_proxy_async_smem();
-                __syncwarp();
-                if ((tid & 31) == 0) mbar_arrive(&full_bar[(q - LOOKAHEAD) % STAGES]);
-            }
         }
-        cp_async_wait<0>();
-        fence_proxy_async_smem();
-        __syncwarp();
-        if ((tid & 31) == 0)
-            for (uint32_t d = (q >= (uint32_t)LOOKAHEAD ? q - LOOKAHEAD : 0); d < q; ++d) mbar_arrive(&full_bar[d % STAGES]);
     } else if (warp == 4) {
         // ======================= MMA issuer: the WHOLE warp walks the tile loop (uniform control flow keeps the
         // descriptor arithmetic in uniform registers), one elected lane issues.  Descriptors differ from a per-stage /
@@ -262,15 +226,23 @@ __global__ void __launch_bounds__(416, 1) tc_conv_win(const __grid_constant__ CU
         const int lrow = ew * 32 + (tid & 31);
         const uint32_t mW = (65536u + (uint32_t)p.Wp - 1u) / (uint32_t)p.Wp;
         const int step_i = 256 / p.G, step_rem = 256 % p.G;
-        int64_t r = ((int64_t)tile_begin + h) * 128 + lrow;
-        int i = (int)(r / p.G);
-        int rem = (int)(r - (int64_t)i * p.G);
+        int64_t r = ((int64_t)tile_begin + h) * 128 + lrow;      // linear-grid mode state (unused when image-aligned)
+        int i_lin = (int)(r / p.G);
+        int rem_lin = (int)(r - (int64_t)i_lin * p.G);
+        const int tmask = (1 << p.tpi_shift) - 1;
         const uint32_t lane_addr = tmem_d + h * BN + ((uint32_t)(ew * 32) << 16);
         constexpr int NW = BN / 32;                          // 32-column groups = mask words per row
         uint32_t k = 0;                                      // use count of accumulator buffer h
         for (int tile = tile_begin + h; tile < tile_end; tile += 2, ++k) {
+            int i = i_lin, rem = rem_lin;
+            bool inside = r < p.M;
+            if (p.tpi_shift) {                               // image-aligned tiles: rows >= G of an image are padding
+                i = tile >> p.tpi_shift;
+                rem = ((tile & tmask) << 7) + lrow;
+                inside = rem < p.G;
+            }
             const int Y = (int)(((uint32_t)rem * mW) >> 16), X = rem - Y * p.Wp;
-            const bool valid = (r < p.M) && (Y < p.vH) && (X < p.vW);
+            const bool valid = inside && (Y < p.vH) && (X < p.vW);
             int64_t o1 = 0, o2 = 0, ob = 0;
             if (p.out_mode == WOUT_DENSE) {
                 const int64_t orow = ((int64_t)i * p.vH + Y) * p.vW + X;
@@ -364,8 +336,8 @@ __global__ void __launch_bounds__(416, 1) tc_conv_win(const __grid_constant__ CU
                     dst2[0] = w[0]; dst2[1] = w[1]; dst2[2] = w[2]; dst2[3] = w[3];
                 }
             }
-            r += 256; i += step_i; rem += step_rem;
-            if (rem >= p.G) { rem -= p.G; ++i; }
+            r += 256; i_lin += step_i; rem_lin += step_rem;
+            if (rem_lin >= p.G) { rem_lin -= p.G; ++i_lin; }
         }
     }
     tc_fence_before_sync();
@@ -422,26 +394,35 @@ __global__ void __launch_bounds__(320, 1) tc_gemm_tma(const __grid_constant__ CU
             }
         }
     } else if (warp == 1) {
-        if ((tid & 31) == 0) {
-            constexpr uint32_t idesc = make_idesc(128, BN, 0, 0);
-            uint32_t q = 0, t = 0;
-            for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++t) {
-                const uint32_t acc = t & 1;
-                if (t >= 2) mbar_wait(&tempty_bar[acc], ((t >> 1) - 1) & 1);
+        // MMA issuer: whole warp walks the loop (uniform control flow), one elected lane issues
+        const bool leader = elect_one();
+        constexpr uint32_t idesc = make_idesc(128, BN, 0, 0);
+        const uint64_t desc_hi = desc_kmajor(0) & 0xFFFFFFFF00000000ull;
+        const uint32_t lo_flags = (uint32_t)(desc_kmajor(0) & 0xFFFFFFFFull);
+        uint32_t q = 0, t = 0;
+        for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++t) {
+            const uint32_t acc = t & 1;
+            if (t >= 2) mbar_wait(&tempty_bar[acc], ((t >> 1) - 1) & 1);
+            tc_fence_after_sync();
+            const uint32_t d_addr = tmem_d + acc * BN;
+            for (int j = 0; j < nch; ++j, ++q) {
+                const uint32_t s = q % STAGES;
+                mbar_wait(&full_bar[s], (q / STAGES) & 1);
                 tc_fence_after_sync();
-                const uint32_t d_addr = tmem_d + acc * BN;
-                for (int j = 0; j < nch; ++j, ++q) {
-                    const uint32_t s = q % STAGES;
-                    mbar_wait(&full_bar[s], (q / STAGES) & 1);
-                    tc_fence_after_sync();
+                if (leader) {
                     const uint32_t stage_addr = smem_u32(smem + (size_t)s * STAGE_BYTES);
-                    const uint64_t adesc = desc_kmajor(stage_addr), bdesc = desc_kmajor(stage_addr + A_BYTES);
+                    const uint32_t a_lo = ((stage_addr & 0x3FFFFu) >> 4) | lo_flags;
+                    const uint32_t b_lo = (((stage_addr + A_BYTES) & 0x3FFFFu) >> 4) | lo_flags;
 #pragma unroll
-                    for (int kk = 0; kk < 4; ++kk) umma_bf16(d_addr, adesc + 2 * kk, bdesc + 2 * kk, idesc, (j | kk) != 0);
+                    for (int kk = 0; kk < 4; ++kk)
+                        umma_bf16(d_addr, desc_hi | (uint64_t)(a_lo + 2 * kk), desc_hi | (uint64_t)(b_lo + 2 * kk), idesc,
+                                  (j | kk) != 0 ? 1u : 0u);
                     umma_commit(&empty_bar[s]);
                 }
-                umma_commit(&tfull_bar[acc]);
+                __syncwarp();
             }
+            if (leader) umma_commit(&tfull_bar[acc]);
+            __syncwarp();
         }
     } else {
         // warps 2-9 = two groups of four (one warp per TMEM lane quadrant); group h owns accumulator buffer h
@@ -653,6 +634,25 @@ static int make_tmap_2d(CUtensorMap* tm, const void* base, int64_t rows, int64_t
     return B200RL_OK;
 }
 
+// [n_images][rows_per_image][cols] bf16, box = [1][box_rows][64]: rows past an image's end are zero-filled
+static int make_tmap_3d(CUtensorMap* tm, const void* base, int64_t n_images, int64_t rows_per_image, int64_t cols, int box_rows,
+                        const char* what) {
+    if (!g_encode) {
+        CUtensorMap dummy;
+        int rc = make_tmap_2d(&dummy, base, 128, 64, 8, what);      // resolves the driver entry point
+        if (rc) return rc;
+    }
+    const cuuint64_t dims[3] = {(cuuint64_t)cols, (cuuint64_t)rows_per_image, (cuuint64_t)n_images};
+    const cuuint64_t strides[2] = {(cuuint64_t)cols * 2, (cuuint64_t)rows_per_image * (cuuint64_t)cols * 2};
+    const cuuint32_t box[3] = {64u, (cuuint32_t)box_rows, 1u};
+    const cuuint32_t estr[3] = {1u, 1u, 1u};
+    CUresult r = g_encode(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(base), dims, strides, box, estr,
+                          CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                          CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return fail(B200RL_ERR_CUDA, "%s: cuTensorMapEncodeTiled (3-D) failed (%d)", what, (int)r);
+    return B200RL_OK;
+}
+
 static int g_num_sms = 0;
 static int num_sms() {
     if (g_num_sms == 0) {
@@ -698,15 +698,18 @@ static int launch_conv_win(const WinParams& p, cudaStream_t s, const char* what)
     }
     if ((int64_t)p.G * p.Wp >= 65536 || p.G < 1 || p.N % 32 != 0)
         return fail(B200RL_ERR_INVALID_ARGUMENT, "%s: grid %d x width %d outside the epilogue's multiply-shift range, or N %% 32 != 0", what, p.G, p.Wp);
-    const int total = (int)ceil_div(p.M, 128);
+    if (p.rows && !p.tpi_shift) return fail(B200RL_ERR_INVALID_ARGUMENT, "%s: the image gather needs image-aligned tiling", what);
+    if (p.tpi_shift && (128 << p.tpi_shift) < p.G) return fail(B200RL_ERR_INVALID_ARGUMENT, "%s: tiles per image too small", what);
+    const int total = p.tpi_shift ? (int)((int64_t)p.n << p.tpi_shift) : (int)ceil_div(p.M, 128);
     int grid = num_sms();
     if (grid > total) grid = total;
     CUtensorMap tmA;
     memset(&tmA, 0, sizeof(tmA));
-    if (!p.rows) {     // contiguous rows: the window is a TMA box [WR rows x 64 channels] per column chunk
-        int rc = make_tmap_2d(&tmA, p.A, p.M, (int64_t)CPR * 64, p.WR, what);
-        if (rc) return rc;
-    }
+    int rc;
+    // the window is a TMA box [WR rows x 64 channels] per column chunk: of the linear grid, or of one image
+    if (p.tpi_shift) rc = make_tmap_3d(&tmA, p.A, p.n_images, p.G, (int64_t)CPR * 64, p.WR, what);
+    else rc = make_tmap_2d(&tmA, p.A, p.M, (int64_t)CPR * 64, p.WR, what);
+    if (rc) return rc;
     tc_conv_win<BN, CPR, STAGES, NTAPS><<<grid, 416, smem, s>>>(tmA, p, total);
     return check_launch(what);
 }
@@ -718,6 +721,8 @@ static int launch_conv_win(const WinParams& p, cudaStream_t s, const char* what)
 // whole rows.  Output tile t pairs the 64-channel chunks slot[2t], slot[2t+1].
 struct WGradWinParams {
     const bf16* X; const int64_t* rows; int64_t M; int n, G;
+    int tpi_shift;           // > 0: image-aligned steps (2^tpi_shift steps of 128 rows per image, M = n << (7 + tpi_shift))
+    int64_t n_images;        // images addressable through `rows`
     int cpr;                 // 64-channel column chunks per X row
     int nslots;              // even; chunk of slot s = (tap slot_tap[s], column chunk slot_cc[s])
     int slot_tap[16], slot_cc[16];
@@ -749,10 +754,12 @@ __global__ void __launch_bounds__(160, 1) tc_wgrad_win(const __grid_constant__ C
     for (int i = tid; i < 4096 / 4; i += blockDim.x) reinterpret_cast<uint32_t*>(sOnes)[i] = 0x3F803F80u;
     fence_proxy_async_smem();
     if (tid == 0) {
-        for (int s = 0; s < STAGES; ++s) { mbar_init(&full_bar[s], use_tma ? 1 : 4); mbar_init(&empty_bar[s], 1); }
+        // full: one expect_tx arrival (TMA); image-aligned mode adds the four cp.async warps that stage dY
+        for (int s = 0; s < STAGES; ++s) { mbar_init(&full_bar[s], use_tma ? 1 : 5); mbar_init(&empty_bar[s], 1); }
         mbar_init(&done_bar, 1);
         fence_barrier_init();
-        if (use_tma) { tma_prefetch_desc(&tmX); tma_prefetch_desc(&tmY); }
+        tma_prefetch_desc(&tmX);
+        if (use_tma) tma_prefetch_desc(&tmY);
     }
     if (warp == 4) tmem_alloc(&tmem_base_smem, tmem_cols);
     tc_fence_before_sync();
@@ -778,53 +785,41 @@ __global__ void __launch_bounds__(160, 1) tc_wgrad_win(const __grid_constant__ C
             }
         }
     } else if (warp < 4) {
-        const int ppr = p.cpr * 8;               // 16-byte pieces per X row
-        const int rstep = 128 / ppr;
-        const int wr0 = tid / ppr, pc = tid % ppr;
-        const int cc = pc >> 3, c16 = pc & 7;
-        int64_t nimg0 = 0, nimg1 = 0;          // gather indices of the NEXT step's window, fetched one step ahead
-        if (p.rows && nsteps > 0) {
-            const int64_t i0 = m_begin / p.G;
-            nimg0 = i0 < p.n ? __ldg(p.rows + i0) : 0;
-            nimg1 = i0 + 1 < p.n ? __ldg(p.rows + i0 + 1) : 0;
+        // image-aligned mode (conv1): every image owns 2^tpi_shift steps of 128 grid rows.  The X window is one 3-D TMA
+        // box per column chunk whose image coordinate is the (optional) minibatch gather; the dY rows are only
+        // ncolsY*2 bytes wide (no 128-byte TMA box), so the four producer warps copy them with cp.async.
+        const int tmask = (1 << p.tpi_shift) - 1;
+        const int64_t g0 = m_begin / R;                   // first global step of this CTA
+        int z_next = 0;
+        if (tid == 0 && nsteps > 0) {
+            const int64_t img = g0 >> p.tpi_shift;
+            z_next = p.rows ? (int)__ldg(p.rows + (img < p.n ? img : 0)) : (int)img;
         }
         for (int it = 0; it < nsteps; ++it) {
             const int s = it % STAGES;
-            const int64_t m0 = m_begin + (int64_t)it * R;
-            const int64_t cimg0 = nimg0, cimg1 = nimg1;
-            int64_t ibase = 0;
-            if (p.rows) {
-                ibase = m0 / p.G;
-                if (it + 1 < nsteps) {
-                    const int64_t i0 = (m0 + R) / p.G;
-                    nimg0 = i0 < p.n ? __ldg(p.rows + i0) : 0;
-                    nimg1 = i0 + 1 < p.n ? __ldg(p.rows + i0 + 1) : 0;
-                }
+            const int64_t g = g0 + it;
+            const int64_t img = g >> p.tpi_shift;
+            const int t_in = (int)(g & tmask);
+            const int z = z_next;
+            if (tid == 0 && it + 1 < nsteps) {
+                const int64_t img1 = (g + 1) >> p.tpi_shift;
+                z_next = p.rows ? (int)__ldg(p.rows + (img1 < p.n ? img1 : 0)) : (int)img1;
             }
             if (it >= STAGES) mbar_wait(&empty_bar[s], ((it / STAGES) - 1) & 1);
             const uint32_t sX = smem_u32(smem + (size_t)s * stage_bytes);
             const uint32_t sY = sX + XBYTES;
-            // X window: rows m0 .. m0+WRX-1 (may run past m_end: those rows belong to the next CTA / are zero)
-            {
-                const int rw = p.cpr * 64;                 // elements per X row
-                int rem = p.rows ? (int)(m0 + wr0 - ibase * p.G) : wr0;
-                const bf16* base0 = p.rows ? p.X + (cimg0 * p.G) * (int64_t)rw + pc * 8 : p.X + m0 * (int64_t)rw + pc * 8;
-                const bf16* base1 = p.rows ? p.X + ((cimg1 - 1) * p.G) * (int64_t)rw + pc * 8 : base0;
-                const int64_t rows_left = p.M - m0;
-                for (int wr = wr0; wr < p.WRX; wr += rstep, rem += rstep) {
-                    const bool ok = wr < rows_left;
-                    const bf16* src = ((p.rows && rem >= p.G) ? base1 : base0) + (int64_t)rem * rw;
-                    cp_async16(sX + cc * IMGX + img_off(wr, c16), ok ? src : p.X, ok ? 16u : 0u);
-                }
+            if (tid == 0) {
+                mbar_arrive_expect_tx(&full_bar[s], (uint32_t)XBYTES);
+                for (int c = 0; c < p.cpr; ++c) tma_load_3d(sX + c * IMGX, &tmX, c * 64, t_in * 128, z, &full_bar[s]);
             }
-            // dY rows m0 .. m0+127 (zero beyond this CTA's range so that boundary rows are counted once)
+            // dY rows of this step (zero past the image's G rows: those grid positions are padding)
 #pragma unroll
             for (int ps = 0; ps < R / 16; ++ps) {
                 const int rr = ps * 16 + (tid >> 3);
-                const int64_t r = m0 + rr;
+                const int rl = t_in * 128 + rr;
                 const int col = (tid & 7) * 8;
-                const bool ok = r < m_end && col < p.ncolsY;
-                cp_async16(sY + img_off(rr, tid & 7), p.Y + (ok ? r * (int64_t)p.ldy + col : 0), ok ? 16u : 0u);
+                const bool ok = rl < p.G && img < p.n && col < p.ncolsY;
+                cp_async16(sY + img_off(rr, tid & 7), p.Y + (ok ? (img * p.G + rl) * (int64_t)p.ldy + col : 0), ok ? 16u : 0u);
             }
             cp_async_commit();
             if (it >= LOOKAHEAD) {
@@ -1160,7 +1155,7 @@ __global__ void tc_pack_fc(const float* __restrict__ w, int O, int C, int PP, bf
 // ------------------------------------------------------------------ policy/value heads (tiny: CUDA cores, fp32 math)
 // A1 = A + 1 head outputs (logits | value), 1 <= A1 <= kMaxHeads.  Head weights live in dynamic shared memory.
 constexpr int kMaxHeads = 32;
-constexpr int kHeadsPartialBlocks = 148;     // row blocks of the head weight gradient (x2 row lanes = partial slabs)
+constexpr int kHeadsPartialBlocks = 296;     // row blocks of the head weight gradient (x2 row lanes = partial slabs)
 // rows per block of tc_heads_bwd_weight: its dhead rows are staged in (static-limit) shared memory, <= 256 x 32 floats
 static inline int64_t heads_rows_per_block(int64_t n) {
     int64_t rpb = (n + kHeadsPartialBlocks - 1) / kHeadsPartialBlocks;
@@ -1395,6 +1390,8 @@ static void win_defaults(WinParams& p) { memset(&p, 0, sizeof(p)); p.scale = 1.f
 static int round8(int v) { return (v + 7) & ~7; }
 static void win_conv1(WinParams& p, const bf16* x0, const int64_t* rows, int64_t n) {     // 2x2 taps on the 21x21 s2d grid
     p.A = x0; p.rows = rows; p.n = (int)n; p.G = 441; p.Wp = 21; p.M = n * 441;
+    p.tpi_shift = 2;                             // 4 tiles of 128 grid rows per image (441 used)
+    p.n_images = rows ? (int64_t)1 << 24 : n;    // gather indices are the caller's contract (never range-checked)
     p.ntaps = 4; p.shift[0] = 0; p.shift[1] = 1; p.shift[2] = 21; p.shift[3] = 22; p.WR = round8(128 + 22);
 }
 static void win_conv2(WinParams& p, const bf16* act1, int64_t n) {                         // 2x2 taps on the 10x10 cell grid
@@ -1432,11 +1429,18 @@ static int launch_wgrad_win(const WGradWinParams& p, int ctas, cudaStream_t s, c
     CUtensorMap tmX, tmY;
     memset(&tmX, 0, sizeof(tmX)); memset(&tmY, 0, sizeof(tmY));
     // TMA when rows are contiguous, dY rows are exactly 128 bytes and every CTA owns whole 128-row steps
-    const int use_tma = (!p.rows && p.ldy == 64 && p.ncolsY == 64 && p.rows_per_cta % 128 == 0) ? 1 : 0;
+    // all-TMA when dY rows are exactly 128 bytes; image-aligned steps (3-D TMA for X, cp.async for dY) otherwise
+    const int use_tma = p.tpi_shift ? 0 : 1;
+    if (p.rows_per_cta % 128 != 0) return fail(B200RL_ERR_INVALID_ARGUMENT, "%s: rows per CTA must be a multiple of 128", what);
+    int rc;
     if (use_tma) {
-        int rc;
+        if (p.rows || p.ldy != 64 || p.ncolsY != 64)
+            return fail(B200RL_ERR_INVALID_ARGUMENT, "%s: linear-grid mode needs contiguous rows and 64-channel dY", what);
         if ((rc = make_tmap_2d(&tmX, p.X, p.M, (int64_t)p.cpr * 64, p.WRX, what))) return rc;
         if ((rc = make_tmap_2d(&tmY, p.Y, p.M, 64, 128, what))) return rc;
+    } else {
+        if ((128 << p.tpi_shift) < p.G) return fail(B200RL_ERR_INVALID_ARGUMENT, "%s: steps per image too small", what);
+        if ((rc = make_tmap_3d(&tmX, p.X, p.n_images, p.G, (int64_t)p.cpr * 64, p.WRX, what))) return rc;
     }
     tc_wgrad_win<<<ctas, 160, smem, s>>>(tmX, tmY, p, use_tma);
     return check_launch(what);
@@ -1481,7 +1485,7 @@ extern "C" size_t b200rl_naturecnn_bf16_workspace_bytes(int64_t n, int A) {
     if (n < 1 || A < 1) return 0;
     size_t a = 0;
     auto mx = [&](size_t v) { if (v > a) a = v; };
-    mx((size_t)wgrad_plan(n * 441, kC1Ctas, 128).splits * 256 * 64 * 4);
+    mx((size_t)wgrad_plan(n * 512, kC1Ctas, 128).splits * 256 * 64 * 4);
     mx((size_t)wgrad_plan(n * 100, kC2Ctas, 128).splits * 512 * 64 * 4);
     mx((size_t)wgrad_plan(n * 81, kC3Ctas, 128).splits * 640 * 64 * 4);
     mx((size_t)wgrad_plan(n, kFcSplits, 64).splits * 512 * (13 * 256) * 4);
@@ -1587,7 +1591,7 @@ extern "C" int b200rl_naturecnn_bf16_backward(const void* obs, int obs_format, c
     size_t big = 0;
     {
         auto mx = [&](size_t v) { if (v > big) big = v; };
-        mx((size_t)wgrad_plan(n * 441, kC1Ctas, 128).splits * 256 * 64 * 4);
+        mx((size_t)wgrad_plan(n * 512, kC1Ctas, 128).splits * 256 * 64 * 4);
         mx((size_t)wgrad_plan(n * 100, kC2Ctas, 128).splits * 512 * 64 * 4);
         mx((size_t)wgrad_plan(n * 81, kC3Ctas, 128).splits * 640 * 64 * 4);
         mx((size_t)wgrad_plan(n, kFcSplits, 64).splits * 512 * (13 * 256) * 4);
@@ -1699,11 +1703,12 @@ extern "C" int b200rl_naturecnn_bf16_backward(const void* obs, int obs_format, c
     // ---- conv1 (no data gradient: the input is the observation)
     {
         wgw_defaults(gw);
-        gw.X = x0; gw.rows = x0rows; gw.M = n * 441; gw.n = (int)n; gw.G = 441; gw.cpr = 1; gw.nslots = 4; gw.WRX = round8(128 + 22);
+        gw.X = x0; gw.rows = x0rows; gw.M = n * 512; gw.n = (int)n; gw.G = 441; gw.cpr = 1; gw.nslots = 4; gw.WRX = round8(128 + 22);
+        gw.tpi_shift = 2; gw.n_images = x0rows ? (int64_t)1 << 24 : n;       // 4 steps of 128 grid rows per image
         gw.shift[0] = 0; gw.shift[1] = 1; gw.shift[2] = 21; gw.shift[3] = 22;
         for (int k = 0; k < 4; ++k) { gw.slot_tap[k] = k; gw.slot_cc[k] = 0; }
         gw.Y = act + Q.dact1; gw.ldy = 32; gw.ncolsY = 32;
-        const WPlan pl = wgrad_plan(n * 441, kC1Ctas, 128);
+        const WPlan pl = wgrad_plan(n * 512, kC1Ctas, 128);
         gw.rows_per_cta = pl.rows_per_cta; gw.ws = wsbig; gw.wsb = wssmall;
         { ProfScope ps(s, "conv1_wgrad", 2.0 * n * 400 * 32 * 256, (double)n * (28224 + 14112) * 2);
           if ((rc = launch_wgrad_win(gw, pl.splits, s, "naturecnn/conv1_wgrad"))) return rc; }

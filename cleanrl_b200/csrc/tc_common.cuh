@@ -166,6 +166,13 @@ __device__ __forceinline__ void tma_load_2d(uint32_t smem_dst, const void* tmap,
                  ::"r"(smem_dst), "l"(reinterpret_cast<uint64_t>(tmap)), "r"(x), "r"(y), "r"(smem_u32(bar))
                  : "memory");
 }
+// 3-D variant: (x, y, z) = (element column, row inside the image, image index); rows past the image end are
+// zero-filled by the hardware and still count towards complete_tx
+__device__ __forceinline__ void tma_load_3d(uint32_t smem_dst, const void* tmap, int x, int y, int z, uint64_t* bar) {
+    asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];"
+                 ::"r"(smem_dst), "l"(reinterpret_cast<uint64_t>(tmap)), "r"(x), "r"(y), "r"(z), "r"(smem_u32(bar))
+                 : "memory");
+}
 __device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t bytes) {
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
 }

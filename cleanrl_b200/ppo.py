@@ -58,6 +58,15 @@ def make_envs(args, run_name):
 def main(argv=None, writer_factory=None, env_factory=None, on_iteration=None, agent_hook=None):
     global run_name
     args = cli.parse(Args, argv)
+    engine, run_name = run(args, Agent, make_envs, np.float32, "cleanrl_b200.ppo", writer_factory, env_factory,
+                           on_iteration, agent_hook)
+    return engine
+
+
+def run(args, agent_cls, make_envs_fn, obs_dtype, who, writer_factory=None, env_factory=None, on_iteration=None,
+        agent_hook=None):
+    """The single-process gymnasium-API PPO loop shared by ppo.py and ppo_atari.py (reference: ppo.py:129-311 and
+    ppo_atari.py:141-330 are the same loop around different Agents).  Returns (engine, run_name)."""
     args.batch_size = int(args.num_envs * args.num_steps)
     args.minibatch_size = int(args.batch_size // args.num_minibatches)
     args.num_iterations = args.total_timesteps // args.batch_size
@@ -79,16 +88,18 @@ def main(argv=None, writer_factory=None, env_factory=None, on_iteration=None, ag
     torch.backends.cudnn.deterministic = args.torch_deterministic
 
     if not (torch.cuda.is_available() and args.cuda) and not PPOEngine.ALLOW_NON_CUDA_FOR_TESTS:
-        raise RuntimeError("cleanrl_b200.ppo runs on libb200rl CUDA kernels: a CUDA device and --cuda are required "
+        raise RuntimeError(f"{who} runs on libb200rl CUDA kernels: a CUDA device and --cuda are required "
                            "(no CPU fallback). Use the reference script for CPU runs.")
     device = torch.device("cuda" if torch.cuda.is_available() else "cpu")
 
-    envs = env_factory(args) if env_factory else make_envs(args, run_name)
+    envs = env_factory(args) if env_factory else make_envs_fn(args, run_name)
     assert hasattr(envs.single_action_space, "n"), "only discrete action space is supported"
-    agent = Agent(envs).to(device)
+    agent = agent_cls(envs).to(device)
+    if hasattr(agent, "precision"):
+        agent.precision = args.precision
     if agent_hook:
         agent_hook(agent)
-    engine = PPOEngine(agent, args, envs.single_observation_space.shape, np.float32, args.num_envs, device,
+    engine = PPOEngine(agent, args, envs.single_observation_space.shape, obs_dtype, args.num_envs, device,
                        gae_mode=0 if args.gae_kernel == "sequential" else 1)
 
     global_step = 0
@@ -135,7 +146,7 @@ def main(argv=None, writer_factory=None, env_factory=None, on_iteration=None, ag
 
     envs.close()
     writer.close()
-    return engine
+    return engine, run_name
 
 
 if __name__ == "__main__":

@@ -23,8 +23,10 @@ def _stack(recs, key):
     return np.stack([r[key] for r in recs])
 
 
-def atari_envpool(name, argv, n_iter):
-    rec, g = run_reference("ppo_atari_envpool.py", argv, atari_mode="fresh")
+def atari_envpool(name, argv, n_iter, script="ppo_atari_envpool.py"):
+    """cleanrl/ppo_atari_envpool.py (envpool/gym-0.23 API) or cleanrl/ppo_atari.py (gymnasium API) on the
+    Breakout-shaped synthetic env."""
+    rec, g = run_reference(script, argv, atari_mode="fresh", gymnasium_kind="atari")
     assert len(rec.iterations) == n_iter
     out = {"argv": np.array(argv)}
     for k in ("actions", "logprobs", "rewards", "dones", "values", "advantages", "returns", "next_value", "next_done",
@@ -122,6 +124,13 @@ def dqn(name, argv):
 
 def main():
     OUT.mkdir(parents=True, exist_ok=True)
+    only = sys.argv[1:]
+    if not only or "ppo_atari_gym" in only:
+        atari_envpool("ppo_atari_gym_n8_t32_seed2.npz",
+                      ["--no-cuda", "--num-envs", "8", "--num-steps", "32", "--total-timesteps", "512", "--seed", "2"], 2,
+                      script="ppo_atari.py")
+        if only:
+            return
     dqn("dqn_atari_b8_seed1.npz",
         ["--no-cuda", "--total-timesteps", "260", "--learning-starts", "40", "--buffer-size", "64", "--batch-size", "8",
          "--train-frequency", "4", "--target-network-frequency", "20", "--seed", "1"])

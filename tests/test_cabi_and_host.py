@@ -83,7 +83,7 @@ def test_product_never_imports_oracle():
 
 @pytest.mark.reference
 @pytest.mark.parametrize("script,factory", [
-    ("ppo.py", "ppo_args"), ("ppo_atari_envpool.py", "ppo_atari_envpool_args"),
+    ("ppo.py", "ppo_args"), ("ppo_atari.py", "ppo_atari_args"), ("ppo_atari_envpool.py", "ppo_atari_envpool_args"),
     ("ppo_atari_multigpu.py", "ppo_atari_multigpu_args"), ("ppo_continuous_action.py", "ppo_continuous_action_args"),
     ("dqn_atari.py", "dqn_atari_args")])
 def test_cli_fields_match_reference_args(script, factory):

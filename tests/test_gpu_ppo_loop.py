@@ -25,10 +25,15 @@ def _cpu_noise(n, A, device):
 
 
 def _run(name, extra=()):
-    from cleanrl_b200 import ppo_atari_envpool as S
+    import importlib
+    # fixtures named ppo_atari_gym_* come from cleanrl/ppo_atari.py (gymnasium API), the others from the envpool script
+    S = importlib.import_module("cleanrl_b200.ppo_atari" if name.startswith("ppo_atari_gym") else
+                                "cleanrl_b200.ppo_atari_envpool")
     from cleanrl_b200.agents import NatureCNNAgent
     z = np.load(GOLDEN / name)
     argv = [a for a in z["argv"].tolist() if a != "--no-cuda"] + list(extra)
+    if name.startswith("ppo_atari_gym"):
+        argv.append("--synthetic-env")
     snaps = []
     writers = []
 
@@ -55,7 +60,8 @@ def _rel(a, b):
     return np.abs(a.astype(np.float64) - b.astype(np.float64)).max() / max(1.0, np.abs(b).max())
 
 
-@pytest.mark.parametrize("name", ["ppo_atari_envpool_n8_t32_seed1.npz", "ppo_atari_envpool_n16_t16_seed3_noclipv.npz"])
+@pytest.mark.parametrize("name", ["ppo_atari_envpool_n8_t32_seed1.npz", "ppo_atari_envpool_n16_t16_seed3_noclipv.npz",
+                                  "ppo_atari_gym_n8_t32_seed2.npz"])
 @pytest.mark.parametrize("gae_kernel", ["sequential", "scan"])
 def test_script_reproduces_reference_run(lib, name, gae_kernel):
     z, snaps, w = _run(name, ["--gae-kernel", gae_kernel])

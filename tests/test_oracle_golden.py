@@ -12,7 +12,8 @@ import pytest
 from conftest import GOLDEN
 from oracle import ppo_oracle as O
 
-ATARI = ["ppo_atari_envpool_n8_t32_seed1.npz", "ppo_atari_envpool_n16_t16_seed3_noclipv.npz"]
+ATARI = ["ppo_atari_envpool_n8_t32_seed1.npz", "ppo_atari_envpool_n16_t16_seed3_noclipv.npz",
+         "ppo_atari_gym_n8_t32_seed2.npz"]
 
 
 def _args(z):

@@ -1,5 +1,8 @@
 """One PPO minibatch update (M = 32768, the BASELINE.json configs[1] minibatch) + a few rollout steps,
-for ncu: `ncu ... python tools/profile_update.py`.  Prints per-kernel CUDA-event times when run bare."""
+for ncu: `ncu ... python tools/profile_update.py [M] [reps] [u8|s2d]`.  Prints per-kernel CUDA-event times when run bare.
+
+u8  (default): the drop-in path, uint8 NCHW frames gathered through random minibatch indices.
+s2d: the engine path, rollout stored as space-to-depth bf16, sorted minibatch indices (what bench.py runs)."""
 import json
 import sys
 import ctypes
@@ -18,6 +21,7 @@ lib = _lib.load()
 M = int(sys.argv[1]) if len(sys.argv) > 1 else 32768
 B = 4 * M
 reps = int(sys.argv[2]) if len(sys.argv) > 2 else 3
+fmt = sys.argv[3] if len(sys.argv) > 3 else "u8"
 
 
 class E:
@@ -32,6 +36,13 @@ agent.precision = "bf16"
 flat = agent.flat
 obs = torch.randint(0, 256, (B, 4, 84, 84), dtype=torch.uint8, device=dev)
 inds = torch.randperm(B, device=dev)[:M].contiguous()
+obs_roll = obs[:1024].clone()
+if fmt == "s2d":
+    s2d = torch.empty((B, 21, 21, 64), dtype=torch.bfloat16, device=dev)
+    for lo in range(0, B, 16384):
+        ops.frames_to_s2d(obs[lo:lo + 16384], out=s2d[lo:lo + 16384])
+    obs = s2d
+    inds = inds.sort().values.contiguous()
 b_act = torch.randint(0, 4, (B,), device=dev)
 b_lp = torch.full((B,), -1.386, device=dev)
 b_adv = torch.randn(B, device=dev)
@@ -50,7 +61,7 @@ def minibatch(step):
 
 
 def rollout_step():
-    agent.get_action_and_value(obs[:1024])
+    agent.get_action_and_value(obs_roll)
 
 
 for i in range(2):
@@ -59,9 +70,12 @@ for i in range(2):
 torch.cuda.synchronize()
 lib.b200rl_profile_reset()
 lib.b200rl_profile_enable(1)
+torch.cuda.profiler.start()          # ncu --profile-from-start off captures exactly the measured region
 for i in range(reps):
     minibatch(i + 3)
     rollout_step()
+torch.cuda.synchronize()
+torch.cuda.profiler.stop()
 lib.b200rl_profile_enable(0)
 buf = ctypes.create_string_buffer(1 << 16)
 lib.b200rl_profile_summary(buf, 1 << 16)
