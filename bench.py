@@ -180,8 +180,11 @@ def run_ours(opt):
 
     def iteration_resident():
         P = pool_dev.shape[0]
-        for step in range(T):
-            eng.policy_step_resident(step, pool_dev[step % P])
+        if eng.cuda_graphs and getattr(agent, "graph_friendly", False):
+            eng.rollout_resident(pool_dev)          # all T steps = one graph launch (no host launch per step)
+        else:
+            for step in range(T):
+                eng.policy_step_resident(step, pool_dev[step % P])
         eng.rewards.copy_(eng_rewards)
         eng.dones.copy_(eng_dones)
         if eng.s2d:

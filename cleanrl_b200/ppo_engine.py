@@ -229,6 +229,24 @@ class PPOEngine:
             self.obs[step].copy_(obs_dev)
         self._run_step(step)
 
+    @torch.no_grad()
+    def rollout_resident(self, obs_pool):
+        """All T policy steps over device-resident frame batches ``obs_pool[t % P]`` (uint8 [P,N,4,84,84] or the
+        engine's storage dtype) replayed as ONE CUDA graph: the kernel-side throughput of the rollout without a
+        host launch per step (measurement path of bench.py's ``value``; the public loop is ``policy_step``)."""
+        P = obs_pool.shape[0]
+
+        def work():
+            for step in range(self.T):
+                src = obs_pool[step % P]
+                if self.s2d and src.dtype == torch.uint8:
+                    ops.frames_to_s2d(src, out=self.obs[step])
+                else:
+                    self.obs[step].copy_(src)
+                self.agent.sample_into(self.obs[step], self.actions[step], self.logprobs[step], self.values[step])
+
+        self._run_graphed(work, ("rollout", obs_pool.data_ptr(), P), warm_key="r")
+
     def record_reward(self, step, reward_np):
         self.rewards_h[step].copy_(torch.as_tensor(np.asarray(reward_np, dtype=np.float32).reshape(-1)))
 

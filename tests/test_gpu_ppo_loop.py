@@ -209,3 +209,34 @@ def test_cuda_graph_rollout_equals_eager(lib, kind):
         outs.append(rec)
     for (a0, l0, v0), (a1, l1, v1) in zip(*outs):
         assert torch.equal(a0, a1) and torch.equal(l0, l1) and torch.equal(v0, v1)
+
+
+def test_whole_rollout_graph_equals_stepwise(lib):
+    """bench.py's resident path replays all T policy steps as ONE CUDA graph (PPOEngine.rollout_resident); it must
+    produce what T separate device-resident steps produce from the same generator state."""
+    from bench import ppo_args
+    from cleanrl_b200.agents import NatureCNNAgent
+    from cleanrl_b200.ppo_engine import PPOEngine
+    from cleanrl_b200.synthetic_envs import SyntheticAtariVec
+    dev = torch.device("cuda")
+    N, T = 32, 5
+    g = torch.Generator().manual_seed(5)
+    pool = torch.randint(0, 256, (3, N, 4, 84, 84), dtype=torch.uint8, generator=g).to(dev)
+    outs = []
+    for whole in (False, True):
+        torch.manual_seed(3)
+        envs = SyntheticAtariVec(N, seed=3, mode="fresh")
+        envs.single_observation_space, envs.single_action_space = envs.observation_space, envs.action_space
+        agent = NatureCNNAgent(envs).to(dev); agent.precision = "bf16"
+        eng = PPOEngine(agent, ppo_args(N, T, 4, "bf16"), (4, 84, 84), np.uint8, N, dev)
+        torch.manual_seed(11)
+        for rep in range(2):                      # second pass replays the captured graph(s)
+            if whole:
+                eng.rollout_resident(pool)
+            else:
+                for t in range(T):
+                    eng.policy_step_resident(t, pool[t % 3])
+        torch.cuda.synchronize()
+        outs.append((eng.actions.clone(), eng.logprobs.clone(), eng.values.clone(), eng.obs.clone()))
+    for a, b in zip(*outs):
+        assert torch.equal(a, b)
