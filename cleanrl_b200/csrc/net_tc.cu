@@ -15,16 +15,17 @@
 //   is an image-index indirection inside the conv1 kernels.
 //
 // Kernels
-//   tc_conv_win<BN,CPR,STAGES>   stride-1 "window" convolution (conv1/2/3 forward, conv3/conv2 data-gradient):
+//   tc_conv_win<BN,CPR,STAGES,NTAPS>   stride-1 "window" convolution (conv1/2/3 forward, conv3/conv2 data-gradient):
 //       GEMM rows enumerate grid positions, so tap (dy,dx) of row r is row r + dy*Wp + dx.  A persistent CTA
-//       stages ONE window of 128+maxshift rows per tile -- by TMA (cp.async.bulk.tensor box) when rows are
-//       contiguous, by 4 cp.async producer warps when conv1 gathers frames through mb_inds -- and every tap is a
-//       UMMA descriptor whose start address is shifted by whole 128-byte rows (legal for SWIZZLE_128B: the pattern
-//       is a function of the smem address bits; tools/experiments/umma_shift_test.cu).  Weights stay resident in
-//       smem.  Warp 4 issues tcgen05.mma; warps 5-12 (two per TMEM lane quadrant) drain double-buffered accumulators.
+//       stages ONE window of 128+maxshift rows per tile as a TMA box (cp.async.bulk.tensor; for conv1 a 3-D box
+//       whose image coordinate is the minibatch gather) and every tap is a UMMA descriptor whose start address is
+//       shifted by whole 128-byte rows (legal for SWIZZLE_128B: the pattern is a function of the smem address
+//       bits; tools/experiments/umma_shift_test.cu).  Weights stay resident in smem.  Warp 4 issues tcgen05.mma
+//       (warp-uniform loop, elected lane); warps 5-12 = two epilogue groups that own alternate tiles and drain
+//       double-buffered accumulators; ReLU masks are exchanged between forward and backward as bits.
 //   tc_wgrad_win                 conv weight gradients: dW^T[(tap,c), co] = sum_r X[r+shift_tap, c] * dY[r, co]; the same
 //       row images are read as MN-major operands (rows = reduction index), taps again by row shifts; the bias
-//       gradient is one extra MMA per step against an all-ones operand.
+//       gradient (column sums of dY) is accumulated by the four dY warps from the staged tiles.
 //   tc_gemm_tma<BN,STAGES>       fc forward / data-gradient: both operands are TMA boxes of row-major matrices.
 //   tc_wgrad_tma                 fc weight gradient (MN-major views of TMA-loaded dhid / act3 row boxes).
 //   tc_heads_*                   the A+1 head outputs in fp32 on CUDA cores.
@@ -731,10 +732,10 @@ struct WGradWinParams {
     const bf16* Y; int ldy, ncolsY;
     int64_t rows_per_cta;    // multiple of 128
     float* ws;               // [gridDim.x][nslots*64][64]
-    float* wsb;              // [gridDim.x][64] bias-gradient partials: sum_r dY[r, co] (an extra all-ones X tile)
+    float* wsb;              // [gridDim.x][64] bias-gradient partials: sum_r dY[r, co]
 };
 
-__global__ void __launch_bounds__(160, 1) tc_wgrad_win(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmY,
+__global__ void __launch_bounds__(192, 1) tc_wgrad_win(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmY,
                                                        const WGradWinParams p, int use_tma) {
     constexpr int R = 128, STAGES = 3, LOOKAHEAD = 1, NY = 64;
     extern __shared__ uint8_t smem_raw[];
@@ -747,15 +748,12 @@ __global__ void __launch_bounds__(160, 1) tc_wgrad_win(const __grid_constant__ C
     const int stage_bytes = XBYTES + R * 128;
     const int xt = p.nslots / 2;
     uint32_t tmem_cols = 32;
-    while ((int)tmem_cols < (xt + 1) * NY) tmem_cols <<= 1;     // + one tile for the bias gradient
-    // 4 KB of bf16 1.0 after the ring: an MN-major operand whose every element is 1 (atoms 2 KB apart, K groups
-    // 1 KB apart all fall inside it) => D_ones[., co] = sum_r dY[r, co] = the bias gradient, for one extra MMA/step
-    uint8_t* sOnes = smem + (size_t)STAGES * stage_bytes;
-    for (int i = tid; i < 4096 / 4; i += blockDim.x) reinterpret_cast<uint32_t*>(sOnes)[i] = 0x3F803F80u;
-    fence_proxy_async_smem();
+    while ((int)tmem_cols < xt * NY) tmem_cols <<= 1;
+    float* sRed = reinterpret_cast<float*>(smem + (size_t)STAGES * stage_bytes);     // [16][64] bias partials (4 KB)
     if (tid == 0) {
-        // full: one expect_tx arrival (TMA); image-aligned mode adds the four cp.async warps that stage dY
-        for (int s = 0; s < STAGES; ++s) { mbar_init(&full_bar[s], use_tma ? 1 : 5); mbar_init(&empty_bar[s], 1); }
+        // full:  one expect_tx arrival (TMA) [+ the four cp.async warps that stage dY in image-aligned mode]
+        // empty: the MMA commit [+ the four dY-summing warps when they read the stage after the TMA landed]
+        for (int s = 0; s < STAGES; ++s) { mbar_init(&full_bar[s], use_tma ? 1 : 5); mbar_init(&empty_bar[s], use_tma ? 5 : 1); }
         mbar_init(&done_bar, 1);
         fence_barrier_init();
         tma_prefetch_desc(&tmX);
@@ -770,74 +768,118 @@ __global__ void __launch_bounds__(160, 1) tc_wgrad_win(const __grid_constant__ C
     int64_t m_end = m_begin + p.rows_per_cta;
     if (m_end > p.M) m_end = p.M;
     const int nsteps = m_end > m_begin ? (int)((m_end - m_begin + R - 1) / R) : 0;
+    const int tmask = (1 << p.tpi_shift) - 1;
+    const int64_t g0 = m_begin / R;                       // first global step of this CTA (image-aligned mode)
 
-    if (warp < 4 && use_tma) {
-        // contiguous rows: X window = one TMA box per column chunk, dY = one box of 128 rows
-        if (tid == 0) {
+    if (warp == 5) {
+        // ======================= TMA producer (one lane): X window [+ dY rows when they are 128 bytes wide] =========
+        if ((tid & 31) == 0) {
+            int z_next = 0;
+            if (!use_tma && nsteps > 0) {
+                const int64_t img = g0 >> p.tpi_shift;
+                z_next = p.rows ? (int)__ldg(p.rows + (img < p.n ? img : 0)) : (int)img;
+            }
             for (int it = 0; it < nsteps; ++it) {
                 const int s = it % STAGES;
+                const int z = z_next;
+                if (!use_tma && it + 1 < nsteps) {        // gather index of the next step, one step ahead
+                    const int64_t img1 = (g0 + it + 1) >> p.tpi_shift;
+                    z_next = p.rows ? (int)__ldg(p.rows + (img1 < p.n ? img1 : 0)) : (int)img1;
+                }
                 if (it >= STAGES) mbar_wait(&empty_bar[s], ((it / STAGES) - 1) & 1);
                 const uint32_t dst = smem_u32(smem + (size_t)s * stage_bytes);
-                const int m0 = (int)(m_begin + (int64_t)it * R);
-                mbar_arrive_expect_tx(&full_bar[s], (uint32_t)stage_bytes);
-                for (int c = 0; c < p.cpr; ++c) tma_load_2d(dst + c * IMGX, &tmX, c * 64, m0, &full_bar[s]);
-                tma_load_2d(dst + XBYTES, &tmY, 0, m0, &full_bar[s]);
+                if (use_tma) {
+                    const int m0 = (int)(m_begin + (int64_t)it * R);
+                    mbar_arrive_expect_tx(&full_bar[s], (uint32_t)stage_bytes);
+                    for (int c = 0; c < p.cpr; ++c) tma_load_2d(dst + c * IMGX, &tmX, c * 64, m0, &full_bar[s]);
+                    tma_load_2d(dst + XBYTES, &tmY, 0, m0, &full_bar[s]);
+                } else {
+                    const int t_in = (int)((g0 + it) & tmask);
+                    mbar_arrive_expect_tx(&full_bar[s], (uint32_t)XBYTES);
+                    for (int c = 0; c < p.cpr; ++c) tma_load_3d(dst + c * IMGX, &tmX, c * 64, t_in * 128, z, &full_bar[s]);
+                }
             }
         }
     } else if (warp < 4) {
-        // image-aligned mode (conv1): every image owns 2^tpi_shift steps of 128 grid rows.  The X window is one 3-D TMA
-        // box per column chunk whose image coordinate is the (optional) minibatch gather; the dY rows are only
-        // ncolsY*2 bytes wide (no 128-byte TMA box), so the four producer warps copy them with cp.async.
-        const int tmask = (1 << p.tpi_shift) - 1;
-        const int64_t g0 = m_begin / R;                   // first global step of this CTA
-        int z_next = 0;
-        if (tid == 0 && nsteps > 0) {
-            const int64_t img = g0 >> p.tpi_shift;
-            z_next = p.rows ? (int)__ldg(p.rows + (img < p.n ? img : 0)) : (int)img;
-        }
-        for (int it = 0; it < nsteps; ++it) {
-            const int s = it % STAGES;
-            const int64_t g = g0 + it;
-            const int64_t img = g >> p.tpi_shift;
-            const int t_in = (int)(g & tmask);
-            const int z = z_next;
-            if (tid == 0 && it + 1 < nsteps) {
-                const int64_t img1 = (g + 1) >> p.tpi_shift;
-                z_next = p.rows ? (int)__ldg(p.rows + (img1 < p.n ? img1 : 0)) : (int)img1;
-            }
-            if (it >= STAGES) mbar_wait(&empty_bar[s], ((it / STAGES) - 1) & 1);
-            const uint32_t sX = smem_u32(smem + (size_t)s * stage_bytes);
-            const uint32_t sY = sX + XBYTES;
-            if (tid == 0) {
-                mbar_arrive_expect_tx(&full_bar[s], (uint32_t)XBYTES);
-                for (int c = 0; c < p.cpr; ++c) tma_load_3d(sX + c * IMGX, &tmX, c * 64, t_in * 128, z, &full_bar[s]);
-            }
-            // dY rows of this step (zero past the image's G rows: those grid positions are padding)
+        // ======================= dY warps: bias gradient = column sums of dY, taken from the staged tile ==========
+        // Thread (tid>>3, tid&7) owns rows ps*16 + (tid>>3) and the 16-byte chunk (tid&7) = 8 channels of every step;
+        // it adds them up in fp32 (fixed order).  This replaces an all-ones MMA per 16 rows, which cost a quarter to a
+        // third of the kernel's shared-memory operand bandwidth.  In image-aligned mode (conv1: dY rows are 64 bytes,
+        // no 128-byte TMA box) the same threads first copy those chunks in with cp.async.
+        const int rq = tid >> 3, c16 = tid & 7;
+        float bsum[8];
+#pragma unroll
+        for (int e = 0; e < 8; ++e) bsum[e] = 0.f;
+        auto add_step = [&](const uint8_t* sYp) {
 #pragma unroll
             for (int ps = 0; ps < R / 16; ++ps) {
-                const int rr = ps * 16 + (tid >> 3);
-                const int rl = t_in * 128 + rr;
-                const int col = (tid & 7) * 8;
-                const bool ok = rl < p.G && img < p.n && col < p.ncolsY;
-                cp_async16(sY + img_off(rr, tid & 7), p.Y + (ok ? (img * p.G + rl) * (int64_t)p.ldy + col : 0), ok ? 16u : 0u);
+                const int rr = ps * 16 + rq;
+                const int4 v = *reinterpret_cast<const int4*>(sYp + img_off(rr, c16));
+                const uint32_t w[4] = {(uint32_t)v.x, (uint32_t)v.y, (uint32_t)v.z, (uint32_t)v.w};
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                    bsum[2 * e] += __uint_as_float(w[e] << 16);
+                    bsum[2 * e + 1] += __uint_as_float(w[e] & 0xFFFF0000u);
+                }
             }
-            cp_async_commit();
-            if (it >= LOOKAHEAD) {
-                cp_async_wait<LOOKAHEAD>();
-                fence_proxy_async_smem();
+        };
+        if (use_tma) {
+            for (int it = 0; it < nsteps; ++it) {
+                const int s = it % STAGES;
+                mbar_wait(&full_bar[s], (it / STAGES) & 1);
+                add_step(smem + (size_t)s * stage_bytes + XBYTES);
                 __syncwarp();
-                if ((tid & 31) == 0) mbar_arrive(&full_bar[(it - LOOKAHEAD) % STAGES]);
+                if ((tid & 31) == 0) mbar_arrive(&empty_bar[s]);
             }
+        } else {
+            for (int it = 0; it < nsteps; ++it) {
+                const int s = it % STAGES;
+                const int64_t g = g0 + it;
+                const int64_t img = g >> p.tpi_shift;
+                const int t_in = (int)(g & tmask);
+                if (it >= STAGES) mbar_wait(&empty_bar[s], ((it / STAGES) - 1) & 1);
+                const uint32_t sY = smem_u32(smem + (size_t)s * stage_bytes + XBYTES);
+                // dY rows of this step (zero past the image's G rows: those grid positions are padding)
+#pragma unroll
+                for (int ps = 0; ps < R / 16; ++ps) {
+                    const int rr = ps * 16 + rq;
+                    const int rl = t_in * 128 + rr;
+                    const int col = c16 * 8;
+                    const bool ok = rl < p.G && img < p.n && col < p.ncolsY;
+                    cp_async16(sY + img_off(rr, c16), p.Y + (ok ? (img * p.G + rl) * (int64_t)p.ldy + col : 0), ok ? 16u : 0u);
+                }
+                cp_async_commit();
+                if (it >= LOOKAHEAD) {
+                    cp_async_wait<LOOKAHEAD>();
+                    const int sd = (it - LOOKAHEAD) % STAGES;
+                    add_step(smem + (size_t)sd * stage_bytes + XBYTES);      // this thread's own chunks have landed
+                    fence_proxy_async_smem();
+                    __syncwarp();
+                    if ((tid & 31) == 0) mbar_arrive(&full_bar[sd]);
+                }
+            }
+            cp_async_wait<0>();
+            for (int d = (nsteps >= LOOKAHEAD ? nsteps - LOOKAHEAD : 0); d < nsteps; ++d)
+                add_step(smem + (size_t)(d % STAGES) * stage_bytes + XBYTES);
+            fence_proxy_async_smem();
+            __syncwarp();
+            if ((tid & 31) == 0)
+                for (int d = (nsteps >= LOOKAHEAD ? nsteps - LOOKAHEAD : 0); d < nsteps; ++d) mbar_arrive(&full_bar[d % STAGES]);
         }
-        cp_async_wait<0>();
-        fence_proxy_async_smem();
-        __syncwarp();
-        if ((tid & 31) == 0)
-            for (int d = (nsteps >= LOOKAHEAD ? nsteps - LOOKAHEAD : 0); d < nsteps; ++d) mbar_arrive(&full_bar[d % STAGES]);
+        // fold the 16 row lanes of every column chunk in fixed order -> 64 bias partials of this CTA
+#pragma unroll
+        for (int e = 0; e < 8; ++e) sRed[rq * 64 + c16 * 8 + e] = bsum[e];
+        asm volatile("bar.sync 1, 128;" ::: "memory");
+        if (tid < 64) {
+            float t = 0.f;
+#pragma unroll
+            for (int l = 0; l < 16; ++l) t += sRed[l * 64 + tid];
+            p.wsb[(int64_t)blockIdx.x * NY + tid] = t;
+        }
     } else {
-        // MMA issuer: the whole warp walks the step loop (uniform control flow), one elected lane issues.  Everything
-        // that does not depend on the stage is hoisted: per output tile the X operand's offset inside the stage and its
-        // LBO field; descriptors then differ only in the 14-bit start-address field.
+        // ======================= MMA issuer: the whole warp walks the step loop (uniform control flow), one elected
+        // lane issues.  Everything that does not depend on the stage is hoisted: per output tile the X operand's offset
+        // inside the stage and its LBO field; descriptors then differ only in the 14-bit start-address field.
         const bool leader = elect_one();
         constexpr uint32_t idesc = make_idesc(128, NY, 1, 1);
         const uint64_t desc_hi = desc_mnmajor(0, 0) & 0xFFFFFFFF00000000ull;
@@ -853,7 +895,6 @@ __global__ void __launch_bounds__(160, 1) tc_wgrad_win(const __grid_constant__ C
             }
         }
         const uint32_t ylbo = (uint32_t)(((R * 128) >> 4) & 0x3FFF) << 16;
-        const uint32_t ones_lo = ((smem_u32(sOnes) & 0x3FFFFu) >> 4) | ((uint32_t)((2048 >> 4) & 0x3FFF) << 16);
         for (int it = 0; it < nsteps; ++it) {
             const int s = it % STAGES;
             mbar_wait(&full_bar[s], (it / STAGES) & 1);
@@ -872,10 +913,6 @@ __global__ void __launch_bounds__(160, 1) tc_wgrad_win(const __grid_constant__ C
                                       idesc, kk != 0 ? 1u : accum);
                     }
                 }
-#pragma unroll
-                for (int kk = 0; kk < R / 16; ++kk)
-                    umma_bf16(tmem_d + xt * NY, desc_hi | (uint64_t)ones_lo, desc_hi | (uint64_t)(ya16 + kk * 128), idesc,
-                              kk != 0 ? 1u : accum);
                 umma_commit(&empty_bar[s]);
             }
             __syncwarp();
@@ -890,20 +927,6 @@ __global__ void __launch_bounds__(160, 1) tc_wgrad_win(const __grid_constant__ C
         }
         float* wsb = p.ws + (int64_t)blockIdx.x * (p.nslots * 64) * NY;
         const uint32_t lane_addr = tmem_d + ((uint32_t)(warp * 32) << 16);
-        if (warp == 0) {      // bias partial: any row of the all-ones tile (row 0)
-            for (int c0 = 0; c0 < NY; c0 += 16) {
-                uint32_t v[16];
-                if (nsteps > 0) { tmem_ld16(lane_addr + xt * NY + c0, v); tmem_ld_wait(); }
-                else {
-#pragma unroll
-                    for (int e = 0; e < 16; ++e) v[e] = 0u;
-                }
-                if (tid == 0) {
-#pragma unroll
-                    for (int e = 0; e < 16; ++e) p.wsb[(int64_t)blockIdx.x * NY + c0 + e] = __uint_as_float(v[e]);
-                }
-            }
-        }
         for (int t = 0; t < xt; ++t) {
             float* dst = wsb + (int64_t)(t * 128 + tid) * NY;
             for (int c0 = 0; c0 < NY; c0 += 16) {
@@ -1442,7 +1465,7 @@ static int launch_wgrad_win(const WGradWinParams& p, int ctas, cudaStream_t s, c
         if ((128 << p.tpi_shift) < p.G) return fail(B200RL_ERR_INVALID_ARGUMENT, "%s: steps per image too small", what);
         if ((rc = make_tmap_3d(&tmX, p.X, p.n_images, p.G, (int64_t)p.cpr * 64, p.WRX, what))) return rc;
     }
-    tc_wgrad_win<<<ctas, 160, smem, s>>>(tmX, tmY, p, use_tma);
+    tc_wgrad_win<<<ctas, 192, smem, s>>>(tmX, tmY, p, use_tma);
     return check_launch(what);
 }
 

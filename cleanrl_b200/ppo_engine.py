@@ -114,6 +114,14 @@ class PPOEngine:
         chunks = int(os.environ.get("CLEANRL_B200_H2D_CHUNKS", "4"))
         self.h2d_chunks = chunks if (self.cuda_graphs and getattr(self, "s2d", False) and chunks > 1
                                      and N % chunks == 0 and N // chunks >= 128) else 1
+        # chunk sizes: a short LAST chunk keeps the work that cannot overlap the upload (its conversion + forward,
+        # the sampler, the action D2H) small; every chunk's compute is still shorter than the next chunk's upload
+        C = self.h2d_chunks
+        if C == 4 and N % 16 == 0:
+            sizes = [5 * N // 16, 5 * N // 16, 4 * N // 16, 2 * N // 16]
+        else:
+            sizes = [N // C] * C
+        self.chunk_bounds = [(sum(sizes[:c]), sum(sizes[:c + 1])) for c in range(C)]
         if self.h2d_chunks > 1:
             self.copy_stream = torch.cuda.Stream(device=device)
             self.chunk_events = [torch.cuda.Event() for _ in range(self.h2d_chunks)]
@@ -149,8 +157,7 @@ class PPOEngine:
         self.agent.sample_into(self.obs[step], self.actions[step], self.logprobs[step], self.values[step])
 
     def _chunk_device_work(self, step, c):
-        n = self.N // self.h2d_chunks
-        sl = slice(c * n, (c + 1) * n)
+        sl = slice(*self.chunk_bounds[c])
         ops.frames_to_s2d(self.obs_u8[sl], out=self.obs[step][sl])
         self.agent.sample_into(self.obs[step][sl], self.actions[step][sl], self.logprobs[step][sl],
                                self.values[step][sl], noise=self.noise_buf[sl])
@@ -189,10 +196,11 @@ class PPOEngine:
     def policy_step(self, step, next_obs_np, next_done_np):
         """obs[step] <- next_obs (H2D), sample actions, return them as a host int64 array.
         Reference: ppo.py:194-205 (store obs/done, no-grad policy, action.cpu())."""
-        self.dones_h[step].copy_(torch.as_tensor(np.asarray(next_done_np, dtype=np.float32)))
         if self.h2d_chunks > 1 and getattr(self.agent, "graph_friendly", False):
-            self._pipelined_step(step, next_obs_np)
+            self._pipelined_step(step, next_obs_np)        # the upload is the critical path: enqueue it first
+            self.dones_h[step].copy_(torch.as_tensor(np.asarray(next_done_np, dtype=np.float32)))
         else:
+            self.dones_h[step].copy_(torch.as_tensor(np.asarray(next_done_np, dtype=np.float32)))
             self._upload_obs(self.obs[step], next_obs_np, convert=False)
             self._run_step(step)
         self.actions_h.copy_(self.actions[step], non_blocking=True)
@@ -207,11 +215,11 @@ class PPOEngine:
         if not src.is_pinned():
             self.obs_stage_h.copy_(src)
             src = self.obs_stage_h
-        C, n = self.h2d_chunks, self.N // self.h2d_chunks
+        C = self.h2d_chunks
         main = torch.cuda.current_stream()
         with torch.cuda.stream(self.copy_stream):
-            for c in range(C):
-                self.obs_u8[c * n:(c + 1) * n].copy_(src[c * n:(c + 1) * n], non_blocking=True)
+            for c, (lo, hi) in enumerate(self.chunk_bounds):
+                self.obs_u8[lo:hi].copy_(src[lo:hi], non_blocking=True)
                 self.chunk_events[c].record(self.copy_stream)
         self.h2d_bytes += src.numel()
         self.agent.draw_noise_into(self.noise_buf)

@@ -223,3 +223,69 @@ class SyntheticGymnasiumVec:
 
     def close(self):
         pass
+
+
+class CartPoleVec:
+    """Vectorised CartPole-v1 dynamics (the classic cart-pole of Barto, Sutton & Anderson: Euler steps of 0.02 s,
+    force +-10 N, failure beyond +-2.4 m or +-12 degrees, 500-step time limit) behind the gymnasium vector API with
+    episode statistics in ``infos["final_info"]`` as ``RecordEpisodeStatistics`` + ``SyncVectorEnv`` deliver them
+    (what cleanrl/ppo.py:210-215 reads).  Lets the PPO drop-in show a real learning curve without gymnasium
+    installed; host-side numpy, not part of the hot path."""
+
+    GRAVITY, M_CART, M_POLE, HALF_LEN, FORCE, TAU = 9.8, 1.0, 0.1, 0.5, 10.0, 0.02
+    X_LIMIT, THETA_LIMIT, MAX_STEPS = 2.4, 12 * 2 * np.pi / 360, 500
+
+    def __init__(self, num_envs):
+        self.num_envs = int(num_envs)
+        self.single_observation_space = Box(-np.inf, np.inf, (4,), np.float32)
+        self.single_action_space = Discrete(2)
+        self.observation_space, self.action_space = self.single_observation_space, self.single_action_space
+        self._rng = np.random.default_rng(0)
+        self._s = np.zeros((self.num_envs, 4), dtype=np.float64)
+        self._ret = np.zeros(self.num_envs, dtype=np.float64)
+        self._len = np.zeros(self.num_envs, dtype=np.int64)
+
+    def _fresh(self, k):
+        return self._rng.uniform(-0.05, 0.05, size=(k, 4))
+
+    def reset(self, seed=None, **kwargs):
+        self._rng = np.random.default_rng(seed)
+        self._s = self._fresh(self.num_envs)
+        self._ret[:] = 0
+        self._len[:] = 0
+        return self._s.astype(np.float32), {}
+
+    def step(self, action):
+        a = np.asarray(action).reshape(self.num_envs)
+        x, xd, th, thd = self._s.T
+        force = np.where(a == 1, self.FORCE, -self.FORCE)
+        total_m = self.M_CART + self.M_POLE
+        pm_l = self.M_POLE * self.HALF_LEN
+        cos, sin = np.cos(th), np.sin(th)
+        tmp = (force + pm_l * thd * thd * sin) / total_m
+        th_acc = (self.GRAVITY * sin - cos * tmp) / (self.HALF_LEN * (4.0 / 3.0 - self.M_POLE * cos * cos / total_m))
+        x_acc = tmp - pm_l * th_acc * cos / total_m
+        self._s = np.stack([x + self.TAU * xd, xd + self.TAU * x_acc, th + self.TAU * thd, thd + self.TAU * th_acc], axis=1)
+        self._ret += 1.0
+        self._len += 1
+        terminated = (np.abs(self._s[:, 0]) > self.X_LIMIT) | (np.abs(self._s[:, 2]) > self.THETA_LIMIT)
+        truncated = (self._len >= self.MAX_STEPS) & ~terminated
+        done = terminated | truncated
+        reward = np.ones(self.num_envs, dtype=np.float32)
+        infos = {}
+        if done.any():
+            idx = np.nonzero(done)[0]
+            final = np.empty(self.num_envs, dtype=object)
+            fobs = np.empty(self.num_envs, dtype=object)
+            for i in idx:
+                final[i] = {"episode": {"r": np.array([self._ret[i]], dtype=np.float32),
+                                        "l": np.array([self._len[i]], dtype=np.int32)}}
+                fobs[i] = self._s[i].astype(np.float32)
+            infos["final_info"], infos["_final_info"], infos["final_observation"] = final, done.copy(), fobs
+            self._s[idx] = self._fresh(len(idx))          # auto-reset: the returned observation starts the next episode
+            self._ret[idx] = 0
+            self._len[idx] = 0
+        return self._s.astype(np.float32), reward, terminated, truncated, infos
+
+    def close(self):
+        pass

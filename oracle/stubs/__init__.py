@@ -67,7 +67,10 @@ class _SyncVectorEnv:
     returns one synthetic vector env with the same count."""
 
     def __new__(cls, env_fns, **kw):
-        env = S.SyntheticGymnasiumVec(len(env_fns), kind=CONFIG["gymnasium_kind"])
+        if CONFIG["gymnasium_kind"] == "cartpole":
+            env = S.CartPoleVec(len(env_fns))
+        else:
+            env = S.SyntheticGymnasiumVec(len(env_fns), kind=CONFIG["gymnasium_kind"])
         LAST_ENVS.append(env)
         return env
 
