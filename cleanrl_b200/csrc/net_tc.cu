@@ -20,8 +20,8 @@
 //       stages ONE window of 128+maxshift rows per tile as a TMA box (cp.async.bulk.tensor; for conv1 a 3-D box
 //       whose image coordinate is the minibatch gather) and every tap is a UMMA descriptor whose start address is
 //       shifted by whole 128-byte rows (legal for SWIZZLE_128B: the pattern is a function of the smem address
-//       bits; tools/experiments/umma_shift_test.cu).  Weights stay resident in smem.  Warp 4 issues tcgen05.mma
-//       (warp-uniform loop, elected lane); warps 5-12 = two epilogue groups that own alternate tiles and drain
+//       bits; tools/experiments/umma_shift_test.cu).  Weights stay resident in smem.  Warp 0 = TMA producer, warp 1 issues tcgen05.mma
+//       (warp-uniform loop, elected lane); warps 2-9 = two epilogue groups that own alternate tiles and drain
 //       double-buffered accumulators; ReLU masks are exchanged between forward and backward as bits.
 //   tc_wgrad_win                 conv weight gradients: dW^T[(tap,c), co] = sum_r X[r+shift_tap, c] * dY[r, co]; the same
 //       row images are read as MN-major operands (rows = reduction index), taps again by row shifts; the bias
@@ -37,27 +37,16 @@ namespace b200rl {
 using namespace tc;
 typedef __nv_bfloat16 bf16;
 
-constexpr int kMaxChunks = 64;
-
+// Plain GEMM out[M, N] = A[M, 64*nchunks] . Bw[N, 64*nchunks]^T with a fused epilogue (tc_gemm_tma: fc layer)
 struct KGemmParams {
-    // ---- A operand (gathered rows)
-    const void* A;
-    const int64_t* rows;   // conv1 only: observation row gather (minibatch indices), may be null
-    int64_t M;             // valid GEMM rows per class
-    int rpi, Ws;           // rows per image and row-grid width: row -> (img, y, x)
-    int SH, SW, CP;        // source pixel grid and channels per pixel (bf16 elements)
-    int sy, sx;            // row-grid -> source-grid stride
-    int nchunks, check;    // K = 64*nchunks; check = bounds-test taps (zero fill outside)
-    signed char dy[kMaxChunks], dx[kMaxChunks];
-    int nclasses;          // 1, or 4 stride-parity classes (conv2 data-gradient)
-    int tiles_per_class;
-    // ---- B operand: packed weights [N, 64*nchunks] (+ class stride)
-    const bf16* Bw;
+    const void* A;         // row-major bf16 [M, 64*nchunks]
+    int64_t M;
+    int nchunks;           // K = 64*nchunks
+    const bf16* Bw;        // packed weights [N, 64*nchunks]
     int N;
-    int64_t b_class_stride;
     // ---- epilogue
     bf16* out;
-    int OH, OW, osy, osx, ldo;
+    int ldo;
     const float* bias;
     float scale;
     int relu;
@@ -110,7 +99,7 @@ struct WinParams {
 };
 
 template <int BN, int CPR, int STAGES, int NTAPS>
-__global__ void __launch_bounds__(416, 1) tc_conv_win(const __grid_constant__ CUtensorMap tmA, const WinParams p,
+__global__ void __launch_bounds__(320, 1) tc_conv_win(const __grid_constant__ CUtensorMap tmA, const WinParams p,
                                                       int total_tiles) {
     constexpr int B_CHUNK = BN * 128;
     constexpr uint32_t TMEM_COLS = (2 * BN) < 32 ? 32 : 2 * BN;
@@ -132,7 +121,7 @@ __global__ void __launch_bounds__(416, 1) tc_conv_win(const __grid_constant__ CU
         fence_barrier_init();
         tma_prefetch_desc(&tmA);
     }
-    if (warp == 4) tmem_alloc(&tmem_base_smem, TMEM_COLS);
+    if (warp == 1) tmem_alloc(&tmem_base_smem, TMEM_COLS);
     for (int idx = tid; idx < nchunks * BN * 8; idx += blockDim.x) {
         const int c16 = idx & 7;
         int t = idx >> 3;
@@ -151,7 +140,7 @@ __global__ void __launch_bounds__(416, 1) tc_conv_win(const __grid_constant__ CU
     const int tile_begin = (int)(((int64_t)total_tiles * blockIdx.x) / gridDim.x);
     const int tile_end = (int)(((int64_t)total_tiles * (blockIdx.x + 1)) / gridDim.x);
 
-    if (warp < 4) {
+    if (warp == 0) {
         // ======================= TMA producer: the window is one rectangular box per 64-channel column chunk ====
         if (tid == 0) {
             uint32_t q = 0;
@@ -182,7 +171,7 @@ __global__ void __launch_bounds__(416, 1) tc_conv_win(const __grid_constant__ CU
                 }
             }
         }
-    } else if (warp == 4) {
+    } else if (warp == 1) {
         // ======================= MMA issuer: the WHOLE warp walks the tile loop (uniform control flow keeps the
         // descriptor arithmetic in uniform registers), one elected lane issues.  Descriptors differ from a per-stage /
         // per-tap base only in their 14-bit start-address field, so each MMA costs two 32-bit adds.
@@ -218,12 +207,12 @@ __global__ void __launch_bounds__(416, 1) tc_conv_win(const __grid_constant__ CU
             __syncwarp();
         }
     } else {
-        // ======================= epilogue: warps 5-12 = two groups of four (one warp per TMEM lane quadrant).
+        // ======================= epilogue: warps 2-9 = two groups of four (one warp per TMEM lane quadrant).
         // Group h owns accumulator buffer h, i.e. every other tile of the CTA's range, and handles ALL BN columns
         // of its rows: the row -> (image, Y, X) -> output offset arithmetic is paid once per tile and thread, and
         // is incremental (a tile step is 256 grid rows; Y = rem / Wp by multiply-shift, exact for G*Wp < 65536).
         const int ew = warp & 3;
-        const int h = (warp - 5) >> 2;
+        const int h = (warp - 2) >> 2;
         const int lrow = ew * 32 + (tid & 31);
         const uint32_t mW = (65536u + (uint32_t)p.Wp - 1u) / (uint32_t)p.Wp;
         const int step_i = 256 / p.G, step_rem = 256 % p.G;
@@ -343,7 +332,7 @@ __global__ void __launch_bounds__(416, 1) tc_conv_win(const __grid_constant__ CU
     }
     tc_fence_before_sync();
     __syncthreads();
-    if (warp == 4) tmem_dealloc(tmem_d, TMEM_COLS);
+    if (warp == 1) tmem_dealloc(tmem_d, TMEM_COLS);
 }
 
 
@@ -711,7 +700,7 @@ static int launch_conv_win(const WinParams& p, cudaStream_t s, const char* what)
     if (p.tpi_shift) rc = make_tmap_3d(&tmA, p.A, p.n_images, p.G, (int64_t)CPR * 64, p.WR, what);
     else rc = make_tmap_2d(&tmA, p.A, p.M, (int64_t)CPR * 64, p.WR, what);
     if (rc) return rc;
-    tc_conv_win<BN, CPR, STAGES, NTAPS><<<grid, 416, smem, s>>>(tmA, p, total);
+    tc_conv_win<BN, CPR, STAGES, NTAPS><<<grid, 320, smem, s>>>(tmA, p, total);
     return check_launch(what);
 }
 
@@ -1013,13 +1002,10 @@ __global__ void __launch_bounds__(256) tc_fold_win(const float* __restrict__ ws,
     dst[o] = s;
 }
 
-// fold partials ws[S][KX][NY] -> fp32 gradient in the REFERENCE's parameter layout.
-// mode 0: dst[co][k] (conv1: K order (c,ky,kx) == torch's)                      src (k, co)
-// mode 1: dst[co][c][ky][kx] from K order (ky,kx,c) with C channels, KK taps       src (k, co)
-// mode 2: dst[o][c*49 + p] from X-side = o (rows), Y-side k = p*64 + c (fc)         src (o, k)
-// mode 3: conv1 on space-to-depth frames (K order (a,b,c,sy,sx))                    src (k, co)
-__global__ void tc_fold_kernel(const float* __restrict__ ws, int S, int KX, int NY, int validX, int validY,
-                               int mode, int C, int KK, float scale, float* __restrict__ dst) {
+// fold the fc weight-gradient partials ws[S][KX rows = o][NY cols = k], k = p*64 + c, into the REFERENCE's layout
+// dst[o][c*49 + p] (torch flattens NCHW activations channel-major); partial slabs are added in ascending order.
+__global__ void tc_fold_fc(const float* __restrict__ ws, int S, int KX, int NY, int validX, int validY,
+                           int C, int KK, float scale, float* __restrict__ dst) {
     const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     const int64_t total = (int64_t)validX * validY;
     if (idx >= total) return;
@@ -1027,23 +1013,8 @@ __global__ void tc_fold_kernel(const float* __restrict__ ws, int S, int KX, int 
     float s = 0.f;
     const int64_t slab = (int64_t)KX * NY;
     for (int z = 0; z < S; ++z) s += ws[z * slab + (int64_t)xi * NY + yi];
-    s *= scale;
-    int64_t o;
-    if (mode == 0) {
-        o = (int64_t)yi * validX + xi;
-    } else if (mode == 1) {
-        const int tap = xi / C, c = xi - tap * C;          // xi = tap*C + c
-        o = ((int64_t)yi * C + c) * KK + tap;
-    } else if (mode == 2) {
-        const int pp = yi / C, c = yi - pp * C;            // yi = p*64 + c ; torch flatten index = c*49 + p
-        o = (int64_t)xi * validY + (int64_t)c * KK + pp;
-    } else {
-        // conv1 on space-to-depth frames: xi = (a*2+b)*64 + c*16 + sy*4 + sx -> dst[co][c][4a+sy][4b+sx]
-        const int tap = xi >> 6, rr = xi & 63;
-        const int c = rr >> 4, sy = (rr >> 2) & 3, sx = rr & 3;
-        o = (((int64_t)yi * 4 + c) * 8 + ((tap >> 1) * 4 + sy)) * 8 + (tap & 1) * 4 + sx;
-    }
-    dst[o] = s;
+    const int pp = yi / C, c = yi - pp * C;
+    dst[(int64_t)xi * validY + (int64_t)c * KK + pp] = s * scale;
 }
 
 // column sums of a bf16 matrix [M, ld] (bias gradients): two-level deterministic reduction.
@@ -1388,23 +1359,10 @@ struct NatureActs {   // bf16 element offsets inside the (zero-initialised) acti
     }
 };
 
-static void gemm_defaults(KGemmParams& p) {
+static void gemm_rowmajor(KGemmParams& p, const bf16* x, int64_t n, int nchunks) {   // x [n, 64*nchunks]
     memset(&p, 0, sizeof(p));
-    p.nclasses = 1;
     p.scale = 1.f;
-    p.osy = p.osx = 1;
-    p.sy = p.sx = 1;
-}
-static void set_rows(KGemmParams& p, int64_t M, int rpi, int Ws) {
-    p.M = M; p.rpi = rpi; p.Ws = Ws;
-    p.tiles_per_class = (int)ceil_div(M, 128);
-}
-
-static void rowmajor_gather(KGemmParams& p, const bf16* x, int64_t n, int nchunks) {   // x [n, 64*nchunks]
-    p.A = x;
-    set_rows(p, n, 1, 1);
-    p.SH = 1; p.SW = nchunks; p.CP = 64; p.nchunks = nchunks; p.check = 0;
-    for (int j = 0; j < nchunks; ++j) { p.dy[j] = 0; p.dx[j] = (signed char)j; }
+    p.A = x; p.M = n; p.nchunks = nchunks;
 }
 
 
@@ -1577,8 +1535,8 @@ extern "C" int b200rl_naturecnn_bf16_forward(const void* obs, int obs_format, co
     { ProfScope ps(s, "conv3_fwd", 2.0 * n * 49 * 64 * 576, (double)n * ((5184 + 3136) * 2 + 392));
       if ((rc = launch_conv_win<64, 1, 6, 9>(wp, s, "naturecnn/conv3"))) return rc; }
     // fc -> hidden [n,512]
-    gemm_defaults(p); rowmajor_gather(p, act + Q.act3, n, 49);
-    p.Bw = P + L.wfcf; p.N = 512; p.out = act + Q.hid; p.OH = 1; p.OW = 1; p.ldo = 512; p.bias = params + L.fcb; p.relu = 1;
+    gemm_rowmajor(p, act + Q.act3, n, 49);
+    p.Bw = P + L.wfcf; p.N = 512; p.out = act + Q.hid; p.ldo = 512; p.bias = params + L.fcb; p.relu = 1;
     p.mask_out = reinterpret_cast<uint32_t*>(act + Q.m4);
     { ProfScope ps(s, "fc_fwd", 2.0 * n * 512 * 3136, (double)n * (3136 + 512) * 2 + 512.0 * 3136 * 2);
       // small batches (rollout step): narrower N tiles => 4x more CTAs for the same work
@@ -1655,12 +1613,12 @@ extern "C" int b200rl_naturecnn_bf16_backward(const void* obs, int obs_format, c
           tc_wgrad_tma<<<dim3(pl.splits, 4, 13), 160, smem, s>>>(tmX, tmY, n, pl.rows_per_cta, 2, 4, wsbig);
           if ((rc = check_launch("naturecnn/fc_wgrad"))) return rc; }
         { ProfScope ps(s, "wgrad_fold_bias", 0, 0);
-          note_launches(1); tc_fold_kernel<<<(unsigned)ceil_div((int64_t)512 * 3136, 256), 256, 0, s>>>(wsbig, pl.splits, 512, 13 * 256, 512, 3136, 2, 64, 49, 1.f, grads + L.fcw);
+          note_launches(1); tc_fold_fc<<<(unsigned)ceil_div((int64_t)512 * 3136, 256), 256, 0, s>>>(wsbig, pl.splits, 512, 13 * 256, 512, 3136, 64, 49, 1.f, grads + L.fcw);
           if ((rc = colsum(act + Q.dhid, n, 512, 512, wssmall, grads + L.fcb, s))) return rc; }
         // dact3_pre = (dhid . Wfc) * (act3 > 0), written on the 9x9 linear grid and the zero-padded 11x11 grid
-        gemm_defaults(p); rowmajor_gather(p, act + Q.dhid, n, 8);
+        gemm_rowmajor(p, act + Q.dhid, n, 8);
         p.Bw = P + L.wfcdg; p.N = 3136; p.out = act + Q.dact3a; p.out2 = act + Q.dact3b; p.dual_dact3 = 1;
-        p.OH = 1; p.OW = 1; p.ldo = 3136; p.mask_bits = reinterpret_cast<const uint32_t*>(act + Q.m3);
+        p.ldo = 3136; p.mask_bits = reinterpret_cast<const uint32_t*>(act + Q.m3);
         { ProfScope ps(s, "fc_dgrad", 2.0 * n * 512 * 3136, (double)n * ((3136 + 512) * 2 + 392) + 512.0 * 3136 * 2);
           if ((rc = launch_gemm_tma<256, 4>(p, s, "naturecnn/fc_dgrad"))) return rc; }
     }
