@@ -1134,16 +1134,36 @@ __global__ void tc_pack_conv_s2_classes(const float* __restrict__ w, int Cout, i
     const int py = cls >> 1, px = cls & 1, a = ab >> 1, b = ab & 1;
     dg[idx] = __float2bfloat16(w[(((int64_t)co * Cin + c) * 4 + (py + 2 * a)) * 4 + (px + 2 * b)]);
 }
-// fc weight w[o][c*49+p] -> fwd[o][p*64+c]; dgrad[p*64+c][o]
-__global__ void tc_pack_fc(const float* __restrict__ w, int O, int C, int PP, bf16* __restrict__ fwd, bf16* __restrict__ dgrad) {
-    const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    const int64_t total = (int64_t)O * C * PP;
-    if (idx >= total) return;
-    const int pp = (int)(idx % PP); int64_t t = idx / PP;
-    const int c = (int)(t % C); const int o = (int)(t / C);
-    const bf16 v = __float2bfloat16(w[idx]);
-    fwd[(int64_t)o * (C * PP) + pp * C + c] = v;
-    dgrad[((int64_t)pp * C + c) * O + o] = v;
+// fc weight w[o][c*49+p] -> fwd[o][p*64+c]; dgrad[p*64+c][o].  Block = 8 output rows x 7 pixels x all 64 channels,
+// staged through shared memory so that both packed layouts are written with 16-byte stores
+// (fwd: 8 consecutive c of one (o, p); dgrad: the 8 o of one (p, c)).  Requires O % 8 == 0, PP % 7 == 0, C == 64.
+__global__ void __launch_bounds__(256) tc_pack_fc(const float* __restrict__ w, int O, int PP, bf16* __restrict__ fwd,
+                                                  bf16* __restrict__ dgrad) {
+    constexpr int C = 64, PS = 7, R = 8;
+    __shared__ float sw[R * C * PS];                    // [r][c][pl]
+    const int K = C * PP;
+    const int o0 = blockIdx.x * R, p0 = blockIdx.y * PS;
+    for (int i = threadIdx.x; i < R * C * PS; i += blockDim.x) {
+        const int pl = i % PS, rc = i / PS;             // rc = r*64 + c
+        sw[i] = w[(int64_t)(o0 + (rc >> 6)) * K + (rc & 63) * PP + p0 + pl];
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < R * PS * (C / 8); i += blockDim.x) {      // fwd[o][p*64 + c0 .. c0+7]
+        const int g = i & 7, pl = (i >> 3) % PS, r = i / (8 * PS);
+        const float* src = sw + (r * C + g * 8) * PS + pl;
+        int4 v;
+        v.x = (int)pack_bf16x2(src[0 * PS], src[1 * PS]); v.y = (int)pack_bf16x2(src[2 * PS], src[3 * PS]);
+        v.z = (int)pack_bf16x2(src[4 * PS], src[5 * PS]); v.w = (int)pack_bf16x2(src[6 * PS], src[7 * PS]);
+        *reinterpret_cast<int4*>(fwd + (int64_t)(o0 + r) * K + (p0 + pl) * C + g * 8) = v;
+    }
+    for (int i = threadIdx.x; i < PS * C; i += blockDim.x) {                 // dgrad[p*64 + c][o0 .. o0+7]
+        const int c = i & 63, pl = i >> 6;
+        const float* src = sw + c * PS + pl;
+        int4 v;
+        v.x = (int)pack_bf16x2(src[0 * C * PS], src[1 * C * PS]); v.y = (int)pack_bf16x2(src[2 * C * PS], src[3 * C * PS]);
+        v.z = (int)pack_bf16x2(src[4 * C * PS], src[5 * C * PS]); v.w = (int)pack_bf16x2(src[6 * C * PS], src[7 * C * PS]);
+        *reinterpret_cast<int4*>(dgrad + ((int64_t)(p0 + pl) * C + c) * O + o0) = v;
+    }
 }
 
 // ------------------------------------------------------------------ policy/value heads (tiny: CUDA cores, fp32 math)
@@ -1488,7 +1508,7 @@ extern "C" int b200rl_naturecnn_bf16_pack(const float* params, int A, void* pack
     tc_pack_conv2_cells<<<128, 256, 0, s>>>(params + L.c2w, P + L.w2f);
     tc_pack_conv_s2_classes<<<(unsigned)ceil_div(32768, 256), 256, 0, s>>>(params + L.c2w, 64, 32, P + L.w2dg);
     tc_pack_conv<<<(unsigned)ceil_div(36864, 256), 256, 0, s>>>(params + L.c3w, 64, 64, 3, 3, 0, P + L.w3f, P + L.w3dg);
-    tc_pack_fc<<<(unsigned)ceil_div(512 * 3136, 256), 256, 0, s>>>(params + L.fcw, 512, 64, 49, P + L.wfcf, P + L.wfcdg);
+    tc_pack_fc<<<dim3(512 / 8, 49 / 7), 256, 0, s>>>(params + L.fcw, 512, 49, P + L.wfcf, P + L.wfcdg);
     return check_launch("naturecnn_pack", 5);
 }
 
