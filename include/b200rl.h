@@ -213,9 +213,9 @@ int b200rl_linear_bwd_weight_f32(const float* x, const int64_t* rows, const floa
 /* ------------------------------------------- NatureCNN, bf16 tensor cores ---
  * The throughput path of Agent.network/actor/critic (cleanrl/ppo_atari_envpool.py:123-149):
  * every conv / linear contraction (forward, data-gradient, weight-gradient) is an implicit GEMM
- * on tcgen05.mma with bf16 operands and fp32 accumulation in TMEM; the uint8 frames are gathered
- * (optionally through minibatch indices) and converted inside the conv1 kernels; the two heads
- * (A+1 outputs) run in fp32 on CUDA cores.
+ * on tcgen05.mma with bf16 operands and fp32 accumulation in TMEM, fed by TMA; a minibatch gather
+ * (rows) is the image coordinate of conv1's TMA boxes, nothing is materialised; the two heads
+ * (A+1 outputs, 1 <= A <= 31) run in fp32 on CUDA cores.
  *
  * params / grads: ONE flat f32 vector in libb200rl order
  *     conv1.w[32,4,8,8] conv1.b[32] conv2.w[64,32,4,4] conv2.b[64] conv3.w[64,64,3,3] conv3.b[64]
@@ -231,7 +231,9 @@ int b200rl_linear_bwd_weight_f32(const float* x, const int64_t* rows, const floa
  *          env step by b200rl_frames_to_s2d_bf16 (channel = c*16 + sy*4 + sx of pixel (4Y+sy, 4X+sx)):
  *          conv1 (8x8 stride 4) is then a 2x2 stride-1 convolution over 128-byte pixels and the 16
  *          minibatch passes of an iteration never touch / convert the uint8 frames again.
- *          rows (i64 [n], may be NULL) selects the samples (ppo.py:250 gather) in either format.
+ *          rows (i64 [n], may be NULL) selects the samples (ppo.py:250 gather) in either format; the
+ *          indices are the caller's contract (not range-checked); ascending order keeps the gather
+ *          DRAM-page friendly (the engine sorts every minibatch).
  * head_out / dhead : f32 [n, A+1] = [logits | value] and its gradient.
  */
 enum { B200RL_OBS_U8_NCHW = 0, B200RL_OBS_S2D_BF16 = 1 };

@@ -152,3 +152,46 @@ def test_bf16_rollout_path_matches_fp32_path(lib):
     assert (v32 - v16).abs().max().item() < 2e-2 * max(1.0, v32.abs().max().item())
     assert (lp32 - lp16).abs().max().item() < 2e-2
     assert (a32 != a16).float().mean().item() < 0.02
+
+
+def test_full_size_minibatch_properties(lib):
+    """Size-independent properties at BASELINE.json's full minibatch (M = 32 768 rows gathered from a 131 072-frame
+    rollout, sorted indices as the engine passes them):
+      * batch invariance: a row's logits/value do not depend on which other rows share its tiles -- the first and
+        last 64 rows of the big batch equal a 64-row batch of the same frames bit for bit;
+      * additivity: the gradient of the full minibatch equals the sum of the gradients of its four quarters
+        (different tile/CTA partition and split reduction order => fp32 re-association only)."""
+    from cleanrl_b200 import ops
+    from cleanrl_b200.agents import NatureCNNAgent
+    torch.manual_seed(7)
+    dev = torch.device("cuda")
+    agent = NatureCNNAgent(_Envs(4)).to(dev)
+    agent.precision = "bf16"
+    B, M = 131072, 32768
+    pool = torch.randint(0, 256, (256, 4, 84, 84), dtype=torch.uint8, device=dev)
+    s2d_pool = ops.frames_to_s2d(pool)
+    roll = s2d_pool[torch.randint(0, 256, (B,), device=dev)].contiguous()          # [B,21,21,64] bf16, 7.4 GB
+    inds = torch.randperm(B, device=dev)[:M].sort().values.contiguous()
+    lg, v = agent.forward_train(roll, inds)
+    lg, v = lg.clone(), v.clone()
+    g = torch.Generator(device="cpu").manual_seed(1)
+    dl_all = (torch.randn(M, 4, generator=g) * 1e-3).to(dev); dv_all = (torch.randn(M, generator=g) * 1e-3).to(dev)
+    dhead, dl, dv = agent.alloc_head_grad(M, dev)
+    dl.copy_(dl_all); dv.copy_(dv_all)
+    agent.backward(dhead)
+    g_full = agent.flat.grad.clone()
+    for sl in (slice(0, 64), slice(M - 64, M)):
+        lg_s, v_s = agent.forward_train(roll, inds[sl].contiguous())
+        assert torch.equal(lg_s, lg[sl]) and torch.equal(v_s, v[sl])
+    g_sum = torch.zeros_like(g_full)
+    Q = M // 4
+    for q in range(4):
+        sl = slice(q * Q, (q + 1) * Q)
+        agent.forward_train(roll, inds[sl].contiguous())
+        dh, dlq, dvq = agent.alloc_head_grad(Q, dev)
+        dlq.copy_(dl_all[sl]); dvq.copy_(dv_all[sl])
+        agent.backward(dh)
+        g_sum += agent.flat.grad
+    rel = ((g_sum - g_full).double().norm() / g_full.double().norm()).item()
+    assert rel < 1e-4, rel
+    assert torch.isfinite(g_full).all() and g_full.abs().max().item() > 0
