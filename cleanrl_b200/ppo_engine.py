@@ -4,12 +4,16 @@ This is the loop body of the reference scripts (cleanrl/ppo.py:185-310 and its
 twins in ppo_atari_envpool.py / ppo_atari_multigpu.py) re-designed around
 device-resident buffers and fused kernels:
 
-* observations stay uint8 end to end: pinned host batch -> async H2D straight
-  into the rollout slot ``obs[t]`` (the reference converts to fp32 on the host
-  and keeps a 14.8 GB fp32 buffer, ppo_atari_envpool.py:203,239);
+* observations cross PCIe as uint8: pinned host batch -> async H2D in chunks on a
+  copy stream while the compute stream already converts / evaluates the chunks
+  that have landed; the rollout slot ``obs[t]`` holds them as space-to-depth bf16
+  (tensor-core path, converted once per env step) or uint8 (exact fp32 path).
+  The reference converts to fp32 on the host and keeps a 14.8 GB fp32 buffer
+  (ppo_atari_envpool.py:203,239);
 * rewards / dones are kept in pinned host memory during the rollout and
   uploaded once per iteration (the reference does 2 H2D + N scalar syncs per step);
-* one launch per network layer + one sampler launch per env step, no autograd;
+* one launch per network layer + one sampler launch per env step, replayed as a
+  CUDA graph per rollout slot, no autograd;
 * GAE is one kernel; the loss (+its gradient) is one kernel; clip+Adam is one
   fused pass over a flat parameter vector; the DP gradient exchange is ONE
   in-place all-reduce of that flat vector (ppo_atari_multigpu.py:360-374).
