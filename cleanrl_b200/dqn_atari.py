@@ -147,6 +147,19 @@ def main(argv=None, writer_factory=None, env_factory=None, on_update=None):
         model_path = f"runs/{run_name}/{args.exp_name}.cleanrl_model"
         torch.save({k: v.detach().cpu() for k, v in q_network.state_dict().items()}, model_path)
         print(f"model saved to {model_path}")
+        # evaluation of the saved model as the reference does (dqn_atari.py:248-261): 10 episodes, epsilon = end_e
+        from cleanrl_b200.evals import evaluate_q
+
+        eval_args = type(args)(**{**vars(args), "num_envs": 1})
+        eval_envs = env_factory(eval_args) if env_factory else make_envs(eval_args, f"{run_name}-eval")
+        episodic_returns = evaluate_q(model_path, None, args.env_id, eval_episodes=10, run_name=f"{run_name}-eval",
+                                      Model=QNetwork, device=device, epsilon=args.end_e, envs=eval_envs)
+        eval_envs.close()
+        for idx, episodic_return in enumerate(episodic_returns):
+            writer.add_scalar("eval/episodic_return", float(np.asarray(episodic_return).reshape(-1)[0]), idx)
+        if args.upload_model:
+            print("[cleanrl_b200] --upload-model needs cleanrl_utils.huggingface (not part of the hot path); skipped",
+                  file=sys.stderr)
 
     envs.close()
     writer.close()

@@ -122,3 +122,27 @@ def test_dqn_script_vs_reference_run(lib, precision):
     assert np.isfinite(got).all()
     tags = {t for t, _, _ in writers[0].scalars}
     assert {"losses/td_loss", "losses/q_values", "charts/SPS"} <= tags
+
+
+@pytest.mark.gpu
+def test_dqn_save_model_and_evaluate(lib, tmp_path, monkeypatch):
+    """--save-model writes a reference-compatible state_dict and evaluates it epsilon-greedily for 10 episodes
+    (cleanrl/dqn_atari.py:244-261, cleanrl_utils/evals/dqn_eval.py), logging eval/episodic_return."""
+    import torch
+    from cleanrl_b200 import dqn_atari as S
+    monkeypatch.chdir(tmp_path)
+    writers = []
+
+    def wf(p):
+        w = _Writer(); writers.append(w); return w
+
+    qn = S.main(["--total-timesteps", "120", "--learning-starts", "40", "--buffer-size", "64", "--batch-size", "8",
+                 "--train-frequency", "4", "--seed", "1", "--synthetic-env", "--save-model"], writer_factory=wf)
+    files = list(tmp_path.glob("runs/*/dqn_atari.cleanrl_model"))
+    assert len(files) == 1
+    sd = torch.load(files[0])
+    assert list(sd.keys()) == list(qn.state_dict().keys())
+    for k, v in qn.state_dict().items():
+        assert torch.equal(sd[k], v.detach().cpu()), k
+    evals = [(step, v) for tag, v, step in writers[0].scalars if tag == "eval/episodic_return"]
+    assert [s for s, _ in evals] == list(range(10)) and all(np.isfinite(v) for _, v in evals)
