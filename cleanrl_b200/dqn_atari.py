@@ -31,32 +31,28 @@ def linear_schedule(start_e: float, end_e: float, duration: int, t: int):
     return max(slope * t + start_e, end_e)
 
 
+def make_env(env_id, seed, idx, capture_video, run_name):
+    """The reference's wrapped Atari env thunk (dqn_atari.py:83-104; also what dqn_eval.py calls); only usable when
+    gymnasium + ALE are installed."""
+    def thunk():
+        import gymnasium as gym  # type: ignore
+        from cleanrl_b200.ppo_atari import make_env as atari_env
+
+        env = atari_env(env_id, idx, capture_video, run_name)()      # same wrapper stack as the PPO Atari scripts
+        env.action_space.seed(seed)
+        return env
+
+    return thunk
+
+
 def make_envs(args, run_name):
-    """gymnasium Atari SyncVectorEnv as the reference (dqn_atari.py:83-104,163-166) when available, else synthetic."""
+    """gymnasium Atari SyncVectorEnv as the reference (dqn_atari.py:163-166) when available, else synthetic."""
     if not args.synthetic_env:
         try:
             import gymnasium as gym  # type: ignore
-            from cleanrl_utils.atari_wrappers import (ClipRewardEnv, EpisodicLifeEnv, FireResetEnv,  # type: ignore
-                                                      MaxAndSkipEnv, NoopResetEnv)
 
-            def make_env(seed, idx):
-                def thunk():
-                    env = gym.make(args.env_id)
-                    env = gym.wrappers.RecordEpisodeStatistics(env)
-                    env = NoopResetEnv(env, noop_max=30)
-                    env = MaxAndSkipEnv(env, skip=4)
-                    env = EpisodicLifeEnv(env)
-                    if "FIRE" in env.unwrapped.get_action_meanings():
-                        env = FireResetEnv(env)
-                    env = ClipRewardEnv(env)
-                    env = gym.wrappers.ResizeObservation(env, (84, 84))
-                    env = gym.wrappers.GrayScaleObservation(env)
-                    env = gym.wrappers.FrameStack(env, 4)
-                    env.action_space.seed(seed)
-                    return env
-                return thunk
-
-            return gym.vector.SyncVectorEnv([make_env(args.seed + i, i) for i in range(args.num_envs)])
+            return gym.vector.SyncVectorEnv([make_env(args.env_id, args.seed + i, i, args.capture_video, run_name)
+                                             for i in range(args.num_envs)])
         except ImportError:
             print("[cleanrl_b200] gymnasium/ALE not installed: using SyntheticGymnasiumVec(atari) (synthetic data)", file=sys.stderr)
     from cleanrl_b200.synthetic_envs import SyntheticGymnasiumVec

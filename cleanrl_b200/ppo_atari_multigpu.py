@@ -31,30 +31,18 @@ Args = cli.ppo_atari_multigpu_args(os.path.basename(__file__)[: -len(".py")])
 run_name = None
 
 
+from cleanrl_b200.ppo_atari import make_env  # noqa: E402,F401  (same wrapper stack, ppo_atari_multigpu.py:105-124)
+
+
 def make_envs(args, run_name):
-    """gymnasium SyncVectorEnv of wrapped Atari envs as the reference (ppo_atari_multigpu.py:105-124,225-227)
-    when gymnasium + cleanrl_utils are importable; otherwise the seeded synthetic gymnasium-style vec env."""
+    """gymnasium SyncVectorEnv of wrapped Atari envs as the reference (ppo_atari_multigpu.py:225-227) when
+    gymnasium + cleanrl_utils are importable; otherwise the seeded synthetic gymnasium-style vec env."""
     if not args.synthetic_env:
         try:
             import gymnasium as gym  # type: ignore
-            from cleanrl_utils.atari_wrappers import (ClipRewardEnv, EpisodicLifeEnv, FireResetEnv,  # type: ignore
-                                                      MaxAndSkipEnv, NoopResetEnv)
 
-            def thunk():
-                env = gym.make(args.env_id)
-                env = gym.wrappers.RecordEpisodeStatistics(env)
-                env = NoopResetEnv(env, noop_max=30)
-                env = MaxAndSkipEnv(env, skip=4)
-                env = EpisodicLifeEnv(env)
-                if "FIRE" in env.unwrapped.get_action_meanings():
-                    env = FireResetEnv(env)
-                env = ClipRewardEnv(env)
-                env = gym.wrappers.ResizeObservation(env, (84, 84))
-                env = gym.wrappers.GrayScaleObservation(env)
-                env = gym.wrappers.FrameStack(env, 4)
-                return env
-
-            return gym.vector.SyncVectorEnv([thunk for _ in range(args.local_num_envs)])
+            return gym.vector.SyncVectorEnv([make_env(args.env_id, i, args.capture_video, run_name)
+                                             for i in range(args.local_num_envs)])
         except ImportError:
             print("[cleanrl_b200] gymnasium/ALE not installed: using SyntheticGymnasiumVec(atari) (synthetic data)",
                   file=sys.stderr)

@@ -119,3 +119,19 @@ def test_cli_fields_match_reference_args(script, factory):
         assert helps and helps[0] == doc, (name, helps, doc)
     extra = set(fields) - set(ref)
     assert extra <= {"precision", "gae_kernel", "synthetic_env", "huber_loss"}, extra
+
+
+@pytest.mark.reference
+@pytest.mark.parametrize("script", ["ppo.py", "ppo_atari.py", "ppo_atari_envpool.py", "ppo_atari_multigpu.py",
+                                    "ppo_continuous_action.py", "dqn_atari.py"])
+def test_module_level_names_match_reference(script):
+    """Every top-level class / function of the reference script (what tuner.py, the eval helpers and user code
+    import: Args, make_env, layer_init, Agent / QNetwork, RecordEpisodeStatistics, linear_schedule) exists in the
+    drop-in module under the same name."""
+    import ast
+    import importlib
+    tree = ast.parse((Path("/root/reference/cleanrl") / script).read_text())
+    names = [n.name for n in tree.body if isinstance(n, (ast.ClassDef, ast.FunctionDef))]
+    mod = importlib.import_module("cleanrl_b200." + script[:-3])
+    missing = [n for n in names if not hasattr(mod, n)]
+    assert names and not missing, (script, missing)
