@@ -259,3 +259,23 @@ def test_ppo_learns_cartpole(lib):
     first, last = float(np.mean(rets[:20])), float(np.mean(rets[-20:]))
     print(f"CartPole: {len(rets)} episodes, mean return first 20 = {first:.1f}, last 20 = {last:.1f}")
     assert first < 60 and last > 150, (first, last)
+
+
+def test_script_runs_under_runpy_like_the_tuner(lib, tmp_path, monkeypatch):
+    """cleanrl_utils/tuner.py:90-98 launches a script with runpy.run_path(..., run_name="__main__") after setting
+    sys.argv, then reads ``run_name`` from the returned globals and the TensorBoard event file under runs/{run_name}."""
+    import runpy
+    import sys
+    from conftest import ROOT
+    monkeypatch.chdir(tmp_path)
+    monkeypatch.setattr(sys, "argv", ["ppo.py", "--total-timesteps", "1024", "--seed", "3", "--synthetic-env"])
+    g = runpy.run_path(str(ROOT / "cleanrl_b200" / "ppo.py"), run_name="__main__")
+    assert isinstance(g["run_name"], str) and g["run_name"].startswith("CartPole-v1__ppo__3__")
+    events = list((tmp_path / "runs" / g["run_name"]).glob("events.out.tfevents.*"))
+    assert len(events) == 1
+    from tensorboard.backend.event_processing.event_accumulator import EventAccumulator
+    ea = EventAccumulator(str(events[0].parent)); ea.Reload()
+    tags = set(ea.Tags()["scalars"])
+    assert {"charts/learning_rate", "losses/value_loss", "losses/policy_loss", "losses/entropy", "losses/approx_kl",
+            "losses/clipfrac", "losses/explained_variance", "charts/SPS"} <= tags
+    assert [e.step for e in ea.Scalars("charts/SPS")] == [512, 1024]
