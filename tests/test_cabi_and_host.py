@@ -7,6 +7,7 @@ import subprocess
 import sys
 from pathlib import Path
 
+import numpy as np
 import pytest
 
 ROOT = Path(__file__).resolve().parent.parent
@@ -135,3 +136,34 @@ def test_module_level_names_match_reference(script):
     mod = importlib.import_module("cleanrl_b200." + script[:-3])
     missing = [n for n in names if not hasattr(mod, n)]
     assert names and not missing, (script, missing)
+
+
+def test_cartpole_vec_dynamics_and_episode_bookkeeping():
+    """CartPoleVec (host-side env for the learning-curve test): a random policy lasts ~22 steps on average, a
+    bang-bang controller on the pole angle + angular velocity reaches the 500-step truncation, and final_info
+    carries return == length at every episode end."""
+    from cleanrl_b200.synthetic_envs import CartPoleVec
+    env = CartPoleVec(4)
+    obs, _ = env.reset(seed=1)
+    rng = np.random.default_rng(0)
+    rets = []
+    for _ in range(4000):
+        obs, r, te, tr, info = env.step(rng.integers(0, 2, 4))
+        assert obs.dtype == np.float32 and obs.shape == (4, 4) and (r == 1).all() and not (te & tr).any()
+        if "final_info" in info:
+            for i, f in enumerate(info["final_info"]):
+                assert (f is not None) == bool(te[i] or tr[i])
+                if f is not None:
+                    assert float(f["episode"]["r"][0]) == float(f["episode"]["l"][0])
+                    rets.append(float(f["episode"]["r"][0]))
+    assert 15 < np.mean(rets) < 35, np.mean(rets)
+    obs, _ = env.reset(seed=2)
+    truncs = 0
+    for _ in range(1200):
+        obs, r, te, tr, info = env.step((obs[:, 2] + 0.5 * obs[:, 3] > 0).astype(np.int64))
+        truncs += int(tr.sum())
+        if "final_info" in info:
+            for f in info["final_info"]:
+                if f is not None:
+                    assert float(f["episode"]["r"][0]) <= 500
+    assert truncs >= 4, truncs
