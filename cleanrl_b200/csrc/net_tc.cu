@@ -1541,7 +1541,7 @@ extern "C" int b200rl_naturecnn_bf16_forward(const void* obs, int obs_format, co
     wp.Bw = P + L.w1f; wp.N = 32; wp.vH = 20; wp.vW = 20; wp.out_mode = WOUT_S2D2; wp.out = act + Q.act1;
     wp.bias = params + L.c1b; wp.scale = 1.0f / 255.0f; wp.relu = 1; wp.mask_out = reinterpret_cast<uint32_t*>(act + Q.m1);
     { ProfScope ps(s, "conv1_fwd", 2.0 * n * 400 * 32 * 256, (double)n * ((28224 + 12800) * 2 + 1600));
-      if ((rc = launch_conv_win<32, 1, 6, 4>(wp, s, "naturecnn/conv1"))) return rc; }
+      if ((rc = launch_conv_win<32, 1, 9, 4>(wp, s, "naturecnn/conv1"))) return rc; }
     // conv2: 2x2 window conv on the 128-channel cells -> act2 [n,9,9,64]
     win_defaults(wp); win_conv2(wp, act + Q.act1, n);
     wp.Bw = P + L.w2f; wp.N = 64; wp.vH = 9; wp.vW = 9; wp.out_mode = WOUT_DENSE; wp.out = act + Q.act2;
