@@ -214,7 +214,7 @@ extern "C" size_t b200rl_naturecnn_bf16_workspace_bytes(int64_t n, int A) {
 }
 
 extern "C" int b200rl_naturecnn_bf16_pack(const float* params, int A, void* packed, void* stream) {
-    B200RL_REQUIRE(params && packed && A >= 1 && A < kMaxHeads, "naturecnn_pack: bad arguments (A must be in [1,31])");
+    B200RL_REQUIRE(params && packed && A >= 1 && A < kMaxHeads, "naturecnn_pack: bad arguments (A must be in [1,23])");
     B200RL_REQUIRE(aligned(packed, 16), "naturecnn_pack: packed buffer must be 16-B aligned");
     const NatureLayout L(A);
     bf16* P = reinterpret_cast<bf16*>(packed);
@@ -234,7 +234,7 @@ extern "C" int b200rl_naturecnn_bf16_forward(const void* obs, int obs_format, co
     B200RL_REQUIRE(n >= 0, "naturecnn_forward: negative n");
     if (n == 0) return B200RL_OK;
     B200RL_REQUIRE(obs && params && packed && acts && head_out, "naturecnn_forward: null pointer");
-    B200RL_REQUIRE(A >= 1 && A < kMaxHeads, "naturecnn_forward: A=%d outside [1,31]", A);
+    B200RL_REQUIRE(A >= 1 && A < kMaxHeads, "naturecnn_forward: A=%d outside [1,23]", A);
     B200RL_REQUIRE(obs_format == B200RL_OBS_U8_NCHW || obs_format == B200RL_OBS_S2D_BF16, "naturecnn_forward: bad obs_format %d", obs_format);
     B200RL_REQUIRE(aligned(obs, 16) && aligned(acts, 16) && aligned(packed, 16), "naturecnn_forward: misaligned buffer");
     B200RL_REQUIRE(n <= (int64_t)1 << 22, "naturecnn_forward: n too large");
@@ -291,7 +291,7 @@ extern "C" int b200rl_naturecnn_bf16_backward(const void* obs, int obs_format, c
                                               void* workspace, size_t workspace_bytes, void* stream) {
     B200RL_REQUIRE(n >= 1, "naturecnn_backward: n must be >= 1");
     B200RL_REQUIRE(obs && params && packed && acts && dhead && grads && workspace, "naturecnn_backward: null pointer");
-    B200RL_REQUIRE(A >= 1 && A < kMaxHeads, "naturecnn_backward: A=%d outside [1,31]", A);
+    B200RL_REQUIRE(A >= 1 && A < kMaxHeads, "naturecnn_backward: A=%d outside [1,23]", A);
     B200RL_REQUIRE(aligned(workspace, 16), "naturecnn_backward: workspace misaligned");
     const size_t need = b200rl_naturecnn_bf16_workspace_bytes(n, A);
     if (workspace_bytes < need) return fail(B200RL_ERR_WORKSPACE, "naturecnn_backward: workspace %zu < %zu", workspace_bytes, need);

@@ -215,7 +215,7 @@ int b200rl_linear_bwd_weight_f32(const float* x, const int64_t* rows, const floa
  * every conv / linear contraction (forward, data-gradient, weight-gradient) is an implicit GEMM
  * on tcgen05.mma with bf16 operands and fp32 accumulation in TMEM, fed by TMA; a minibatch gather
  * (rows) is the image coordinate of conv1's TMA boxes, nothing is materialised; the two heads
- * (A+1 outputs, 1 <= A <= 31) run in fp32 on CUDA cores.
+ * (A+1 outputs, 1 <= A <= 23) run in fp32 on CUDA cores.
  *
  * params / grads: ONE flat f32 vector in libb200rl order
  *     conv1.w[32,4,8,8] conv1.b[32] conv2.w[64,32,4,4] conv2.b[64] conv3.w[64,64,3,3] conv3.b[64]
