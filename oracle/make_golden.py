@@ -129,8 +129,14 @@ def main():
         atari_envpool("ppo_atari_gym_n8_t32_seed2.npz",
                       ["--no-cuda", "--num-envs", "8", "--num-steps", "32", "--total-timesteps", "512", "--seed", "2"], 2,
                       script="ppo_atari.py")
-        if only:
-            return
+    if not only or "ppo_atari_flags" in only:
+        # flag coverage: no advantage normalisation, early stop on target_kl, other clip / coefficient values
+        atari_envpool("ppo_atari_envpool_n8_t16_seed5_flags.npz",
+                      ["--no-cuda", "--num-envs", "8", "--num-steps", "16", "--total-timesteps", "384", "--seed", "5",
+                       "--no-norm-adv", "--target-kl", "0.0005", "--max-grad-norm", "0.3", "--vf-coef", "0.25",
+                       "--clip-coef", "0.2", "--learning-rate", "1e-3"], 3)
+    if only:
+        return
     dqn("dqn_atari_b8_seed1.npz",
         ["--no-cuda", "--total-timesteps", "260", "--learning-starts", "40", "--buffer-size", "64", "--batch-size", "8",
          "--train-frequency", "4", "--target-network-frequency", "20", "--seed", "1"])

@@ -61,7 +61,7 @@ def _rel(a, b):
 
 
 @pytest.mark.parametrize("name", ["ppo_atari_envpool_n8_t32_seed1.npz", "ppo_atari_envpool_n16_t16_seed3_noclipv.npz",
-                                  "ppo_atari_gym_n8_t32_seed2.npz"])
+                                  "ppo_atari_gym_n8_t32_seed2.npz", "ppo_atari_envpool_n8_t16_seed5_flags.npz"])
 @pytest.mark.parametrize("gae_kernel", ["sequential", "scan"])
 def test_script_reproduces_reference_run(lib, name, gae_kernel):
     z, snaps, w = _run(name, ["--gae-kernel", gae_kernel])

@@ -13,7 +13,7 @@ from conftest import GOLDEN
 from oracle import ppo_oracle as O
 
 ATARI = ["ppo_atari_envpool_n8_t32_seed1.npz", "ppo_atari_envpool_n16_t16_seed3_noclipv.npz",
-         "ppo_atari_gym_n8_t32_seed2.npz"]
+         "ppo_atari_gym_n8_t32_seed2.npz", "ppo_atari_envpool_n8_t16_seed5_flags.npz"]
 
 
 def _args(z):
@@ -23,7 +23,8 @@ def _args(z):
     return dict(gamma=get("--gamma", 0.99), lam=get("--gae-lambda", 0.95), seed=get("--seed", 1, int),
                 num_envs=get("--num-envs", 8, int), num_steps=get("--num-steps", 128, int),
                 clip_vloss="--no-clip-vloss" not in argv, ent_coef=get("--ent-coef", 0.01),
-                update_epochs=get("--update-epochs", 4, int))
+                update_epochs=get("--update-epochs", 4, int), num_minibatches=get("--num-minibatches", 4, int),
+                target_kl=get("--target-kl", None), anneal_lr="--no-anneal-lr" not in argv)
 
 
 @pytest.mark.parametrize("name", ATARI + ["ppo_mlp_n4_t128_seed1.npz"])
@@ -107,12 +108,22 @@ def test_numpy_shuffle_stream_matches_reference(name):
     try:
         np.random.seed(a["seed"])
         k = 0
-        for it in range(z["rewards"].shape[0]):
+        # epochs actually run per iteration: all of them, unless --target-kl stopped the update early (ppo.py:292-293);
+        # the reference logged one learning rate per update, constant within an iteration
+        lrs = z["upd_lr"]
+        n_it = z["rewards"].shape[0]
+        if a.get("target_kl") is not None and a.get("anneal_lr", True):
+            per_it = [int((lrs == v).sum()) // a["num_minibatches"] for v in sorted(set(lrs.tolist()), reverse=True)]
+        else:
+            per_it = [a["update_epochs"]] * n_it
+        assert len(per_it) == n_it
+        for it in range(n_it):
             inds = np.arange(B)
-            for e in range(a["update_epochs"]):
+            for e in range(per_it[it]):
                 np.random.shuffle(inds)
                 assert np.array_equal(inds[:32], z["shuffles"][k])
                 k += 1
+        assert k == z["shuffles"].shape[0]
     finally:
         np.random.set_state(np_state)
 
