@@ -23,7 +23,6 @@ import os
 import subprocess
 import sys
 import threading
-import time
 from pathlib import Path
 from types import SimpleNamespace
 
@@ -215,7 +214,6 @@ def run_ours(opt):
         prof = None
         if profile:
             lib.b200rl_profile_enable(0)
-            buf = (b"\0" * (1 << 16))
             import ctypes
             cbuf = ctypes.create_string_buffer(1 << 16)
             _lib.check(lib.b200rl_profile_summary(cbuf, 1 << 16), "profile_summary")
