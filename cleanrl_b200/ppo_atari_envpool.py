@@ -121,10 +121,11 @@ def main(argv=None, writer_factory=None, env_factory=None, on_iteration=None):
     torch.manual_seed(args.seed)
     torch.backends.cudnn.deterministic = args.torch_deterministic
 
-    if not (torch.cuda.is_available() and args.cuda):
+    if not (torch.cuda.is_available() and args.cuda) and not PPOEngine.ALLOW_NON_CUDA_FOR_TESTS:
         raise RuntimeError("cleanrl_b200.ppo_atari_envpool runs on libb200rl CUDA kernels: a CUDA device and "
                            "--cuda are required (no CPU fallback). Use the reference script for CPU runs.")
-    device = torch.device("cuda")
+    # "cpu" is only reachable from the CPU test harness (tests/cpu_backend.py drives the host logic with injected ops)
+    device = torch.device("cuda" if torch.cuda.is_available() else "cpu")
 
     envs = env_factory(args) if env_factory else make_envs(args)
     agent = Agent(envs).to(device)   # CPU init (same RNG stream as the reference), then moved
