@@ -36,6 +36,15 @@ FLOP_PER_ENV_STEP = 243.1e6     # fwd 18.69 MFLOP x [129/128 + 4
 HBM_BYTES_PER_ENV_STEP = 169344  # uint8 frame x [1 H2D write + 1 rollout read + 4 epoch reads]
 
 
+def bench_config(N, T, world):
+    """`config` of the JSON line: identical for our arm and for the reference arm (same workload, same shapes)."""
+    return {"workload": "ppo_atari_envpool Breakout-shaped synthetic vec env; per GPU num_envs=%d num_steps=%d, "
+                        "4 epochs x 4 minibatches of %d, NatureCNN A=4; one step = one PPO iteration" % (N, T, N * T // 4),
+            "global_num_envs": N * world, "parallelism": f"dp{world}",
+            "timing": "inputs_larger_than_L2 (3.7 GB uint8 rollout + 2.8 GB activations per minibatch vs 126 MB L2)",
+            "gae_kernel": "scan"}
+
+
 def ppo_args(num_envs, num_steps, num_iterations, precision):
     """Reference defaults of ppo_atari_envpool.py:19-80."""
     a = SimpleNamespace(
@@ -125,7 +134,6 @@ def run_ours(opt):
     device = torch.device("cuda", local_rank)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        os.environ["NCCL_DEBUG"] = "WARN"        # keep stdout to the single JSON line (NCCL prints its version there)
         dist.init_process_group("nccl", rank=rank, world_size=world, device_id=device)
     build.build()
     lib = _lib.load()
@@ -187,7 +195,7 @@ def run_ours(opt):
         eng.rewards.copy_(eng_rewards)
         eng.dones.copy_(eng_dones)
         if eng.s2d:
-            ops.frames_to_s2d(pool_dev[T % P], out=eng.next_obs)
+            eng._to_storage(pool_dev[T % P], None)
         else:
             eng.next_obs.copy_(pool_dev[T % P])
         eng.finish_rollout(None, None, resident=True)
@@ -264,6 +272,20 @@ def run_ours(opt):
     gae = {"T": T, "N": N, "sequential_bit_exact_us": round(gae_us(0), 2), "chunked_scan_us": round(gae_us(1), 2),
            "reference_torch_loop_on_gpu_us": round(gae_ref_us(), 1), "algorithmic_bytes": 20 * T * N + 8 * N}
 
+    # data-parallel correctness, checked on the hardware the number was measured on: after K + W iterations x 16
+    # updates x 2 loops every rank must hold bit-identical parameters and Adam state (the reference's own cross-rank
+    # check is the debug print of ppo_atari_multigpu.py:284-286)
+    replicas_identical = None
+    if world > 1:
+        ok = torch.ones(1, device=device)
+        for buf in (eng.flat.flat, eng.flat.exp_avg, eng.flat.exp_avg_sq):
+            ref = buf.clone()
+            dist.broadcast(ref, 0)
+            if not torch.equal(ref, buf):
+                ok.zero_()
+        dist.all_reduce(ok, op=dist.ReduceOp.MIN)
+        replicas_identical = bool(ok.item() == 1.0)
+
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -313,11 +335,7 @@ def run_ours(opt):
         "metric": METRIC, "value": round(sps, 1), "unit": "env_steps/s", "n_gpus": world, "steps": K, "warmup": W,
         "ms_per_step": round(res["ms"] / K, 3), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": opt.precision, "data": "synthetic",
-        "config": {"workload": "ppo_atari_envpool Breakout-shaped synthetic vec env; per GPU num_envs=%d num_steps=%d, "
-                               "4 epochs x 4 minibatches, NatureCNN A=4; one step = one PPO iteration" % (N, T),
-                   "global_num_envs": N * world, "parallelism": f"dp{world}", "timing": "inputs_larger_than_L2 "
-                   "(3.7 GB uint8 rollout + 2.8 GB activations per minibatch vs 126 MB L2)",
-                   "gae_kernel": "scan"},
+        "config": bench_config(N, T, world),
         "clocks": res["clocks"],
         "e2e": {"value": round(sps_e2e, 1), "unit": "env_steps/s", "ms_per_step": round(e2e["ms"] / K, 3),
                 "h2d_bytes_per_step": int(e2e["h2d"]), "d2h_bytes_per_step": int(e2e["d2h"]), "clocks": e2e["clocks"]},
@@ -327,62 +345,85 @@ def run_ours(opt):
         "losses_last": {k: (float(v) if isinstance(v, (int, float)) else None) for k, v in (e2e["stats"] or {}).items()
                         if k in ("pg_loss", "v_loss", "entropy", "approx_kl")},
     }
+    if world > 1:
+        out["replicas_identical"] = replicas_identical
+        out["exchange"] = {"collectives_per_update": 2 if eng.overlap_exchange else 1,
+                           "overlapped_with_backward": bool(eng.overlap_exchange), "bytes_per_update": eng.flat.flat.numel() * 4}
     if world == 1 and not opt.no_cpu_baseline:
         out["cpu_baseline"] = cpu_baseline(opt)
+    if world == 1 and not opt.no_gpu_eager_baseline:
+        out["gpu_eager_baseline"] = gpu_eager_baseline(opt)
     print(json.dumps(out))
     if world > 1:
         dist.destroy_process_group()
 
 
 # ---------------------------------------------------------------------- reference / cpu legs
-def cpu_sample(num_envs, sample_steps, iters, threads):
+def cpu_sample(opt, n_slices, warmup_slices, threads):
+    """oracle/ppo_port.run_sliced: 1/16-iteration slices of the reference's torch-CPU loop at FULL tensor shapes
+    (num_envs x num_steps rollout buffer, full minibatch size); 16 slices = one iteration's work."""
     from oracle import ppo_port
-    r = ppo_port.run(num_envs=num_envs, num_steps=sample_steps, num_iterations=iters, total_iterations=1000,
-                     seed=1, env_mode="pool", threads=threads)
-    return r
+    return ppo_port.run_sliced(num_envs=opt.num_envs, num_steps=opt.num_steps, slices_per_iteration=16, n_slices=n_slices,
+                               warmup_slices=warmup_slices, seed=1, threads=threads)
 
 
 def cpu_baseline(opt):
-    """Oracle port (oracle/ppo_port.py: the reference's torch-CPU loop restated) on the host cores, on a
-    bounded sample: same per-env-step work (1 rollout forward + 4 epochs fwd/bwd per sample), fewer
-    policy steps per iteration."""
+    """The reference loop (oracle port, validated against the unmodified script) on the host cores, bounded sample:
+    2 timed slices (after 1 warm-up slice) of 1/16 iteration each, all tensors at the benchmarked shapes."""
     import torch
     cores = os.cpu_count() or 1
     threads = min(cores, 64)
-    t_s = opt.cpu_sample_steps
-    r = cpu_sample(opt.num_envs, t_s, 1, threads)
-    sps = r["env_steps"] / r["seconds"]
-    return {"value": round(sps, 1), "unit": "env_steps/s", "cores": threads, "kind": "port",
-            "sample": f"1 PPO iteration at num_envs={opt.num_envs}, num_steps={t_s} (instead of {opt.num_steps}): "
-                      f"{r['env_steps']} env steps in {r['seconds']:.1f} s, torch {torch.__version__} CPU, "
-                      f"{threads} threads of {cores} host cores"}
+    r = cpu_sample(opt, 2, 1, threads)
+    secs = sum(r["slice_seconds"])
+    steps = r["env_steps_per_slice"] * len(r["slice_seconds"])
+    return {"value": round(steps / secs, 1), "unit": "env_steps/s", "cores": threads, "kind": "port",
+            "sample": f"{len(r['slice_seconds'])} slices of 1/16 PPO iteration at num_envs={opt.num_envs}, num_steps={opt.num_steps}, "
+                      f"minibatch {r['minibatch_size']} (full shapes): {steps} env steps in {secs:.1f} s, "
+                      f"torch {torch.__version__} CPU, {threads} threads of {cores} host cores"}
+
+
+def gpu_eager_baseline(opt):
+    """what `python cleanrl/ppo_atari_envpool.py --cuda` executes on this same GPU -- fp32 rollout
+    storage on the device, eager torch / cuDNN / cuBLAS ops, autograd, foreach Adam, per-step action sync -- restated
+    by oracle/ppo_port.py with device="cuda" (no /root/reference on the GPU box).  2 iterations, the second is timed."""
+    import torch
+    from oracle import ppo_port
+    try:
+        r = ppo_port.run(num_envs=opt.num_envs, num_steps=opt.num_steps, num_iterations=2, seed=1, env_mode="pool",
+                         device="cuda", total_iterations=10)
+        sec = r["iter_seconds"][-1]
+        out = {"value": round(opt.num_envs * opt.num_steps / sec, 1), "unit": "env_steps/s", "kind": "port on cuda (torch eager)",
+               "iter_seconds": [round(x, 3) for x in r["iter_seconds"]], "torch": torch.__version__}
+    except Exception as e:  # the baseline must never take the product's number down with it
+        out = {"unavailable": f"{type(e).__name__}: {e}"[:200]}
+    torch.cuda.empty_cache()
+    return out
 
 
 def run_reference(opt):
-    """--impl reference: the reference's own CPU implementation of the path (torch CPU loop, all host
-    threads it can use) -- here the oracle port, because /root/reference does not exist on the GPU box."""
+    """--impl reference: the reference's own CPU implementation of the path (torch CPU loop, all host threads it can
+    use) -- the oracle port, because /root/reference does not exist on the GPU box.  Same `config` as our arm; every
+    step is a bounded sample of that workload: one 1/16-iteration slice at full tensor shapes (see cpu_sample)."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
     import torch
     cores = os.cpu_count() or 1
     threads = min(cores, 64)
-    K, W, t_s = opt.steps, opt.warmup, opt.cpu_sample_steps
-    W = min(W, 1)
-    r = cpu_sample(opt.num_envs, t_s, W + K, threads)
-    secs = sum(r["iter_seconds"][W:])
-    steps = opt.num_envs * t_s * K
+    K, W = opt.steps, opt.warmup
+    r = cpu_sample(opt, K, W, threads)
+    secs = sum(r["slice_seconds"])
+    steps = r["env_steps_per_slice"] * K
     sps = steps / secs
+    sample = (f"each step = one slice of 1/16 PPO iteration at full shapes (num_envs={opt.num_envs}, num_steps={opt.num_steps}, "
+              f"minibatch {r['minibatch_size']}): {opt.num_steps // 16} policy steps x {opt.num_envs} envs + 1 minibatch update; "
+              f"{K} timed + {W} warm-up slices, torch {torch.__version__} CPU, {threads} threads of {cores} host cores")
     line = {
         "impl": "reference", "metric": METRIC, "value": round(sps, 1), "unit": "env_steps/s", "n_gpus": opt.gpus,
         "steps": K, "warmup": W, "ms_per_step": round(1e3 * secs / K, 1), "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": "ppo_atari_envpool Breakout-shaped synthetic vec env; num_envs=%d, NatureCNN A=4; "
-                               "each step = one PPO iteration on a bounded sample (num_steps=%d instead of %d)"
-                               % (opt.num_envs, t_s, opt.num_steps)},
-        "cpu_baseline": {"value": round(sps, 1), "unit": "env_steps/s", "cores": threads, "kind": "port",
-                         "sample": f"{K} iterations x num_envs={opt.num_envs} x num_steps={t_s}, torch {torch.__version__} "
-                                   f"CPU, {threads} threads of {cores} host cores"},
+        "config": bench_config(opt.num_envs, opt.num_steps, opt.gpus),
+        "cpu_baseline": {"value": round(sps, 1), "unit": "env_steps/s", "cores": threads, "kind": "port", "sample": sample},
         "e2e": {"value": round(sps, 1), "unit": "env_steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
     print(json.dumps(line))
@@ -397,8 +438,8 @@ def main():
     ap.add_argument("--num-envs", type=int, default=1024)
     ap.add_argument("--num-steps", type=int, default=128)
     ap.add_argument("--precision", choices=["bf16", "fp32"], default="bf16")
-    ap.add_argument("--cpu-sample-steps", type=int, default=4)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-gpu-eager-baseline", action="store_true")
     opt = ap.parse_args()
     if opt.impl == "reference":
         run_reference(opt)

@@ -81,11 +81,14 @@ class KernelAgent(nn.Module):
     action_dim = 0          # 0 = discrete (int64 actions [n]); D > 0 = continuous (f32 actions [n, D])
 
     @property
+    def graph_capturable(self):
+        """May the engine capture the per-step device work (frame conversion, network, sampler) in CUDA graphs?"""
+        return getattr(self, "precision", "bf16") == "bf16" or not hasattr(self, "network")
+
+    @property
     def graph_friendly(self):
-        """May the engine capture the per-step device work in CUDA graphs?  (small per-step temporaries, noise
-        drawn on the device)"""
-        return getattr(self.noise_fn, "graph_safe", False) and (getattr(self, "precision", "bf16") == "bf16" or
-                                                                not hasattr(self, "network"))
+        """... and may the noise draw be captured too (device generator)?  Needed for whole-rollout graphs."""
+        return getattr(self.noise_fn, "graph_safe", False) and self.graph_capturable
 
     def noise_shape(self, n):
         return (n, self.num_actions)
@@ -197,14 +200,19 @@ class NatureCNNAgent(KernelAgent):
         self._tc_dirty = True
         return out
 
-    def _forward_heads(self, x, rows=None, keep=False):
+    def pin_workspaces(self):
+        """A CUDA graph captured by the engine holds raw pointers into the activation workspaces: never evict them."""
+        if self._tc is not None:
+            self._tc.pin()
+
+    def _forward_heads(self, x, rows=None, keep=False, aux=None):
         if self.precision == "bf16":
             if x.dtype not in (torch.uint8, torch.bfloat16):
                 x = x.to(torch.uint8)       # frames are integers 0..255 (reference passes them as fp32)
             tc = self._tc_plan()
             out = tc.forward(x.contiguous(), rows, self._flat.flat)
             if keep:
-                self._tc_obs, self._tc_rows = x, rows
+                self._tc_obs, self._tc_rows, self._tc_aux = x, rows, aux
             A = self.num_actions
             return out[:, :A], out[:, A]
         if x.dtype not in (torch.uint8, torch.float32):
@@ -216,21 +224,34 @@ class NatureCNNAgent(KernelAgent):
         A = self.num_actions
         return out[:, :A], out[:, A]
 
-    def forward_train(self, b_obs, mb_inds):
-        """Minibatch forward with fused row gather (b_obs[mb_inds] never materialised); keeps activations."""
+    def forward_train(self, b_obs, mb_inds, aux=None):
+        """Minibatch forward with fused row gather (b_obs[mb_inds] never materialised); keeps activations.
+        ``aux``: channel-major copy of a uint8 space-to-depth rollout (consumed by the conv1 weight gradient)."""
         self.flat
-        return self._forward_heads(b_obs, rows=mb_inds, keep=True)
+        return self._forward_heads(b_obs, rows=mb_inds, keep=True, aux=aux)
 
     def alloc_head_grad(self, M, device):
         A = self.num_actions
         d = torch.empty(M, A + 1, dtype=torch.float32, device=device)
         return d, d[:, :A], d[:, A]
 
+    def grad_tail(self):
+        """(offset, event): ``flat.grad[offset:]`` (fc + heads, 95 % of the vector) is final when ``event`` fires in the
+        middle of ``backward`` -- lets the engine overlap the DP exchange of the tail with the conv backward.  None on
+        the fp32 path (layer-by-layer backward finishes the first layers' gradients last anyway, but records no event)."""
+        if self.precision != "bf16":
+            return None
+        if getattr(self, "_tail_event", None) is None:
+            self._tail_event = torch.cuda.Event()
+            self._tail_event.record()                      # materialise the cudaEvent_t handle
+        return self._tc_plan().grad_tail_offset(), self._tail_event
+
     def backward(self, dhead):
         """dhead [M, A+1] = [dlogits | dvalue]; fills the flat gradient buffer."""
         if self.precision == "bf16":
-            self._tc.backward(self._tc_obs, self._tc_rows, self._flat.flat, dhead, self._flat.grad)
-            self._tc_obs = self._tc_rows = None
+            self._tc.backward(self._tc_obs, self._tc_rows, self._flat.flat, dhead, self._flat.grad,
+                              tail_event=getattr(self, "_tail_event", None), obs_aux=getattr(self, "_tc_aux", None))
+            self._tc_obs = self._tc_rows = self._tc_aux = None
             return
         hidden = self._hidden
         self.head.bwd_weight(hidden, dhead)

@@ -57,7 +57,8 @@ _EXTRA = [
     ("gae_kernel", Literal["sequential", "scan"], "sequential",
      "[b200] GAE kernel: sequential = bit-identical to the reference loop, scan = chunked affine scan"),
     ("synthetic_env", bool, False,
-     "[b200] use the built-in synthetic vector env even if the real env library is importable"),
+     "[b200] train on the built-in synthetic vector env instead of the real env library "
+     "(never chosen silently: without this flag a missing env library is an error)"),
 ]
 
 
@@ -154,3 +155,27 @@ def dqn_atari_args(exp_name="dqn_atari"):
 
 def parse(cls, argv=None):
     return tyro.cli(cls, args=argv)
+
+
+def use_synthetic(args):
+    """The synthetic envs are used ONLY on request: ``--synthetic-env`` or ``CLEANRL_B200_SYNTHETIC_ENV=1``.
+    A run that asks for Breakout must never quietly train on synthetic frames."""
+    import os
+    if os.environ.get("CLEANRL_B200_SYNTHETIC_ENV", "0") not in ("", "0"):
+        args.synthetic_env = True
+    return bool(args.synthetic_env)
+
+
+def env_import_error(what, err):
+    """Re-raise a missing env dependency with an actionable message (instead of falling back to synthetic data)."""
+    return ImportError(f"{what} could not be imported ({err}). Install the reference's env extras "
+                       f"(e.g. `pip install envpool` / `gymnasium[atari,accept-rom-license]` / `gymnasium[mujoco]`) "
+                       f"or pass --synthetic-env (or CLEANRL_B200_SYNTHETIC_ENV=1) to run on the built-in synthetic "
+                       f"vector env.")
+
+
+def run_name_for(args):
+    """runs/{run_name}: the reference's pattern (ppo.py:140); runs on synthetic data are tagged as such."""
+    import time
+    env = args.env_id + ("-synthetic" if getattr(args, "synthetic_env", False) else "")
+    return f"{env}__{args.exp_name}__{args.seed}__{int(time.time())}"

@@ -32,6 +32,7 @@
 #include <cuda.h>            // CUtensorMap types only; the encoder is resolved at run time (no libcuda link)
 #include "tc_base.cuh"
 #include "tc_conv_win.cuh"
+#include "tc_conv1_u8.cuh"
 #include "tc_gemm_tma.cuh"
 #include "tc_wgrad_win.cuh"
 #include "tc_reduce.cuh"
@@ -48,7 +49,7 @@ struct NatureLayout {
     // flat fp32 parameter offsets (libb200rl order: trunk, then both head weights, then both head biases)
     int64_t c1w, c1b, c2w, c2b, c3w, c3b, fcw, fcb, hw, hb, total;
     // packed bf16 operand offsets (elements)
-    int64_t w1f, w2f, w2dg, w3f, w3dg, wfcf, wfcdg, packed_total;
+    int64_t w1f, w2f, w2dg, w3f, w3dg, wfcf, wfcdg, w1l, w1sc, packed_total;
     explicit NatureLayout(int A_) : A(A_) {
         int64_t o = 0;
         c1w = o; o += 32 * 4 * 8 * 8;  c1b = o; o += 32;
@@ -66,6 +67,8 @@ struct NatureLayout {
         w3dg = q; q += 64 * 576;
         wfcf = q; q += 512 * 3136;
         wfcdg = q; q += 3136 * 512;
+        w1l = q; q += 64 * 256 / 2;          // conv1 weight limbs: s8 [64][256] (16 KB)
+        w1sc = q; q += 64 * 2;               // conv1 column scales: f32 [64]
         packed_total = q;
     }
 };
@@ -137,12 +140,8 @@ static const int kC1Ctas = 296, kC2Ctas = 148, kC3Ctas = 148, kFcSplits = 8;
 
 static int launch_wgrad_win(const WGradWinParams& p, int ctas, cudaStream_t s, const char* what) {
     const size_t smem = (size_t)kWgradWinStages * ((size_t)p.WRX * 128 * p.cpr + 128 * 128) + 4096 + 1024;
-    static size_t attr = 0;
-    if (smem > attr) {
-        cudaError_t e = cudaFuncSetAttribute(tc_wgrad_win, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e != cudaSuccess) return fail(B200RL_ERR_CUDA, "%s: smem attribute (%zu B): %s", what, smem, cudaGetErrorString(e));
-        attr = smem;
-    }
+    static SmemAttrCache attr;
+    if (int rc0 = attr.ensure(tc_wgrad_win, smem, what)) return rc0;
     CUtensorMap tmX, tmY;
     memset(&tmX, 0, sizeof(tmX)); memset(&tmY, 0, sizeof(tmY));
     // TMA when rows are contiguous, dY rows are exactly 128 bytes and every CTA owns whole 128-row steps
@@ -159,7 +158,7 @@ static int launch_wgrad_win(const WGradWinParams& p, int ctas, cudaStream_t s, c
         if ((128 << p.tpi_shift) < p.G) return fail(B200RL_ERR_INVALID_ARGUMENT, "%s: steps per image too small", what);
         if ((rc = make_tmap_3d(&tmX, p.X, p.n_images, p.G, (int64_t)p.cpr * 64, p.WRX, what))) return rc;
     }
-    tc_wgrad_win<<<ctas, 192, smem, s>>>(tmX, tmY, p, use_tma);
+    tc_wgrad_win<<<ctas, kWgradWinThreads, smem, s>>>(tmX, tmY, p, use_tma);
     return check_launch(what);
 }
 
@@ -182,6 +181,7 @@ static size_t colsum_ws(int64_t M, int ncols) {
 using namespace b200rl;
 
 extern "C" int64_t b200rl_naturecnn_param_count(int A) { return A >= 1 ? NatureLayout(A).total : -1; }
+extern "C" int64_t b200rl_naturecnn_grad_tail_offset(int A) { return A >= 1 ? NatureLayout(A).fcw : -1; }
 extern "C" size_t b200rl_naturecnn_bf16_packed_bytes(int A) { return A >= 1 ? (size_t)NatureLayout(A).packed_total * 2 : 0; }
 extern "C" size_t b200rl_naturecnn_bf16_acts_bytes(int64_t n, int obs_format) {
     return n >= 0 ? (size_t)NatureActs(n, obs_format == B200RL_OBS_U8_NCHW).total * 2 + 256 : 0;
@@ -196,6 +196,18 @@ extern "C" int b200rl_frames_to_s2d_bf16(const uint8_t* obs, const int64_t* rows
     ProfScope ps(s, "frames_to_s2d", 0, (double)n * 28224 * 3);
     tc_frames_to_s2d<<<(unsigned)ceil_div(n * 1764, 256), 256, 0, s>>>(obs, rows, n, reinterpret_cast<bf16*>(out));
     return check_launch("frames_to_s2d");
+}
+
+extern "C" int b200rl_frames_to_s2d_u8(const uint8_t* obs, const int64_t* rows, int64_t n, uint8_t* out_rm, uint8_t* out_cm, void* stream) {
+    B200RL_REQUIRE(n >= 0, "frames_to_s2d_u8: negative n");
+    if (n == 0) return B200RL_OK;
+    B200RL_REQUIRE(obs && out_rm && out_cm, "frames_to_s2d_u8: null pointer");
+    B200RL_REQUIRE(aligned(obs, 16) && aligned(out_rm, 16) && aligned(out_cm, 16), "frames_to_s2d_u8: misaligned buffer");
+    B200RL_REQUIRE(n <= (int64_t)1 << 28, "frames_to_s2d_u8: n too large");
+    cudaStream_t s = (cudaStream_t)stream;
+    ProfScope ps(s, "frames_to_s2d", 0, (double)n * (28224 + 28224 + 28672));
+    tc_frames_to_s2d_u8<<<(unsigned)(n * 4), 256, 0, s>>>(obs, rows, n, out_rm, out_cm);
+    return check_launch("frames_to_s2d_u8");
 }
 
 extern "C" size_t b200rl_naturecnn_bf16_workspace_bytes(int64_t n, int A) {
@@ -221,11 +233,12 @@ extern "C" int b200rl_naturecnn_bf16_pack(const float* params, int A, void* pack
     cudaStream_t s = (cudaStream_t)stream;
     ProfScope ps(s, "pack_weights", 0, (double)L.total * 4 + (double)L.packed_total * 2);
     tc_pack_conv1_s2d<<<32, 256, 0, s>>>(params + L.c1w, P + L.w1f);
+    tc_pack_conv1_i8<<<32, 256, 0, s>>>(params + L.c1w, reinterpret_cast<int8_t*>(P + L.w1l), reinterpret_cast<float*>(P + L.w1sc));
     tc_pack_conv2_cells<<<128, 256, 0, s>>>(params + L.c2w, P + L.w2f);
     tc_pack_conv_s2_classes<<<(unsigned)ceil_div(32768, 256), 256, 0, s>>>(params + L.c2w, 64, 32, P + L.w2dg);
     tc_pack_conv<<<(unsigned)ceil_div(36864, 256), 256, 0, s>>>(params + L.c3w, 64, 64, 3, 3, 0, P + L.w3f, P + L.w3dg);
     tc_pack_fc<<<dim3(512 / 8, 49 / 7), 256, 0, s>>>(params + L.fcw, 512, 49, P + L.wfcf, P + L.wfcdg);
-    return check_launch("naturecnn_pack", 5);
+    return check_launch("naturecnn_pack", 6);
 }
 
 extern "C" int b200rl_naturecnn_bf16_forward(const void* obs, int obs_format, const int64_t* rows, int64_t n, int A,
@@ -235,7 +248,8 @@ extern "C" int b200rl_naturecnn_bf16_forward(const void* obs, int obs_format, co
     if (n == 0) return B200RL_OK;
     B200RL_REQUIRE(obs && params && packed && acts && head_out, "naturecnn_forward: null pointer");
     B200RL_REQUIRE(A >= 1 && A < kMaxHeads, "naturecnn_forward: A=%d outside [1,23]", A);
-    B200RL_REQUIRE(obs_format == B200RL_OBS_U8_NCHW || obs_format == B200RL_OBS_S2D_BF16, "naturecnn_forward: bad obs_format %d", obs_format);
+    B200RL_REQUIRE(obs_format == B200RL_OBS_U8_NCHW || obs_format == B200RL_OBS_S2D_BF16 || obs_format == B200RL_OBS_S2D_U8,
+                   "naturecnn_forward: bad obs_format %d", obs_format);
     B200RL_REQUIRE(aligned(obs, 16) && aligned(acts, 16) && aligned(packed, 16), "naturecnn_forward: misaligned buffer");
     B200RL_REQUIRE(n <= (int64_t)1 << 22, "naturecnn_forward: n too large");
     const NatureLayout L(A);
@@ -253,11 +267,22 @@ extern "C" int b200rl_naturecnn_bf16_forward(const void* obs, int obs_format, co
         if ((rc = b200rl_frames_to_s2d_bf16(reinterpret_cast<const uint8_t*>(obs), rows, n, act + Q.x0, stream))) return rc;
         x0 = act + Q.x0; x0rows = nullptr;
     }
+    if (obs_format == B200RL_OBS_S2D_U8) {
+        // uint8 space-to-depth frames straight into the integer tensor cores (tc_conv1_u8.cuh)
+        Conv1U8Params cp;
+        memset(&cp, 0, sizeof(cp));
+        cp.rows = rows; cp.n = (int)n; cp.n_images = rows ? (int64_t)1 << 24 : n;
+        cp.limbs = reinterpret_cast<const int8_t*>(P + L.w1l); cp.sc = reinterpret_cast<const float*>(P + L.w1sc);
+        cp.bias = params + L.c1b; cp.out = act + Q.act1; cp.mask_out = reinterpret_cast<uint32_t*>(act + Q.m1);
+        ProfScope ps(s, "conv1_fwd", 2.0 * n * 400 * 32 * 256, (double)n * (28224 + 12800 * 2 + 1600));
+        if ((rc = launch_conv1_i8(cp, obs, s, "naturecnn/conv1_i8"))) return rc;
+    } else {
     win_defaults(wp); win_conv1(wp, x0, x0rows, n);
     wp.Bw = P + L.w1f; wp.N = 32; wp.vH = 20; wp.vW = 20; wp.out_mode = WOUT_S2D2; wp.out = act + Q.act1;
     wp.bias = params + L.c1b; wp.scale = 1.0f / 255.0f; wp.relu = 1; wp.mask_out = reinterpret_cast<uint32_t*>(act + Q.m1);
     { ProfScope ps(s, "conv1_fwd", 2.0 * n * 400 * 32 * 256, (double)n * ((28224 + 12800) * 2 + 1600));
       if ((rc = launch_conv_win<32, 1, 9, 4>(wp, s, "naturecnn/conv1"))) return rc; }
+    }
     // conv2: 2x2 window conv on the 128-channel cells -> act2 [n,9,9,64]
     win_defaults(wp); win_conv2(wp, act + Q.act1, n);
     wp.Bw = P + L.w2f; wp.N = 64; wp.vH = 9; wp.vW = 9; wp.out_mode = WOUT_DENSE; wp.out = act + Q.act2;
@@ -285,24 +310,26 @@ extern "C" int b200rl_naturecnn_bf16_forward(const void* obs, int obs_format, co
     return check_launch("naturecnn/heads");
 }
 
-extern "C" int b200rl_naturecnn_bf16_backward(const void* obs, int obs_format, const int64_t* rows, int64_t n, int A,
+extern "C" int b200rl_naturecnn_bf16_backward(const void* obs, const void* obs_aux, int obs_format, const int64_t* rows, int64_t n, int A,
                                               const float* params, const void* packed, void* acts,
                                               const float* dhead, float* grads,
-                                              void* workspace, size_t workspace_bytes, void* stream) {
+                                              void* workspace, size_t workspace_bytes, void* tail_ready_event, void* stream) {
     B200RL_REQUIRE(n >= 1, "naturecnn_backward: n must be >= 1");
     B200RL_REQUIRE(obs && params && packed && acts && dhead && grads && workspace, "naturecnn_backward: null pointer");
     B200RL_REQUIRE(A >= 1 && A < kMaxHeads, "naturecnn_backward: A=%d outside [1,23]", A);
     B200RL_REQUIRE(aligned(workspace, 16), "naturecnn_backward: workspace misaligned");
     const size_t need = b200rl_naturecnn_bf16_workspace_bytes(n, A);
     if (workspace_bytes < need) return fail(B200RL_ERR_WORKSPACE, "naturecnn_backward: workspace %zu < %zu", workspace_bytes, need);
-    B200RL_REQUIRE(obs_format == B200RL_OBS_U8_NCHW || obs_format == B200RL_OBS_S2D_BF16, "naturecnn_backward: bad obs_format %d", obs_format);
+    B200RL_REQUIRE(obs_format == B200RL_OBS_U8_NCHW || obs_format == B200RL_OBS_S2D_BF16 || obs_format == B200RL_OBS_S2D_U8,
+                   "naturecnn_backward: bad obs_format %d", obs_format);
+    B200RL_REQUIRE(obs_format != B200RL_OBS_S2D_U8 || (obs_aux && aligned(obs_aux, 16)), "naturecnn_backward: the uint8 rollout needs obs_aux");
     const NatureLayout L(A);
     const NatureActs Q(n, obs_format == B200RL_OBS_U8_NCHW);
     const bf16* P = reinterpret_cast<const bf16*>(packed);
     bf16* act = reinterpret_cast<bf16*>(acts);
     cudaStream_t s = (cudaStream_t)stream;
     // uint8 input: forward left the space-to-depth frames of this minibatch in the workspace
-    const bf16* x0 = obs_format == B200RL_OBS_U8_NCHW ? act + Q.x0 : reinterpret_cast<const bf16*>(obs);
+    const bf16* x0 = obs_format == B200RL_OBS_U8_NCHW ? act + Q.x0 : reinterpret_cast<const bf16*>(obs);   // unused for S2D_U8
     const int64_t* x0rows = obs_format == B200RL_OBS_U8_NCHW ? nullptr : rows;
     // workspace split: [wgrad partials | small partials]
     size_t big = 0;
@@ -340,17 +367,18 @@ extern "C" int b200rl_naturecnn_bf16_backward(const void* obs, int obs_format, c
           if ((rc = make_tmap_2d(&tmX, act + Q.dhid, n, 512, 64, "naturecnn/fc_wgrad"))) return rc;
           if ((rc = make_tmap_2d(&tmY, act + Q.act3, n, 3136, 64, "naturecnn/fc_wgrad"))) return rc;
           const size_t smem = (size_t)4 * (2 + 4) * 64 * 128 + 1024;
-          static bool attr_done = false;
-          if (!attr_done) {
-              cudaError_t e = cudaFuncSetAttribute(tc_wgrad_tma, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-              if (e != cudaSuccess) return fail(B200RL_ERR_CUDA, "fc_wgrad: smem attribute: %s", cudaGetErrorString(e));
-              attr_done = true;
-          }
+          static SmemAttrCache attr;
+          if ((rc = attr.ensure(tc_wgrad_tma, smem, "naturecnn/fc_wgrad"))) return rc;
           tc_wgrad_tma<<<dim3(pl.splits, 4, 13), 160, smem, s>>>(tmX, tmY, n, pl.rows_per_cta, 2, 4, wsbig);
           if ((rc = check_launch("naturecnn/fc_wgrad"))) return rc; }
         { ProfScope ps(s, "wgrad_fold_bias", 0, 0);
           note_launches(1); tc_fold_fc<<<(unsigned)ceil_div((int64_t)512 * 3136, 256), 256, 0, s>>>(wsbig, pl.splits, 512, 13 * 256, 512, 3136, 64, 49, 1.f, grads + L.fcw);
           if ((rc = colsum(act + Q.dhid, n, 512, 512, wssmall, grads + L.fcb, s))) return rc; }
+        // grads[fcw .. total) (fc weight + bias, both heads) are final: the caller may start exchanging them now
+        if (tail_ready_event) {
+            cudaError_t e = cudaEventRecord(reinterpret_cast<cudaEvent_t>(tail_ready_event), s);
+            if (e != cudaSuccess) return fail(B200RL_ERR_CUDA, "naturecnn_backward: cudaEventRecord: %s", cudaGetErrorString(e));
+        }
         // dact3_pre = (dhid . Wfc) * (act3 > 0), written on the 9x9 linear grid and the zero-padded 11x11 grid
         gemm_rowmajor(p, act + Q.dhid, n, 8);
         p.Bw = P + L.wfcdg; p.N = 3136; p.out = act + Q.dact3a; p.out2 = act + Q.dact3b; p.dual_dact3 = 1;
@@ -374,7 +402,7 @@ extern "C" int b200rl_naturecnn_bf16_backward(const void* obs, int obs_format, c
         { ProfScope ps(s, "conv3_wgrad", 2.0 * n * 49 * 64 * 576, (double)n * (5184 + 5184) * 2);
           if ((rc = launch_wgrad_win(gw, pl.splits, s, "naturecnn/conv3_wgrad"))) return rc; }
         memset(&fw, 0, sizeof(fw));
-        fw.layer = 3; fw.S = pl.splits; fw.nslots = 10; fw.Cout = 64; fw.scale = 1.f;
+        fw.layer = 3; fw.S = pl.splits; fw.nslots = 10; fw.Cout = 64; fw.scale = 1.f; fw.bscale = 1.f;
         for (int k = 0; k < 10; ++k) { fw.slot_tap[k] = st[k]; fw.slot_skip[k] = (k == 8); }
         { ProfScope ps(s, "wgrad_fold_bias", 0, 0);
           fw.wsb = wssmall; fw.db = grads + L.c3b;
@@ -402,7 +430,7 @@ extern "C" int b200rl_naturecnn_bf16_backward(const void* obs, int obs_format, c
         { ProfScope ps(s, "conv2_wgrad", 2.0 * n * 81 * 64 * 512, (double)n * (12800 + 6400) * 2);
           if ((rc = launch_wgrad_win(gw, pl.splits, s, "naturecnn/conv2_wgrad"))) return rc; }
         memset(&fw, 0, sizeof(fw));
-        fw.layer = 2; fw.S = pl.splits; fw.nslots = 8; fw.Cout = 64; fw.scale = 1.f;
+        fw.layer = 2; fw.S = pl.splits; fw.nslots = 8; fw.Cout = 64; fw.scale = 1.f; fw.bscale = 1.f;
         for (int k = 0; k < 8; ++k) { fw.slot_tap[k] = k >> 1; fw.slot_cc[k] = k & 1; }
         { ProfScope ps(s, "wgrad_fold_bias", 0, 0);
           fw.wsb = wssmall; fw.db = grads + L.c2b;
@@ -414,11 +442,28 @@ extern "C" int b200rl_naturecnn_bf16_backward(const void* obs, int obs_format, c
         wp.WR = round8(128 + 12);
         wp.Bw = P + L.w2dg; wp.N = 128; wp.vH = 10; wp.vW = 10; wp.out_mode = WOUT_DACT1;
         wp.out = act + Q.dact1; wp.mask_bits = reinterpret_cast<const uint32_t*>(act + Q.m1);
+        if (obs_format == B200RL_OBS_S2D_U8) { wp.out_f16 = 1; wp.scale = kDact1Scale; }     // fp16 x 2^12 for the TMEM-fed conv1 wgrad
         { ProfScope ps(s, "conv2_dgrad", 2.0 * n * 400 * 32 * 256, (double)n * ((7744 + 14112) * 2 + 1600));
           if ((rc = launch_conv_win<128, 1, 6, 4>(wp, s, "naturecnn/conv2_dgrad"))) return rc; }
     }
     // ---- conv1 (no data gradient: the input is the observation)
-    {
+    if (obs_format == B200RL_OBS_S2D_U8) {
+        // uint8 channel-major frames -> fp16 in registers -> tensor memory (tc_conv1_u8.cuh); 1 CTA per SM (512 TMEM columns)
+        Conv1WgradU8Params cw;
+        memset(&cw, 0, sizeof(cw));
+        const WPlan pl = wgrad_plan(n * 512, kC2Ctas, 128);
+        cw.rows = rows; cw.n = (int)n; cw.rows_per_cta = pl.rows_per_cta; cw.ws = wsbig; cw.wsb = wssmall;
+        { ProfScope ps(s, "conv1_wgrad", 2.0 * n * 400 * 32 * 256, (double)n * (28672 + 14112 * 2));
+          if ((rc = launch_conv1_wgrad_u8(cw, obs_aux, rows ? (int64_t)1 << 24 : n, act + Q.dact1, pl.splits, s, "naturecnn/conv1_wgrad_u8"))) return rc; }
+        memset(&fw, 0, sizeof(fw));
+        fw.layer = 1; fw.S = pl.splits; fw.nslots = 4; fw.Cout = 32; fw.scale = 1.0f / 255.0f / kDact1Scale; fw.bscale = 1.0f / kDact1Scale;
+        const int st1[4] = {0, 2, 1, 3};               // ws rows: tile j, lane m -> tap 2 (m >> 6) + j
+        for (int k = 0; k < 4; ++k) fw.slot_tap[k] = st1[k];
+        { ProfScope ps(s, "wgrad_fold_bias", 0, 0);
+          fw.wsb = wssmall; fw.db = grads + L.c1b;
+          tc_fold_win<<<(unsigned)ceil_div(256 * 32 + 32, 32), 256, 0, s>>>(wsbig, fw, grads + L.c1w);
+          if ((rc = check_launch("naturecnn/conv1_fold"))) return rc; }
+    } else {
         wgw_defaults(gw);
         gw.X = x0; gw.rows = x0rows; gw.M = n * 512; gw.n = (int)n; gw.G = 441; gw.cpr = 1; gw.nslots = 4; gw.WRX = round8(128 + 22);
         gw.tpi_shift = 2; gw.n_images = x0rows ? (int64_t)1 << 24 : n;       // 4 steps of 128 grid rows per image
@@ -430,7 +475,7 @@ extern "C" int b200rl_naturecnn_bf16_backward(const void* obs, int obs_format, c
         { ProfScope ps(s, "conv1_wgrad", 2.0 * n * 400 * 32 * 256, (double)n * (28224 + 14112) * 2);
           if ((rc = launch_wgrad_win(gw, pl.splits, s, "naturecnn/conv1_wgrad"))) return rc; }
         memset(&fw, 0, sizeof(fw));
-        fw.layer = 1; fw.S = pl.splits; fw.nslots = 4; fw.Cout = 32; fw.scale = 1.0f / 255.0f;
+        fw.layer = 1; fw.S = pl.splits; fw.nslots = 4; fw.Cout = 32; fw.scale = 1.0f / 255.0f; fw.bscale = 1.f;
         for (int k = 0; k < 4; ++k) fw.slot_tap[k] = k;
         { ProfScope ps(s, "wgrad_fold_bias", 0, 0);
           fw.wsb = wssmall; fw.db = grads + L.c1b;

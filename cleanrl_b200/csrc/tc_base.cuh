@@ -55,6 +55,43 @@ static int make_tmap_3d(CUtensorMap* tm, const void* base, int64_t n_images, int
     return B200RL_OK;
 }
 
+// uint8 [n_images][rows_per_image][cols <= 256] (row pitch `pitch` bytes), box = [1][box_rows][box_cols]; swizzle 64B when
+// box_cols == 64 (K-major operand rows), none otherwise (register-converted operands).  Out-of-range rows / columns are
+// zero-filled.
+static int make_tmap_3d_u8(CUtensorMap* tm, const void* base, int64_t n_images, int64_t rows_per_image, int64_t cols, int64_t pitch,
+                           int box_rows, int box_cols, const char* what) {
+    if (!g_encode) {
+        CUtensorMap dummy;
+        int rc = make_tmap_2d(&dummy, base, 128, 64, 8, what);      // resolves the driver entry point
+        if (rc) return rc;
+    }
+    const cuuint64_t dims[3] = {(cuuint64_t)cols, (cuuint64_t)rows_per_image, (cuuint64_t)n_images};
+    const cuuint64_t strides[2] = {(cuuint64_t)pitch, (cuuint64_t)rows_per_image * (cuuint64_t)pitch};
+    const cuuint32_t box[3] = {(cuuint32_t)box_cols, (cuuint32_t)box_rows, 1u};
+    const cuuint32_t estr[3] = {1u, 1u, 1u};
+    CUresult r = g_encode(tm, CU_TENSOR_MAP_DATA_TYPE_UINT8, 3, const_cast<void*>(base), dims, strides, box, estr,
+                          CU_TENSOR_MAP_INTERLEAVE_NONE, box_cols == 64 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_NONE,
+                          CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return fail(B200RL_ERR_CUDA, "%s: cuTensorMapEncodeTiled (u8 3-D) failed (%d)", what, (int)r);
+    return B200RL_OK;
+}
+
+// cudaFuncAttributeMaxDynamicSharedMemorySize is a per-device (per-context) attribute: cache the opt-in per device
+struct SmemAttrCache {
+    size_t v[64] = {};
+    template <class F>
+    int ensure(F* func, size_t smem, const char* what) {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        const bool cached = dev >= 0 && dev < 64;
+        if (cached && smem <= v[dev]) return B200RL_OK;
+        cudaError_t e = cudaFuncSetAttribute(func, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return fail(B200RL_ERR_CUDA, "%s: smem attribute (%zu B): %s", what, smem, cudaGetErrorString(e));
+        if (cached) v[dev] = smem;
+        return B200RL_OK;
+    }
+};
+
 static int g_num_sms = 0;
 static int num_sms() {
     if (g_num_sms == 0) {

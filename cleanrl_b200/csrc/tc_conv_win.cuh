@@ -41,10 +41,24 @@ struct WinParams {
     const float* bias;
     float scale;
     int relu;
+    int out_f16;             // store fp16 (saturating) instead of bf16: d(act1) feeding the uint8 conv1 weight gradient
 };
 
+__device__ __forceinline__ uint32_t pack_f16x2_sat(float lo, float hi) {
+    uint32_t d;
+    asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(d) : "f"(hi), "f"(lo));
+    return d;
+}
+
+// Thread roles (352 threads): warp 0 = TMA producer; warps 1 and 10 = MMA issuers; warps 2-9 = epilogue.
+// TWO issuer warps: a tcgen05.mma costs its issuing thread ~8-10 dependent scalar/uniform instructions (descriptor
+// adds, moves into uniform registers, predicate), and a lone warp retires those at roughly one per 6 cycles, so a
+// single issuer delivered one M128 x N<=64 x K16 MMA per 65-79 cycles in EVERY narrow-N kernel regardless of its
+// byte traffic (tools/experiments/umma_chain_test.cu: the cost does not depend on N, the operand source or the
+// accumulator).  Issuer h owns accumulator buffer h = every other tile -- two independent chains on two schedulers.
+constexpr int kConvWinThreads = 352;
 template <int BN, int CPR, int STAGES, int NTAPS>
-__global__ void __launch_bounds__(320, 1) tc_conv_win(const __grid_constant__ CUtensorMap tmA, const WinParams p,
+__global__ void __launch_bounds__(kConvWinThreads, 1) tc_conv_win(const __grid_constant__ CUtensorMap tmA, const WinParams p,
                                                       int total_tiles) {
     constexpr int B_CHUNK = BN * 128;
     constexpr uint32_t TMEM_COLS = (2 * BN) < 32 ? 32 : 2 * BN;
@@ -116,18 +130,19 @@ __global__ void __launch_bounds__(320, 1) tc_conv_win(const __grid_constant__ CU
                 }
             }
         }
-    } else if (warp == 1) {
-        // ======================= MMA issuer: the WHOLE warp walks the tile loop (uniform control flow keeps the
+    } else if (warp == 1 || warp == 10) {
+        // ======================= MMA issuers: the WHOLE warp walks its tile loop (uniform control flow keeps the
         // descriptor arithmetic in uniform registers), one elected lane issues.  Descriptors differ from a per-stage /
-        // per-tap base only in their 14-bit start-address field, so each MMA costs two 32-bit adds.
+        // per-tap base only in their 14-bit start-address field, so each MMA costs two 32-bit adds.  Issuer ih takes
+        // the tiles of parity ih (accumulator buffer ih, epilogue group ih).
+        const uint32_t ih = warp == 1 ? 0u : 1u;
         const bool leader = elect_one();
         constexpr uint32_t idesc = make_idesc(128, BN, 0, 0);
         const uint64_t desc_hi = desc_kmajor(0) & 0xFFFFFFFF00000000ull;
         const uint32_t desc_lo_flags = (uint32_t)(desc_kmajor(0) & 0xFFFFFFFFull);       // LBO field
         const uint32_t w_lo = ((smem_u32(sW) & 0x3FFFFu) >> 4) | desc_lo_flags;
-        uint32_t q = 0;
-        for (int tile = tile_begin; tile < tile_end; ++tile, ++q) {
-            const uint32_t acc = q & 1, s = q % STAGES;
+        for (uint32_t q = ih; (int)q < tile_end - tile_begin; q += 2) {
+            const uint32_t acc = ih, s = q % STAGES;
             if (q >= 2) mbar_wait(&tempty_bar[acc], ((q >> 1) - 1) & 1);
             mbar_wait(&full_bar[s], (q / STAGES) & 1);
             tc_fence_after_sync();
@@ -251,12 +266,22 @@ __global__ void __launch_bounds__(320, 1) tc_conv_win(const __grid_constant__ CU
                     for (int e = 0; e < 32; ++e) if (!((mb[g] >> e) & 1u)) v[e] = 0u;
                 }
                 int4 w[4];
+                if (p.out_f16) {
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) {
+                        w[e].x = (int)pack_f16x2_sat(__uint_as_float(v[8 * e]), __uint_as_float(v[8 * e + 1]));
+                        w[e].y = (int)pack_f16x2_sat(__uint_as_float(v[8 * e + 2]), __uint_as_float(v[8 * e + 3]));
+                        w[e].z = (int)pack_f16x2_sat(__uint_as_float(v[8 * e + 4]), __uint_as_float(v[8 * e + 5]));
+                        w[e].w = (int)pack_f16x2_sat(__uint_as_float(v[8 * e + 6]), __uint_as_float(v[8 * e + 7]));
+                    }
+                } else {
 #pragma unroll
                 for (int e = 0; e < 4; ++e) {
                     w[e].x = (int)pack_bf16x2(__uint_as_float(v[8 * e]), __uint_as_float(v[8 * e + 1]));
                     w[e].y = (int)pack_bf16x2(__uint_as_float(v[8 * e + 2]), __uint_as_float(v[8 * e + 3]));
                     w[e].z = (int)pack_bf16x2(__uint_as_float(v[8 * e + 4]), __uint_as_float(v[8 * e + 5]));
                     w[e].w = (int)pack_bf16x2(__uint_as_float(v[8 * e + 6]), __uint_as_float(v[8 * e + 7]));
+                }
                 }
                 int4* dst;
                 if (p.out_mode == WOUT_DACT1) {
@@ -284,12 +309,8 @@ template <int BN, int CPR, int STAGES, int NTAPS>
 static int launch_conv_win(const WinParams& p, cudaStream_t s, const char* what) {
     if (p.ntaps != NTAPS) return fail(B200RL_ERR_INVALID_ARGUMENT, "%s: %d taps, kernel instance has %d", what, p.ntaps, NTAPS);
     const size_t smem = (size_t)p.ntaps * CPR * BN * 128 + (size_t)STAGES * p.WR * 128 * CPR + 1024;
-    static size_t attr = 0;
-    if (smem > attr) {
-        cudaError_t e = cudaFuncSetAttribute(tc_conv_win<BN, CPR, STAGES, NTAPS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e != cudaSuccess) return fail(B200RL_ERR_CUDA, "%s: smem attribute (%zu B): %s", what, smem, cudaGetErrorString(e));
-        attr = smem;
-    }
+    static SmemAttrCache attr;
+    if (int rc = attr.ensure(tc_conv_win<BN, CPR, STAGES, NTAPS>, smem, what)) return rc;
     if ((int64_t)p.G * p.Wp >= 65536 || p.G < 1 || p.N % 32 != 0)
         return fail(B200RL_ERR_INVALID_ARGUMENT, "%s: grid %d x width %d outside the epilogue's multiply-shift range, or N %% 32 != 0", what, p.G, p.Wp);
     if (p.rows && !p.tpi_shift) return fail(B200RL_ERR_INVALID_ARGUMENT, "%s: the image gather needs image-aligned tiling", what);
@@ -304,7 +325,7 @@ static int launch_conv_win(const WinParams& p, cudaStream_t s, const char* what)
     if (p.tpi_shift) rc = make_tmap_3d(&tmA, p.A, p.n_images, p.G, (int64_t)CPR * 64, p.WR, what);
     else rc = make_tmap_2d(&tmA, p.A, p.M, (int64_t)CPR * 64, p.WR, what);
     if (rc) return rc;
-    tc_conv_win<BN, CPR, STAGES, NTAPS><<<grid, 320, smem, s>>>(tmA, p, total);
+    tc_conv_win<BN, CPR, STAGES, NTAPS><<<grid, kConvWinThreads, smem, s>>>(tmA, p, total);
     return check_launch(what);
 }
 

@@ -293,14 +293,10 @@ __global__ void __launch_bounds__(160, 1) tc_wgrad_tma(const __grid_constant__ C
 template <int BN, int STAGES>
 static int launch_gemm_tma(const KGemmParams& p, cudaStream_t s, const char* what) {
     const size_t smem = (size_t)STAGES * (128 * 128 + BN * 128) + 1024;
-    static size_t attr = 0;
-    if (smem > attr) {
-        cudaError_t e = cudaFuncSetAttribute(tc_gemm_tma<BN, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e != cudaSuccess) return fail(B200RL_ERR_CUDA, "%s: smem attribute (%zu B): %s", what, smem, cudaGetErrorString(e));
-        attr = smem;
-    }
-    CUtensorMap tmA, tmB;
+    static SmemAttrCache attr;
     int rc;
+    if ((rc = attr.ensure(tc_gemm_tma<BN, STAGES>, smem, what))) return rc;
+    CUtensorMap tmA, tmB;
     const int64_t K = (int64_t)p.nchunks * 64;
     if ((rc = make_tmap_2d(&tmA, p.A, p.M, K, 128, what))) return rc;
     if ((rc = make_tmap_2d(&tmB, p.Bw, p.N, K, BN, what))) return rc;

@@ -36,6 +36,7 @@ __device__ __forceinline__ float zlane_sum(const float* __restrict__ part, int64
 //   layer 2: slot = (tap (a,b), cc); q = cc*64 + row = (py*2+px)*32 + c; ky = 2a+py, kx = 2b+px; Cin 32, 4x4
 //   layer 3: slot -> tap (ky,kx) via slot_tap (a duplicate slot is skipped); q = c; Cin 64, 3x3
 struct FoldWin { int layer, S, nslots, Cout; int slot_tap[16], slot_cc[16], slot_skip[16]; float scale;
+                 float bscale;     // scale of the bias gradient (1, or 1 / kDact1Scale when dY was stored scaled)
                  const float* wsb; float* db; };
 __global__ void __launch_bounds__(256) tc_fold_win(const float* __restrict__ ws, const FoldWin f, float* __restrict__ dst) {
     __shared__ float red[256];
@@ -45,7 +46,7 @@ __global__ void __launch_bounds__(256) tc_fold_win(const float* __restrict__ ws,
         const int co = idx - KX * f.Cout;
         const bool valid = co < f.Cout && f.db != nullptr;
         const float s = zlane_sum(f.wsb, 64, f.S, co, valid, red);
-        if (valid && threadIdx.x < 32) f.db[co] = s;
+        if (valid && threadIdx.x < 32) f.db[co] = s * f.bscale;
         return;
     }
     const int xi = idx / f.Cout, co = idx - xi * f.Cout;

@@ -26,7 +26,10 @@ struct WGradWinParams {
     float* wsb;              // [gridDim.x][64] bias-gradient partials: sum_r dY[r, co]
 };
 
-__global__ void __launch_bounds__(192, 1) tc_wgrad_win(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmY,
+// 224 threads: warps 0-3 = dY warps (bias sums, final TMEM drain), warps 4 and 6 = MMA issuers (output tiles of even /
+// odd index: independent accumulators, see tc_conv_win.cuh for why one issuing thread is not enough), warp 5 = TMA.
+constexpr int kWgradWinThreads = 224;
+__global__ void __launch_bounds__(kWgradWinThreads, 1) tc_wgrad_win(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmY,
                                                        const WGradWinParams p, int use_tma) {
     constexpr int R = 128, STAGES = kWgradWinStages, LOOKAHEAD = 1, NY = 64;
     extern __shared__ uint8_t smem_raw[];
@@ -44,8 +47,8 @@ __global__ void __launch_bounds__(192, 1) tc_wgrad_win(const __grid_constant__ C
     if (tid == 0) {
         // full:  one expect_tx arrival (TMA) [+ the four cp.async warps that stage dY in image-aligned mode]
         // empty: the MMA commit [+ the four dY-summing warps when they read the stage after the TMA landed]
-        for (int s = 0; s < STAGES; ++s) { mbar_init(&full_bar[s], use_tma ? 1 : 5); mbar_init(&empty_bar[s], use_tma ? 5 : 1); }
-        mbar_init(&done_bar, 1);
+        for (int s = 0; s < STAGES; ++s) { mbar_init(&full_bar[s], use_tma ? 1 : 5); mbar_init(&empty_bar[s], use_tma ? 6 : 2); }
+        mbar_init(&done_bar, 2);
         fence_barrier_init();
         tma_prefetch_desc(&tmX);
         if (use_tma) tma_prefetch_desc(&tmY);
@@ -168,10 +171,11 @@ __global__ void __launch_bounds__(192, 1) tc_wgrad_win(const __grid_constant__ C
             p.wsb[(int64_t)blockIdx.x * NY + tid] = t;
         }
     } else {
-        // ======================= MMA issuer: the whole warp walks the step loop (uniform control flow), one elected
-        // lane issues.  Everything that does not depend on the stage is hoisted: per output tile the X operand's offset
+        // ======================= MMA issuers (warps 4 and 6): the whole warp walks the step loop (uniform control flow),
+        // one elected lane issues the output tiles of its parity.  Everything that does not depend on the stage is hoisted: per output tile the X operand's offset
         // inside the stage and its LBO field; descriptors then differ only in the 14-bit start-address field.
         const bool leader = elect_one();
+        const int ih = warp == 4 ? 0 : 1;
         constexpr uint32_t idesc = make_idesc(128, NY, 1, 1);
         const uint64_t desc_hi = desc_mnmajor(0, 0) & 0xFFFFFFFF00000000ull;
         uint32_t arel[8], albo[8];
@@ -196,7 +200,7 @@ __global__ void __launch_bounds__(192, 1) tc_wgrad_win(const __grid_constant__ C
                 const uint32_t accum = it != 0 ? 1u : 0u;
 #pragma unroll
                 for (int t = 0; t < 8; ++t) {
-                    if (t < xt) {
+                    if (t < xt && (t & 1) == ih) {
                         const uint32_t a_lo = (xa16 + arel[t]) | albo[t];
 #pragma unroll
                         for (int kk = 0; kk < R / 16; ++kk)

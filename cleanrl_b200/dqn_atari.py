@@ -47,14 +47,13 @@ def make_env(env_id, seed, idx, capture_video, run_name):
 
 def make_envs(args, run_name):
     """gymnasium Atari SyncVectorEnv as the reference (dqn_atari.py:163-166) when available, else synthetic."""
-    if not args.synthetic_env:
+    if not cli.use_synthetic(args):
         try:
-            import gymnasium as gym  # type: ignore
-
-            return gym.vector.SyncVectorEnv([make_env(args.env_id, args.seed + i, i, args.capture_video, run_name)
-                                             for i in range(args.num_envs)])
-        except ImportError:
-            print("[cleanrl_b200] gymnasium/ALE not installed: using SyntheticGymnasiumVec(atari) (synthetic data)", file=sys.stderr)
+            import gymnasium as gym  # type: ignore  # noqa: F401
+        except ImportError as e:
+            raise cli.env_import_error("gymnasium (+ ale-py, cleanrl_utils.atari_wrappers)", e) from e
+        return gym.vector.SyncVectorEnv([make_env(args.env_id, args.seed + i, i, args.capture_video, run_name)
+                                         for i in range(args.num_envs)])
     from cleanrl_b200.synthetic_envs import SyntheticGymnasiumVec
 
     return SyntheticGymnasiumVec(args.num_envs, kind="atari")
@@ -64,7 +63,8 @@ def main(argv=None, writer_factory=None, env_factory=None, on_update=None):
     global run_name
     args = cli.parse(Args, argv)
     assert args.num_envs == 1, "vectorized envs are not supported at the moment"   # dqn_atari.py:135
-    run_name = f"{args.env_id}__{args.exp_name}__{args.seed}__{int(time.time())}"
+    cli.use_synthetic(args)
+    run_name = cli.run_name_for(args)
     if args.track:
         import wandb
 

@@ -303,27 +303,41 @@ class NatureCNNBf16:
         self.A, self.device = int(A), device
         self.param_count = lib.b200rl_naturecnn_param_count(self.A)
         self.packed = torch.empty(lib.b200rl_naturecnn_bf16_packed_bytes(self.A), dtype=torch.uint8, device=device)
-        self._acts = {}
+        self._acts = {}          # (n, fmt) -> workspace, in least-recently-used order
+        self._pinned = set()     # keys referenced by captured CUDA graphs (raw pointers baked in): never evicted
         self._ws = None
+
+    MAX_UNPINNED = 4
+
+    def pin(self):
+        """Called by the engine after a CUDA-graph capture: every workspace that exists now may be referenced by a
+        graph (and by its baked CUtensorMaps) through its raw device pointer, so it must outlive the graph."""
+        self._pinned.update(self._acts.keys())
 
     def acts(self, n, fmt):
         lib = _lib.load()
         key = (n, fmt)
-        if key not in self._acts:
-            if len(self._acts) > 4:
-                self._acts.clear()
+        buf = self._acts.pop(key, None)
+        if buf is None:
+            # bounded cache of batch shapes: evict least-recently-used workspaces that no graph can reference
+            unpinned = [k for k in self._acts if k not in self._pinned]
+            while len(unpinned) >= self.MAX_UNPINNED:
+                del self._acts[unpinned.pop(0)]
             # zero-initialised: the padded-grid gradient buffers rely on never-written positions being 0
-            self._acts[key] = torch.zeros(lib.b200rl_naturecnn_bf16_acts_bytes(n, fmt), dtype=torch.uint8, device=self.device)
-        return self._acts[key]
+            buf = torch.zeros(lib.b200rl_naturecnn_bf16_acts_bytes(n, fmt), dtype=torch.uint8, device=self.device)
+        self._acts[key] = buf    # most recently used = last
+        return buf
 
     @staticmethod
     def obs_format(obs):
-        if obs.dtype == torch.uint8 and tuple(obs.shape[-3:]) == (4, 84, 84):
+        if obs.dtype == torch.uint8 and obs.dim() >= 4 and tuple(obs.shape[-3:]) == (4, 84, 84):
             return 0
         if obs.dtype == torch.bfloat16 and tuple(obs.shape[-3:]) == (21, 21, 64):
             return 1
-        raise TypeError("bf16 NatureCNN path consumes uint8 [*,4,84,84] frames or space-to-depth bf16 "
-                        f"[*,21,21,64] (got {obs.dtype} {tuple(obs.shape)})")
+        if obs.dtype == torch.uint8 and tuple(obs.shape[-2:]) == (441, 64):
+            return 2
+        raise TypeError("tensor-core NatureCNN path consumes uint8 [*,4,84,84] frames, uint8 space-to-depth rollout rows "
+                        f"[*,441,64] or space-to-depth bf16 [*,21,21,64] (got {obs.dtype} {tuple(obs.shape)})")
 
     def pack(self, flat_params):
         lib = _lib.load()
@@ -344,19 +358,31 @@ class NatureCNNBf16:
         _lib.check(rc, "naturecnn_bf16_forward")
         return head_out
 
-    def backward(self, obs, rows, flat_params, dhead, flat_grads):
+    def grad_tail_offset(self):
+        """Element offset from which the flat gradient (fc + heads, 95 % of it) is final when ``tail_event`` fires."""
+        return int(_lib.load().b200rl_naturecnn_grad_tail_offset(self.A))
+
+    def backward(self, obs, rows, flat_params, dhead, flat_grads, tail_event=None, obs_aux=None):
+        """``obs_aux``: the channel-major uint8 copy [*,64,448] of a uint8 space-to-depth rollout (format 2)."""
         lib = _lib.load()
         fmt = self.obs_format(obs)
+        if fmt == 2:
+            if obs_aux is None or obs_aux.dtype != torch.uint8 or tuple(obs_aux.shape[-2:]) != (64, 448) or \
+                    obs_aux.shape[0] != obs.shape[0]:
+                raise ValueError("uint8 rollout rows need their channel-major copy [*,64,448] (obs_aux) for the backward pass")
+            _contig(obs_aux, "obs_aux")
         n = dhead.shape[0]
         _contig(dhead, "dhead")
         nbytes = lib.b200rl_naturecnn_bf16_workspace_bytes(n, self.A)
         if self._ws is None or self._ws.numel() < nbytes:
             self._ws = torch.empty(nbytes, dtype=torch.uint8, device=self.device)
-        rc = lib.b200rl_naturecnn_bf16_backward(_ptr(obs, None, "obs"), fmt, _ptr(rows, torch.int64, "rows", True), n, self.A,
+        rc = lib.b200rl_naturecnn_bf16_backward(_ptr(obs, None, "obs"), _ptr(obs_aux, None, "obs_aux", True), fmt,
+                                                _ptr(rows, torch.int64, "rows", True), n, self.A,
                                                 _ptr(flat_params, torch.float32, "params"), self.packed.data_ptr(),
                                                 self.acts(n, fmt).data_ptr(), _ptr(dhead, torch.float32, "dhead"),
                                                 _ptr(flat_grads, torch.float32, "grads"),
-                                                self._ws.data_ptr(), self._ws.numel(), _stream())
+                                                self._ws.data_ptr(), self._ws.numel(),
+                                                tail_event.cuda_event if tail_event is not None else None, _stream())
         _lib.check(rc, "naturecnn_bf16_backward")
 
 
@@ -371,6 +397,24 @@ def frames_to_s2d(obs_u8, out=None, rows=None):
                                        _ptr(out, torch.bfloat16, "out"), _stream())
     _lib.check(rc, "frames_to_s2d")
     return out
+
+
+def frames_to_s2d_u8(obs_u8, out_rm=None, out_cm=None, rows=None):
+    """uint8 [n,4,84,84] frames -> uint8 space-to-depth rollout rows: row-major [n,441,64] (conv1 forward on the integer
+    tensor cores) and channel-major [n,64,448] (conv1 weight gradient); once per env step, 1 byte per pixel each."""
+    lib = _lib.load()
+    _contig(obs_u8, "obs")
+    n = rows.numel() if rows is not None else obs_u8.shape[0]
+    if out_rm is None:
+        out_rm = torch.empty(n, 441, 64, dtype=torch.uint8, device=obs_u8.device)
+    if out_cm is None:
+        out_cm = torch.empty(n, 64, 448, dtype=torch.uint8, device=obs_u8.device)
+    _contig(out_rm, "out_rm"); _contig(out_cm, "out_cm")
+    assert out_rm.shape[0] == n and out_cm.shape[0] == n
+    rc = lib.b200rl_frames_to_s2d_u8(_ptr(obs_u8, torch.uint8, "obs"), _ptr(rows, torch.int64, "rows", True), n,
+                                     _ptr(out_rm, torch.uint8, "out_rm"), _ptr(out_cm, torch.uint8, "out_cm"), _stream())
+    _lib.check(rc, "frames_to_s2d_u8")
+    return out_rm, out_cm
 
 
 # ----------------------------------------------------------- diagonal Gaussian policy

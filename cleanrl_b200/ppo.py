@@ -42,14 +42,13 @@ def make_env(env_id, idx, capture_video, run_name):
 
 
 def make_envs(args, run_name):
-    if not args.synthetic_env:
+    if not cli.use_synthetic(args):
         try:
-            import gymnasium as gym  # type: ignore
-
-            return gym.vector.SyncVectorEnv([make_env(args.env_id, i, args.capture_video, run_name)
-                                             for i in range(args.num_envs)])
-        except ImportError:
-            print("[cleanrl_b200] gymnasium is not installed: using SyntheticGymnasiumVec (synthetic data)", file=sys.stderr)
+            import gymnasium as gym  # type: ignore  # noqa: F401
+        except ImportError as e:
+            raise cli.env_import_error("gymnasium", e) from e
+        return gym.vector.SyncVectorEnv([make_env(args.env_id, i, args.capture_video, run_name)
+                                         for i in range(args.num_envs)])
     from cleanrl_b200.synthetic_envs import SyntheticGymnasiumVec
 
     return SyntheticGymnasiumVec(args.num_envs, kind="discrete")
@@ -70,7 +69,8 @@ def run(args, agent_cls, make_envs_fn, obs_dtype, who, writer_factory=None, env_
     args.batch_size = int(args.num_envs * args.num_steps)
     args.minibatch_size = int(args.batch_size // args.num_minibatches)
     args.num_iterations = args.total_timesteps // args.batch_size
-    run_name = f"{args.env_id}__{args.exp_name}__{args.seed}__{int(time.time())}"
+    cli.use_synthetic(args)
+    run_name = cli.run_name_for(args)
     if args.track:
         import wandb
 

@@ -47,15 +47,13 @@ def make_env(env_id, idx, capture_video, run_name):
 
 
 def make_envs(args, run_name):
-    if not args.synthetic_env:
+    if not cli.use_synthetic(args):
         try:
-            import gymnasium as gym  # type: ignore
-
-            return gym.vector.SyncVectorEnv([make_env(args.env_id, i, args.capture_video, run_name)
-                                             for i in range(args.num_envs)])
-        except ImportError:
-            print("[cleanrl_b200] gymnasium/ALE not installed: using SyntheticGymnasiumVec(atari) (synthetic data)",
-                  file=sys.stderr)
+            import gymnasium as gym  # type: ignore  # noqa: F401
+        except ImportError as e:
+            raise cli.env_import_error("gymnasium (+ ale-py, cleanrl_utils.atari_wrappers)", e) from e
+        return gym.vector.SyncVectorEnv([make_env(args.env_id, i, args.capture_video, run_name)
+                                         for i in range(args.num_envs)])
     from cleanrl_b200.synthetic_envs import SyntheticGymnasiumVec
 
     return SyntheticGymnasiumVec(args.num_envs, kind="atari")

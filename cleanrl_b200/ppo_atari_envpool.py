@@ -76,14 +76,13 @@ def make_envs(args, pinned=True, mode=None):
     """envpool.make(...) as the reference (ppo_atari_envpool.py:185-196); when envpool is not
     installed (this image) or --synthetic-env is set, a seeded synthetic Breakout-shaped env."""
     envs = None
-    if not args.synthetic_env:
+    if not cli.use_synthetic(args):
         try:
             import envpool  # type: ignore
-
-            envs = envpool.make(args.env_id, env_type="gym", num_envs=args.num_envs, episodic_life=True,
-                                reward_clip=True, seed=args.seed)
-        except ImportError:
-            print("[cleanrl_b200] envpool is not installed: using SyntheticAtariVec (synthetic data)", file=sys.stderr)
+        except ImportError as e:
+            raise cli.env_import_error("envpool", e) from e
+        envs = envpool.make(args.env_id, env_type="gym", num_envs=args.num_envs, episodic_life=True,
+                            reward_clip=True, seed=args.seed)
     if envs is None:
         from cleanrl_b200.synthetic_envs import SyntheticAtariVec
 
@@ -103,7 +102,8 @@ def main(argv=None, writer_factory=None, env_factory=None, on_iteration=None):
     args.batch_size = int(args.num_envs * args.num_steps)
     args.minibatch_size = int(args.batch_size // args.num_minibatches)
     args.num_iterations = args.total_timesteps // args.batch_size
-    run_name = f"{args.env_id}__{args.exp_name}__{args.seed}__{int(time.time())}"
+    cli.use_synthetic(args)
+    run_name = cli.run_name_for(args)
     if args.track:
         import wandb
 

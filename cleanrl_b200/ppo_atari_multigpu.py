@@ -37,15 +37,13 @@ from cleanrl_b200.ppo_atari import make_env  # noqa: E402,F401  (same wrapper st
 def make_envs(args, run_name):
     """gymnasium SyncVectorEnv of wrapped Atari envs as the reference (ppo_atari_multigpu.py:225-227) when
     gymnasium + cleanrl_utils are importable; otherwise the seeded synthetic gymnasium-style vec env."""
-    if not args.synthetic_env:
+    if not cli.use_synthetic(args):
         try:
-            import gymnasium as gym  # type: ignore
-
-            return gym.vector.SyncVectorEnv([make_env(args.env_id, i, args.capture_video, run_name)
-                                             for i in range(args.local_num_envs)])
-        except ImportError:
-            print("[cleanrl_b200] gymnasium/ALE not installed: using SyntheticGymnasiumVec(atari) (synthetic data)",
-                  file=sys.stderr)
+            import gymnasium as gym  # type: ignore  # noqa: F401
+        except ImportError as e:
+            raise cli.env_import_error("gymnasium (+ ale-py, cleanrl_utils.atari_wrappers)", e) from e
+        return gym.vector.SyncVectorEnv([make_env(args.env_id, i, args.capture_video, run_name)
+                                         for i in range(args.local_num_envs)])
     from cleanrl_b200.synthetic_envs import SyntheticGymnasiumVec
 
     return SyntheticGymnasiumVec(args.local_num_envs, kind="atari")
@@ -68,7 +66,8 @@ def main(argv=None, writer_factory=None, env_factory=None, on_iteration=None, ag
     else:
         warnings.warn("Not using distributed mode! Launch with `torchrun --standalone --nnodes=1 "
                       "--nproc_per_node=N cleanrl_b200/ppo_atari_multigpu.py` to use N GPUs.")
-    run_name = f"{args.env_id}__{args.exp_name}__{args.seed}__{int(time.time())}"
+    cli.use_synthetic(args)
+    run_name = cli.run_name_for(args)
     writer = None
     if local_rank == 0:
         if args.track:

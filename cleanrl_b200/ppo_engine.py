@@ -64,6 +64,9 @@ class PPOEngine:
         self.M = self.B // self.num_minibatches
         self.world_size = int(world_size)
         self.all_reduce = all_reduce
+        self.overlap_exchange = (device.type == "cuda" and world_size > 1 and
+                                 os.environ.get("CLEANRL_B200_OVERLAP_EXCHANGE", "1") != "0")
+        self._xchg_stream = None
         self.gae_mode = gae_mode
         T, N = self.T, self.N
         self.obs_dtype = _torch_dtype(obs_dtype)
@@ -74,8 +77,18 @@ class PPOEngine:
         self.sort_minibatch = os.environ.get("CLEANRL_B200_SORT_MINIBATCH", "1") != "0"
         self.s2d = (getattr(agent, "precision", "fp32") == "bf16" and self.obs_dtype == torch.uint8
                     and tuple(obs_shape) == (4, 84, 84) and device.type == "cuda")
+        # uint8 rollout (default): every frame is kept ONCE per orientation as 1-byte space-to-depth pixels --
+        # row-major [T,N,441,64] for conv1's forward on the integer tensor cores, channel-major [T,N,64,448] for its weight
+        # gradient -- 28 KB per frame and pass instead of 56 KB of bf16 (CLEANRL_B200_OBS_LAYOUT=bf16 keeps the old layout)
+        self.obs_t = self.next_obs_t = None
+        self.u8_rollout = self.s2d and os.environ.get("CLEANRL_B200_OBS_LAYOUT", "u8") != "bf16"
         if self.s2d:
-            self.obs = torch.zeros((T, N, 21, 21, 64), dtype=torch.bfloat16, device=device)
+            if self.u8_rollout:
+                self.obs = torch.zeros((T, N, 441, 64), dtype=torch.uint8, device=device)
+                self.obs_t = torch.zeros((T, N, 64, 448), dtype=torch.uint8, device=device)
+                self.next_obs_t = torch.zeros((N, 64, 448), dtype=torch.uint8, device=device)
+            else:
+                self.obs = torch.zeros((T, N, 21, 21, 64), dtype=torch.bfloat16, device=device)
             self.obs_u8 = torch.zeros((N,) + tuple(obs_shape), dtype=torch.uint8, device=device)
         else:
             self.obs = torch.zeros((T, N) + tuple(obs_shape), dtype=self.obs_dtype, device=device)
@@ -107,6 +120,8 @@ class PPOEngine:
         self.stats_h = _pin(torch.zeros(max(n_upd, 1), 16, dtype=f32))
         self.grad_norm = torch.zeros(1, dtype=f32, device=device)
         self.flat = agent.flat
+        if self.overlap_exchange and hasattr(agent, "grad_tail"):
+            agent.grad_tail()          # create the tail event BEFORE the first backward records it
         # One CUDA graph per rollout slot: the per-step device work (frame conversion, 5 network launches, noise
         # draw, sampler) becomes a single graph launch that writes straight into obs[t]/actions[t]/...; the
         # rollout is launch-latency bound otherwise (~12 launches + torch ops per 1024-env step).
@@ -126,11 +141,13 @@ class PPOEngine:
         else:
             sizes = [N // C] * C
         self.chunk_bounds = [(sum(sizes[:c]), sum(sizes[:c + 1])) for c in range(C)]
+        self.noise_buf = None
         if self.h2d_chunks > 1:
             self.copy_stream = torch.cuda.Stream(device=device)
             self.chunk_events = [torch.cuda.Event() for _ in range(self.h2d_chunks)]
             self.noise_buf = torch.zeros(agent.noise_shape(N), dtype=f32, device=device)
         self._graphs = {}
+        self._graph_pool = None
         self._graph_kernels = {}
         self._graph_warm = set()
         self.graph_launches = 0          # libb200rl kernels executed through graph replays
@@ -139,7 +156,18 @@ class PPOEngine:
         self.kernel_launches = 0
 
     # ------------------------------------------------------------------ rollout
-    def _upload_obs(self, dst, obs_np, convert=True):
+    def _to_storage(self, src_u8, step, sl=slice(None)):
+        """uint8 NCHW frames (device) -> the rollout slot ``step`` (None = the bootstrap slot ``next_obs``), rows ``sl``."""
+        dst = self.next_obs if step is None else self.obs[step]
+        if self.u8_rollout:
+            dst_t = self.next_obs_t if step is None else self.obs_t[step]
+            ops.frames_to_s2d_u8(src_u8, dst[sl], dst_t[sl])
+        else:
+            ops.frames_to_s2d(src_u8, out=dst[sl])
+
+    def _upload_obs(self, step, obs_np, convert=True):
+        """Host frames -> device (pinned staging when needed) -> rollout slot ``step`` (None = bootstrap slot)."""
+        dst = self.next_obs if step is None else self.obs[step]
         src = torch.from_numpy(np.ascontiguousarray(obs_np))
         if src.dtype != self.obs_dtype:
             src = src.to(self.obs_dtype)
@@ -149,32 +177,41 @@ class PPOEngine:
         if self.s2d:
             self.obs_u8.copy_(src, non_blocking=True)
             if convert:
-                ops.frames_to_s2d(self.obs_u8, out=dst)
+                self._to_storage(self.obs_u8, step)
         else:
             dst.copy_(src, non_blocking=True)
         self.h2d_bytes += src.numel() * src.element_size()
 
-    def _step_device_work(self, step):
+    def _step_device_work(self, step, noise=None):
         """Everything a policy step does on the device after the observation batch has landed."""
         if self.s2d:
-            ops.frames_to_s2d(self.obs_u8, out=self.obs[step])
-        self.agent.sample_into(self.obs[step], self.actions[step], self.logprobs[step], self.values[step])
+            self._to_storage(self.obs_u8, step)
+        self.agent.sample_into(self.obs[step], self.actions[step], self.logprobs[step], self.values[step], noise=noise)
 
     def _chunk_device_work(self, step, c):
         sl = slice(*self.chunk_bounds[c])
-        ops.frames_to_s2d(self.obs_u8[sl], out=self.obs[step][sl])
+        self._to_storage(self.obs_u8[sl], step, sl)
         self.agent.sample_into(self.obs[step][sl], self.actions[step][sl], self.logprobs[step][sl],
                                self.values[step][sl], noise=self.noise_buf[sl])
 
     def _run_step(self, step, chunk=None):
         if chunk is not None:
             work, key = (lambda: self._chunk_device_work(step, chunk)), (step, chunk)
-        else:
-            work, key = (lambda: self._step_device_work(step)), step
-        return self._run_graphed(work, key, warm_key="c" if chunk is not None else "f")
+            return self._run_graphed(work, key, warm_key=("c", chunk))
+        if self._graphable() and not getattr(self.agent.noise_fn, "graph_safe", False):
+            # the noise source cannot be captured (e.g. a CPU generator injected by the parity tests): draw the
+            # step's noise eagerly -- ONE draw per step, as the reference -- and let the graph consume the buffer
+            if self.noise_buf is None:
+                self.noise_buf = torch.zeros(self.agent.noise_shape(self.N), dtype=torch.float32, device=self.device)
+            self.agent.draw_noise_into(self.noise_buf)
+            return self._run_graphed(lambda: self._step_device_work(step, noise=self.noise_buf), step, warm_key=("f", 0))
+        return self._run_graphed(lambda: self._step_device_work(step), step, warm_key=("f", 0))
+
+    def _graphable(self):
+        return self.cuda_graphs and getattr(self.agent, "graph_capturable", getattr(self.agent, "graph_friendly", False))
 
     def _run_graphed(self, work, key, warm_key):
-        if not (self.cuda_graphs and getattr(self.agent, "graph_friendly", False)):
+        if not self._graphable():
             return work()
         if hasattr(self.agent, "_tc_plan") and getattr(self.agent, "precision", "fp32") == "bf16":
             self.agent._tc_plan()                      # (re)pack weights outside the graph
@@ -189,9 +226,13 @@ class PPOEngine:
             from . import _lib
             l0 = _lib.load().b200rl_launch_count()
             g = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(g):
+            if self._graph_pool is None:
+                self._graph_pool = torch.cuda.graph_pool_handle()      # one private pool shared by all step graphs
+            with torch.cuda.graph(g, pool=self._graph_pool):
                 work()
             self._graphs[key] = g
+            if hasattr(self.agent, "pin_workspaces"):
+                self.agent.pin_workspaces()     # captured graphs hold raw pointers into the activation workspaces
             self._graph_kernels[key] = _lib.load().b200rl_launch_count() - l0
         g.replay()
         self.graph_launches += self._graph_kernels[key]
@@ -200,12 +241,12 @@ class PPOEngine:
     def policy_step(self, step, next_obs_np, next_done_np):
         """obs[step] <- next_obs (H2D), sample actions, return them as a host int64 array.
         Reference: ppo.py:194-205 (store obs/done, no-grad policy, action.cpu())."""
-        if self.h2d_chunks > 1 and getattr(self.agent, "graph_friendly", False):
+        if self.h2d_chunks > 1 and self._graphable():
             self._pipelined_step(step, next_obs_np)        # the upload is the critical path: enqueue it first
             self.dones_h[step].copy_(torch.as_tensor(np.asarray(next_done_np, dtype=np.float32)))
         else:
             self.dones_h[step].copy_(torch.as_tensor(np.asarray(next_done_np, dtype=np.float32)))
-            self._upload_obs(self.obs[step], next_obs_np, convert=False)
+            self._upload_obs(step, next_obs_np, convert=False)
             self._run_step(step)
         self.actions_h.copy_(self.actions[step], non_blocking=True)
         self.d2h_bytes += self.actions_h.numel() * self.actions_h.element_size()
@@ -252,11 +293,13 @@ class PPOEngine:
             for step in range(self.T):
                 src = obs_pool[step % P]
                 if self.s2d and src.dtype == torch.uint8:
-                    ops.frames_to_s2d(src, out=self.obs[step])
+                    self._to_storage(src, step)
                 else:
                     self.obs[step].copy_(src)
                 self.agent.sample_into(self.obs[step], self.actions[step], self.logprobs[step], self.values[step])
 
+        if not getattr(self.agent, "graph_friendly", False):
+            return work()          # the noise draw cannot be captured: plain launches
         self._run_graphed(work, ("rollout", obs_pool.data_ptr(), P), warm_key="r")
 
     def record_reward(self, step, reward_np):
@@ -272,7 +315,7 @@ class PPOEngine:
             self.next_done_h.copy_(torch.as_tensor(np.asarray(next_done_np, dtype=np.float32)))
             self.next_done.copy_(self.next_done_h, non_blocking=True)
             self.h2d_bytes += 2 * self.B * 4 + self.N * 4
-            self._upload_obs(self.next_obs, next_obs_np)
+            self._upload_obs(None, next_obs_np)
         _, value = self.agent._forward_heads(self.next_obs)
         self.next_value.copy_(value)
         ops.gae(self.rewards, self.values, self.dones, self.next_value, self.next_done,
@@ -286,13 +329,7 @@ class PPOEngine:
         Returns dict of the logged scalars (last minibatch's losses, mean clipfrac)."""
         a = self.args
         B, M = self.B, self.M
-        agent, flat = self.agent, self.flat
-        b_obs = self.obs.view((B,) + tuple(self.obs.shape[2:]))
-        b = {"actions": self.actions.view((B,) + tuple(self.actions.shape[2:])), "logprobs": self.logprobs.view(B),
-             "advantages": self.advantages.view(B), "returns": self.returns.view(B), "values": self.values.view(B)}
         b_inds_np = np.arange(B)
-        if not hasattr(self, "_scratch"):
-            self._scratch = {}
         k = 0
         E = int(a.update_epochs)
         pre = a.target_kl is None
@@ -316,17 +353,7 @@ class PPOEngine:
                 self.b_inds[epoch].copy_(self.b_inds_h[epoch], non_blocking=True)
                 self.h2d_bytes += B * 8
             for start in range(0, B, M):
-                mb_inds = self.b_inds[epoch, start:start + M]
-                policy_out, value = agent.forward_train(b_obs, mb_inds)
-                agent.loss_backward(policy_out, value, mb_inds, b, a, self.stats[k], self._scratch)
-                if self.world_size > 1:
-                    self.all_reduce(flat.grad)
-                flat.step += 1
-                ops.clip_adam(flat.flat, flat.grad, flat.exp_avg, flat.exp_avg_sq, flat.step, lr,
-                              eps=1e-5, max_norm=a.max_grad_norm, world_size=self.world_size,
-                              norm_out=self.grad_norm)
-                if hasattr(agent, "params_updated"):
-                    agent.params_updated()
+                self.minibatch_update(self.b_inds[epoch, start:start + M], lr, k)
                 k += 1
             if a.target_kl is not None:
                 approx_kl = self.stats[k - 1, 4].item()
@@ -341,6 +368,60 @@ class PPOEngine:
         out["num_updates"] = k
         out["per_update"] = s.copy()
         return out
+
+    @torch.no_grad()
+    def minibatch_update(self, mb_inds, lr, k=0):
+        """ONE fused update on the rollout rows ``mb_inds`` (device int64): forward with the row gather folded in,
+        loss + its gradient, hand-written backward, DP gradient exchange, clip + Adam (ppo.py:250-290,
+        ppo_atari_multigpu.py:360-377).  ``stats[k]`` receives the logged scalars."""
+        a, agent, flat, B = self.args, self.agent, self.flat, self.B
+        b_obs = self.obs.view((B,) + tuple(self.obs.shape[2:]))
+        b = {"actions": self.actions.view((B,) + tuple(self.actions.shape[2:])), "logprobs": self.logprobs.view(B),
+             "advantages": self.advantages.view(B), "returns": self.returns.view(B), "values": self.values.view(B)}
+        if not hasattr(self, "_scratch"):
+            self._scratch = {}
+        if self.u8_rollout:
+            policy_out, value = agent.forward_train(b_obs, mb_inds, aux=self.obs_t.view(B, 64, 448))
+        else:
+            policy_out, value = agent.forward_train(b_obs, mb_inds)
+        agent.loss_backward(policy_out, value, mb_inds, b, a, self.stats[k], self._scratch)
+        if self.world_size > 1:
+            self._exchange_gradients()
+        flat.step += 1
+        ops.clip_adam(flat.flat, flat.grad, flat.exp_avg, flat.exp_avg_sq, flat.step, lr,
+                      eps=1e-5, max_norm=a.max_grad_norm, world_size=self.world_size,
+                      norm_out=self.grad_norm)
+        if hasattr(agent, "params_updated"):
+            agent.params_updated()
+
+    def _exchange_gradients(self):
+        """The ONE data-parallel exchange per update: SUM of the flat gradient over ranks (the mean's 1/world_size is
+        folded into clip+Adam).  Reference: cat + all_reduce + 12 copy-backs after the whole backward
+        (ppo_atari_multigpu.py:360-374).  Here the fc + head gradients -- 95 % of the vector, finished first by the
+        hand-written backward -- start their all-reduce on a side stream as soon as the kernel that completes them has
+        run, underneath the ~2 ms of convolution backward; only the 78 k conv gradients are exchanged after the
+        backward.  Both parts are elementwise sums of disjoint slices: same result as one all-reduce."""
+        flat = self.flat
+        tail = self.agent.grad_tail() if (self.overlap_exchange and hasattr(self.agent, "grad_tail")) else None
+        if tail is None:
+            self.all_reduce(flat.grad)
+            return
+        off, ev = tail
+        main = torch.cuda.current_stream()
+        if self._xchg_stream is None:
+            self._xchg_stream = torch.cuda.Stream(device=self.device)
+            self._xchg_done = torch.cuda.Event()
+            self._bwd_done = torch.cuda.Event()
+        side = self._xchg_stream
+        side.wait_event(ev)                               # recorded inside backward, after the fc gradients
+        with torch.cuda.stream(side):
+            self.all_reduce(flat.grad[off:])
+        self._bwd_done.record(main)
+        side.wait_event(self._bwd_done)
+        with torch.cuda.stream(side):
+            self.all_reduce(flat.grad[:off])
+            self._xchg_done.record(side)
+        main.wait_event(self._xchg_done)
 
     def explained_variance(self):
         """ppo.py:295-297 on host numpy."""

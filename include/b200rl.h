@@ -236,8 +236,15 @@ int b200rl_linear_bwd_weight_f32(const float* x, const int64_t* rows, const floa
  *          DRAM-page friendly (the engine sorts every minibatch).
  * head_out / dhead : f32 [n, A+1] = [logits | value] and its gradient.
  */
-enum { B200RL_OBS_U8_NCHW = 0, B200RL_OBS_S2D_BF16 = 1 };
+enum { B200RL_OBS_U8_NCHW = 0, B200RL_OBS_S2D_BF16 = 1, B200RL_OBS_S2D_U8 = 2 };
 int b200rl_frames_to_s2d_bf16(const uint8_t* obs, const int64_t* rows, int64_t n, void* out_s2d, void* stream);
+/* B200RL_OBS_S2D_U8: the rollout keeps each frame as uint8 space-to-depth(4) pixels (28 224 B, the algorithmic minimum;
+ * reference: fp32, 112 896 B, ppo_atari_envpool.py:203) in TWO orientations written once per env step:
+ *   out_rm u8 [n, 441 grid rows, 64 channels]  -> `obs` of forward: conv1 on the integer tensor cores (kind::i8)
+ *   out_cm u8 [n, 64 channels, 448 grid rows]  -> `obs_aux` of backward: conv1 weight gradient (pixels converted
+ *                                                  uint8 -> fp16 in registers, fed to the MMA from tensor memory)
+ * channel = c*16 + sy*4 + sx of source pixel (4Y+sy, 4X+sx), grid row = Y*21 + X; rows 441..447 of out_cm are zero. */
+int b200rl_frames_to_s2d_u8(const uint8_t* obs, const int64_t* rows, int64_t n, uint8_t* out_rm, uint8_t* out_cm, void* stream);
 int64_t b200rl_naturecnn_param_count(int A);
 size_t b200rl_naturecnn_bf16_packed_bytes(int A);
 size_t b200rl_naturecnn_bf16_acts_bytes(int64_t n, int obs_format);
@@ -246,10 +253,16 @@ int b200rl_naturecnn_bf16_pack(const float* params, int A, void* packed, void* s
 int b200rl_naturecnn_bf16_forward(const void* obs, int obs_format, const int64_t* rows, int64_t n, int A,
                                   const float* params, const void* packed, void* acts,
                                   float* head_out, void* stream);
-int b200rl_naturecnn_bf16_backward(const void* obs, int obs_format, const int64_t* rows, int64_t n, int A,
+int b200rl_naturecnn_bf16_backward(const void* obs, const void* obs_aux, int obs_format, const int64_t* rows, int64_t n, int A,
                                    const float* params, const void* packed, void* acts,
                                    const float* dhead, float* grads,
-                                   void* workspace, size_t workspace_bytes, void* stream);
+                                   void* workspace, size_t workspace_bytes, void* tail_ready_event, void* stream);
+/* Data-parallel overlap (cleanrl/ppo_atari_multigpu.py:360-374 exchanges the gradient after the whole backward):
+ * the backward finishes the head and fc gradients FIRST; they are the contiguous tail
+ * grads[b200rl_naturecnn_grad_tail_offset(A) .. param_count) = 95 % of the vector.  When `tail_ready_event`
+ * (a cudaEvent_t, may be NULL) is given, it is recorded on `stream` at that point, so the caller can all-reduce the
+ * tail on another stream while the convolution gradients are still being computed. */
+int64_t b200rl_naturecnn_grad_tail_offset(int A);
 
 /* --------------------------------------------------------- DQN TD update ---
  * td_target = r + gamma * max_a' Q_target(s')[a'] * (1 - done); old = Q(s)[a]; loss = mean((td - old)^2)

@@ -46,6 +46,32 @@ def atari_envpool(name, argv, n_iter, script="ppo_atari_envpool.py"):
     print("wrote", name, {k: v.shape for k, v in out.items() if hasattr(v, "shape")})
 
 
+def atari_envpool_full(name, argv):
+    """The HEADLINE configuration (BASELINE.json configs[1]: num_envs=1024, num_steps=128, minibatch 32 768), one
+    iteration of the unmodified cleanrl/ppo_atari_envpool.py on the Breakout-shaped synthetic env.  Integer-valued
+    tensors are stored narrow (actions int8, rewards int8, dones uint8) to keep the fixture at a few MB."""
+    rec, g = run_reference("ppo_atari_envpool.py", argv, atari_mode="fresh", gymnasium_kind="atari")
+    assert len(rec.iterations) == 1
+    it = rec.iterations[0]
+    out = {"argv": np.array(argv)}
+    assert np.array_equal(it["actions"], it["actions"].astype(np.int8)) and np.array_equal(it["rewards"], it["rewards"].astype(np.int8))
+    out["actions"] = it["actions"].astype(np.int8)[None]
+    out["rewards"] = it["rewards"].astype(np.int8)[None]
+    out["dones"] = it["dones"].astype(np.uint8)[None]
+    for k in ("logprobs", "values", "advantages", "returns", "next_value", "next_done", "param_sums", "param_abs_sums"):
+        out[k] = it[k][None]
+    for k in ("pg_loss", "v_loss", "entropy_loss", "old_approx_kl", "approx_kl", "loss", "clipfrac", "lr",
+              "grad_norm_postclip"):
+        out["upd_" + k] = np.array([u[k] for u in rec.updates])
+    out["upd_param_sums"] = _stack(rec.updates, "param_sums")
+    out["upd_mb_inds_head"] = _stack(rec.updates, "mb_inds_head")
+    out["shuffles"] = np.stack(rec.shuffles)
+    for t in sorted({t for t, _, _ in rec.scalars}):
+        out["tb/" + t] = np.array([(s, v) for tt, v, s in rec.scalars if tt == t], dtype=np.float64)
+    np.savez_compressed(OUT / name, **out)
+    print("wrote", name, {k: v.shape for k, v in out.items() if hasattr(v, "shape")})
+
+
 def mlp_ppo(name, argv):
     """cleanrl/ppo.py with the CartPole-shaped synthetic env: per-update tensors for loss/Adam oracles."""
     rec, g = run_reference("ppo.py", argv, gymnasium_kind="discrete", keep_params=True)
@@ -135,6 +161,10 @@ def main():
                       ["--no-cuda", "--num-envs", "8", "--num-steps", "16", "--total-timesteps", "384", "--seed", "5",
                        "--no-norm-adv", "--target-kl", "0.0005", "--max-grad-norm", "0.3", "--vf-coef", "0.25",
                        "--clip-coef", "0.2", "--learning-rate", "1e-3"], 3)
+    if "ppo_atari_full" in only:
+        # ~3 CPU-minutes: generated on request only (python -m oracle.make_golden ppo_atari_full)
+        atari_envpool_full("ppo_atari_envpool_n1024_t128_seed1.npz",
+                           ["--no-cuda", "--num-envs", "1024", "--num-steps", "128", "--total-timesteps", "131072", "--seed", "1"])
     if only:
         return
     dqn("dqn_atari_b8_seed1.npz",

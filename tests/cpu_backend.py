@@ -124,6 +124,7 @@ def install():
             _saved[(cls, attr)] = getattr(cls, attr)
             setattr(cls, attr, fn)
     agents.KernelAgent.bind = _bind_cpu
+    _saved[(agents.KernelAgent, "_build_plan")] = agents.KernelAgent._build_plan
     agents.KernelAgent._build_plan = lambda self: None
 
 

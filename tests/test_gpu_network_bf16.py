@@ -195,3 +195,94 @@ def test_full_size_minibatch_properties(lib):
     rel = ((g_sum - g_full).double().norm() / g_full.double().norm()).item()
     assert rel < 1e-4, rel
     assert torch.isfinite(g_full).all() and g_full.abs().max().item() > 0
+
+
+@pytest.mark.parametrize("n,B,A", [(24, 64, 4), (130, 130, 6), (1, 3, 4), (300, 300, 18), (37, 1000, 4)])
+def test_u8_rollout_forward_backward_layerwise(lib, n, B, A):
+    """The uint8 rollout format (what the engine stores and bench.py times): frames as 1-byte space-to-depth pixels in two
+    orientations, conv1 forward on the integer tensor cores (exact pixels, two signed 8-bit weight limbs, exact s32
+    accumulation), conv1 weight gradient with the pixels converted uint8 -> fp16 in registers and fed from tensor memory.
+    Reference = torch fp32 with bf16-rounded conv2/conv3/fc weights and inter-layer activations (what the other layers
+    compute) and UNROUNDED conv1 weights (the limb split resolves 2^-15 of the row maximum)."""
+    from cleanrl_b200 import ops
+    from cleanrl_b200.agents import NatureCNNAgent
+    torch.manual_seed(1)
+    agent = NatureCNNAgent(_Envs(A)).cuda()
+    agent.precision = "bf16"
+    agent.flat
+    sd = {k: v.detach().cpu().clone() for k, v in agent.state_dict().items()}
+    g = torch.Generator().manual_seed(2)
+    obs = torch.randint(0, 256, (B, 4, 84, 84), dtype=torch.uint8, generator=g)
+    rows = torch.randperm(B, generator=g)[:n].sort().values
+    rm, cm = ops.frames_to_s2d_u8(obs.cuda())
+    # layouts: rm[i, Y*21+X, c*16+sy*4+sx] = obs[i, c, 4Y+sy, 4X+sx]; cm[i, ch, pos] likewise, rows 441..447 zero
+    ref_rm = obs.view(B, 4, 21, 4, 21, 4).permute(0, 2, 4, 1, 3, 5).reshape(B, 441, 64)
+    assert torch.equal(rm.cpu(), ref_rm), "row-major uint8 space-to-depth frames must be exact"
+    assert torch.equal(cm.cpu()[:, :, :441], ref_rm.permute(0, 2, 1)) and cm.cpu()[:, :, 441:].abs().sum() == 0
+    W = {k: (_bf16_round(v) if k.startswith("network") and k.endswith("weight") and not k.startswith("network.0") else v.clone())
+         .requires_grad_(True) for k, v in sd.items()}
+    x = obs[rows].float()
+    a1 = torch.relu(F.conv2d(x, W["network.0.weight"], None, stride=4) / 255.0 + W["network.0.bias"].view(1, -1, 1, 1))
+    a1r = a1 + (_bf16_round(a1) - a1).detach()
+    a2 = torch.relu(F.conv2d(a1r, W["network.2.weight"], W["network.2.bias"], stride=2))
+    a2r = a2 + (_bf16_round(a2) - a2).detach()
+    a3 = torch.relu(F.conv2d(a2r, W["network.4.weight"], W["network.4.bias"], stride=1))
+    a3r = a3 + (_bf16_round(a3) - a3).detach()
+    hid = torch.relu(F.linear(a3r.flatten(1), W["network.7.weight"], W["network.7.bias"]))
+    hidr = hid + (_bf16_round(hid) - hid).detach()
+    logits = F.linear(hidr, W["actor.weight"], W["actor.bias"])
+    value = F.linear(hidr, W["critic.weight"], W["critic.bias"])
+    lg, val = agent.forward_train(rm, rows.cuda(), aux=cm)
+    torch.cuda.synchronize()
+    acts = agent._tc.acts(n, 2).view(torch.bfloat16)
+    o = 0
+    got = {}
+    for name, shape in (("act1", (n, 10, 10, 128)), ("act2", (n, 9, 9, 64)), ("act3", (n, 7, 7, 64)), ("hid", (n, 512))):
+        cnt = int(np.prod(shape))
+        got[name] = acts[o:o + cnt].view(shape).float().cpu()
+        o += cnt
+    a1_cells = a1.view(n, 32, 10, 2, 10, 2).permute(0, 2, 4, 3, 5, 1).reshape(n, 10, 10, 128)
+    errs = {"act1": _maxrel(got["act1"], a1_cells), "act2": _maxrel(got["act2"], a2.permute(0, 2, 3, 1)),
+            "act3": _maxrel(got["act3"], a3.permute(0, 2, 3, 1)), "hid": _maxrel(got["hid"], hid),
+            "logits": _maxrel(lg, logits), "value": _maxrel(val, value[:, 0])}
+    print("u8 rollout forward max-rel errors:", errs)
+    assert errs["act1"] < 4e-3, errs          # bf16 OUTPUT rounding only (2^-9): inputs exact, weights to 2^-15 of the row max
+    for k, v in errs.items():
+        assert v < 1e-2, (k, errs)
+    gl = torch.randn(n, A, generator=g) * 1e-3          # realistic gradient magnitudes (loss means over 32 768 samples)
+    gv = torch.randn(n, generator=g) * 1e-3
+    dhead, dl, dv = agent.alloc_head_grad(n, torch.device("cuda"))
+    dl.copy_(gl); dv.copy_(gv)
+    agent.backward(dhead)
+    torch.cuda.synchronize()
+    ((logits * gl).sum() + (value[:, 0] * gv).sum()).backward()
+    gerrs = {k: _rel(p.grad, W[k].grad) for k, p in agent.named_parameters()}
+    print("u8 rollout gradient rel-L2 errors:", gerrs)
+    for k, v in gerrs.items():
+        assert v < 2e-2, (k, gerrs)
+    assert torch.isfinite(agent.flat.grad).all()
+
+
+def test_u8_rollout_equals_bf16_rollout_downstream(lib):
+    """Both rollout layouts hold the same pixels exactly; their conv1 outputs differ only by the weight representation
+    (two 8-bit limbs vs one bf16), so heads and gradients agree to bf16 accuracy, with and without the row gather."""
+    from cleanrl_b200 import ops
+    from cleanrl_b200.agents import NatureCNNAgent
+    torch.manual_seed(2)
+    agent = NatureCNNAgent(_Envs(4)).cuda()
+    agent.precision = "bf16"
+    B, n = 96, 40
+    obs = torch.randint(0, 256, (B, 4, 84, 84), dtype=torch.uint8).cuda()
+    s2d = ops.frames_to_s2d(obs)
+    rm, cm = ops.frames_to_s2d_u8(obs)
+    for rows in (torch.randperm(B)[:n].sort().values.cuda(), None):
+        m = n if rows is not None else B
+        res = []
+        for x, aux in ((s2d, None), (rm, cm)):
+            lg, v = agent.forward_train(x, rows, **({"aux": aux} if aux is not None else {}))
+            dhead, dl, dv = agent.alloc_head_grad(m, torch.device("cuda"))
+            dl.copy_(torch.ones(m, 4, device="cuda") * 1e-3); dv.copy_(torch.linspace(-1, 1, m, device="cuda") * 1e-3)
+            agent.backward(dhead)
+            res.append((lg.clone(), v.clone(), agent.flat.grad.clone()))
+        assert _maxrel(res[1][0], res[0][0]) < 1e-2 and _maxrel(res[1][1], res[0][1]) < 1e-2
+        assert _rel(res[1][2], res[0][2]) < 2e-2

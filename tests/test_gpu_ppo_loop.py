@@ -32,8 +32,7 @@ def _run(name, extra=()):
     from cleanrl_b200.agents import NatureCNNAgent
     z = np.load(GOLDEN / name)
     argv = [a for a in z["argv"].tolist() if a != "--no-cuda"] + list(extra)
-    if name.startswith("ppo_atari_gym"):
-        argv.append("--synthetic-env")
+    argv.append("--synthetic-env")
     snaps = []
     writers = []
 
@@ -270,7 +269,7 @@ def test_script_runs_under_runpy_like_the_tuner(lib, tmp_path, monkeypatch):
     monkeypatch.chdir(tmp_path)
     monkeypatch.setattr(sys, "argv", ["ppo.py", "--total-timesteps", "1024", "--seed", "3", "--synthetic-env"])
     g = runpy.run_path(str(ROOT / "cleanrl_b200" / "ppo.py"), run_name="__main__")
-    assert isinstance(g["run_name"], str) and g["run_name"].startswith("CartPole-v1__ppo__3__")
+    assert isinstance(g["run_name"], str) and g["run_name"].startswith("CartPole-v1-synthetic__ppo__3__")
     events = list((tmp_path / "runs" / g["run_name"]).glob("events.out.tfevents.*"))
     assert len(events) == 1
     from tensorboard.backend.event_processing.event_accumulator import EventAccumulator

@@ -26,7 +26,7 @@ WORKER = textwrap.dedent('''
     import importlib
     S = importlib.import_module("cleanrl_b200." + os.environ["SCRIPT"])
     z = np.load(os.environ["FIXTURE"])
-    argv = [a for a in z["argv"].tolist()] + (["--synthetic-env"] if os.environ["SCRIPT"] != "ppo_atari_envpool" else [])
+    argv = [a for a in z["argv"].tolist()] + ["--synthetic-env"]
     class W:
         def __init__(self, *a): self.s = []
         def add_text(self, *a): pass
