@@ -165,10 +165,22 @@ def run_ours(opt):
         it_counter[0] += 1
         return (1.0 - (it_counter[0] - 1.0) / total_iters) * args.learning_rate
 
-    # ---- e2e: the public loop with host buffers
-    state = {"obs": envs.reset(), "done": np.zeros(N, dtype=np.float32)}
+    # ---- e2e: the public loop with host buffers.  --env-groups G > 1 (default 2): PPOEngine.collect over G independent
+    #      vector envs, software-pipelined (what `ppo_atari_envpool.py --env-groups G` runs); 1: the reference's loop order
+    G = max(1, int(opt.env_groups))
+    if G > 1:
+        env_parts = [SyntheticAtariVec(N // G, seed=seed + g * (N // G), mode="pool", pinned=True) for g in range(G)]
+        state = {"obs": [e.reset() for e in env_parts], "done": [np.zeros(N // G, dtype=np.float32) for _ in env_parts]}
+    else:
+        state = {"obs": envs.reset(), "done": np.zeros(N, dtype=np.float32)}
 
     def iteration_e2e():
+        if G > 1:
+            obs_p, done_p = eng.collect(env_parts, state["obs"], state["done"])
+            eng.finish_rollout_parts(obs_p, done_p)
+            st = eng.update(lr_now())
+            state["obs"], state["done"] = obs_p, done_p
+            return st
         next_obs, next_done = state["obs"], state["done"]
         for step in range(T):
             action = eng.policy_step(step, next_obs, next_done)
@@ -338,7 +350,8 @@ def run_ours(opt):
         "config": bench_config(N, T, world),
         "clocks": res["clocks"],
         "e2e": {"value": round(sps_e2e, 1), "unit": "env_steps/s", "ms_per_step": round(e2e["ms"] / K, 3),
-                "h2d_bytes_per_step": int(e2e["h2d"]), "d2h_bytes_per_step": int(e2e["d2h"]), "clocks": e2e["clocks"]},
+                "h2d_bytes_per_step": int(e2e["h2d"]), "d2h_bytes_per_step": int(e2e["d2h"]), "clocks": e2e["clocks"],
+                "env_groups": G, "loop": "PPOEngine.collect (pipelined env groups)" if G > 1 else "policy_step / env.step"},
         "gpu_launches": int(res["launches"]),
         "gae_us_per_rollout": gae,
         "roofline": roofline,
@@ -438,6 +451,7 @@ def main():
     ap.add_argument("--num-envs", type=int, default=1024)
     ap.add_argument("--num-steps", type=int, default=128)
     ap.add_argument("--precision", choices=["bf16", "fp32"], default="bf16")
+    ap.add_argument("--env-groups", type=int, default=2)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-gpu-eager-baseline", action="store_true")
     opt = ap.parse_args()

@@ -85,9 +85,16 @@ def ppo_args(exp_name="ppo"):
     return _make("Args", _override(_COMMON, exp_name=exp_name) + _ALGO + _RUNTIME + _EXTRA)
 
 
+_ENV_GROUPS = [
+    ("env_groups", int, 1,
+     "[b200] split the envs into this many independent vector envs and software-pipeline them: while one group's frames "
+     "are evaluated and its env steps on the host, the next group's frames cross PCIe (1 = the reference's loop order)"),
+]
+
+
 def ppo_atari_envpool_args(exp_name="ppo_atari_envpool"):
     algo = _override(_ALGO, env_id="Breakout-v5", total_timesteps=10000000, num_envs=8, clip_coef=0.1)
-    return _make("Args", _override(_COMMON, exp_name=exp_name) + algo + _RUNTIME + _EXTRA)
+    return _make("Args", _override(_COMMON, exp_name=exp_name) + algo + _RUNTIME + _EXTRA + _ENV_GROUPS)
 
 
 def ppo_atari_args(exp_name="ppo_atari"):
@@ -103,6 +110,28 @@ def ppo_atari_multigpu_args(exp_name="ppo_atari_multigpu"):
     dist = [
         ("device_ids", List[int], [], "the device ids that subprocess workers will use"),
         ("backend", Literal["gloo", "nccl", "mpi"], "gloo", "the backend for distributed training"),
+    ]
+    runtime = [
+        ("local_batch_size", int, 0, "the local batch size in the local rank (computed in runtime)"),
+        ("local_minibatch_size", int, 0, "the local mini-batch size in the local rank (computed in runtime)"),
+        ("num_envs", int, 0, "the number of parallel game environments (computed in runtime)"),
+    ] + _RUNTIME + [("world_size", int, 0, "the number of processes (computed in runtime)")]
+    return _make("Args", _override(_COMMON, exp_name=exp_name) + algo + dist + runtime + _EXTRA)
+
+
+def ppo_atari_multigpu_envpool_args(exp_name="ppo_atari_multigpu_envpool"):
+    """The script the reference defers (docs/rl-algorithms/ppo.md:1020): ppo_atari_multigpu.py's data parallelism over
+    ppo_atari_envpool.py's vector env.  Fields = the multi-GPU script's, env defaults = the envpool script's."""
+    algo = _override(_ALGO, env_id="Breakout-v5", total_timesteps=10000000, clip_coef=0.1)
+    algo = [r if r[0] != "num_envs" else
+            ("local_num_envs", int, 8, "the number of parallel game environments (in the local rank)") for r in algo]
+    dist = [
+        ("device_ids", List[int], [], "the device ids that subprocess workers will use"),
+        ("backend", Literal["gloo", "nccl", "mpi"], "nccl", "the backend for distributed training"),
+        ("env_threads", int, 0, "[b200] envpool worker threads per rank (0 = host cores / world size)"),
+        ("pin_env_threads", bool, True,
+         "[b200] pin each rank (and the env worker threads it spawns) to its own slice of the host cores, so the "
+         "ranks' env pools do not fight each other (docs/rl-algorithms/ppo.md:1020)"),
     ]
     runtime = [
         ("local_batch_size", int, 0, "the local batch size in the local rank (computed in runtime)"),

@@ -55,8 +55,8 @@ static int make_tmap_3d(CUtensorMap* tm, const void* base, int64_t n_images, int
     return B200RL_OK;
 }
 
-// uint8 [n_images][rows_per_image][cols <= 256] (row pitch `pitch` bytes), box = [1][box_rows][box_cols]; swizzle 64B when
-// box_cols == 64 (K-major operand rows), none otherwise (register-converted operands).  Out-of-range rows / columns are
+// uint8 [n_images][rows_per_image][cols] (row pitch `pitch` bytes), box = [1][box_rows][box_cols]; swizzle = the box
+// width (64 B or 128 B rows), none otherwise.  Out-of-range rows / columns are
 // zero-filled.
 static int make_tmap_3d_u8(CUtensorMap* tm, const void* base, int64_t n_images, int64_t rows_per_image, int64_t cols, int64_t pitch,
                            int box_rows, int box_cols, const char* what) {
@@ -70,9 +70,29 @@ static int make_tmap_3d_u8(CUtensorMap* tm, const void* base, int64_t n_images, 
     const cuuint32_t box[3] = {(cuuint32_t)box_cols, (cuuint32_t)box_rows, 1u};
     const cuuint32_t estr[3] = {1u, 1u, 1u};
     CUresult r = g_encode(tm, CU_TENSOR_MAP_DATA_TYPE_UINT8, 3, const_cast<void*>(base), dims, strides, box, estr,
-                          CU_TENSOR_MAP_INTERLEAVE_NONE, box_cols == 64 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_NONE,
+                          CU_TENSOR_MAP_INTERLEAVE_NONE,
+                          box_cols == 64 ? CU_TENSOR_MAP_SWIZZLE_64B : (box_cols == 128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_NONE),
                           CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) return fail(B200RL_ERR_CUDA, "%s: cuTensorMapEncodeTiled (u8 3-D) failed (%d)", what, (int)r);
+    return B200RL_OK;
+}
+
+// uint8 frames [n_images][441 positions][64 ch] read as [n_images][221 pair rows][128 B] (image stride 28 224 B), box =
+// [1][144 rows][128 B], SWIZZLE_128B; rows >= 221 are zero-filled
+static int make_tmap_pairs_u8(CUtensorMap* tm, const void* base, int64_t n_images, const char* what) {
+    if (!g_encode) {
+        CUtensorMap dummy;
+        int rc = make_tmap_2d(&dummy, base, 128, 64, 8, what);
+        if (rc) return rc;
+    }
+    const cuuint64_t dims[3] = {128u, 221u, (cuuint64_t)n_images};
+    const cuuint64_t strides[2] = {128u, 28224u};
+    const cuuint32_t box[3] = {128u, 144u, 1u};
+    const cuuint32_t estr[3] = {1u, 1u, 1u};
+    CUresult r = g_encode(tm, CU_TENSOR_MAP_DATA_TYPE_UINT8, 3, const_cast<void*>(base), dims, strides, box, estr,
+                          CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                          CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return fail(B200RL_ERR_CUDA, "%s: cuTensorMapEncodeTiled (u8 pair rows) failed (%d)", what, (int)r);
     return B200RL_OK;
 }
 

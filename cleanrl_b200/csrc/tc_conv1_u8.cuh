@@ -162,24 +162,33 @@ struct Conv1U8Params {
     uint32_t* mask_out;      // act1 > 0 bits: [n,100 cells] x 4 words
 };
 
+// Pair rows: TMA delivers one shared-memory row (<= 128 B) per request at ~5.5 cycles per request and SM -- the rate at
+// which 128-byte rows saturate HBM -- so a box of 64-byte rows moves half the bytes in the same time (measured: the first
+// version of this kernel, boxes of 152 x 64 B, sat at 44 % DRAM with its MMA issuer waiting on the TMA barrier).  The
+// row-major image [441][64 B] is therefore read as 221 rows of 128 B = PAIRS of grid positions (2q, 2q+1): one box of
+// 139 pair rows per 256 output positions.  GEMM rows are pair rows; the even and the odd position of each pair get their own
+// accumulator, and a tap (dy, dx) of position p = 2q + e is the 64-byte half ((e + dx + dy) & 1) of pair row
+// q + (e + 21 dy + dx) / 2 -- a K-major SWIZZLE_128B descriptor shifted by whole rows plus a 64-byte K offset.
 template <int STAGES>
 __global__ void __launch_bounds__(kConvWinThreads, 1) tc_conv1_i8(const __grid_constant__ CUtensorMap tmA, const Conv1U8Params p, int total_tiles) {
-    constexpr int BN = 64, WR = 152, NTAPS = 4;
-    constexpr int STAGE_BYTES = WR * 64;            // 9728: a multiple of 512, so every stage is atom-aligned
-    constexpr int B_CHUNK = BN * 64;                // one tap of the limb image: 64 rows x 64 B
-    constexpr uint32_t TMEM_COLS = 2 * BN;
+    constexpr int BN = 64, WR = 144, NTAPS = 4;
+    constexpr int STAGE_BYTES = WR * 128;           // 18432 = 18 x 1024
+    constexpr int B_CHUNK = BN * 64;                // one tap of the limb image: 64 rows x 64 B (SWIZZLE_64B)
+    constexpr int NT = 4;                           // tiles in flight in TMEM (see conv_win_acc_bufs)
+    constexpr uint32_t TMEM_COLS = 2 * NT * BN;     // accumulator 2 (q % NT) + e: tile q, e = 0 even / 1 odd positions
     extern __shared__ uint8_t smem_raw[];
-    __shared__ uint64_t full_bar[STAGES], empty_bar[STAGES], tfull_bar[2], tempty_bar[2];
+    __shared__ uint64_t full_bar[STAGES], empty_bar[STAGES], tfull_bar[2 * NT], tempty_bar[2 * NT];
     __shared__ uint32_t tmem_base_smem;
-    __shared__ float s_sc[64], s_bias[32];
+    __shared__ __align__(16) float s_sc[32], s_bias[32];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     const int tid = threadIdx.x, warp = tid >> 5;
     uint8_t* sW = smem;                             // 4 taps x 4096 B
     uint8_t* sRing = smem + NTAPS * B_CHUNK;        // 16384: 1024-aligned
+    uint8_t* sStage = sRing + (size_t)STAGES * STAGE_BYTES;     // 8 epilogue warps x (32 rows x 64 B + 32 row offsets)
 
     if (tid == 0) {
         for (int s = 0; s < STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
-        for (int a = 0; a < 2; ++a) { mbar_init(&tfull_bar[a], 1); mbar_init(&tempty_bar[a], 4); }
+        for (int a = 0; a < 2 * NT; ++a) { mbar_init(&tfull_bar[a], 1); mbar_init(&tempty_bar[a], 4); }
         fence_barrier_init();
         tma_prefetch_desc(&tmA);
     }
@@ -190,86 +199,96 @@ __global__ void __launch_bounds__(kConvWinThreads, 1) tc_conv1_i8(const __grid_c
         const int r = idx >> 4;
         *reinterpret_cast<int4*>(sW + t * B_CHUNK + img64_off(r, c16)) = ldg16(p.limbs + r * 256 + t * 64 + c16 * 16);
     }
-    if (tid < 64) s_sc[tid] = p.sc[tid];
-    if (tid < 32) s_bias[tid] = p.bias[tid];
+    if (tid < 32) { s_sc[tid] = p.sc[32 + tid]; s_bias[tid] = p.bias[tid]; }      // sc[32 + co] = s_co / 2^14 / 255
     fence_proxy_async_smem();
     tc_fence_before_sync();
     __syncthreads();
     tc_fence_after_sync();
     const uint32_t tmem_d = tmem_base_smem;
+    // a tile = 128 pair rows = 256 grid positions; 2 tiles per image (441 positions used)
     const int tile_begin = (int)(((int64_t)total_tiles * blockIdx.x) / gridDim.x);
     const int tile_end = (int)(((int64_t)total_tiles * (blockIdx.x + 1)) / gridDim.x);
 
     if (warp == 0) {
-        // ======================= TMA producer: one [152 rows x 64 B] box of one image per tile (4 tiles per image);
-        // the image coordinate is the minibatch gather, fetched one tile ahead
+        // ======================= TMA producer: one [139 (144) pair rows x 128 B] box of one image per tile; the image
+        // coordinate is the minibatch gather, fetched one tile ahead
         if (tid == 0) {
             uint32_t q = 0;
             int z_next = 0;
             if (tile_begin < tile_end) {
-                const int img = tile_begin >> 2;
+                const int img = tile_begin >> 1;
                 z_next = p.rows ? (int)__ldg(p.rows + img) : img;
             }
             for (int tile = tile_begin; tile < tile_end; ++tile, ++q) {
                 const uint32_t s = q % STAGES;
                 const int z = z_next;
                 if (tile + 1 < tile_end) {
-                    const int img = (tile + 1) >> 2;
+                    const int img = (tile + 1) >> 1;
                     z_next = p.rows ? (int)__ldg(p.rows + img) : img;
                 }
                 if (q >= (uint32_t)STAGES) mbar_wait(&empty_bar[s], ((q / STAGES) - 1) & 1);
                 mbar_arrive_expect_tx(&full_bar[s], (uint32_t)STAGE_BYTES);
-                tma_load_3d(smem_u32(sRing + (size_t)s * STAGE_BYTES), &tmA, 0, (tile & 3) * 128, z, &full_bar[s]);
+                tma_load_3d(smem_u32(sRing + (size_t)s * STAGE_BYTES), &tmA, 0, (tile & 1) * 128, z, &full_bar[s]);
             }
         }
-    } else if (warp == 1 || warp == 10) {
-        // ======================= MMA issuers (warp-uniform loop, one elected lane each; issuer ih owns the tiles of parity ih
-        // = accumulator buffer ih, as in tc_conv_win): per tile 4 taps x 2 K-steps of 32 bytes
-        const uint32_t ih = warp == 1 ? 0u : 1u;
+    } else if (warp == 1) {
+        // ======================= MMA issuer (warp-uniform loop, one elected lane): per tile and parity 4 taps x 2 K-steps of
+        // 32 bytes.  A: K-major SWIZZLE_128B pair rows (row shift + 64-byte half); B: K-major SWIZZLE_64B limb rows.
         const bool leader = elect_one();
         constexpr uint32_t idesc = make_idesc_i8(128, BN);
-        const uint64_t desc_hi = desc_kmajor_sw64(0) & 0xFFFFFFFF00000000ull;
-        const uint32_t desc_lo_flags = (uint32_t)(desc_kmajor_sw64(0) & 0xFFFFFFFFull);
-        const uint32_t w_lo = ((smem_u32(sW) & 0x3FFFFu) >> 4) | desc_lo_flags;
-        constexpr int shift[4] = {0, 1, 21, 22};
-        for (uint32_t q = ih; (int)q < tile_end - tile_begin; q += 2) {
-            const uint32_t acc = ih, s = q % STAGES;
-            if (q >= 2) mbar_wait(&tempty_bar[acc], ((q >> 1) - 1) & 1);
+        const uint64_t a_hi = desc_kmajor(0) & 0xFFFFFFFF00000000ull;
+        const uint32_t a_flags = (uint32_t)(desc_kmajor(0) & 0xFFFFFFFFull);
+        const uint64_t b_hi = desc_kmajor_sw64(0) & 0xFFFFFFFF00000000ull;
+        const uint32_t b_flags = (uint32_t)(desc_kmajor_sw64(0) & 0xFFFFFFFFull);
+        const uint32_t w_lo = ((smem_u32(sW) & 0x3FFFFu) >> 4) | b_flags;
+        // tap t = (dy, dx): position offset 21 dy + dx; for parity e the operand is half (e + off) & 1 of pair row + (e + off) >> 1
+        constexpr int off[4] = {0, 1, 21, 22};
+        uint32_t q = 0;
+        for (int tile = tile_begin; tile < tile_end; ++tile, ++q) {
+            const uint32_t s = q % STAGES;
             mbar_wait(&full_bar[s], (q / STAGES) & 1);
-            tc_fence_after_sync();
-            if (leader) {
-                const uint32_t d_addr = tmem_d + acc * BN;
-                const uint32_t win_lo = ((smem_u32(sRing + (size_t)s * STAGE_BYTES) & 0x3FFFFu) >> 4) | desc_lo_flags;
+            const uint32_t win_lo = ((smem_u32(sRing + (size_t)s * STAGE_BYTES) & 0x3FFFFu) >> 4) | a_flags;
 #pragma unroll
-                for (int t = 0; t < NTAPS; ++t) {
-                    const uint32_t a_lo = win_lo + (uint32_t)shift[t] * 4u;          // whole 64-byte rows
-                    const uint32_t b_lo = w_lo + (uint32_t)((t * B_CHUNK) >> 4);
+            for (int e = 0; e < 2; ++e) {
+                const uint32_t acc = 2 * (q % NT) + e;
+                if (q >= (uint32_t)NT) mbar_wait(&tempty_bar[acc], ((q / NT) - 1) & 1);
+                tc_fence_after_sync();
+                if (leader) {
+                    const uint32_t d_addr = tmem_d + acc * BN;
 #pragma unroll
-                    for (int kk = 0; kk < 2; ++kk)
-                        umma_i8(d_addr, desc_hi | (uint64_t)(a_lo + 2 * kk), desc_hi | (uint64_t)(b_lo + 2 * kk), idesc,
-                                (t | kk) != 0 ? 1u : 0u);
+                    for (int t = 0; t < NTAPS; ++t) {
+                        const int po = e + off[t];
+                        const uint32_t a_lo = win_lo + (uint32_t)((po >> 1) * 8 + (po & 1) * 4);      // rows of 128 B, halves of 64 B
+                        const uint32_t b_lo = w_lo + (uint32_t)((t * B_CHUNK) >> 4);
+#pragma unroll
+                        for (int kk = 0; kk < 2; ++kk)
+                            umma_i8(d_addr, a_hi | (uint64_t)(a_lo + 2 * kk), b_hi | (uint64_t)(b_lo + 2 * kk), idesc,
+                                    (t | kk) != 0 ? 1u : 0u);
+                    }
+                    if (e == 1) umma_commit(&empty_bar[s]);
+                    umma_commit(&tfull_bar[acc]);
                 }
-                umma_commit(&empty_bar[s]);
-                umma_commit(&tfull_bar[acc]);
+                __syncwarp();
             }
-            __syncwarp();
         }
-    } else {
-        // ======================= epilogue: warps 2-9 = two groups of four (one warp per TMEM lane quadrant); group h owns
-        // accumulator buffer h = every other tile.  Row -> (image, Y, X) -> 2x2-cell offset once per tile and thread.
+    } else if (warp < 10) {
+        // ======================= epilogue: warps 2-9 = two groups of four (one warp per TMEM lane quadrant); group e drains
+        // the accumulator of parity e of EVERY tile: lane = pair row q, output position p = 2q + e.
         const int ew = warp & 3;
-        const int h = (warp - 2) >> 2;
+        const int e = (warp - 2) >> 2;
         const int lrow = ew * 32 + (tid & 31);
-        const uint32_t lane_addr = tmem_d + h * BN + ((uint32_t)(ew * 32) << 16);
+        const uint32_t lane_base = tmem_d + ((uint32_t)(ew * 32) << 16);
         uint32_t k = 0;
-        for (int tile = tile_begin + h; tile < tile_end; tile += 2, ++k) {
-            const int i = tile >> 2;
-            const int rem = ((tile & 3) << 7) + lrow;
+        for (int tile = tile_begin; tile < tile_end; ++tile, ++k) {
+            const uint32_t acc = 2 * (k % NT) + e;
+            const uint32_t lane_addr = lane_base + acc * BN;
+            const int i = tile >> 1;
+            const int rem = 2 * (((tile & 1) << 7) + lrow) + e;
             const int Y = (rem * 3121) >> 16, X = rem - Y * 21;          // rem / 21 for rem < 512
             const bool valid = rem < 441 && Y < 20 && X < 20;
             const int64_t cell = ((int64_t)i * 10 + (Y >> 1)) * 10 + (X >> 1);
             const int cls = (Y & 1) * 2 + (X & 1);
-            mbar_wait(&tfull_bar[h], k & 1);
+            mbar_wait(&tfull_bar[acc], (k / NT) & 1);
             tc_fence_after_sync();
             uint32_t a1[32], a2[32];
             tmem_ld32(lane_addr, a1);
@@ -277,25 +296,49 @@ __global__ void __launch_bounds__(kConvWinThreads, 1) tc_conv1_i8(const __grid_c
             tmem_ld_wait();
             tc_fence_before_sync();
             __syncwarp();
-            if ((tid & 31) == 0) mbar_arrive(&tempty_bar[h]);              // accumulator drained
-            if (!valid) continue;
+            if ((tid & 31) == 0) mbar_arrive(&tempty_bar[acc]);            // accumulator drained
+            // y = (128 acc1 + acc2) * (s / 2^14 / 255) + bias: the limb recombination is exact in int32 (|128 acc1| < 2^31)
             uint32_t bits = 0u;
-            int4 w[4];
             uint32_t pk[16];
 #pragma unroll
-            for (int e = 0; e < 32; e += 2) {
-                float f0 = fmaf((float)(int)a1[e], s_sc[e], fmaf((float)(int)a2[e], s_sc[32 + e], s_bias[e]));
-                float f1 = fmaf((float)(int)a1[e + 1], s_sc[e + 1], fmaf((float)(int)a2[e + 1], s_sc[33 + e], s_bias[e + 1]));
-                const bool p0 = f0 > 0.f, p1 = f1 > 0.f;
-                bits |= (p0 ? 1u : 0u) << e;
-                bits |= (p1 ? 1u : 0u) << (e + 1);
-                pk[e >> 1] = pack_bf16x2(p0 ? f0 : 0.f, p1 ? f1 : 0.f);
+            for (int c4 = 0; c4 < 32; c4 += 4) {
+                const float4 sc = *reinterpret_cast<const float4*>(s_sc + c4);
+                const float4 bi = *reinterpret_cast<const float4*>(s_bias + c4);
+                const float f0 = fmaf((float)((int)a1[c4] * 128 + (int)a2[c4]), sc.x, bi.x);
+                const float f1 = fmaf((float)((int)a1[c4 + 1] * 128 + (int)a2[c4 + 1]), sc.y, bi.y);
+                const float f2 = fmaf((float)((int)a1[c4 + 2] * 128 + (int)a2[c4 + 2]), sc.z, bi.z);
+                const float f3 = fmaf((float)((int)a1[c4 + 3] * 128 + (int)a2[c4 + 3]), sc.w, bi.w);
+                bits |= (f0 > 0.f ? 1u : 0u) << c4;
+                bits |= (f1 > 0.f ? 1u : 0u) << (c4 + 1);
+                bits |= (f2 > 0.f ? 1u : 0u) << (c4 + 2);
+                bits |= (f3 > 0.f ? 1u : 0u) << (c4 + 3);
+                pk[c4 >> 1] = pack_bf16x2(fmaxf(f0, 0.f), fmaxf(f1, 0.f));
+                pk[(c4 >> 1) + 1] = pack_bf16x2(fmaxf(f2, 0.f), fmaxf(f3, 0.f));
             }
-            p.mask_out[cell * 4 + cls] = bits;
+            if (valid) p.mask_out[cell * 4 + cls] = bits;
+            // Stores: a lane owns one output row (64 B at its own 2x2-cell address), so a direct 16-byte store instruction of
+            // the warp touches 32 different lines = 32 L1 wavefronts -- measured, the epilogue's global stores took more of
+            // the L1 data pipe than the MMAs' operand reads.  The rows go through a per-warp staging tile instead (XOR
+            // swizzle: conflict-free both ways), and 4 consecutive lanes write one row's 64 bytes: 8 lines per instruction.
+            uint8_t* stg = sStage + (size_t)(warp - 2) * 2304;
+            const int lane = tid & 31;
+            {
+                const uint32_t f = (uint32_t)(lane >> 1) & 3u;
 #pragma unroll
-            for (int e = 0; e < 4; ++e) w[e] = make_int4((int)pk[4 * e], (int)pk[4 * e + 1], (int)pk[4 * e + 2], (int)pk[4 * e + 3]);
-            int4* dst = reinterpret_cast<int4*>(p.out + cell * 128 + cls * 32);
-            dst[0] = w[0]; dst[1] = w[1]; dst[2] = w[2]; dst[3] = w[3];
+                for (int c = 0; c < 4; ++c)
+                    *reinterpret_cast<int4*>(stg + lane * 64 + ((((uint32_t)c) ^ f) << 4)) =
+                        make_int4((int)pk[4 * c], (int)pk[4 * c + 1], (int)pk[4 * c + 2], (int)pk[4 * c + 3]);
+                reinterpret_cast<int*>(stg + 2048)[lane] = valid ? (int)(cell * 4 + cls) : -1;      // 64-byte units of act1
+            }
+            __syncwarp();
+#pragma unroll
+            for (int i2 = 0; i2 < 4; ++i2) {
+                const int R = (lane >> 2) + 8 * i2, c = lane & 3;
+                const int unit = reinterpret_cast<const int*>(stg + 2048)[R];
+                const int4 v = *reinterpret_cast<const int4*>(stg + R * 64 + ((((uint32_t)c) ^ ((uint32_t)(R >> 1) & 3u)) << 4));
+                if (unit >= 0) *reinterpret_cast<int4*>(reinterpret_cast<uint8_t*>(p.out) + (int64_t)unit * 64 + c * 16) = v;
+            }
+            __syncwarp();
         }
     }
     tc_fence_before_sync();
@@ -303,17 +346,17 @@ __global__ void __launch_bounds__(kConvWinThreads, 1) tc_conv1_i8(const __grid_c
     if (warp == 1) tmem_dealloc(tmem_d, TMEM_COLS);
 }
 
-
 // ------------------------------------------------------------------------------------ conv1 weight gradient (uint8 frames -> TMEM)
 // dW^T[(tap, c), co] = sum_r X[r + shift_tap, c] * dY[r, co] over the grid rows r of a step of 128 rows (4 steps per image).
-//   X   : channel-major frames [img][64 ch][448 rows] u8: one TMA box [64 ch][176 rows] per step (row pitch 176 B in shared
-//         memory: 16-byte reads of 32 consecutive channels are bank-conflict free).
+//   X   : channel-major frames [img][64 ch][448 rows] u8, staged in blocks of 128 positions (SWIZZLE_128B boxes of 64 full
+//         lines; 16-byte reads of 32 consecutive channel rows are bank-conflict free through the swizzle).
 //   dY  : d(act1) on the 21x21 grid, fp16 [img][441][32] scaled by 2^12 (written by conv2's data gradient with a
 //         saturating conversion): one SWIZZLE_64B TMA box of 128 rows per step = MN-major B operand, N = 32.
 //   A   : 2 M-tiles of 128 lanes; lane m of tile j = (tap = 2 (m >> 6) + j, channel m & 63); K = the 128 rows of the step
 //         = 64 TMEM columns per tile, double-buffered.  Eight convert warps (lane quadrant = warp % 4, K half = warp / 4)
-//         read their channel's bytes with 16-byte loads, funnel-shift the two taps' windows (PRMT), expand uint8 -> fp16 with
-//         one PRMT per two pixels (bytes (x, 0x64) = fp16 1024 + x) and one HSUB2, and tcgen05.st them into tensor memory.
+//         read their channel's bytes with 16-byte loads, funnel-shift the first tap's window (PRMT), expand uint8 -> fp16 with
+//         one PRMT per two pixels (bytes (x, 0x64) = fp16 1024 + x; the offset is taken out again through the bias partial),
+//         derive the second tap's window (one pixel later) with one PRMT per pair, and tcgen05.st both into tensor memory.
 //   Two issuer warps (one per M-tile) run tcgen05.mma with A in TMEM; four more warps accumulate the bias gradient
 //   (column sums of dY) from the staged tiles and drain the accumulators at the end.  Partial tiles go to
 //   ws[cta][256][64] / wsb[cta][64] (first 32 columns used) and are folded in fixed order by tc_fold_win.
@@ -324,8 +367,11 @@ struct Conv1WgradU8Params {
     float* ws;
     float* wsb;
 };
-constexpr int kC1WStages = 6;
-constexpr int kC1WXBytes = 64 * 176, kC1WYBytes = 128 * 64, kC1WStageBytes = kC1WXBytes + kC1WYBytes;    // 19456 = 19 * 1024
+// X blocks (8 KB: 64 channels x 128 positions) and dY steps (8 KB) in flight: 176 KB per SM.  With 80 KB (6 + 4 stages) every
+// role of the kernel spent its time waiting on the TMA barriers at 41 % of the HBM bandwidth: the gather reads need ~3 us of
+// loads in flight to cover their latency.
+constexpr int kC1WXStages = 12, kC1WYStages = 10;
+constexpr int kC1WBlock = 64 * 128, kC1WYBytes = 128 * 64;
 constexpr float kDact1Scale = 4096.0f;
 
 __device__ __forceinline__ uint32_t prmt(uint32_t a, uint32_t b, uint32_t sel) {
@@ -333,38 +379,45 @@ __device__ __forceinline__ uint32_t prmt(uint32_t a, uint32_t b, uint32_t sel) {
     asm("prmt.b32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(sel));
     return d;
 }
-__device__ __forceinline__ uint32_t hsub2_1024(uint32_t h) {         // (1024 + x) - 1024, exact
-    uint32_t d;
-    asm("sub.rn.f16x2 %0, %1, %2;" : "=r"(d) : "r"(h), "r"(0x64006400u));
-    return d;
-}
-// 64 pixels (16 words starting at byte offset `b` of W[w0]) -> 32 packed fp16 pairs, K order preserved
+// 68 pixels (17 words starting at byte offset B of W[0]) -> 34 fp16 pairs H with value 1024 + x (bytes (x, 0x64) are the
+// fp16 1024 + x exactly); the 1024 is NOT removed here: sum_r (1024 + x) dY = dW + 1024 sum_r dY, and sum_r dY is the bias
+// partial the same CTA computes anyway, so the drain subtracts 1024 x it (fp32; the offset costs < 1e-5 relative accuracy).
 template <int B>
-__device__ __forceinline__ void u8_window_to_f16(const uint32_t* W, uint32_t (&out)[32]) {
+__device__ __forceinline__ void u8_to_f16_biased(const uint32_t* W, uint32_t (&H)[34]) {
 #pragma unroll
-    for (int j = 0; j < 16; ++j) {
+    for (int j = 0; j < 17; ++j) {
         uint32_t x = W[j];
         if (B == 1) x = prmt(W[j], W[j + 1], 0x4321u);
         if (B == 2) x = prmt(W[j], W[j + 1], 0x5432u);
         if (B == 3) x = prmt(W[j], W[j + 1], 0x6543u);
-        out[2 * j] = hsub2_1024(prmt(x, 0x64646464u, 0x5140u));
-        out[2 * j + 1] = hsub2_1024(prmt(x, 0x64646464u, 0x7362u));
+        H[2 * j] = prmt(x, 0x64646464u, 0x5140u);
+        H[2 * j + 1] = prmt(x, 0x64646464u, 0x7362u);
     }
 }
+constexpr float kU8Bias = 1024.0f;
 
+// X staging: the channel-major image [64 ch][448 positions] is read in BLOCKS of 128 positions (one SWIZZLE_128B TMA box
+// of 64 rows x 128 B = 64 full lines; boxes with a 22-position halo would straddle two lines per channel and cost twice the
+// TMA requests).  Step k of the CTA's contiguous range uses block k and, for the taps' halo (<= 22 positions), the first
+// bytes of block k + 1 -- the next block of the same image, or of the next image after the last step of an image, where
+// the halo only multiplies dY rows that are zero (positions >= 441).  One extra block follows the CTA's last step.
 __global__ void __launch_bounds__(512, 1) tc_conv1_wgrad_u8(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmY,
                                                             const Conv1WgradU8Params p) {
-    constexpr int STAGES = kC1WStages;
+    constexpr int XS = kC1WXStages, YS = kC1WYStages;
     constexpr uint32_t TMEM_COLS = 512, COL_D = 0, COL_A = 64;
     extern __shared__ uint8_t smem_raw[];
-    __shared__ uint64_t full_bar[STAGES], empty_bar[STAGES], a_full[2], a_empty[2], done_bar;
+    constexpr int NA = 3;                                 // A-operand buffers in TMEM (128 columns each)
+    __shared__ uint64_t xfull[XS], xempty[XS], yfull[YS], yempty[YS], a_full[NA], a_empty[NA], done_bar;
     __shared__ uint32_t tmem_base_smem;
-    __shared__ float sRed[32 * 32];
+    __shared__ float sRed[32 * 32], sBias[32];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint8_t* sX = smem;                                 // XS blocks of 8 KB
+    uint8_t* sYb = smem + (size_t)XS * kC1WBlock;       // YS tiles of 8 KB
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     if (tid == 0) {
-        for (int s = 0; s < STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 8 + 2 + 4); }
-        for (int b = 0; b < 2; ++b) { mbar_init(&a_full[b], 8); mbar_init(&a_empty[b], 2); }
+        for (int s = 0; s < XS; ++s) { mbar_init(&xfull[s], 1); mbar_init(&xempty[s], 8); }
+        for (int s = 0; s < YS; ++s) { mbar_init(&yfull[s], 1); mbar_init(&yempty[s], 2 + 4); }
+        for (int b = 0; b < NA; ++b) { mbar_init(&a_full[b], 8); mbar_init(&a_empty[b], 2); }
         mbar_init(&done_bar, 2);
         fence_barrier_init();
         tma_prefetch_desc(&tmX);
@@ -383,27 +436,28 @@ __global__ void __launch_bounds__(512, 1) tc_conv1_wgrad_u8(const __grid_constan
     const int64_t g0 = m_begin >> 7;                       // first global step (4 steps per image)
 
     if (warp == 0) {
-        // ======================= TMA producer: dY rows (SW64) + the channel-major frame window of the step
-        if (lane == 0) {
-            int z_next = 0;
-            if (nsteps > 0) {
-                const int64_t img = g0 >> 2;
-                z_next = p.rows ? (int)__ldg(p.rows + img) : (int)img;
-            }
-            for (int it = 0; it < nsteps; ++it) {
-                const int s = it % STAGES;
-                const int64_t g = g0 + it;
+        // ======================= TMA producer: X block k (k = 0 .. nsteps, the last one is halo only) and dY rows of step k
+        if (lane == 0 && nsteps > 0) {
+            auto image_of = [&](int64_t g) -> int {
+                int64_t img = g >> 2;
+                if (img >= p.n) img = p.n - 1;             // the halo block after the very last step: any mapped block will do
+                return p.rows ? (int)__ldg(p.rows + img) : (int)img;
+            };
+            int z_next = image_of(g0);
+            for (int k = 0; k <= nsteps; ++k) {
+                const int64_t g = g0 + k;
                 const int z = z_next;
-                if (it + 1 < nsteps) {
-                    const int64_t img1 = (g + 1) >> 2;
-                    z_next = p.rows ? (int)__ldg(p.rows + img1) : (int)img1;
+                if (k < nsteps) z_next = image_of(g + 1);
+                const int xs = k % XS;
+                if (k >= XS) mbar_wait(&xempty[xs], ((k / XS) - 1) & 1);
+                mbar_arrive_expect_tx(&xfull[xs], (uint32_t)kC1WBlock);
+                tma_load_3d(smem_u32(sX + (size_t)xs * kC1WBlock), &tmX, (int)(g & 3) * 128, 0, z, &xfull[xs]);
+                if (k < nsteps) {
+                    const int ys = k % YS;
+                    if (k >= YS) mbar_wait(&yempty[ys], ((k / YS) - 1) & 1);
+                    mbar_arrive_expect_tx(&yfull[ys], (uint32_t)kC1WYBytes);
+                    tma_load_3d(smem_u32(sYb + (size_t)ys * kC1WYBytes), &tmY, 0, (int)(g & 3) * 128, (int)(g >> 2), &yfull[ys]);
                 }
-                if (it >= STAGES) mbar_wait(&empty_bar[s], ((it / STAGES) - 1) & 1);
-                const uint32_t dst = smem_u32(smem + (size_t)s * kC1WStageBytes);
-                const int t_in = (int)(g & 3);
-                mbar_arrive_expect_tx(&full_bar[s], (uint32_t)kC1WStageBytes);
-                tma_load_3d(dst, &tmY, 0, t_in * 128, (int)(g >> 2), &full_bar[s]);
-                tma_load_3d(dst + kC1WYBytes, &tmX, t_in * 128, 0, z, &full_bar[s]);
             }
         }
     } else if (warp == 1 || warp == 2) {
@@ -414,18 +468,18 @@ __global__ void __launch_bounds__(512, 1) tc_conv1_wgrad_u8(const __grid_constan
         const uint64_t desc_hi = desc_mnmajor_sw64(0) & 0xFFFFFFFF00000000ull;
         const uint32_t desc_lo_flags = (uint32_t)(desc_mnmajor_sw64(0) & 0xFFFFFFFFull);
         for (int it = 0; it < nsteps; ++it) {
-            const int s = it % STAGES, buf = it & 1;
-            mbar_wait(&full_bar[s], (it / STAGES) & 1);
-            mbar_wait(&a_full[buf], (it >> 1) & 1);
+            const int ys = it % YS, buf = it % NA;
+            mbar_wait(&yfull[ys], (it / YS) & 1);
+            mbar_wait(&a_full[buf], (it / NA) & 1);
             tc_fence_after_sync();
             if (leader) {
-                const uint32_t y_lo = ((smem_u32(smem + (size_t)s * kC1WStageBytes) & 0x3FFFFu) >> 4) | desc_lo_flags;
-                const uint32_t a_col = tmem0 + COL_A + (uint32_t)(buf * 128 + j * 64);
+                const uint32_t y_lo = ((smem_u32(sYb + (size_t)ys * kC1WYBytes) & 0x3FFFFu) >> 4) | desc_lo_flags;
+                const uint32_t a_col = tmem0 + COL_A + (uint32_t)(buf * 128 + j * 64);     // COL_A + NA * 128 = 448 <= 512
 #pragma unroll
                 for (int kk = 0; kk < 8; ++kk)
                     umma_f16_ts(tmem0 + COL_D + (uint32_t)(j * 32), a_col + 8 * kk, desc_hi | (uint64_t)(y_lo + 64 * kk), idesc,
                                 (it | kk) != 0 ? 1u : 0u);
-                umma_commit(&empty_bar[s]);
+                umma_commit(&yempty[ys]);
                 umma_commit(&a_empty[buf]);
             }
             __syncwarp();
@@ -438,26 +492,37 @@ __global__ void __launch_bounds__(512, 1) tc_conv1_wgrad_u8(const __grid_constan
         const int tapslot = q >> 1;
         const int c = (q & 1) * 32 + lane;
         const uint32_t lane_base = tmem0 + COL_A + ((uint32_t)(q * 32) << 16) + (uint32_t)(kh * 32);
+        const int chunk0 = tapslot + kh * 4;               // first 16-byte chunk this thread needs (tapslot 1 starts at byte 16)
+        const uint32_t row_off = (uint32_t)c * 128u, sw = (uint32_t)(c & 7);
         for (int it = 0; it < nsteps; ++it) {
-            const int s = it % STAGES, buf = it & 1;
-            mbar_wait(&full_bar[s], (it / STAGES) & 1);
-            const uint8_t* src = smem + (size_t)s * kC1WStageBytes + kC1WYBytes + c * 176 + (tapslot ? 16 : 0) + kh * 64;
+            const int xm = it % XS, xh = (it + 1) % XS, buf = it % NA;
+            mbar_wait(&xfull[xm], (it / XS) & 1);
+            mbar_wait(&xfull[xh], ((it + 1) / XS) & 1);
+            const uint8_t* bm = sX + (size_t)xm * kC1WBlock + row_off;
+            const uint8_t* bh = sX + (size_t)xh * kC1WBlock + row_off;
             uint32_t W[24];
 #pragma unroll
             for (int v = 0; v < 6; ++v) {
-                const int4 t = *reinterpret_cast<const int4*>(src + 16 * v);
+                const int ci = chunk0 + v;
+                const uint8_t* src = (ci < 8 ? bm : bh) + ((((uint32_t)ci & 7u) ^ sw) << 4);
+                const int4 t = *reinterpret_cast<const int4*>(src);
                 W[4 * v] = (uint32_t)t.x; W[4 * v + 1] = (uint32_t)t.y; W[4 * v + 2] = (uint32_t)t.z; W[4 * v + 3] = (uint32_t)t.w;
             }
             __syncwarp();
-            if (lane == 0) mbar_arrive(&empty_bar[s]);             // this warp's bytes are in registers
-            if (it >= 2) mbar_wait(&a_empty[buf], ((it >> 1) - 1) & 1);
+            if (lane == 0) mbar_arrive(&xempty[xm]);               // block `it` was halo of step it-1 and main of step it: done
+            // tile 0 = first tap of the slot (shift 0 / 21): pixels k .. k + 63 of this K half; tile 1 = second tap (shift 1 /
+            // 22) = the same stream one pixel later: its pair m is (high half of H[m], low half of H[m + 1]).  tapslot 1 reads
+            // from byte 16, so its stream starts 5 bytes in: word 1, byte 1.
+            uint32_t H[34];
+            if (tapslot == 0) u8_to_f16_biased<0>(W, H); else u8_to_f16_biased<1>(W + 1, H);
+            if (it >= NA) mbar_wait(&a_empty[buf], ((it / NA) - 1) & 1);
             tc_fence_after_sync();
             uint32_t o[32];
-            // tile 0 = first tap of the slot (shift 0 / 21), tile 1 = second tap (shift 1 / 22); tapslot 1 reads from byte 16,
-            // so its windows start 5 / 6 bytes in: word 1, byte 1 / 2
-            if (tapslot == 0) u8_window_to_f16<0>(W, o); else u8_window_to_f16<1>(W + 1, o);
+#pragma unroll
+            for (int m = 0; m < 32; ++m) o[m] = H[m];
             tmem_st32(lane_base + (uint32_t)(buf * 128), o);
-            if (tapslot == 0) u8_window_to_f16<1>(W, o); else u8_window_to_f16<2>(W + 1, o);
+#pragma unroll
+            for (int m = 0; m < 32; ++m) o[m] = prmt(H[m], H[m + 1], 0x5432u);
             tmem_st32(lane_base + (uint32_t)(buf * 128 + 64), o);
             tmem_st_wait();
             tc_fence_before_sync();
@@ -472,9 +537,9 @@ __global__ void __launch_bounds__(512, 1) tc_conv1_wgrad_u8(const __grid_constan
 #pragma unroll
         for (int e = 0; e < 8; ++e) bsum[e] = 0.f;
         for (int it = 0; it < nsteps; ++it) {
-            const int s = it % STAGES;
-            mbar_wait(&full_bar[s], (it / STAGES) & 1);
-            const uint8_t* sY = smem + (size_t)s * kC1WStageBytes;
+            const int ys = it % YS;
+            mbar_wait(&yfull[ys], (it / YS) & 1);
+            const uint8_t* sY = sYb + (size_t)ys * kC1WYBytes;
 #pragma unroll
             for (int ps = 0; ps < 4; ++ps) {
                 const int rr = ps * 32 + rq;
@@ -488,7 +553,7 @@ __global__ void __launch_bounds__(512, 1) tc_conv1_wgrad_u8(const __grid_constan
                 }
             }
             __syncwarp();
-            if (lane == 0) mbar_arrive(&empty_bar[s]);
+            if (lane == 0) mbar_arrive(&yempty[ys]);
         }
 #pragma unroll
         for (int e = 0; e < 8; ++e) sRed[rq * 32 + c16 * 8 + e] = bsum[e];
@@ -498,7 +563,9 @@ __global__ void __launch_bounds__(512, 1) tc_conv1_wgrad_u8(const __grid_constan
 #pragma unroll
             for (int l = 0; l < 32; ++l) t += sRed[l * 32 + tb];
             p.wsb[(int64_t)blockIdx.x * 64 + tb] = t;
+            sBias[tb] = t * kU8Bias;                   // what the 1024 offset of every pixel added to each (tap, c) row
         }
+        asm volatile("bar.sync 1, 128;" ::: "memory");
         // drain the two accumulator tiles
         if (nsteps > 0) {
             mbar_wait(&done_bar, 0);
@@ -519,8 +586,8 @@ __global__ void __launch_bounds__(512, 1) tc_conv1_wgrad_u8(const __grid_constan
             float4* dst = reinterpret_cast<float4*>(wsc + (int64_t)(j * 128 + lrow) * 64);
 #pragma unroll
             for (int e = 0; e < 8; ++e)
-                dst[e] = make_float4(__uint_as_float(v[4 * e]), __uint_as_float(v[4 * e + 1]), __uint_as_float(v[4 * e + 2]),
-                                     __uint_as_float(v[4 * e + 3]));
+                dst[e] = make_float4(__uint_as_float(v[4 * e]) - sBias[4 * e], __uint_as_float(v[4 * e + 1]) - sBias[4 * e + 1],
+                                     __uint_as_float(v[4 * e + 2]) - sBias[4 * e + 2], __uint_as_float(v[4 * e + 3]) - sBias[4 * e + 3]);
         }
     }
     tc_fence_before_sync();
@@ -530,32 +597,35 @@ __global__ void __launch_bounds__(512, 1) tc_conv1_wgrad_u8(const __grid_constan
 
 static int launch_conv1_wgrad_u8(const Conv1WgradU8Params& p, const void* frames_cm, int64_t n_images, const void* dact1_f16, int ctas,
                                  cudaStream_t s, const char* what) {
-    const size_t smem = (size_t)kC1WStages * kC1WStageBytes + 1024;
+    const size_t smem = (size_t)kC1WXStages * kC1WBlock + (size_t)kC1WYStages * kC1WYBytes + 1024;
     static SmemAttrCache attr;
     int rc;
     if ((rc = attr.ensure(tc_conv1_wgrad_u8, smem, what))) return rc;
     if (p.rows_per_cta % 128 != 0) return fail(B200RL_ERR_INVALID_ARGUMENT, "%s: rows per CTA must be a multiple of 128", what);
     CUtensorMap tmX, tmY;
     memset(&tmX, 0, sizeof(tmX)); memset(&tmY, 0, sizeof(tmY));
-    // frames [img][64 ch][448 rows] u8: box = [64 ch][176 rows]; dY [img][441 rows][32 co] fp16 = 64-byte rows: box [128 rows][64 B]
-    if ((rc = make_tmap_3d_u8(&tmX, frames_cm, n_images, 64, 448, 448, 64, 176, what))) return rc;
+    // frames [img][64 ch][448 positions] u8: box = [64 ch][128 positions], SWIZZLE_128B; dY [img][441 rows][32 co] fp16 = 64-byte
+    // rows: box [128 rows][64 B], SWIZZLE_64B
+    if ((rc = make_tmap_3d_u8(&tmX, frames_cm, n_images, 64, 448, 448, 64, 128, what))) return rc;
     if ((rc = make_tmap_3d_u8(&tmY, dact1_f16, p.n, 441, 64, 64, 128, 64, what))) return rc;
     tc_conv1_wgrad_u8<<<ctas, 512, smem, s>>>(tmX, tmY, p);
     return check_launch(what);
 }
 
-constexpr int kConv1I8Stages = 12;
+constexpr int kConv1I8Stages = 8;
 static int launch_conv1_i8(const Conv1U8Params& p, const void* frames_rm, cudaStream_t s, const char* what) {
     constexpr int STAGES = kConv1I8Stages;
-    const size_t smem = (size_t)4 * 64 * 64 + (size_t)STAGES * 152 * 64 + 1024;
+    const size_t smem = (size_t)4 * 64 * 64 + (size_t)STAGES * 144 * 128 + 8 * 2304 + 1024;
     static SmemAttrCache attr;
     if (int rc = attr.ensure(tc_conv1_i8<STAGES>, smem, what)) return rc;
-    const int total = p.n * 4;                     // 4 tiles of 128 grid rows per image (441 used)
+    const int total = p.n * 2;                     // 2 tiles of 128 pair rows (256 grid positions) per image (441 used)
     int grid = num_sms();
     if (grid > total) grid = total;
     CUtensorMap tmA;
     memset(&tmA, 0, sizeof(tmA));
-    int rc = make_tmap_3d_u8(&tmA, frames_rm, p.n_images, 441, 64, 64, 152, 64, what);
+    // the row-major image [441][64 B] viewed as 221 pair rows of 128 B (image stride 28 224 B = 220.5 rows: the second
+    // half of row 220 belongs to the next image and only ever feeds invalid positions); SWIZZLE_128B boxes of 144 rows
+    int rc = make_tmap_pairs_u8(&tmA, frames_rm, p.n_images, what);
     if (rc) return rc;
     tc_conv1_i8<STAGES><<<grid, kConvWinThreads, smem, s>>>(tmA, p, total);
     return check_launch(what);

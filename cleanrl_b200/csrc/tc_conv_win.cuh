@@ -50,20 +50,26 @@ __device__ __forceinline__ uint32_t pack_f16x2_sat(float lo, float hi) {
     return d;
 }
 
-// Thread roles (352 threads): warp 0 = TMA producer; warps 1 and 10 = MMA issuers; warps 2-9 = epilogue.
-// TWO issuer warps: a tcgen05.mma costs its issuing thread ~8-10 dependent scalar/uniform instructions (descriptor
-// adds, moves into uniform registers, predicate), and a lone warp retires those at roughly one per 6 cycles, so a
-// single issuer delivered one M128 x N<=64 x K16 MMA per 65-79 cycles in EVERY narrow-N kernel regardless of its
-// byte traffic (tools/experiments/umma_chain_test.cu: the cost does not depend on N, the operand source or the
-// accumulator).  Issuer h owns accumulator buffer h = every other tile -- two independent chains on two schedulers.
+// Thread roles (352 threads): warp 0 = TMA producer; warp 1 (and warp 10 when kConvWinIssuers == 2) = MMA issuer;
+// warps 2-9 = epilogue.  A second issuer warp (issuer h owns accumulator buffer h = every other tile) was measured on the
+// bf16 kernels: no gain -- they sit at ~77 % of the shared-memory operand bandwidth (ncu sm__throughput), i.e. the 65-79
+// cycles per M128 x N<=64 x K16 MMA are the 5-6 KB of SS-mode operand reads, not the issuing thread -- and 5-13 % slower
+// on conv2 forward / conv3 data gradient (two more resident warps competing with the epilogue).  Kept as a switch.
 constexpr int kConvWinThreads = 352;
+constexpr int kConvWinIssuers = 1;
+// Accumulator buffers in TMEM.  With two, issuer and epilogue hand each buffer back and forth once per tile and a tile of
+// 8-36 small MMAs is shorter than that round trip (tcgen05.commit -> mbarrier -> epilogue wake-up -> tcgen05.ld ->
+// arrive -> issuer wake-up, ~1 us in total): ncu showed the issuer stalled on the `tempty` barrier and the epilogue on
+// `tfull` at the same time.  Four buffers (two per epilogue group) let the issuer run two tiles ahead of each group.
+__host__ __device__ constexpr int conv_win_acc_bufs(int BN) { return BN <= 128 ? 4 : 2; }
 template <int BN, int CPR, int STAGES, int NTAPS>
 __global__ void __launch_bounds__(kConvWinThreads, 1) tc_conv_win(const __grid_constant__ CUtensorMap tmA, const WinParams p,
                                                       int total_tiles) {
     constexpr int B_CHUNK = BN * 128;
-    constexpr uint32_t TMEM_COLS = (2 * BN) < 32 ? 32 : 2 * BN;
+    constexpr int NB = conv_win_acc_bufs(BN);
+    constexpr uint32_t TMEM_COLS = (NB * BN) < 32 ? 32 : NB * BN;
     extern __shared__ uint8_t smem_raw[];
-    __shared__ uint64_t full_bar[STAGES], empty_bar[STAGES], tfull_bar[2], tempty_bar[2];
+    __shared__ uint64_t full_bar[STAGES], empty_bar[STAGES], tfull_bar[NB], tempty_bar[NB];
     __shared__ uint32_t tmem_base_smem;
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     const int tid = threadIdx.x, warp = tid >> 5;
@@ -76,7 +82,7 @@ __global__ void __launch_bounds__(kConvWinThreads, 1) tc_conv_win(const __grid_c
 
     if (tid == 0) {
         for (int s = 0; s < STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
-        for (int a = 0; a < 2; ++a) { mbar_init(&tfull_bar[a], 1); mbar_init(&tempty_bar[a], 4); }
+        for (int a = 0; a < NB; ++a) { mbar_init(&tfull_bar[a], 1); mbar_init(&tempty_bar[a], 4); }
         fence_barrier_init();
         tma_prefetch_desc(&tmA);
     }
@@ -136,14 +142,15 @@ __global__ void __launch_bounds__(kConvWinThreads, 1) tc_conv_win(const __grid_c
         // per-tap base only in their 14-bit start-address field, so each MMA costs two 32-bit adds.  Issuer ih takes
         // the tiles of parity ih (accumulator buffer ih, epilogue group ih).
         const uint32_t ih = warp == 1 ? 0u : 1u;
+        if (ih < (uint32_t)kConvWinIssuers) {
         const bool leader = elect_one();
         constexpr uint32_t idesc = make_idesc(128, BN, 0, 0);
         const uint64_t desc_hi = desc_kmajor(0) & 0xFFFFFFFF00000000ull;
         const uint32_t desc_lo_flags = (uint32_t)(desc_kmajor(0) & 0xFFFFFFFFull);       // LBO field
         const uint32_t w_lo = ((smem_u32(sW) & 0x3FFFFu) >> 4) | desc_lo_flags;
-        for (uint32_t q = ih; (int)q < tile_end - tile_begin; q += 2) {
-            const uint32_t acc = ih, s = q % STAGES;
-            if (q >= 2) mbar_wait(&tempty_bar[acc], ((q >> 1) - 1) & 1);
+        for (uint32_t q = ih; (int)q < tile_end - tile_begin; q += kConvWinIssuers) {
+            const uint32_t acc = q % NB, s = q % STAGES;
+            if (q >= (uint32_t)NB) mbar_wait(&tempty_bar[acc], ((q / NB) - 1) & 1);
             mbar_wait(&full_bar[s], (q / STAGES) & 1);
             tc_fence_after_sync();
             if (leader) {
@@ -166,6 +173,7 @@ __global__ void __launch_bounds__(kConvWinThreads, 1) tc_conv_win(const __grid_c
             }
             __syncwarp();
         }
+        }
     } else {
         // ======================= epilogue: warps 2-9 = two groups of four (one warp per TMEM lane quadrant).
         // Group h owns accumulator buffer h, i.e. every other tile of the CTA's range, and handles ALL BN columns
@@ -180,10 +188,12 @@ __global__ void __launch_bounds__(kConvWinThreads, 1) tc_conv_win(const __grid_c
         int i_lin = (int)(r / p.G);
         int rem_lin = (int)(r - (int64_t)i_lin * p.G);
         const int tmask = (1 << p.tpi_shift) - 1;
-        const uint32_t lane_addr = tmem_d + h * BN + ((uint32_t)(ew * 32) << 16);
+        const uint32_t lane_base = tmem_d + ((uint32_t)(ew * 32) << 16);
         constexpr int NW = BN / 32;                          // 32-column groups = mask words per row
-        uint32_t k = 0;                                      // use count of accumulator buffer h
+        uint32_t k = 0;                                      // tiles this group has drained
         for (int tile = tile_begin + h; tile < tile_end; tile += 2, ++k) {
+            const uint32_t acc = (uint32_t)(tile - tile_begin) % NB;           // group h drains buffers h, h + 2, ...
+            const uint32_t lane_addr = lane_base + acc * BN;
             int i = i_lin, rem = rem_lin;
             bool inside = r < p.M;
             if (p.tpi_shift) {                               // image-aligned tiles: rows >= G of an image are padding
@@ -223,7 +233,7 @@ __global__ void __launch_bounds__(kConvWinThreads, 1) tc_conv_win(const __grid_c
                     mb[0] = __ldg(p.mask_bits + ob);
                 }
             }
-            mbar_wait(&tfull_bar[h], k & 1);
+            mbar_wait(&tfull_bar[acc], ((uint32_t)(tile - tile_begin) / NB) & 1);
             tc_fence_after_sync();
 #pragma unroll
             for (int g = 0; g < NW; ++g) {
@@ -233,7 +243,7 @@ __global__ void __launch_bounds__(kConvWinThreads, 1) tc_conv_win(const __grid_c
                 if (g == NW - 1) {             // accumulator drained: hand the buffer back before the global stores
                     tc_fence_before_sync();
                     __syncwarp();
-                    if ((tid & 31) == 0) mbar_arrive(&tempty_bar[h]);
+                    if ((tid & 31) == 0) mbar_arrive(&tempty_bar[acc]);
                 }
                 if (!valid || g * 32 >= p.N) continue;
                 if (p.bias) {

@@ -29,6 +29,7 @@ struct WGradWinParams {
 // 224 threads: warps 0-3 = dY warps (bias sums, final TMEM drain), warps 4 and 6 = MMA issuers (output tiles of even /
 // odd index: independent accumulators, see tc_conv_win.cuh for why one issuing thread is not enough), warp 5 = TMA.
 constexpr int kWgradWinThreads = 224;
+constexpr int kWgradWinIssuers = 1;      // 2 = warps 4 and 6 issue alternate output tiles; measured: no gain (shared-memory operand bound)
 __global__ void __launch_bounds__(kWgradWinThreads, 1) tc_wgrad_win(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmY,
                                                        const WGradWinParams p, int use_tma) {
     constexpr int R = 128, STAGES = kWgradWinStages, LOOKAHEAD = 1, NY = 64;
@@ -47,8 +48,8 @@ __global__ void __launch_bounds__(kWgradWinThreads, 1) tc_wgrad_win(const __grid
     if (tid == 0) {
         // full:  one expect_tx arrival (TMA) [+ the four cp.async warps that stage dY in image-aligned mode]
         // empty: the MMA commit [+ the four dY-summing warps when they read the stage after the TMA landed]
-        for (int s = 0; s < STAGES; ++s) { mbar_init(&full_bar[s], use_tma ? 1 : 5); mbar_init(&empty_bar[s], use_tma ? 6 : 2); }
-        mbar_init(&done_bar, 2);
+        for (int s = 0; s < STAGES; ++s) { mbar_init(&full_bar[s], use_tma ? 1 : 5); mbar_init(&empty_bar[s], (use_tma ? 4 : 0) + kWgradWinIssuers); }
+        mbar_init(&done_bar, kWgradWinIssuers);
         fence_barrier_init();
         tma_prefetch_desc(&tmX);
         if (use_tma) tma_prefetch_desc(&tmY);
@@ -176,6 +177,7 @@ __global__ void __launch_bounds__(kWgradWinThreads, 1) tc_wgrad_win(const __grid
         // inside the stage and its LBO field; descriptors then differ only in the 14-bit start-address field.
         const bool leader = elect_one();
         const int ih = warp == 4 ? 0 : 1;
+        if (ih < kWgradWinIssuers) {
         constexpr uint32_t idesc = make_idesc(128, NY, 1, 1);
         const uint64_t desc_hi = desc_mnmajor(0, 0) & 0xFFFFFFFF00000000ull;
         uint32_t arel[8], albo[8];
@@ -200,7 +202,7 @@ __global__ void __launch_bounds__(kWgradWinThreads, 1) tc_wgrad_win(const __grid
                 const uint32_t accum = it != 0 ? 1u : 0u;
 #pragma unroll
                 for (int t = 0; t < 8; ++t) {
-                    if (t < xt && (t & 1) == ih) {
+                    if (t < xt && (kWgradWinIssuers == 1 || (t & 1) == ih)) {
                         const uint32_t a_lo = (xa16 + arel[t]) | albo[t];
 #pragma unroll
                         for (int kk = 0; kk < R / 16; ++kk)
@@ -214,6 +216,7 @@ __global__ void __launch_bounds__(kWgradWinThreads, 1) tc_wgrad_win(const __grid
         }
         if (leader) umma_commit(&done_bar);
         __syncwarp();
+        }
     }
     if (warp < 4) {
         if (nsteps > 0) {

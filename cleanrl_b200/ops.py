@@ -399,6 +399,16 @@ def frames_to_s2d(obs_u8, out=None, rows=None):
     return out
 
 
+def alloc_u8_rollout_rows(shape, device):
+    """uint8 row-major rollout rows [..., 441, 64] with 256 bytes of slack behind the last frame: conv1 reads a frame as
+    221 rows of 128 bytes (pairs of grid positions), and the second half of the last pair row lies 64 bytes past the frame."""
+    n = 1
+    for d in shape:
+        n *= int(d)
+    flat = torch.zeros(n + 256, dtype=torch.uint8, device=device)
+    return flat[:n].view(*shape)
+
+
 def frames_to_s2d_u8(obs_u8, out_rm=None, out_cm=None, rows=None):
     """uint8 [n,4,84,84] frames -> uint8 space-to-depth rollout rows: row-major [n,441,64] (conv1 forward on the integer
     tensor cores) and channel-major [n,64,448] (conv1 weight gradient); once per env step, 1 byte per pixel each."""
@@ -406,7 +416,7 @@ def frames_to_s2d_u8(obs_u8, out_rm=None, out_cm=None, rows=None):
     _contig(obs_u8, "obs")
     n = rows.numel() if rows is not None else obs_u8.shape[0]
     if out_rm is None:
-        out_rm = torch.empty(n, 441, 64, dtype=torch.uint8, device=obs_u8.device)
+        out_rm = alloc_u8_rollout_rows((n, 441, 64), obs_u8.device)
     if out_cm is None:
         out_cm = torch.empty(n, 64, 448, dtype=torch.uint8, device=obs_u8.device)
     _contig(out_rm, "out_rm"); _contig(out_cm, "out_cm")

@@ -96,6 +96,20 @@ def make_envs(args, pinned=True, mode=None):
     return envs
 
 
+def make_env_groups(args, groups, pinned=True, mode=None):
+    """``groups`` independent vector envs over contiguous slices of the envs.  Group g is seeded ``seed + g * n`` so that,
+    with envpool's per-env seeding (seed + env index), every env keeps the stream it has in the single-pool run."""
+    import copy
+    assert args.num_envs % groups == 0, "--num-envs must be divisible by --env-groups"
+    n = args.num_envs // groups
+    parts = []
+    for g in range(groups):
+        sub = copy.copy(args)
+        sub.num_envs, sub.seed = n, args.seed + g * n
+        parts.append(make_envs(sub, pinned=pinned, mode=mode))
+    return parts
+
+
 def main(argv=None, writer_factory=None, env_factory=None, on_iteration=None):
     global run_name
     args = cli.parse(Args, argv)
@@ -127,7 +141,13 @@ def main(argv=None, writer_factory=None, env_factory=None, on_iteration=None):
     # "cpu" is only reachable from the CPU test harness (tests/cpu_backend.py drives the host logic with injected ops)
     device = torch.device("cuda" if torch.cuda.is_available() else "cpu")
 
-    envs = env_factory(args) if env_factory else make_envs(args)
+    groups = int(getattr(args, "env_groups", 1))
+    env_parts = None
+    if groups > 1:
+        env_parts = make_env_groups(args, groups)
+        envs = env_parts[0]
+    else:
+        envs = env_factory(args) if env_factory else make_envs(args)
     agent = Agent(envs).to(device)   # CPU init (same RNG stream as the reference), then moved
     agent.precision = args.precision
     engine = PPOEngine(agent, args, envs.single_observation_space.shape, envs.single_observation_space.dtype,
@@ -136,29 +156,47 @@ def main(argv=None, writer_factory=None, env_factory=None, on_iteration=None):
 
     global_step = 0
     start_time = time.time()
-    next_obs = envs.reset()
-    next_done = np.zeros(args.num_envs, dtype=np.float32)
+    if env_parts is not None:
+        obs_parts = [e.reset() for e in env_parts]
+        done_parts = [np.zeros(e.num_envs, dtype=np.float32) for e in env_parts]
+    else:
+        next_obs = envs.reset()
+        next_done = np.zeros(args.num_envs, dtype=np.float32)
     lrnow = args.learning_rate
+
+    def log_episodes(step_global, next_done, info):
+        finished = np.nonzero(np.logical_and(next_done, info["lives"] == 0))[0]
+        for idx in finished:
+            print(f"global_step={step_global}, episodic_return={info['r'][idx]}")
+            avg_returns.append(info["r"][idx])
+            writer.add_scalar("charts/avg_episodic_return", np.average(avg_returns), step_global)
+            writer.add_scalar("charts/episodic_return", info["r"][idx], step_global)
+            writer.add_scalar("charts/episodic_length", info["l"][idx], step_global)
 
     for iteration in range(1, args.num_iterations + 1):
         if args.anneal_lr:
             frac = 1.0 - (iteration - 1.0) / args.num_iterations
             lrnow = frac * args.learning_rate
 
-        for step in range(0, args.num_steps):
+        if env_parts is not None:
+            # grouped, software-pipelined rollout (PPOEngine.collect); global_step advances by num_envs per step as in the
+            # reference (ppo_atari_envpool.py:225)
+            base = global_step
+            obs_parts, done_parts = engine.collect(
+                env_parts, obs_parts, done_parts,
+                on_step=lambda t, p, reward, done, info: log_episodes(base + (t + 1) * args.num_envs, done, info))
+            global_step = base + args.num_steps * args.num_envs
+            engine.finish_rollout_parts(obs_parts, done_parts)
+
+        for step in range(0, args.num_steps if env_parts is None else 0):
             global_step += args.num_envs
             action = engine.policy_step(step, next_obs, next_done)
             next_obs, reward, next_done, info = envs.step(action)
             engine.record_reward(step, reward)
-            finished = np.nonzero(np.logical_and(next_done, info["lives"] == 0))[0]
-            for idx in finished:
-                print(f"global_step={global_step}, episodic_return={info['r'][idx]}")
-                avg_returns.append(info["r"][idx])
-                writer.add_scalar("charts/avg_episodic_return", np.average(avg_returns), global_step)
-                writer.add_scalar("charts/episodic_return", info["r"][idx], global_step)
-                writer.add_scalar("charts/episodic_length", info["l"][idx], global_step)
+            log_episodes(global_step, next_done, info)
 
-        engine.finish_rollout(next_obs, next_done)
+        if env_parts is None:
+            engine.finish_rollout(next_obs, next_done)
         st = engine.update(lrnow)
         explained_var = engine.explained_variance()
 
@@ -176,7 +214,8 @@ def main(argv=None, writer_factory=None, env_factory=None, on_iteration=None):
         if on_iteration is not None:
             on_iteration(iteration, engine, st)
 
-    envs.close()
+    for e in (env_parts or [envs]):
+        e.close()
     writer.close()
     return engine
 

@@ -84,7 +84,7 @@ class PPOEngine:
         self.u8_rollout = self.s2d and os.environ.get("CLEANRL_B200_OBS_LAYOUT", "u8") != "bf16"
         if self.s2d:
             if self.u8_rollout:
-                self.obs = torch.zeros((T, N, 441, 64), dtype=torch.uint8, device=device)
+                self.obs = ops.alloc_u8_rollout_rows((T, N, 441, 64), device)
                 self.obs_t = torch.zeros((T, N, 64, 448), dtype=torch.uint8, device=device)
                 self.next_obs_t = torch.zeros((N, 64, 448), dtype=torch.uint8, device=device)
             else:
@@ -103,7 +103,7 @@ class PPOEngine:
         self.dones = torch.zeros((T, N), dtype=f32, device=device)
         self.advantages = torch.zeros((T, N), dtype=f32, device=device)
         self.returns = torch.zeros((T, N), dtype=f32, device=device)
-        self.next_obs = torch.zeros_like(self.obs[0])
+        self.next_obs = ops.alloc_u8_rollout_rows((N, 441, 64), device) if self.u8_rollout else torch.zeros_like(self.obs[0])
         self.next_done = torch.zeros(N, dtype=f32, device=device)
         self.next_value = torch.zeros(N, dtype=f32, device=device)
         # pinned host mirrors
@@ -146,6 +146,7 @@ class PPOEngine:
             self.copy_stream = torch.cuda.Stream(device=device)
             self.chunk_events = [torch.cuda.Event() for _ in range(self.h2d_chunks)]
             self.noise_buf = torch.zeros(agent.noise_shape(N), dtype=f32, device=device)
+        self._parts = None
         self._graphs = {}
         self._graph_pool = None
         self._graph_kernels = {}
@@ -302,20 +303,125 @@ class PPOEngine:
             return work()          # the noise draw cannot be captured: plain launches
         self._run_graphed(work, ("rollout", obs_pool.data_ptr(), P), warm_key="r")
 
+    # ------------------------------------------------------------ pipelined rollout over env groups
+    # The reference steps all envs, then runs the policy on all envs (ppo_atari_envpool.py:224-247): host and device take
+    # turns, and PCIe idles while the last chunk is evaluated, the actions come back and the env steps.  With the envs in P
+    # independent groups (each its own vector env over a contiguous slice of the N envs) group B's frames cross PCIe while
+    # group A is evaluated, its actions return and its env steps; A's next frames queue behind B's.  Per env nothing changes:
+    # same policy, same per-step noise tensor (ONE draw per step for all N envs, the reference's RNG contract), same buffers.
+    def _part_setup(self, P):
+        if getattr(self, "_parts", None) is not None and len(self._parts) == P:
+            return
+        N = self.N
+        assert N % P == 0, "num_envs must be divisible by the number of env groups"
+        n = N // P
+        self._parts = [(p * n, (p + 1) * n) for p in range(P)]
+        C = 2 if (n % 2 == 0 and n // 2 >= 64 and self.s2d and self._graphable()) else 1
+        self._part_chunks = [[(lo + c * (n // C), lo + (c + 1) * (n // C)) for c in range(C)] for lo, hi in self._parts]
+        if getattr(self, "copy_stream", None) is None:
+            self.copy_stream = torch.cuda.Stream(device=self.device)
+        self._part_h2d = [[torch.cuda.Event() for _ in ch] for ch in self._part_chunks]
+        self._part_d2h = [torch.cuda.Event() for _ in range(P)]
+        if self.noise_buf is None:
+            self.noise_buf = torch.zeros(self.agent.noise_shape(N), dtype=torch.float32, device=self.device)
+        if not hasattr(self, "obs_u8"):
+            self.obs_u8 = None
+
+    def _part_work(self, step, lo, hi):
+        sl = slice(lo, hi)
+        if self.s2d:
+            self._to_storage(self.obs_u8[sl], step, sl)
+        self.agent.sample_into(self.obs[step][sl], self.actions[step][sl], self.logprobs[step][sl], self.values[step][sl],
+                               noise=self.noise_buf[sl])
+
+    @torch.no_grad()
+    def launch_part(self, step, part, obs_np, done_np):
+        """Enqueue everything group ``part`` needs at ``step``: H2D of its frames (copy stream, in chunks), storage
+        conversion + policy + sampler per chunk (main stream, graph replays), D2H of its actions.  Returns immediately."""
+        lo, hi = self._parts[part]
+        src = torch.from_numpy(np.ascontiguousarray(obs_np))
+        if src.dtype != self.obs_dtype:
+            src = src.to(self.obs_dtype)
+        if not src.is_pinned():
+            self.obs_stage_h[lo:hi].copy_(src)
+            src = self.obs_stage_h[lo:hi]
+        main = torch.cuda.current_stream()
+        dst = self.obs_u8 if self.s2d else self.obs[step]
+        with torch.cuda.stream(self.copy_stream):
+            for c, (clo, chi) in enumerate(self._part_chunks[part]):
+                dst[clo:chi].copy_(src[clo - lo:chi - lo], non_blocking=True)
+                self._part_h2d[part][c].record(self.copy_stream)
+        self.h2d_bytes += src.numel() * src.element_size()
+        self.dones_h[step][lo:hi].copy_(torch.as_tensor(np.asarray(done_np, dtype=np.float32)))
+        if part == 0:
+            self.agent.draw_noise_into(self.noise_buf)         # the step's ONE noise draw, all N envs
+        for c, (clo, chi) in enumerate(self._part_chunks[part]):
+            main.wait_event(self._part_h2d[part][c])
+            self._run_graphed(lambda: self._part_work(step, clo, chi), ("part", step, part, c), warm_key=("p", part, c))
+        self.actions_h[lo:hi].copy_(self.actions[step][lo:hi], non_blocking=True)
+        self._part_d2h[part].record(main)
+        self.d2h_bytes += (hi - lo) * self.actions_h.element_size() * max(1, self.act_dim)
+
+    def wait_actions(self, part):
+        """Host view of group ``part``'s actions of the step launched last (blocks on that group's D2H event only)."""
+        lo, hi = self._parts[part]
+        self._part_d2h[part].synchronize()
+        return self.actions_h[lo:hi].numpy()
+
+    def collect(self, env_parts, obs_parts, done_parts, on_step=None):
+        """One rollout of T steps over ``env_parts`` (gym-0.23 style ``step(a) -> obs, reward, done, info``), software
+        pipelined across the groups.  ``on_step(step, part, reward, done, info)`` sees every group step (logging).
+        Returns the groups' next observations / dones for ``finish_rollout_parts`` and the next iteration."""
+        P = len(env_parts)
+        self._part_setup(P)
+        obs_parts, done_parts = list(obs_parts), list(done_parts)
+        for p in range(P):
+            self.launch_part(0, p, obs_parts[p], done_parts[p])
+        for t in range(self.T):
+            for p in range(P):
+                lo, hi = self._parts[p]
+                action = self.wait_actions(p)
+                obs, reward, done, info = env_parts[p].step(action)
+                self.rewards_h[t][lo:hi].copy_(torch.as_tensor(np.asarray(reward, dtype=np.float32).reshape(-1)))
+                if on_step is not None:
+                    on_step(t, p, reward, done, info)
+                obs_parts[p], done_parts[p] = obs, done
+                if t + 1 < self.T:
+                    self.launch_part(t + 1, p, obs, done)
+        return obs_parts, done_parts
+
+    @torch.no_grad()
+    def finish_rollout_parts(self, obs_parts, done_parts):
+        """``finish_rollout`` for the grouped loop: bootstrap observation / done of every group."""
+        nd = np.concatenate([np.asarray(d, dtype=np.float32).reshape(-1) for d in done_parts])
+        if self.s2d:
+            for (lo, hi), o in zip(self._parts, obs_parts):
+                src = torch.from_numpy(np.ascontiguousarray(o))
+                if not src.is_pinned():
+                    self.obs_stage_h[lo:hi].copy_(src)
+                    src = self.obs_stage_h[lo:hi]
+                self.obs_u8[lo:hi].copy_(src, non_blocking=True)
+                self.h2d_bytes += src.numel()
+            self._to_storage(self.obs_u8, None)
+            self.finish_rollout(None, nd, resident=False, obs_uploaded=True)
+        else:
+            self.finish_rollout(np.concatenate([np.asarray(o) for o in obs_parts]), nd)
+
     def record_reward(self, step, reward_np):
         self.rewards_h[step].copy_(torch.as_tensor(np.asarray(reward_np, dtype=np.float32).reshape(-1)))
 
     @torch.no_grad()
-    def finish_rollout(self, next_obs_np, next_done_np, resident=False):
+    def finish_rollout(self, next_obs_np, next_done_np, resident=False, obs_uploaded=False):
         """Bootstrap value + GAE (reference: ppo.py:217-231).  ``resident``: rewards/dones/next_obs
-        were already written on the device."""
+        were already written on the device; ``obs_uploaded``: only the bootstrap frames were."""
         if not resident:
             self.rewards.copy_(self.rewards_h, non_blocking=True)
             self.dones.copy_(self.dones_h, non_blocking=True)
             self.next_done_h.copy_(torch.as_tensor(np.asarray(next_done_np, dtype=np.float32)))
             self.next_done.copy_(self.next_done_h, non_blocking=True)
             self.h2d_bytes += 2 * self.B * 4 + self.N * 4
-            self._upload_obs(None, next_obs_np)
+            if not obs_uploaded:
+                self._upload_obs(None, next_obs_np)
         _, value = self.agent._forward_heads(self.next_obs)
         self.next_value.copy_(value)
         ops.gae(self.rewards, self.values, self.dones, self.next_value, self.next_done,

@@ -119,7 +119,7 @@ def test_cli_fields_match_reference_args(script, factory):
         helps = [m.help for m in getattr(f.type, "__metadata__", ()) if hasattr(m, "help")]
         assert helps and helps[0] == doc, (name, helps, doc)
     extra = set(fields) - set(ref)
-    assert extra <= {"precision", "gae_kernel", "synthetic_env", "huber_loss"}, extra
+    assert extra <= {"precision", "gae_kernel", "synthetic_env", "huber_loss", "env_groups"}, extra
 
 
 @pytest.mark.reference

@@ -15,10 +15,13 @@ pytestmark = pytest.mark.gpu
 
 
 @pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs 2 GPUs")
+@pytest.mark.parametrize("script", ["ppo_atari_multigpu.py", "ppo_atari_multigpu_envpool.py"])
 @pytest.mark.parametrize("precision", ["bf16", "fp32"])
-def test_two_rank_nccl_replicas_identical(lib, precision):
+def test_two_rank_nccl_replicas_identical(lib, precision, script):
+    """bf16: the gradient exchange is split (fc + heads on a side stream under the conv backward, conv layers after it);
+    fp32: one all-reduce.  Either way replicas must stay bit-identical."""
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2", "--master-addr", "127.0.0.1",
-           "--master-port", "29533", str(ROOT / "cleanrl_b200" / "ppo_atari_multigpu.py"), "--backend", "nccl",
+           "--master-port", "29533", str(ROOT / "cleanrl_b200" / script), "--backend", "nccl",
            "--local-num-envs", "16", "--num-steps", "8", "--total-timesteps", "768", "--synthetic-env",
            "--precision", precision, "--seed", "3"]
     env = dict(os.environ, CLEANRL_B200_TB_OFF="1")

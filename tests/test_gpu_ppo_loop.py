@@ -278,3 +278,70 @@ def test_script_runs_under_runpy_like_the_tuner(lib, tmp_path, monkeypatch):
     assert {"charts/learning_rate", "losses/value_loss", "losses/policy_loss", "losses/entropy", "losses/approx_kl",
             "losses/clipfrac", "losses/explained_variance", "charts/SPS"} <= tags
     assert [e.step for e in ea.Scalars("charts/SPS")] == [512, 1024]
+
+
+class _PerEnvAtari:
+    """Deterministic Breakout-shaped vector env whose env i depends only on (i, its own step count, its own actions): any
+    grouping of the envs into separate vector envs yields the same per-env trajectories (envpool's per-env seeding)."""
+
+    def __init__(self, ids, frames):
+        self.ids = np.asarray(ids)
+        self.num_envs = len(self.ids)
+        self.frames = frames
+        self.t = 0
+        self.last = np.zeros(self.num_envs, dtype=np.int64)
+
+    def _obs(self):
+        return self.frames[(self.ids * 7 + self.t * 3 + self.last) % len(self.frames)]
+
+    def reset(self):
+        self.t = 0
+        self.last[:] = 0
+        return self._obs()
+
+    def step(self, action):
+        self.last = np.asarray(action).astype(np.int64)
+        self.t += 1
+        reward = (((self.ids + self.t) % 3) == 0).astype(np.float32) * (self.last != 0)
+        done = ((self.ids * 5 + self.t) % 17) == 0
+        return self._obs(), reward, done, {}
+
+
+def test_grouped_pipelined_rollout_equals_reference_order(lib):
+    """PPOEngine.collect over 2 env groups (software-pipelined H2D / policy / env.step) fills the rollout buffers with
+    exactly what the reference's step-all-then-policy-all loop produces: same per-step noise tensor, same rows."""
+    from bench import ppo_args
+    from cleanrl_b200.agents import NatureCNNAgent
+    from cleanrl_b200.ppo_engine import PPOEngine
+    from cleanrl_b200.synthetic_envs import SyntheticAtariVec
+    dev = torch.device("cuda")
+    N, T = 256, 5
+    g = np.random.default_rng(7)
+    frames = g.integers(0, 256, size=(32, 4, 84, 84), dtype=np.uint8)
+    outs = []
+    for groups in (1, 2):
+        torch.manual_seed(3)
+        spaces = SyntheticAtariVec(2, seed=1)
+        spaces.single_observation_space, spaces.single_action_space = spaces.observation_space, spaces.action_space
+        agent = NatureCNNAgent(spaces).to(dev); agent.precision = "bf16"
+        eng = PPOEngine(agent, ppo_args(N, T, 4, "bf16"), (4, 84, 84), np.uint8, N, dev, gae_mode=1)
+        torch.manual_seed(11)
+        if groups == 1:
+            env = _PerEnvAtari(np.arange(N), frames)
+            obs, done = env.reset(), np.zeros(N, dtype=np.float32)
+            for t in range(T):
+                a = eng.policy_step(t, obs, done)
+                obs, r, done, _ = env.step(a.copy())
+                eng.record_reward(t, r)
+            eng.finish_rollout(obs, done)
+        else:
+            parts = [_PerEnvAtari(np.arange(0, N // 2), frames), _PerEnvAtari(np.arange(N // 2, N), frames)]
+            obs_p = [e.reset() for e in parts]
+            done_p = [np.zeros(N // 2, dtype=np.float32) for _ in parts]
+            obs_p, done_p = eng.collect(parts, obs_p, done_p)
+            eng.finish_rollout_parts(obs_p, done_p)
+        torch.cuda.synchronize()
+        outs.append({k: getattr(eng, k).clone() for k in ("obs", "actions", "logprobs", "values", "rewards", "dones",
+                                                          "advantages", "returns")})
+    for k in outs[0]:
+        assert torch.equal(outs[0][k], outs[1][k]), k

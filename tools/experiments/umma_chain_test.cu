@@ -136,12 +136,59 @@ __global__ void k_mixed(const __half* A, const void* B, float* D, int b_bf16) {
     if (tid < 32) tmem_dealloc(td, 64);
 }
 
+// ---- part 3: B = MN-major SWIZZLE_128B rows of 64 fp16 (128 B); the MMA uses N = 32 starting at column `col0` (0 or 32):
+// D[128 x 32] = A[128 x 32 (K)] (fp16, TMEM) * B[K = 32 rows][col0 .. col0 + 32)
+__global__ void k_halfrow(const __half* A, const __half* B, float* D, int col0) {
+    extern __shared__ uint8_t raw[];
+    __shared__ uint64_t bar;
+    __shared__ uint32_t tbase;
+    uint8_t* smem = (uint8_t*)(((uintptr_t)raw + 1023) & ~uintptr_t(1023));
+    uint8_t* sB = smem;                   // 32 rows (K) x 128 B
+    const int tid = threadIdx.x, warp = tid >> 5;
+    if (tid == 0) { mbar_init(&bar, 1); fence_barrier_init(); }
+    if (tid < 32) tmem_alloc(&tbase, 64);
+    for (int i = tid; i < 32 * 8; i += blockDim.x) { int r = i >> 3, c = i & 7; *(int4*)(sB + img_off(r, c)) = *(const int4*)((const uint8_t*)B + r * 128 + c * 16); }
+    fence_proxy_async_smem();
+    tc_fence_before_sync();
+    __syncthreads();
+    tc_fence_after_sync();
+    const uint32_t td = tbase, ta = tbase + 32;
+    {
+        uint32_t v[32];
+        const uint32_t* src = reinterpret_cast<const uint32_t*>(A + tid * 32);
+#pragma unroll
+        for (int j = 0; j < 32; ++j) v[j] = j < 16 ? src[j] : 0u;
+        tmem_st32(ta + ((uint32_t)(warp * 32) << 16), v);
+        tmem_st_wait();
+    }
+    tc_fence_before_sync();
+    __syncthreads();
+    tc_fence_after_sync();
+    if (tid == 0) {
+        const uint32_t idesc = idesc_f16(128, 32, 0, 0, 1);
+        for (int kk = 0; kk < 2; ++kk)           // K step of 16 rows = 2 x 8-row groups of 1024 B
+            umma_f16_ts(td, ta + 8 * kk, desc_mnmajor(smem_u32(sB) + kk * 2048 + col0 * 2, 64 * 128), idesc, kk != 0);
+        umma_commit(&bar);
+    }
+    mbar_wait(&bar, 0);
+    tc_fence_after_sync();
+    uint32_t v[16];
+    for (int c0 = 0; c0 < 32; c0 += 16) {
+        tmem_ld16(td + ((uint32_t)(warp * 32) << 16) + c0, v);
+        tmem_ld_wait();
+        for (int e = 0; e < 16; ++e) D[tid * 32 + c0 + e] = __uint_as_float(v[e]);
+    }
+    tc_fence_before_sync();
+    __syncthreads();
+    if (tid < 32) tmem_dealloc(td, 64);
+}
+
 int main() {
     float* out; cudaMalloc(&out, 4);
     const size_t smem = 65536 + 32768 + 1024;
     cudaFuncSetAttribute(k_rate, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     const char* names[3] = {"SS f16 (K16)", "TS f16 (K16)", "SS i8  (K32)"};
-    for (int kind = 0; kind < 3; ++kind)
+    for (int kind = 0; kind < 3 && getenv("UMMA_RATES"); ++kind)
         for (int N = 32; N <= 256; N *= 2)
             for (int nacc = 1; nacc <= 4; nacc *= 2) {
                 if (N * nacc > 448) continue;
@@ -160,7 +207,7 @@ int main() {
     __half* Ad; void* Bd; float* Dd;
     cudaMalloc(&Ad, Ah.size() * 2); cudaMalloc(&Bd, 32 * 32 * 2); cudaMalloc(&Dd, 128 * 32 * 4);
     cudaMemcpy(Ad, Ah.data(), Ah.size() * 2, cudaMemcpyHostToDevice);
-    for (int bb = 0; bb < 2; ++bb) {
+    for (int bb = 0; bb < (getenv("UMMA_MIXED") ? 2 : 1); ++bb) {      // bb = 1 (bf16 B with fp16 A) raises 'illegal instruction' on B200
         cudaMemcpy(Bd, bb ? (void*)Bb.data() : (void*)Bh.data(), 32 * 32 * 2, cudaMemcpyHostToDevice);
         cudaMemset(Dd, 0, 128 * 32 * 4);
         k_mixed<<<1, 128, 8192>>>(Ad, Bd, Dd, bb);
@@ -175,6 +222,29 @@ int main() {
         }
         printf("TS A=fp16(TMEM) x B=%s (MN-major SW64, N=32): %s maxerr %.4f %s\n", bb ? "bf16" : "fp16", maxerr < 1e-2 ? "OK " : "BAD", maxerr,
                e == cudaSuccess ? "" : cudaGetErrorString(e));
+    }
+    // part 3
+    {
+        std::vector<float> Bw(32 * 64);
+        std::vector<__half> Bwh(32 * 64);
+        for (int k = 0; k < 32; ++k) for (int n = 0; n < 64; ++n) { float v = (float)(((k * 5 + n * 3) % 11) - 5) * 0.0625f; Bw[k * 64 + n] = v; Bwh[k * 64 + n] = __float2half(v); }
+        __half* Bd2; cudaMalloc(&Bd2, 32 * 64 * 2);
+        cudaMemcpy(Bd2, Bwh.data(), 32 * 64 * 2, cudaMemcpyHostToDevice);
+        for (int col0 = 0; col0 <= 32; col0 += 32) {
+            cudaMemset(Dd, 0, 128 * 32 * 4);
+            k_halfrow<<<1, 128, 8192>>>(Ad, Bd2, Dd, col0);
+            cudaError_t e = cudaDeviceSynchronize();
+            std::vector<float> D(128 * 32);
+            cudaMemcpy(D.data(), Dd, D.size() * 4, cudaMemcpyDeviceToHost);
+            double maxerr = 0;
+            for (int m = 0; m < 128; ++m) for (int n = 0; n < 32; ++n) {
+                double ref = 0;
+                for (int k = 0; k < 32; ++k) ref += (double)Af[m * 32 + k] * Bw[k * 64 + col0 + n];
+                maxerr = fmax(maxerr, fabs(ref - D[m * 32 + n]));
+            }
+            printf("TS A x B MN-major SW128 half row (N=32 at column %2d of 64): %s maxerr %.4f %s\n", col0, maxerr < 1e-2 ? "OK " : "BAD", maxerr,
+                   e == cudaSuccess ? "" : cudaGetErrorString(e));
+        }
     }
     return 0;
 }

@@ -1,5 +1,5 @@
 """One PPO minibatch update (M = 32768, the BASELINE.json configs[1] minibatch) + a few rollout steps,
-for ncu: `ncu ... python tools/profile_update.py [M] [reps] [u8|s2d]`.  Prints per-kernel CUDA-event times when run bare.
+for ncu: `ncu ... python tools/profile_update.py [M] [reps] [u8|s2d|u8s2d]`.  Prints per-kernel CUDA-event times when run bare.
 
 u8  (default): the drop-in path, uint8 NCHW frames gathered through random minibatch indices.
 s2d: the engine path, rollout stored as space-to-depth bf16, sorted minibatch indices (what bench.py runs)."""
@@ -37,11 +37,20 @@ flat = agent.flat
 obs = torch.randint(0, 256, (B, 4, 84, 84), dtype=torch.uint8, device=dev)
 inds = torch.randperm(B, device=dev)[:M].contiguous()
 obs_roll = obs[:1024].clone()
+aux = {}
 if fmt == "s2d":
     s2d = torch.empty((B, 21, 21, 64), dtype=torch.bfloat16, device=dev)
     for lo in range(0, B, 16384):
         ops.frames_to_s2d(obs[lo:lo + 16384], out=s2d[lo:lo + 16384])
     obs = s2d
+    inds = inds.sort().values.contiguous()
+elif fmt == "u8s2d":       # the engine's default rollout: uint8 space-to-depth rows in both orientations
+    rm = ops.alloc_u8_rollout_rows((B, 441, 64), dev)
+    cm = torch.empty((B, 64, 448), dtype=torch.uint8, device=dev)
+    for lo in range(0, B, 16384):
+        ops.frames_to_s2d_u8(obs[lo:lo + 16384], rm[lo:lo + 16384], cm[lo:lo + 16384])
+    obs = rm
+    aux = {"aux": cm}
     inds = inds.sort().values.contiguous()
 b_act = torch.randint(0, 4, (B,), device=dev)
 b_lp = torch.full((B,), -1.386, device=dev)
@@ -53,7 +62,7 @@ stats = torch.zeros(16, device=dev)
 
 
 def minibatch(step):
-    logits, value = agent.forward_train(obs, inds)
+    logits, value = agent.forward_train(obs, inds, **aux)
     ops.ppo_loss(logits, value, inds, b_act, b_lp, b_adv, b_ret, b_val, 0.1, 0.01, 0.5, dlogits=dl, dvalue=dv, stats=stats)
     agent.backward(dhead)
     ops.clip_adam(flat.flat, flat.grad, flat.exp_avg, flat.exp_avg_sq, step, 2.5e-4)
