@@ -299,6 +299,156 @@ class MLPAgent(KernelAgent):
         self.c_chain.bwd(dv)
 
 
+class LSTMAgent(KernelAgent):
+    """Recurrent actor-critic (reference: cleanrl/ppo_atari_lstm.py:117-160): NatureCNN trunk over ONE grayscale frame,
+    ``nn.LSTM(512, 128)`` with the state reset by ``(1 - done)`` before every step, ``actor`` / ``critic`` on the LSTM
+    output.  Same module names / ``state_dict`` keys (``network.*``, ``lstm.weight_ih_l0`` ..., ``actor.*``, ``critic.*``),
+    same initialisation order (orthogonal_ on the two LSTM weight matrices with gain 1, biases zero).
+
+    Execution: fp32 kernels of libb200rl, no autograd.  The trunk and the input-gate GEMM ``x W_ih^T + b_ih`` run once over
+    ALL steps of a sequence; per step there is one small GEMM ``h' W_hh^T + b_hh`` and one fused cell kernel.  The backward
+    pass is explicit back-propagation through time (one cell-backward kernel + one ``dgates W_hh`` GEMM per step), after
+    which the weight gradients of both LSTM matrices and of the trunk are single GEMMs over the whole sequence."""
+
+    def __init__(self, envs):
+        super().__init__()
+        c, h, w = envs.single_observation_space.shape
+        assert (h, w) == (84, 84), "NatureCNN trunk geometry is 84x84"
+        trunk = []
+        for cin, cout, k, s in ((c, 32, 8, 4), (32, 64, 4, 2), (64, 64, 3, 1)):
+            trunk += [layer_init(nn.Conv2d(cin, cout, k, stride=s)), nn.ReLU()]
+        trunk += [nn.Flatten(), layer_init(nn.Linear(64 * 7 * 7, 512)), nn.ReLU()]
+        self.network = nn.Sequential(*trunk)
+        self.lstm = nn.LSTM(512, 128)
+        for name, param in self.lstm.named_parameters():
+            if "bias" in name:
+                nn.init.constant_(param, 0)
+            elif "weight" in name:
+                nn.init.orthogonal_(param, 1.0)
+        self.actor = layer_init(nn.Linear(128, envs.single_action_space.n), std=0.01)
+        self.critic = layer_init(nn.Linear(128, 1), std=1)
+        self.num_actions = int(envs.single_action_space.n)
+        self.hidden_size = 128
+
+    def _param_order(self):
+        net = [p for m in self.network for p in m.parameters()]
+        return net + list(self.lstm.parameters()) + [self.actor.weight, self.critic.weight, self.actor.bias, self.critic.bias]
+
+    def _build_plan(self):
+        f = self._flat
+        A, H = self.num_actions, self.hidden_size
+        wa, _ = f.view_of(self.actor.weight)
+        ba, _ = f.view_of(self.actor.bias)
+        off_w = (wa.data_ptr() - f.flat.data_ptr()) // 4
+        off_b = (ba.data_ptr() - f.flat.data_ptr()) // 4
+        head_w = f.flat[off_w:off_w + (A + 1) * H].view(A + 1, H)
+        head_b = f.flat[off_b:off_b + A + 1]
+        head_dw = f.grad[off_w:off_w + (A + 1) * H].view(A + 1, H)
+        head_db = f.grad[off_b:off_b + A + 1]
+        n = self.network
+        self.trunk = nets.Chain([nets.Conv(n[0], "relu", in_div=255.0), nets.Conv(n[2], "relu"), nets.Conv(n[4], "relu"),
+                                 nets.Linear(n[7], "relu")])
+        self.head = nets.Linear(None, None, head_w, head_b, head_dw, head_db)
+        L = self.lstm
+        self.l_ih = nets.Linear(None, None, L.weight_ih_l0.data, L.bias_ih_l0.data, L.weight_ih_l0.grad, L.bias_ih_l0.grad)
+        self.l_hh = nets.Linear(None, None, L.weight_hh_l0.data, L.bias_hh_l0.data, L.weight_hh_l0.grad, L.bias_hh_l0.grad)
+
+    graph_capturable = False
+
+    # ------------------------------------------------------------------ forward
+    def get_states(self, x, lstm_state, done, rows=None, keep=False):
+        """hidden [S*n, H], (h_S, c_S): ``x`` = S*n frames (or ``rows`` gathering them from a larger buffer), time-major."""
+        self.flat
+        H = self.hidden_size
+        h, c = lstm_state[0].reshape(-1, H).contiguous(), lstm_state[1].reshape(-1, H).contiguous()
+        n = h.shape[0]
+        if x.dtype not in (torch.uint8, torch.float32):
+            x = x.float()
+        feats = self.trunk.fwd(x.contiguous(), rows=rows, keep=keep)            # [S*n, 512], post-ReLU
+        total = feats.shape[0]
+        assert total % n == 0, "the sequence batch must be steps x envs"
+        S = total // n
+        dev = feats.device
+        done = done.reshape(S, n).to(torch.float32).contiguous()
+        gx = self.l_ih.fwd(feats)                                               # [S*n, 4H] for every step at once
+        hidden = torch.empty(S, n, H, dtype=torch.float32, device=dev)
+        hm = torch.empty(S, n, H, dtype=torch.float32, device=dev)
+        cm = torch.empty(S, n, H, dtype=torch.float32, device=dev)
+        save = torch.empty(S, n, 5 * H, dtype=torch.float32, device=dev) if keep else None
+        c_cur = torch.empty(n, H, dtype=torch.float32, device=dev)
+        for t in range(S):
+            ops.lstm_mask_state(h, c, done[t], out=(hm[t], cm[t]))
+            gh = self.l_hh.fwd(hm[t])
+            ops.lstm_cell_fwd(gx[t * n:(t + 1) * n], gh, cm[t], hidden[t], c_cur, save[t] if keep else None)
+            h, c = hidden[t], c_cur
+            if t + 1 < S:
+                c_cur = torch.empty(n, H, dtype=torch.float32, device=dev)
+        if keep:
+            self._seq = dict(feats=feats, hidden=hidden, hm=hm, cm=cm, save=save, done=done, S=S, n=n)
+        return hidden.view(S * n, H), (h.reshape(1, n, H).clone(), c.reshape(1, n, H).clone())
+
+    def _heads(self, hidden):
+        out = self.head.fwd(hidden)
+        A = self.num_actions
+        return out[:, :A], out[:, A]
+
+    def get_value(self, x, lstm_state, done):
+        hidden, _ = self.get_states(x, lstm_state, done)
+        _, value = self._heads(hidden)
+        return value.reshape(-1, 1).clone()
+
+    def get_action_and_value(self, x, lstm_state, done, action=None, rows=None, keep=False):
+        hidden, lstm_state = self.get_states(x, lstm_state, done, rows=rows, keep=keep)
+        logits, value = self._heads(hidden)
+        if keep:
+            self._seq["logits"], self._seq["value"] = logits, value
+        m, A = logits.shape
+        if action is None:
+            q = self.noise_fn(m, A, logits.device)
+            action, logprob, entropy, v = ops.categorical_sample(logits, q, value)
+        else:
+            logprob, entropy = ops.categorical_eval(logits, action)
+            v = value.clone()
+        return action, logprob, entropy, v.reshape(-1, 1), lstm_state
+
+    def forward_train(self, b_obs, mb_inds, lstm_state, b_dones):
+        """Minibatch forward over whole env sequences (mb_inds time-major: step t of every env of the minibatch, then
+        step t+1, ... as cleanrl/ppo_atari_lstm.py:303), activations kept for ``backward``."""
+        done = b_dones.reshape(-1)[mb_inds]
+        hidden, _ = self.get_states(b_obs, lstm_state, done, rows=mb_inds, keep=True)
+        return self._heads(hidden)
+
+    def alloc_head_grad(self, M, device):
+        A = self.num_actions
+        d = torch.empty(M, A + 1, dtype=torch.float32, device=device)
+        return d, d[:, :A], d[:, A]
+
+    # ----------------------------------------------------------------- backward
+    def backward(self, dhead):
+        q = self._seq
+        S, n, H = q["S"], q["n"], self.hidden_size
+        hidden = q["hidden"].view(S * n, H)
+        self.head.bwd_weight(hidden, dhead)
+        dh_heads = self.head.bwd_data(dhead, None, None).view(S, n, H)
+        dev = dhead.device
+        dgates = torch.empty(S, n, 4 * H, dtype=torch.float32, device=dev)
+        dc_a = torch.empty(n, H, dtype=torch.float32, device=dev)
+        dc_b = torch.empty(n, H, dtype=torch.float32, device=dev)
+        dh_rec, dc_rec = None, None
+        for t in reversed(range(S)):
+            ops.lstm_cell_bwd(dh_heads[t], dh_rec, q["done"][t + 1] if t + 1 < S else None, dc_rec, q["save"][t], q["cm"][t],
+                              q["done"][t], dgates[t], dc_a)
+            dc_rec, dc_a, dc_b = dc_a, dc_b, dc_a
+            if t > 0:
+                dh_rec = self.l_hh.bwd_data(dgates[t], None, None)             # dgates_t W_hh -> d h'_{t-1} (masked at t-1's kernel)
+        dg = dgates.view(S * n, 4 * H)
+        self.l_hh.bwd_weight(q["hm"].view(S * n, H), dg)
+        self.l_ih.bwd_weight(q["feats"], dg)
+        dfeats = self.l_ih.bwd_data(dg, q["feats"], "relu")
+        self.trunk.bwd(dfeats)
+        self._seq = None
+
+
 def _normal_noise(n, D, device):
     # what Normal(mean, std).sample() == torch.normal(mean, std) consumes: one N(0,1) per element
     return torch.randn(n, D, dtype=torch.float32, device=device)

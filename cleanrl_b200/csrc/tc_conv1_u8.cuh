@@ -23,6 +23,7 @@
 #pragma once
 #include "tc_base.cuh"
 #include <cuda_fp16.h>
+#include <cstdlib>
 #include "tc_conv_win.cuh"
 
 namespace b200rl {
@@ -160,6 +161,8 @@ struct Conv1U8Params {
     const float* bias;       // [32]
     bf16* out;               // act1 as 2x2 cells [n,100,128]
     uint32_t* mask_out;      // act1 > 0 bits: [n,100 cells] x 4 words
+    int dbg;                 // stage knock-out for bottleneck analysis (B200RL_DBG_CONV1): 1 = no global stores, 2 = no TMA
+                             // loads, 4 = no MMAs; results are then garbage by construction
 };
 
 // Pair rows: TMA delivers one shared-memory row (<= 128 B) per request at ~5.5 cycles per request and SM -- the rate at
@@ -184,7 +187,7 @@ __global__ void __launch_bounds__(kConvWinThreads, 1) tc_conv1_i8(const __grid_c
     const int tid = threadIdx.x, warp = tid >> 5;
     uint8_t* sW = smem;                             // 4 taps x 4096 B
     uint8_t* sRing = smem + NTAPS * B_CHUNK;        // 16384: 1024-aligned
-    uint8_t* sStage = sRing + (size_t)STAGES * STAGE_BYTES;     // 8 epilogue warps x (32 rows x 64 B + 32 row offsets)
+    uint8_t* sStage = sRing + (size_t)STAGES * STAGE_BYTES;     // 16 epilogue warps x (32 rows x 64 B + 32 row offsets)
 
     if (tid == 0) {
         for (int s = 0; s < STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
@@ -227,6 +230,7 @@ __global__ void __launch_bounds__(kConvWinThreads, 1) tc_conv1_i8(const __grid_c
                     z_next = p.rows ? (int)__ldg(p.rows + img) : img;
                 }
                 if (q >= (uint32_t)STAGES) mbar_wait(&empty_bar[s], ((q / STAGES) - 1) & 1);
+                if (p.dbg & 2) { mbar_arrive(&full_bar[s]); continue; }
                 mbar_arrive_expect_tx(&full_bar[s], (uint32_t)STAGE_BYTES);
                 tma_load_3d(smem_u32(sRing + (size_t)s * STAGE_BYTES), &tmA, 0, (tile & 1) * 128, z, &full_bar[s]);
             }
@@ -257,6 +261,7 @@ __global__ void __launch_bounds__(kConvWinThreads, 1) tc_conv1_i8(const __grid_c
                     const uint32_t d_addr = tmem_d + acc * BN;
 #pragma unroll
                     for (int t = 0; t < NTAPS; ++t) {
+                        if (p.dbg & 4) break;
                         const int po = e + off[t];
                         const uint32_t a_lo = win_lo + (uint32_t)((po >> 1) * 8 + (po & 1) * 4);      // rows of 128 B, halves of 64 B
                         const uint32_t b_lo = w_lo + (uint32_t)((t * B_CHUNK) >> 4);
@@ -271,15 +276,17 @@ __global__ void __launch_bounds__(kConvWinThreads, 1) tc_conv1_i8(const __grid_c
                 __syncwarp();
             }
         }
-    } else if (warp < 10) {
-        // ======================= epilogue: warps 2-9 = two groups of four (one warp per TMEM lane quadrant); group e drains
-        // the accumulator of parity e of EVERY tile: lane = pair row q, output position p = 2q + e.
+    } else {
+        // ======================= epilogue: warps 2-17 = four groups of four (one warp per TMEM lane quadrant); group
+        // (e, tp) drains the accumulator of parity e of the tiles of parity tp: lane = pair row q, output position p = 2q + e.
+        // (Four groups: see tc_conv_win.cuh -- the epilogue's dependent instruction chain is the tile period otherwise.)
         const int ew = warp & 3;
-        const int e = (warp - 2) >> 2;
+        const int grp = (warp - 2) >> 2;
+        const int e = grp & 1, tp = grp >> 1;
         const int lrow = ew * 32 + (tid & 31);
         const uint32_t lane_base = tmem_d + ((uint32_t)(ew * 32) << 16);
-        uint32_t k = 0;
-        for (int tile = tile_begin; tile < tile_end; ++tile, ++k) {
+        for (int tile = tile_begin + tp; tile < tile_end; tile += 2) {
+            const uint32_t k = (uint32_t)(tile - tile_begin);
             const uint32_t acc = 2 * (k % NT) + e;
             const uint32_t lane_addr = lane_base + acc * BN;
             const int i = tile >> 1;
@@ -315,7 +322,7 @@ __global__ void __launch_bounds__(kConvWinThreads, 1) tc_conv1_i8(const __grid_c
                 pk[c4 >> 1] = pack_bf16x2(fmaxf(f0, 0.f), fmaxf(f1, 0.f));
                 pk[(c4 >> 1) + 1] = pack_bf16x2(fmaxf(f2, 0.f), fmaxf(f3, 0.f));
             }
-            if (valid) p.mask_out[cell * 4 + cls] = bits;
+            if (valid && !(p.dbg & 1)) p.mask_out[cell * 4 + cls] = bits;
             // Stores: a lane owns one output row (64 B at its own 2x2-cell address), so a direct 16-byte store instruction of
             // the warp touches 32 different lines = 32 L1 wavefronts -- measured, the epilogue's global stores took more of
             // the L1 data pipe than the MMAs' operand reads.  The rows go through a per-warp staging tile instead (XOR
@@ -336,7 +343,7 @@ __global__ void __launch_bounds__(kConvWinThreads, 1) tc_conv1_i8(const __grid_c
                 const int R = (lane >> 2) + 8 * i2, c = lane & 3;
                 const int unit = reinterpret_cast<const int*>(stg + 2048)[R];
                 const int4 v = *reinterpret_cast<const int4*>(stg + R * 64 + ((((uint32_t)c) ^ ((uint32_t)(R >> 1) & 3u)) << 4));
-                if (unit >= 0) *reinterpret_cast<int4*>(reinterpret_cast<uint8_t*>(p.out) + (int64_t)unit * 64 + c * 16) = v;
+                if (unit >= 0 && !(p.dbg & 1)) *reinterpret_cast<int4*>(reinterpret_cast<uint8_t*>(p.out) + (int64_t)unit * 64 + c * 16) = v;
             }
             __syncwarp();
         }
@@ -615,10 +622,13 @@ static int launch_conv1_wgrad_u8(const Conv1WgradU8Params& p, const void* frames
 constexpr int kConv1I8Stages = 8;
 static int launch_conv1_i8(const Conv1U8Params& p, const void* frames_rm, cudaStream_t s, const char* what) {
     constexpr int STAGES = kConv1I8Stages;
-    const size_t smem = (size_t)4 * 64 * 64 + (size_t)STAGES * 144 * 128 + 8 * 2304 + 1024;
+    const size_t smem = (size_t)4 * 64 * 64 + (size_t)STAGES * 144 * 128 + 16 * 2304 + 1024;
     static SmemAttrCache attr;
     if (int rc = attr.ensure(tc_conv1_i8<STAGES>, smem, what)) return rc;
     const int total = p.n * 2;                     // 2 tiles of 128 pair rows (256 grid positions) per image (441 used)
+    static const int dbg = getenv("B200RL_DBG_CONV1") ? atoi(getenv("B200RL_DBG_CONV1")) : 0;
+    Conv1U8Params q = p;
+    q.dbg = dbg;
     int grid = num_sms();
     if (grid > total) grid = total;
     CUtensorMap tmA;
@@ -627,7 +637,7 @@ static int launch_conv1_i8(const Conv1U8Params& p, const void* frames_rm, cudaSt
     // half of row 220 belongs to the next image and only ever feeds invalid positions); SWIZZLE_128B boxes of 144 rows
     int rc = make_tmap_pairs_u8(&tmA, frames_rm, p.n_images, what);
     if (rc) return rc;
-    tc_conv1_i8<STAGES><<<grid, kConvWinThreads, smem, s>>>(tmA, p, total);
+    tc_conv1_i8<STAGES><<<grid, kConvWinThreads, smem, s>>>(tmA, q, total);
     return check_launch(what);
 }
 

@@ -50,23 +50,21 @@ __device__ __forceinline__ uint32_t pack_f16x2_sat(float lo, float hi) {
     return d;
 }
 
-// Thread roles (352 threads): warp 0 = TMA producer; warp 1 (and warp 10 when kConvWinIssuers == 2) = MMA issuer;
-// warps 2-9 = epilogue.  A second issuer warp (issuer h owns accumulator buffer h = every other tile) was measured on the
-// bf16 kernels: no gain -- they sit at ~77 % of the shared-memory operand bandwidth (ncu sm__throughput), i.e. the 65-79
-// cycles per M128 x N<=64 x K16 MMA are the 5-6 KB of SS-mode operand reads, not the issuing thread -- and 5-13 % slower
-// on conv2 forward / conv3 data gradient (two more resident warps competing with the epilogue).  Kept as a switch.
-constexpr int kConvWinThreads = 352;
-constexpr int kConvWinIssuers = 1;
-// Accumulator buffers in TMEM.  With two, issuer and epilogue hand each buffer back and forth once per tile and a tile of
-// 8-36 small MMAs is shorter than that round trip (tcgen05.commit -> mbarrier -> epilogue wake-up -> tcgen05.ld ->
-// arrive -> issuer wake-up, ~1 us in total): ncu showed the issuer stalled on the `tempty` barrier and the epilogue on
-// `tfull` at the same time.  Four buffers (two per epilogue group) let the issuer run two tiles ahead of each group.
+// Thread roles (576 threads): warp 0 = TMA producer; warp 1 = MMA issuer; warps 2-17 = FOUR epilogue groups of four warps
+// (one warp per TMEM lane quadrant).  Group h owns accumulator buffer h and drains tiles h, h + 4, ...
+// Why four groups: an epilogue warp runs a ~250-500 instruction dependent chain per tile (tcgen05.ld, scale/bias, ReLU
+// mask, bf16 packing, stores); with two groups every scheduler held two such warps and ncu showed 0.2-0.4 instructions per
+// cycle and scheduler with the tensor pipe at 25-45 % -- the epilogue's LATENCY was the tile period.  Four warps per scheduler
+// hide it.  Measured and dropped: a second MMA-issuer warp (no gain: the issuing thread is not the limit).
+constexpr int kConvWinThreads = 576;
+constexpr int kConvWinGroups = 4;
 __host__ __device__ constexpr int conv_win_acc_bufs(int BN) { return BN <= 128 ? 4 : 2; }
 template <int BN, int CPR, int STAGES, int NTAPS>
 __global__ void __launch_bounds__(kConvWinThreads, 1) tc_conv_win(const __grid_constant__ CUtensorMap tmA, const WinParams p,
                                                       int total_tiles) {
     constexpr int B_CHUNK = BN * 128;
     constexpr int NB = conv_win_acc_bufs(BN);
+    static_assert(NB == kConvWinGroups, "one accumulator buffer per epilogue group");
     constexpr uint32_t TMEM_COLS = (NB * BN) < 32 ? 32 : NB * BN;
     extern __shared__ uint8_t smem_raw[];
     __shared__ uint64_t full_bar[STAGES], empty_bar[STAGES], tfull_bar[NB], tempty_bar[NB];
@@ -136,19 +134,16 @@ __global__ void __launch_bounds__(kConvWinThreads, 1) tc_conv_win(const __grid_c
                 }
             }
         }
-    } else if (warp == 1 || warp == 10) {
-        // ======================= MMA issuers: the WHOLE warp walks its tile loop (uniform control flow keeps the
+    } else if (warp == 1) {
+        // ======================= MMA issuer: the WHOLE warp walks the tile loop (uniform control flow keeps the
         // descriptor arithmetic in uniform registers), one elected lane issues.  Descriptors differ from a per-stage /
-        // per-tap base only in their 14-bit start-address field, so each MMA costs two 32-bit adds.  Issuer ih takes
-        // the tiles of parity ih (accumulator buffer ih, epilogue group ih).
-        const uint32_t ih = warp == 1 ? 0u : 1u;
-        if (ih < (uint32_t)kConvWinIssuers) {
+        // per-tap base only in their 14-bit start-address field, so each MMA costs two 32-bit adds.
         const bool leader = elect_one();
         constexpr uint32_t idesc = make_idesc(128, BN, 0, 0);
         const uint64_t desc_hi = desc_kmajor(0) & 0xFFFFFFFF00000000ull;
         const uint32_t desc_lo_flags = (uint32_t)(desc_kmajor(0) & 0xFFFFFFFFull);       // LBO field
         const uint32_t w_lo = ((smem_u32(sW) & 0x3FFFFu) >> 4) | desc_lo_flags;
-        for (uint32_t q = ih; (int)q < tile_end - tile_begin; q += kConvWinIssuers) {
+        for (uint32_t q = 0; (int)q < tile_end - tile_begin; ++q) {
             const uint32_t acc = q % NB, s = q % STAGES;
             if (q >= (uint32_t)NB) mbar_wait(&tempty_bar[acc], ((q / NB) - 1) & 1);
             mbar_wait(&full_bar[s], (q / STAGES) & 1);
@@ -173,17 +168,17 @@ __global__ void __launch_bounds__(kConvWinThreads, 1) tc_conv_win(const __grid_c
             }
             __syncwarp();
         }
-        }
     } else {
-        // ======================= epilogue: warps 2-9 = two groups of four (one warp per TMEM lane quadrant).
+        // ======================= epilogue: warps 2-17 = two groups of four (one warp per TMEM lane quadrant).
         // Group h owns accumulator buffer h, i.e. every other tile of the CTA's range, and handles ALL BN columns
         // of its rows: the row -> (image, Y, X) -> output offset arithmetic is paid once per tile and thread, and
         // is incremental (a tile step is 256 grid rows; Y = rem / Wp by multiply-shift, exact for G*Wp < 65536).
         const int ew = warp & 3;
-        const int h = (warp - 2) >> 2;
+        const int h = (warp - 2) >> 2;                       // epilogue group 0..3
         const int lrow = ew * 32 + (tid & 31);
         const uint32_t mW = (65536u + (uint32_t)p.Wp - 1u) / (uint32_t)p.Wp;
-        const int step_i = 256 / p.G, step_rem = 256 % p.G;
+        constexpr int TSTEP = kConvWinGroups * 128;          // grid rows between two tiles of one group
+        const int step_i = TSTEP / p.G, step_rem = TSTEP % p.G;
         int64_t r = ((int64_t)tile_begin + h) * 128 + lrow;      // linear-grid mode state (unused when image-aligned)
         int i_lin = (int)(r / p.G);
         int rem_lin = (int)(r - (int64_t)i_lin * p.G);
@@ -191,8 +186,8 @@ __global__ void __launch_bounds__(kConvWinThreads, 1) tc_conv_win(const __grid_c
         const uint32_t lane_base = tmem_d + ((uint32_t)(ew * 32) << 16);
         constexpr int NW = BN / 32;                          // 32-column groups = mask words per row
         uint32_t k = 0;                                      // tiles this group has drained
-        for (int tile = tile_begin + h; tile < tile_end; tile += 2, ++k) {
-            const uint32_t acc = (uint32_t)(tile - tile_begin) % NB;           // group h drains buffers h, h + 2, ...
+        for (int tile = tile_begin + h; tile < tile_end; tile += kConvWinGroups, ++k) {
+            const uint32_t acc = (uint32_t)(tile - tile_begin) % NB;           // NB = 4: buffer h; NB = 2: h & 1
             const uint32_t lane_addr = lane_base + acc * BN;
             int i = i_lin, rem = rem_lin;
             bool inside = r < p.M;
@@ -306,7 +301,7 @@ __global__ void __launch_bounds__(kConvWinThreads, 1) tc_conv_win(const __grid_c
                     dst2[0] = w[0]; dst2[1] = w[1]; dst2[2] = w[2]; dst2[3] = w[3];
                 }
             }
-            r += 256; i_lin += step_i; rem_lin += step_rem;
+            r += TSTEP; i_lin += step_i; rem_lin += step_rem;
             if (rem_lin >= p.G) { rem_lin -= p.G; ++i_lin; }
         }
     }

@@ -294,6 +294,47 @@ def linear_bwd_weight(x, dy, dw, db, rows=None):
     _lib.check(rc, "linear_bwd_weight")
 
 
+# ------------------------------------------------------------------------ LSTM cell
+def lstm_mask_state(h, c, done, out=None):
+    """(h', c') = (1 - done) * (h, c): the state reset of cleanrl/ppo_atari_lstm.py:137-142, [n, H] fp32."""
+    lib = _lib.load()
+    n, H = h.shape
+    f = torch.float32
+    hm, cm = out if out is not None else (torch.empty_like(h), torch.empty_like(c))
+    rc = lib.b200rl_lstm_mask_state_f32(_ptr(_contig(h, "h"), f, "h"), _ptr(_contig(c, "c"), f, "c"),
+                                        _ptr(_contig(done, "done"), f, "done"), n, H, _ptr(hm, f, "hm"), _ptr(cm, f, "cm"), _stream())
+    _lib.check(rc, "lstm_mask_state")
+    return hm, cm
+
+
+def lstm_cell_fwd(gates_x, gates_h, c_masked, h_out, c_out, save=None):
+    """One LSTM step from the two gate GEMMs (gate order i, f, g, o); ``save`` [n, 5H] keeps what the backward needs."""
+    lib = _lib.load()
+    n, H = c_masked.shape
+    f = torch.float32
+    for nm, t in (("gates_x", gates_x), ("gates_h", gates_h), ("c_masked", c_masked), ("h_out", h_out), ("c_out", c_out)):
+        _contig(t, nm)
+    assert gates_x.shape == (n, 4 * H) and gates_h.shape == (n, 4 * H)
+    rc = lib.b200rl_lstm_cell_fwd_f32(_ptr(gates_x, f, "gates_x"), _ptr(gates_h, f, "gates_h"), _ptr(c_masked, f, "c_masked"), n, H,
+                                      _ptr(h_out, f, "h_out"), _ptr(c_out, f, "c_out"), _ptr(save, f, "save", True), _stream())
+    _lib.check(rc, "lstm_cell_fwd")
+
+
+def lstm_cell_bwd(dh_heads, dh_rec_raw, done_next, dc_rec, save, c_masked, done, dgates, dc_rec_out):
+    """One step of back-propagation through time (see include/b200rl.h)."""
+    lib = _lib.load()
+    n, H = c_masked.shape
+    f = torch.float32
+    for nm, t in (("dh_heads", dh_heads), ("save", save), ("c_masked", c_masked), ("done", done), ("dgates", dgates),
+                  ("dc_rec_out", dc_rec_out)):
+        _contig(t, nm)
+    rc = lib.b200rl_lstm_cell_bwd_f32(_ptr(dh_heads, f, "dh_heads"), _ptr(dh_rec_raw, f, "dh_rec_raw", True),
+                                      _ptr(done_next, f, "done_next", True), _ptr(dc_rec, f, "dc_rec", True), _ptr(save, f, "save"),
+                                      _ptr(c_masked, f, "c_masked"), _ptr(done, f, "done"), n, H, _ptr(dgates, f, "dgates"),
+                                      _ptr(dc_rec_out, f, "dc_rec_out"), _stream())
+    _lib.check(rc, "lstm_cell_bwd")
+
+
 # ------------------------------------------------------ NatureCNN bf16 (tcgen05) plan
 class NatureCNNBf16:
     """Owns the packed bf16 weights and activation workspaces of the tensor-core NatureCNN path."""

@@ -157,8 +157,8 @@ class SyntheticGymnasiumVec:
             od = obs_dim or 17
             self.single_observation_space = Box(-np.inf, np.inf, (od,), np.float32)
             self.single_action_space = Box(-1.0, 1.0, (act_dim or 6,), np.float32)
-        elif kind == "atari":
-            self.single_observation_space = Box(0, 255, (4, 84, 84), np.uint8)
+        elif kind in ("atari", "atari1"):     # atari1: FrameStack(1) as cleanrl/ppo_atari_lstm.py:105
+            self.single_observation_space = Box(0, 255, (4 if kind == "atari" else 1, 84, 84), np.uint8)
             self.single_action_space = Discrete(act_dim or 4)
         else:
             raise ValueError(kind)
@@ -174,7 +174,7 @@ class SyntheticGymnasiumVec:
     def _draw_obs(self, act_term):
         n = self.num_envs
         shp = self.single_observation_space.shape
-        if self.kind == "atari":
+        if self.kind.startswith("atari"):
             return self._rng.integers(0, 256, size=(n,) + shp, dtype=np.uint8)
         self._state = 0.9 * self._state + 0.3 * self._rng.standard_normal((n,) + shp) + 0.05 * act_term
         return np.clip(self._state, -10, 10).astype(np.float32)
@@ -217,7 +217,7 @@ class SyntheticGymnasiumVec:
             infos["final_observation"] = fobs
             self._ep_ret[done] = 0
             self._ep_len[done] = 0
-            if self.kind != "atari":
+            if not self.kind.startswith("atari"):
                 self._state[done] = 0
         return obs, reward, terminated, truncated, infos
 

@@ -264,6 +264,23 @@ int b200rl_naturecnn_bf16_backward(const void* obs, const void* obs_aux, int obs
  * tail on another stream while the convolution gradients are still being computed. */
 int64_t b200rl_naturecnn_grad_tail_offset(int A);
 
+/* ------------------------------------------------------------ LSTM cell ---
+ * Recurrent PPO agent (cleanrl/ppo_atari_lstm.py:117-160: nn.LSTM(512, 128), gate order i, f, g, o; the state is reset
+ * by (1 - done) BEFORE the cell, :137-142).  The gate GEMMs are b200rl_linear_fwd_f32 calls (x W_ih^T + b_ih for all
+ * steps at once, h' W_hh^T + b_hh per step); these are the elementwise parts, fp32, [n, H] row-major.
+ *   mask_state : (h', c') = (1 - done[n]) * (h, c)
+ *   cell_fwd   : gates_x, gates_h [n, 4H] -> h_out, c_out [n, H]; save [n, 5H] = (i, f, g, o, tanh c), may be NULL
+ *   cell_bwd   : one BPTT step.  dh = dh_heads + (1 - done_next) * dh_rec_raw (dh_rec_raw = dgates_{t+1} W_hh, NULL at the
+ *                last step), dc = dc_rec (NULL at the last step) + dh o (1 - tanh(c)^2); writes the pre-activation gate
+ *                gradients dgates [n, 4H] and dc_rec_out = (1 - done) dc f for step t-1. */
+int b200rl_lstm_mask_state_f32(const float* h, const float* c, const float* done, int64_t n, int H,
+                               float* h_masked, float* c_masked, void* stream);
+int b200rl_lstm_cell_fwd_f32(const float* gates_x, const float* gates_h, const float* c_masked, int64_t n, int H,
+                             float* h_out, float* c_out, float* save, void* stream);
+int b200rl_lstm_cell_bwd_f32(const float* dh_heads, const float* dh_rec_raw, const float* done_next, const float* dc_rec,
+                             const float* save, const float* c_masked, const float* done, int64_t n, int H,
+                             float* dgates, float* dc_rec_out, void* stream);
+
 /* --------------------------------------------------------- DQN TD update ---
  * td_target = r + gamma * max_a' Q_target(s')[a'] * (1 - done); old = Q(s)[a]; loss = mean((td - old)^2)
  * (F.mse_loss, cleanrl/dqn_atari.py:220-224; huber = 1: smooth-L1) and dL/dQ [B, A] in one pass.

@@ -23,10 +23,10 @@ def _stack(recs, key):
     return np.stack([r[key] for r in recs])
 
 
-def atari_envpool(name, argv, n_iter, script="ppo_atari_envpool.py"):
-    """cleanrl/ppo_atari_envpool.py (envpool/gym-0.23 API) or cleanrl/ppo_atari.py (gymnasium API) on the
-    Breakout-shaped synthetic env."""
-    rec, g = run_reference(script, argv, atari_mode="fresh", gymnasium_kind="atari")
+def atari_envpool(name, argv, n_iter, script="ppo_atari_envpool.py", gymnasium_kind="atari"):
+    """cleanrl/ppo_atari_envpool.py (envpool/gym-0.23 API), cleanrl/ppo_atari.py (gymnasium API) or
+    cleanrl/ppo_atari_lstm.py (gymnasium API, one grayscale frame: kind "atari1") on the Breakout-shaped synthetic env."""
+    rec, g = run_reference(script, argv, atari_mode="fresh", gymnasium_kind=gymnasium_kind)
     assert len(rec.iterations) == n_iter
     out = {"argv": np.array(argv)}
     for k in ("actions", "logprobs", "rewards", "dones", "values", "advantages", "returns", "next_value", "next_done",
@@ -161,6 +161,10 @@ def main():
                       ["--no-cuda", "--num-envs", "8", "--num-steps", "16", "--total-timesteps", "384", "--seed", "5",
                        "--no-norm-adv", "--target-kl", "0.0005", "--max-grad-norm", "0.3", "--vf-coef", "0.25",
                        "--clip-coef", "0.2", "--learning-rate", "1e-3"], 3)
+    if not only or "ppo_atari_lstm" in only:
+        atari_envpool("ppo_atari_lstm_n8_t16_seed4.npz",
+                      ["--no-cuda", "--num-envs", "8", "--num-steps", "16", "--total-timesteps", "384", "--seed", "4"], 3,
+                      script="ppo_atari_lstm.py", gymnasium_kind="atari1")
     if "ppo_atari_full" in only:
         # ~3 CPU-minutes: generated on request only (python -m oracle.make_golden ppo_atari_full)
         atari_envpool_full("ppo_atari_envpool_n1024_t128_seed1.npz",

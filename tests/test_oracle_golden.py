@@ -27,13 +27,14 @@ def _args(z):
                 target_kl=get("--target-kl", None), anneal_lr="--no-anneal-lr" not in argv)
 
 
-@pytest.mark.parametrize("name", ATARI + ["ppo_mlp_n4_t128_seed1.npz"])
+@pytest.mark.parametrize("name", ATARI + ["ppo_mlp_n4_t128_seed1.npz", "ppo_atari_lstm_n8_t16_seed4.npz",
+                                          "ppo_atari_envpool_n1024_t128_seed1.npz"])
 def test_gae_oracle_bit_exact_vs_reference_run(name):
     z = np.load(GOLDEN / name)
     a = _args(z)
     for it in range(z["rewards"].shape[0]):
-        adv, ret = O.gae(z["rewards"][it], z["values"][it], z["dones"][it], z["next_value"][it].reshape(-1),
-                         z["next_done"][it], a["gamma"], a["lam"])
+        adv, ret = O.gae(z["rewards"][it].astype(np.float32), z["values"][it], z["dones"][it].astype(np.float32),
+                         z["next_value"][it].reshape(-1), z["next_done"][it], a["gamma"], a["lam"])
         assert np.array_equal(adv, z["advantages"][it])
         assert np.array_equal(ret, z["returns"][it])
 
@@ -223,3 +224,21 @@ def test_gaussian_oracle_vs_torch_normal_and_autograd():
     assert np.abs(dm - mean.grad.numpy()).max() <= 1e-5 * np.abs(mean.grad.numpy()).max()
     assert np.abs(dls - logstd.grad.numpy().reshape(-1)).max() <= 1e-5 * max(1.0, np.abs(logstd.grad.numpy()).max())
     assert np.abs(dv - nv.grad.numpy()).max() <= 1e-7
+
+
+def test_lstm_env_shuffle_stream_matches_reference():
+    """cleanrl/ppo_atari_lstm.py:297-303 shuffles ENV indices (not samples) per epoch: np.random.seed(seed) + shuffle(arange(N))."""
+    z = np.load(GOLDEN / "ppo_atari_lstm_n8_t16_seed4.npz")
+    a = _args(z)
+    state = np.random.get_state()
+    try:
+        np.random.seed(a["seed"])
+        k = 0
+        for it in range(z["rewards"].shape[0]):
+            env = np.arange(a["num_envs"])
+            for e in range(a["update_epochs"]):
+                np.random.shuffle(env)
+                assert np.array_equal(env, z["shuffles"][k])
+                k += 1
+    finally:
+        np.random.set_state(state)
