@@ -43,6 +43,16 @@ SIGNATURES = {
     "b200rl_conv2d_bwd_data_f32": (_i, [_p, _p, _p, _i, _p, _i64, _i, _i, _i, _i, _i, _i, _i, _p]),
     "b200rl_conv2d_bwd_weight_workspace_bytes": (_sz, [_i64, _i, _i, _i, _i, _i, _i, _i]),
     "b200rl_conv2d_bwd_weight_f32": (_i, [_p, _i, _p, _d, _p, _p, _p, _i64, _i, _i, _i, _i, _i, _i, _i, _p, _sz, _p]),
+    "b200rl_conv2d_fwd_pad_f32": (_i, [_p, _i, _p, _d, _p, _p, _p, _i64, _i, _i, _i, _i, _i, _i, _i, _i, _i, _p]),
+    "b200rl_conv2d_bwd_data_pad_f32": (_i, [_p, _p, _p, _i, _p, _i64, _i, _i, _i, _i, _i, _i, _i, _i, _p]),
+    "b200rl_conv2d_bwd_weight_pad_workspace_bytes": (_sz, [_i64, _i, _i, _i, _i, _i, _i, _i, _i]),
+    "b200rl_conv2d_bwd_weight_pad_f32": (_i, [_p, _i, _p, _d, _p, _p, _p, _i64, _i, _i, _i, _i, _i, _i, _i, _i, _p, _sz, _p]),
+    "b200rl_maxpool3s2_fwd_f32": (_i, [_p, _i64, _i, _i, _p, _p, _p]),
+    "b200rl_maxpool3s2_bwd_f32": (_i, [_p, _p, _i64, _i, _i, _p, _p]),
+    "b200rl_relu_f32": (_i, [_p, _i64, _p, _p]),
+    "b200rl_relu_bwd_f32": (_i, [_p, _p, _p, _i64, _p, _p]),
+    "b200rl_add_f32": (_i, [_p, _p, _i64, _p, _p]),
+    "b200rl_nhwc_to_nchw_u8": (_i, [_p, _p, _i64, _i, _i, _i, _p, _p]),
     "b200rl_linear_fwd_f32": (_i, [_p, _p, _p, _p, _p, _i64, _i, _i, _i, _p]),
     "b200rl_linear_bwd_data_f32": (_i, [_p, _p, _p, _i, _p, _i64, _i, _i, _p]),
     "b200rl_linear_bwd_weight_workspace_bytes": (_sz, [_i64, _i, _i]),

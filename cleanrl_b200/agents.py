@@ -449,6 +449,142 @@ class LSTMAgent(KernelAgent):
         self._seq = None
 
 
+class ResidualBlock(nn.Module):
+    """Parameter container with the reference's names (cleanrl/ppo_procgen.py:89-102); executed by ImpalaAgent."""
+
+    def __init__(self, channels):
+        super().__init__()
+        self.conv0 = nn.Conv2d(in_channels=channels, out_channels=channels, kernel_size=3, padding=1)
+        self.conv1 = nn.Conv2d(in_channels=channels, out_channels=channels, kernel_size=3, padding=1)
+
+
+class ConvSequence(nn.Module):
+    """cleanrl/ppo_procgen.py:105-124: conv3x3 -> max_pool(3, stride 2, padding 1) -> two residual blocks."""
+
+    def __init__(self, input_shape, out_channels):
+        super().__init__()
+        self._input_shape = input_shape
+        self._out_channels = out_channels
+        self.conv = nn.Conv2d(in_channels=self._input_shape[0], out_channels=self._out_channels, kernel_size=3, padding=1)
+        self.res_block0 = ResidualBlock(self._out_channels)
+        self.res_block1 = ResidualBlock(self._out_channels)
+
+    def get_output_shape(self):
+        _c, h, w = self._input_shape
+        return (self._out_channels, (h + 1) // 2, (w + 1) // 2)
+
+
+class ImpalaAgent(KernelAgent):
+    """IMPALA-CNN actor-critic (reference: cleanrl/ppo_procgen.py:89-150): three ConvSequences (16, 32, 32 channels),
+    Flatten, ReLU, Linear(2048 -> 256), ReLU, ``actor`` / ``critic``.  Same module tree (``network.{0,1,2}.conv``,
+    ``network.{0,1,2}.res_block{0,1}.conv{0,1}``, ``network.5``), same construction order, torch's default initialisation
+    for the trunk (the reference only ``layer_init``s the heads), so a seed yields the reference's weights and
+    ``state_dict`` files interchange.  Frames arrive NHWC uint8 ([n, 64, 64, 3]) and are permuted on the device.
+
+    Execution: fp32 kernels of libb200rl (padded 3x3 convolutions, max-pool with arg-max, ReLU / add glue), explicit
+    backward in reverse order; no autograd, no cuDNN."""
+
+    def __init__(self, envs):
+        super().__init__()
+        h, w, c = envs.single_observation_space.shape
+        shape = (c, h, w)
+        conv_seqs = []
+        for out_channels in [16, 32, 32]:
+            conv_seq = ConvSequence(shape, out_channels)
+            shape = conv_seq.get_output_shape()
+            conv_seqs.append(conv_seq)
+        conv_seqs += [nn.Flatten(), nn.ReLU(),
+                      nn.Linear(in_features=shape[0] * shape[1] * shape[2], out_features=256), nn.ReLU()]
+        self.network = nn.Sequential(*conv_seqs)
+        self.actor = layer_init(nn.Linear(256, envs.single_action_space.n), std=0.01)
+        self.critic = layer_init(nn.Linear(256, 1), std=1)
+        self.num_actions = int(envs.single_action_space.n)
+        self._feat_shape = shape
+
+    graph_capturable = False
+
+    def _param_order(self):
+        net = [p for p in self.network.parameters()]
+        return net + [self.actor.weight, self.critic.weight, self.actor.bias, self.critic.bias]
+
+    def _build_plan(self):
+        f = self._flat
+        A = self.num_actions
+        wa, _ = f.view_of(self.actor.weight)
+        ba, _ = f.view_of(self.actor.bias)
+        off_w = (wa.data_ptr() - f.flat.data_ptr()) // 4
+        off_b = (ba.data_ptr() - f.flat.data_ptr()) // 4
+        self.head = nets.Linear(None, None, f.flat[off_w:off_w + (A + 1) * 256].view(A + 1, 256), f.flat[off_b:off_b + A + 1],
+                                f.grad[off_w:off_w + (A + 1) * 256].view(A + 1, 256), f.grad[off_b:off_b + A + 1])
+        self.fc = nets.Linear(self.network[5], "relu")
+        self.seqs = []
+        for i in range(3):
+            q = self.network[i]
+            self.seqs.append(dict(conv=nets.Conv(q.conv, None, in_div=255.0 if i == 0 else 1.0),
+                                  blocks=[(nets.Conv(b.conv0, "relu"), nets.Conv(b.conv1, None))
+                                          for b in (q.res_block0, q.res_block1)]))
+
+    # ------------------------------------------------------------------ forward
+    def _forward_heads(self, x, rows=None, keep=False):
+        if x.dtype != torch.uint8:
+            x = x.to(torch.uint8)          # frames are integers 0..255 (the reference passes them as fp32)
+        x = ops.nhwc_to_nchw_u8(x.contiguous(), rows)          # [n, 3, 64, 64] uint8; /255 inside the first convolution
+        saved = []
+        h = x
+        for s in self.seqs:
+            c = s["conv"].fwd(h)                               # conv, no activation
+            p, arg = ops.maxpool3s2_fwd(c)
+            rec = dict(x=h, c_hw=tuple(c.shape[-2:]), arg=arg, blocks=[])
+            b = p
+            for conv0, conv1 in s["blocks"]:
+                r0 = ops.relu(b)                               # x -> relu -> conv0 -> relu -> conv1 -> + x
+                y0 = conv0.fwd(r0)                             # relu fused on the output (the next op is a relu)
+                c1 = conv1.fwd(y0)
+                out = ops.add(c1, b)
+                rec["blocks"].append((r0, y0))
+                b = out
+            saved.append(rec)
+            h = b
+        flat = h.reshape(h.shape[0], -1)
+        h0 = ops.relu(flat)                                    # Flatten, ReLU
+        hid = self.fc.fwd(h0)                                  # Linear + ReLU
+        out = self.head.fwd(hid)
+        if keep:
+            self._saved = dict(seqs=saved, h0=h0, hid=hid, last_shape=tuple(h.shape))
+        A = self.num_actions
+        return out[:, :A], out[:, A]
+
+    def forward_train(self, b_obs, mb_inds):
+        self.flat
+        return self._forward_heads(b_obs, rows=mb_inds, keep=True)
+
+    def alloc_head_grad(self, M, device):
+        A = self.num_actions
+        d = torch.empty(M, A + 1, dtype=torch.float32, device=device)
+        return d, d[:, :A], d[:, A]
+
+    # ----------------------------------------------------------------- backward
+    def backward(self, dhead):
+        q = self._saved
+        self.head.bwd_weight(q["hid"], dhead)
+        d_hid = self.head.bwd_data(dhead, q["hid"], "relu")                    # through the ReLU after the Linear
+        self.fc.bwd_weight(q["h0"], d_hid)
+        d = self.fc.bwd_data(d_hid, q["h0"], "relu").view(q["last_shape"])     # through the ReLU after Flatten
+        for si in (2, 1, 0):
+            s, rec = self.seqs[si], q["seqs"][si]
+            for (conv0, conv1), (r0, y0) in zip(reversed(s["blocks"]), reversed(rec["blocks"])):
+                conv1.bwd_weight(y0, d)
+                dy0 = conv1.bwd_data(d, y0, "relu")                            # * (y0 > 0)
+                conv0.bwd_weight(r0, dy0)
+                d_in = conv0.bwd_data(dy0, None, None, in_hw=tuple(r0.shape[-2:]))
+                d = ops.relu_bwd(d_in, r0, extra=d)                            # * (x > 0) + skip connection
+            d_c = ops.maxpool3s2_bwd(d, rec["arg"], rec["c_hw"])
+            s["conv"].bwd_weight(rec["x"], d_c)
+            if si > 0:
+                d = s["conv"].bwd_data(d_c, None, None, in_hw=tuple(rec["x"].shape[-2:]))
+        self._saved = None
+
+
 def _normal_noise(n, D, device):
     # what Normal(mean, std).sample() == torch.normal(mean, std) consumes: one N(0,1) per element
     return torch.randn(n, D, dtype=torch.float32, device=device)

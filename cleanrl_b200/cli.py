@@ -119,6 +119,13 @@ def ppo_atari_multigpu_args(exp_name="ppo_atari_multigpu"):
     return _make("Args", _override(_COMMON, exp_name=exp_name) + algo + dist + runtime + _EXTRA)
 
 
+def ppo_procgen_args(exp_name="ppo_procgen"):
+    """cleanrl/ppo_procgen.py:16-79."""
+    algo = _override(_ALGO, env_id="starpilot", total_timesteps=int(25e6), learning_rate=5e-4, num_envs=64, num_steps=256,
+                     anneal_lr=False, gamma=0.999, num_minibatches=8, update_epochs=3)
+    return _make("Args", _override(_COMMON, exp_name=exp_name) + algo + _RUNTIME + _EXTRA)
+
+
 def ppo_atari_multigpu_envpool_args(exp_name="ppo_atari_multigpu_envpool"):
     """The script the reference defers (docs/rl-algorithms/ppo.md:1020): ppo_atari_multigpu.py's data parallelism over
     ppo_atari_envpool.py's vector env.  Fields = the multi-GPU script's, env defaults = the envpool script's."""

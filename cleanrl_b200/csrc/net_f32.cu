@@ -34,6 +34,7 @@ __device__ __forceinline__ float act_bwd(float y, int act) {   // derivative fro
 struct Geo {            // conv geometry (linear layers use H=W=KH=KW=1)
     int64_t n;
     int Cin, H, W, Cout, KH, KW, s, OH, OW;
+    int pad;             // zero padding on every side (IMPALA-CNN 3x3 convolutions, cleanrl/ppo_procgen.py:92-93)
 };
 
 template <typename XT>
@@ -58,7 +59,9 @@ struct ConvFwd {
         const int c = (int)(r / khw); const int rr = (int)(r - (int64_t)c * khw);
         const int ky = rr / g.KW, kx = rr - ky * g.KW;
         const int64_t sn = rows ? rows[n_] : n_;
-        return decode(x, ((sn * g.Cin + c) * g.H + oy * g.s + ky) * g.W + ox * g.s + kx, div);
+        const int iy = oy * g.s + ky - g.pad, ix = ox * g.s + kx - g.pad;
+        if (iy < 0 || ix < 0 || iy >= g.H || ix >= g.W) return 0.f;
+        return decode(x, ((sn * g.Cin + c) * g.H + iy) * g.W + ix, div);
     }
     __device__ float B(int64_t j, int64_t r) const { return w[j * R() + r]; }
     __device__ void store(int64_t i, int64_t j, float acc, int) const {
@@ -81,7 +84,7 @@ struct ConvBwdData {
         const int khw = g.KH * g.KW;
         const int co = (int)(r / khw); const int rr = (int)(r - (int64_t)co * khw);
         const int ky = rr / g.KW, kx = rr - ky * g.KW;
-        const int ty = iy - ky, tx = ix - kx;
+        const int ty = iy + g.pad - ky, tx = ix + g.pad - kx;
         if (ty < 0 || tx < 0) return 0.f;
         const int oy = ty / g.s, ox = tx / g.s;
         if (oy * g.s != ty || ox * g.s != tx || oy >= g.OH || ox >= g.OW) return 0.f;
@@ -122,7 +125,9 @@ struct ConvBwdWeight {
         const int c = (int)(j / khw); const int rr = (int)(j - (int64_t)c * khw);
         const int ky = rr / g.KW, kx = rr - ky * g.KW;
         const int64_t sn = rows ? rows[n_] : n_;
-        return decode(x, ((sn * g.Cin + c) * g.H + oy * g.s + ky) * g.W + ox * g.s + kx, div);
+        const int iy = oy * g.s + ky - g.pad, ix = ox * g.s + kx - g.pad;
+        if (iy < 0 || ix < 0 || iy >= g.H || ix >= g.W) return 0.f;
+        return decode(x, ((sn * g.Cin + c) * g.H + iy) * g.W + ix, div);
     }
     __device__ void store(int64_t i, int64_t j, float acc, int z) const {
         partial[((int64_t)z * M() + i) * N() + j] = acc;
@@ -262,11 +267,12 @@ static int split_count(int64_t tiles, int64_t R) {
     return (int)want;
 }
 
-static bool make_geo(Geo& g, int64_t n, int Cin, int H, int W, int Cout, int KH, int KW, int stride) {
-    if (n < 0 || Cin < 1 || H < 1 || W < 1 || Cout < 1 || KH < 1 || KW < 1 || stride < 1 || KH > H || KW > W)
+static bool make_geo(Geo& g, int64_t n, int Cin, int H, int W, int Cout, int KH, int KW, int stride, int pad = 0) {
+    if (n < 0 || Cin < 1 || H < 1 || W < 1 || Cout < 1 || KH < 1 || KW < 1 || stride < 1 || pad < 0 || pad >= KH || pad >= KW ||
+        KH > H + 2 * pad || KW > W + 2 * pad)
         return false;
-    g.n = n; g.Cin = Cin; g.H = H; g.W = W; g.Cout = Cout; g.KH = KH; g.KW = KW; g.s = stride;
-    g.OH = (H - KH) / stride + 1; g.OW = (W - KW) / stride + 1;
+    g.n = n; g.Cin = Cin; g.H = H; g.W = W; g.Cout = Cout; g.KH = KH; g.KW = KW; g.s = stride; g.pad = pad;
+    g.OH = (H + 2 * pad - KH) / stride + 1; g.OW = (W + 2 * pad - KW) / stride + 1;
     return true;
 }
 
@@ -278,8 +284,14 @@ extern "C" int b200rl_conv2d_fwd_f32(const void* x, int x_dtype, const int64_t* 
                                      const float* w, const float* b, float* y,
                                      int64_t n, int Cin, int H, int W, int Cout, int KH, int KW, int stride,
                                      int act, void* stream) {
+    return b200rl_conv2d_fwd_pad_f32(x, x_dtype, rows, in_div, w, b, y, n, Cin, H, W, Cout, KH, KW, stride, 0, act, stream);
+}
+extern "C" int b200rl_conv2d_fwd_pad_f32(const void* x, int x_dtype, const int64_t* rows, double in_div,
+                                         const float* w, const float* b, float* y,
+                                         int64_t n, int Cin, int H, int W, int Cout, int KH, int KW, int stride, int pad,
+                                         int act, void* stream) {
     Geo g;
-    B200RL_REQUIRE(make_geo(g, n, Cin, H, W, Cout, KH, KW, stride), "conv2d_fwd: bad geometry");
+    B200RL_REQUIRE(make_geo(g, n, Cin, H, W, Cout, KH, KW, stride, pad), "conv2d_fwd: bad geometry");
     if (n == 0) return B200RL_OK;
     B200RL_REQUIRE(x && w && y, "conv2d_fwd: null pointer");
     B200RL_REQUIRE(act >= 0 && act <= 2, "conv2d_fwd: bad act %d", act);
@@ -300,8 +312,14 @@ extern "C" int b200rl_conv2d_bwd_data_f32(const float* dy, const float* w, const
                                           float* dx,
                                           int64_t n, int Cin, int H, int W, int Cout, int KH, int KW, int stride,
                                           void* stream) {
+    return b200rl_conv2d_bwd_data_pad_f32(dy, w, x_post, prev_act, dx, n, Cin, H, W, Cout, KH, KW, stride, 0, stream);
+}
+extern "C" int b200rl_conv2d_bwd_data_pad_f32(const float* dy, const float* w, const float* x_post, int prev_act,
+                                              float* dx,
+                                              int64_t n, int Cin, int H, int W, int Cout, int KH, int KW, int stride, int pad,
+                                              void* stream) {
     Geo g;
-    B200RL_REQUIRE(make_geo(g, n, Cin, H, W, Cout, KH, KW, stride), "conv2d_bwd_data: bad geometry");
+    B200RL_REQUIRE(make_geo(g, n, Cin, H, W, Cout, KH, KW, stride, pad), "conv2d_bwd_data: bad geometry");
     if (n == 0) return B200RL_OK;
     B200RL_REQUIRE(dy && w && dx, "conv2d_bwd_data: null pointer");
     B200RL_REQUIRE(prev_act == 0 || x_post, "conv2d_bwd_data: x_post required when prev_act != none");
@@ -311,8 +329,12 @@ extern "C" int b200rl_conv2d_bwd_data_f32(const float* dy, const float* w, const
 
 extern "C" size_t b200rl_conv2d_bwd_weight_workspace_bytes(int64_t n, int Cin, int H, int W, int Cout, int KH, int KW,
                                                            int stride) {
+    return b200rl_conv2d_bwd_weight_pad_workspace_bytes(n, Cin, H, W, Cout, KH, KW, stride, 0);
+}
+extern "C" size_t b200rl_conv2d_bwd_weight_pad_workspace_bytes(int64_t n, int Cin, int H, int W, int Cout, int KH, int KW,
+                                                               int stride, int pad) {
     Geo g;
-    if (!make_geo(g, n, Cin, H, W, Cout, KH, KW, stride)) return 0;
+    if (!make_geo(g, n, Cin, H, W, Cout, KH, KW, stride, pad)) return 0;
     const int64_t cols1 = (int64_t)Cin * KH * KW + 1;
     const int64_t tiles = ceil_div(Cout, BM) * ceil_div(cols1, BN);
     const int S = split_count(tiles, n * g.OH * g.OW);
@@ -323,11 +345,18 @@ extern "C" int b200rl_conv2d_bwd_weight_f32(const void* x, int x_dtype, const in
                                             const float* dy, float* dw, float* db,
                                             int64_t n, int Cin, int H, int W, int Cout, int KH, int KW, int stride,
                                             void* workspace, size_t workspace_bytes, void* stream) {
+    return b200rl_conv2d_bwd_weight_pad_f32(x, x_dtype, rows, in_div, dy, dw, db, n, Cin, H, W, Cout, KH, KW, stride, 0, workspace,
+                                            workspace_bytes, stream);
+}
+extern "C" int b200rl_conv2d_bwd_weight_pad_f32(const void* x, int x_dtype, const int64_t* rows, double in_div,
+                                                const float* dy, float* dw, float* db,
+                                                int64_t n, int Cin, int H, int W, int Cout, int KH, int KW, int stride, int pad,
+                                                void* workspace, size_t workspace_bytes, void* stream) {
     Geo g;
-    B200RL_REQUIRE(make_geo(g, n, Cin, H, W, Cout, KH, KW, stride), "conv2d_bwd_weight: bad geometry");
+    B200RL_REQUIRE(make_geo(g, n, Cin, H, W, Cout, KH, KW, stride, pad), "conv2d_bwd_weight: bad geometry");
     B200RL_REQUIRE(x && dy && dw && workspace, "conv2d_bwd_weight: null pointer");
     B200RL_REQUIRE(in_div != 0.0, "conv2d_bwd_weight: in_div == 0");
-    const size_t need = b200rl_conv2d_bwd_weight_workspace_bytes(n, Cin, H, W, Cout, KH, KW, stride);
+    const size_t need = b200rl_conv2d_bwd_weight_pad_workspace_bytes(n, Cin, H, W, Cout, KH, KW, stride, pad);
     if (workspace_bytes < need) return fail(B200RL_ERR_WORKSPACE, "conv2d_bwd_weight: workspace %zu < %zu", workspace_bytes, need);
     cudaStream_t s = (cudaStream_t)stream;
     const int64_t cols1 = (int64_t)Cin * KH * KW + 1;

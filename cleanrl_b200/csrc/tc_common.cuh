@@ -136,6 +136,12 @@ __host__ __device__ constexpr uint32_t make_idesc(int M, int N, int a_mn_major, 
 // byte offset of 16-byte chunk `c` of row `r` inside an operand image (rows stacked 128 B apart)
 __device__ __forceinline__ uint32_t img_off(int r, int c) { return (uint32_t)(r * 128 + ((c ^ (r & 7)) << 4)); }
 
+// max(x, 0) folded into the fp32 -> bf16x2 conversion (one F2FP instead of two FMNMX + one F2FP)
+__device__ __forceinline__ uint32_t pack_bf16x2_relu(float lo, float hi) {
+    uint32_t d;
+    asm("cvt.rn.relu.bf16x2.f32 %0, %1, %2;" : "=r"(d) : "f"(hi), "f"(lo));
+    return d;
+}
 __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
     __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);
     return *reinterpret_cast<uint32_t*>(&v);

@@ -319,8 +319,8 @@ __global__ void __launch_bounds__(kConvWinThreads, 1) tc_conv1_i8(const __grid_c
                 bits |= (f1 > 0.f ? 1u : 0u) << (c4 + 1);
                 bits |= (f2 > 0.f ? 1u : 0u) << (c4 + 2);
                 bits |= (f3 > 0.f ? 1u : 0u) << (c4 + 3);
-                pk[c4 >> 1] = pack_bf16x2(fmaxf(f0, 0.f), fmaxf(f1, 0.f));
-                pk[(c4 >> 1) + 1] = pack_bf16x2(fmaxf(f2, 0.f), fmaxf(f3, 0.f));
+                pk[c4 >> 1] = pack_bf16x2_relu(f0, f1);
+                pk[(c4 >> 1) + 1] = pack_bf16x2_relu(f2, f3);
             }
             if (valid && !(p.dbg & 1)) p.mask_out[cell * 4 + cls] = bits;
             // Stores: a lane owns one output row (64 B at its own 2x2-cell address), so a direct 16-byte store instruction of

@@ -56,15 +56,19 @@ __device__ __forceinline__ uint32_t pack_f16x2_sat(float lo, float hi) {
 // mask, bf16 packing, stores); with two groups every scheduler held two such warps and ncu showed 0.2-0.4 instructions per
 // cycle and scheduler with the tensor pipe at 25-45 % -- the epilogue's LATENCY was the tile period.  Four warps per scheduler
 // hide it.  Measured and dropped: a second MMA-issuer warp (no gain: the issuing thread is not the limit).
-constexpr int kConvWinThreads = 576;
-constexpr int kConvWinGroups = 4;
+constexpr int kConvWinThreads = 576;                     // the widest instance (4 groups); see conv_win_groups
+// N = 128 tiles (conv2 data gradient) keep two groups: their epilogue holds 4 x 32 accumulator columns per row and was
+// measured 10 % slower with four groups (register pressure at 576 threads); the narrower kernels gain 0-12 %.
+__host__ __device__ constexpr int conv_win_groups(int BN) { return BN >= 128 ? 2 : 4; }
+__host__ __device__ constexpr int conv_win_threads(int BN) { return 64 + conv_win_groups(BN) * 128; }
 __host__ __device__ constexpr int conv_win_acc_bufs(int BN) { return BN <= 128 ? 4 : 2; }
 template <int BN, int CPR, int STAGES, int NTAPS>
-__global__ void __launch_bounds__(kConvWinThreads, 1) tc_conv_win(const __grid_constant__ CUtensorMap tmA, const WinParams p,
+__global__ void __launch_bounds__(conv_win_threads(BN), 1) tc_conv_win(const __grid_constant__ CUtensorMap tmA, const WinParams p,
                                                       int total_tiles) {
     constexpr int B_CHUNK = BN * 128;
     constexpr int NB = conv_win_acc_bufs(BN);
-    static_assert(NB == kConvWinGroups, "one accumulator buffer per epilogue group");
+    constexpr int NG = conv_win_groups(BN);
+    static_assert(NB % NG == 0, "every epilogue group owns NB / NG accumulator buffers");
     constexpr uint32_t TMEM_COLS = (NB * BN) < 32 ? 32 : NB * BN;
     extern __shared__ uint8_t smem_raw[];
     __shared__ uint64_t full_bar[STAGES], empty_bar[STAGES], tfull_bar[NB], tempty_bar[NB];
@@ -177,7 +181,7 @@ __global__ void __launch_bounds__(kConvWinThreads, 1) tc_conv_win(const __grid_c
         const int h = (warp - 2) >> 2;                       // epilogue group 0..3
         const int lrow = ew * 32 + (tid & 31);
         const uint32_t mW = (65536u + (uint32_t)p.Wp - 1u) / (uint32_t)p.Wp;
-        constexpr int TSTEP = kConvWinGroups * 128;          // grid rows between two tiles of one group
+        constexpr int TSTEP = NG * 128;                      // grid rows between two tiles of one group
         const int step_i = TSTEP / p.G, step_rem = TSTEP % p.G;
         int64_t r = ((int64_t)tile_begin + h) * 128 + lrow;      // linear-grid mode state (unused when image-aligned)
         int i_lin = (int)(r / p.G);
@@ -186,8 +190,8 @@ __global__ void __launch_bounds__(kConvWinThreads, 1) tc_conv_win(const __grid_c
         const uint32_t lane_base = tmem_d + ((uint32_t)(ew * 32) << 16);
         constexpr int NW = BN / 32;                          // 32-column groups = mask words per row
         uint32_t k = 0;                                      // tiles this group has drained
-        for (int tile = tile_begin + h; tile < tile_end; tile += kConvWinGroups, ++k) {
-            const uint32_t acc = (uint32_t)(tile - tile_begin) % NB;           // NB = 4: buffer h; NB = 2: h & 1
+        for (int tile = tile_begin + h; tile < tile_end; tile += NG, ++k) {
+            const uint32_t acc = (uint32_t)(tile - tile_begin) % NB;           // group h drains buffers h, h + NG, ...
             const uint32_t lane_addr = lane_base + acc * BN;
             int i = i_lin, rem = rem_lin;
             bool inside = r < p.M;
@@ -260,9 +264,7 @@ __global__ void __launch_bounds__(kConvWinThreads, 1) tc_conv_win(const __grid_c
 #pragma unroll
                     for (int e = 0; e < 32; ++e) {
                         const float f = __uint_as_float(v[e]);
-                        const bool pos = f > 0.f;
-                        bits |= (pos ? 1u : 0u) << e;
-                        v[e] = pos ? v[e] : 0u;
+                        bits |= (f > 0.f ? 1u : 0u) << e;           // the clamp itself is folded into the bf16 conversion below
                     }
                     if (p.mask_out) p.mask_out[ob + g] = bits;
                 }
@@ -278,6 +280,14 @@ __global__ void __launch_bounds__(kConvWinThreads, 1) tc_conv_win(const __grid_c
                         w[e].y = (int)pack_f16x2_sat(__uint_as_float(v[8 * e + 2]), __uint_as_float(v[8 * e + 3]));
                         w[e].z = (int)pack_f16x2_sat(__uint_as_float(v[8 * e + 4]), __uint_as_float(v[8 * e + 5]));
                         w[e].w = (int)pack_f16x2_sat(__uint_as_float(v[8 * e + 6]), __uint_as_float(v[8 * e + 7]));
+                    }
+                } else if (p.relu) {
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) {
+                        w[e].x = (int)pack_bf16x2_relu(__uint_as_float(v[8 * e]), __uint_as_float(v[8 * e + 1]));
+                        w[e].y = (int)pack_bf16x2_relu(__uint_as_float(v[8 * e + 2]), __uint_as_float(v[8 * e + 3]));
+                        w[e].z = (int)pack_bf16x2_relu(__uint_as_float(v[8 * e + 4]), __uint_as_float(v[8 * e + 5]));
+                        w[e].w = (int)pack_bf16x2_relu(__uint_as_float(v[8 * e + 6]), __uint_as_float(v[8 * e + 7]));
                     }
                 } else {
 #pragma unroll
@@ -330,7 +340,7 @@ static int launch_conv_win(const WinParams& p, cudaStream_t s, const char* what)
     if (p.tpi_shift) rc = make_tmap_3d(&tmA, p.A, p.n_images, p.G, (int64_t)CPR * 64, p.WR, what);
     else rc = make_tmap_2d(&tmA, p.A, p.M, (int64_t)CPR * 64, p.WR, what);
     if (rc) return rc;
-    tc_conv_win<BN, CPR, STAGES, NTAPS><<<grid, kConvWinThreads, smem, s>>>(tmA, p, total);
+    tc_conv_win<BN, CPR, STAGES, NTAPS><<<grid, conv_win_threads(BN), smem, s>>>(tmA, p, total);
     return check_launch(what);
 }
 

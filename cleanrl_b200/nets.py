@@ -61,17 +61,19 @@ class _Layer:
 
 class Conv(_Layer):
     def __init__(self, conv: nn.Conv2d, act, in_div=1.0):
-        assert conv.stride[0] == conv.stride[1] and conv.padding == (0, 0) and conv.dilation == (1, 1)
-        self.m, self.stride, self.act, self.in_div = conv, conv.stride[0], act, in_div
+        assert conv.stride[0] == conv.stride[1] and conv.padding[0] == conv.padding[1] and conv.dilation == (1, 1)
+        self.m, self.stride, self.act, self.in_div, self.pad = conv, conv.stride[0], act, in_div, int(conv.padding[0])
 
     def fwd(self, x, rows=None):
-        return ops.conv2d_fwd(x, self.m.weight.data, self.m.bias.data, self.stride, self.act, rows=rows, in_div=self.in_div)
+        return ops.conv2d_fwd(x, self.m.weight.data, self.m.bias.data, self.stride, self.act, rows=rows, in_div=self.in_div,
+                              pad=self.pad)
 
     def bwd_weight(self, x, dy, rows=None):
-        ops.conv2d_bwd_weight(x, dy, self.m.weight.grad, self.m.bias.grad, self.stride, rows=rows, in_div=self.in_div)
+        ops.conv2d_bwd_weight(x, dy, self.m.weight.grad, self.m.bias.grad, self.stride, rows=rows, in_div=self.in_div,
+                              pad=self.pad)
 
-    def bwd_data(self, dy, x_post, prev_act):
-        return ops.conv2d_bwd_data(dy, self.m.weight.data, x_post, prev_act, self.stride)
+    def bwd_data(self, dy, x_post, prev_act, in_hw=None):
+        return ops.conv2d_bwd_data(dy, self.m.weight.data, x_post, prev_act, self.stride, pad=self.pad, in_hw=in_hw)
 
 
 class Linear(_Layer):

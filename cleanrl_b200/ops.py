@@ -200,52 +200,54 @@ def _xdtype(x):
     raise TypeError(f"unsupported input dtype {x.dtype} (need uint8 or float32)")
 
 
-def conv2d_fwd(x, w, b, stride, act, rows=None, in_div=1.0, out=None):
-    """y = act(conv2d(x / in_div, w) + b), NCHW (reference: nn.Conv2d + ReLU, ppo_atari_envpool.py:126-132).
-    ``rows`` (int64) gathers the batch dimension of x without materialising it (ppo.py:250)."""
+def conv2d_fwd(x, w, b, stride, act, rows=None, in_div=1.0, out=None, pad=0):
+    """y = act(conv2d(x / in_div, w, padding=pad) + b), NCHW (reference: nn.Conv2d + ReLU, ppo_atari_envpool.py:126-132;
+    padded 3x3: ppo_procgen.py:92-93).  ``rows`` (int64) gathers the batch dimension of x without materialising it (ppo.py:250)."""
     lib = _lib.load()
     _contig(x, "x"); _contig(w, "w")
     Cout, Cin, KH, KW = w.shape
     H, W = x.shape[-2:]
     assert x.shape[-3] == Cin
     n = rows.numel() if rows is not None else x.shape[0]
-    OH, OW = (H - KH) // stride + 1, (W - KW) // stride + 1
+    OH, OW = (H + 2 * pad - KH) // stride + 1, (W + 2 * pad - KW) // stride + 1
     if out is None:
         out = torch.empty(n, Cout, OH, OW, dtype=torch.float32, device=x.device)
-    rc = lib.b200rl_conv2d_fwd_f32(_ptr(x, None, "x"), _xdtype(x), _ptr(rows, torch.int64, "rows", True), float(in_div),
-                                   _ptr(w, torch.float32, "w"), _ptr(b, torch.float32, "b", True),
-                                   _ptr(out, torch.float32, "y"), n, Cin, H, W, Cout, KH, KW, stride, ACT[act], _stream())
+    rc = lib.b200rl_conv2d_fwd_pad_f32(_ptr(x, None, "x"), _xdtype(x), _ptr(rows, torch.int64, "rows", True), float(in_div),
+                                       _ptr(w, torch.float32, "w"), _ptr(b, torch.float32, "b", True),
+                                       _ptr(out, torch.float32, "y"), n, Cin, H, W, Cout, KH, KW, stride, int(pad), ACT[act], _stream())
     _lib.check(rc, "conv2d_fwd")
     return out
 
 
-def conv2d_bwd_data(dy, w, x_post, prev_act, stride, out=None):
+def conv2d_bwd_data(dy, w, x_post, prev_act, stride, out=None, pad=0, in_hw=None):
+    """dx of the convolution; ``x_post`` / ``prev_act`` fold the derivative of the activation that produced the layer
+    input (``prev_act=None``: pass ``in_hw=(H, W)`` instead of ``x_post``)."""
     lib = _lib.load()
     _contig(dy, "dy"); _contig(w, "w")
     Cout, Cin, KH, KW = w.shape
     n = dy.shape[0]
-    H, W = x_post.shape[-2:]
+    H, W = x_post.shape[-2:] if x_post is not None else in_hw
     if out is None:
         out = torch.empty(n, Cin, H, W, dtype=torch.float32, device=dy.device)
-    rc = lib.b200rl_conv2d_bwd_data_f32(_ptr(dy, torch.float32, "dy"), _ptr(w, torch.float32, "w"),
-                                        _ptr(x_post, torch.float32, "x_post"), ACT[prev_act],
-                                        _ptr(out, torch.float32, "dx"), n, Cin, H, W, Cout, KH, KW, stride, _stream())
+    rc = lib.b200rl_conv2d_bwd_data_pad_f32(_ptr(dy, torch.float32, "dy"), _ptr(w, torch.float32, "w"),
+                                            _ptr(x_post, torch.float32, "x_post", True), ACT[prev_act] if x_post is not None else 0,
+                                            _ptr(out, torch.float32, "dx"), n, Cin, H, W, Cout, KH, KW, stride, int(pad), _stream())
     _lib.check(rc, "conv2d_bwd_data")
     return out
 
 
-def conv2d_bwd_weight(x, dy, dw, db, stride, rows=None, in_div=1.0):
+def conv2d_bwd_weight(x, dy, dw, db, stride, rows=None, in_div=1.0, pad=0):
     lib = _lib.load()
     _contig(x, "x"); _contig(dy, "dy"); _contig(dw, "dw")
     Cout, Cin, KH, KW = dw.shape
     H, W = x.shape[-2:]
     n = dy.shape[0]
-    nbytes = lib.b200rl_conv2d_bwd_weight_workspace_bytes(n, Cin, H, W, Cout, KH, KW, stride)
+    nbytes = lib.b200rl_conv2d_bwd_weight_pad_workspace_bytes(n, Cin, H, W, Cout, KH, KW, stride, int(pad))
     ws = _workspace(x.device, "wgrad", nbytes)
-    rc = lib.b200rl_conv2d_bwd_weight_f32(_ptr(x, None, "x"), _xdtype(x), _ptr(rows, torch.int64, "rows", True),
-                                          float(in_div), _ptr(dy, torch.float32, "dy"), _ptr(dw, torch.float32, "dw"),
-                                          _ptr(db, torch.float32, "db", True), n, Cin, H, W, Cout, KH, KW, stride,
-                                          ws.data_ptr(), ws.numel(), _stream())
+    rc = lib.b200rl_conv2d_bwd_weight_pad_f32(_ptr(x, None, "x"), _xdtype(x), _ptr(rows, torch.int64, "rows", True),
+                                              float(in_div), _ptr(dy, torch.float32, "dy"), _ptr(dw, torch.float32, "dw"),
+                                              _ptr(db, torch.float32, "db", True), n, Cin, H, W, Cout, KH, KW, stride, int(pad),
+                                              ws.data_ptr(), ws.numel(), _stream())
     _lib.check(rc, "conv2d_bwd_weight")
 
 
@@ -292,6 +294,67 @@ def linear_bwd_weight(x, dy, dw, db, rows=None):
                                           _ptr(db, torch.float32, "db", True), n, in_f, out_f,
                                           ws.data_ptr(), ws.numel(), _stream())
     _lib.check(rc, "linear_bwd_weight")
+
+
+# ------------------------------------------------------------------ IMPALA-CNN glue
+def maxpool3s2_fwd(x):
+    """max_pool2d(x, kernel_size=3, stride=2, padding=1) on NCHW fp32 (ppo_procgen.py:113); returns (y, argmax u8)."""
+    lib = _lib.load()
+    _contig(x, "x")
+    n, C, H, W = x.shape
+    y = torch.empty(n, C, (H + 1) // 2, (W + 1) // 2, dtype=torch.float32, device=x.device)
+    arg = torch.empty(y.shape, dtype=torch.uint8, device=x.device)
+    _lib.check(lib.b200rl_maxpool3s2_fwd_f32(_ptr(x, torch.float32, "x"), n * C, H, W, _ptr(y, torch.float32, "y"),
+                                             _ptr(arg, torch.uint8, "argmax"), _stream()), "maxpool_fwd")
+    return y, arg
+
+
+def maxpool3s2_bwd(dy, arg, in_hw):
+    lib = _lib.load()
+    _contig(dy, "dy")
+    n, C = dy.shape[:2]
+    H, W = in_hw
+    dx = torch.empty(n, C, H, W, dtype=torch.float32, device=dy.device)
+    _lib.check(lib.b200rl_maxpool3s2_bwd_f32(_ptr(dy, torch.float32, "dy"), _ptr(arg, torch.uint8, "argmax"), n * C, H, W,
+                                             _ptr(dx, torch.float32, "dx"), _stream()), "maxpool_bwd")
+    return dx
+
+
+def relu(x):
+    lib = _lib.load()
+    y = torch.empty_like(_contig(x, "x"))
+    _lib.check(lib.b200rl_relu_f32(_ptr(x, torch.float32, "x"), x.numel(), _ptr(y, torch.float32, "y"), _stream()), "relu")
+    return y
+
+
+def relu_bwd(dy, x, extra=None):
+    """dx = dy * (x > 0) [+ extra]."""
+    lib = _lib.load()
+    dx = torch.empty_like(_contig(dy, "dy"))
+    _lib.check(lib.b200rl_relu_bwd_f32(_ptr(dy, torch.float32, "dy"), _ptr(_contig(x, "x"), torch.float32, "x"),
+                                       _ptr(extra, torch.float32, "extra", True), dy.numel(), _ptr(dx, torch.float32, "dx"),
+                                       _stream()), "relu_bwd")
+    return dx
+
+
+def add(a, b):
+    lib = _lib.load()
+    y = torch.empty_like(_contig(a, "a"))
+    _lib.check(lib.b200rl_add_f32(_ptr(a, torch.float32, "a"), _ptr(_contig(b, "b"), torch.float32, "b"), a.numel(),
+                                  _ptr(y, torch.float32, "y"), _stream()), "add")
+    return y
+
+
+def nhwc_to_nchw_u8(x, rows=None):
+    """uint8 frames [*, H, W, C] (optionally gathered through int64 ``rows``) -> [n, C, H, W] (ppo_procgen.py:143 permute)."""
+    lib = _lib.load()
+    _contig(x, "x")
+    H, W, C = x.shape[-3:]
+    n = rows.numel() if rows is not None else x.shape[0]
+    y = torch.empty(n, C, H, W, dtype=torch.uint8, device=x.device)
+    _lib.check(lib.b200rl_nhwc_to_nchw_u8(_ptr(x, torch.uint8, "x"), _ptr(rows, torch.int64, "rows", True), n, H, W, C,
+                                          _ptr(y, torch.uint8, "y"), _stream()), "nhwc_to_nchw")
+    return y
 
 
 # ------------------------------------------------------------------------ LSTM cell

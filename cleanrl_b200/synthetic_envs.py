@@ -289,3 +289,46 @@ class CartPoleVec:
 
     def close(self):
         pass
+
+
+class SyntheticProcgenVec:
+    """Procgen-shaped vector env (gym3 / old-gym vector API as cleanrl/ppo_procgen.py:176-186,237-247 uses it after its
+    wrappers): uint8 RGB frames [N, 64, 64, 3], Discrete(15) actions, ``reset() -> obs``, ``step(a) -> (obs, reward, done,
+    info)`` with ``info`` a list of per-env dicts carrying ``{"episode": {"r", "l"}}`` when an episode ends.  The next frame
+    of an env depends on its own step count and the action it received (a wrong action changes later observations)."""
+
+    def __init__(self, num_envs, seed=0, n_actions=15, pool=32, p_done=0.02):
+        self.num_envs = int(num_envs)
+        self.observation_space = Box(0, 255, (64, 64, 3), np.uint8)
+        self.action_space = Discrete(n_actions)
+        self.single_observation_space, self.single_action_space = self.observation_space, self.action_space
+        self.is_vector_env = True
+        self._rng = np.random.default_rng(seed)
+        self._frames = self._rng.integers(0, 256, size=(pool, 64, 64, 3), dtype=np.uint8)
+        self._idx = np.zeros(self.num_envs, dtype=np.int64)
+        self._ret = np.zeros(self.num_envs, dtype=np.float64)
+        self._len = np.zeros(self.num_envs, dtype=np.int64)
+        self.p_done = float(p_done)
+
+    def reset(self, **kwargs):
+        self._idx = self._rng.integers(0, len(self._frames), size=self.num_envs)
+        self._ret[:] = 0
+        self._len[:] = 0
+        return self._frames[self._idx]
+
+    def step(self, action):
+        a = np.asarray(action).reshape(self.num_envs).astype(np.int64)
+        reward = (self._rng.integers(0, 4, size=self.num_envs) == 0).astype(np.float32) * (a % 3 != 0)
+        done = self._rng.random(self.num_envs) < self.p_done
+        self._ret += reward
+        self._len += 1
+        info = [{} for _ in range(self.num_envs)]
+        for i in np.nonzero(done)[0]:
+            info[i] = {"episode": {"r": float(self._ret[i]), "l": int(self._len[i])}}
+        self._ret[done] = 0
+        self._len[done] = 0
+        self._idx = (self._idx * 5 + a + 1) % len(self._frames)
+        return self._frames[self._idx], reward, done, info
+
+    def close(self):
+        pass

@@ -187,6 +187,28 @@ int b200rl_conv2d_fwd_f32(const void* x, int x_dtype, const int64_t* rows, doubl
                           const float* w, const float* b, float* y,
                           int64_t n, int Cin, int H, int W, int Cout, int KH, int KW, int stride,
                           int act, void* stream);
+/* Same with zero padding `pad` on every side (IMPALA-CNN 3x3 convolutions, cleanrl/ppo_procgen.py:92-93,110). */
+int b200rl_conv2d_fwd_pad_f32(const void* x, int x_dtype, const int64_t* rows, double in_div,
+                              const float* w, const float* b, float* y,
+                              int64_t n, int Cin, int H, int W, int Cout, int KH, int KW, int stride, int pad,
+                              int act, void* stream);
+int b200rl_conv2d_bwd_data_pad_f32(const float* dy, const float* w, const float* x_post, int prev_act, float* dx,
+                                   int64_t n, int Cin, int H, int W, int Cout, int KH, int KW, int stride, int pad, void* stream);
+size_t b200rl_conv2d_bwd_weight_pad_workspace_bytes(int64_t n, int Cin, int H, int W, int Cout, int KH, int KW, int stride, int pad);
+int b200rl_conv2d_bwd_weight_pad_f32(const void* x, int x_dtype, const int64_t* rows, double in_div,
+                                     const float* dy, float* dw, float* db,
+                                     int64_t n, int Cin, int H, int W, int Cout, int KH, int KW, int stride, int pad,
+                                     void* workspace, size_t workspace_bytes, void* stream);
+/* IMPALA-CNN glue (cleanrl/ppo_procgen.py:89-150), fp32 NCHW:
+ *   maxpool3s2: max_pool2d(kernel 3, stride 2, padding 1) on [nc, H, W] planes -> [nc, (H+1)/2, (W+1)/2]; argmax u8 (0..8)
+ *   relu / relu_bwd (dx = dy * (x > 0) + extra, extra may be NULL) / add: pre-activation residual blocks
+ *   nhwc_to_nchw_u8: frames [n, H, W, C] (optionally gathered through rows) -> [n, C, H, W] */
+int b200rl_maxpool3s2_fwd_f32(const float* x, int64_t nc, int H, int W, float* y, uint8_t* argmax, void* stream);
+int b200rl_maxpool3s2_bwd_f32(const float* dy, const uint8_t* argmax, int64_t nc, int H, int W, float* dx, void* stream);
+int b200rl_relu_f32(const float* x, int64_t n, float* y, void* stream);
+int b200rl_relu_bwd_f32(const float* dy, const float* x, const float* extra, int64_t n, float* dx, void* stream);
+int b200rl_add_f32(const float* a, const float* b, int64_t n, float* y, void* stream);
+int b200rl_nhwc_to_nchw_u8(const uint8_t* x, const int64_t* rows, int64_t n, int H, int W, int C, uint8_t* y, void* stream);
 /* dx = conv_transpose(dy, w) * act'(x_post) ; x_post = the layer input as the
  * previous layer's post-activation output (prev_act selects the derivative). */
 int b200rl_conv2d_bwd_data_f32(const float* dy, const float* w, const float* x_post, int prev_act,

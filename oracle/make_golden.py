@@ -165,6 +165,10 @@ def main():
         atari_envpool("ppo_atari_lstm_n8_t16_seed4.npz",
                       ["--no-cuda", "--num-envs", "8", "--num-steps", "16", "--total-timesteps", "384", "--seed", "4"], 3,
                       script="ppo_atari_lstm.py", gymnasium_kind="atari1")
+    if not only or "ppo_procgen" in only:
+        atari_envpool("ppo_procgen_n8_t16_seed2.npz",
+                      ["--no-cuda", "--num-envs", "8", "--num-steps", "16", "--total-timesteps", "384", "--seed", "2",
+                       "--num-minibatches", "4", "--update-epochs", "2"], 3, script="ppo_procgen.py")
     if "ppo_atari_full" in only:
         # ~3 CPU-minutes: generated on request only (python -m oracle.make_golden ppo_atari_full)
         atari_envpool_full("ppo_atari_envpool_n1024_t128_seed1.npz",

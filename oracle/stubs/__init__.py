@@ -75,10 +75,56 @@ class _SyncVectorEnv:
         return env
 
 
+class _DictObsProcgen:
+    """procgen.ProcgenEnv stand-in: observations are dicts {"rgb": uint8 [N, 64, 64, 3]} until the script's own
+    gym.wrappers.TransformObservation(envs, lambda obs: obs["rgb"]) unwraps them (cleanrl/ppo_procgen.py:176-178)."""
+
+    def __init__(self, num_envs, env_name="starpilot", num_levels=0, start_level=0, distribution_mode="easy", **kw):
+        self.env = S.SyntheticProcgenVec(num_envs, seed=CONFIG.get("procgen_seed", 0))
+        self.num_envs = num_envs
+        self.action_space = self.env.action_space
+        self.observation_space = {"rgb": self.env.observation_space}
+        LAST_ENVS.append(self.env)
+
+    def reset(self, **kw):
+        return {"rgb": self.env.reset()}
+
+    def step(self, action):
+        o, r, d, info = self.env.step(action)
+        return {"rgb": o}, r, d, info
+
+    def close(self):
+        pass
+
+
+class _TransformObservation(_Wrapper):
+    def __init__(self, env, f):
+        super().__init__(env)
+        self.f = f
+
+    def reset(self, **kwargs):
+        return self.f(self.env.reset(**kwargs))
+
+    def step(self, action):
+        o, r, d, info = self.env.step(action)
+        return self.f(o), r, d, info
+
+
+class _PassThrough(_Wrapper):
+    def __init__(self, env, *a, **k):
+        super().__init__(env)
+
+
 def install():
     gym = types.ModuleType("gym")
     gym.Wrapper = _Wrapper
     gym.spaces = _spaces_module("gym.spaces")
+    gym.wrappers = types.ModuleType("gym.wrappers")
+    gym.wrappers.TransformObservation = _TransformObservation
+    for w in ("RecordEpisodeStatistics", "RecordVideo", "NormalizeReward", "TransformReward"):
+        setattr(gym.wrappers, w, _PassThrough)      # reward normalisation is host-side env code, identity in the fixtures
+    procgen = types.ModuleType("procgen")
+    procgen.ProcgenEnv = _DictObsProcgen
     envpool = types.ModuleType("envpool")
     envpool.make = _envpool_make
 
@@ -99,7 +145,7 @@ def install():
     gymn.ActionWrapper = _Wrapper
 
     mods = {
-        "gym": gym, "gym.spaces": gym.spaces, "envpool": envpool,
+        "gym": gym, "gym.spaces": gym.spaces, "gym.wrappers": gym.wrappers, "procgen": procgen, "envpool": envpool,
         "gymnasium": gymn, "gymnasium.spaces": gymn.spaces,
         "gymnasium.vector": gymn.vector, "gymnasium.wrappers": gymn.wrappers,
     }
@@ -109,6 +155,6 @@ def install():
 
 
 def uninstall():
-    for k in ("gym", "gym.spaces", "envpool", "gymnasium", "gymnasium.spaces",
+    for k in ("gym", "gym.spaces", "gym.wrappers", "procgen", "envpool", "gymnasium", "gymnasium.spaces",
               "gymnasium.vector", "gymnasium.wrappers"):
         sys.modules.pop(k, None)

@@ -86,7 +86,8 @@ def test_product_never_imports_oracle():
 @pytest.mark.parametrize("script,factory", [
     ("ppo.py", "ppo_args"), ("ppo_atari.py", "ppo_atari_args"), ("ppo_atari_envpool.py", "ppo_atari_envpool_args"),
     ("ppo_atari_multigpu.py", "ppo_atari_multigpu_args"), ("ppo_continuous_action.py", "ppo_continuous_action_args"),
-    ("dqn_atari.py", "dqn_atari_args")])
+    ("dqn_atari.py", "dqn_atari_args"), ("ppo_procgen.py", "ppo_procgen_args"),
+    ("ppo_atari_lstm.py", "ppo_atari_args")])
 def test_cli_fields_match_reference_args(script, factory):
     """Every reference flag exists with the same default and help text (reference Args dataclasses)."""
     import ast
