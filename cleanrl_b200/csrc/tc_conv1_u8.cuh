@@ -57,6 +57,15 @@ __device__ __forceinline__ void tmem_st32(uint32_t taddr, const uint32_t (&v)[32
         "r"(v[28]), "r"(v[29]), "r"(v[30]), "r"(v[31])
         : "memory");
 }
+__device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t (&v)[16]) {
+    asm volatile(
+        "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16};" ::"r"(taddr),
+        "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]), "r"(v[8]), "r"(v[9]),
+        "r"(v[10]), "r"(v[11]), "r"(v[12]), "r"(v[13]), "r"(v[14]), "r"(v[15])
+        : "memory");
+}
+__device__ __forceinline__ void tmem_st_cols(uint32_t taddr, const uint32_t (&v)[32]) { tmem_st32(taddr, v); }
+__device__ __forceinline__ void tmem_st_cols(uint32_t taddr, const uint32_t (&v)[16]) { tmem_st16(taddr, v); }
 __device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 
 constexpr uint64_t kDescSwizzle64 = 4ull << 61;      // LayoutType::SWIZZLE_64B
@@ -373,6 +382,8 @@ struct Conv1WgradU8Params {
     int64_t rows_per_cta;      // multiple of 128 grid rows (M = n * 512)
     float* ws;
     float* wsb;
+    int dbg;                   // stage knock-out (B200RL_DBG_CONV1W): 1 = no uint8 -> fp16 conversion, 2 = no TMA, 4 = no MMAs,
+                               // 8 = no bias sums; results are then garbage by construction
 };
 // X blocks (8 KB: 64 channels x 128 positions) and dY steps (8 KB) in flight: 176 KB per SM.  With 80 KB (6 + 4 stages) every
 // role of the kernel spent its time waiting on the TMA barriers at 41 % of the HBM bandwidth: the gather reads need ~3 us of
@@ -386,13 +397,13 @@ __device__ __forceinline__ uint32_t prmt(uint32_t a, uint32_t b, uint32_t sel) {
     asm("prmt.b32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(sel));
     return d;
 }
-// 68 pixels (17 words starting at byte offset B of W[0]) -> 34 fp16 pairs H with value 1024 + x (bytes (x, 0x64) are the
+// 2 NH pixels (NH / 2 words starting at byte offset B of W[0]) -> NH fp16 pairs H with value 1024 + x (bytes (x, 0x64) are the
 // fp16 1024 + x exactly); the 1024 is NOT removed here: sum_r (1024 + x) dY = dW + 1024 sum_r dY, and sum_r dY is the bias
 // partial the same CTA computes anyway, so the drain subtracts 1024 x it (fp32; the offset costs < 1e-5 relative accuracy).
-template <int B>
-__device__ __forceinline__ void u8_to_f16_biased(const uint32_t* W, uint32_t (&H)[34]) {
+template <int B, int NH>
+__device__ __forceinline__ void u8_to_f16_biased(const uint32_t* W, uint32_t (&H)[NH]) {
 #pragma unroll
-    for (int j = 0; j < 17; ++j) {
+    for (int j = 0; j < NH / 2; ++j) {
         uint32_t x = W[j];
         if (B == 1) x = prmt(W[j], W[j + 1], 0x4321u);
         if (B == 2) x = prmt(W[j], W[j + 1], 0x5432u);
@@ -408,7 +419,14 @@ constexpr float kU8Bias = 1024.0f;
 // TMA requests).  Step k of the CTA's contiguous range uses block k and, for the taps' halo (<= 22 positions), the first
 // bytes of block k + 1 -- the next block of the same image, or of the next image after the last step of an image, where
 // the halo only multiplies dY rows that are zero (positions >= 441).  One extra block follows the CTA's last step.
-__global__ void __launch_bounds__(512, 1) tc_conv1_wgrad_u8(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmY,
+// K parts per step: the 128 grid rows of a step are converted by kC1WKParts warps per TMEM lane quarter.  A convert warp's
+// step is a serial chain (wait, 16-byte loads, PRMTs, tcgen05.st, wait::st, arrive); with 2 parts (8 warps) the chain took
+// ~1400 cycles per step although no unit was busy for more than ~330 (stage knock-outs, profiles/r2_knockout_conv1_wgrad.txt);
+// 4 parts (16 warps, 4 per scheduler) overlap the chains.
+constexpr int kC1WKParts = 4;
+constexpr int kC1WConvWarps = 4 * kC1WKParts;
+constexpr int kC1WThreads = (4 + kC1WConvWarps + 4) * 32;
+__global__ void __launch_bounds__(kC1WThreads, 1) tc_conv1_wgrad_u8(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmY,
                                                             const Conv1WgradU8Params p) {
     constexpr int XS = kC1WXStages, YS = kC1WYStages;
     constexpr uint32_t TMEM_COLS = 512, COL_D = 0, COL_A = 64;
@@ -422,9 +440,9 @@ __global__ void __launch_bounds__(512, 1) tc_conv1_wgrad_u8(const __grid_constan
     uint8_t* sYb = smem + (size_t)XS * kC1WBlock;       // YS tiles of 8 KB
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     if (tid == 0) {
-        for (int s = 0; s < XS; ++s) { mbar_init(&xfull[s], 1); mbar_init(&xempty[s], 8); }
+        for (int s = 0; s < XS; ++s) { mbar_init(&xfull[s], 1); mbar_init(&xempty[s], kC1WConvWarps); }
         for (int s = 0; s < YS; ++s) { mbar_init(&yfull[s], 1); mbar_init(&yempty[s], 2 + 4); }
-        for (int b = 0; b < NA; ++b) { mbar_init(&a_full[b], 8); mbar_init(&a_empty[b], 2); }
+        for (int b = 0; b < NA; ++b) { mbar_init(&a_full[b], kC1WConvWarps); mbar_init(&a_empty[b], 2); }
         mbar_init(&done_bar, 2);
         fence_barrier_init();
         tma_prefetch_desc(&tmX);
@@ -457,13 +475,19 @@ __global__ void __launch_bounds__(512, 1) tc_conv1_wgrad_u8(const __grid_constan
                 if (k < nsteps) z_next = image_of(g + 1);
                 const int xs = k % XS;
                 if (k >= XS) mbar_wait(&xempty[xs], ((k / XS) - 1) & 1);
-                mbar_arrive_expect_tx(&xfull[xs], (uint32_t)kC1WBlock);
-                tma_load_3d(smem_u32(sX + (size_t)xs * kC1WBlock), &tmX, (int)(g & 3) * 128, 0, z, &xfull[xs]);
+                if (p.dbg & 2) mbar_arrive(&xfull[xs]);
+                else {
+                    mbar_arrive_expect_tx(&xfull[xs], (uint32_t)kC1WBlock);
+                    tma_load_3d(smem_u32(sX + (size_t)xs * kC1WBlock), &tmX, (int)(g & 3) * 128, 0, z, &xfull[xs]);
+                }
                 if (k < nsteps) {
                     const int ys = k % YS;
                     if (k >= YS) mbar_wait(&yempty[ys], ((k / YS) - 1) & 1);
-                    mbar_arrive_expect_tx(&yfull[ys], (uint32_t)kC1WYBytes);
-                    tma_load_3d(smem_u32(sYb + (size_t)ys * kC1WYBytes), &tmY, 0, (int)(g & 3) * 128, (int)(g >> 2), &yfull[ys]);
+                    if (p.dbg & 2) mbar_arrive(&yfull[ys]);
+                    else {
+                        mbar_arrive_expect_tx(&yfull[ys], (uint32_t)kC1WYBytes);
+                        tma_load_3d(smem_u32(sYb + (size_t)ys * kC1WYBytes), &tmY, 0, (int)(g & 3) * 128, (int)(g >> 2), &yfull[ys]);
+                    }
                 }
             }
         }
@@ -483,9 +507,11 @@ __global__ void __launch_bounds__(512, 1) tc_conv1_wgrad_u8(const __grid_constan
                 const uint32_t y_lo = ((smem_u32(sYb + (size_t)ys * kC1WYBytes) & 0x3FFFFu) >> 4) | desc_lo_flags;
                 const uint32_t a_col = tmem0 + COL_A + (uint32_t)(buf * 128 + j * 64);     // COL_A + NA * 128 = 448 <= 512
 #pragma unroll
-                for (int kk = 0; kk < 8; ++kk)
+                for (int kk = 0; kk < 8; ++kk) {
+                    if (p.dbg & 4) break;
                     umma_f16_ts(tmem0 + COL_D + (uint32_t)(j * 32), a_col + 8 * kk, desc_hi | (uint64_t)(y_lo + 64 * kk), idesc,
                                 (it | kk) != 0 ? 1u : 0u);
+                }
                 umma_commit(&yempty[ys]);
                 umma_commit(&a_empty[buf]);
             }
@@ -493,13 +519,15 @@ __global__ void __launch_bounds__(512, 1) tc_conv1_wgrad_u8(const __grid_constan
         }
         if (leader) umma_commit(&done_bar);
         __syncwarp();
-    } else if (warp >= 4 && warp < 12) {
+    } else if (warp >= 4 && warp < 4 + kC1WConvWarps) {
         // ======================= convert warps: uint8 channel rows -> fp16 pairs -> tensor memory
-        const int q = warp & 3, kh = (warp - 4) >> 2;
+        constexpr int KP = kC1WKParts, CW = 64 / KP;        // CW TMEM columns (2 CW grid rows) per warp and tile
+        constexpr int NCH = 2 * CW / 16 + 1, NH = CW + 2;   // 16-byte chunks loaded; fp16 pairs converted (one spare pair)
+        const int q = warp & 3, kp = (warp - 4) >> 2;
         const int tapslot = q >> 1;
         const int c = (q & 1) * 32 + lane;
-        const uint32_t lane_base = tmem0 + COL_A + ((uint32_t)(q * 32) << 16) + (uint32_t)(kh * 32);
-        const int chunk0 = tapslot + kh * 4;               // first 16-byte chunk this thread needs (tapslot 1 starts at byte 16)
+        const uint32_t lane_base = tmem0 + COL_A + ((uint32_t)(q * 32) << 16) + (uint32_t)(kp * CW);
+        const int chunk0 = tapslot + kp * (2 * CW / 16);   // first 16-byte chunk this thread needs (tapslot 1 starts at byte 16)
         const uint32_t row_off = (uint32_t)c * 128u, sw = (uint32_t)(c & 7);
         for (int it = 0; it < nsteps; ++it) {
             const int xm = it % XS, xh = (it + 1) % XS, buf = it % NA;
@@ -507,9 +535,9 @@ __global__ void __launch_bounds__(512, 1) tc_conv1_wgrad_u8(const __grid_constan
             mbar_wait(&xfull[xh], ((it + 1) / XS) & 1);
             const uint8_t* bm = sX + (size_t)xm * kC1WBlock + row_off;
             const uint8_t* bh = sX + (size_t)xh * kC1WBlock + row_off;
-            uint32_t W[24];
+            uint32_t W[4 * NCH];
 #pragma unroll
-            for (int v = 0; v < 6; ++v) {
+            for (int v = 0; v < NCH; ++v) {
                 const int ci = chunk0 + v;
                 const uint8_t* src = (ci < 8 ? bm : bh) + ((((uint32_t)ci & 7u) ^ sw) << 4);
                 const int4 t = *reinterpret_cast<const int4*>(src);
@@ -517,28 +545,31 @@ __global__ void __launch_bounds__(512, 1) tc_conv1_wgrad_u8(const __grid_constan
             }
             __syncwarp();
             if (lane == 0) mbar_arrive(&xempty[xm]);               // block `it` was halo of step it-1 and main of step it: done
-            // tile 0 = first tap of the slot (shift 0 / 21): pixels k .. k + 63 of this K half; tile 1 = second tap (shift 1 /
-            // 22) = the same stream one pixel later: its pair m is (high half of H[m], low half of H[m + 1]).  tapslot 1 reads
-            // from byte 16, so its stream starts 5 bytes in: word 1, byte 1.
-            uint32_t H[34];
-            if (tapslot == 0) u8_to_f16_biased<0>(W, H); else u8_to_f16_biased<1>(W + 1, H);
+            // tile 0 = first tap of the slot (shift 0 / 21): pixels k .. k + 2 CW - 1 of this K part; tile 1 = second tap
+            // (shift 1 / 22) = the same stream one pixel later: its pair m is (high half of H[m], low half of H[m + 1]).
+            // tapslot 1 reads from byte 16, so its stream starts 5 bytes in: word 1, byte 1.
+            uint32_t H[NH];
+            if (p.dbg & 1) {
+#pragma unroll
+                for (int m = 0; m < NH; ++m) H[m] = W[m % (4 * NCH)];
+            } else if (tapslot == 0) u8_to_f16_biased<0, NH>(W, H); else u8_to_f16_biased<1, NH>(W + 1, H);
             if (it >= NA) mbar_wait(&a_empty[buf], ((it / NA) - 1) & 1);
             tc_fence_after_sync();
-            uint32_t o[32];
+            uint32_t o[CW];
 #pragma unroll
-            for (int m = 0; m < 32; ++m) o[m] = H[m];
-            tmem_st32(lane_base + (uint32_t)(buf * 128), o);
+            for (int m = 0; m < CW; ++m) o[m] = H[m];
+            tmem_st_cols(lane_base + (uint32_t)(buf * 128), o);
 #pragma unroll
-            for (int m = 0; m < 32; ++m) o[m] = prmt(H[m], H[m + 1], 0x5432u);
-            tmem_st32(lane_base + (uint32_t)(buf * 128 + 64), o);
+            for (int m = 0; m < CW; ++m) o[m] = (p.dbg & 1) ? H[m + 1] : prmt(H[m], H[m + 1], 0x5432u);
+            tmem_st_cols(lane_base + (uint32_t)(buf * 128 + 64), o);
             tmem_st_wait();
             tc_fence_before_sync();
             __syncwarp();
             if (lane == 0) mbar_arrive(&a_full[buf]);
         }
-    } else if (warp >= 12) {
+    } else if (warp >= 4 + kC1WConvWarps) {
         // ======================= dY warps: bias gradient = column sums of dY from the staged tiles (fp32, fixed order)
-        const int tb = tid - 384;
+        const int tb = tid - (4 + kC1WConvWarps) * 32;
         const int rq = tb >> 2, c16 = tb & 3;
         float bsum[8];
 #pragma unroll
@@ -549,6 +580,7 @@ __global__ void __launch_bounds__(512, 1) tc_conv1_wgrad_u8(const __grid_constan
             const uint8_t* sY = sYb + (size_t)ys * kC1WYBytes;
 #pragma unroll
             for (int ps = 0; ps < 4; ++ps) {
+                if (p.dbg & 8) break;
                 const int rr = ps * 32 + rq;
                 const int4 v = *reinterpret_cast<const int4*>(sY + img64_off(rr, c16));
                 const uint32_t w[4] = {(uint32_t)v.x, (uint32_t)v.y, (uint32_t)v.z, (uint32_t)v.w};
@@ -615,7 +647,10 @@ static int launch_conv1_wgrad_u8(const Conv1WgradU8Params& p, const void* frames
     // rows: box [128 rows][64 B], SWIZZLE_64B
     if ((rc = make_tmap_3d_u8(&tmX, frames_cm, n_images, 64, 448, 448, 64, 128, what))) return rc;
     if ((rc = make_tmap_3d_u8(&tmY, dact1_f16, p.n, 441, 64, 64, 128, 64, what))) return rc;
-    tc_conv1_wgrad_u8<<<ctas, 512, smem, s>>>(tmX, tmY, p);
+    static const int dbg = getenv("B200RL_DBG_CONV1W") ? atoi(getenv("B200RL_DBG_CONV1W")) : 0;
+    Conv1WgradU8Params q = p;
+    q.dbg = dbg;
+    tc_conv1_wgrad_u8<<<ctas, kC1WThreads, smem, s>>>(tmX, tmY, q);
     return check_launch(what);
 }
 

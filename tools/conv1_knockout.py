@@ -1,6 +1,7 @@
-"""Bottleneck analysis of the uint8 conv1 forward kernel: time it with pipeline stages knocked out (B200RL_DBG_CONV1 bit
-mask: 1 = no global stores, 2 = no TMA loads, 4 = no MMAs) and with / without the minibatch row gather.
-Each configuration runs in a fresh process (the flag is read once).   python tools/conv1_knockout.py [M]"""
+"""Bottleneck analysis of the uint8 conv1 kernels: time them with pipeline stages knocked out.
+  forward  (B200RL_DBG_CONV1  bits): 1 = no global stores, 2 = no TMA loads, 4 = no MMAs
+  wgrad    (B200RL_DBG_CONV1W bits): 1 = no uint8 -> fp16 conversion, 2 = no TMA loads, 4 = no MMAs, 8 = no bias sums
+Each configuration runs in a fresh process (the flag is read once).   python tools/conv1_knockout.py [M] [fwd|wgrad]"""
 import json
 import os
 import subprocess
@@ -23,29 +24,42 @@ B = 4 * M if gather else M
 rm = ops.alloc_u8_rollout_rows((B, 441, 64), dev); rm.random_(0, 256)
 rows = torch.randperm(B, device=dev)[:M].sort().values.contiguous() if gather else None
 lib = ops._lib.load()
-for _ in range(3): agent._forward_heads(rm, rows=rows)
+which = sys.argv[3]
+cm = torch.empty((B, 64, 448), dtype=torch.uint8, device=dev).random_(0, 256)
+dhead, dl, dv = agent.alloc_head_grad(M, dev); dhead.normal_(0, 1e-3)
+def go():
+    agent._forward_heads(rm, rows=rows, keep=(which == "wgrad"), aux=cm)
+    if which == "wgrad": agent.backward(dhead)
+for _ in range(3): go()
 torch.cuda.synchronize()
 lib.b200rl_profile_reset(); lib.b200rl_profile_enable(1)
-for _ in range(10): agent._forward_heads(rm, rows=rows)
+for _ in range(10): go()
 torch.cuda.synchronize(); lib.b200rl_profile_enable(0)
 import ctypes
 buf = ctypes.create_string_buffer(1 << 16); lib.b200rl_profile_summary(buf, 1 << 16)
-r = [x for x in json.loads(buf.value.decode()) if x["name"] == "conv1_fwd"][0]
+r = [x for x in json.loads(buf.value.decode()) if x["name"] == ("conv1_fwd" if which == "fwd" else "conv1_wgrad")][0]
 print(json.dumps({"us": 1e3 * r["ms"] / r["launches"]}))
 ''' % ROOT
 
 M = sys.argv[1] if len(sys.argv) > 1 else "32768"
+which = sys.argv[2] if len(sys.argv) > 2 else "fwd"
 out = []
-for gather in ("1", "0"):
-    for dbg in (0, 1, 2, 4, 3, 6, 7):
-        env = dict(os.environ, B200RL_DBG_CONV1=str(dbg))
-        r = subprocess.run([sys.executable, "-c", WORKER, M, gather], env=env, capture_output=True, text=True)
+configs = (0, 1, 2, 4, 3, 6, 7) if which == "fwd" else (0, 1, 2, 4, 8, 9, 3, 6, 15)
+if os.environ.get("KNOCKOUT_CONFIGS"):
+    configs = tuple(int(x) for x in os.environ["KNOCKOUT_CONFIGS"].split(","))
+var = "B200RL_DBG_CONV1" if which == "fwd" else "B200RL_DBG_CONV1W"
+for gather in ("1",) if which == "wgrad" else ("1", "0"):
+    for dbg in configs:
+        env = dict(os.environ, **{var: str(dbg)})
+        r = subprocess.run([sys.executable, "-c", WORKER, M, gather, which], env=env, capture_output=True, text=True)
         try:
             us = json.loads(r.stdout.strip().splitlines()[-1])["us"]
         except Exception:
             us = None
             print(r.stderr[-500:])
-        names = [n for b, n in ((1, "no-store"), (2, "no-tma"), (4, "no-mma")) if dbg & b] or ["full"]
+        labels = ((1, "no-store"), (2, "no-tma"), (4, "no-mma")) if which == "fwd" else \
+            ((1, "no-convert"), (2, "no-tma"), (4, "no-mma"), (8, "no-bias-sums"))
+        names = [n for b, n in labels if dbg & b] or ["full"]
         out.append({"gather": gather == "1", "dbg": dbg, "config": "+".join(names), "us": us})
         print(out[-1], flush=True)
 print(json.dumps(out))

@@ -24,6 +24,9 @@ ALGO = {
     "conv2_dgrad": (7744 + 14112) * 2 + 1600, "conv3_wgrad": (5184 + 5184) * 2, "conv2_wgrad": (12800 + 6400) * 2,
     "conv1_wgrad": (28224 + 14112) * 2, "fc_wgrad": (3136 + 512) * 2,
 }
+# uint8 rollout (round 2): conv1 reads the frames as bytes (row-major 28224 B forward, channel-major 28672 B for the
+# weight gradient whose dY operand is fp16)
+ALGO_U8 = {"conv1_fwd": 28224 + 12800 * 2 + 1600, "conv1_wgrad": 28672 + 14112 * 2}
 
 
 def to_bytes(v, unit):
@@ -43,7 +46,8 @@ def main():
     col = {h: i for i, h in enumerate(hdr)}
     seen = {}
     kernels = []
-    n_rows = None
+    u8 = any("tc_conv1_i8" in r[col["Kernel Name"]] for r in data)
+    algo = dict(ALGO, **ALGO_U8) if u8 else ALGO
     for r in data:
         name = r[col["Kernel Name"]]
         short = name.split("(")[0].replace("void ", "").replace("b200rl::", "").replace("(int)", "")
@@ -51,11 +55,13 @@ def main():
         k = seen.get(short, 0)
         seen[short] = k + 1
         layer = None
-        if short.startswith("tc_conv_win<32"): layer = "conv1_fwd"
+        if short.startswith("tc_conv1_i8"): layer = "conv1_fwd"
+        elif short.startswith("tc_conv1_wgrad_u8"): layer = "conv1_wgrad"
+        elif short.startswith("tc_conv_win<32"): layer = "conv1_fwd"
         elif short.startswith("tc_conv_win<64, 2"): layer = "conv2_fwd"
         elif short.startswith("tc_conv_win<64, 1"): layer = "conv3_fwd" if k % 2 == 0 else "conv3_dgrad"
         elif short.startswith("tc_conv_win<128"): layer = "conv2_dgrad"
-        elif short.startswith("tc_wgrad_win"): layer = ["conv3_wgrad", "conv2_wgrad", "conv1_wgrad"][k % 3]
+        elif short.startswith("tc_wgrad_win"): layer = ["conv3_wgrad", "conv2_wgrad", "conv1_wgrad"][k % (2 if u8 else 3)]
         elif short.startswith("tc_gemm_tma<256"): layer = "fc_fwd" if k % 2 == 0 else "fc_dgrad"
         elif short.startswith("tc_wgrad_tma"): layer = "fc_wgrad"
         e = {"id": int(r[col["ID"]]), "kernel": short, "layer": layer, "grid": grid,
@@ -68,7 +74,7 @@ def main():
              "issue_active_pct": float(r[col[METRICS[10]]])}
         kernels.append(e)
     json.dump({"source": "ncu --set full --clock-control none --profile-from-start off python tools/profile_update.py "
-                         "32768 1 s2d (one minibatch update at M=32768 + one rollout step at N=1024; under the "
+                         "32768 1 [s2d|u8s2d] (one minibatch update at M=32768 + one rollout step at N=1024; under the "
                          "profiler: cold caches, serialised launches)", "kernels": kernels}, open(out, "w"), indent=1)
     if len(sys.argv) > 3:
         n = int(sys.argv[4]) if len(sys.argv) > 4 else 32768
@@ -77,7 +83,7 @@ def main():
         for e in kernels:
             if e["layer"] and e["layer"] not in tr and e["time_us"] > 60:      # the n = 32768 launch, not the rollout one
                 tr[e["layer"]] = {"n": n, "dram_bytes": e["dram_read_bytes"] + e["dram_write_bytes"],
-                                  "algorithmic_bytes": ALGO[e["layer"]] * n, "kernel": e["kernel"],
+                                  "algorithmic_bytes": algo[e["layer"]] * n, "kernel": e["kernel"],
                                   "time_us_under_ncu": e["time_us"]}
         json.dump(tr, open(sys.argv[3], "w"), indent=1)
     for e in kernels:

@@ -69,8 +69,16 @@ def minibatch(step):
     agent.params_updated()
 
 
+roll_rm = ops.alloc_u8_rollout_rows((1024, 441, 64), dev) if fmt == "u8s2d" else None
+roll_cm = torch.empty((1024, 64, 448), dtype=torch.uint8, device=dev) if fmt == "u8s2d" else None
+
+
 def rollout_step():
-    agent.get_action_and_value(obs_roll)
+    if fmt == "u8s2d":               # what PPOEngine.policy_step launches: frame conversion into the slot, then the forward
+        ops.frames_to_s2d_u8(obs_roll, roll_rm, roll_cm)
+        agent.get_action_and_value(roll_rm)
+    else:
+        agent.get_action_and_value(obs_roll)
 
 
 for i in range(2):
