@@ -451,13 +451,13 @@ extern "C" int b200rl_naturecnn_bf16_backward(const void* obs, const void* obs_a
         // uint8 channel-major frames -> fp16 in registers -> tensor memory (tc_conv1_u8.cuh); 1 CTA per SM (512 TMEM columns)
         Conv1WgradU8Params cw;
         memset(&cw, 0, sizeof(cw));
-        const WPlan pl = wgrad_plan(n * 512, kC2Ctas, 128);
+        const WPlan pl = wgrad_plan(n * 512, kC2Ctas, 512);          // whole images per CTA
         cw.rows = rows; cw.n = (int)n; cw.rows_per_cta = pl.rows_per_cta; cw.ws = wsbig; cw.wsb = wssmall;
         { ProfScope ps(s, "conv1_wgrad", 2.0 * n * 400 * 32 * 256, (double)n * (28672 + 14112 * 2));
           if ((rc = launch_conv1_wgrad_u8(cw, obs_aux, rows ? (int64_t)1 << 24 : n, act + Q.dact1, pl.splits, s, "naturecnn/conv1_wgrad_u8"))) return rc; }
         memset(&fw, 0, sizeof(fw));
         fw.layer = 1; fw.S = pl.splits; fw.nslots = 4; fw.Cout = 32; fw.scale = 1.0f / 255.0f / kDact1Scale; fw.bscale = 1.0f / kDact1Scale;
-        const int st1[4] = {0, 2, 1, 3};               // ws rows: tile j, lane m -> tap 2 (m >> 6) + j
+        const int st1[4] = {0, 1, 2, 3};               // ws rows: tile b, lane m -> tap 2 b + (m >> 6)
         for (int k = 0; k < 4; ++k) fw.slot_tap[k] = st1[k];
         { ProfScope ps(s, "wgrad_fold_bias", 0, 0);
           fw.wsb = wssmall; fw.db = grads + L.c1b;

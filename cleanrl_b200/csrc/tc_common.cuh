@@ -37,15 +37,36 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
         : "memory");
     return ok != 0;
 }
-// Bounded wait: a protocol bug must surface as a launch failure (trap), never as a hung GPU.
+// Bounded wait: a protocol bug must surface as a launch failure (trap), never as a hung GPU.  The bound is counted on the
+// SM's own cycle counter: reading %globaltimer inside the spin loop (round 1) costs several hundred cycles per poll, which
+// became the period of every tight producer/consumer handshake (stage knock-outs of tc_conv1_wgrad_u8: 850 cycles per step
+// with every stage switched off).
+#ifndef B200RL_WAIT_MODE
+#define B200RL_WAIT_MODE 0
+#endif
+__device__ __forceinline__ bool mbar_try_wait_hint(uint64_t* bar, uint32_t parity, uint32_t ns) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}\n"
+        : "=r"(ok)
+        : "r"(smem_u32(bar)), "r"(parity), "r"(ns)
+        : "memory");
+    return ok != 0;
+}
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
     if (mbar_try_wait(bar, parity)) return;
-    uint64_t t0;
-    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t0));
+    const long long t0 = clock64();
+#if B200RL_WAIT_MODE == 1
+    while (!mbar_try_wait_hint(bar, parity, 1000000u)) {
+#elif B200RL_WAIT_MODE == 2
     while (!mbar_try_wait(bar, parity)) {
-        uint64_t t1;
-        asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t1));
-        if (t1 - t0 > 4000000000ull) __trap();      // 4 s without progress
+        __nanosleep(40);
+#else
+    while (!mbar_try_wait(bar, parity)) {
+#endif
+        if (clock64() - t0 > (1ll << 33)) __trap();      // ~4 s without progress
     }
 }
 

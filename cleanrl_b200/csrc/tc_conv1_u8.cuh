@@ -15,11 +15,12 @@
 //   Same window scheme as tc_conv_win: one TMA box of 128 + 22 rows per tile, the four 2x2 taps are descriptors
 //   shifted by whole 64-byte rows of a SWIZZLE_64B image.
 //
-// Weight gradient  tc_conv1_wgrad_u8: dW^T[(tap, c), co] = sum_r X[r + shift_tap, c] * dY[r, co].  The pixels go
+// Weight gradient  tc_conv1_wgrad_u8: dW[tap, c, co] = sum_p X[p + off_tap, c] * dY[p, co].  The pixels go
 //   uint8 (shared memory, channel-major TMA box) -> fp16 pairs in REGISTERS (one PRMT per two pixels builds
-//   1024 + x, one HSUB2 removes the 1024) -> tensor memory (tcgen05.st), and are consumed as the A operand
-//   straight from TMEM (tcgen05.mma with A in TMEM); dY rows are a SWIZZLE_64B TMA box used as an MN-major B
-//   operand with N = 32.  No 16-bit image of the frames ever exists in shared or global memory.
+//   1024 + x; the offset is removed once per CTA through the bias partial) -> tensor memory (tcgen05.st), and are
+//   consumed as the A operand straight from TMEM (tcgen05.mma with A in TMEM); dY rows are SWIZZLE_64B TMA boxes used
+//   as an MN-major B operand with N = 32, loaded at two row offsets (0 and -21) so that one A tile serves all four
+//   taps.  No 16-bit image of the frames ever exists in shared or global memory.
 #pragma once
 #include "tc_base.cuh"
 #include <cuda_fp16.h>
@@ -170,8 +171,6 @@ struct Conv1U8Params {
     const float* bias;       // [32]
     bf16* out;               // act1 as 2x2 cells [n,100,128]
     uint32_t* mask_out;      // act1 > 0 bits: [n,100 cells] x 4 words
-    int dbg;                 // stage knock-out for bottleneck analysis (B200RL_DBG_CONV1): 1 = no global stores, 2 = no TMA
-                             // loads, 4 = no MMAs; results are then garbage by construction
 };
 
 // Pair rows: TMA delivers one shared-memory row (<= 128 B) per request at ~5.5 cycles per request and SM -- the rate at
@@ -181,7 +180,7 @@ struct Conv1U8Params {
 // 139 pair rows per 256 output positions.  GEMM rows are pair rows; the even and the odd position of each pair get their own
 // accumulator, and a tap (dy, dx) of position p = 2q + e is the 64-byte half ((e + dx + dy) & 1) of pair row
 // q + (e + 21 dy + dx) / 2 -- a K-major SWIZZLE_128B descriptor shifted by whole rows plus a 64-byte K offset.
-template <int STAGES>
+template <int STAGES, int DBG>
 __global__ void __launch_bounds__(kConvWinThreads, 1) tc_conv1_i8(const __grid_constant__ CUtensorMap tmA, const Conv1U8Params p, int total_tiles) {
     constexpr int BN = 64, WR = 144, NTAPS = 4;
     constexpr int STAGE_BYTES = WR * 128;           // 18432 = 18 x 1024
@@ -239,7 +238,7 @@ __global__ void __launch_bounds__(kConvWinThreads, 1) tc_conv1_i8(const __grid_c
                     z_next = p.rows ? (int)__ldg(p.rows + img) : img;
                 }
                 if (q >= (uint32_t)STAGES) mbar_wait(&empty_bar[s], ((q / STAGES) - 1) & 1);
-                if (p.dbg & 2) { mbar_arrive(&full_bar[s]); continue; }
+                if (DBG & 2) { mbar_arrive(&full_bar[s]); continue; }
                 mbar_arrive_expect_tx(&full_bar[s], (uint32_t)STAGE_BYTES);
                 tma_load_3d(smem_u32(sRing + (size_t)s * STAGE_BYTES), &tmA, 0, (tile & 1) * 128, z, &full_bar[s]);
             }
@@ -270,7 +269,7 @@ __global__ void __launch_bounds__(kConvWinThreads, 1) tc_conv1_i8(const __grid_c
                     const uint32_t d_addr = tmem_d + acc * BN;
 #pragma unroll
                     for (int t = 0; t < NTAPS; ++t) {
-                        if (p.dbg & 4) break;
+                        if (DBG & 4) break;
                         const int po = e + off[t];
                         const uint32_t a_lo = win_lo + (uint32_t)((po >> 1) * 8 + (po & 1) * 4);      // rows of 128 B, halves of 64 B
                         const uint32_t b_lo = w_lo + (uint32_t)((t * B_CHUNK) >> 4);
@@ -331,7 +330,7 @@ __global__ void __launch_bounds__(kConvWinThreads, 1) tc_conv1_i8(const __grid_c
                 pk[c4 >> 1] = pack_bf16x2_relu(f0, f1);
                 pk[(c4 >> 1) + 1] = pack_bf16x2_relu(f2, f3);
             }
-            if (valid && !(p.dbg & 1)) p.mask_out[cell * 4 + cls] = bits;
+            if (valid && !(DBG & 1)) p.mask_out[cell * 4 + cls] = bits;
             // Stores: a lane owns one output row (64 B at its own 2x2-cell address), so a direct 16-byte store instruction of
             // the warp touches 32 different lines = 32 L1 wavefronts -- measured, the epilogue's global stores took more of
             // the L1 data pipe than the MMAs' operand reads.  The rows go through a per-warp staging tile instead (XOR
@@ -352,7 +351,7 @@ __global__ void __launch_bounds__(kConvWinThreads, 1) tc_conv1_i8(const __grid_c
                 const int R = (lane >> 2) + 8 * i2, c = lane & 3;
                 const int unit = reinterpret_cast<const int*>(stg + 2048)[R];
                 const int4 v = *reinterpret_cast<const int4*>(stg + R * 64 + ((((uint32_t)c) ^ ((uint32_t)(R >> 1) & 3u)) << 4));
-                if (unit >= 0 && !(p.dbg & 1)) *reinterpret_cast<int4*>(reinterpret_cast<uint8_t*>(p.out) + (int64_t)unit * 64 + c * 16) = v;
+                if (unit >= 0 && !(DBG & 1)) *reinterpret_cast<int4*>(reinterpret_cast<uint8_t*>(p.out) + (int64_t)unit * 64 + c * 16) = v;
             }
             __syncwarp();
         }
@@ -363,33 +362,44 @@ __global__ void __launch_bounds__(kConvWinThreads, 1) tc_conv1_i8(const __grid_c
 }
 
 // ------------------------------------------------------------------------------------ conv1 weight gradient (uint8 frames -> TMEM)
-// dW^T[(tap, c), co] = sum_r X[r + shift_tap, c] * dY[r, co] over the grid rows r of a step of 128 rows (4 steps per image).
-//   X   : channel-major frames [img][64 ch][448 rows] u8, staged in blocks of 128 positions (SWIZZLE_128B boxes of 64 full
-//         lines; 16-byte reads of 32 consecutive channel rows are bank-conflict free through the swizzle).
-//   dY  : d(act1) on the 21x21 grid, fp16 [img][441][32] scaled by 2^12 (written by conv2's data gradient with a
-//         saturating conversion): one SWIZZLE_64B TMA box of 128 rows per step = MN-major B operand, N = 32.
-//   A   : 2 M-tiles of 128 lanes; lane m of tile j = (tap = 2 (m >> 6) + j, channel m & 63); K = the 128 rows of the step
-//         = 64 TMEM columns per tile, double-buffered.  Eight convert warps (lane quadrant = warp % 4, K half = warp / 4)
-//         read their channel's bytes with 16-byte loads, funnel-shift the first tap's window (PRMT), expand uint8 -> fp16 with
-//         one PRMT per two pixels (bytes (x, 0x64) = fp16 1024 + x; the offset is taken out again through the bias partial),
-//         derive the second tap's window (one pixel later) with one PRMT per pair, and tcgen05.st both into tensor memory.
-//   Two issuer warps (one per M-tile) run tcgen05.mma with A in TMEM; four more warps accumulate the bias gradient
+// dW[tap, c, co] = sum_p X[p + off_tap, c] * dY[p, co] over the grid positions p of an image, off = {0, 1, 21, 22}
+// (taps (dy, dx) of the 2x2 window on the 21-wide grid).  Written over k = p + s_b with s_b = {0, 21}:
+//       D_b[(h, c), co] = sum_k X[k + h, c] * dY[k - s_b, co],    tap = 2 b + h.
+//   A  (tensor memory, 128 lanes x 64 columns per step of 128 grid rows k): lanes 0-63 hold channel c of the pixel
+//       stream X[k], lanes 64-127 the same stream one pixel later (h = 1).  ONE tile per step serves all four taps.
+//   B  (shared memory, MN-major SWIZZLE_64B, N = 32): the dY rows of the step, loaded twice by TMA -- rows [k0, k0 + 128)
+//       for b = 0 and rows [k0 - 21, k0 + 107) for b = 1 (negative rows and rows >= 441 are zero-filled by the TMA unit:
+//       images are independent and occupy 512-row slots).  The second box hits L2.
+//   X  : channel-major frames [img][64 ch][448 rows] u8, staged in blocks of 128 positions (SWIZZLE_128B boxes of 64 full
+//        lines; 16-byte reads of 32 consecutive channel rows are bank-conflict free through the swizzle).  The h = 1 stream
+//        needs one pixel of the next block.
+//   dY : d(act1) on the 21x21 grid, fp16 [img][441][32] scaled by 2^12 (written by conv2's data gradient with a
+//        saturating conversion); rows of invalid positions (x = 20 or y = 20) are zero.
+//   Sixteen convert warps (two sets alternating steps; lane quadrant = warp % 4, K half) read their channel's bytes with 16-byte loads, expand
+//   uint8 -> fp16 with one PRMT per two pixels (bytes (x, 0x64) = fp16 1024 + x; the offset is taken out again through the
+//   bias partial) -- the h = 1 warps first funnel-shift by one byte -- and tcgen05.st 32 columns into tensor memory.
+//   Two issuer warps (one per tap group b) run tcgen05.mma with A in TMEM; four more warps accumulate the bias gradient
 //   (column sums of dY) from the staged tiles and drain the accumulators at the end.  Partial tiles go to
-//   ws[cta][256][64] / wsb[cta][64] (first 32 columns used) and are folded in fixed order by tc_fold_win.
+//   ws[cta][256][64] / wsb[cta][64] (first 32 columns used; row = tap * 64 + c) and are folded in fixed order by tc_fold_win.
+//
+// Round-2 history: the first version kept the shift on the A side (four tap tiles = 128 TMEM columns per step, written by
+// the convert warps as two shifted copies) with three A buffers.  Stage knock-outs (tools/conv1_knockout.py, compile-time
+// instantiations) showed 1150 cycles per step against an HBM floor of 625: 540 cycles of pure barrier hand-shake
+// (convert -> issuer -> tcgen05.commit -> convert, only three steps in flight), 330 of conversion ALU and 150 of
+// tcgen05.st/ld.shared, added up rather than overlapped.  Moving the shift to the B side halves the conversions and the
+// tensor-memory writes and leaves room for six A buffers.
 struct Conv1WgradU8Params {
     const int64_t* rows;       // optional image gather (minibatch rows of the rollout)
     int n;                     // images of the minibatch
-    int64_t rows_per_cta;      // multiple of 128 grid rows (M = n * 512)
+    int64_t rows_per_cta;      // multiple of 512 grid rows = whole images (M = n * 512)
     float* ws;
     float* wsb;
-    int dbg;                   // stage knock-out (B200RL_DBG_CONV1W): 1 = no uint8 -> fp16 conversion, 2 = no TMA, 4 = no MMAs,
-                               // 8 = no bias sums; results are then garbage by construction
 };
-// X blocks (8 KB: 64 channels x 128 positions) and dY steps (8 KB) in flight: 176 KB per SM.  With 80 KB (6 + 4 stages) every
-// role of the kernel spent its time waiting on the TMA barriers at 41 % of the HBM bandwidth: the gather reads need ~3 us of
-// loads in flight to cover their latency.
-constexpr int kC1WXStages = 12, kC1WYStages = 10;
-constexpr int kC1WBlock = 64 * 128, kC1WYBytes = 128 * 64;
+// X blocks (8 KB: 64 channels x 128 positions) and dY steps (2 x 8 KB) in flight: 192 KB per SM; the gather reads need ~3 us
+// of loads in flight to cover their latency.
+constexpr int kC1WXStages = 8, kC1WYStages = 8;
+constexpr int kC1WBlock = 64 * 128, kC1WYBox = 128 * 64, kC1WYBytes = 2 * kC1WYBox;
+constexpr int kC1WShift = 21;                     // grid rows between the two tap groups
 constexpr float kDact1Scale = 4096.0f;
 
 __device__ __forceinline__ uint32_t prmt(uint32_t a, uint32_t b, uint32_t sel) {
@@ -398,7 +408,7 @@ __device__ __forceinline__ uint32_t prmt(uint32_t a, uint32_t b, uint32_t sel) {
     return d;
 }
 // 2 NH pixels (NH / 2 words starting at byte offset B of W[0]) -> NH fp16 pairs H with value 1024 + x (bytes (x, 0x64) are the
-// fp16 1024 + x exactly); the 1024 is NOT removed here: sum_r (1024 + x) dY = dW + 1024 sum_r dY, and sum_r dY is the bias
+// fp16 1024 + x exactly); the 1024 is NOT removed here: sum_k (1024 + x) dY = dW + 1024 sum_k dY, and sum_k dY is the bias
 // partial the same CTA computes anyway, so the drain subtracts 1024 x it (fp32; the offset costs < 1e-5 relative accuracy).
 template <int B, int NH>
 __device__ __forceinline__ void u8_to_f16_biased(const uint32_t* W, uint32_t (&H)[NH]) {
@@ -414,35 +424,28 @@ __device__ __forceinline__ void u8_to_f16_biased(const uint32_t* W, uint32_t (&H
 }
 constexpr float kU8Bias = 1024.0f;
 
-// X staging: the channel-major image [64 ch][448 positions] is read in BLOCKS of 128 positions (one SWIZZLE_128B TMA box
-// of 64 rows x 128 B = 64 full lines; boxes with a 22-position halo would straddle two lines per channel and cost twice the
-// TMA requests).  Step k of the CTA's contiguous range uses block k and, for the taps' halo (<= 22 positions), the first
-// bytes of block k + 1 -- the next block of the same image, or of the next image after the last step of an image, where
-// the halo only multiplies dY rows that are zero (positions >= 441).  One extra block follows the CTA's last step.
-// K parts per step: the 128 grid rows of a step are converted by kC1WKParts warps per TMEM lane quarter.  A convert warp's
-// step is a serial chain (wait, 16-byte loads, PRMTs, tcgen05.st, wait::st, arrive); with 2 parts (8 warps) the chain took
-// ~1400 cycles per step although no unit was busy for more than ~330 (stage knock-outs, profiles/r2_knockout_conv1_wgrad.txt);
-// 4 parts (16 warps, 4 per scheduler) overlap the chains.
-constexpr int kC1WKParts = 4;
-constexpr int kC1WConvWarps = 4 * kC1WKParts;
+constexpr int kC1WConvWarps = 16;                // two sets of eight: set s converts the steps it = s (mod 2)
 constexpr int kC1WThreads = (4 + kC1WConvWarps + 4) * 32;
+// DBG (stage knock-outs, tools/conv1_knockout.py): 1 = no uint8 -> fp16 conversion, 2 = no TMA, 4 = no MMAs, 8 = no bias
+// sums, 16 = no tcgen05.st, 32 = no shared-memory loads; results are then garbage by construction.  The product is DBG = 0.
+template <int DBG>
 __global__ void __launch_bounds__(kC1WThreads, 1) tc_conv1_wgrad_u8(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmY,
-                                                            const Conv1WgradU8Params p) {
+                                                                  const Conv1WgradU8Params p) {
     constexpr int XS = kC1WXStages, YS = kC1WYStages;
-    constexpr uint32_t TMEM_COLS = 512, COL_D = 0, COL_A = 64;
+    constexpr int NA = 6;                                 // A-operand buffers in TMEM (64 columns each)
+    constexpr uint32_t TMEM_COLS = 512, COL_D = 0, COL_A = 64;          // COL_A + NA * 64 = 448 <= 512
     extern __shared__ uint8_t smem_raw[];
-    constexpr int NA = 3;                                 // A-operand buffers in TMEM (128 columns each)
     __shared__ uint64_t xfull[XS], xempty[XS], yfull[YS], yempty[YS], a_full[NA], a_empty[NA], done_bar;
     __shared__ uint32_t tmem_base_smem;
     __shared__ float sRed[32 * 32], sBias[32];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     uint8_t* sX = smem;                                 // XS blocks of 8 KB
-    uint8_t* sYb = smem + (size_t)XS * kC1WBlock;       // YS tiles of 8 KB
+    uint8_t* sYb = smem + (size_t)XS * kC1WBlock;       // YS stages of two 8 KB boxes
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     if (tid == 0) {
         for (int s = 0; s < XS; ++s) { mbar_init(&xfull[s], 1); mbar_init(&xempty[s], kC1WConvWarps); }
         for (int s = 0; s < YS; ++s) { mbar_init(&yfull[s], 1); mbar_init(&yempty[s], 2 + 4); }
-        for (int b = 0; b < NA; ++b) { mbar_init(&a_full[b], kC1WConvWarps); mbar_init(&a_empty[b], 2); }
+        for (int b = 0; b < NA; ++b) { mbar_init(&a_full[b], 8); mbar_init(&a_empty[b], 2); }
         mbar_init(&done_bar, 2);
         fence_barrier_init();
         tma_prefetch_desc(&tmX);
@@ -461,7 +464,8 @@ __global__ void __launch_bounds__(kC1WThreads, 1) tc_conv1_wgrad_u8(const __grid
     const int64_t g0 = m_begin >> 7;                       // first global step (4 steps per image)
 
     if (warp == 0) {
-        // ======================= TMA producer: X block k (k = 0 .. nsteps, the last one is halo only) and dY rows of step k
+        // ======================= TMA producer: X block k (k = 0 .. nsteps, the last one only feeds the one-pixel halo) and the
+        // two dY boxes of step k
         if (lane == 0 && nsteps > 0) {
             auto image_of = [&](int64_t g) -> int {
                 int64_t img = g >> 2;
@@ -475,7 +479,7 @@ __global__ void __launch_bounds__(kC1WThreads, 1) tc_conv1_wgrad_u8(const __grid
                 if (k < nsteps) z_next = image_of(g + 1);
                 const int xs = k % XS;
                 if (k >= XS) mbar_wait(&xempty[xs], ((k / XS) - 1) & 1);
-                if (p.dbg & 2) mbar_arrive(&xfull[xs]);
+                if (DBG & 2) mbar_arrive(&xfull[xs]);
                 else {
                     mbar_arrive_expect_tx(&xfull[xs], (uint32_t)kC1WBlock);
                     tma_load_3d(smem_u32(sX + (size_t)xs * kC1WBlock), &tmX, (int)(g & 3) * 128, 0, z, &xfull[xs]);
@@ -483,17 +487,19 @@ __global__ void __launch_bounds__(kC1WThreads, 1) tc_conv1_wgrad_u8(const __grid
                 if (k < nsteps) {
                     const int ys = k % YS;
                     if (k >= YS) mbar_wait(&yempty[ys], ((k / YS) - 1) & 1);
-                    if (p.dbg & 2) mbar_arrive(&yfull[ys]);
+                    if (DBG & 2) mbar_arrive(&yfull[ys]);
                     else {
+                        const uint32_t dst = smem_u32(sYb + (size_t)ys * kC1WYBytes);
                         mbar_arrive_expect_tx(&yfull[ys], (uint32_t)kC1WYBytes);
-                        tma_load_3d(smem_u32(sYb + (size_t)ys * kC1WYBytes), &tmY, 0, (int)(g & 3) * 128, (int)(g >> 2), &yfull[ys]);
+                        tma_load_3d(dst, &tmY, 0, (int)(g & 3) * 128, (int)(g >> 2), &yfull[ys]);
+                        tma_load_3d(dst + kC1WYBox, &tmY, 0, (int)(g & 3) * 128 - kC1WShift, (int)(g >> 2), &yfull[ys]);
                     }
                 }
             }
         }
     } else if (warp == 1 || warp == 2) {
-        // ======================= MMA issuers: M-tile j = warp - 1; 8 K-steps of 16 rows per step, A from tensor memory
-        const int j = warp - 1;
+        // ======================= MMA issuers: tap group b = warp - 1 (dY box b); 8 K-steps of 16 rows per step, A from TMEM
+        const int b = warp - 1;
         const bool leader = elect_one();
         constexpr uint32_t idesc = make_idesc_f16ts(128, 32, 0, 1);
         const uint64_t desc_hi = desc_mnmajor_sw64(0) & 0xFFFFFFFF00000000ull;
@@ -504,12 +510,12 @@ __global__ void __launch_bounds__(kC1WThreads, 1) tc_conv1_wgrad_u8(const __grid
             mbar_wait(&a_full[buf], (it / NA) & 1);
             tc_fence_after_sync();
             if (leader) {
-                const uint32_t y_lo = ((smem_u32(sYb + (size_t)ys * kC1WYBytes) & 0x3FFFFu) >> 4) | desc_lo_flags;
-                const uint32_t a_col = tmem0 + COL_A + (uint32_t)(buf * 128 + j * 64);     // COL_A + NA * 128 = 448 <= 512
+                const uint32_t y_lo = ((smem_u32(sYb + (size_t)ys * kC1WYBytes + (size_t)b * kC1WYBox) & 0x3FFFFu) >> 4) | desc_lo_flags;
+                const uint32_t a_col = tmem0 + COL_A + (uint32_t)(buf * 64);
 #pragma unroll
                 for (int kk = 0; kk < 8; ++kk) {
-                    if (p.dbg & 4) break;
-                    umma_f16_ts(tmem0 + COL_D + (uint32_t)(j * 32), a_col + 8 * kk, desc_hi | (uint64_t)(y_lo + 64 * kk), idesc,
+                    if (DBG & 4) break;
+                    umma_f16_ts(tmem0 + COL_D + (uint32_t)(b * 32), a_col + 8 * kk, desc_hi | (uint64_t)(y_lo + 64 * kk), idesc,
                                 (it | kk) != 0 ? 1u : 0u);
                 }
                 umma_commit(&yempty[ys]);
@@ -520,16 +526,18 @@ __global__ void __launch_bounds__(kC1WThreads, 1) tc_conv1_wgrad_u8(const __grid
         if (leader) umma_commit(&done_bar);
         __syncwarp();
     } else if (warp >= 4 && warp < 4 + kC1WConvWarps) {
-        // ======================= convert warps: uint8 channel rows -> fp16 pairs -> tensor memory
-        constexpr int KP = kC1WKParts, CW = 64 / KP;        // CW TMEM columns (2 CW grid rows) per warp and tile
-        constexpr int NCH = 2 * CW / 16 + 1, NH = CW + 2;   // 16-byte chunks loaded; fp16 pairs converted (one spare pair)
-        const int q = warp & 3, kp = (warp - 4) >> 2;
-        const int tapslot = q >> 1;
+        // ======================= convert warps: uint8 channel rows -> fp16 pairs -> tensor memory.
+        // A warp's step is a serial chain -- three mbarrier waits (~90 cycles each even when already complete), the 16-byte
+        // loads, ~50 PRMTs, tcgen05.st + wait::st, two arrives: ~1000 cycles, and with one set of eight warps that chain WAS
+        // the step period (knock-outs: 520 cycles per step with every stage switched off).  Two sets alternate steps.
+        const int q = warp & 3, kh = ((warp - 4) >> 2) & 1, set = (warp - 4) >> 3;
+        const int h = q >> 1;                               // pixel stream: X[k] (lanes 0-63) or X[k + 1] (lanes 64-127)
         const int c = (q & 1) * 32 + lane;
-        const uint32_t lane_base = tmem0 + COL_A + ((uint32_t)(q * 32) << 16) + (uint32_t)(kp * CW);
-        const int chunk0 = tapslot + kp * (2 * CW / 16);   // first 16-byte chunk this thread needs (tapslot 1 starts at byte 16)
+        const uint32_t lane_base = tmem0 + COL_A + ((uint32_t)(q * 32) << 16) + (uint32_t)(kh * 32);
+        const int chunk0 = kh * 4;                          // first 16-byte chunk of this K half (64 pixels)
+        constexpr int NCH = 5;                              // + one chunk for the h = 1 stream's last pixel
         const uint32_t row_off = (uint32_t)c * 128u, sw = (uint32_t)(c & 7);
-        for (int it = 0; it < nsteps; ++it) {
+        for (int it = set; it < nsteps; it += 2) {
             const int xm = it % XS, xh = (it + 1) % XS, buf = it % NA;
             mbar_wait(&xfull[xm], (it / XS) & 1);
             mbar_wait(&xfull[xh], ((it + 1) / XS) & 1);
@@ -538,30 +546,29 @@ __global__ void __launch_bounds__(kC1WThreads, 1) tc_conv1_wgrad_u8(const __grid
             uint32_t W[4 * NCH];
 #pragma unroll
             for (int v = 0; v < NCH; ++v) {
+                if (DBG & 32) { W[4 * v] = W[4 * v + 1] = W[4 * v + 2] = W[4 * v + 3] = (uint32_t)(it + v); continue; }
                 const int ci = chunk0 + v;
                 const uint8_t* src = (ci < 8 ? bm : bh) + ((((uint32_t)ci & 7u) ^ sw) << 4);
                 const int4 t = *reinterpret_cast<const int4*>(src);
                 W[4 * v] = (uint32_t)t.x; W[4 * v + 1] = (uint32_t)t.y; W[4 * v + 2] = (uint32_t)t.z; W[4 * v + 3] = (uint32_t)t.w;
             }
             __syncwarp();
-            if (lane == 0) mbar_arrive(&xempty[xm]);               // block `it` was halo of step it-1 and main of step it: done
-            // tile 0 = first tap of the slot (shift 0 / 21): pixels k .. k + 2 CW - 1 of this K part; tile 1 = second tap
-            // (shift 1 / 22) = the same stream one pixel later: its pair m is (high half of H[m], low half of H[m + 1]).
-            // tapslot 1 reads from byte 16, so its stream starts 5 bytes in: word 1, byte 1.
-            uint32_t H[NH];
-            if (p.dbg & 1) {
+            // block k is read as the main block of step k and as the halo of step k - 1 (the other set): 16 arrivals release
+            // it; block 0 has no halo reader, so its main readers arrive twice
+            if (lane == 0) {
+                mbar_arrive(&xempty[xm]);
+                if (it == 0) mbar_arrive(&xempty[xm]);
+                mbar_arrive(&xempty[xh]);
+            }
+            uint32_t H[32];
+            if (DBG & 1) {
 #pragma unroll
-                for (int m = 0; m < NH; ++m) H[m] = W[m % (4 * NCH)];
-            } else if (tapslot == 0) u8_to_f16_biased<0, NH>(W, H); else u8_to_f16_biased<1, NH>(W + 1, H);
+                for (int m = 0; m < 32; ++m) H[m] = W[m % (4 * NCH)];
+            } else if (h == 0) u8_to_f16_biased<0, 32>(W, H); else u8_to_f16_biased<1, 32>(W, H);
             if (it >= NA) mbar_wait(&a_empty[buf], ((it / NA) - 1) & 1);
             tc_fence_after_sync();
-            uint32_t o[CW];
-#pragma unroll
-            for (int m = 0; m < CW; ++m) o[m] = H[m];
-            tmem_st_cols(lane_base + (uint32_t)(buf * 128), o);
-#pragma unroll
-            for (int m = 0; m < CW; ++m) o[m] = (p.dbg & 1) ? H[m + 1] : prmt(H[m], H[m + 1], 0x5432u);
-            tmem_st_cols(lane_base + (uint32_t)(buf * 128 + 64), o);
+            if (!(DBG & 16)) tmem_st32(lane_base + (uint32_t)(buf * 64), H);
+            else if (H[0] == 0x12345u && H[31] == 0x54321u) mbar_arrive(&a_full[buf]);     // keep the values alive
             tmem_st_wait();
             tc_fence_before_sync();
             __syncwarp();
@@ -577,10 +584,10 @@ __global__ void __launch_bounds__(kC1WThreads, 1) tc_conv1_wgrad_u8(const __grid
         for (int it = 0; it < nsteps; ++it) {
             const int ys = it % YS;
             mbar_wait(&yfull[ys], (it / YS) & 1);
-            const uint8_t* sY = sYb + (size_t)ys * kC1WYBytes;
+            const uint8_t* sY = sYb + (size_t)ys * kC1WYBytes;          // box 0: the step's own rows
 #pragma unroll
             for (int ps = 0; ps < 4; ++ps) {
-                if (p.dbg & 8) break;
+                if (DBG & 8) break;
                 const int rr = ps * 32 + rq;
                 const int4 v = *reinterpret_cast<const int4*>(sY + img64_off(rr, c16));
                 const uint32_t w[4] = {(uint32_t)v.x, (uint32_t)v.y, (uint32_t)v.z, (uint32_t)v.w};
@@ -602,7 +609,9 @@ __global__ void __launch_bounds__(kC1WThreads, 1) tc_conv1_wgrad_u8(const __grid
 #pragma unroll
             for (int l = 0; l < 32; ++l) t += sRed[l * 32 + tb];
             p.wsb[(int64_t)blockIdx.x * 64 + tb] = t;
-            sBias[tb] = t * kU8Bias;                   // what the 1024 offset of every pixel added to each (tap, c) row
+            // what the 1024 offset of every pixel added to each (tap, c) row: the CTA owns whole images, so the rows of box 1
+            // (shifted by 21, zero outside the image) sum to the same value as the rows of box 0
+            sBias[tb] = t * kU8Bias;
         }
         asm volatile("bar.sync 1, 128;" ::: "memory");
         // drain the two accumulator tiles
@@ -637,20 +646,30 @@ __global__ void __launch_bounds__(kC1WThreads, 1) tc_conv1_wgrad_u8(const __grid
 static int launch_conv1_wgrad_u8(const Conv1WgradU8Params& p, const void* frames_cm, int64_t n_images, const void* dact1_f16, int ctas,
                                  cudaStream_t s, const char* what) {
     const size_t smem = (size_t)kC1WXStages * kC1WBlock + (size_t)kC1WYStages * kC1WYBytes + 1024;
-    static SmemAttrCache attr;
     int rc;
-    if ((rc = attr.ensure(tc_conv1_wgrad_u8, smem, what))) return rc;
-    if (p.rows_per_cta % 128 != 0) return fail(B200RL_ERR_INVALID_ARGUMENT, "%s: rows per CTA must be a multiple of 128", what);
+    if (p.rows_per_cta % 512 != 0) return fail(B200RL_ERR_INVALID_ARGUMENT, "%s: a CTA must own whole images (512 grid rows)", what);
     CUtensorMap tmX, tmY;
     memset(&tmX, 0, sizeof(tmX)); memset(&tmY, 0, sizeof(tmY));
     // frames [img][64 ch][448 positions] u8: box = [64 ch][128 positions], SWIZZLE_128B; dY [img][441 rows][32 co] fp16 = 64-byte
     // rows: box [128 rows][64 B], SWIZZLE_64B
     if ((rc = make_tmap_3d_u8(&tmX, frames_cm, n_images, 64, 448, 448, 64, 128, what))) return rc;
     if ((rc = make_tmap_3d_u8(&tmY, dact1_f16, p.n, 441, 64, 64, 128, 64, what))) return rc;
+    // stage knock-outs (tools/conv1_knockout.py) are separate instantiations: flags tested at run time inside the convert
+    // loop cost the product kernel 20 % (measured)
     static const int dbg = getenv("B200RL_DBG_CONV1W") ? atoi(getenv("B200RL_DBG_CONV1W")) : 0;
-    Conv1WgradU8Params q = p;
-    q.dbg = dbg;
-    tc_conv1_wgrad_u8<<<ctas, kC1WThreads, smem, s>>>(tmX, tmY, q);
+#define B200RL_C1W_CASE(D)                                                                  \
+    case D: {                                                                               \
+        static SmemAttrCache attr;                                                          \
+        if ((rc = attr.ensure(tc_conv1_wgrad_u8<D>, smem, what))) return rc;                \
+        tc_conv1_wgrad_u8<D><<<ctas, kC1WThreads, smem, s>>>(tmX, tmY, p);                  \
+        break;                                                                              \
+    }
+    switch (dbg) {
+        B200RL_C1W_CASE(0) B200RL_C1W_CASE(1) B200RL_C1W_CASE(2) B200RL_C1W_CASE(4) B200RL_C1W_CASE(8) B200RL_C1W_CASE(16)
+        B200RL_C1W_CASE(32) B200RL_C1W_CASE(15) B200RL_C1W_CASE(63)
+        default: return fail(B200RL_ERR_INVALID_ARGUMENT, "%s: no knock-out instantiation %d", what, dbg);
+    }
+#undef B200RL_C1W_CASE
     return check_launch(what);
 }
 
@@ -658,12 +677,8 @@ constexpr int kConv1I8Stages = 8;
 static int launch_conv1_i8(const Conv1U8Params& p, const void* frames_rm, cudaStream_t s, const char* what) {
     constexpr int STAGES = kConv1I8Stages;
     const size_t smem = (size_t)4 * 64 * 64 + (size_t)STAGES * 144 * 128 + 16 * 2304 + 1024;
-    static SmemAttrCache attr;
-    if (int rc = attr.ensure(tc_conv1_i8<STAGES>, smem, what)) return rc;
     const int total = p.n * 2;                     // 2 tiles of 128 pair rows (256 grid positions) per image (441 used)
     static const int dbg = getenv("B200RL_DBG_CONV1") ? atoi(getenv("B200RL_DBG_CONV1")) : 0;
-    Conv1U8Params q = p;
-    q.dbg = dbg;
     int grid = num_sms();
     if (grid > total) grid = total;
     CUtensorMap tmA;
@@ -672,7 +687,19 @@ static int launch_conv1_i8(const Conv1U8Params& p, const void* frames_rm, cudaSt
     // half of row 220 belongs to the next image and only ever feeds invalid positions); SWIZZLE_128B boxes of 144 rows
     int rc = make_tmap_pairs_u8(&tmA, frames_rm, p.n_images, what);
     if (rc) return rc;
-    tc_conv1_i8<STAGES><<<grid, kConvWinThreads, smem, s>>>(tmA, q, total);
+#define B200RL_C1F_CASE(D)                                                                  \
+    case D: {                                                                               \
+        static SmemAttrCache attr;                                                          \
+        if ((rc = attr.ensure(tc_conv1_i8<STAGES, D>, smem, what))) return rc;              \
+        tc_conv1_i8<STAGES, D><<<grid, kConvWinThreads, smem, s>>>(tmA, p, total);          \
+        break;                                                                              \
+    }
+    switch (dbg) {
+        B200RL_C1F_CASE(0) B200RL_C1F_CASE(1) B200RL_C1F_CASE(2) B200RL_C1F_CASE(4) B200RL_C1F_CASE(3) B200RL_C1F_CASE(6)
+        B200RL_C1F_CASE(7)
+        default: return fail(B200RL_ERR_INVALID_ARGUMENT, "%s: no knock-out instantiation %d", what, dbg);
+    }
+#undef B200RL_C1F_CASE
     return check_launch(what);
 }
 

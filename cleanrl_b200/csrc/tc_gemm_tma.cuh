@@ -43,6 +43,7 @@ __global__ void __launch_bounds__(320, 1) tc_gemm_tma(const __grid_constant__ CU
     __shared__ uint64_t full_bar[STAGES], empty_bar[STAGES], tfull_bar[2], tempty_bar[2];
     __shared__ uint32_t tmem_base_smem;
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint8_t* sStage = smem + (size_t)STAGES * STAGE_BYTES;            // 8 epilogue warps x 4 KB
     const int tid = threadIdx.x, warp = tid >> 5;
     const int nch = p.nchunks;
     if (tid == 0) {
@@ -118,7 +119,6 @@ __global__ void __launch_bounds__(320, 1) tc_gemm_tma(const __grid_constant__ CU
             const int mt = tile / ntiles_n, n0 = (tile - mt * ntiles_n) * BN;
             const int r = mt * 128 + lrow;
             const bool rvalid = r < (int)p.M;
-            const int64_t ooff = (int64_t)r * p.ldo;
             const int64_t wb = (int64_t)r * nwords + (n0 >> 5);
             uint32_t mb[NW];
 #pragma unroll
@@ -126,65 +126,86 @@ __global__ void __launch_bounds__(320, 1) tc_gemm_tma(const __grid_constant__ CU
                 mb[g] = (p.mask_bits != nullptr && rvalid && n0 + g * 32 < p.N) ? __ldg(p.mask_bits + wb + g) : 0xFFFFFFFFu;
             mbar_wait(&tfull_bar[h], k & 1);
             tc_fence_after_sync();
+            // Stores: a lane owns one output row, so a direct 16-byte store instruction of the warp touches 32 different lines
+            // = 32 L1 wavefronts and 32 half-written sectors (ncu on the data-gradient: l1tex lsu wavefronts 54 % of the elapsed
+            // cycles, lg_throttle the top stall after the barrier waits, tensor pipe 26 %).  The rows go through a per-warp
+            // staging tile of 32 rows x 128 B (two 32-column groups; XOR swizzle, conflict-free both ways) and 8 consecutive
+            // lanes write one row's 128 bytes: 4 full lines per store instruction.
+            uint8_t* stg = sStage + (size_t)(warp - 2) * 4096;
+            const int lane = tid & 31;
 #pragma unroll
-            for (int g = 0; g < NW; ++g) {
-                uint32_t v[32];
-                tmem_ld32(lane_addr + g * 32, v);
-                tmem_ld_wait();
-                if (g == NW - 1) {
-                    tc_fence_before_sync();
-                    __syncwarp();
-                    if ((tid & 31) == 0) mbar_arrive(&tempty_bar[h]);
-                }
-                const int col = n0 + g * 32;
-                if (!rvalid || col >= p.N) continue;
-                if (p.bias) {
-                    const float4* bp = reinterpret_cast<const float4*>(p.bias + col);
+            for (int gp = 0; gp < NW / 2; ++gp) {
+                const int col0 = n0 + gp * 64;
 #pragma unroll
-                    for (int e = 0; e < 8; ++e) {
-                        const float4 bv = __ldg(bp + e);
-                        v[4 * e] = __float_as_uint(fmaf(__uint_as_float(v[4 * e]), p.scale, bv.x));
-                        v[4 * e + 1] = __float_as_uint(fmaf(__uint_as_float(v[4 * e + 1]), p.scale, bv.y));
-                        v[4 * e + 2] = __float_as_uint(fmaf(__uint_as_float(v[4 * e + 2]), p.scale, bv.z));
-                        v[4 * e + 3] = __float_as_uint(fmaf(__uint_as_float(v[4 * e + 3]), p.scale, bv.w));
+                for (int hf = 0; hf < 2; ++hf) {
+                    const int g = 2 * gp + hf;
+                    uint32_t v[32];
+                    tmem_ld32(lane_addr + g * 32, v);
+                    tmem_ld_wait();
+                    if (g == NW - 1) {
+                        tc_fence_before_sync();
+                        __syncwarp();
+                        if (lane == 0) mbar_arrive(&tempty_bar[h]);
                     }
-                } else {
+                    if (col0 >= p.N) continue;                      // warp-uniform: the ragged last column tile
+                    const int col = n0 + g * 32;
+                    if (p.bias) {
+                        const float4* bp = reinterpret_cast<const float4*>(p.bias + col);
 #pragma unroll
-                    for (int e = 0; e < 32; ++e) v[e] = __float_as_uint(__uint_as_float(v[e]) * p.scale);
-                }
-                if (p.relu) {
-                    uint32_t bits = 0u;
+                        for (int e = 0; e < 8; ++e) {
+                            const float4 bv = __ldg(bp + e);
+                            v[4 * e] = __float_as_uint(fmaf(__uint_as_float(v[4 * e]), p.scale, bv.x));
+                            v[4 * e + 1] = __float_as_uint(fmaf(__uint_as_float(v[4 * e + 1]), p.scale, bv.y));
+                            v[4 * e + 2] = __float_as_uint(fmaf(__uint_as_float(v[4 * e + 2]), p.scale, bv.z));
+                            v[4 * e + 3] = __float_as_uint(fmaf(__uint_as_float(v[4 * e + 3]), p.scale, bv.w));
+                        }
+                    } else {
 #pragma unroll
-                    for (int e = 0; e < 32; ++e) {
-                        const bool pos = __uint_as_float(v[e]) > 0.f;
-                        bits |= (pos ? 1u : 0u) << e;
-                        v[e] = pos ? v[e] : 0u;
+                        for (int e = 0; e < 32; ++e) v[e] = __float_as_uint(__uint_as_float(v[e]) * p.scale);
                     }
-                    if (p.mask_out) p.mask_out[wb + g] = bits;
-                }
-                if (p.mask_bits) {
+                    if (p.relu) {
+                        uint32_t bits = 0u;
 #pragma unroll
-                    for (int e = 0; e < 32; ++e) if (!((mb[g] >> e) & 1u)) v[e] = 0u;
-                }
-                int4 w[4];
+                        for (int e = 0; e < 32; ++e) {
+                            const bool pos = __uint_as_float(v[e]) > 0.f;
+                            bits |= (pos ? 1u : 0u) << e;
+                            v[e] = pos ? v[e] : 0u;
+                        }
+                        if (p.mask_out && rvalid) p.mask_out[wb + g] = bits;
+                    }
+                    if (p.mask_bits) {
 #pragma unroll
-                for (int e = 0; e < 4; ++e) {
-                    w[e].x = (int)pack_bf16x2(__uint_as_float(v[8 * e]), __uint_as_float(v[8 * e + 1]));
-                    w[e].y = (int)pack_bf16x2(__uint_as_float(v[8 * e + 2]), __uint_as_float(v[8 * e + 3]));
-                    w[e].z = (int)pack_bf16x2(__uint_as_float(v[8 * e + 4]), __uint_as_float(v[8 * e + 5]));
-                    w[e].w = (int)pack_bf16x2(__uint_as_float(v[8 * e + 6]), __uint_as_float(v[8 * e + 7]));
+                        for (int e = 0; e < 32; ++e) if (!((mb[g] >> e) & 1u)) v[e] = 0u;
+                    }
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) {
+                        int4 w;
+                        w.x = (int)pack_bf16x2(__uint_as_float(v[8 * e]), __uint_as_float(v[8 * e + 1]));
+                        w.y = (int)pack_bf16x2(__uint_as_float(v[8 * e + 2]), __uint_as_float(v[8 * e + 3]));
+                        w.z = (int)pack_bf16x2(__uint_as_float(v[8 * e + 4]), __uint_as_float(v[8 * e + 5]));
+                        w.w = (int)pack_bf16x2(__uint_as_float(v[8 * e + 6]), __uint_as_float(v[8 * e + 7]));
+                        *reinterpret_cast<int4*>(stg + lane * 128 + ((((uint32_t)(hf * 4 + e)) ^ ((uint32_t)lane & 7u)) << 4)) = w;
+                    }
                 }
-                if (p.dual_dact3) {
-                    const int px = col >> 6, ch = col & 63;
-                    const int oy = px / 7, ox = px - oy * 7;
-                    int4* da = reinterpret_cast<int4*>(p.out + ((int64_t)r * 81 + oy * 9 + ox) * 64 + ch);
-                    int4* db = reinterpret_cast<int4*>(p.out2 + ((int64_t)r * 121 + (oy + 2) * 11 + ox + 2) * 64 + ch);
-                    da[0] = w[0]; da[1] = w[1]; da[2] = w[2]; da[3] = w[3];
-                    db[0] = w[0]; db[1] = w[1]; db[2] = w[2]; db[3] = w[3];
-                } else {
-                    int4* dst = reinterpret_cast<int4*>(p.out + ooff + col);
-                    dst[0] = w[0]; dst[1] = w[1]; dst[2] = w[2]; dst[3] = w[3];
+                if (col0 >= p.N) continue;
+                __syncwarp();
+                const int c = lane & 7;
+                const int px = col0 >> 6;
+                const int oy = px / 7, ox = px - oy * 7;
+#pragma unroll
+                for (int i2 = 0; i2 < 8; ++i2) {
+                    const int R = (lane >> 3) + 4 * i2;
+                    const int64_t rr = (int64_t)mt * 128 + ew * 32 + R;
+                    const int4 w = *reinterpret_cast<const int4*>(stg + R * 128 + ((((uint32_t)c) ^ ((uint32_t)R & 7u)) << 4));
+                    if (rr >= p.M) continue;
+                    if (p.dual_dact3) {
+                        reinterpret_cast<int4*>(p.out + (rr * 81 + oy * 9 + ox) * 64)[c] = w;
+                        reinterpret_cast<int4*>(p.out2 + (rr * 121 + (oy + 2) * 11 + ox + 2) * 64)[c] = w;
+                    } else {
+                        reinterpret_cast<int4*>(p.out + rr * p.ldo + col0)[c] = w;
+                    }
                 }
+                __syncwarp();
             }
         }
     }
@@ -292,9 +313,10 @@ __global__ void __launch_bounds__(160, 1) tc_wgrad_tma(const __grid_constant__ C
 // A: row-major [M, 64*nchunks] bf16 (p.A), weights p.Bw [N, 64*nchunks]; epilogue fields as tc_gemm_ws
 template <int BN, int STAGES>
 static int launch_gemm_tma(const KGemmParams& p, cudaStream_t s, const char* what) {
-    const size_t smem = (size_t)STAGES * (128 * 128 + BN * 128) + 1024;
+    const size_t smem = (size_t)STAGES * (128 * 128 + BN * 128) + 8 * 4096 + 1024;
     static SmemAttrCache attr;
     int rc;
+    if (p.N % 64 != 0 || BN % 64 != 0) return fail(B200RL_ERR_INVALID_ARGUMENT, "%s: N must be a multiple of 64", what);
     if ((rc = attr.ensure(tc_gemm_tma<BN, STAGES>, smem, what))) return rc;
     CUtensorMap tmA, tmB;
     const int64_t K = (int64_t)p.nchunks * 64;
