@@ -70,6 +70,14 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
     }
 }
 
+// Two barriers at once: both polls are in flight together (a try_wait costs ~90 cycles even when the phase is complete)
+__device__ __forceinline__ void mbar_wait2(uint64_t* bar_a, uint32_t parity_a, uint64_t* bar_b, uint32_t parity_b) {
+    const bool a = mbar_try_wait(bar_a, parity_a), b = mbar_try_wait(bar_b, parity_b);
+    if (a && b) return;
+    if (!a) mbar_wait(bar_a, parity_a);
+    if (!b) mbar_wait(bar_b, parity_b);
+}
+
 // one lane of the (converged) warp
 __device__ __forceinline__ bool elect_one() {
     uint32_t pred;

@@ -306,9 +306,14 @@ __global__ void __launch_bounds__(kConvWinThreads, 1) tc_conv1_i8(const __grid_c
             mbar_wait(&tfull_bar[acc], (k / NT) & 1);
             tc_fence_after_sync();
             uint32_t a1[32], a2[32];
-            tmem_ld32(lane_addr, a1);
-            tmem_ld32(lane_addr + 32, a2);
-            tmem_ld_wait();
+            if (DBG & 8) {
+#pragma unroll
+                for (int c4 = 0; c4 < 32; ++c4) { a1[c4] = (uint32_t)(tile + c4); a2[c4] = (uint32_t)(lrow * c4); }
+            } else {
+                tmem_ld32(lane_addr, a1);
+                tmem_ld32(lane_addr + 32, a2);
+                tmem_ld_wait();
+            }
             tc_fence_before_sync();
             __syncwarp();
             if ((tid & 31) == 0) mbar_arrive(&tempty_bar[acc]);            // accumulator drained
@@ -367,9 +372,12 @@ __global__ void __launch_bounds__(kConvWinThreads, 1) tc_conv1_i8(const __grid_c
 //       D_b[(h, c), co] = sum_k X[k + h, c] * dY[k - s_b, co],    tap = 2 b + h.
 //   A  (tensor memory, 128 lanes x 64 columns per step of 128 grid rows k): lanes 0-63 hold channel c of the pixel
 //       stream X[k], lanes 64-127 the same stream one pixel later (h = 1).  ONE tile per step serves all four taps.
-//   B  (shared memory, MN-major SWIZZLE_64B, N = 32): the dY rows of the step, loaded twice by TMA -- rows [k0, k0 + 128)
-//       for b = 0 and rows [k0 - 21, k0 + 107) for b = 1 (negative rows and rows >= 441 are zero-filled by the TMA unit:
-//       images are independent and occupy 512-row slots).  The second box hits L2.
+//   B  (shared memory, MN-major SWIZZLE_64B, N = 32): the dY rows of the step, rows [k0, k0 + 128) for b = 0 and rows
+//       [k0 - 21, k0 + 107) for b = 1.  The stages form one contiguous ring, so the b = 1 operand is the same tile with its
+//       descriptor start moved 21 rows back into the previous stage (the swizzle is a function of the address bits:
+//       tools/experiments/umma_mnshift_test.cu); stage 0 is preceded by a 24-row pad that receives the previous rows by a
+//       second small TMA box.  Negative rows and rows >= 441 are zero-filled by the TMA unit: images are independent and
+//       occupy 512-row slots, and a CTA owns whole images.
 //   X  : channel-major frames [img][64 ch][448 rows] u8, staged in blocks of 128 positions (SWIZZLE_128B boxes of 64 full
 //        lines; 16-byte reads of 32 consecutive channel rows are bank-conflict free through the swizzle).  The h = 1 stream
 //        needs one pixel of the next block.
@@ -395,10 +403,10 @@ struct Conv1WgradU8Params {
     float* ws;
     float* wsb;
 };
-// X blocks (8 KB: 64 channels x 128 positions) and dY steps (2 x 8 KB) in flight: 192 KB per SM; the gather reads need ~3 us
+// X blocks (8 KB: 64 channels x 128 positions) and dY steps (8 KB) in flight: 210 KB per SM; the gather reads need ~3 us
 // of loads in flight to cover their latency.
-constexpr int kC1WXStages = 8, kC1WYStages = 8;
-constexpr int kC1WBlock = 64 * 128, kC1WYBox = 128 * 64, kC1WYBytes = 2 * kC1WYBox;
+constexpr int kC1WXStages = 12, kC1WYStages = 14;
+constexpr int kC1WBlock = 64 * 128, kC1WYBytes = 128 * 64, kC1WYPadRows = 24, kC1WYPad = kC1WYPadRows * 64;
 constexpr int kC1WShift = 21;                     // grid rows between the two tap groups
 constexpr float kDact1Scale = 4096.0f;
 
@@ -425,31 +433,35 @@ __device__ __forceinline__ void u8_to_f16_biased(const uint32_t* W, uint32_t (&H
 constexpr float kU8Bias = 1024.0f;
 
 constexpr int kC1WConvWarps = 16;                // two sets of eight: set s converts the steps it = s (mod 2)
-constexpr int kC1WThreads = (4 + kC1WConvWarps + 4) * 32;
+constexpr int kC1WThreads = (4 + kC1WConvWarps + 4 + 2) * 32;     // + two more MMA issuer warps
 // DBG (stage knock-outs, tools/conv1_knockout.py): 1 = no uint8 -> fp16 conversion, 2 = no TMA, 4 = no MMAs, 8 = no bias
 // sums, 16 = no tcgen05.st, 32 = no shared-memory loads; results are then garbage by construction.  The product is DBG = 0.
 template <int DBG>
 __global__ void __launch_bounds__(kC1WThreads, 1) tc_conv1_wgrad_u8(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmY,
-                                                                  const Conv1WgradU8Params p) {
+                                                                  const __grid_constant__ CUtensorMap tmYpad, const Conv1WgradU8Params p) {
     constexpr int XS = kC1WXStages, YS = kC1WYStages;
     constexpr int NA = 6;                                 // A-operand buffers in TMEM (64 columns each)
-    constexpr uint32_t TMEM_COLS = 512, COL_D = 0, COL_A = 64;          // COL_A + NA * 64 = 448 <= 512
+    constexpr uint32_t TMEM_COLS = 512, COL_D = 0, COL_A = 128;         // 4 accumulator tiles of 32 columns; COL_A + NA * 64 = 512
     extern __shared__ uint8_t smem_raw[];
     __shared__ uint64_t xfull[XS], xempty[XS], yfull[YS], yempty[YS], a_full[NA], a_empty[NA], done_bar;
     __shared__ uint32_t tmem_base_smem;
     __shared__ float sRed[32 * 32], sBias[32];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     uint8_t* sX = smem;                                 // XS blocks of 8 KB
-    uint8_t* sYb = smem + (size_t)XS * kC1WBlock;       // YS stages of two 8 KB boxes
+    uint8_t* sYpad = smem + (size_t)XS * kC1WBlock;     // 24 rows in front of stage 0 (the ring's wrap-around halo)
+    uint8_t* sYb = sYpad + kC1WYPad;                    // YS stages of 8 KB, contiguous
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     if (tid == 0) {
-        for (int s = 0; s < XS; ++s) { mbar_init(&xfull[s], 1); mbar_init(&xempty[s], kC1WConvWarps); }
-        for (int s = 0; s < YS; ++s) { mbar_init(&yfull[s], 1); mbar_init(&yempty[s], 2 + 4); }
-        for (int b = 0; b < NA; ++b) { mbar_init(&a_full[b], 8); mbar_init(&a_empty[b], 2); }
-        mbar_init(&done_bar, 2);
+        // one arrival per warp GROUP (a set of eight convert warps, the four dY warps): the groups synchronise internally
+        // with named barriers and one thread talks to the mbarriers
+        for (int s = 0; s < XS; ++s) { mbar_init(&xfull[s], 1); mbar_init(&xempty[s], 2); }
+        for (int s = 0; s < YS; ++s) { mbar_init(&yfull[s], 1); mbar_init(&yempty[s], 2 + 1); }
+        for (int b = 0; b < NA; ++b) { mbar_init(&a_full[b], 1); mbar_init(&a_empty[b], 2); }
+        mbar_init(&done_bar, 4);
         fence_barrier_init();
         tma_prefetch_desc(&tmX);
         tma_prefetch_desc(&tmY);
+        tma_prefetch_desc(&tmYpad);
     }
     if (warp == 3) tmem_alloc(&tmem_base_smem, TMEM_COLS);
     tc_fence_before_sync();
@@ -464,19 +476,20 @@ __global__ void __launch_bounds__(kC1WThreads, 1) tc_conv1_wgrad_u8(const __grid
     const int64_t g0 = m_begin >> 7;                       // first global step (4 steps per image)
 
     if (warp == 0) {
-        // ======================= TMA producer: X block k (k = 0 .. nsteps, the last one only feeds the one-pixel halo) and the
-        // two dY boxes of step k
+        // ======================= TMA producer 1: X block k (k = 0 .. nsteps, the last one only feeds the one-pixel halo).
+        // Two producer threads: one thread's step is a serial chain too (gather index, mbarrier wait ~90 cycles, expect_tx,
+        // bulk-tensor issue); with X and dY in one thread it was the step period once the convert warps alternated.
         if (lane == 0 && nsteps > 0) {
             auto image_of = [&](int64_t g) -> int {
                 int64_t img = g >> 2;
                 if (img >= p.n) img = p.n - 1;             // the halo block after the very last step: any mapped block will do
                 return p.rows ? (int)__ldg(p.rows + img) : (int)img;
             };
-            int z_next = image_of(g0);
+            // the gather index is fetched one IMAGE (four steps) ahead: a load per step sat on this thread's critical path
+            int z = image_of(g0), z_next = image_of(g0 + 4);        // g0 is image-aligned (whole images per CTA)
             for (int k = 0; k <= nsteps; ++k) {
                 const int64_t g = g0 + k;
-                const int z = z_next;
-                if (k < nsteps) z_next = image_of(g + 1);
+                if (k > 0 && (g & 3) == 0) { z = z_next; z_next = image_of(g + 4); }
                 const int xs = k % XS;
                 if (k >= XS) mbar_wait(&xempty[xs], ((k / XS) - 1) & 1);
                 if (DBG & 2) mbar_arrive(&xfull[xs]);
@@ -484,39 +497,48 @@ __global__ void __launch_bounds__(kC1WThreads, 1) tc_conv1_wgrad_u8(const __grid
                     mbar_arrive_expect_tx(&xfull[xs], (uint32_t)kC1WBlock);
                     tma_load_3d(smem_u32(sX + (size_t)xs * kC1WBlock), &tmX, (int)(g & 3) * 128, 0, z, &xfull[xs]);
                 }
-                if (k < nsteps) {
-                    const int ys = k % YS;
-                    if (k >= YS) mbar_wait(&yempty[ys], ((k / YS) - 1) & 1);
-                    if (DBG & 2) mbar_arrive(&yfull[ys]);
-                    else {
-                        const uint32_t dst = smem_u32(sYb + (size_t)ys * kC1WYBytes);
-                        mbar_arrive_expect_tx(&yfull[ys], (uint32_t)kC1WYBytes);
-                        tma_load_3d(dst, &tmY, 0, (int)(g & 3) * 128, (int)(g >> 2), &yfull[ys]);
-                        tma_load_3d(dst + kC1WYBox, &tmY, 0, (int)(g & 3) * 128 - kC1WShift, (int)(g >> 2), &yfull[ys]);
-                    }
+            }
+        }
+    } else if (warp == 3) {
+        // ======================= TMA producer 2: the dY rows of step k.  The tail of stage s is read by step k + 1 (b = 1), so
+        // stage s is reloaded (step k + YS) once step k + 1 has been consumed: the ring is YS - 1 steps deep.
+        if (lane == 0) {
+            for (int k = 0; k < nsteps; ++k) {
+                const int64_t g = g0 + k;
+                const int ys = k % YS;
+                if (k >= YS) mbar_wait(&yempty[(k + 1) % YS], ((k - YS + 1) / YS) & 1);
+                if (DBG & 2) mbar_arrive(&yfull[ys]);
+                else {
+                    mbar_arrive_expect_tx(&yfull[ys], (uint32_t)(kC1WYBytes + (ys == 0 ? kC1WYPad : 0)));
+                    tma_load_3d(smem_u32(sYb + (size_t)ys * kC1WYBytes), &tmY, 0, (int)(g & 3) * 128, (int)(g >> 2), &yfull[ys]);
+                    if (ys == 0) tma_load_3d(smem_u32(sYpad), &tmYpad, 0, (int)(g & 3) * 128 - kC1WYPadRows, (int)(g >> 2), &yfull[ys]);
                 }
             }
         }
-    } else if (warp == 1 || warp == 2) {
-        // ======================= MMA issuers: tap group b = warp - 1 (dY box b); 8 K-steps of 16 rows per step, A from TMEM
-        const int b = warp - 1;
+        __syncwarp();
+    } else if (warp == 1 || warp == 2 || warp >= 4 + kC1WConvWarps + 4) {
+        // ======================= MMA issuers: tap group b, step parity par; 8 K-steps of 16 rows per step, A from TMEM.
+        // An issuer's step is a serial chain as well (two mbarrier waits, eight descriptor/issue sequences, two commits:
+        // ~480 cycles, the kernel's period with every stage knocked out), so each tap group has two issuers that alternate
+        // steps into their OWN accumulator tiles (summed in the drain: the accumulation order stays fixed).
+        const int b = warp <= 2 ? warp - 1 : warp - (4 + kC1WConvWarps + 4);
+        const int par = warp <= 2 ? 0 : 1;
         const bool leader = elect_one();
         constexpr uint32_t idesc = make_idesc_f16ts(128, 32, 0, 1);
         const uint64_t desc_hi = desc_mnmajor_sw64(0) & 0xFFFFFFFF00000000ull;
         const uint32_t desc_lo_flags = (uint32_t)(desc_mnmajor_sw64(0) & 0xFFFFFFFFull);
-        for (int it = 0; it < nsteps; ++it) {
+        const uint32_t d_col = tmem0 + COL_D + (uint32_t)((par * 2 + b) * 32);
+        for (int it = par; it < nsteps; it += 2) {
             const int ys = it % YS, buf = it % NA;
-            mbar_wait(&yfull[ys], (it / YS) & 1);
-            mbar_wait(&a_full[buf], (it / NA) & 1);
+            mbar_wait2(&yfull[ys], (it / YS) & 1, &a_full[buf], (it / NA) & 1);
             tc_fence_after_sync();
             if (leader) {
-                const uint32_t y_lo = ((smem_u32(sYb + (size_t)ys * kC1WYBytes + (size_t)b * kC1WYBox) & 0x3FFFFu) >> 4) | desc_lo_flags;
+                const uint32_t y_lo = ((smem_u32(sYb + (size_t)ys * kC1WYBytes - (size_t)(b * kC1WShift * 64)) & 0x3FFFFu) >> 4) | desc_lo_flags;
                 const uint32_t a_col = tmem0 + COL_A + (uint32_t)(buf * 64);
 #pragma unroll
                 for (int kk = 0; kk < 8; ++kk) {
                     if (DBG & 4) break;
-                    umma_f16_ts(tmem0 + COL_D + (uint32_t)(b * 32), a_col + 8 * kk, desc_hi | (uint64_t)(y_lo + 64 * kk), idesc,
-                                (it | kk) != 0 ? 1u : 0u);
+                    umma_f16_ts(d_col, a_col + 8 * kk, desc_hi | (uint64_t)(y_lo + 64 * kk), idesc, (it != par || kk != 0) ? 1u : 0u);
                 }
                 umma_commit(&yempty[ys]);
                 umma_commit(&a_empty[buf]);
@@ -537,10 +559,15 @@ __global__ void __launch_bounds__(kC1WThreads, 1) tc_conv1_wgrad_u8(const __grid
         const int chunk0 = kh * 4;                          // first 16-byte chunk of this K half (64 pixels)
         constexpr int NCH = 5;                              // + one chunk for the h = 1 stream's last pixel
         const uint32_t row_off = (uint32_t)c * 128u, sw = (uint32_t)(c & 7);
+        const bool set_leader = ((warp - 4) & 7) == 0;
         for (int it = set; it < nsteps; it += 2) {
             const int xm = it % XS, xh = (it + 1) % XS, buf = it % NA;
-            mbar_wait(&xfull[xm], (it / XS) & 1);
-            mbar_wait(&xfull[xh], ((it + 1) / XS) & 1);
+            if (set_leader) {                                  // all three polls of the step go out together
+                const bool a_free = it < NA || mbar_try_wait(&a_empty[buf], ((it / NA) - 1) & 1);
+                mbar_wait2(&xfull[xm], (it / XS) & 1, &xfull[xh], ((it + 1) / XS) & 1);
+                if (!a_free) mbar_wait(&a_empty[buf], ((it / NA) - 1) & 1);
+            }
+            if (set == 0) asm volatile("bar.sync 2, 256;" ::: "memory"); else asm volatile("bar.sync 3, 256;" ::: "memory");
             const uint8_t* bm = sX + (size_t)xm * kC1WBlock + row_off;
             const uint8_t* bh = sX + (size_t)xh * kC1WBlock + row_off;
             uint32_t W[4 * NCH];
@@ -552,29 +579,27 @@ __global__ void __launch_bounds__(kC1WThreads, 1) tc_conv1_wgrad_u8(const __grid
                 const int4 t = *reinterpret_cast<const int4*>(src);
                 W[4 * v] = (uint32_t)t.x; W[4 * v + 1] = (uint32_t)t.y; W[4 * v + 2] = (uint32_t)t.z; W[4 * v + 3] = (uint32_t)t.w;
             }
-            __syncwarp();
-            // block k is read as the main block of step k and as the halo of step k - 1 (the other set): 16 arrivals release
-            // it; block 0 has no halo reader, so its main readers arrive twice
-            if (lane == 0) {
-                mbar_arrive(&xempty[xm]);
-                if (it == 0) mbar_arrive(&xempty[xm]);
-                mbar_arrive(&xempty[xh]);
-            }
             uint32_t H[32];
             if (DBG & 1) {
 #pragma unroll
                 for (int m = 0; m < 32; ++m) H[m] = W[m % (4 * NCH)];
             } else if (h == 0) u8_to_f16_biased<0, 32>(W, H); else u8_to_f16_biased<1, 32>(W, H);
-            if (it >= NA) mbar_wait(&a_empty[buf], ((it / NA) - 1) & 1);
             tc_fence_after_sync();
             if (!(DBG & 16)) tmem_st32(lane_base + (uint32_t)(buf * 64), H);
             else if (H[0] == 0x12345u && H[31] == 0x54321u) mbar_arrive(&a_full[buf]);     // keep the values alive
             tmem_st_wait();
             tc_fence_before_sync();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(&a_full[buf]);
+            if (set == 0) asm volatile("bar.sync 2, 256;" ::: "memory"); else asm volatile("bar.sync 3, 256;" ::: "memory");
+            // block k is read as the main block of step k and as the halo of step k - 1 (the other set): two arrivals release
+            // it; block 0 has no halo reader, so its main readers arrive twice
+            if (set_leader && lane == 0) {
+                mbar_arrive(&xempty[xm]);
+                if (it == 0) mbar_arrive(&xempty[xm]);
+                mbar_arrive(&xempty[xh]);
+                mbar_arrive(&a_full[buf]);
+            }
         }
-    } else if (warp >= 4 + kC1WConvWarps) {
+    } else if (warp >= 4 + kC1WConvWarps && warp < 4 + kC1WConvWarps + 4) {
         // ======================= dY warps: bias gradient = column sums of dY from the staged tiles (fp32, fixed order)
         const int tb = tid - (4 + kC1WConvWarps) * 32;
         const int rq = tb >> 2, c16 = tb & 3;
@@ -583,8 +608,9 @@ __global__ void __launch_bounds__(kC1WThreads, 1) tc_conv1_wgrad_u8(const __grid
         for (int e = 0; e < 8; ++e) bsum[e] = 0.f;
         for (int it = 0; it < nsteps; ++it) {
             const int ys = it % YS;
-            mbar_wait(&yfull[ys], (it / YS) & 1);
-            const uint8_t* sY = sYb + (size_t)ys * kC1WYBytes;          // box 0: the step's own rows
+            if (tb < 32) mbar_wait(&yfull[ys], (it / YS) & 1);
+            asm volatile("bar.sync 1, 128;" ::: "memory");
+            const uint8_t* sY = sYb + (size_t)ys * kC1WYBytes;          // the step's own rows
 #pragma unroll
             for (int ps = 0; ps < 4; ++ps) {
                 if (DBG & 8) break;
@@ -598,8 +624,8 @@ __global__ void __launch_bounds__(kC1WThreads, 1) tc_conv1_wgrad_u8(const __grid
                     bsum[2 * e + 1] += f.y;
                 }
             }
-            __syncwarp();
-            if (lane == 0) mbar_arrive(&yempty[ys]);
+            asm volatile("bar.sync 1, 128;" ::: "memory");
+            if (tb == 0) mbar_arrive(&yempty[ys]);
         }
 #pragma unroll
         for (int e = 0; e < 8; ++e) sRed[rq * 32 + c16 * 8 + e] = bsum[e];
@@ -609,8 +635,8 @@ __global__ void __launch_bounds__(kC1WThreads, 1) tc_conv1_wgrad_u8(const __grid
 #pragma unroll
             for (int l = 0; l < 32; ++l) t += sRed[l * 32 + tb];
             p.wsb[(int64_t)blockIdx.x * 64 + tb] = t;
-            // what the 1024 offset of every pixel added to each (tap, c) row: the CTA owns whole images, so the rows of box 1
-            // (shifted by 21, zero outside the image) sum to the same value as the rows of box 0
+            // what the 1024 offset of every pixel added to each (tap, c) row: the CTA owns whole images, so the rows of the
+            // b = 1 operand (shifted by 21, zero outside the image) sum to the same value as the rows of the b = 0 operand
             sBias[tb] = t * kU8Bias;
         }
         asm volatile("bar.sync 1, 128;" ::: "memory");
@@ -623,19 +649,25 @@ __global__ void __launch_bounds__(kC1WThreads, 1) tc_conv1_wgrad_u8(const __grid
         float* wsc = p.ws + (int64_t)blockIdx.x * 256 * 64;
 #pragma unroll
         for (int j = 0; j < 2; ++j) {
-            uint32_t v[32];
-            if (nsteps > 0) {
-                tmem_ld32(tmem0 + COL_D + (uint32_t)(j * 32) + ((uint32_t)((warp & 3) * 32) << 16), v);
-                tmem_ld_wait();
-            } else {
-#pragma unroll
-                for (int e = 0; e < 32; ++e) v[e] = 0u;
-            }
+            const uint32_t taddr = tmem0 + COL_D + (uint32_t)(j * 32) + ((uint32_t)((warp & 3) * 32) << 16);
             float4* dst = reinterpret_cast<float4*>(wsc + (int64_t)(j * 128 + lrow) * 64);
 #pragma unroll
-            for (int e = 0; e < 8; ++e)
-                dst[e] = make_float4(__uint_as_float(v[4 * e]) - sBias[4 * e], __uint_as_float(v[4 * e + 1]) - sBias[4 * e + 1],
-                                     __uint_as_float(v[4 * e + 2]) - sBias[4 * e + 2], __uint_as_float(v[4 * e + 3]) - sBias[4 * e + 3]);
+            for (int hc = 0; hc < 2; ++hc) {                     // 16 columns at a time (register budget of the 832-thread CTA)
+                uint32_t v[16], v2[16];
+#pragma unroll
+                for (int e = 0; e < 16; ++e) v[e] = v2[e] = 0u;
+                if (nsteps > 0) tmem_ld16(taddr + hc * 16, v);
+                if (nsteps > 1) tmem_ld16(taddr + 64 + hc * 16, v2);     // the odd steps' accumulator of the same tap group
+                if (nsteps > 0) tmem_ld_wait();
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                    const int c0 = hc * 16 + 4 * e;
+                    dst[hc * 4 + e] = make_float4(__uint_as_float(v[4 * e]) + __uint_as_float(v2[4 * e]) - sBias[c0],
+                                                  __uint_as_float(v[4 * e + 1]) + __uint_as_float(v2[4 * e + 1]) - sBias[c0 + 1],
+                                                  __uint_as_float(v[4 * e + 2]) + __uint_as_float(v2[4 * e + 2]) - sBias[c0 + 2],
+                                                  __uint_as_float(v[4 * e + 3]) + __uint_as_float(v2[4 * e + 3]) - sBias[c0 + 3]);
+                }
+            }
         }
     }
     tc_fence_before_sync();
@@ -645,15 +677,16 @@ __global__ void __launch_bounds__(kC1WThreads, 1) tc_conv1_wgrad_u8(const __grid
 
 static int launch_conv1_wgrad_u8(const Conv1WgradU8Params& p, const void* frames_cm, int64_t n_images, const void* dact1_f16, int ctas,
                                  cudaStream_t s, const char* what) {
-    const size_t smem = (size_t)kC1WXStages * kC1WBlock + (size_t)kC1WYStages * kC1WYBytes + 1024;
+    const size_t smem = (size_t)kC1WXStages * kC1WBlock + kC1WYPad + (size_t)kC1WYStages * kC1WYBytes + 1024;
     int rc;
     if (p.rows_per_cta % 512 != 0) return fail(B200RL_ERR_INVALID_ARGUMENT, "%s: a CTA must own whole images (512 grid rows)", what);
-    CUtensorMap tmX, tmY;
-    memset(&tmX, 0, sizeof(tmX)); memset(&tmY, 0, sizeof(tmY));
+    CUtensorMap tmX, tmY, tmYpad;
+    memset(&tmX, 0, sizeof(tmX)); memset(&tmY, 0, sizeof(tmY)); memset(&tmYpad, 0, sizeof(tmYpad));
     // frames [img][64 ch][448 positions] u8: box = [64 ch][128 positions], SWIZZLE_128B; dY [img][441 rows][32 co] fp16 = 64-byte
     // rows: box [128 rows][64 B], SWIZZLE_64B
     if ((rc = make_tmap_3d_u8(&tmX, frames_cm, n_images, 64, 448, 448, 64, 128, what))) return rc;
     if ((rc = make_tmap_3d_u8(&tmY, dact1_f16, p.n, 441, 64, 64, 128, 64, what))) return rc;
+    if ((rc = make_tmap_3d_u8(&tmYpad, dact1_f16, p.n, 441, 64, 64, kC1WYPadRows, 64, what))) return rc;
     // stage knock-outs (tools/conv1_knockout.py) are separate instantiations: flags tested at run time inside the convert
     // loop cost the product kernel 20 % (measured)
     static const int dbg = getenv("B200RL_DBG_CONV1W") ? atoi(getenv("B200RL_DBG_CONV1W")) : 0;
@@ -661,7 +694,7 @@ static int launch_conv1_wgrad_u8(const Conv1WgradU8Params& p, const void* frames
     case D: {                                                                               \
         static SmemAttrCache attr;                                                          \
         if ((rc = attr.ensure(tc_conv1_wgrad_u8<D>, smem, what))) return rc;                \
-        tc_conv1_wgrad_u8<D><<<ctas, kC1WThreads, smem, s>>>(tmX, tmY, p);                  \
+        tc_conv1_wgrad_u8<D><<<ctas, kC1WThreads, smem, s>>>(tmX, tmY, tmYpad, p);                  \
         break;                                                                              \
     }
     switch (dbg) {
@@ -696,7 +729,7 @@ static int launch_conv1_i8(const Conv1U8Params& p, const void* frames_rm, cudaSt
     }
     switch (dbg) {
         B200RL_C1F_CASE(0) B200RL_C1F_CASE(1) B200RL_C1F_CASE(2) B200RL_C1F_CASE(4) B200RL_C1F_CASE(3) B200RL_C1F_CASE(6)
-        B200RL_C1F_CASE(7)
+        B200RL_C1F_CASE(7) B200RL_C1F_CASE(8) B200RL_C1F_CASE(12) B200RL_C1F_CASE(15)
         default: return fail(B200RL_ERR_INVALID_ARGUMENT, "%s: no knock-out instantiation %d", what, dbg);
     }
 #undef B200RL_C1F_CASE

@@ -1,5 +1,5 @@
 """Bottleneck analysis of the uint8 conv1 kernels: time them with pipeline stages knocked out.
-  forward  (B200RL_DBG_CONV1  bits): 1 = no global stores, 2 = no TMA loads, 4 = no MMAs
+  forward  (B200RL_DBG_CONV1  bits): 1 = no global stores, 2 = no TMA loads, 4 = no MMAs, 8 = no tcgen05.ld
   wgrad    (B200RL_DBG_CONV1W bits): 1 = no uint8 -> fp16 conversion, 2 = no TMA loads, 4 = no MMAs, 8 = no bias sums,
                                       16 = no tcgen05.st, 32 = no shared-memory loads
 Each configuration runs in a fresh process (the flag is read once).   python tools/conv1_knockout.py [M] [fwd|wgrad]"""
@@ -58,7 +58,7 @@ for gather in ("1",) if which == "wgrad" else ("1", "0"):
         except Exception:
             us = None
             print(r.stderr[-500:])
-        labels = ((1, "no-store"), (2, "no-tma"), (4, "no-mma")) if which == "fwd" else \
+        labels = ((1, "no-store"), (2, "no-tma"), (4, "no-mma"), (8, "no-tmem-ld")) if which == "fwd" else \
             ((1, "no-convert"), (2, "no-tma"), (4, "no-mma"), (8, "no-bias-sums"), (16, "no-tmem-st"), (32, "no-lds"))
         names = [n for b, n in labels if dbg & b] or ["full"]
         out.append({"gather": gather == "1", "dbg": dbg, "config": "+".join(names), "us": us})
