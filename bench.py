@@ -319,12 +319,13 @@ def run_ours(opt):
     ach_tf = top["flops"] / secs / 1e12 if secs > 0 else 0.0
     ach_gb = top["bytes"] / secs / 1e9 if secs > 0 else 0.0
     traffic = None
-    tp = ROOT / "profiles" / "r1_traffic.json"
-    if tp.exists():
-        tr = json.loads(tp.read_text()).get(top["name"])
+    for name in ("r2_traffic.json", "r1_traffic.json"):      # the newest ncu --set full capture that has this kernel
+        tp = ROOT / "profiles" / name
+        tr = json.loads(tp.read_text()).get(top["name"]) if tp.exists() else None
         if tr:
             traffic = {"dram_bytes_per_launch": tr["dram_bytes"], "algorithmic_bytes_per_launch": tr["algorithmic_bytes"],
-                       "at_n": tr["n"], "from": "profiles/r1_traffic.json (ncu --set full)"}
+                       "at_n": tr["n"], "from": f"profiles/{name} (ncu --set full)"}
+            break
     roofline = {
         "bound": "hbm" if hbm_bound else "tensor", "kernel": top["name"],
         "achieved": round(ach_gb if hbm_bound else ach_tf, 2), "peak": peak_hbm if hbm_bound else peak_tf,
