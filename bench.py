@@ -174,11 +174,18 @@ def run_ours(opt):
     else:
         state = {"obs": envs.reset(), "done": np.zeros(N, dtype=np.float32)}
 
+    phase_ev = []                                  # (start, rollout done, update done) events per e2e iteration
+
     def iteration_e2e():
         if G > 1:
+            evs = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
+            evs[0].record()
             obs_p, done_p = eng.collect(env_parts, state["obs"], state["done"])
             eng.finish_rollout_parts(obs_p, done_p)
+            evs[1].record()
             st = eng.update(lr_now())
+            evs[2].record()
+            phase_ev.append(evs)
             state["obs"], state["done"] = obs_p, done_p
             return st
         next_obs, next_done = state["obs"], state["done"]
@@ -248,6 +255,11 @@ def run_ours(opt):
 
     res = timed(iteration_resident, profile=True)
     e2e = timed(iteration_e2e)
+    if phase_ev:                                   # where an end-to-end iteration goes (device time, the K timed iterations)
+        torch.cuda.synchronize()
+        last = phase_ev[-K:]
+        e2e["rollout_ms"] = sum(a.elapsed_time(b) for a, b, _ in last) / K
+        e2e["update_ms"] = sum(b.elapsed_time(c) for _, b, c in last) / K
 
     # ---- second headline metric: GAE microseconds per rollout (T x N per GPU), kernel time via CUDA-graph
     #      replays of 20 back-to-back launches (no launch gaps), plus the reference loop with torch ops on the GPU
@@ -352,6 +364,8 @@ def run_ours(opt):
         "clocks": res["clocks"],
         "e2e": {"value": round(sps_e2e, 1), "unit": "env_steps/s", "ms_per_step": round(e2e["ms"] / K, 3),
                 "h2d_bytes_per_step": int(e2e["h2d"]), "d2h_bytes_per_step": int(e2e["d2h"]), "clocks": e2e["clocks"],
+                "rollout_ms": round(e2e.get("rollout_ms", 0.0), 3), "update_ms": round(e2e.get("update_ms", 0.0), 3),
+                "h2d_gbps_during_rollout": round(e2e["h2d"] / max(e2e.get("rollout_ms", 0.0), 1e-9) * 1e-6, 1),
                 "env_groups": G, "loop": "PPOEngine.collect (pipelined env groups)" if G > 1 else "policy_step / env.step"},
         "gpu_launches": int(res["launches"]),
         "gae_us_per_rollout": gae,

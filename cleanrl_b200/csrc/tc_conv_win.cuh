@@ -227,7 +227,8 @@ __global__ void __launch_bounds__(conv_win_threads(BN), 1) tc_conv_win(const __g
             // conflict-free both ways) and 4 consecutive lanes write one row's 64 bytes: 8 lines per instruction; the rows'
             // output offsets travel with them (64-byte units).  Measured per instance at M = 32 768: conv3 data gradient (two
             // output layouts) 308 -> 264 us, conv2 forward 255 -> 230; conv3 forward +5 % and the N = 128 conv2 data gradient
-            // +18 % (four column groups x two extra warp syncs), so those keep the direct stores.
+            // +18 % (four column groups x two extra warp syncs; rows of 128 bytes through a pair of groups: +23 %), so those keep
+            // the direct stores.
             uint8_t* stg = sStage + (size_t)(warp - 2) * kConvWinStage;
             const int lane = tid & 31;
             if (p.stage_stores) {
