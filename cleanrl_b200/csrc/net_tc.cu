@@ -285,10 +285,10 @@ extern "C" int b200rl_naturecnn_bf16_forward(const void* obs, int obs_format, co
     }
     // conv2: 2x2 window conv on the 128-channel cells -> act2 [n,9,9,64]
     win_defaults(wp); win_conv2(wp, act + Q.act1, n);
-    wp.Bw = P + L.w2f; wp.N = 64; wp.vH = 9; wp.vW = 9; wp.out_mode = WOUT_DENSE; wp.out = act + Q.act2; wp.stage_stores = 1;
+    wp.Bw = P + L.w2f; wp.N = 64; wp.vH = 9; wp.vW = 9; wp.out_mode = WOUT_DENSE; wp.out = act + Q.act2;
     wp.bias = params + L.c2b; wp.relu = 1; wp.mask_out = reinterpret_cast<uint32_t*>(act + Q.m2);
     { ProfScope ps(s, "conv2_fwd", 2.0 * n * 81 * 64 * 512, (double)n * ((12800 + 5184) * 2 + 648));
-      if ((rc = launch_conv_win<64, 2, 3, 4>(wp, s, "naturecnn/conv2"))) return rc; }
+      if ((rc = launch_conv_win<64, 2, 4, 4>(wp, s, "naturecnn/conv2"))) return rc; }
     // conv3: 3x3 window conv -> act3 [n,7,7,64]
     win_defaults(wp); win_conv3(wp, act + Q.act2, n);
     wp.Bw = P + L.w3f; wp.N = 64; wp.vH = 7; wp.vW = 7; wp.out_mode = WOUT_DENSE; wp.out = act + Q.act3;
@@ -412,7 +412,7 @@ extern "C" int b200rl_naturecnn_bf16_backward(const void* obs, const void* obs_a
         wp.A = act + Q.dact3b; wp.n = (int)n; wp.G = 121; wp.Wp = 11; wp.M = n * 121; wp.ntaps = 9;
         for (int ky = 0; ky < 3; ++ky) for (int kx = 0; kx < 3; ++kx) wp.shift[ky * 3 + kx] = (2 - ky) * 11 + (2 - kx);
         wp.WR = round8(128 + 24);
-        wp.Bw = P + L.w3dg; wp.N = 64; wp.vH = 9; wp.vW = 9; wp.out_mode = WOUT_DACT2; wp.stage_stores = 1;
+        wp.Bw = P + L.w3dg; wp.N = 64; wp.vH = 9; wp.vW = 9; wp.out_mode = WOUT_DACT2;
         wp.out = act + Q.dact2a; wp.out2 = act + Q.dact2b; wp.mask_bits = reinterpret_cast<const uint32_t*>(act + Q.m2);
         { ProfScope ps(s, "conv3_dgrad", 2.0 * n * 81 * 64 * 576, (double)n * ((7744 + 6400 + 7744) * 2 + 648));
           if ((rc = launch_conv_win<64, 1, 6, 9>(wp, s, "naturecnn/conv3_dgrad"))) return rc; }

@@ -78,6 +78,14 @@ __device__ __forceinline__ void mbar_wait2(uint64_t* bar_a, uint32_t parity_a, u
     if (!b) mbar_wait(bar_b, parity_b);
 }
 
+// 256-bit global store (sm_100: STG.E.ENL2.256): half the store instructions -- and L1 wavefronts -- of two 16-byte stores
+// when every lane writes its own line.  `p` must be 32-byte aligned.
+__device__ __forceinline__ void st_global_256(void* p, const int4& a, const int4& b) {
+    asm volatile("st.global.v8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(p), "r"(a.x), "r"(a.y), "r"(a.z), "r"(a.w), "r"(b.x),
+                 "r"(b.y), "r"(b.z), "r"(b.w)
+                 : "memory");
+}
+
 // one lane of the (converged) warp
 __device__ __forceinline__ bool elect_one() {
     uint32_t pred;

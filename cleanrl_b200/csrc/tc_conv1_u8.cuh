@@ -180,6 +180,7 @@ struct Conv1U8Params {
 // 139 pair rows per 256 output positions.  GEMM rows are pair rows; the even and the odd position of each pair get their own
 // accumulator, and a tap (dy, dx) of position p = 2q + e is the 64-byte half ((e + dx + dy) & 1) of pair row
 // q + (e + 21 dy + dx) / 2 -- a K-major SWIZZLE_128B descriptor shifted by whole rows plus a 64-byte K offset.
+constexpr bool kConv1I8Direct256 = true;
 template <int STAGES, int DBG>
 __global__ void __launch_bounds__(kConvWinThreads, 1) tc_conv1_i8(const __grid_constant__ CUtensorMap tmA, const Conv1U8Params p, int total_tiles) {
     constexpr int BN = 64, WR = 144, NTAPS = 4;
@@ -340,6 +341,16 @@ __global__ void __launch_bounds__(kConvWinThreads, 1) tc_conv1_i8(const __grid_c
             // the warp touches 32 different lines = 32 L1 wavefronts -- measured, the epilogue's global stores took more of
             // the L1 data pipe than the MMAs' operand reads.  The rows go through a per-warp staging tile instead (XOR
             // swizzle: conflict-free both ways), and 4 consecutive lanes write one row's 64 bytes: 8 lines per instruction.
+            if (kConv1I8Direct256) {
+                // two 256-bit stores per row instead of the staging round trip (two warp syncs, 8 shared-memory instructions)
+                if (valid && !(DBG & 1)) {
+                    uint8_t* dst = reinterpret_cast<uint8_t*>(p.out) + (cell * 4 + cls) * 64;
+                    st_global_256(dst, make_int4((int)pk[0], (int)pk[1], (int)pk[2], (int)pk[3]), make_int4((int)pk[4], (int)pk[5], (int)pk[6], (int)pk[7]));
+                    st_global_256(dst + 32, make_int4((int)pk[8], (int)pk[9], (int)pk[10], (int)pk[11]),
+                                  make_int4((int)pk[12], (int)pk[13], (int)pk[14], (int)pk[15]));
+                }
+                continue;
+            }
             uint8_t* stg = sStage + (size_t)(warp - 2) * 2304;
             const int lane = tid & 31;
             {

@@ -41,7 +41,6 @@ struct WinParams {
     const float* bias;
     float scale;
     int relu;
-    int stage_stores;        // 1: coalesce the epilogue's global stores through shared memory (see the epilogue)
     int out_f16;             // store fp16 (saturating) instead of bf16: d(act1) feeding the uint8 conv1 weight gradient
 };
 
@@ -63,8 +62,6 @@ constexpr int kConvWinThreads = 576;                     // the widest instance 
 __host__ __device__ constexpr int conv_win_groups(int BN) { return BN >= 128 ? 2 : 4; }
 __host__ __device__ constexpr int conv_win_threads(int BN) { return 64 + conv_win_groups(BN) * 128; }
 __host__ __device__ constexpr int conv_win_acc_bufs(int BN) { return BN <= 128 ? 4 : 2; }
-// epilogue staging tile per warp: 32 rows x 64 B (one 32-column group) + the rows' output offsets (2 x int per row)
-constexpr int kConvWinStage = 32 * 64 + 32 * 8;
 template <int BN, int CPR, int STAGES, int NTAPS>
 __global__ void __launch_bounds__(conv_win_threads(BN), 1) tc_conv_win(const __grid_constant__ CUtensorMap tmA, const WinParams p,
                                                       int total_tiles) {
@@ -84,7 +81,6 @@ __global__ void __launch_bounds__(conv_win_threads(BN), 1) tc_conv_win(const __g
     const int STAGE_BYTES = IMG * CPR;
     uint8_t* sW = smem;
     uint8_t* sRing = smem + (size_t)nchunks * B_CHUNK;
-    uint8_t* sStage = sRing + (size_t)STAGES * STAGE_BYTES;          // one kConvWinStage tile per epilogue warp
 
     if (tid == 0) {
         for (int s = 0; s < STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
@@ -219,21 +215,7 @@ __global__ void __launch_bounds__(conv_win_threads(BN), 1) tc_conv_win(const __g
                 o2 = ((int64_t)i * 121 + (Y + 1) * 11 + (X + 1)) * 64;     // zero-padded 11x11 (conv2 dgrad)
                 ob = ((int64_t)i * 81 + Y * 9 + X) * 2;                    // act2 mask words
             } else {
-                o1 = ((int64_t)i * 441 + 42 * Y + 2 * X) * 32;             // pixel (2Y, 2X) of the 21-grid, 32 channels (+ per group)
                 ob = ((int64_t)i * 100 + Y * 10 + X) * 4;                  // act1 (2x2 cells) mask words
-            }
-            // Stores: a lane owns one output row, so a direct 16-byte store instruction of the warp touches 32 different lines
-            // = 32 L1 wavefronts.  With p.stage_stores the packed rows go through a per-warp staging tile (XOR swizzle:
-            // conflict-free both ways) and 4 consecutive lanes write one row's 64 bytes: 8 lines per instruction; the rows'
-            // output offsets travel with them (64-byte units).  Measured per instance at M = 32 768: conv3 data gradient (two
-            // output layouts) 308 -> 264 us, conv2 forward 255 -> 230; conv3 forward +5 % and the N = 128 conv2 data gradient
-            // +18 % (four column groups x two extra warp syncs; rows of 128 bytes through a pair of groups: +23 %), so those keep
-            // the direct stores.
-            uint8_t* stg = sStage + (size_t)(warp - 2) * kConvWinStage;
-            const int lane = tid & 31;
-            if (p.stage_stores) {
-                __syncwarp();
-                reinterpret_cast<int2*>(stg + 2048)[lane] = make_int2(valid ? (int)(o1 >> 5) : -1, (int)(o2 >> 5));
             }
             // the row's mask words are requested BEFORE waiting for the accumulator (latency overlaps the MMAs)
             uint32_t mb[NW];
@@ -262,7 +244,7 @@ __global__ void __launch_bounds__(conv_win_threads(BN), 1) tc_conv_win(const __g
                     __syncwarp();
                     if ((tid & 31) == 0) mbar_arrive(&tempty_bar[acc]);
                 }
-                if (g * 32 >= p.N) continue;                   // warp-uniform; invalid rows stay in the collective staging
+                if (!valid || g * 32 >= p.N) continue;
                 if (p.bias) {
                     const float4* bp = reinterpret_cast<const float4*>(p.bias + g * 32);
 #pragma unroll
@@ -284,7 +266,7 @@ __global__ void __launch_bounds__(conv_win_threads(BN), 1) tc_conv_win(const __g
                         const float f = __uint_as_float(v[e]);
                         bits |= (f > 0.f ? 1u : 0u) << e;           // the clamp itself is folded into the bf16 conversion below
                     }
-                    if (p.mask_out && valid) p.mask_out[ob + g] = bits;
+                    if (p.mask_out) p.mask_out[ob + g] = bits;
                 }
                 if (p.mask_bits) {
 #pragma unroll
@@ -316,30 +298,25 @@ __global__ void __launch_bounds__(conv_win_threads(BN), 1) tc_conv_win(const __g
                     w[e].w = (int)pack_bf16x2(__uint_as_float(v[8 * e + 6]), __uint_as_float(v[8 * e + 7]));
                 }
                 }
-                // column group g: + g * 32 elements, or (conv2 data gradient) pixel (2Y + py, 2X + px) of the 21-grid
-                const int gdelta = p.out_mode == WOUT_DACT1 ? ((g >> 1) * 21 + (g & 1)) : g;
-                if (p.stage_stores) {
-                    const uint32_t f = (uint32_t)(lane >> 1) & 3u;
-#pragma unroll
-                    for (int c = 0; c < 4; ++c) *reinterpret_cast<int4*>(stg + lane * 64 + ((((uint32_t)c) ^ f) << 4)) = w[c];
-                    __syncwarp();
-#pragma unroll
-                    for (int i2 = 0; i2 < 4; ++i2) {
-                        const int R = (lane >> 2) + 8 * i2, c = lane & 3;
-                        const int2 u = reinterpret_cast<const int2*>(stg + 2048)[R];
-                        const int4 v4 = *reinterpret_cast<const int4*>(stg + R * 64 + ((((uint32_t)c) ^ ((uint32_t)(R >> 1) & 3u)) << 4));
-                        if (u.x < 0) continue;
-                        reinterpret_cast<int4*>(p.out + ((int64_t)(u.x + gdelta) << 5))[c] = v4;
-                        if (p.out_mode == WOUT_DACT2) reinterpret_cast<int4*>(p.out2 + ((int64_t)(u.y + gdelta) << 5))[c] = v4;
-                    }
-                    __syncwarp();
-                } else if (valid) {
-                    int4* dst = reinterpret_cast<int4*>(p.out + o1 + (int64_t)gdelta * 32);
-                    dst[0] = w[0]; dst[1] = w[1]; dst[2] = w[2]; dst[3] = w[3];
-                    if (p.out_mode == WOUT_DACT2) {
-                        int4* dst2 = reinterpret_cast<int4*>(p.out2 + o2 + g * 32);
-                        dst2[0] = w[0]; dst2[1] = w[1]; dst2[2] = w[2]; dst2[3] = w[3];
-                    }
+                // Stores: a lane owns one output row, so every store instruction of the warp touches 32 different lines = 32 L1
+                // wavefronts; on the N = 128 conv2 data gradient they were ~70 % of the tile period.  256-bit stores halve
+                // the instructions (conv2 data gradient 338 -> 288 us, conv3 data gradient 308 -> 256, conv2 forward -5 %).
+                // Measured against it: coalescing through a shared-memory tile (4 or 8 lanes per row) -- conv3 data gradient 263,
+                // conv2 forward equal, conv3 forward +5 %, conv2 data gradient +18..23 % (extra warp syncs in a latency-bound
+                // epilogue) -- so the direct form stays.
+                bf16* dst;
+                if (p.out_mode == WOUT_DACT1) {
+                    // column group g = (py,px) of the cell -> input pixel (2Y+py, 2X+px) of the 21-grid, 32 channels
+                    dst = p.out + ((int64_t)i * 441 + (2 * Y + (g >> 1)) * 21 + 2 * X + (g & 1)) * 32;
+                } else {
+                    dst = p.out + o1 + g * 32;
+                }
+                st_global_256(dst, w[0], w[1]);
+                st_global_256(dst + 16, w[2], w[3]);
+                if (p.out_mode == WOUT_DACT2) {
+                    bf16* dst2 = p.out2 + o2 + g * 32;
+                    st_global_256(dst2, w[0], w[1]);
+                    st_global_256(dst2 + 16, w[2], w[3]);
                 }
             }
             r += TSTEP; i_lin += step_i; rem_lin += step_rem;
@@ -354,7 +331,7 @@ __global__ void __launch_bounds__(conv_win_threads(BN), 1) tc_conv_win(const __g
 template <int BN, int CPR, int STAGES, int NTAPS>
 static int launch_conv_win(const WinParams& p, cudaStream_t s, const char* what) {
     if (p.ntaps != NTAPS) return fail(B200RL_ERR_INVALID_ARGUMENT, "%s: %d taps, kernel instance has %d", what, p.ntaps, NTAPS);
-    const size_t smem = (size_t)p.ntaps * CPR * BN * 128 + (size_t)STAGES * p.WR * 128 * CPR + (size_t)conv_win_groups(BN) * 4 * kConvWinStage + 1024;
+    const size_t smem = (size_t)p.ntaps * CPR * BN * 128 + (size_t)STAGES * p.WR * 128 * CPR + 1024;
     static SmemAttrCache attr;
     if (int rc = attr.ensure(tc_conv_win<BN, CPR, STAGES, NTAPS>, smem, what)) return rc;
     if ((int64_t)p.G * p.Wp >= 65536 || p.G < 1 || p.N % 32 != 0)
