@@ -23,6 +23,7 @@ import os
 import subprocess
 import sys
 import threading
+import time
 from pathlib import Path
 from types import SimpleNamespace
 
@@ -67,12 +68,14 @@ class ClockSampler:
     def __init__(self, gpu_index):
         self.idx = gpu_index
         self.proc = None
-        self.lines = []
+        self.lines = []                # (arrival time, csv line)
+        self.t0 = self.t1 = None
 
     def start(self):
+        """Start sampling (nvidia-smi needs ~0.5 s to deliver its first line: start it BEFORE the warm-up)."""
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.idx}", f"--query-gpu={self.Q}",
-                                          "--format=csv,noheader,nounits", "-lms", "200"],
+                                          "--format=csv,noheader,nounits", "-lms", "50"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.t = threading.Thread(target=self._read, daemon=True)
             self.t.start()
@@ -81,11 +84,18 @@ class ClockSampler:
 
     def _read(self):
         for line in self.proc.stdout:
-            self.lines.append(line.strip())
+            self.lines.append((time.time(), line.strip()))
+
+    def mark_begin(self):
+        self.t0 = time.time()
+
+    def mark_end(self):
+        self.t1 = time.time()
 
     def stop(self):
         if self.proc is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.06)               # let the sample that covers the end of the region arrive
         self.proc.terminate()
         try:
             self.proc.wait(timeout=2)
@@ -93,7 +103,13 @@ class ClockSampler:
             self.proc.kill()
         sm, smmax, reasons = [], [], set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for ln in self.lines:
+        lines = [ln for ts, ln in self.lines if self.t0 is None or (self.t0 <= ts <= (self.t1 or ts) + 0.06)]
+        window = "timed region"
+        if not lines and self.lines:   # region shorter than one sampling period: the sample nearest to it
+            mid = 0.5 * (self.t0 + (self.t1 or self.t0))
+            lines = [min(self.lines, key=lambda x: abs(x[0] - mid))[1]]
+            window = "nearest sample"
+        for ln in lines:
             f = [x.strip() for x in ln.split(",")]
             if len(f) < 9:
                 continue
@@ -105,7 +121,7 @@ class ClockSampler:
                 if v.lower().startswith("active"):
                     reasons.add(nm)
         return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(smmax) if smmax else None,
-                "samples": len(sm), "reasons": sorted(reasons)}
+                "samples": len(sm), "window": window, "reasons": sorted(reasons)}
 
 
 def measured_peaks():
@@ -167,10 +183,20 @@ def run_ours(opt):
 
     # ---- e2e: the public loop with host buffers.  --env-groups G > 1 (default 2): PPOEngine.collect over G independent
     #      vector envs, software-pipelined (what `ppo_atari_envpool.py --env-groups G` runs); 1: the reference's loop order
+    #      Observations: `--env-obs stack` (default) = frame-stacked like envpool's stack_num=4 Atari observation (planes 0..2 of
+    #      an env's observation are planes 1..3 of its previous one; done envs come back with 4 fresh planes), so the engine's
+    #      frame-stack delta upload applies; `pool` = unrelated random batches every step (every observation goes up whole).
     G = max(1, int(opt.env_groups))
+    env_sets = {}
+
+    def use_envs(mode):
+        if mode not in env_sets:
+            parts = [SyntheticAtariVec(N // G, seed=seed + g * (N // G), mode=mode, pinned=True) for g in range(G)]
+            env_sets[mode] = (parts, {"obs": [e.reset() for e in parts], "done": [np.zeros(N // G, dtype=np.float32) for _ in parts]})
+        return env_sets[mode]
+
     if G > 1:
-        env_parts = [SyntheticAtariVec(N // G, seed=seed + g * (N // G), mode="pool", pinned=True) for g in range(G)]
-        state = {"obs": [e.reset() for e in env_parts], "done": [np.zeros(N // G, dtype=np.float32) for _ in env_parts]}
+        env_parts, state = use_envs(opt.env_obs)
     else:
         state = {"obs": envs.reset(), "done": np.zeros(N, dtype=np.float32)}
 
@@ -221,11 +247,12 @@ def run_ours(opt):
         return eng.update(lr_now())
 
     def timed(fn, profile=False):
+        sampler = ClockSampler(local_rank)
+        sampler.start()
         for _ in range(W):
             fn()
         barrier()
-        sampler = ClockSampler(local_rank)
-        sampler.start()
+        sampler.mark_begin()
         h2d0, d2h0, l0 = eng.h2d_bytes, eng.d2h_bytes, lib.b200rl_launch_count() + eng.graph_launches
         if profile:
             lib.b200rl_profile_reset()
@@ -237,6 +264,7 @@ def run_ours(opt):
             st = fn()
         e1.record()
         torch.cuda.synchronize()
+        sampler.mark_end()
         ms = e0.elapsed_time(e1)
         prof = None
         if profile:
@@ -253,13 +281,28 @@ def run_ours(opt):
         return dict(ms=float(t.item()), h2d=(eng.h2d_bytes - h2d0) / K, d2h=(eng.d2h_bytes - d2h0) / K,
                     launches=lib.b200rl_launch_count() + eng.graph_launches - l0, clocks=clocks, stats=st, prof=prof)
 
+    def phases(r):
+        if phase_ev:                               # where an end-to-end iteration goes (device time, the K timed iterations)
+            torch.cuda.synchronize()
+            last = phase_ev[-K:]
+            r["rollout_ms"] = sum(a.elapsed_time(b) for a, b, _ in last) / K
+            r["update_ms"] = sum(b.elapsed_time(c) for _, b, c in last) / K
+        return r
+
     res = timed(iteration_resident, profile=True)
-    e2e = timed(iteration_e2e)
-    if phase_ev:                                   # where an end-to-end iteration goes (device time, the K timed iterations)
-        torch.cuda.synchronize()
-        last = phase_ev[-K:]
-        e2e["rollout_ms"] = sum(a.elapsed_time(b) for a, b, _ in last) / K
-        e2e["update_ms"] = sum(b.elapsed_time(c) for _, b, c in last) / K
+    e2e_whole = None
+    if G > 1 and opt.env_obs == "stack" and eng.delta_upload and not opt.no_whole_upload_arm:
+        # secondary arm: the same loop on unrelated observations, every one uploaded whole (round 2's headline path)
+        env_parts, state = use_envs("pool")
+        eng.delta_upload = False
+        e2e_whole = phases(timed(iteration_e2e))
+        eng.delta_upload = True
+        env_parts, state = use_envs("stack")
+    ff0, rd0 = eng.delta_full_frames, eng.delta_redos
+    e2e = phases(timed(iteration_e2e))
+    e2e["full_frames"] = (eng.delta_full_frames - ff0) / max(W + K, 1)
+    e2e["redos"] = eng.delta_redos - rd0
+    e2e["delta"] = bool(G > 1 and eng.delta_upload)
 
     # ---- second headline metric: GAE microseconds per rollout (T x N per GPU), kernel time via CUDA-graph
     #      replays of 20 back-to-back launches (no launch gaps), plus the reference loop with torch ops on the GPU
@@ -366,13 +409,25 @@ def run_ours(opt):
                 "h2d_bytes_per_step": int(e2e["h2d"]), "d2h_bytes_per_step": int(e2e["d2h"]), "clocks": e2e["clocks"],
                 "rollout_ms": round(e2e.get("rollout_ms", 0.0), 3), "update_ms": round(e2e.get("update_ms", 0.0), 3),
                 "h2d_gbps_during_rollout": round(e2e["h2d"] / max(e2e.get("rollout_ms", 0.0), 1e-9) * 1e-6, 1),
-                "env_groups": G, "loop": "PPOEngine.collect (pipelined env groups)" if G > 1 else "policy_step / env.step"},
+                "env_groups": G, "loop": "PPOEngine.collect (pipelined env groups)" if G > 1 else "policy_step / env.step",
+                "observations": ("frame-stacked synthetic env (envpool stack_num=4 semantics)" if opt.env_obs == "stack" and G > 1
+                                 else "unrelated random batches"),
+                "upload": ({"mode": "frame-stack delta: newest plane of every env + whole observations of done envs; "
+                                    "shifted-stack property verified on the host for every env, every step",
+                            "whole_observations_per_iteration": round(e2e["full_frames"], 1), "redone_steps": e2e["redos"]}
+                           if e2e["delta"] else {"mode": "whole observation every step"})},
         "gpu_launches": int(res["launches"]),
         "gae_us_per_rollout": gae,
         "roofline": roofline,
         "losses_last": {k: (float(v) if isinstance(v, (int, float)) else None) for k, v in (e2e["stats"] or {}).items()
                         if k in ("pg_loss", "v_loss", "entropy", "approx_kl")},
     }
+    if e2e_whole is not None:
+        out["e2e_whole_upload"] = {
+            "value": round(steps_total * K / (e2e_whole["ms"] * 1e-3), 1), "unit": "env_steps/s",
+            "ms_per_step": round(e2e_whole["ms"] / K, 3), "h2d_bytes_per_step": int(e2e_whole["h2d"]),
+            "d2h_bytes_per_step": int(e2e_whole["d2h"]), "rollout_ms": round(e2e_whole.get("rollout_ms", 0.0), 3),
+            "update_ms": round(e2e_whole.get("update_ms", 0.0), 3), "observations": "unrelated random batches, uploaded whole"}
     if world > 1:
         out["replicas_identical"] = replicas_identical
         out["exchange"] = {"collectives_per_update": 2 if eng.overlap_exchange else 1,
@@ -381,9 +436,90 @@ def run_ours(opt):
         out["cpu_baseline"] = cpu_baseline(opt)
     if world == 1 and not opt.no_gpu_eager_baseline:
         out["gpu_eager_baseline"] = gpu_eager_baseline(opt)
+    if world == 1 and not opt.no_extra:
+        del eng
+        torch.cuda.empty_cache()
+        out["extra"] = extra_configs()
     print(json.dumps(out))
     if world > 1:
         dist.destroy_process_group()
+
+
+# ------------------------------------------------------------------ BASELINE.json configs[3] and configs[4]
+def extra_configs():
+    """Short measured lines for the two other GPU configurations BASELINE.json names (not the headline metric):
+    configs[3] ppo_continuous_action HalfCheetah-shaped, num_envs=512 (the drop-in script end to end, host envs);
+    configs[4] dqn_atari replay-ring sample + TD update at batch 8192 (device-resident ring)."""
+    import torch
+    out = {}
+    try:
+        from cleanrl_b200 import ppo_continuous_action as pca
+
+        class _NullWriter:
+            def __init__(self, *a, **k): pass
+            def add_text(self, *a, **k): pass
+            def add_scalar(self, *a, **k): pass
+            def close(self): pass
+
+        n_envs, n_steps, iters = 512, 256, 4
+        marks = []
+
+        def on_iteration(it, engine, st):
+            torch.cuda.synchronize()
+            marks.append(time.time())
+
+        import contextlib
+        import io
+        with contextlib.redirect_stdout(io.StringIO()):
+            pca.main(["--synthetic-env", "--num-envs", str(n_envs), "--num-steps", str(n_steps),
+                      "--total-timesteps", str(n_envs * n_steps * iters), "--seed", "1"],
+                     writer_factory=_NullWriter, on_iteration=on_iteration)
+        sec = (marks[-1] - marks[0]) / (len(marks) - 1)
+        out["config4_ppo_continuous_action"] = {
+            "value": round(n_envs * n_steps / sec, 1), "unit": "env_steps/s", "ms_per_iteration": round(1e3 * sec, 2),
+            "workload": f"cleanrl_b200/ppo_continuous_action.py (public script, host synthetic HalfCheetah-shaped env, obs 17 / act 6), "
+                        f"num_envs={n_envs} num_steps={n_steps}, 10 epochs x 32 minibatches, fp32 kernels; {iters - 1} timed iterations "
+                        "after 1 warm-up, wall clock around the whole iteration"}
+    except Exception as e:  # an extra line must never take the headline down with it
+        out["config4_ppo_continuous_action"] = {"unavailable": f"{type(e).__name__}: {e}"[:200]}
+    try:
+        from cleanrl_b200.agents import QNetworkAgent, dqn_update
+        from cleanrl_b200.replay import DeviceReplayRing
+        from cleanrl_b200.synthetic_envs import Box, Discrete
+
+        class E:
+            single_observation_space = Box(0, 255, (4, 84, 84), np.uint8)
+            single_action_space = Discrete(4)
+
+        dev = torch.device("cuda", torch.cuda.current_device())
+        B, SIZE, reps = 8192, 65536, 20
+        q, t = QNetworkAgent(E()).to(dev), QNetworkAgent(E()).to(dev)
+        q.precision = t.precision = "bf16"
+        t.load_state_dict(q.state_dict())
+        ring = DeviceReplayRing(SIZE, (4, 84, 84), 1, dev)
+        ring.observations.random_(0, 256)
+        ring.actions.random_(0, 4); ring.rewards.normal_(); ring.dones.bernoulli_(0.02)
+        ring.pos, ring.full = 0, True
+        stats = torch.zeros(2, device=dev)
+        for _ in range(3):
+            dqn_update(q, t, ring, ring.sample(B), 0.99, 1e-4, huber=True, stats=stats)
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        torch.cuda.synchronize()
+        a.record()
+        for _ in range(reps):
+            dqn_update(q, t, ring, ring.sample(B), 0.99, 1e-4, huber=True, stats=stats)
+        b.record()
+        torch.cuda.synchronize()
+        ms = a.elapsed_time(b) / reps
+        out["config5_dqn_atari"] = {
+            "value": round(B / (ms * 1e-3), 1), "unit": "transitions/s", "ms_per_sample_plus_update": round(ms, 3),
+            "workload": f"replay-ring sample + Huber TD update, batch {B}, ring of {SIZE} uint8 frames resident in HBM, "
+                        f"bf16 tensor-core QNetwork; {reps} timed updates (CUDA events) after 3 warm-up"}
+        del q, t, ring
+        torch.cuda.empty_cache()
+    except Exception as e:
+        out["config5_dqn_atari"] = {"unavailable": f"{type(e).__name__}: {e}"[:200]}
+    return out
 
 
 # ---------------------------------------------------------------------- reference / cpu legs
@@ -467,6 +603,9 @@ def main():
     ap.add_argument("--num-steps", type=int, default=128)
     ap.add_argument("--precision", choices=["bf16", "fp32"], default="bf16")
     ap.add_argument("--env-groups", type=int, default=2)
+    ap.add_argument("--env-obs", choices=["stack", "pool"], default="stack")
+    ap.add_argument("--no-whole-upload-arm", action="store_true")
+    ap.add_argument("--no-extra", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-gpu-eager-baseline", action="store_true")
     opt = ap.parse_args()

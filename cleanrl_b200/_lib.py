@@ -73,6 +73,13 @@ SIGNATURES = {
     "b200rl_lstm_cell_fwd_f32": (_i, [_p, _p, _p, _i64, _i, _p, _p, _p, _p]),
     "b200rl_lstm_cell_bwd_f32": (_i, [_p, _p, _p, _p, _p, _p, _p, _i64, _i, _p, _p, _p]),
     "b200rl_naturecnn_grad_tail_offset": (_i64, [_i]),
+    "b200rl_frames_delta_s2d_u8": (_i, [_p, _p, _p, _p, _p, _i64, _p, _p, _p]),
+    "b200rl_h2d_rows_async": (_i, [_p, _p, _i64, _i64, _i64, _p]),
+    "b200rl_stackdelta_create": (_p, [_i64, _i, _i64, _i]),
+    "b200rl_stackdelta_destroy": (None, [_p]),
+    "b200rl_stackdelta_invalidate": (None, [_p]),
+    "b200rl_stackdelta_begin": (_i64, [_p, _p, _i64, _p, _p, _p, _p]),
+    "b200rl_stackdelta_wait": (_i64, [_p, _p]),
 }
 
 _lib = None

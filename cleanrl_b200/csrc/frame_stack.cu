@@ -1,0 +1,306 @@
+// Frame-stack aware observation upload (include/b200rl.h, "frame-stack delta upload").
+//
+// The Atari observation of cleanrl/ppo_atari_envpool.py:185-196,237-239 is a stack of the 4 newest 84x84 frames: from
+// one env step to the next, planes 0..2 of an env's observation are planes 1..3 of its previous one unless the env was
+// reset.  The reference uploads the whole stack as fp32 every step (115.6 MB at 1024 envs); the round-1/2 engine uploads
+// it as uint8 (28.9 MB) and is PCIe-bound.  Here only the newest plane crosses PCIe (7.2 MB):
+//
+//   host   b200rl_stackdelta_*   a worker pool keeps a private mirror of the last observation of every env and VERIFIES
+//                                on the host, asynchronously to the upload, that the shifted-stack property really holds
+//                                for every env that is not flagged done (memcmp of 3 planes per env); envs flagged done
+//                                are staged as full frames up front, envs that fail the check are reported so that the
+//                                caller can re-stage them as full frames and redo the step (never a silent error).
+//   device tc_frames_delta_s2d_u8   builds rollout slot t (both uint8 space-to-depth orientations, tc_conv1_u8.cuh) from
+//                                slot t-1 (channel groups 1..3 -> 0..2) plus the newest plane (-> channel group 3), or
+//                                from a full staged frame for the envs that have one.
+#include <algorithm>
+#include <atomic>
+#include <condition_variable>
+#include <cstring>
+#include <mutex>
+#include <thread>
+#include <vector>
+
+#include "common.cuh"
+
+namespace b200rl {
+
+// ------------------------------------------------------------------------------------------------ device
+// grid = 4 n blocks; block (i, c) owns channel group c (= frame plane c) of frame i:
+//   row-major    out_rm[i][pos][c*16 .. c*16+15]   (16 bytes = 4 rows x 4 pixels of grid position pos)
+//   channel-major out_cm[i][c*16 + sy*4 + sx][pos]  (448-byte rows, positions 441..447 zero)
+__global__ void __launch_bounds__(256) tc_frames_delta_s2d_u8(const uint8_t* __restrict__ newp, const int32_t* __restrict__ full_slot,
+                                                              const uint8_t* __restrict__ full, const uint8_t* __restrict__ prev_rm,
+                                                              const uint8_t* __restrict__ prev_cm, int64_t n,
+                                                              uint8_t* __restrict__ out_rm, uint8_t* __restrict__ out_cm) {
+    __shared__ __align__(16) uint8_t plane[7056];
+    const int64_t i = blockIdx.x >> 2;
+    const int c = blockIdx.x & 3;
+    const int slot = full_slot ? full_slot[i] : -1;
+    if (slot < 0 && c < 3) {
+        // shifted stack: plane c of this observation is plane c+1 of the previous one (already in storage layout)
+        const uint8_t* prm = prev_rm + i * 28224 + (c + 1) * 16;
+        uint8_t* orm = out_rm + i * 28224 + c * 16;
+        for (int pos = threadIdx.x; pos < 441; pos += 256)
+            *reinterpret_cast<int4*>(orm + pos * 64) = __ldg(reinterpret_cast<const int4*>(prm + pos * 64));
+        const int4* pcm = reinterpret_cast<const int4*>(prev_cm + (i * 64 + (c + 1) * 16) * 448);
+        int4* ocm = reinterpret_cast<int4*>(out_cm + (i * 64 + c * 16) * 448);
+        for (int t = threadIdx.x; t < 16 * 28; t += 256) ocm[t] = __ldg(pcm + t);
+        return;
+    }
+    const uint8_t* srcp = slot >= 0 ? full + (int64_t)slot * 28224 + c * 7056 : newp + i * 7056;
+    const int4* src = reinterpret_cast<const int4*>(srcp);
+    for (int t = threadIdx.x; t < 441; t += 256) reinterpret_cast<int4*>(plane)[t] = __ldg(src + t);
+    __syncthreads();
+    for (int pos = threadIdx.x; pos < 441; pos += 256) {
+        const int Y = pos / 21, X = pos - Y * 21;
+        const uint8_t* p = plane + (Y * 4) * 84 + X * 4;
+        int4 v;
+        v.x = *reinterpret_cast<const int*>(p); v.y = *reinterpret_cast<const int*>(p + 84);
+        v.z = *reinterpret_cast<const int*>(p + 168); v.w = *reinterpret_cast<const int*>(p + 252);
+        *reinterpret_cast<int4*>(out_rm + (i * 441 + pos) * 64 + c * 16) = v;
+    }
+    for (int t = threadIdx.x; t < 16 * 112; t += 256) {
+        const int ch = t / 112, q = t - ch * 112;
+        const int sy = ch >> 2, sx = ch & 3;
+        uint32_t w = 0;
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+            const int pos = q * 4 + e;
+            if (pos < 441) {
+                const int Y = pos / 21, X = pos - Y * 21;
+                w |= (uint32_t)plane[(Y * 4 + sy) * 84 + X * 4 + sx] << (8 * e);
+            }
+        }
+        *reinterpret_cast<uint32_t*>(out_cm + (i * 64 + c * 16 + ch) * 448 + q * 4) = w;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------ host
+// One tracker per vector env (or env group).  A small pool of worker threads (sleeping on a condition variable when idle)
+// runs two kinds of passes over env ranges: PACK (synchronous: copy planes into pinned staging) and VERIFY
+// (asynchronous: compare against the mirror, refresh the mirror).
+struct StackDelta {
+    int64_t n, plane_bytes;
+    int planes;
+    std::vector<uint8_t> mirror;     // [n][planes][plane_bytes]; logical plane j of the last observation = ring slot (base + j) % planes
+    int base = 0;
+    bool primed = false;
+
+    enum Kind { NONE, PACK_NEW, PACK_FULL, VERIFY };
+    struct Job {
+        Kind kind = NONE;
+        const uint8_t* obs = nullptr;
+        int64_t env_stride = 0;
+        uint8_t* out = nullptr;            // PACK_NEW: new_out, PACK_FULL: full_out
+        const int32_t* slot = nullptr;
+    } job;
+    std::vector<std::thread> workers;
+    std::mutex mu;
+    std::condition_variable cv_work, cv_done;
+    uint64_t seq = 0;                      // bumped per job
+    int running = 0;                       // workers still inside the current job
+    bool stop = false;
+    bool verify_pending = false;
+    std::atomic<int64_t> next{0};
+    std::vector<int32_t> mismatch;         // filled under mu
+    static constexpr int64_t kGrain = 8;   // envs per work item
+
+    StackDelta(int64_t n_, int planes_, int64_t pb, int threads) : n(n_), plane_bytes(pb), planes(planes_) {
+        mirror.resize((size_t)n * planes * pb);
+        for (int t = 0; t < threads; ++t) workers.emplace_back([this] { loop(); });
+    }
+    ~StackDelta() {
+        { std::lock_guard<std::mutex> g(mu); stop = true; }
+        cv_work.notify_all();
+        for (auto& w : workers) w.join();
+    }
+    uint8_t* mslot(int64_t i, int s) { return mirror.data() + ((size_t)i * planes + s) * plane_bytes; }
+
+    void run_range(const Job& j, int64_t a, int64_t b, std::vector<int32_t>& bad) {
+        const int P = planes;
+        const int64_t pb = plane_bytes;
+        for (int64_t i = a; i < b; ++i) {
+            const uint8_t* cur = j.obs + i * j.env_stride;
+            switch (j.kind) {
+                case PACK_NEW: memcpy(j.out + i * pb, cur + (P - 1) * pb, (size_t)pb); break;
+                case PACK_FULL: if (j.slot[i] >= 0) memcpy(j.out + (int64_t)j.slot[i] * P * pb, cur, (size_t)(P * pb)); break;
+                case VERIFY: {
+                    bool shifted = j.slot[i] < 0;
+                    if (shifted)
+                        for (int p = 0; p + 1 < P; ++p)
+                            if (memcmp(cur + p * pb, mslot(i, (base + p + 1) % P), (size_t)pb) != 0) { shifted = false; break; }
+                    if (shifted) {
+                        memcpy(mslot(i, base), cur + (P - 1) * pb, (size_t)pb);
+                    } else {
+                        if (j.slot[i] < 0) bad.push_back((int32_t)i);
+                        for (int p = 0; p < P; ++p) memcpy(mslot(i, (base + 1 + p) % P), cur + p * pb, (size_t)pb);
+                    }
+                    break;
+                }
+                default: break;
+            }
+        }
+    }
+    void work(const Job& j) {
+        std::vector<int32_t> bad;
+        for (;;) {
+            const int64_t a = next.fetch_add(kGrain);
+            if (a >= n) break;
+            run_range(j, a, a + kGrain < n ? a + kGrain : n, bad);
+        }
+        if (!bad.empty()) {
+            std::lock_guard<std::mutex> g(mu);
+            mismatch.insert(mismatch.end(), bad.begin(), bad.end());
+        }
+    }
+    void loop() {
+        uint64_t seen = 0;
+        for (;;) {
+            Job j;
+            {
+                std::unique_lock<std::mutex> g(mu);
+                cv_work.wait(g, [&] { return stop || seq != seen; });
+                if (stop) return;
+                seen = seq;
+                j = job;
+            }
+            work(j);
+            {
+                std::lock_guard<std::mutex> g(mu);
+                if (--running == 0) cv_done.notify_all();
+            }
+        }
+    }
+    void start(const Job& j) {               // caller holds no lock; no job may be in flight
+        if (workers.empty()) { next = 0; work(j); return; }
+        {
+            std::lock_guard<std::mutex> g(mu);
+            job = j;
+            next = 0;
+            running = (int)workers.size();
+            ++seq;
+        }
+        cv_work.notify_all();
+    }
+    void join() {
+        if (workers.empty()) return;
+        std::unique_lock<std::mutex> g(mu);
+        cv_done.wait(g, [&] { return running == 0; });
+    }
+    void finish_verify() {
+        if (!verify_pending) return;
+        join();
+        base = (base + 1) % planes;
+        primed = true;
+        verify_pending = false;
+    }
+};
+
+}  // namespace b200rl
+
+using namespace b200rl;
+
+extern "C" int b200rl_frames_delta_s2d_u8(const uint8_t* new_planes, const int32_t* full_slot, const uint8_t* full_frames,
+                                          const uint8_t* prev_rm, const uint8_t* prev_cm, int64_t n,
+                                          uint8_t* out_rm, uint8_t* out_cm, void* stream) {
+    B200RL_REQUIRE(n >= 0, "frames_delta_s2d_u8: negative n");
+    if (n == 0) return B200RL_OK;
+    B200RL_REQUIRE(new_planes && prev_rm && prev_cm && out_rm && out_cm, "frames_delta_s2d_u8: null pointer");
+    B200RL_REQUIRE(!full_slot || full_frames, "frames_delta_s2d_u8: full_slot without full_frames");
+    B200RL_REQUIRE(aligned(new_planes, 16) && aligned(prev_rm, 16) && aligned(prev_cm, 16) && aligned(out_rm, 16) && aligned(out_cm, 16) &&
+                   aligned(full_frames, 16) && aligned(full_slot, 4), "frames_delta_s2d_u8: misaligned buffer");
+    B200RL_REQUIRE(out_rm != prev_rm && out_cm != prev_cm, "frames_delta_s2d_u8: in-place update is not supported");
+    B200RL_REQUIRE(n <= (int64_t)1 << 28, "frames_delta_s2d_u8: n too large");
+    cudaStream_t s = (cudaStream_t)stream;
+    ProfScope ps(s, "frames_delta", 0, (double)n * (7056 + 21168 + 21504 + 28224 + 28672));
+    tc_frames_delta_s2d_u8<<<(unsigned)(n * 4), 256, 0, s>>>(new_planes, full_slot, full_frames, prev_rm, prev_cm, n, out_rm, out_cm);
+    return check_launch("frames_delta_s2d_u8");
+}
+
+extern "C" int b200rl_h2d_rows_async(void* dst, const void* src, int64_t src_pitch, int64_t row_bytes, int64_t rows, void* stream) {
+    B200RL_REQUIRE(rows >= 0 && row_bytes >= 0 && src_pitch >= row_bytes, "h2d_rows_async: bad geometry");
+    if (rows == 0 || row_bytes == 0) return B200RL_OK;
+    B200RL_REQUIRE(dst && src, "h2d_rows_async: null pointer");
+    cudaError_t e = src_pitch == row_bytes
+        ? cudaMemcpyAsync(dst, src, (size_t)(rows * row_bytes), cudaMemcpyHostToDevice, (cudaStream_t)stream)
+        : cudaMemcpy2DAsync(dst, (size_t)row_bytes, src, (size_t)src_pitch, (size_t)row_bytes, (size_t)rows, cudaMemcpyHostToDevice,
+                            (cudaStream_t)stream);
+    if (e != cudaSuccess) return fail(B200RL_ERR_CUDA, "h2d_rows_async: %s", cudaGetErrorString(e));
+    return B200RL_OK;
+}
+
+extern "C" void* b200rl_stackdelta_create(int64_t n_envs, int planes, int64_t plane_bytes, int threads) {
+    if (n_envs < 1 || planes < 2 || planes > 64 || plane_bytes < 1 || threads < 0 || threads > 256) {
+        fail(B200RL_ERR_INVALID_ARGUMENT, "stackdelta_create: bad arguments (n_envs=%lld planes=%d plane_bytes=%lld threads=%d)",
+             (long long)n_envs, planes, (long long)plane_bytes, threads);
+        return nullptr;
+    }
+    try {
+        return new StackDelta(n_envs, planes, plane_bytes, threads);
+    } catch (const std::exception& e) {
+        fail(B200RL_ERR_INVALID_ARGUMENT, "stackdelta_create: %s", e.what());
+        return nullptr;
+    }
+}
+
+extern "C" void b200rl_stackdelta_destroy(void* h) {
+    if (!h) return;
+    StackDelta* sd = reinterpret_cast<StackDelta*>(h);
+    if (sd->verify_pending) sd->join();
+    delete sd;
+}
+
+extern "C" void b200rl_stackdelta_invalidate(void* h) {
+    if (!h) return;
+    StackDelta* sd = reinterpret_cast<StackDelta*>(h);
+    sd->finish_verify();
+    sd->primed = false;
+}
+
+extern "C" int64_t b200rl_stackdelta_begin(void* h, const uint8_t* obs, int64_t env_stride, const float* done,
+                                           uint8_t* new_out, uint8_t* full_out, int32_t* slot_out) {
+    if (!h || !obs || !full_out || !slot_out) return (int64_t)fail(B200RL_ERR_INVALID_ARGUMENT, "stackdelta_begin: null pointer");
+    StackDelta* sd = reinterpret_cast<StackDelta*>(h);
+    if (env_stride < sd->planes * sd->plane_bytes)
+        return (int64_t)fail(B200RL_ERR_INVALID_ARGUMENT, "stackdelta_begin: env_stride %lld smaller than one observation", (long long)env_stride);
+    if (sd->verify_pending)
+        return (int64_t)fail(B200RL_ERR_INVALID_ARGUMENT, "stackdelta_begin: the previous pass was not joined (call b200rl_stackdelta_wait)");
+    int64_t k = 0;
+    for (int64_t i = 0; i < sd->n; ++i) slot_out[i] = (!sd->primed || (done && done[i] != 0.f)) ? (int32_t)k++ : -1;
+    StackDelta::Job j;
+    j.obs = obs; j.env_stride = env_stride; j.slot = slot_out;
+    if (k > 0) {
+        if (k <= 32) {                       // a handful of resets: cheaper than waking the pool
+            std::vector<int32_t> none;
+            j.kind = StackDelta::PACK_FULL; j.out = full_out;
+            sd->run_range(j, 0, sd->n, none);
+        } else {
+            j.kind = StackDelta::PACK_FULL; j.out = full_out;
+            sd->start(j); sd->join();
+        }
+    }
+    if (new_out) {
+        j.kind = StackDelta::PACK_NEW; j.out = new_out;
+        sd->start(j); sd->join();
+    }
+    j.kind = StackDelta::VERIFY; j.out = nullptr;
+    sd->mismatch.clear();
+    sd->verify_pending = true;
+    sd->start(j);
+    return k;
+}
+
+extern "C" int64_t b200rl_stackdelta_wait(void* h, int32_t* mismatch_out) {
+    if (!h) return (int64_t)fail(B200RL_ERR_INVALID_ARGUMENT, "stackdelta_wait: null handle");
+    StackDelta* sd = reinterpret_cast<StackDelta*>(h);
+    sd->finish_verify();
+    const int64_t m = (int64_t)sd->mismatch.size();
+    if (m > 0 && mismatch_out) {
+        std::vector<int32_t> s(sd->mismatch);
+        std::sort(s.begin(), s.end());
+        memcpy(mismatch_out, s.data(), (size_t)m * sizeof(int32_t));
+    }
+    sd->mismatch.clear();
+    return m;
+}

@@ -531,6 +531,106 @@ def frames_to_s2d_u8(obs_u8, out_rm=None, out_cm=None, rows=None):
     return out_rm, out_cm
 
 
+def frames_delta_s2d_u8(new_planes, prev_rm, prev_cm, out_rm, out_cm, full_slot=None, full_frames=None):
+    """Rollout slot t from slot t-1 and the newest frame plane of every env (frame-stack delta upload, csrc/frame_stack.cu):
+    ``new_planes`` u8 [n,7056]; envs with ``full_slot[i] = k >= 0`` take all four planes from ``full_frames[k]`` instead."""
+    lib = _lib.load()
+    n = new_planes.shape[0]
+    for nm, t in (("new_planes", new_planes), ("prev_rm", prev_rm), ("prev_cm", prev_cm), ("out_rm", out_rm), ("out_cm", out_cm)):
+        _contig(t, nm)
+        assert t.shape[0] == n, nm
+    if full_slot is not None:
+        _contig(full_slot, "full_slot"); _contig(full_frames, "full_frames")
+        assert full_slot.shape[0] == n
+    rc = lib.b200rl_frames_delta_s2d_u8(_ptr(new_planes, torch.uint8, "new_planes"), _ptr(full_slot, torch.int32, "full_slot", True),
+                                        _ptr(full_frames, torch.uint8, "full_frames", True), _ptr(prev_rm, torch.uint8, "prev_rm"),
+                                        _ptr(prev_cm, torch.uint8, "prev_cm"), n, _ptr(out_rm, torch.uint8, "out_rm"),
+                                        _ptr(out_cm, torch.uint8, "out_cm"), _stream())
+    _lib.check(rc, "frames_delta_s2d_u8")
+
+
+def h2d_rows_async(dst, src_ptr, src_pitch, row_bytes, rows, stream=None):
+    """``rows`` rows of ``row_bytes`` from pitched host memory at address ``src_ptr`` into the dense device tensor ``dst``."""
+    lib = _lib.load()
+    assert dst.is_contiguous() and dst.numel() * dst.element_size() >= rows * row_bytes
+    rc = lib.b200rl_h2d_rows_async(dst.data_ptr(), src_ptr, src_pitch, row_bytes, rows,
+                                   stream.cuda_stream if stream is not None else _stream())
+    _lib.check(rc, "h2d_rows_async")
+
+
+class StackDeltaTracker:
+    """Host side of the frame-stack delta upload for one vector env of ``n`` envs (b200rl_stackdelta_*): private mirror of
+    every env's last observation + worker threads that verify, off the critical path, that the newest observation really
+    is the previous one shifted by a plane for every env not flagged done."""
+
+    def __init__(self, n, planes=4, plane_bytes=7056, threads=None, pinned=True):
+        lib = _lib.load()
+        if threads is None:
+            import os
+            ranks = max(1, int(os.environ.get("LOCAL_WORLD_SIZE", "1")))        # one process per GPU shares the host cores
+            threads = int(os.environ.get("CLEANRL_B200_HOST_THREADS", min(16, max(2, (os.cpu_count() or 2) // (4 * ranks)))))
+        self.n, self.planes, self.plane_bytes = int(n), int(planes), int(plane_bytes)
+        self._h = lib.b200rl_stackdelta_create(self.n, self.planes, self.plane_bytes, int(threads))
+        if not self._h:
+            _lib.check(-1, "stackdelta_create")
+        pin = pinned and torch.cuda.is_available()
+        mk = lambda shape, dt: (torch.zeros(shape, dtype=dt).pin_memory() if pin else torch.zeros(shape, dtype=dt))
+        self.new_h = mk((self.n, self.plane_bytes), torch.uint8)
+        self.full_h = mk((self.n, self.planes * self.plane_bytes), torch.uint8)
+        self.slot_h = mk((self.n,), torch.int32)
+        self.mis_h = torch.zeros(self.n, dtype=torch.int32)
+        self._pending = False
+
+    def begin(self, obs, done=None, pack_new=True):
+        """obs: uint8 ndarray [n, planes, ...] whose planes are contiguous per env (any env stride).  Returns the number of
+        envs staged as full frames; ``slot_h`` / ``full_h`` (and ``new_h`` when ``pack_new``) are filled on return."""
+        lib = _lib.load()
+        assert obs.dtype.name == "uint8" and obs.shape[0] == self.n
+        itemsz = self.planes * self.plane_bytes
+        inner = 1
+        for d, st in zip(obs.shape[:0:-1], obs.strides[:0:-1]):
+            assert st == inner, "observation planes must be contiguous per env"
+            inner *= d
+        assert inner == itemsz, "observation size does not match the tracker geometry"
+        d32 = None
+        if done is not None:
+            import numpy as np
+            d32 = np.ascontiguousarray(done, dtype=np.float32).reshape(-1)
+            assert d32.shape[0] == self.n
+        self._keep = (obs, d32)                                  # the workers read these until wait()
+        k = lib.b200rl_stackdelta_begin(self._h, obs.__array_interface__["data"][0], int(obs.strides[0]),
+                                        d32.__array_interface__["data"][0] if d32 is not None else None,
+                                        self.new_h.data_ptr() if pack_new else None, self.full_h.data_ptr(), self.slot_h.data_ptr())
+        if k < 0:
+            _lib.check(int(k), "stackdelta_begin")
+        self._pending = True
+        return int(k)
+
+    def wait(self):
+        """Join the verification; returns the (ascending) indices of envs that were NOT a shifted stack although not done."""
+        if not self._pending:
+            return self.mis_h[:0].numpy()
+        m = _lib.load().b200rl_stackdelta_wait(self._h, self.mis_h.data_ptr())
+        self._pending = False
+        self._keep = None
+        if m < 0:
+            _lib.check(int(m), "stackdelta_wait")
+        return self.mis_h[:int(m)].numpy()
+
+    def invalidate(self):
+        if self._pending:
+            self.wait()
+        _lib.load().b200rl_stackdelta_invalidate(self._h)
+
+    def __del__(self):
+        h, self._h = getattr(self, "_h", None), None
+        if h:
+            try:
+                _lib.load().b200rl_stackdelta_destroy(h)
+            except Exception:
+                pass
+
+
 # ----------------------------------------------------------- diagonal Gaussian policy
 def gaussian_sample(mean, logstd, noise, value_in=None, out=None):
     """action, logprob, entropy[, value] for Normal(mean, exp(logstd)) with caller-supplied N(0,1) noise

@@ -147,6 +147,13 @@ class PPOEngine:
             self.chunk_events = [torch.cuda.Event() for _ in range(self.h2d_chunks)]
             self.noise_buf = torch.zeros(agent.noise_shape(N), dtype=f32, device=device)
         self._parts = None
+        # frame-stack delta upload (grouped loop, uint8 rollout): only the newest frame plane of every env crosses PCIe, the
+        # device rebuilds slot t from slot t-1, a host worker pool verifies the shifted-stack property (csrc/frame_stack.cu)
+        self.delta_upload = bool(getattr(self, "u8_rollout", False)) and os.environ.get("CLEANRL_B200_DELTA_UPLOAD", "1") != "0"
+        self._delta_allowed = self.delta_upload      # trackers / staging exist; ``delta_upload`` is the current state
+        self._delta = None
+        self.delta_redos = 0             # steps redone because an env broke the shifted-stack contract without being done
+        self.delta_full_frames = 0       # env observations uploaded whole (resets, first step, redos)
         self._graphs = {}
         self._graph_pool = None
         self._graph_kernels = {}
@@ -326,18 +333,28 @@ class PPOEngine:
             self.noise_buf = torch.zeros(self.agent.noise_shape(N), dtype=torch.float32, device=self.device)
         if not hasattr(self, "obs_u8"):
             self.obs_u8 = None
+        self._noise_bufs = [self.noise_buf, torch.zeros_like(self.noise_buf)]      # by step parity (see _redo_part)
+        self._delta = None
+        if self._delta_allowed and self._graphable():
+            u8 = torch.uint8
+            self._delta = [dict(tr=ops.StackDeltaTracker(n), full_d=torch.zeros((n, 28224), dtype=u8, device=self.device),
+                                last=None, boot_obs=None, consumed=torch.cuda.Event()) for _ in range(P)]
+            self._new_d = torch.zeros((N, 7056), dtype=u8, device=self.device)
+            self._slot_d = torch.zeros(N, dtype=torch.int32, device=self.device)
 
     def _part_work(self, step, lo, hi):
         sl = slice(lo, hi)
         if self.s2d:
             self._to_storage(self.obs_u8[sl], step, sl)
         self.agent.sample_into(self.obs[step][sl], self.actions[step][sl], self.logprobs[step][sl], self.values[step][sl],
-                               noise=self.noise_buf[sl])
+                               noise=self._noise_bufs[step & 1][sl])
 
     @torch.no_grad()
     def launch_part(self, step, part, obs_np, done_np):
         """Enqueue everything group ``part`` needs at ``step``: H2D of its frames (copy stream, in chunks), storage
         conversion + policy + sampler per chunk (main stream, graph replays), D2H of its actions.  Returns immediately."""
+        if self._delta is not None and self.delta_upload:
+            return self._launch_part_delta(step, part, obs_np, done_np)
         lo, hi = self._parts[part]
         src = torch.from_numpy(np.ascontiguousarray(obs_np))
         if src.dtype != self.obs_dtype:
@@ -354,7 +371,7 @@ class PPOEngine:
         self.h2d_bytes += src.numel() * src.element_size()
         self.dones_h[step][lo:hi].copy_(torch.as_tensor(np.asarray(done_np, dtype=np.float32)))
         if part == 0:
-            self.agent.draw_noise_into(self.noise_buf)         # the step's ONE noise draw, all N envs
+            self.agent.draw_noise_into(self._noise_bufs[step & 1])         # the step's ONE noise draw, all N envs
         for c, (clo, chi) in enumerate(self._part_chunks[part]):
             main.wait_event(self._part_h2d[part][c])
             self._run_graphed(lambda: self._part_work(step, clo, chi), ("part", step, part, c), warm_key=("p", part, c))
@@ -366,7 +383,129 @@ class PPOEngine:
         """Host view of group ``part``'s actions of the step launched last (blocks on that group's D2H event only)."""
         lo, hi = self._parts[part]
         self._part_d2h[part].synchronize()
+        if self._delta is not None:
+            self._join_part(part)
         return self.actions_h[lo:hi].numpy()
+
+    # ---- frame-stack delta upload (csrc/frame_stack.cu): the observation of cleanrl/ppo_atari_envpool.py:185-196 is a stack
+    # of the 4 newest frames, so planes 0..2 of an env's observation are planes 1..3 of its previous one unless it was reset.
+    # Only the newest plane is uploaded (7 KB instead of 28 KB per env); the device rebuilds slot t from slot t-1.  Envs
+    # flagged done go up whole; a host worker pool memcmp's the other envs against a private mirror while the device already
+    # works, and a step whose env broke the contract without being done is redone from full frames before its actions are
+    # handed out (``delta_redos``; an env that is not frame-stacked at all switches the engine back to whole uploads).
+    def _slot_pair(self, step):
+        """(row-major, channel-major) storage of rollout slot ``step``; ``T`` = the bootstrap slot."""
+        return (self.next_obs, self.next_obs_t) if step == self.T else (self.obs[step], self.obs_t[step])
+
+    def _part_work_delta(self, step, part, lo, hi, sample, reuse):
+        sl = slice(lo, hi)
+        dst_rm, dst_cm = self._slot_pair(step)
+        if reuse:            # step 0 of an iteration: the observation is the one the bootstrap slot already holds
+            dst_rm[sl].copy_(self.next_obs[sl])
+            dst_cm[sl].copy_(self.next_obs_t[sl])
+        else:
+            prev_rm, prev_cm = self._slot_pair(self.T if step == 0 else step - 1)
+            ops.frames_delta_s2d_u8(self._new_d[sl], prev_rm[sl], prev_cm[sl], dst_rm[sl], dst_cm[sl],
+                                    full_slot=self._slot_d[sl], full_frames=self._delta[part]["full_d"])
+        if sample:
+            self.agent.sample_into(dst_rm[sl], self.actions[step][sl], self.logprobs[step][sl], self.values[step][sl],
+                                   noise=self._noise_bufs[step & 1][sl])
+
+    @staticmethod
+    def _host_pinned(arr):
+        try:
+            return bool(torch.from_numpy(arr).is_pinned())
+        except Exception:
+            return False
+
+    def _launch_part_delta(self, step, part, obs_np, done_np, sample=True):
+        lo, hi = self._parts[part]
+        n = hi - lo
+        d = self._delta[part]
+        tr = d["tr"]
+        main, cs = torch.cuda.current_stream(), self.copy_stream
+        reuse = step == 0 and d["boot_obs"] is not None and d["boot_obs"] is obs_np
+        d["boot_obs"] = obs_np if step == self.T else None
+        if reuse:
+            d["last"] = None
+            for c in range(len(self._part_chunks[part])):
+                self._part_h2d[part][c].record(main)
+        else:
+            obs = np.asarray(obs_np)
+            if obs.dtype != np.uint8 or obs.ndim != 4 or obs.strides[1:] != (7056, 84, 1):
+                obs = np.ascontiguousarray(obs, dtype=np.uint8)
+            if step == 0:
+                tr.invalidate()          # an observation the engine has not seen before: every env goes up whole
+            pinned = self._host_pinned(obs)
+            k = tr.begin(obs, done_np, pack_new=not pinned)
+            cs.wait_event(d["consumed"])                 # the staging buffers' last readers on the main stream
+            if k:
+                ops.h2d_rows_async(d["full_d"], tr.full_h.data_ptr(), k * 28224, k * 28224, 1, cs)
+            ops.h2d_rows_async(self._slot_d[lo:hi], tr.slot_h.data_ptr(), n * 4, n * 4, 1, cs)
+            if pinned:
+                src, pitch = obs.__array_interface__["data"][0] + 3 * 7056, int(obs.strides[0])
+            else:
+                src, pitch = tr.new_h.data_ptr(), 7056
+            for c, (clo, chi) in enumerate(self._part_chunks[part]):
+                ops.h2d_rows_async(self._new_d[clo:chi], src + (clo - lo) * pitch, pitch, 7056, chi - clo, cs)
+                self._part_h2d[part][c].record(cs)
+            self.h2d_bytes += n * (7056 + 4) + k * 28224
+            self.delta_full_frames += k
+            d["last"] = (step, obs, k, sample)
+        if sample:
+            self.dones_h[step][lo:hi].copy_(torch.as_tensor(np.asarray(done_np, dtype=np.float32)))
+            if part == 0:
+                self.agent.draw_noise_into(self._noise_bufs[step & 1])        # the step's ONE noise draw, all N envs
+        for c, (clo, chi) in enumerate(self._part_chunks[part]):
+            main.wait_event(self._part_h2d[part][c])
+            self._run_graphed(lambda: self._part_work_delta(step, part, clo, chi, sample, reuse),
+                              ("dpart", step, part, c, reuse), warm_key=("dp", part, c, sample, reuse))
+        d["consumed"].record(main)
+        if sample:
+            self.actions_h[lo:hi].copy_(self.actions[step][lo:hi], non_blocking=True)
+            self._part_d2h[part].record(main)
+            self.d2h_bytes += n * self.actions_h.element_size() * max(1, self.act_dim)
+
+    def _join_part(self, part):
+        """Join the host-side verification of the observation launched last for ``part``; redo the step from full frames
+        for envs that were not a shifted stack although not done."""
+        d = self._delta[part]
+        if d["last"] is None:
+            return
+        mis = d["tr"].wait()
+        if len(mis):
+            self._redo_part(part, mis)
+        d["last"] = None
+
+    def _redo_part(self, part, mis):
+        lo, hi = self._parts[part]
+        n = hi - lo
+        d = self._delta[part]
+        tr = d["tr"]
+        step, obs, k, sample = d["last"]
+        main = torch.cuda.current_stream()
+        self.copy_stream.synchronize()                   # the pinned staging buffers are about to be rewritten
+        main.synchronize()
+        m = len(mis)
+        full = tr.full_h.numpy().reshape(n, 4, 84, 84)
+        slot = tr.slot_h.numpy()
+        for j, i in enumerate(mis):
+            full[k + j] = obs[i]
+            slot[i] = k + j
+        ops.h2d_rows_async(d["full_d"][k:k + m], tr.full_h.data_ptr() + k * 28224, m * 28224, m * 28224, 1, main)
+        ops.h2d_rows_async(self._slot_d[lo:hi], tr.slot_h.data_ptr(), n * 4, n * 4, 1, main)
+        for clo, chi in self._part_chunks[part]:
+            self._part_work_delta(step, part, clo, chi, sample, False)       # eager; same noise rows as the first attempt
+        if sample:
+            self.actions_h[lo:hi].copy_(self.actions[step][lo:hi], non_blocking=True)
+        main.synchronize()
+        self.h2d_bytes += m * 28224 + n * 4
+        self.delta_full_frames += m
+        self.delta_redos += 1
+        if m > n // 8:
+            # this env does not deliver shifted frame stacks (no frame stacking, or a different stacking order):
+            # go back to whole-observation uploads for the rest of the run
+            self.delta_upload = False
 
     def collect(self, env_parts, obs_parts, done_parts, on_step=None):
         """One rollout of T steps over ``env_parts`` (gym-0.23 style ``step(a) -> obs, reward, done, info``), software
@@ -394,6 +533,12 @@ class PPOEngine:
     def finish_rollout_parts(self, obs_parts, done_parts):
         """``finish_rollout`` for the grouped loop: bootstrap observation / done of every group."""
         nd = np.concatenate([np.asarray(d, dtype=np.float32).reshape(-1) for d in done_parts])
+        if self._delta is not None and self.delta_upload:
+            for p in range(len(self._parts)):
+                self._launch_part_delta(self.T, p, obs_parts[p], done_parts[p], sample=False)
+            for p in range(len(self._parts)):
+                self._join_part(p)
+            return self.finish_rollout(None, nd, resident=False, obs_uploaded=True)   # (a redo leaves the slot correct too)
         if self.s2d:
             for (lo, hi), o in zip(self._parts, obs_parts):
                 src = torch.from_numpy(np.ascontiguousarray(o))

@@ -22,6 +22,11 @@ Two observation modes:
            later observation (used for parity runs).
 ``pool``   whole pre-generated pinned batches are handed out round-robin at
            ~zero host cost (used for throughput runs; data = "synthetic").
+``stack``  (Atari only) frame-stacked like envpool's ``stack_num=4`` observation
+           (cleanrl/ppo_atari_envpool.py:185-196): planes 0..2 of an env's
+           observation are planes 1..3 of its previous one, a done env comes back
+           with four fresh planes.  Observations are strided zero-copy windows into
+           one pinned frame ring (also ~zero host cost).
 
 The environments own their ``np.random.Generator`` and never touch numpy's
 global RNG (that one drives the minibatch shuffle, cleanrl/ppo.py:155,245).
@@ -79,7 +84,7 @@ class SyntheticAtariVec:
 
     def __init__(self, num_envs, seed=1, mode="fresh", n_actions=4, obs_shape=(4, 84, 84),
                  pool=32, p_done=0.02, pinned=False):
-        assert mode in ("fresh", "pool")
+        assert mode in ("fresh", "pool", "stack")
         self.num_envs = int(num_envs)
         self.mode = mode
         self.observation_space = Box(0, 255, obs_shape, np.uint8)
@@ -91,6 +96,16 @@ class SyntheticAtariVec:
             self._frames = self._rng.integers(0, 256, size=(pool,) + tuple(obs_shape), dtype=np.uint8)
             self._idx = np.zeros(self.num_envs, dtype=np.int64)
             self._obs = _alloc_host((self.num_envs,) + tuple(obs_shape), np.uint8, pinned)
+        elif mode == "stack":
+            # frame ring [N, P+C-1, H, W]: the observation at time t is the window ring[:, w:w+C] with w = t mod P; planes
+            # P..P+C-2 duplicate planes 0..C-2 so that the window after w = P-1 (w = 0) is again a shift by one plane
+            C, H, W = obs_shape
+            self._P = P = max(int(pool), 2 * C)
+            self._ring = _alloc_host((self.num_envs, P + C - 1, H, W), np.uint8, pinned)
+            self._bank = self._rng.integers(0, 256, size=(64, H, W), dtype=np.uint8)       # fresh planes for resets
+            for q in range(P):
+                self._ring[:, q] = self._rng.integers(0, 256, size=(self.num_envs, H, W), dtype=np.uint8)
+            self._ring[:, P:] = self._ring[:, :C - 1]
         else:
             pool = min(int(pool), 8)
             self._batches = _alloc_host((pool, self.num_envs) + tuple(obs_shape), np.uint8, pinned)
@@ -107,6 +122,8 @@ class SyntheticAtariVec:
             self._idx = self._rng.integers(0, len(self._frames), size=self.num_envs)
             np.take(self._frames, self._idx, axis=0, out=self._obs)
             return self._obs
+        if self.mode == "stack":
+            return self._ring[:, 0:self.observation_space.shape[0]]
         return self._batches[0]
 
     def step(self, action):
@@ -130,6 +147,21 @@ class SyntheticAtariVec:
             self._idx = (self._idx * 5 + action + 1 + self._t) % len(self._frames)
             np.take(self._frames, self._idx, axis=0, out=self._obs)
             obs = self._obs
+        elif self.mode == "stack":
+            C, P = self.observation_space.shape[0], self._P
+            w = self._t % P
+            idx = np.nonzero(done)[0]
+            if len(idx):
+                # a done env returns a reset observation: the C-1 planes it would share with its previous observation
+                # get fresh content (and so do their wrap-around duplicates)
+                for q in range(w, w + C - 1):
+                    fresh = self._bank[self._rng.integers(0, len(self._bank), size=len(idx))]
+                    self._ring[idx, q] = fresh
+                    if q < C - 1:
+                        self._ring[idx, q + P] = fresh
+                    elif q >= P:
+                        self._ring[idx, q - P] = fresh
+            obs = self._ring[:, w:w + C]
         else:
             obs = self._batches[self._t % len(self._batches)]
         return obs, reward, done, info

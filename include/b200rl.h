@@ -267,6 +267,37 @@ int b200rl_frames_to_s2d_bf16(const uint8_t* obs, const int64_t* rows, int64_t n
  *                                                  uint8 -> fp16 in registers, fed to the MMA from tensor memory)
  * channel = c*16 + sy*4 + sx of source pixel (4Y+sy, 4X+sx), grid row = Y*21 + X; rows 441..447 of out_cm are zero. */
 int b200rl_frames_to_s2d_u8(const uint8_t* obs, const int64_t* rows, int64_t n, uint8_t* out_rm, uint8_t* out_cm, void* stream);
+/* Frame-stack delta upload (csrc/frame_stack.cu).  The Atari observation the reference uploads whole every step
+ * (cleanrl/ppo_atari_envpool.py:185-196 stack_num=4, :226,239 `torch.Tensor(next_obs).to(device)`) is a stack of the 4 newest
+ * frames: planes 0..2 of an env's observation are planes 1..3 of its previous one unless the env was reset.  Only the newest
+ * plane (7 056 B instead of 28 224 B per env) has to cross PCIe; the device rebuilds rollout slot t from slot t-1:
+ *   new_planes  u8 [n, 7056]   newest plane of every env
+ *   full_slot   i32 [n] or NULL: -1 = shifted stack, k >= 0 = take all 4 planes from full_frames[k] (u8 [*, 4, 84, 84])
+ *   prev_rm/prev_cm            the previous slot in the two B200RL_OBS_S2D_U8 orientations (must not alias the outputs) */
+int b200rl_frames_delta_s2d_u8(const uint8_t* new_planes, const int32_t* full_slot, const uint8_t* full_frames,
+                               const uint8_t* prev_rm, const uint8_t* prev_cm, int64_t n,
+                               uint8_t* out_rm, uint8_t* out_cm, void* stream);
+/* rows x row_bytes from pitched (pinned) host memory into a dense device buffer (cudaMemcpy2DAsync): the newest planes are
+ * uploaded straight from the env's own observation batch, no host-side packing. */
+int b200rl_h2d_rows_async(void* dst, const void* src, int64_t src_pitch, int64_t row_bytes, int64_t rows, void* stream);
+/* Host-side tracker, one per vector env (HOST pointers; no stream).  It owns a private mirror of every env's last
+ * observation and a pool of `threads` worker threads (0 = run inline).
+ *   begin(): env i's observation starts at obs + i*env_stride (planes contiguous).  Envs with done[i] != 0 (f32, may be NULL)
+ *            -- and every env on the first pass / after invalidate() -- are staged as full frames: full_out[k] (pinned,
+ *            [n, planes*plane_bytes]) and slot_out[i] = k; all other envs get slot_out[i] = -1.  new_out (pinned
+ *            [n, plane_bytes], may be NULL when the caller uploads the newest planes from `obs` itself) receives the newest
+ *            planes.  Returns the number of full frames (>= 0; negative = error) and starts the ASYNCHRONOUS verification:
+ *            the workers memcmp the first planes-1 planes of every slot -1 env against the mirror and refresh the mirror.
+ *            `obs` must stay unchanged until wait() returns.
+ *   wait():  joins the verification; returns how many slot -1 envs did NOT hold the shifted stack (their indices, ascending,
+ *            in mismatch_out i32 [n]): the caller must re-stage those as full frames and redo the step.  Every begin() must
+ *            be followed by one wait(). */
+void* b200rl_stackdelta_create(int64_t n_envs, int planes, int64_t plane_bytes, int threads);
+void b200rl_stackdelta_destroy(void* tracker);
+void b200rl_stackdelta_invalidate(void* tracker);
+int64_t b200rl_stackdelta_begin(void* tracker, const uint8_t* obs, int64_t env_stride, const float* done,
+                                uint8_t* new_out, uint8_t* full_out, int32_t* slot_out);
+int64_t b200rl_stackdelta_wait(void* tracker, int32_t* mismatch_out);
 int64_t b200rl_naturecnn_param_count(int A);
 size_t b200rl_naturecnn_bf16_packed_bytes(int A);
 size_t b200rl_naturecnn_bf16_acts_bytes(int64_t n, int obs_format);
