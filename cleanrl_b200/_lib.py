@@ -80,7 +80,20 @@ SIGNATURES = {
     "b200rl_stackdelta_invalidate": (None, [_p]),
     "b200rl_stackdelta_begin": (_i64, [_p, _p, _i64, _p, _p, _p, _p]),
     "b200rl_stackdelta_wait": (_i64, [_p, _p]),
+    "b200rl_stackdelta_launch": (_i64, [_p, _p, _i64, _p]),
+    "b200rl_stackdelta_join": (_i64, [_p, _p, _p]),
 }
+
+
+
+class PartLaunch(C.Structure):
+    """struct B200rlPartLaunch (include/b200rl.h)."""
+    _fields_ = [("tracker", _p), ("copy_stream", _p), ("main_stream", _p), ("consumed_event", _p),
+                ("n", C.c_int32), ("nchunks", C.c_int32), ("chunk_lo", C.c_int32 * 4), ("chunk_hi", C.c_int32 * 4),
+                ("h2d_event", _p * 4), ("graph_exec", _p * 4),
+                ("new_d", _p), ("slot_d", _p), ("full_d", _p), ("new_h", _p), ("full_h", _p), ("slot_h", _p),
+                ("actions_d", _p), ("actions_h", _p), ("actions_bytes", _i64), ("d2h_event", _p)]
+
 
 _lib = None
 

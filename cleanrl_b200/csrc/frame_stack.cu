@@ -304,3 +304,61 @@ extern "C" int64_t b200rl_stackdelta_wait(void* h, int32_t* mismatch_out) {
     sd->mismatch.clear();
     return m;
 }
+
+// ------------------------------------------------------------------------------------------------ one-call launcher
+// Everything one env group needs enqueued for one rollout step, in ONE call from the host language (the per-step host
+// overhead of the grouped loop is what bounds the end-to-end rollout once only a plane per env crosses PCIe):
+// classify + stage + start the verification (tracker), H2D of the staged pieces on the copy stream, the captured step
+// graphs of every chunk on the main stream behind their upload events, the actions D2H and its event.
+extern "C" int64_t b200rl_stackdelta_launch(const B200rlPartLaunch* p, const uint8_t* obs, int64_t env_stride, const float* done) {
+    if (!p || p->nchunks < 1 || p->nchunks > 4) return (int64_t)fail(B200RL_ERR_INVALID_ARGUMENT, "stackdelta_launch: bad plan");
+    cudaStream_t cs = (cudaStream_t)p->copy_stream, ms = (cudaStream_t)p->main_stream;
+    int64_t k = 0;
+    cudaError_t e = cudaSuccess;
+    auto ok = [&](cudaError_t r) { if (e == cudaSuccess && r != cudaSuccess) e = r; };
+    if (p->tracker) {
+        if (!obs) return (int64_t)fail(B200RL_ERR_INVALID_ARGUMENT, "stackdelta_launch: null observation batch");
+        StackDelta* sd = reinterpret_cast<StackDelta*>(p->tracker);
+        const int64_t pb = sd->plane_bytes, fb = sd->planes * sd->plane_bytes;
+        bool pinned = false;
+        cudaPointerAttributes attr;
+        if (cudaPointerGetAttributes(&attr, obs) == cudaSuccess) pinned = attr.type == cudaMemoryTypeHost;
+        else cudaGetLastError();
+        k = b200rl_stackdelta_begin(p->tracker, obs, env_stride, done, pinned ? nullptr : p->new_h, p->full_h, p->slot_h);
+        if (k < 0) return k;
+        ok(cudaStreamWaitEvent(cs, (cudaEvent_t)p->consumed_event, 0));
+        if (k > 0) ok(cudaMemcpyAsync(p->full_d, p->full_h, (size_t)(k * fb), cudaMemcpyHostToDevice, cs));
+        ok(cudaMemcpyAsync(p->slot_d, p->slot_h, (size_t)p->n * sizeof(int32_t), cudaMemcpyHostToDevice, cs));
+        for (int c = 0; c < p->nchunks; ++c) {
+            const int64_t lo = p->chunk_lo[c], rows = p->chunk_hi[c] - p->chunk_lo[c];
+            if (pinned)
+                ok(cudaMemcpy2DAsync(p->new_d + lo * pb, (size_t)pb, obs + lo * env_stride + (sd->planes - 1) * pb, (size_t)env_stride,
+                                     (size_t)pb, (size_t)rows, cudaMemcpyHostToDevice, cs));
+            else
+                ok(cudaMemcpyAsync(p->new_d + lo * pb, p->new_h + lo * pb, (size_t)(rows * pb), cudaMemcpyHostToDevice, cs));
+            ok(cudaEventRecord((cudaEvent_t)p->h2d_event[c], cs));
+        }
+    }
+    for (int c = 0; c < p->nchunks; ++c) {
+        if (p->tracker) ok(cudaStreamWaitEvent(ms, (cudaEvent_t)p->h2d_event[c], 0));
+        ok(cudaGraphLaunch((cudaGraphExec_t)p->graph_exec[c], ms));
+    }
+    ok(cudaEventRecord((cudaEvent_t)p->consumed_event, ms));
+    if (p->actions_bytes > 0) {
+        ok(cudaMemcpyAsync(p->actions_h, p->actions_d, (size_t)p->actions_bytes, cudaMemcpyDeviceToHost, ms));
+        ok(cudaEventRecord((cudaEvent_t)p->d2h_event, ms));
+    }
+    if (e != cudaSuccess) return (int64_t)fail(B200RL_ERR_CUDA, "stackdelta_launch: %s", cudaGetErrorString(e));
+    return k;
+}
+
+extern "C" int64_t b200rl_stackdelta_join(void* tracker, void* d2h_event, int32_t* mismatch_out) {
+    if (d2h_event) {
+        cudaError_t e = cudaEventSynchronize((cudaEvent_t)d2h_event);
+        if (e != cudaSuccess) return (int64_t)fail(B200RL_ERR_CUDA, "stackdelta_join: %s", cudaGetErrorString(e));
+    }
+    if (!tracker) return 0;
+    StackDelta* sd = reinterpret_cast<StackDelta*>(tracker);
+    if (!sd->verify_pending) return 0;
+    return b200rl_stackdelta_wait(tracker, mismatch_out);
+}

@@ -324,6 +324,9 @@ class PPOEngine:
         n = N // P
         self._parts = [(p * n, (p + 1) * n) for p in range(P)]
         C = 2 if (n % 2 == 0 and n // 2 >= 64 and self.s2d and self._graphable()) else 1
+        want = os.environ.get("CLEANRL_B200_PART_CHUNKS")          # upload / compute overlap granularity inside a group
+        if want and self.s2d and self._graphable() and 1 <= int(want) <= 4 and n % int(want) == 0:
+            C = int(want)
         self._part_chunks = [[(lo + c * (n // C), lo + (c + 1) * (n // C)) for c in range(C)] for lo, hi in self._parts]
         if getattr(self, "copy_stream", None) is None:
             self.copy_stream = torch.cuda.Stream(device=self.device)
@@ -334,6 +337,15 @@ class PPOEngine:
         if not hasattr(self, "obs_u8"):
             self.obs_u8 = None
         self._noise_bufs = [self.noise_buf, torch.zeros_like(self.noise_buf)]      # by step parity (see _redo_part)
+        self._actions_np = self.actions_h.numpy()
+        self._rewards_np, self._dones_np = self.rewards_h.numpy(), self.dones_h.numpy()
+        self._dones_ptr = self.dones_h.data_ptr()
+        self._part_d2h_bytes = n * self.actions_h.element_size() * max(1, self.act_dim)
+        self._part_d2h_handles = [None] * P
+        self._plans, self._plan_refs, self._plan_kernels, self._plan_stream = {}, {}, {}, None
+        if self.device.type == "cuda":
+            from . import _lib
+            self._lib = _lib.load()
         self._delta = None
         if self._delta_allowed and self._graphable():
             u8 = torch.uint8
@@ -341,6 +353,7 @@ class PPOEngine:
                                 last=None, boot_obs=None, consumed=torch.cuda.Event()) for _ in range(P)]
             self._new_d = torch.zeros((N, 7056), dtype=u8, device=self.device)
             self._slot_d = torch.zeros(N, dtype=torch.int32, device=self.device)
+            self._mis_ptr = [d["tr"].mis_h.data_ptr() for d in self._delta]
 
     def _part_work(self, step, lo, hi):
         sl = slice(lo, hi)
@@ -382,10 +395,14 @@ class PPOEngine:
     def wait_actions(self, part):
         """Host view of group ``part``'s actions of the step launched last (blocks on that group's D2H event only)."""
         lo, hi = self._parts[part]
-        self._part_d2h[part].synchronize()
         if self._delta is not None:
-            self._join_part(part)
-        return self.actions_h[lo:hi].numpy()
+            h = self._part_d2h_handles[part]
+            if h is None:
+                self._part_d2h[part].synchronize()
+            self._join_part(part, h)          # one C call: event wait + verification join
+        else:
+            self._part_d2h[part].synchronize()
+        return self._actions_np[lo:hi]
 
     # ---- frame-stack delta upload (csrc/frame_stack.cu): the observation of cleanrl/ppo_atari_envpool.py:185-196 is a stack
     # of the 4 newest frames, so planes 0..2 of an env's observation are planes 1..3 of its previous one unless it was reset.
@@ -419,13 +436,88 @@ class PPOEngine:
             return False
 
     def _launch_part_delta(self, step, part, obs_np, done_np, sample=True):
+        """One env group's rollout step.  Steady state = ONE C call (b200rl_stackdelta_launch over a plan that was filled
+        when the step's graphs were captured): classification + staging + verification start, the uploads, the chunk
+        graphs, the actions D2H.  The first pass over a (step, group) takes the python path below it and captures."""
+        d = self._delta[part]
+        reuse = step == 0 and d["boot_obs"] is not None and d["boot_obs"] is obs_np
+        d["boot_obs"] = obs_np if step == self.T else None
+        plan = self._plans.get((step, part, reuse))
+        if plan is None or self._plan_stream != torch.cuda.current_stream().cuda_stream:
+            return self._launch_part_delta_capture(step, part, obs_np, done_np, sample, reuse)
+        lo, hi = self._parts[part]
+        n = hi - lo
+        lib = self._lib
+        obs, optr, ostride = None, None, 0
+        if not reuse:
+            obs = obs_np
+            if type(obs) is not np.ndarray or obs.dtype != np.uint8 or obs.ndim != 4 or obs.strides[1:] != (7056, 84, 1):
+                obs = np.ascontiguousarray(obs_np, dtype=np.uint8)
+            optr, ostride = obs.__array_interface__["data"][0], obs.strides[0]
+            if step == 0:
+                lib.b200rl_stackdelta_invalidate(d["tr"]._h)     # an observation the engine has not seen before
+        if sample:
+            np.copyto(self._dones_np[step, lo:hi], done_np, casting="unsafe")
+            dptr = self._dones_ptr + (step * self.N + lo) * 4
+            if part == 0:
+                self.agent.draw_noise_into(self._noise_bufs[step & 1])        # the step's ONE noise draw, all N envs
+        else:
+            dkeep = np.ascontiguousarray(done_np, dtype=np.float32)
+            dptr = dkeep.__array_interface__["data"][0]
+        k = lib.b200rl_stackdelta_launch(self._plan_refs[(step, part, reuse)], optr, ostride, dptr)
+        if k < 0:
+            from . import _lib
+            _lib.check(int(k), "stackdelta_launch")
+        self.graph_launches += self._plan_kernels[(step, part, reuse)]
+        if reuse:
+            d["last"] = None
+        else:
+            self.h2d_bytes += n * (7056 + 4) + k * 28224
+            self.delta_full_frames += k
+            d["last"] = (step, obs, k, sample)
+        if sample:
+            self.d2h_bytes += self._part_d2h_bytes
+
+    def _make_plan(self, step, part, reuse, sample):
+        """Fill the B200rlPartLaunch of (step, group) once its chunk graphs exist (raw handles of torch's objects)."""
+        import ctypes
+        from . import _lib
+        lo, hi = self._parts[part]
+        d = self._delta[part]
+        tr = d["tr"]
+        chunks = self._part_chunks[part]
+        keys = [("dpart", step, part, c, reuse) for c in range(len(chunks))]
+        if any(k not in self._graphs for k in keys):
+            return
+        pl = _lib.PartLaunch()
+        pl.tracker = None if reuse else tr._h
+        pl.copy_stream = self.copy_stream.cuda_stream
+        pl.main_stream = torch.cuda.current_stream().cuda_stream
+        pl.consumed_event = d["consumed"].cuda_event
+        pl.n, pl.nchunks = hi - lo, len(chunks)
+        for c, (clo, chi) in enumerate(chunks):
+            pl.chunk_lo[c], pl.chunk_hi[c] = clo - lo, chi - lo
+            pl.h2d_event[c] = self._part_h2d[part][c].cuda_event
+            pl.graph_exec[c] = self._graphs[keys[c]].raw_cuda_graph_exec()
+        pl.new_d, pl.slot_d, pl.full_d = self._new_d[lo:hi].data_ptr(), self._slot_d[lo:hi].data_ptr(), d["full_d"].data_ptr()
+        pl.new_h, pl.full_h, pl.slot_h = tr.new_h.data_ptr(), tr.full_h.data_ptr(), tr.slot_h.data_ptr()
+        if sample:
+            pl.actions_d, pl.actions_h = self.actions[step][lo:hi].data_ptr(), self.actions_h[lo:hi].data_ptr()
+            pl.actions_bytes = self._part_d2h_bytes
+            pl.d2h_event = self._part_d2h[part].cuda_event
+        key = (step, part, reuse)
+        self._plans[key] = pl
+        self._plan_refs[key] = ctypes.byref(pl)
+        self._plan_kernels[key] = sum(self._graph_kernels[k] for k in keys)
+        self._plan_stream = pl.main_stream
+        self._part_d2h_handles[part] = self._part_d2h[part].cuda_event
+
+    def _launch_part_delta_capture(self, step, part, obs_np, done_np, sample, reuse):
         lo, hi = self._parts[part]
         n = hi - lo
         d = self._delta[part]
         tr = d["tr"]
         main, cs = torch.cuda.current_stream(), self.copy_stream
-        reuse = step == 0 and d["boot_obs"] is not None and d["boot_obs"] is obs_np
-        d["boot_obs"] = obs_np if step == self.T else None
         if reuse:
             d["last"] = None
             for c in range(len(self._part_chunks[part])):
@@ -464,17 +556,24 @@ class PPOEngine:
         if sample:
             self.actions_h[lo:hi].copy_(self.actions[step][lo:hi], non_blocking=True)
             self._part_d2h[part].record(main)
-            self.d2h_bytes += n * self.actions_h.element_size() * max(1, self.act_dim)
+            self.d2h_bytes += self._part_d2h_bytes
+        if os.environ.get("CLEANRL_B200_LAUNCH_PLANS", "1") != "0":
+            self._make_plan(step, part, reuse, sample)
 
-    def _join_part(self, part):
-        """Join the host-side verification of the observation launched last for ``part``; redo the step from full frames
-        for envs that were not a shifted stack although not done."""
+    def _join_part(self, part, d2h_event=None):
+        """Join the host-side verification of the observation launched last for ``part`` (after ``d2h_event``, a raw handle,
+        when given); redo the step from full frames for envs that were not a shifted stack although not done."""
         d = self._delta[part]
-        if d["last"] is None:
+        tr = d["tr"]
+        if d["last"] is None and d2h_event is None:
             return
-        mis = d["tr"].wait()
-        if len(mis):
-            self._redo_part(part, mis)
+        m = self._lib.b200rl_stackdelta_join(tr._h if d["last"] is not None else None, d2h_event, self._mis_ptr[part])
+        tr._pending, tr._keep = False, None
+        if m < 0:
+            from . import _lib
+            _lib.check(int(m), "stackdelta_join")
+        if m > 0:
+            self._redo_part(part, tr.mis_h[:int(m)].numpy().copy())
         d["last"] = None
 
     def _redo_part(self, part, mis):
@@ -514,14 +613,17 @@ class PPOEngine:
         P = len(env_parts)
         self._part_setup(P)
         obs_parts, done_parts = list(obs_parts), list(done_parts)
+        if hasattr(self.agent, "_tc_plan") and getattr(self.agent, "precision", "fp32") == "bf16":
+            self.agent._tc_plan()          # (re)pack the weights once: they do not change during a rollout
         for p in range(P):
             self.launch_part(0, p, obs_parts[p], done_parts[p])
+        rewards_np = self._rewards_np
         for t in range(self.T):
             for p in range(P):
                 lo, hi = self._parts[p]
                 action = self.wait_actions(p)
                 obs, reward, done, info = env_parts[p].step(action)
-                self.rewards_h[t][lo:hi].copy_(torch.as_tensor(np.asarray(reward, dtype=np.float32).reshape(-1)))
+                np.copyto(rewards_np[t, lo:hi], np.asarray(reward).reshape(-1), casting="unsafe")
                 if on_step is not None:
                     on_step(t, p, reward, done, info)
                 obs_parts[p], done_parts[p] = obs, done

@@ -298,6 +298,29 @@ void b200rl_stackdelta_invalidate(void* tracker);
 int64_t b200rl_stackdelta_begin(void* tracker, const uint8_t* obs, int64_t env_stride, const float* done,
                                 uint8_t* new_out, uint8_t* full_out, int32_t* slot_out);
 int64_t b200rl_stackdelta_wait(void* tracker, int32_t* mismatch_out);
+/* One env group's whole rollout step in ONE host call (the grouped loop of PPOEngine.collect is bounded by per-step host
+ * overhead once only a plane per env crosses PCIe).  `plan` is filled once per (step, group):
+ *   launch(): begin() on `tracker` (NULL = nothing to upload: the slot is rebuilt from device data only), H2D of the staged
+ *             full frames / slot table / newest planes on `copy_stream` (straight from `obs` when it is pinned memory, else
+ *             through new_h), then per chunk c: main_stream waits h2d_event[c] and launches graph_exec[c] (a cudaGraphExec_t
+ *             holding that chunk's storage rebuild + policy + sampler), records `consumed_event`, copies the actions D2H
+ *             (actions_bytes > 0) and records d2h_event.  Returns the number of whole observations staged (or < 0).
+ *   join():   cudaEventSynchronize(d2h_event) (may be NULL) + wait() on `tracker` (may be NULL / nothing pending -> 0). */
+typedef struct B200rlPartLaunch {
+    void* tracker;
+    void* copy_stream;
+    void* main_stream;
+    void* consumed_event;
+    int32_t n, nchunks;
+    int32_t chunk_lo[4], chunk_hi[4];      /* env ranges of the chunks, relative to the group */
+    void* h2d_event[4];
+    void* graph_exec[4];
+    uint8_t* new_d; int32_t* slot_d; uint8_t* full_d;     /* device staging of the group */
+    uint8_t* new_h; uint8_t* full_h; int32_t* slot_h;     /* pinned host staging of the group */
+    const void* actions_d; void* actions_h; int64_t actions_bytes; void* d2h_event;
+} B200rlPartLaunch;
+int64_t b200rl_stackdelta_launch(const B200rlPartLaunch* plan, const uint8_t* obs, int64_t env_stride, const float* done);
+int64_t b200rl_stackdelta_join(void* tracker, void* d2h_event, int32_t* mismatch_out);
 int64_t b200rl_naturecnn_param_count(int A);
 size_t b200rl_naturecnn_bf16_packed_bytes(int A);
 size_t b200rl_naturecnn_bf16_acts_bytes(int64_t n, int obs_format);

@@ -55,7 +55,7 @@ class _SilentResets:
         if self.t % self.every == 0:
             obs = np.array(obs)                         # private copy (the ring itself stays consistent)
             for i in (1, self.num_envs // 2, self.num_envs - 1):
-                obs[i, self.t % 3, 10:20, 30] ^= 0x5A
+                obs[i, (self.t // self.every) % 3, 10:20, 30] ^= 0x5A
         return obs, r, d, info
 
 
@@ -111,12 +111,14 @@ def test_delta_upload_equals_whole_upload(lib, pinned):
 
 
 def test_contract_violations_are_redone_from_full_frames(lib):
-    N, T = 128, 9
-    _, full = _rollouts(False, N, T, 1, False, wrap=_SilentResets)
-    e_delta, delta = _rollouts(True, N, T, 1, False, wrap=_SilentResets)
-    for k in full[0]:
-        assert torch.equal(full[0][k], delta[0][k]), k
-    assert e_delta.delta_redos >= 4 and e_delta.delta_upload       # a few bad envs: redo, keep the delta path
+    N, T = 256, 9                                        # iteration 1: python launch path (captures), iteration 2: one-call plans
+    _, full = _rollouts(False, N, T, 2, False, wrap=_SilentResets)
+    e_delta, delta = _rollouts(True, N, T, 2, False, wrap=_SilentResets)
+    for it in range(2):
+        for k in full[it]:
+            assert torch.equal(full[it][k], delta[it][k]), (it, k)
+    assert e_delta.delta_redos >= 8 and e_delta.delta_upload       # a few bad envs: redo, keep the delta path
+    assert len(e_delta._plans) > 0
 
 
 def test_unstacked_env_falls_back_to_whole_uploads(lib):
