@@ -165,6 +165,7 @@ struct StackDelta {
                 seen = seq;
                 j = job;
             }
+            cv_work.notify_one();            // chained wake-up: the submitting thread pays for ONE futex wake, not for all
             work(j);
             {
                 std::lock_guard<std::mutex> g(mu);
@@ -181,7 +182,7 @@ struct StackDelta {
             running = (int)workers.size();
             ++seq;
         }
-        cv_work.notify_all();
+        cv_work.notify_one();
     }
     void join() {
         if (workers.empty()) return;
