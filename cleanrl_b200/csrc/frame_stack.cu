@@ -15,6 +15,7 @@
 //                                from a full staged frame for the envs that have one.
 #include <algorithm>
 #include <atomic>
+#include <chrono>
 #include <condition_variable>
 #include <cstring>
 #include <mutex>
@@ -95,15 +96,17 @@ struct StackDelta {
         uint8_t* out = nullptr;            // PACK_NEW: new_out, PACK_FULL: full_out
         const int32_t* slot = nullptr;
     } job;
+    // ---- work distribution: one item = kGrain consecutive envs.  Everything a worker needs to claim an item (the job, the
+    // next unclaimed item) and to report it (items done, mismatches) is guarded by `mu`, so a worker that wakes up late can
+    // never run an item of a newer job with an older job's description, and a pass is complete when its ITEMS are done --
+    // it never waits for every worker to have woken up.
     std::vector<std::thread> workers;
     std::mutex mu;
     std::condition_variable cv_work, cv_done;
-    uint64_t seq = 0;                      // bumped per job
-    int running = 0;                       // workers still inside the current job
+    int64_t items_total = 0, next_item = 0, items_done = 0;
     bool stop = false;
     bool verify_pending = false;
-    std::atomic<int64_t> next{0};
-    std::vector<int32_t> mismatch;         // filled under mu
+    std::vector<int32_t> mismatch;         // guarded by mu
     static constexpr int64_t kGrain = 8;   // envs per work item
 
     StackDelta(int64_t n_, int planes_, int64_t pb, int threads) : n(n_), plane_bytes(pb), planes(planes_) {
@@ -142,59 +145,53 @@ struct StackDelta {
             }
         }
     }
-    void work(const Job& j) {
-        std::vector<int32_t> bad;
-        for (;;) {
-            const int64_t a = next.fetch_add(kGrain);
-            if (a >= n) break;
-            run_range(j, a, a + kGrain < n ? a + kGrain : n, bad);
-        }
-        if (!bad.empty()) {
-            std::lock_guard<std::mutex> g(mu);
-            mismatch.insert(mismatch.end(), bad.begin(), bad.end());
-        }
-    }
     void loop() {
-        uint64_t seen = 0;
+        std::vector<int32_t> bad;
+        std::unique_lock<std::mutex> g(mu);
         for (;;) {
-            Job j;
-            {
-                std::unique_lock<std::mutex> g(mu);
-                cv_work.wait(g, [&] { return stop || seq != seen; });
-                if (stop) return;
-                seen = seq;
-                j = job;
-            }
-            cv_work.notify_one();            // chained wake-up: the submitting thread pays for ONE futex wake, not for all
-            work(j);
-            {
-                std::lock_guard<std::mutex> g(mu);
-                if (--running == 0) cv_done.notify_all();
-            }
+            cv_work.wait(g, [&] { return stop || next_item < items_total; });
+            if (stop) return;
+            const int64_t item = next_item++;
+            const Job j = job;
+            const bool more = next_item < items_total;
+            g.unlock();
+            if (more) cv_work.notify_one();          // chained wake-up: the submitting thread pays for ONE futex wake
+            bad.clear();
+            const int64_t a = item * kGrain;
+            run_range(j, a, a + kGrain < n ? a + kGrain : n, bad);
+            g.lock();
+            if (!bad.empty()) mismatch.insert(mismatch.end(), bad.begin(), bad.end());
+            if (++items_done == items_total) cv_done.notify_all();
         }
     }
-    void start(const Job& j) {               // caller holds no lock; no job may be in flight
-        if (workers.empty()) { next = 0; work(j); return; }
+    void start(const Job& j) {               // no pass may be in flight
+        if (workers.empty()) {
+            std::vector<int32_t> bad;
+            run_range(j, 0, n, bad);
+            mismatch.insert(mismatch.end(), bad.begin(), bad.end());
+            return;
+        }
         {
             std::lock_guard<std::mutex> g(mu);
             job = j;
-            next = 0;
-            running = (int)workers.size();
-            ++seq;
+            next_item = 0;
+            items_done = 0;
+            items_total = (n + kGrain - 1) / kGrain;
         }
         cv_work.notify_one();
     }
-    void join() {
-        if (workers.empty()) return;
+    bool join(double timeout_s = 60.0) {     // false = the pass did not finish in time (a bug: report, never hang)
+        if (workers.empty()) return true;
         std::unique_lock<std::mutex> g(mu);
-        cv_done.wait(g, [&] { return running == 0; });
+        return cv_done.wait_for(g, std::chrono::duration<double>(timeout_s), [&] { return items_done == items_total; });
     }
-    void finish_verify() {
-        if (!verify_pending) return;
-        join();
+    bool finish_verify() {
+        if (!verify_pending) return true;
+        if (!join()) return false;
         base = (base + 1) % planes;
         primed = true;
         verify_pending = false;
+        return true;
     }
 };
 
@@ -278,12 +275,14 @@ extern "C" int64_t b200rl_stackdelta_begin(void* h, const uint8_t* obs, int64_t 
             sd->run_range(j, 0, sd->n, none);
         } else {
             j.kind = StackDelta::PACK_FULL; j.out = full_out;
-            sd->start(j); sd->join();
+            sd->start(j);
+            if (!sd->join()) return (int64_t)fail(B200RL_ERR_UNSUPPORTED, "stackdelta_begin: worker pool timed out");
         }
     }
     if (new_out) {
         j.kind = StackDelta::PACK_NEW; j.out = new_out;
-        sd->start(j); sd->join();
+        sd->start(j);
+        if (!sd->join()) return (int64_t)fail(B200RL_ERR_UNSUPPORTED, "stackdelta_begin: worker pool timed out");
     }
     j.kind = StackDelta::VERIFY; j.out = nullptr;
     sd->mismatch.clear();
@@ -295,7 +294,7 @@ extern "C" int64_t b200rl_stackdelta_begin(void* h, const uint8_t* obs, int64_t 
 extern "C" int64_t b200rl_stackdelta_wait(void* h, int32_t* mismatch_out) {
     if (!h) return (int64_t)fail(B200RL_ERR_INVALID_ARGUMENT, "stackdelta_wait: null handle");
     StackDelta* sd = reinterpret_cast<StackDelta*>(h);
-    sd->finish_verify();
+    if (!sd->finish_verify()) return (int64_t)fail(B200RL_ERR_UNSUPPORTED, "stackdelta_wait: worker pool timed out");
     const int64_t m = (int64_t)sd->mismatch.size();
     if (m > 0 && mismatch_out) {
         std::vector<int32_t> s(sd->mismatch);

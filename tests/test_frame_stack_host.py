@@ -80,3 +80,22 @@ def test_tracker_rejects_bad_geometry():
         tr.begin(np.zeros((4, 4, 84, 84), dtype=np.uint8)[:, :, ::2], None)
     with pytest.raises(AssertionError):
         tr.begin(np.zeros((4, 3, 84, 84), dtype=np.uint8), None)
+
+
+@pytest.mark.timeout(120)
+def test_worker_pool_never_stalls_with_more_threads_than_items():
+    """Regression: a pass is complete when its work items are done, not when every worker has woken up (a pool that counted
+    workers dead-locked when a wake-up was consumed by a worker that had already finished its share)."""
+    rng = np.random.default_rng(1)
+    n = 64                                                # 8 work items, 16 workers
+    big = rng.integers(0, 256, size=(n, 12, 84, 84), dtype=np.uint8)
+    trs = [ops.StackDeltaTracker(n, threads=16, pinned=False) for _ in range(2)]
+    for it in range(600):
+        w = it % 8
+        for tr in trs:
+            tr.begin(big[:, w:w + 4], (rng.random(n) < 0.05).astype(np.float32), pack_new=(it % 3 == 0))
+        for tr in trs:
+            exp_bad = 0 if (it == 0 or w != 0) else None
+            mis = tr.wait()
+            if exp_bad == 0:
+                assert len(mis) == 0
