@@ -107,7 +107,7 @@ struct StackDelta {
     bool stop = false;
     bool verify_pending = false;
     std::vector<int32_t> mismatch;         // guarded by mu
-    static constexpr int64_t kGrain = 8;   // envs per work item
+    static constexpr int64_t kGrain = 16;  // envs per work item
 
     StackDelta(int64_t n_, int planes_, int64_t pb, int threads) : n(n_), plane_bytes(pb), planes(planes_) {
         mirror.resize((size_t)n * planes * pb);

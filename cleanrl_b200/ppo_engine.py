@@ -337,6 +337,7 @@ class PPOEngine:
         if not hasattr(self, "obs_u8"):
             self.obs_u8 = None
         self._noise_bufs = [self.noise_buf, torch.zeros_like(self.noise_buf)]      # by step parity (see _redo_part)
+        self._noise_step = -1
         self._actions_np = self.actions_h.numpy()
         self._rewards_np, self._dones_np = self.rewards_h.numpy(), self.dones_h.numpy()
         self._dones_ptr = self.dones_h.data_ptr()
@@ -384,7 +385,7 @@ class PPOEngine:
         self.h2d_bytes += src.numel() * src.element_size()
         self.dones_h[step][lo:hi].copy_(torch.as_tensor(np.asarray(done_np, dtype=np.float32)))
         if part == 0:
-            self.agent.draw_noise_into(self._noise_bufs[step & 1])         # the step's ONE noise draw, all N envs
+            self._ensure_noise(step)
         for c, (clo, chi) in enumerate(self._part_chunks[part]):
             main.wait_event(self._part_h2d[part][c])
             self._run_graphed(lambda: self._part_work(step, clo, chi), ("part", step, part, c), warm_key=("p", part, c))
@@ -410,6 +411,14 @@ class PPOEngine:
     # flagged done go up whole; a host worker pool memcmp's the other envs against a private mirror while the device already
     # works, and a step whose env broke the contract without being done is redone from full frames before its actions are
     # handed out (``delta_redos``; an env that is not frame-stacked at all switches the engine back to whole uploads).
+    def _ensure_noise(self, step):
+        """The step's ONE noise draw for all N envs (the reference's RNG contract), into the buffer of the step's parity.
+        ``collect`` calls it one step ahead, right after a step's last group was launched, so that the draw is off the
+        critical path of the next step's first group; draws still happen once per step, in step order."""
+        if self._noise_step != step:
+            self.agent.draw_noise_into(self._noise_bufs[step & 1])
+            self._noise_step = step
+
     def _slot_pair(self, step):
         """(row-major, channel-major) storage of rollout slot ``step``; ``T`` = the bootstrap slot."""
         return (self.next_obs, self.next_obs_t) if step == self.T else (self.obs[step], self.obs_t[step])
@@ -460,7 +469,7 @@ class PPOEngine:
             np.copyto(self._dones_np[step, lo:hi], done_np, casting="unsafe")
             dptr = self._dones_ptr + (step * self.N + lo) * 4
             if part == 0:
-                self.agent.draw_noise_into(self._noise_bufs[step & 1])        # the step's ONE noise draw, all N envs
+                self._ensure_noise(step)
         else:
             dkeep = np.ascontiguousarray(done_np, dtype=np.float32)
             dptr = dkeep.__array_interface__["data"][0]
@@ -547,7 +556,7 @@ class PPOEngine:
         if sample:
             self.dones_h[step][lo:hi].copy_(torch.as_tensor(np.asarray(done_np, dtype=np.float32)))
             if part == 0:
-                self.agent.draw_noise_into(self._noise_bufs[step & 1])        # the step's ONE noise draw, all N envs
+                self._ensure_noise(step)
         for c, (clo, chi) in enumerate(self._part_chunks[part]):
             main.wait_event(self._part_h2d[part][c])
             self._run_graphed(lambda: self._part_work_delta(step, part, clo, chi, sample, reuse),
@@ -615,8 +624,11 @@ class PPOEngine:
         obs_parts, done_parts = list(obs_parts), list(done_parts)
         if hasattr(self.agent, "_tc_plan") and getattr(self.agent, "precision", "fp32") == "bf16":
             self.agent._tc_plan()          # (re)pack the weights once: they do not change during a rollout
+        self._noise_step = -1
         for p in range(P):
             self.launch_part(0, p, obs_parts[p], done_parts[p])
+        if self.T > 1:
+            self._ensure_noise(1)
         rewards_np = self._rewards_np
         for t in range(self.T):
             for p in range(P):
@@ -629,6 +641,8 @@ class PPOEngine:
                 obs_parts[p], done_parts[p] = obs, done
                 if t + 1 < self.T:
                     self.launch_part(t + 1, p, obs, done)
+                    if p == P - 1 and t + 2 < self.T:
+                        self._ensure_noise(t + 2)        # (its buffer was last read by step t, whose actions are all back)
         return obs_parts, done_parts
 
     @torch.no_grad()
