@@ -72,10 +72,16 @@ class ClockSampler:
         self.t0 = self.t1 = None
 
     def start(self):
-        """Start sampling (nvidia-smi needs ~0.5 s to deliver its first line: start it BEFORE the warm-up)."""
+        """Start sampling (nvidia-smi needs ~0.5 s to deliver its first line: start it BEFORE the warm-up).  200 ms is the
+        recipe's period (B200_PROFILING.md); every query takes driver locks, and at 50 ms the end-to-end rollout -- which is
+        bound by host-side CUDA API calls -- measurably slowed down."""
+        period = os.environ.get("BENCH_CLOCK_SAMPLE_MS", "200")
+        if period == "0":
+            self.proc = None
+            return
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.idx}", f"--query-gpu={self.Q}",
-                                          "--format=csv,noheader,nounits", "-lms", "50"],
+                                          "--format=csv,noheader,nounits", "-lms", period],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.t = threading.Thread(target=self._read, daemon=True)
             self.t.start()
@@ -95,7 +101,7 @@ class ClockSampler:
     def stop(self):
         if self.proc is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        time.sleep(0.06)               # let the sample that covers the end of the region arrive
+        time.sleep(0.21)               # let the sample that covers the end of the region arrive
         self.proc.terminate()
         try:
             self.proc.wait(timeout=2)
@@ -103,7 +109,7 @@ class ClockSampler:
             self.proc.kill()
         sm, smmax, reasons = [], [], set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        lines = [ln for ts, ln in self.lines if self.t0 is None or (self.t0 <= ts <= (self.t1 or ts) + 0.06)]
+        lines = [ln for ts, ln in self.lines if self.t0 is None or (self.t0 <= ts <= (self.t1 or ts) + 0.2)]
         window = "timed region"
         if not lines and self.lines:   # region shorter than one sampling period: the sample nearest to it
             mid = 0.5 * (self.t0 + (self.t1 or self.t0))
