@@ -130,6 +130,27 @@ class ClockSampler:
                 "samples": len(sm), "window": window, "reasons": sorted(reasons)}
 
 
+def pin_to_gpu_cores(gpu_index):
+    """Run this process (and the threads it creates later: the engine's host worker pools) on the CPU cores NVML reports as
+    local to the GPU, so that pinned staging memory, the env buffers and the upload path sit on the GPU's NUMA node.  One
+    process per GPU: every rank pins to its own GPU's cores.  BENCH_CPU_AFFINITY=0 leaves the scheduler alone."""
+    if os.environ.get("BENCH_CPU_AFFINITY", "1") == "0" or not hasattr(os, "sched_setaffinity"):
+        return None
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(gpu_index)
+        words = pynvml.nvmlDeviceGetCpuAffinity(h, (os.cpu_count() + 63) // 64)
+        cpus = {64 * w + b for w, word in enumerate(words) for b in range(64) if (word >> b) & 1}
+        cpus &= os.sched_getaffinity(0)
+        if len(cpus) >= 4:
+            os.sched_setaffinity(0, cpus)
+            return len(cpus)
+    except Exception:
+        return None
+    return None
+
+
 def measured_peaks():
     p = ROOT / "MEASURED_PEAKS.json"
     if p.exists():
@@ -154,6 +175,7 @@ def run_ours(opt):
         raise RuntimeError("bench.py (impl=ours) needs a CUDA device: the product has no CPU fallback")
     torch.cuda.set_device(local_rank)
     device = torch.device("cuda", local_rank)
+    pinned_cores = pin_to_gpu_cores(local_rank)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", rank=rank, world_size=world, device_id=device)
@@ -305,7 +327,25 @@ def run_ours(opt):
         eng.delta_upload = True
         env_parts, state = use_envs("stack")
     ff0, rd0 = eng.delta_full_frames, eng.delta_redos
+    host_acc = None
+    if os.environ.get("BENCH_E2E_BREAKDOWN") and G > 1:      # diagnostic: host wall time per group step (adds ~1 us per call)
+        host_acc = {"wait": 0.0, "env": 0.0, "launch": 0.0}
+
+        def _wrap(obj, name, key):
+            f = getattr(obj, name)
+
+            def g(*a, **k):
+                t0 = time.perf_counter()
+                r = f(*a, **k)
+                host_acc[key] += time.perf_counter() - t0
+                return r
+            setattr(obj, name, g)
+        _wrap(eng, "wait_actions", "wait"); _wrap(eng, "launch_part", "launch")
+        for e in env_parts:
+            _wrap(e, "step", "env")
     e2e = phases(timed(iteration_e2e))
+    if host_acc is not None:
+        e2e["host_us_per_env_step"] = {k: round(v / ((W + K) * T) * 1e6, 1) for k, v in host_acc.items()}
     e2e["full_frames"] = (eng.delta_full_frames - ff0) / max(W + K, 1)
     e2e["redos"] = eng.delta_redos - rd0
     e2e["delta"] = bool(G > 1 and eng.delta_upload)
@@ -416,6 +456,9 @@ def run_ours(opt):
                 "rollout_ms": round(e2e.get("rollout_ms", 0.0), 3), "update_ms": round(e2e.get("update_ms", 0.0), 3),
                 "h2d_gbps_during_rollout": round(e2e["h2d"] / max(e2e.get("rollout_ms", 0.0), 1e-9) * 1e-6, 1),
                 "env_groups": G, "loop": "PPOEngine.collect (pipelined env groups)" if G > 1 else "policy_step / env.step",
+                "host": {"cores": os.cpu_count(), "process_pinned_to_gpu_local_cores": pinned_cores,
+                         "verification_threads_per_group": (eng._delta[0]["tr"].threads if getattr(eng, "_delta", None) else 0)},
+                **({"host_us_per_env_step": e2e["host_us_per_env_step"]} if "host_us_per_env_step" in e2e else {}),
                 "observations": ("frame-stacked synthetic env (envpool stack_num=4 semantics)" if opt.env_obs == "stack" and G > 1
                                  else "unrelated random batches"),
                 "upload": ({"mode": "frame-stack delta: newest plane of every env + whole observations of done envs; "
