@@ -317,7 +317,12 @@ def run_ours(opt):
             r["update_ms"] = sum(b.elapsed_time(c) for _, b, c in last) / K
         return r
 
-    res = timed(iteration_resident, profile=True)
+    res = timed(iteration_resident)                 # `value`: update replayed as per-epoch CUDA graphs, no profiling events
+    eng.update_graphs = False                       # per-kernel CUDA-event brackets cannot live inside a captured graph:
+    prof_run = timed(iteration_resident, profile=True)      # the kernel table comes from an eager pass of the same iteration
+    eng.update_graphs = os.environ.get("CLEANRL_B200_UPDATE_GRAPHS", "1") != "0"
+    res["prof"] = prof_run["prof"]
+    res["eager_ms"] = prof_run["ms"]
     e2e_whole = None
     if G > 1 and opt.env_obs == "stack" and eng.delta_upload and not opt.no_whole_upload_arm:
         # secondary arm: the same loop on unrelated observations, every one uploaded whole (round 2's headline path)
@@ -466,6 +471,8 @@ def run_ours(opt):
                             "whole_observations_per_iteration": round(e2e["full_frames"], 1), "redone_steps": e2e["redos"]}
                            if e2e["delta"] else {"mode": "whole observation every step"})},
         "gpu_launches": int(res["launches"]),
+        "update_cuda_graphs": {"enabled": bool(eng.update_graphs and world == 1 or os.environ.get("CLEANRL_B200_UPDATE_GRAPHS_DP", "0") == "1"),
+                               "ms_per_step_eager_with_profile_events": round(res["eager_ms"] / K, 3)},
         "gae_us_per_rollout": gae,
         "roofline": roofline,
         "losses_last": {k: (float(v) if isinstance(v, (int, float)) else None) for k, v in (e2e["stats"] or {}).items()

@@ -39,6 +39,8 @@ SIGNATURES = {
                                           _p, _i64, _p, _p, _i64, _p, _p, _sz, _p]),
     "b200rl_clip_adam_workspace_bytes": (_sz, [_i64]),
     "b200rl_clip_adam_f32": (_i, [_p, _p, _p, _p, _i64, _i64, _d, _d, _d, _d, _d, _i, _p, _p, _sz, _p]),
+    "b200rl_adam_step_scalars": (_i, [_i64, _d, _d, _d, _p]),
+    "b200rl_clip_adam_dyn_f32": (_i, [_p, _p, _p, _p, _i64, _p, _d, _d, _d, _d, _i, _p, _p, _sz, _p]),
     "b200rl_conv2d_fwd_f32": (_i, [_p, _i, _p, _d, _p, _p, _p, _i64, _i, _i, _i, _i, _i, _i, _i, _i, _p]),
     "b200rl_conv2d_bwd_data_f32": (_i, [_p, _p, _p, _i, _p, _i64, _i, _i, _i, _i, _i, _i, _i, _p]),
     "b200rl_conv2d_bwd_weight_workspace_bytes": (_sz, [_i64, _i, _i, _i, _i, _i, _i, _i]),

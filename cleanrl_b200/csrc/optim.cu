@@ -97,7 +97,8 @@ __device__ __forceinline__ void adam_one(float& p, float g, float& m, float& v, 
 
 __global__ void __launch_bounds__(kOptThreads) adam_kernel(
     float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m, float* __restrict__ v,
-    int64_t P, AdamScalars a, const OptScratch* sc) {
+    int64_t P, AdamScalars a, const OptScratch* sc, const float* __restrict__ dyn) {
+    if (dyn) { a.bc2_sqrt = __ldg(dyn); a.neg_step_size = __ldg(dyn + 1); }     // step / lr dependent scalars from device memory
     const float coef = a.do_clip ? sc->coef : 1.f;
     const int64_t stride = (int64_t)gridDim.x * blockDim.x;
     const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -135,17 +136,27 @@ extern "C" size_t b200rl_clip_adam_workspace_bytes(int64_t P) {
     return sizeof(b200rl::OptScratch) + sizeof(double) * b200rl::kOptMaxBlocks;
 }
 
-extern "C" int b200rl_clip_adam_f32(float* params, const float* grads, float* exp_avg, float* exp_avg_sq,
-                                    int64_t P, int64_t step, double lr, double beta1, double beta2, double eps,
-                                    double max_norm, int world_size, float* norm_out,
-                                    void* workspace, size_t workspace_bytes, void* stream) {
-    using namespace b200rl;
+namespace b200rl {
+static void adam_step_scalars(int64_t step, double lr, double beta1, double beta2, float* bc2_sqrt, float* neg_step_size) {
+    // scalar algebra in double exactly as torch/optim/adam.py does it in python
+    const double bc1 = 1.0 - pow(beta1, (double)step);
+    const double bc2 = 1.0 - pow(beta2, (double)step);
+    const double step_size = lr / bc1;
+    *bc2_sqrt = (float)sqrt(bc2);
+    *neg_step_size = (float)(-step_size);
+}
+
+// dyn == nullptr: (step, lr) by value; else the two step-dependent scalars are read from device memory (CUDA-graph replays)
+static int clip_adam_impl(float* params, const float* grads, float* exp_avg, float* exp_avg_sq, int64_t P, int64_t step, double lr,
+                          const float* dyn, double beta1, double beta2, double eps, double max_norm, int world_size, float* norm_out,
+                          void* workspace, size_t workspace_bytes, void* stream) {
     B200RL_REQUIRE(P >= 0, "clip_adam: negative P");
     if (P == 0) return B200RL_OK;
     B200RL_REQUIRE(params && grads && exp_avg && exp_avg_sq, "clip_adam: null pointer");
     B200RL_REQUIRE(aligned(params, 16) && aligned(grads, 16) && aligned(exp_avg, 16) && aligned(exp_avg_sq, 16),
                    "clip_adam: buffers must be 16-B aligned (float4 path)");
-    B200RL_REQUIRE(step >= 1, "clip_adam: step is 1-based (got %lld)", (long long)step);
+    B200RL_REQUIRE(dyn || step >= 1, "clip_adam: step is 1-based (got %lld)", (long long)step);
+    B200RL_REQUIRE(!dyn || aligned(dyn, 4), "clip_adam: misaligned scalar table");
     B200RL_REQUIRE(world_size >= 1, "clip_adam: world_size must be >= 1");
     B200RL_REQUIRE(workspace && aligned(workspace, 16), "clip_adam: workspace null or misaligned");
     if (workspace_bytes < b200rl_clip_adam_workspace_bytes(P))
@@ -165,20 +176,41 @@ extern "C" int b200rl_clip_adam_f32(float* params, const float* grads, float* ex
         int rc = check_launch("clip_adam/sumsq");
         if (rc) return rc;
     }
-    // scalar algebra in double exactly as torch/optim/adam.py does it in python
-    const double bc1 = 1.0 - pow(beta1, (double)step);
-    const double bc2 = 1.0 - pow(beta2, (double)step);
-    const double step_size = lr / bc1;
     AdamScalars a;
     a.w1 = (float)(1.0 - beta1);
     a.beta2 = (float)beta2;
     a.w2 = (float)(1.0 - beta2);
-    a.bc2_sqrt = (float)sqrt(bc2);
+    a.bc2_sqrt = 1.f;
+    a.neg_step_size = 0.f;
+    if (!dyn) adam_step_scalars(step, lr, beta1, beta2, &a.bc2_sqrt, &a.neg_step_size);
     a.eps = (float)eps;
-    a.neg_step_size = (float)(-step_size);
     a.world = (float)world_size;
     a.divide_world = world_size > 1;
     a.do_clip = max_norm >= 0.0;
-    adam_kernel<<<blocks, kOptThreads, 0, s>>>(params, grads, exp_avg, exp_avg_sq, P, a, sc);
+    adam_kernel<<<blocks, kOptThreads, 0, s>>>(params, grads, exp_avg, exp_avg_sq, P, a, sc, dyn);
     return check_launch("clip_adam/adam");
+}
+}  // namespace b200rl
+
+extern "C" int b200rl_clip_adam_f32(float* params, const float* grads, float* exp_avg, float* exp_avg_sq,
+                                    int64_t P, int64_t step, double lr, double beta1, double beta2, double eps,
+                                    double max_norm, int world_size, float* norm_out,
+                                    void* workspace, size_t workspace_bytes, void* stream) {
+    return b200rl::clip_adam_impl(params, grads, exp_avg, exp_avg_sq, P, step, lr, nullptr, beta1, beta2, eps, max_norm, world_size,
+                                  norm_out, workspace, workspace_bytes, stream);
+}
+
+extern "C" int b200rl_adam_step_scalars(int64_t step, double lr, double beta1, double beta2, float* out2) {
+    B200RL_REQUIRE(out2 && step >= 1, "adam_step_scalars: bad arguments");
+    b200rl::adam_step_scalars(step, lr, beta1, beta2, out2, out2 + 1);
+    return B200RL_OK;
+}
+
+extern "C" int b200rl_clip_adam_dyn_f32(float* params, const float* grads, float* exp_avg, float* exp_avg_sq,
+                                        int64_t P, const float* step_scalars, double beta1, double beta2, double eps,
+                                        double max_norm, int world_size, float* norm_out,
+                                        void* workspace, size_t workspace_bytes, void* stream) {
+    B200RL_REQUIRE(step_scalars, "clip_adam_dyn: null scalar table");
+    return b200rl::clip_adam_impl(params, grads, exp_avg, exp_avg_sq, P, 0, 0.0, step_scalars, beta1, beta2, eps, max_norm, world_size,
+                                  norm_out, workspace, workspace_bytes, stream);
 }

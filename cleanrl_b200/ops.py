@@ -188,6 +188,35 @@ def clip_adam(params, grads, exp_avg, exp_avg_sq, step, lr, beta1=0.9, beta2=0.9
     return params
 
 
+def adam_step_scalars(step, lr, beta1=0.9, beta2=0.999):
+    """(sqrt(1 - beta2^step), -lr / (1 - beta1^step)) as float32, computed by the library in double as ``clip_adam`` does."""
+    import ctypes
+    out = (ctypes.c_float * 2)()
+    _lib.check(_lib.load().b200rl_adam_step_scalars(int(step), float(lr), float(beta1), float(beta2), out), "adam_step_scalars")
+    return float(out[0]), float(out[1])
+
+
+def clip_adam_dyn(params, grads, exp_avg, exp_avg_sq, step_scalars, beta1=0.9, beta2=0.999, eps=1e-5, max_norm=0.5,
+                  world_size=1, norm_out=None):
+    """``clip_adam`` with the (step, lr)-dependent scalars in device memory (``step_scalars`` f32[2], see
+    ``adam_step_scalars``): what a captured CUDA graph of the update replays."""
+    lib = _lib.load()
+    P = params.numel()
+    f = torch.float32
+    for n_, t in (("params", params), ("grads", grads), ("exp_avg", exp_avg), ("exp_avg_sq", exp_avg_sq)):
+        _contig(t, n_)
+        assert t.numel() == P
+    assert step_scalars.numel() == 2 and step_scalars.is_contiguous()
+    ws = _workspace(params.device, "adam", lib.b200rl_clip_adam_workspace_bytes(P))
+    rc = lib.b200rl_clip_adam_dyn_f32(
+        _ptr(params, f, "params"), _ptr(grads, f, "grads"), _ptr(exp_avg, f, "exp_avg"), _ptr(exp_avg_sq, f, "exp_avg_sq"), P,
+        _ptr(step_scalars, f, "step_scalars"), float(beta1), float(beta2), float(eps),
+        -1.0 if max_norm is None else float(max_norm), int(world_size), _ptr(norm_out, f, "norm_out", True),
+        ws.data_ptr(), ws.numel(), _stream())
+    _lib.check(rc, "clip_adam_dyn")
+    return params
+
+
 # ----------------------------------------------------------------- fp32 layers
 ACT = {None: 0, "none": 0, "relu": 1, "tanh": 2}
 

@@ -119,6 +119,13 @@ class PPOEngine:
         self.stats = torch.zeros(max(n_upd, 1), 16, dtype=f32, device=device)
         self.stats_h = _pin(torch.zeros(max(n_upd, 1), 16, dtype=f32))
         self.grad_norm = torch.zeros(1, dtype=f32, device=device)
+        # CUDA graphs of the update: one graph per epoch (sort + its minibatch updates), replayed every iteration; the Adam
+        # scalars that depend on (step, lr) come from a small device table refreshed once per iteration.  Takes the host
+        # out of the update (about 650 kernel launches per iteration): the device no longer waits on python / driver jitter.
+        self.update_graphs = os.environ.get("CLEANRL_B200_UPDATE_GRAPHS", "1") != "0"
+        self._upd_graphs, self._upd_kernels, self._upd_iters = {}, {}, 0
+        self.hyper = torch.zeros(max(n_upd, 1), 2, dtype=f32, device=device)
+        self.hyper_h = _pin(torch.zeros(max(n_upd, 1), 2, dtype=f32))
         self.flat = agent.flat
         if self.overlap_exchange and hasattr(agent, "grad_tail"):
             agent.grad_tail()          # create the tail event BEFORE the first backward records it
@@ -700,6 +707,15 @@ class PPOEngine:
         k = 0
         E = int(a.update_epochs)
         nmb = self.num_minibatches
+        graphed = (self.update_graphs and a.target_kl is None and self._graphable() and self._upd_iters >= 1
+                   and getattr(self.agent, "precision", "fp32") == "bf16" and hasattr(self.agent, "_tc_plan")
+                   and (self.world_size == 1 or os.environ.get("CLEANRL_B200_UPDATE_GRAPHS_DP", "0") == "1"))
+        self._upd_iters += 1
+        if graphed:
+            hy = self.hyper_h.numpy()
+            for j in range(E * nmb):                 # the scalars of every update of this iteration (host, double, as clip_adam)
+                hy[j] = ops.adam_step_scalars(self.flat.step + 1 + j, lr)
+            self.hyper.copy_(self.hyper_h, non_blocking=True)
         for epoch in range(E):
             # numpy global RNG, in-place and cumulative across epochs as the reference (ppo.py:245).  A shuffle of 131 072
             # indices costs the host 1.5-3 ms: it is drawn per epoch, right before that epoch's launches, so that every
@@ -708,18 +724,21 @@ class PPOEngine:
             self.b_inds_h[epoch].copy_(torch.from_numpy(b_inds_np))        # one pinned slot per epoch: never rewritten in flight
             self.b_inds[epoch].copy_(self.b_inds_h[epoch], non_blocking=True)
             self.h2d_bytes += B * 8
-            if self.s2d and self.sort_minibatch:
-                # same minibatch SETS as the reference's shuffle; rows visited in ascending address order so the frames
-                # gathered by conv1 share DRAM pages / TLB entries (the sums over a minibatch are order-independent up
-                # to fp rounding)
-                self.b_inds[epoch].copy_(torch.sort(self.b_inds[epoch].view(nmb, M), dim=1).values.view(B))
-            for start in range(0, B, M):
-                self.minibatch_update(self.b_inds[epoch, start:start + M], lr, k)
-                k += 1
+            if graphed:
+                g = self._upd_graphs.get(epoch)
+                if g is None:
+                    g = self._capture_epoch(epoch)
+                g.replay()
+                self.graph_launches += self._upd_kernels[epoch]
+                k += nmb
+                continue
+            k = self._epoch_work(epoch, lr, k, False)
             if a.target_kl is not None:
                 approx_kl = self.stats[k - 1, 4].item()
                 if approx_kl > a.target_kl:
                     break
+        if graphed:
+            self.flat.step += E * nmb
         self.stats_h[:k].copy_(self.stats[:k], non_blocking=True)
         _sync()
         self.d2h_bytes += k * 64
@@ -730,8 +749,35 @@ class PPOEngine:
         out["per_update"] = s.copy()
         return out
 
+    def _epoch_work(self, epoch, lr, k, dyn):
+        B, M, nmb = self.B, self.M, self.num_minibatches
+        if self.s2d and self.sort_minibatch:
+            # same minibatch SETS as the reference's shuffle; rows visited in ascending address order so the frames gathered
+            # by conv1 share DRAM pages / TLB entries (the sums over a minibatch are order-independent up to fp rounding)
+            self.b_inds[epoch].copy_(torch.sort(self.b_inds[epoch].view(nmb, M), dim=1).values.view(B))
+        for start in range(0, B, M):
+            self.minibatch_update(self.b_inds[epoch, start:start + M], lr, k, dyn=self.hyper[k] if dyn else None)
+            k += 1
+        return k
+
+    def _capture_epoch(self, epoch):
+        from . import _lib
+        if epoch == 0 and hasattr(self.agent, "params_updated"):
+            self.agent.params_updated()     # the graph of epoch 0 always starts by packing the weights it was given
+        l0 = _lib.load().b200rl_launch_count()
+        g = torch.cuda.CUDAGraph()
+        if self._graph_pool is None:
+            self._graph_pool = torch.cuda.graph_pool_handle()
+        with torch.cuda.graph(g, pool=self._graph_pool):
+            self._epoch_work(epoch, None, epoch * self.num_minibatches, True)
+        self._upd_graphs[epoch] = g
+        self._upd_kernels[epoch] = _lib.load().b200rl_launch_count() - l0
+        if hasattr(self.agent, "pin_workspaces"):
+            self.agent.pin_workspaces()
+        return g
+
     @torch.no_grad()
-    def minibatch_update(self, mb_inds, lr, k=0):
+    def minibatch_update(self, mb_inds, lr, k=0, dyn=None):
         """ONE fused update on the rollout rows ``mb_inds`` (device int64): forward with the row gather folded in,
         loss + its gradient, hand-written backward, DP gradient exchange, clip + Adam (ppo.py:250-290,
         ppo_atari_multigpu.py:360-377).  ``stats[k]`` receives the logged scalars."""
@@ -748,10 +794,14 @@ class PPOEngine:
         agent.loss_backward(policy_out, value, mb_inds, b, a, self.stats[k], self._scratch)
         if self.world_size > 1:
             self._exchange_gradients()
-        flat.step += 1
-        ops.clip_adam(flat.flat, flat.grad, flat.exp_avg, flat.exp_avg_sq, flat.step, lr,
-                      eps=1e-5, max_norm=a.max_grad_norm, world_size=self.world_size,
-                      norm_out=self.grad_norm)
+        if dyn is not None:      # captured: the (step, lr) scalars of update k come from the device table
+            ops.clip_adam_dyn(flat.flat, flat.grad, flat.exp_avg, flat.exp_avg_sq, dyn, eps=1e-5, max_norm=a.max_grad_norm,
+                              world_size=self.world_size, norm_out=self.grad_norm)
+        else:
+            flat.step += 1
+            ops.clip_adam(flat.flat, flat.grad, flat.exp_avg, flat.exp_avg_sq, flat.step, lr,
+                          eps=1e-5, max_norm=a.max_grad_norm, world_size=self.world_size,
+                          norm_out=self.grad_norm)
         if hasattr(agent, "params_updated"):
             agent.params_updated()
 

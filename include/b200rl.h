@@ -167,6 +167,14 @@ int b200rl_clip_adam_f32(float* params, const float* grads, float* exp_avg, floa
                          int64_t P, int64_t step, double lr, double beta1, double beta2, double eps,
                          double max_norm, int world_size, float* norm_out,
                          void* workspace, size_t workspace_bytes, void* stream);
+/* The same update with the two scalars that depend on (step, lr) -- sqrt(1 - beta2^step) and -lr / (1 - beta1^step), computed
+ * on the host in double by b200rl_adam_step_scalars exactly as the by-value entry point computes them -- read from DEVICE
+ * memory (step_scalars f32[2]): a captured CUDA graph of the update can be replayed for every later step / learning rate. */
+int b200rl_adam_step_scalars(int64_t step, double lr, double beta1, double beta2, float* out2);
+int b200rl_clip_adam_dyn_f32(float* params, const float* grads, float* exp_avg, float* exp_avg_sq,
+                             int64_t P, const float* step_scalars, double beta1, double beta2, double eps,
+                             double max_norm, int world_size, float* norm_out,
+                             void* workspace, size_t workspace_bytes, void* stream);
 
 /* ------------------------------------------------ fp32 network layers ------
  * Exact-arithmetic (fp32 FMA, CUDA cores) layers in the reference's own NCHW /

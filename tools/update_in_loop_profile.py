@@ -58,6 +58,7 @@ def profiled(mb_inds, lr, k=0):
     rows.append(r)
 
 
+eng.update_graphs = False
 eng.minibatch_update = profiled
 eng.update(2.5e-4)
 names = sorted(rows[0], key=lambda n: -rows[0][n])
