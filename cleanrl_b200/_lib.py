@@ -82,6 +82,7 @@ SIGNATURES = {
     "b200rl_stackdelta_invalidate": (None, [_p]),
     "b200rl_stackdelta_begin": (_i64, [_p, _p, _i64, _p, _p, _p, _p]),
     "b200rl_stackdelta_wait": (_i64, [_p, _p]),
+    "b200rl_mt19937_shuffle_i64": (_i, [_p, _p, _p, _i64]),
     "b200rl_stackdelta_launch": (_i64, [_p, _p, _i64, _p]),
     "b200rl_stackdelta_join": (_i64, [_p, _p, _p]),
 }

@@ -362,3 +362,54 @@ extern "C" int64_t b200rl_stackdelta_join(void* tracker, void* d2h_event, int32_
     if (!sd->verify_pending) return 0;
     return b200rl_stackdelta_wait(tracker, mismatch_out);
 }
+
+// ------------------------------------------------------------------------------------------------ minibatch shuffle
+// numpy.random.shuffle of the reference's index vector (cleanrl/ppo.py:245, the GLOBAL legacy RandomState = MT19937),
+// restated natively: the Fisher-Yates walk `for i = n-1 .. 1: j = interval(i); swap(x[i], x[j])` with numpy's masked
+// rejection sampler over 32-bit draws.  Consumes the generator exactly as numpy does (the caller hands in / takes back
+// the 624-word state), so the permutation AND every later numpy draw are bit-identical -- at a fraction of the host
+// time, which is all the host contributes to an update once its kernels are replayed from CUDA graphs.
+namespace b200rl {
+struct MT19937 {
+    uint32_t* key;
+    int pos;
+    void gen() {
+        constexpr int N = 624, M = 397;
+        constexpr uint32_t A = 0x9908b0dfu, UP = 0x80000000u, LO = 0x7fffffffu;
+        int i = 0;
+        uint32_t y;
+        for (; i < N - M; ++i) { y = (key[i] & UP) | (key[i + 1] & LO); key[i] = key[i + M] ^ (y >> 1) ^ ((0u - (y & 1u)) & A); }
+        for (; i < N - 1; ++i) { y = (key[i] & UP) | (key[i + 1] & LO); key[i] = key[i + (M - N)] ^ (y >> 1) ^ ((0u - (y & 1u)) & A); }
+        y = (key[N - 1] & UP) | (key[0] & LO);
+        key[N - 1] = key[M - 1] ^ (y >> 1) ^ ((0u - (y & 1u)) & A);
+        pos = 0;
+    }
+    uint32_t next32() {
+        if (pos == 624) gen();
+        uint32_t y = key[pos++];
+        y ^= (y >> 11);
+        y ^= (y << 7) & 0x9d2c5680u;
+        y ^= (y << 15) & 0xefc60000u;
+        y ^= (y >> 18);
+        return y;
+    }
+};
+}  // namespace b200rl
+
+extern "C" int b200rl_mt19937_shuffle_i64(uint32_t* key624, int32_t* pos, int64_t* data, int64_t n) {
+    B200RL_REQUIRE(key624 && pos && (data || n == 0), "mt19937_shuffle: null pointer");
+    B200RL_REQUIRE(*pos >= 0 && *pos <= 624, "mt19937_shuffle: generator position %d outside [0, 624]", (int)*pos);
+    B200RL_REQUIRE(n >= 0 && n <= 0xffffffffLL, "mt19937_shuffle: n outside the 32-bit draw path");
+    b200rl::MT19937 g{key624, (int)*pos};
+    for (int64_t i = n - 1; i >= 1; --i) {
+        uint32_t mask = (uint32_t)i;
+        mask |= mask >> 1; mask |= mask >> 2; mask |= mask >> 4; mask |= mask >> 8; mask |= mask >> 16;
+        uint32_t j;
+        while ((j = (g.next32() & mask)) > (uint32_t)i) {}
+        const int64_t t = data[j];
+        data[j] = data[i];
+        data[i] = t;
+    }
+    *pos = g.pos;
+    return B200RL_OK;
+}

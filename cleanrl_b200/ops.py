@@ -188,6 +188,24 @@ def clip_adam(params, grads, exp_avg, exp_avg_sq, step, lr, beta1=0.9, beta2=0.9
     return params
 
 
+def numpy_global_shuffle(arr):
+    """``np.random.shuffle(arr)`` for a contiguous int64 vector, bit-exact (same permutation, same generator state afterwards)
+    but 4-6x faster: libb200rl walks numpy's own algorithm over the global RandomState's MT19937 words.  Falls back to
+    numpy itself for anything else (other dtypes / strides, a replaced bit generator)."""
+    import ctypes
+    import numpy as np
+    if not (isinstance(arr, np.ndarray) and arr.dtype == np.int64 and arr.ndim == 1 and arr.flags.c_contiguous):
+        return np.random.shuffle(arr)
+    st = np.random.get_state(legacy=True)
+    if st[0] != "MT19937":
+        return np.random.shuffle(arr)
+    key = np.ascontiguousarray(st[1], dtype=np.uint32).copy()
+    pos = ctypes.c_int32(int(st[2]))
+    rc = _lib.load().b200rl_mt19937_shuffle_i64(key.ctypes.data, ctypes.addressof(pos), arr.ctypes.data, arr.shape[0])
+    _lib.check(rc, "mt19937_shuffle")
+    np.random.set_state(("MT19937", key, int(pos.value), st[3], st[4]))
+
+
 def adam_step_scalars(step, lr, beta1=0.9, beta2=0.999):
     """(sqrt(1 - beta2^step), -lr / (1 - beta1^step)) as float32, computed by the library in double as ``clip_adam`` does."""
     import ctypes

@@ -24,6 +24,7 @@ sampling noise, so seeds mean what they mean in the reference (ppo.py:153-157).
 from __future__ import annotations
 
 import os
+import time
 
 import numpy as np
 import torch
@@ -123,6 +124,10 @@ class PPOEngine:
         # scalars that depend on (step, lr) come from a small device table refreshed once per iteration.  Takes the host
         # out of the update (about 650 kernel launches per iteration): the device no longer waits on python / driver jitter.
         self.update_graphs = os.environ.get("CLEANRL_B200_UPDATE_GRAPHS", "1") != "0"
+        self.host_seconds = {"shuffle": 0.0, "update_enqueue": 0.0, "update_wait": 0.0}     # host wall time, accumulated
+        # np.random.shuffle restated natively (bit-exact, same generator consumption; ops.numpy_global_shuffle)
+        self._shuffle = (ops.numpy_global_shuffle if device.type == "cuda" and os.environ.get("CLEANRL_B200_NATIVE_SHUFFLE", "1") != "0"
+                         else np.random.shuffle)
         self._upd_graphs, self._upd_kernels, self._upd_iters = {}, {}, 0
         self.hyper = torch.zeros(max(n_upd, 1), 2, dtype=f32, device=device)
         self.hyper_h = _pin(torch.zeros(max(n_upd, 1), 2, dtype=f32))
@@ -703,6 +708,7 @@ class PPOEngine:
         Returns dict of the logged scalars (last minibatch's losses, mean clipfrac)."""
         a = self.args
         B, M = self.B, self.M
+        t_up = time.perf_counter()
         b_inds_np = np.arange(B)
         k = 0
         E = int(a.update_epochs)
@@ -720,7 +726,9 @@ class PPOEngine:
             # numpy global RNG, in-place and cumulative across epochs as the reference (ppo.py:245).  A shuffle of 131 072
             # indices costs the host 1.5-3 ms: it is drawn per epoch, right before that epoch's launches, so that every
             # shuffle but the first runs while the device is still busy with the previous epoch's minibatches.
-            np.random.shuffle(b_inds_np)
+            t_sh = time.perf_counter()
+            self._shuffle(b_inds_np)
+            self.host_seconds["shuffle"] += time.perf_counter() - t_sh
             self.b_inds_h[epoch].copy_(torch.from_numpy(b_inds_np))        # one pinned slot per epoch: never rewritten in flight
             self.b_inds[epoch].copy_(self.b_inds_h[epoch], non_blocking=True)
             self.h2d_bytes += B * 8
@@ -739,8 +747,13 @@ class PPOEngine:
                     break
         if graphed:
             self.flat.step += E * nmb
+            if hasattr(self.agent, "params_updated"):
+                self.agent.params_updated()      # no python ran inside the replays: the packed operand copies are stale
         self.stats_h[:k].copy_(self.stats[:k], non_blocking=True)
+        t_sy = time.perf_counter()
+        self.host_seconds["update_enqueue"] += t_sy - t_up
         _sync()
+        self.host_seconds["update_wait"] += time.perf_counter() - t_sy
         self.d2h_bytes += k * 64
         s = self.stats_h[:k].numpy()
         out = {name: float(s[k - 1, i]) for i, name in enumerate(STAT_NAMES)}

@@ -327,6 +327,10 @@ typedef struct B200rlPartLaunch {
     uint8_t* new_h; uint8_t* full_h; int32_t* slot_h;     /* pinned host staging of the group */
     const void* actions_d; void* actions_h; int64_t actions_bytes; void* d2h_event;
 } B200rlPartLaunch;
+/* numpy.random.shuffle(x) of an int64 vector on the legacy MT19937 generator (the reference's minibatch shuffle,
+ * cleanrl/ppo.py:245, driven by numpy's GLOBAL RandomState), restated natively and bit-exact: key624 / pos are the state
+ * words of numpy.random.get_state(); both are advanced exactly as numpy would advance them. */
+int b200rl_mt19937_shuffle_i64(uint32_t* key624, int32_t* pos, int64_t* data, int64_t n);
 int64_t b200rl_stackdelta_launch(const B200rlPartLaunch* plan, const uint8_t* obs, int64_t env_stride, const float* done);
 int64_t b200rl_stackdelta_join(void* tracker, void* d2h_event, int32_t* mismatch_out);
 int64_t b200rl_naturecnn_param_count(int A);

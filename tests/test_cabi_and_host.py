@@ -168,3 +168,28 @@ def test_cartpole_vec_dynamics_and_episode_bookkeeping():
                 if f is not None:
                     assert float(f["episode"]["r"][0]) <= 500
     assert truncs >= 4, truncs
+
+
+def test_native_minibatch_shuffle_is_numpy_shuffle_bit_for_bit(lib):
+    """b200rl_mt19937_shuffle_i64 == np.random.shuffle on the global RandomState (the reference's minibatch shuffle,
+    cleanrl/ppo.py:245): same permutations, and the generator is left in the same state (later draws agree)."""
+    from cleanrl_b200 import ops
+    for seed in (0, 1, 7, 2 ** 31 - 1):
+        for n in (1, 2, 3, 17, 1000, 4 * 128, 131072):
+            np.random.seed(seed)
+            np.random.random(seed % 5)                    # generator position anywhere inside the 624-word block
+            a = np.arange(n)
+            for _ in range(3):                            # cumulative, in place, as the epochs of an update
+                np.random.shuffle(a)
+            tail_a = np.random.randint(0, 1 << 30, size=5)
+            np.random.seed(seed)
+            np.random.random(seed % 5)
+            b = np.arange(n)
+            for _ in range(3):
+                ops.numpy_global_shuffle(b)
+            tail_b = np.random.randint(0, 1 << 30, size=5)
+            assert np.array_equal(a, b) and np.array_equal(tail_a, tail_b), (seed, n)
+    # anything that is not a contiguous int64 vector takes numpy's own path
+    np.random.seed(3); x = np.arange(10, dtype=np.int32); np.random.shuffle(x)
+    np.random.seed(3); y = np.arange(10, dtype=np.int32); ops.numpy_global_shuffle(y)
+    assert np.array_equal(x, y)
