@@ -133,8 +133,10 @@ class ClockSampler:
 def pin_to_gpu_cores(gpu_index):
     """Run this process (and the threads it creates later: the engine's host worker pools) on the CPU cores NVML reports as
     local to the GPU, so that pinned staging memory, the env buffers and the upload path sit on the GPU's NUMA node.  One
-    process per GPU: every rank pins to its own GPU's cores.  BENCH_CPU_AFFINITY=0 leaves the scheduler alone."""
-    if os.environ.get("BENCH_CPU_AFFINITY", "1") == "0" or not hasattr(os, "sched_setaffinity"):
+    process per GPU: every rank pins to its own GPU's cores.  OFF by default (BENCH_CPU_AFFINITY=1 turns it on): on the
+    shared hosts this was measured on, the GPU-local socket is where every other tenant's processes sit as well, and the
+    pinned run was 2x slower than letting the scheduler pick idle cores (profiles/r2_host_sensitivity.md)."""
+    if os.environ.get("BENCH_CPU_AFFINITY", "0") != "1" or not hasattr(os, "sched_setaffinity"):
         return None
     try:
         import pynvml
