@@ -615,7 +615,7 @@ class StackDeltaTracker:
         if threads is None:
             import os
             ranks = max(1, int(os.environ.get("LOCAL_WORLD_SIZE", "1")))        # one process per GPU shares the host cores
-            threads = int(os.environ.get("CLEANRL_B200_HOST_THREADS", min(8, max(2, (os.cpu_count() or 2) // (8 * ranks)))))
+            threads = int(os.environ.get("CLEANRL_B200_HOST_THREADS", min(8, max(2, (os.cpu_count() or 2) // (4 * ranks)))))
         self.n, self.planes, self.plane_bytes, self.threads = int(n), int(planes), int(plane_bytes), int(threads)
         self._h = lib.b200rl_stackdelta_create(self.n, self.planes, self.plane_bytes, int(threads))
         if not self._h:
