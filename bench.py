@@ -185,7 +185,7 @@ def run_ours(opt):
     lib = _lib.load()
 
     N, T, K, W = opt.num_envs, opt.num_steps, opt.steps, opt.warmup
-    total_iters = 2 * (K + W) + 4
+    total_iters = 5 * (K + W) + 8                # up to five timed loops (resident, profiled, whole-upload, e2e): lr stays > 0
     args = ppo_args(N, T, total_iters, opt.precision)
     seed = args.seed + rank                      # per-rank env / numpy streams (ppo_atari_multigpu.py:208-210)
     np.random.seed(seed)
@@ -406,9 +406,15 @@ def run_ours(opt):
         dist.all_reduce(ok, op=dist.ReduceOp.MIN)
         replicas_identical = bool(ok.item() == 1.0)
 
-    if rank != 0:
+    def shutdown():
         if world > 1:
+            eng._upd_graphs.clear()                # graphs that captured NCCL kernels must be gone before the communicator
+            torch.cuda.synchronize()
+            dist.barrier()
             dist.destroy_process_group()
+
+    if rank != 0:
+        shutdown()
         return
     steps_total = N * T * world
     sps = steps_total * K / (res["ms"] * 1e-3)
@@ -498,9 +504,8 @@ def run_ours(opt):
         del eng
         torch.cuda.empty_cache()
         out["extra"] = extra_configs()
-    print(json.dumps(out))
-    if world > 1:
-        dist.destroy_process_group()
+    print(json.dumps(out), flush=True)
+    shutdown()
 
 
 # ------------------------------------------------------------------ BASELINE.json configs[3] and configs[4]
