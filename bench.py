@@ -199,6 +199,20 @@ def run_ours(opt):
     eng = PPOEngine(agent, args, envs.observation_space.shape, np.uint8, N, device, world_size=world,
                     gae_mode=1, all_reduce=all_reduce)
 
+    def replica_trace(tag):
+        """BENCH_REPLICA_TRACE=1: after which phase do the replicas stop being bit-identical (diagnostic, stderr)."""
+        if world == 1 or not os.environ.get("BENCH_REPLICA_TRACE"):
+            return
+        torch.cuda.synchronize()
+        res_ = []
+        for nm, buf in (("params", eng.flat.flat), ("grad", eng.flat.grad), ("exp_avg", eng.flat.exp_avg), ("exp_avg_sq", eng.flat.exp_avg_sq)):
+            ref = buf.clone()
+            dist.broadcast(ref, 0)
+            d_ = (ref - buf).abs()
+            res_.append((nm, bool(torch.equal(ref, buf)), float(d_.max()), int((d_ > 0).sum()),
+                         int((d_ > 0).nonzero()[0]) if bool((d_ > 0).any()) else -1))
+        print(f"[replica_trace rank {rank}] {tag}: step={eng.flat.step} {res_}", file=sys.stderr, flush=True)
+
     def barrier():
         torch.cuda.synchronize()
         if world > 1:
@@ -319,10 +333,13 @@ def run_ours(opt):
             r["update_ms"] = sum(b.elapsed_time(c) for _, b, c in last) / K
         return r
 
+    replica_trace("init")
     res = timed(iteration_resident)                 # `value`: update replayed as per-epoch CUDA graphs, no profiling events
+    replica_trace("after resident loop")
     eng.update_graphs = False                       # per-kernel CUDA-event brackets cannot live inside a captured graph:
     prof_run = timed(iteration_resident, profile=True)      # the kernel table comes from an eager pass of the same iteration
     eng.update_graphs = os.environ.get("CLEANRL_B200_UPDATE_GRAPHS", "1") != "0"
+    replica_trace("after profiled resident loop")
     res["prof"] = prof_run["prof"]
     res["eager_ms"] = prof_run["ms"]
     e2e_whole = None
@@ -331,6 +348,7 @@ def run_ours(opt):
         env_parts, state = use_envs("pool")
         eng.delta_upload = False
         e2e_whole = phases(timed(iteration_e2e))
+        replica_trace("after whole-upload e2e loop")
         eng.delta_upload = True
         env_parts, state = use_envs("stack")
     ff0, rd0 = eng.delta_full_frames, eng.delta_redos
@@ -353,6 +371,7 @@ def run_ours(opt):
     e2e = phases(timed(iteration_e2e))
     if host_acc is not None:
         e2e["host_us_per_env_step"] = {k: round(v / ((W + K) * T) * 1e6, 1) for k, v in host_acc.items()}
+    replica_trace("after e2e loop")
     e2e["full_frames"] = (eng.delta_full_frames - ff0) / max(W + K, 1)
     e2e["redos"] = eng.delta_redos - rd0
     e2e["delta"] = bool(G > 1 and eng.delta_upload)
