@@ -201,17 +201,22 @@ def run_ours(opt):
 
     def replica_trace(tag):
         """BENCH_REPLICA_TRACE=1: after which phase do the replicas stop being bit-identical (diagnostic, stderr)."""
-        if world == 1 or not os.environ.get("BENCH_REPLICA_TRACE"):
+        if not os.environ.get("BENCH_REPLICA_TRACE"):
             return
         torch.cuda.synchronize()
         res_ = []
+        L = eng.agent._tc_plan()
         for nm, buf in (("params", eng.flat.flat), ("grad", eng.flat.grad), ("exp_avg", eng.flat.exp_avg), ("exp_avg_sq", eng.flat.exp_avg_sq)):
-            ref = buf.clone()
-            dist.broadcast(ref, 0)
-            d_ = (ref - buf).abs()
-            res_.append((nm, bool(torch.equal(ref, buf)), float(d_.max()), int((d_ > 0).sum()),
-                         int((d_ > 0).nonzero()[0]) if bool((d_ > 0).any()) else -1))
-        print(f"[replica_trace rank {rank}] {tag}: step={eng.flat.step} {res_}", file=sys.stderr, flush=True)
+            bad = ~torch.isfinite(buf)
+            nbad = int(bad.sum())
+            first = [int(i) for i in bad.nonzero().flatten()[:6]] if nbad else []
+            same = None
+            if world > 1:
+                ref = buf.clone()
+                dist.broadcast(ref, 0)
+                same = bool(torch.equal(torch.nan_to_num(ref, nan=12345.0), torch.nan_to_num(buf, nan=12345.0)))
+            res_.append((nm, "nonfinite", nbad, first, "same_as_rank0", same))
+        print(f"[replica_trace rank {rank}] {tag}: step={eng.flat.step} numel={eng.flat.flat.numel()} {res_}", file=sys.stderr, flush=True)
 
     def barrier():
         torch.cuda.synchronize()
