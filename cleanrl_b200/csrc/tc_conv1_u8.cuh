@@ -517,7 +517,9 @@ __global__ void __launch_bounds__(kC1WThreads, 1) tc_conv1_wgrad_u8(const __grid
             for (int k = 0; k < nsteps; ++k) {
                 const int64_t g = g0 + k;
                 const int ys = k % YS;
-                if (k >= YS) mbar_wait(&yempty[(k + 1) % YS], ((k - YS + 1) / YS) & 1);
+                // stage ys was read by step k - YS (its own rows, both tap groups) and by step k - YS + 1 (its tail, b = 1): the
+                // two steps belong to different issuer warps (step parity), so BOTH must have been consumed before the reload
+                if (k >= YS) mbar_wait2(&yempty[ys], ((k / YS) - 1) & 1, &yempty[(k + 1) % YS], ((k - YS + 1) / YS) & 1);
                 if (DBG & 2) mbar_arrive(&yfull[ys]);
                 else {
                     mbar_arrive_expect_tx(&yfull[ys], (uint32_t)(kC1WYBytes + (ys == 0 ? kC1WYPad : 0)));
@@ -541,7 +543,20 @@ __global__ void __launch_bounds__(kC1WThreads, 1) tc_conv1_wgrad_u8(const __grid
         const uint32_t d_col = tmem0 + COL_D + (uint32_t)((par * 2 + b) * 32);
         for (int it = par; it < nsteps; it += 2) {
             const int ys = it % YS, buf = it % NA;
-            mbar_wait2(&yfull[ys], (it / YS) & 1, &a_full[buf], (it / NA) & 1);
+            // The b = 1 operand starts 21 rows back, inside the PREVIOUS stage (or the halo in front of stage 0, which arrives
+            // with stage 0's own transaction count).  That stage belongs to step it - 1, whose bulk copy is tracked by a
+            // barrier only the other parity's issuers wait on -- and bulk copies issued in order may COMPLETE out of order.
+            // Without this wait the tail could be read before its copy had landed: stale rows, and on the first pass over the
+            // ring never-written shared memory (non-finite fp16 bit patterns -> NaN gradients for the dy = 1 taps, seen once
+            // in ~20 bench iterations).  All polls of the step go out together.
+            {
+                const bool need_prev = (b == 1) && ys != 0;
+                const int ps = need_prev ? ys - 1 : ys;
+                const uint32_t pph = need_prev ? (uint32_t)(((it - 1) / YS) & 1) : (uint32_t)((it / YS) & 1);
+                const bool p_ok = mbar_try_wait(&yfull[ps], pph);
+                mbar_wait2(&yfull[ys], (it / YS) & 1, &a_full[buf], (it / NA) & 1);
+                if (!p_ok) mbar_wait(&yfull[ps], pph);
+            }
             tc_fence_after_sync();
             if (leader) {
                 const uint32_t y_lo = ((smem_u32(sYb + (size_t)ys * kC1WYBytes - (size_t)(b * kC1WShift * 64)) & 0x3FFFFu) >> 4) | desc_lo_flags;
