@@ -161,7 +161,14 @@ class PPOEngine:
         self._parts = None
         # frame-stack delta upload (grouped loop, uint8 rollout): only the newest frame plane of every env crosses PCIe, the
         # device rebuilds slot t from slot t-1, a host worker pool verifies the shifted-stack property (csrc/frame_stack.cu)
-        self.delta_upload = bool(getattr(self, "u8_rollout", False)) and os.environ.get("CLEANRL_B200_DELTA_UPLOAD", "1") != "0"
+        # Default: on for a single process per host, off when several ranks share the host (LOCAL_WORLD_SIZE > 1): the
+        # verification and the leaner launch path make the rollout HOST-bound instead of PCIe-bound, which wins on an idle host
+        # (1.39 M vs 1.03 M env-steps/s) and loses when the ranks' worker pools compete for the same cores and memory
+        # bandwidth (profiles/r2_host_sensitivity.md).  CLEANRL_B200_DELTA_UPLOAD=1 / 0 overrides either way.
+        want_delta = os.environ.get("CLEANRL_B200_DELTA_UPLOAD")
+        if want_delta is None:
+            want_delta = "1" if int(os.environ.get("LOCAL_WORLD_SIZE", "1") or 1) <= 1 else "0"
+        self.delta_upload = bool(getattr(self, "u8_rollout", False)) and want_delta != "0"
         self._delta_allowed = self.delta_upload      # trackers / staging exist; ``delta_upload`` is the current state
         self._delta = None
         self.delta_redos = 0             # steps redone because an env broke the shifted-stack contract without being done
