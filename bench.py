@@ -244,8 +244,11 @@ def run_ours(opt):
             env_sets[mode] = (parts, {"obs": [e.reset() for e in parts], "done": [np.zeros(N // G, dtype=np.float32) for _ in parts]})
         return env_sets[mode]
 
+    # frame-stacked observations only pay off through the delta upload; where the engine uploads whole observations (several
+    # ranks per host by default, CLEANRL_B200_DELTA_UPLOAD=0) the e2e arm hands it dense pinned batches as rounds 1-2 did
+    obs_mode = opt.env_obs if (opt.env_obs == "pool" or eng.delta_upload) else "pool"
     if G > 1:
-        env_parts, state = use_envs(opt.env_obs)
+        env_parts, state = use_envs(obs_mode)
     else:
         state = {"obs": envs.reset(), "done": np.zeros(N, dtype=np.float32)}
 
@@ -348,7 +351,7 @@ def run_ours(opt):
     res["prof"] = prof_run["prof"]
     res["eager_ms"] = prof_run["ms"]
     e2e_whole = None
-    if G > 1 and opt.env_obs == "stack" and eng.delta_upload and not opt.no_whole_upload_arm:
+    if G > 1 and obs_mode == "stack" and eng.delta_upload and not opt.no_whole_upload_arm:
         # secondary arm: the same loop on unrelated observations, every one uploaded whole (round 2's headline path)
         env_parts, state = use_envs("pool")
         eng.delta_upload = False
@@ -496,7 +499,7 @@ def run_ours(opt):
                 "host": {"cores": os.cpu_count(), "process_pinned_to_gpu_local_cores": pinned_cores,
                          "verification_threads_per_group": (eng._delta[0]["tr"].threads if getattr(eng, "_delta", None) else 0)},
                 **({"host_us_per_env_step": e2e["host_us_per_env_step"]} if "host_us_per_env_step" in e2e else {}),
-                "observations": ("frame-stacked synthetic env (envpool stack_num=4 semantics)" if opt.env_obs == "stack" and G > 1
+                "observations": ("frame-stacked synthetic env (envpool stack_num=4 semantics)" if obs_mode == "stack" and G > 1
                                  else "unrelated random batches"),
                 "upload": ({"mode": "frame-stack delta: newest plane of every env + whole observations of done envs; "
                                     "shifted-stack property verified on the host for every env, every step",
