@@ -644,6 +644,11 @@ class PPOEngine:
         if hasattr(self.agent, "_tc_plan") and getattr(self.agent, "precision", "fp32") == "bf16":
             self.agent._tc_plan()          # (re)pack the weights once: they do not change during a rollout
         self._noise_step = -1
+        if self._delta is not None:
+            for p, d in enumerate(self._delta):
+                if d["last"] is not None:      # a rollout abandoned mid-step (exception in env.step): drop its pending pass
+                    self._lib.b200rl_stackdelta_join(d["tr"]._h, None, self._mis_ptr[p])
+                    d["tr"]._pending, d["tr"]._keep, d["last"], d["boot_obs"] = False, None, None, None
         for p in range(P):
             self.launch_part(0, p, obs_parts[p], done_parts[p])
         if self.T > 1:
