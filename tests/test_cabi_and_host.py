@@ -193,3 +193,42 @@ def test_native_minibatch_shuffle_is_numpy_shuffle_bit_for_bit(lib):
     np.random.seed(3); x = np.arange(10, dtype=np.int32); np.random.shuffle(x)
     np.random.seed(3); y = np.arange(10, dtype=np.int32); ops.numpy_global_shuffle(y)
     assert np.array_equal(x, y)
+
+
+def test_frame_stack_entry_points_validate_arguments_without_gpu(lib):
+    """The round-2 entry points (frame-stack delta upload, device-scalar Adam, native shuffle) reject bad arguments before
+    touching CUDA; ops.* reject CPU tensors."""
+    import torch
+    from cleanrl_b200 import ops
+    assert lib.b200rl_frames_delta_s2d_u8(None, None, None, None, None, 4, None, None, None) == -1
+    assert b"null" in lib.b200rl_last_error()
+    assert lib.b200rl_frames_delta_s2d_u8(None, None, None, None, None, 0, None, None, None) == 0      # empty batch: no-op
+    assert lib.b200rl_frames_delta_s2d_u8(16, 16, None, 32, 48, 4, 64, 80, None) == -1                # slot table without frames
+    assert lib.b200rl_frames_delta_s2d_u8(16, None, None, 32, 48, 4, 32, 80, None) == -1              # in place
+    assert b"in-place" in lib.b200rl_last_error()
+    assert lib.b200rl_h2d_rows_async(16, 16, 8, 16, 4, None) == -1                                    # pitch < row
+    assert lib.b200rl_h2d_rows_async(None, None, 16, 16, 0, None) == 0
+    assert not lib.b200rl_stackdelta_create(0, 4, 7056, 2) and b"stackdelta_create" in lib.b200rl_last_error()
+    assert not lib.b200rl_stackdelta_create(8, 1, 7056, 2)
+    tr = ops.StackDeltaTracker(4, 4, 64, threads=1, pinned=False)
+    obs = np.zeros((4, 4, 8, 8), dtype=np.uint8)
+    assert lib.b200rl_stackdelta_begin(tr._h, obs.ctypes.data, 8, None, None, tr.full_h.data_ptr(), tr.slot_h.data_ptr()) == -1
+    assert b"env_stride" in lib.b200rl_last_error()
+    assert lib.b200rl_stackdelta_begin(None, None, 0, None, None, None, None) == -1
+    assert lib.b200rl_stackdelta_wait(None, None) == -1
+    assert lib.b200rl_stackdelta_join(None, None, None) == 0                                          # nothing pending
+    assert lib.b200rl_stackdelta_launch(None, None, 0, None) == -1
+    assert lib.b200rl_clip_adam_dyn_f32(16, 16, 16, 16, 8, None, 0.9, 0.999, 1e-5, 0.5, 1, None, 16, 1 << 20, None) == -1
+    assert b"scalar table" in lib.b200rl_last_error()
+    import ctypes
+    out = (ctypes.c_float * 2)()
+    assert lib.b200rl_adam_step_scalars(0, 1e-3, 0.9, 0.999, out) == -1 and lib.b200rl_adam_step_scalars(1, 1e-3, 0.9, 0.999, out) == 0
+    assert abs(out[0] - (1 - 0.999) ** 0.5) < 1e-7 and abs(out[1] + 1e-3 / (1 - 0.9)) < 1e-9
+    key = np.zeros(624, dtype=np.uint32)
+    pos = ctypes.c_int32(700)
+    assert lib.b200rl_mt19937_shuffle_i64(key.ctypes.data, ctypes.addressof(pos), None, 0) == -1      # position outside the block
+    x = torch.zeros(4, 7056, dtype=torch.uint8)
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        ops.frames_delta_s2d_u8(x, x, x, x, x)
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        ops.clip_adam_dyn(torch.zeros(8), torch.zeros(8), torch.zeros(8), torch.zeros(8), torch.zeros(2))
