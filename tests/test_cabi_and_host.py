@@ -245,5 +245,4 @@ def test_public_header_is_plain_c(tmp_path):
                        capture_output=True, text=True)
     assert r.returncode == 0, r.stderr
     txt = (ROOT / "include" / "b200rl.h").read_text()
-    assert "torch" not in txt.lower().replace("pytorch", "").replace("torch.", "") or True   # informational: prose may mention torch
     assert "#include <cuda" not in txt and "at::" not in txt and "std::" not in txt
